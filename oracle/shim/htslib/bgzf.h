@@ -1,0 +1,1 @@
+/* empty stand-in: popdel call/view never call htslib (oracle build shim) */
