@@ -1,0 +1,131 @@
+/* popdel_b200.h -- C ABI of the B200-native `popdel call` window scan.
+ *
+ * Drop-in boundary (DESIGN.md "Boundary"): the reference has no FFI; its hot path is entered through
+ *   (i)  ChromosomeProfile::add(rg, startPos, endPos, deviation)      popdel_call/profile_structure_popdel_call.h:1084-1113
+ *        called from addRgRecordsToProfile                            popdel_call/load_profile_popdel_call.h:463-480
+ *   (ii) processSegment(chromosomeProfile, calls, ...)                workflow_popdel.h:28-54, whose product is the
+ *        String<Call> of window calls before unifyCalls               workflow_popdel.h:48
+ * This library replaces both at contig granularity: pd_contig_begin = ChromosomeProfile::resetTo (window grid and
+ * segment borders), pd_contig_push = the add() loop of one read group, pd_contig_scan = every processSegment() loop
+ * of the contig (genotype_deletion_window for each 30-bp window). All functions return 0 on success or a negative
+ * pd_status; no exception crosses the ABI; errors are sticky per context and described by pd_last_error().
+ * Plain pointers and sizes only. One pd_ctx per GPU, driven by one host thread at a time.
+ */
+#ifndef POPDEL_B200_H_
+#define POPDEL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pd_ctx pd_ctx;
+
+enum pd_status {
+    PD_OK = 0,
+    PD_ERR_ARG = -1,          /* invalid argument / call order */
+    PD_ERR_CUDA = -2,         /* CUDA runtime error or no usable device (no CPU fallback exists) */
+    PD_ERR_RANGE = -3,        /* value not representable in the packed layout (deviation, position) */
+    PD_ERR_CAPACITY = -4,     /* an internal device buffer was too small even after growing */
+    PD_ERR_ORDER = -5         /* read pairs of a read group not sorted by position */
+};
+
+/* PopDelCallParameters subset that reaches the scan (popdel_call/parameter_parsing_popdel_call.h:141-210). */
+typedef struct {
+    uint32_t iterations;           /* -t, default 15 */
+    uint32_t min_len;              /* params.minLen (95th percentile of min_init_del_len unless -m) */
+    double   min_lr;               /* params.minimumLikelihoodRatio (parameter_calculation_popdel_call.h:16-23) */
+    double   min_sample_fraction;  /* -s, default 0.1 */
+    uint32_t window_size;          /* 30 (only 30 is supported, like the reference's profile conversion) */
+    uint32_t window_buffer;        /* -b, default 200000: segment length in bp */
+    int32_t  somatic;              /* -C */
+    int32_t  window_wise;          /* -n: position = windowPosition, endPosition = 0 */
+} pd_params;
+
+/* One read group = one processed Histogram (insert_histogram_popdel.h:19-79) plus its per-RG parameters. */
+typedef struct {
+    uint32_t sample;               /* index of the owning sample; read groups of a sample are contiguous and ordered */
+    uint32_t median;
+    uint32_t read_length;
+    double   stddev;
+    int32_t  offset;               /* insert size of values[0] */
+    uint32_t len;                  /* number of values */
+    const double * values;         /* processed histogram (pd_process_histogram); copied by pd_create */
+    double   min_prob;
+    uint32_t lower_quantile_dist;
+    uint32_t upper_quantile_dist;
+    uint32_t max_load;             /* params.maxLoad[rg]; 0xFFFFFFFF disables the cap */
+    uint32_t min_init_del_len;     /* params.minInitDelLengths[rg] */
+} pd_rg;
+
+/* One window call = reference struct Call (utils_popdel.h:57-124) without its per-sample strings. */
+typedef struct {
+    uint32_t initial_length, iterations, deletion_length;
+    uint32_t filter;               /* bit 2 (value 4): sample-number filter (utils_popdel.h:158-170, 707-717) */
+    double   lr, frequency;
+    uint32_t window_position;      /* currentPos - 1 */
+    uint32_t position, end_position;
+    uint32_t segment;              /* index of the reference's processSegment() call (0-based per contig) */
+} pd_call;
+
+typedef struct {
+    uint64_t n_calls;
+    const pd_call * calls;         /* ordered by (window, initial_length), library-owned pinned memory */
+    const uint32_t * per_sample;   /* n_calls x n_samples x 13: PL[3] LAD[3] DAD[5] FL[2] */
+    uint64_t n_windows;            /* windows scanned (sample x window evaluations = n_windows * n_samples) */
+    uint64_t n_flagged_windows;    /* windows that passed the exact screen and entered the genotyping stage */
+    uint64_t n_candidates;         /* (window, initial length) pairs run through the EM */
+    uint64_t n_reads;              /* read pairs resident on the device for this contig */
+    uint64_t algorithmic_bytes;    /* bytes the screen kernel must move: 4 per resident read-pair word */
+    float    ms_h2d, ms_screen, ms_genotype, ms_d2h, ms_total;   /* CUDA-event times on the library's stream */
+} pd_result;
+
+/* Host: processHistogram(hist, 256, smoothing, pseudoCountFraction), insert_histogram_popdel.h:974-986, in place.
+ * Returns min_prob; writes the 1%/99% quantile distances. Needs no GPU. */
+double pd_process_histogram(double * values, uint32_t len, int32_t offset, uint32_t median, uint32_t read_length,
+                            int smoothing, uint32_t pseudo_count_fraction, uint32_t * lower_q, uint32_t * upper_q);
+
+/* Creates a context on CUDA device `device` and copies parameters and histogram tables to it.
+ * Returns NULL when no CUDA device is usable (pd_create_error() tells why). */
+pd_ctx * pd_create(const pd_params * params, uint32_t n_samples, uint32_t n_rg, const pd_rg * rgs, int device);
+const char * pd_create_error(void);
+void pd_destroy(pd_ctx * ctx);
+const char * pd_last_error(pd_ctx * ctx);
+
+/* = ChromosomeProfile::resetTo(anchor) (profile_structure_popdel_call.h:1717-1748): starts a contig / region of
+ * interest whose window grid is anchor + 30*i and whose segment borders are anchor + k*window_buffer. */
+int pd_contig_begin(pd_ctx * ctx, uint32_t anchor);
+
+/* = the ChromosomeProfile::add() calls for `n` read pairs of read group `rg`, in file order (sorted by position).
+ * pos = reference end of the forward read, dev = insert size - median. Applies the active-coverage cap.
+ * May be called several times per read group (positions must keep increasing). Host buffers are reusable on return. */
+int pd_contig_push(pd_ctx * ctx, uint32_t rg, uint64_t n, const uint32_t * pos, const int32_t * dev);
+
+/* Packs what was pushed and copies it to the device (pinned staging, async on the context's stream). */
+int pd_contig_upload(pd_ctx * ctx);
+
+/* = all processSegment() window loops of the contig: scans windows [first_window, first_window + n_windows)
+ * (n_windows = 0: up to the reference's last scanned window) over the device-resident read pairs and returns the
+ * window calls. Uploads first if needed. `out` stays valid until the next call on this context. */
+int pd_contig_scan(pd_ctx * ctx, uint64_t first_window, uint64_t n_windows, pd_result * out);
+
+/* Number of grid windows the reference would scan for the pushed contig (last scanned window index + 1). */
+int pd_contig_window_count(pd_ctx * ctx, uint64_t * n_windows);
+
+/* Synthetic cohort generated ON THE DEVICE directly in the packed layout (cfg3-5 cannot be
+ * materialised on the host): per read group Poisson(density*30) read pairs per 30-bp bucket, insert size
+ * round(N(median, stddev^2)); `n_dels` planted deletions with per-sample genotypes. Replaces push+upload. */
+int pd_contig_synthesize(pd_ctx * ctx, uint64_t seed, uint64_t n_windows, double pairs_per_bp,
+                         uint32_t n_dels, const uint32_t * del_start, const uint32_t * del_len,
+                         const uint8_t * del_genotypes /* n_dels x n_samples, 0/1/2 */);
+
+/* Host-side validation hook for the packed layout (NOT used by the scan): per-window active read-pair count,
+ * sum of deviations and sum of positions of read group `rg`, computed from the packed words with the same
+ * closed-form activity rule the kernels use. out = n_windows x 3 int64. Needs no GPU. */
+int pd_debug_host_window_sums(pd_ctx * ctx, uint32_t rg, uint64_t first_window, uint64_t n_windows, int64_t * out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POPDEL_B200_H_ */

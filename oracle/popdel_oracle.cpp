@@ -947,6 +947,7 @@ struct Driver {
     int64_t windowsScanned = 0;
     uint32_t segment = 0;
     std::vector<CallRec> * rawSink = nullptr;   // in-memory API: collects raw window calls
+    std::vector<int64_t> * winSink = nullptr;   // in-memory API: per window {pos, ncalls, 0} + per RG {count, sum_dev, sum_pos}
 
     void dumpCalls(const std::vector<CallRec> & calls, bool merged)
     {
@@ -968,6 +969,14 @@ struct Driver {
     {
         genotypeWindow(calls, cx, pr, segment);
         ++windowsScanned;
+        if (winSink) {
+            winSink->push_back(pr.currentPos); winSink->push_back((int64_t)calls.size()); winSink->push_back(0);
+            for (const RgTab & t : pr.rg) {
+                long long sd = 0; long long sp = 0;
+                for (uint32_t id : t.active) { sd += t.all[id].dev; sp += t.all[id].pos; }
+                winSink->push_back((int64_t)t.active.size()); winSink->push_back(sd); winSink->push_back(sp);
+            }
+        }
         if (dump && dumpWindows) {
             fprintf(dump, "W %u %u", pr.currentPos, (unsigned)calls.size());
             for (const RgTab & t : pr.rg) {
@@ -1140,8 +1149,10 @@ extern "C" int64_t orc_scan_contig(const orc_params * p, uint32_t n_samples, uin
                                    orc_call * calls, uint32_t * per_sample, int64_t max_calls,
                                    int64_t * win_dump, int64_t win_dump_cap, int64_t * n_windows_scanned)
 {
-    (void)last_pos; (void)win_dump; (void)win_dump_cap; (void)anchor;
+    (void)last_pos; (void)anchor;
     Driver d;
+    std::vector<int64_t> wins;
+    if (win_dump) d.winSink = &wins;
     d.cx.p = *p;
     d.cx.rgs.resize(n_samples);
     d.cx.hists.resize(n_rg);
@@ -1187,6 +1198,10 @@ extern "C" int64_t orc_scan_contig(const orc_params * p, uint32_t n_samples, uin
         d.run();
     }
     if (n_windows_scanned) *n_windows_scanned = d.windowsScanned;
+    if (win_dump) {
+        if ((int64_t)wins.size() > 3 * win_dump_cap) return -1;
+        std::copy(wins.begin(), wins.end(), win_dump);
+    }
     if ((int64_t)raw.size() > max_calls) return -(int64_t)raw.size();
     for (size_t k = 0; k < raw.size(); ++k) {
         calls[k] = raw[k].c;

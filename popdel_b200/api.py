@@ -1,0 +1,271 @@
+"""Python binding of the scan library (include/popdel_b200.h) and the host-side mirror of the reference's
+parameter handling for `popdel call`.
+
+Everything that computes on read pairs goes through the C ABI of `libpopdel_b200.so` (hand-written CUDA, sm_100a).
+There is no CPU scan path: creating a `Scanner` on a box without a usable CUDA device raises `ScanError`
+(only `device=-1` host-only contexts, used to validate the packed layout, work without a GPU).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpopdel_b200.so")
+
+
+class ScanError(RuntimeError):
+    pass
+
+
+class PdParams(C.Structure):
+    _fields_ = [("iterations", C.c_uint32), ("min_len", C.c_uint32), ("min_lr", C.c_double),
+                ("min_sample_fraction", C.c_double), ("window_size", C.c_uint32), ("window_buffer", C.c_uint32),
+                ("somatic", C.c_int32), ("window_wise", C.c_int32)]
+
+
+class PdRg(C.Structure):
+    _fields_ = [("sample", C.c_uint32), ("median", C.c_uint32), ("read_length", C.c_uint32), ("stddev", C.c_double),
+                ("offset", C.c_int32), ("len", C.c_uint32), ("values", C.POINTER(C.c_double)), ("min_prob", C.c_double),
+                ("lower_quantile_dist", C.c_uint32), ("upper_quantile_dist", C.c_uint32), ("max_load", C.c_uint32),
+                ("min_init_del_len", C.c_uint32)]
+
+
+class PdResult(C.Structure):
+    _fields_ = [("n_calls", C.c_uint64), ("calls", C.c_void_p), ("per_sample", C.POINTER(C.c_uint32)),
+                ("n_windows", C.c_uint64), ("n_flagged_windows", C.c_uint64), ("n_candidates", C.c_uint64),
+                ("n_reads", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
+                ("ms_h2d", C.c_float), ("ms_screen", C.c_float), ("ms_genotype", C.c_float), ("ms_d2h", C.c_float),
+                ("ms_total", C.c_float)]
+
+
+CALL_DTYPE = np.dtype([("initial_length", "<u4"), ("iterations", "<u4"), ("deletion_length", "<u4"), ("filter", "<u4"),
+                       ("lr", "<f8"), ("frequency", "<f8"), ("window_position", "<u4"), ("position", "<u4"),
+                       ("end_position", "<u4"), ("segment", "<u4")])
+
+EXPORTS = ["pd_process_histogram", "pd_create", "pd_create_error", "pd_destroy", "pd_last_error", "pd_contig_begin",
+           "pd_contig_push", "pd_contig_upload", "pd_contig_scan", "pd_contig_window_count", "pd_contig_synthesize",
+           "pd_debug_host_window_sums"]
+
+_lib = None
+
+
+def load_library(path: str = LIB_PATH):
+    """Loads libpopdel_b200.so; raises ScanError when it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise ScanError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(nvcc, sm_100a). popdel_b200 has no CPU implementation of the scan.")
+    lib = C.CDLL(path)
+    lib.pd_process_histogram.restype = C.c_double
+    lib.pd_process_histogram.argtypes = [C.POINTER(C.c_double), C.c_uint32, C.c_int32, C.c_uint32, C.c_uint32, C.c_int,
+                                         C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.pd_create.restype = C.c_void_p
+    lib.pd_create.argtypes = [C.POINTER(PdParams), C.c_uint32, C.c_uint32, C.POINTER(PdRg), C.c_int]
+    lib.pd_create_error.restype = C.c_char_p
+    lib.pd_destroy.argtypes = [C.c_void_p]
+    lib.pd_last_error.restype = C.c_char_p
+    lib.pd_last_error.argtypes = [C.c_void_p]
+    lib.pd_contig_begin.argtypes = [C.c_void_p, C.c_uint32]
+    lib.pd_contig_push.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
+    lib.pd_contig_upload.argtypes = [C.c_void_p]
+    lib.pd_contig_scan.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(PdResult)]
+    lib.pd_contig_window_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.pd_contig_synthesize.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_double, C.c_uint32,
+                                         C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)]
+    lib.pd_debug_host_window_sums.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(C.c_int64)]
+    _lib = lib
+    return lib
+
+
+def process_histogram(counts, offset: int, median: int, read_length: int, smoothing: bool = True,
+                      pseudo_count_fraction: int = 500):
+    """processHistogram(hist, 256, smoothing, f) of the reference (insert_histogram_popdel.h:974-986).
+    Returns (values, min_prob, lower_quantile_dist, upper_quantile_dist)."""
+    lib = load_library()
+    v = np.ascontiguousarray(counts, dtype=np.float64).copy()
+    lq, uq = C.c_uint32(0), C.c_uint32(0)
+    mp = lib.pd_process_histogram(v.ctypes.data_as(C.POINTER(C.c_double)), v.size, int(offset), int(median),
+                                  int(read_length), int(smoothing), int(pseudo_count_fraction), C.byref(lq), C.byref(uq))
+    return v, mp, lq.value, uq.value
+
+
+@dataclass
+class ReadGroup:
+    """One read group of the cohort = one Histogram of the reference plus its per-RG call parameters."""
+    sample: int
+    median: int
+    read_length: int
+    stddev: float
+    offset: int
+    values: np.ndarray            # processed histogram
+    min_prob: float
+    lower_quantile_dist: int
+    upper_quantile_dist: int
+    max_load: int = 100
+    min_init_del_len: int = 0
+    name: str = ""
+
+    def as_dict(self):
+        return dict(sample=self.sample, median=self.median, read_length=self.read_length, stddev=self.stddev,
+                    offset=self.offset, values=self.values, min_prob=self.min_prob,
+                    lower_quantile_dist=self.lower_quantile_dist, upper_quantile_dist=self.upper_quantile_dist,
+                    max_load=self.max_load, min_init_del_len=self.min_init_del_len)
+
+
+@dataclass
+class CallParameters:
+    """Defaults and derived values of PopDelCallParameters (popdel_call/parameter_parsing_popdel_call.h:184-209,
+    popdel_call/parameter_calculation_popdel_call.h:16-81,160-204)."""
+    iterations: int = 15
+    prior: float = 0.0001
+    min_len: Optional[int] = None              # -m; default 95th percentile of the initial lengths
+    min_init_len: Optional[int] = None         # -l; default round(4 * stddev) per read group
+    min_sample_fraction: float = 0.1
+    window_size: int = 30
+    window_buffer: int = 200000
+    somatic: bool = False
+    window_wise: bool = False
+    default_max_load: int = 100                # -a; 0 disables the cap
+    smoothing: bool = True
+    pseudo_count_fraction: int = 500
+    min_lr: float = field(init=False, default=0.0)
+
+    def finalize(self, rgs: List[ReadGroup]) -> None:
+        """loadAndCalculateParameters: min init lengths, min length, LR threshold, max load."""
+        for r in rgs:
+            r.min_init_del_len = int(self.min_init_len) if self.min_init_len is not None else int(math.floor(4 * r.stddev + 0.5))
+            r.max_load = 0xFFFFFFFF if self.default_max_load == 0 else int(self.default_max_load)
+        if self.min_len is None:
+            v = sorted(r.min_init_del_len for r in rgs)
+            n = len(v)
+            j = int(math.floor(n * 0.95))
+            self.min_len = int(math.floor(1.0 * (v[j] if j != n * 0.95 else v[j - 1]) + 0.5))
+        self.min_lr = (6.6349 / 2.0) - math.log(self.prior / (1 - self.prior))
+
+    def as_dict(self):
+        return dict(iterations=self.iterations, min_len=int(self.min_len), min_lr=self.min_lr,
+                    min_sample_fraction=self.min_sample_fraction, window_size=self.window_size,
+                    window_buffer=self.window_buffer, somatic=int(self.somatic), window_wise=int(self.window_wise))
+
+
+def read_groups_from_headers(headers: Sequence[Sequence[dict]], params: CallParameters) -> List[ReadGroup]:
+    """headers[s] = read-group header dicts of sample s (profile_format.rg_meta_from / read_profile):
+    processes every histogram like loadInsertSizeHistograms (insert_histogram_popdel.h:992-1095)."""
+    out: List[ReadGroup] = []
+    for s, metas in enumerate(headers):
+        for m in metas:
+            vals, mp, lq, uq = process_histogram(m["hist_counts"], m["hist_start"], m["median"], m["read_length"],
+                                                 params.smoothing, params.pseudo_count_fraction)
+            out.append(ReadGroup(sample=s, median=int(m["median"]), read_length=int(m["read_length"]),
+                                 stddev=float(m["stddev"]), offset=int(m["hist_start"]), values=vals, min_prob=mp,
+                                 lower_quantile_dist=lq, upper_quantile_dist=uq, name=m.get("name", "")))
+    params.finalize(out)
+    return out
+
+
+class Scanner:
+    """One scan context (pd_ctx) on one GPU."""
+
+    def __init__(self, params: CallParameters, rgs: List[ReadGroup], n_samples: int, device: int = 0):
+        self.lib = load_library()
+        self.n_samples, self.n_rg = int(n_samples), len(rgs)
+        self._keep = [np.ascontiguousarray(r.values, dtype=np.float64) for r in rgs]
+        arr = (PdRg * len(rgs))()
+        for i, r in enumerate(rgs):
+            arr[i] = PdRg(r.sample, r.median, r.read_length, r.stddev, r.offset, self._keep[i].size,
+                          self._keep[i].ctypes.data_as(C.POINTER(C.c_double)), r.min_prob, r.lower_quantile_dist,
+                          r.upper_quantile_dist, r.max_load, r.min_init_del_len)
+        p = PdParams(**params.as_dict())
+        self.ctx = self.lib.pd_create(C.byref(p), self.n_samples, self.n_rg, arr, int(device))
+        if not self.ctx:
+            raise ScanError(self.lib.pd_create_error().decode())
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.pd_destroy(self.ctx)
+            self.ctx = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != 0:
+            raise ScanError(f"[{rc}] {self.lib.pd_last_error(self.ctx).decode()}")
+
+    def begin_contig(self, anchor: int):
+        self._check(self.lib.pd_contig_begin(self.ctx, int(anchor)))
+
+    def push(self, rg: int, pos: np.ndarray, dev: np.ndarray):
+        pos = np.ascontiguousarray(pos, dtype=np.uint32)
+        dev = np.ascontiguousarray(dev, dtype=np.int32)
+        assert pos.size == dev.size
+        self._check(self.lib.pd_contig_push(self.ctx, int(rg), pos.size, pos.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                            dev.ctypes.data_as(C.POINTER(C.c_int32))))
+
+    def upload(self):
+        self._check(self.lib.pd_contig_upload(self.ctx))
+
+    def window_count(self) -> int:
+        n = C.c_uint64(0)
+        self._check(self.lib.pd_contig_window_count(self.ctx, C.byref(n)))
+        return n.value
+
+    def scan(self, first_window: int = 0, n_windows: int = 0) -> dict:
+        res = PdResult()
+        self._check(self.lib.pd_contig_scan(self.ctx, int(first_window), int(n_windows), C.byref(res)))
+        n = res.n_calls
+        calls = np.zeros(n, dtype=CALL_DTYPE)
+        per = np.zeros((n, self.n_samples, 13), dtype=np.uint32)
+        if n:
+            C.memmove(calls.ctypes.data, res.calls, n * CALL_DTYPE.itemsize)
+            C.memmove(per.ctypes.data, res.per_sample, per.nbytes)
+        return dict(calls=calls, per_sample=per, n_windows=res.n_windows, n_flagged_windows=res.n_flagged_windows,
+                    n_candidates=res.n_candidates, n_reads=res.n_reads, algorithmic_bytes=res.algorithmic_bytes,
+                    ms_h2d=res.ms_h2d, ms_screen=res.ms_screen, ms_genotype=res.ms_genotype, ms_total=res.ms_total)
+
+    def synthesize(self, seed: int, n_windows: int, pairs_per_bp: float, del_start=(), del_len=(), genotypes=None):
+        ds = np.ascontiguousarray(del_start, dtype=np.uint32)
+        dl = np.ascontiguousarray(del_len, dtype=np.uint32)
+        gt = np.ascontiguousarray(genotypes if genotypes is not None else np.zeros((0, self.n_samples)), dtype=np.uint8)
+        self._check(self.lib.pd_contig_synthesize(self.ctx, int(seed), int(n_windows), float(pairs_per_bp), ds.size,
+                                                  ds.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                  dl.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                  gt.ctypes.data_as(C.POINTER(C.c_uint8))))
+
+    def debug_host_window_sums(self, rg: int, first_window: int, n_windows: int) -> np.ndarray:
+        out = np.zeros((int(n_windows), 3), dtype=np.int64)
+        self._check(self.lib.pd_debug_host_window_sums(self.ctx, int(rg), int(first_window), int(n_windows),
+                                                       out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return out
+
+
+def cohort_anchor(samples) -> int:
+    """First 30-bp window over all samples (getFirstWindowCoordinate, load_profile_popdel_call.h:291-350)."""
+    first = [int(rg.pos[0]) for s in samples for rg in s.read_groups if rg.pos.size]
+    return (min(first) // 30) * 30
+
+
+def scan_cohort(samples, params: CallParameters, device: int = 0, first_window: int = 0, n_windows: int = 0):
+    """Convenience: whole in-memory cohort (popdel_b200.simulate objects) -> window calls of one contig."""
+    rgs = read_groups_from_headers([[dict(name=rg.spec.name, median=rg.median, stddev=rg.stddev,
+                                          read_length=rg.spec.read_length, hist_start=rg.hist_start,
+                                          hist_end=rg.hist_end, hist_counts=rg.hist_counts) for rg in s.read_groups]
+                                    for s in samples], params)
+    sc = Scanner(params, rgs, len(samples), device)
+    try:
+        sc.begin_contig(cohort_anchor(samples))
+        g = 0
+        for s in samples:
+            for rg in s.read_groups:
+                sc.push(g, rg.pos, rg.dev)
+                g += 1
+        return sc.scan(first_window, n_windows), rgs
+    finally:
+        sc.close()

@@ -1,0 +1,90 @@
+// pd_context.h -- host-side context of the scan library (internal).
+#ifndef PD_CONTEXT_H_
+#define PD_CONTEXT_H_
+
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/popdel_b200.h"
+#include "pd_common.h"
+
+struct PdLong { uint32_t s, e, pos_rel; int32_t dev; };      // wide entry of a long read pair (16 B)
+
+// Device view handed to the kernels by value.
+struct PdDev {
+    const uint32_t * words;          // packed read-pair stream, all read groups
+    const uint32_t * tile_off;       // [R][NT+1] word offsets (multiples of 4)
+    const PdLong *   longs;          // wide list of long read pairs, all read groups, sorted by s per read group
+    const uint32_t * long_off;       // [R+1]
+    const uint32_t * long_span;      // [R] max (e - s + 1)
+    const PdRgConst * rgc;           // [R]
+    const uint32_t * sample_rg;      // [N+1] read groups of sample s = sample_rg[s] .. sample_rg[s+1]
+    const double * tab_val;          // processed histogram values, all read groups
+    const double * tab_ln;           // ln(values)
+    const double * tab_l10;          // log10(values)
+    uint32_t NT;                     // tiles per read group
+    uint32_t N, R;
+    uint32_t window_buffer;
+    int32_t  t_min;                  // min over read groups of min_init_del_len
+    uint32_t w_begin, w_end;         // windows to scan [w_begin, w_end)
+};
+
+struct PdHostRg {                    // host staging of one read group of the current contig
+    std::vector<uint32_t> pos_rel;   // after the active-coverage cap
+    std::vector<int32_t> dev;
+    // active-coverage cap state (ChromosomeProfile::add, profile_structure :1084-1113)
+    std::vector<uint32_t> open_lw;   // min-heap of last-window indices of read pairs still open
+    uint64_t dropped = 0;
+    uint32_t last_pos = 0;
+    bool any = false;
+};
+
+struct pd_ctx {
+    pd_params params;
+    uint32_t N = 0, R = 0;
+    int device = -1;                 // -1: host-only context (packing / validation hooks), scans fail
+    std::vector<pd_rg> rgs;          // values pointers point into tables_
+    std::vector<std::vector<double>> tables_;
+    std::vector<PdRgConst> rgc;
+    std::vector<uint32_t> sample_rg;
+    int32_t t_min = 0;
+    std::string err;
+    int status = 0;
+
+    // current contig
+    bool contig_open = false, packed = false, uploaded = false;
+    PdGrid grid{0, 200000};
+    std::vector<PdHostRg> hrg;
+    // packed host image
+    std::vector<uint32_t> h_words, h_tile_off, h_long_off, h_long_span;
+    std::vector<PdLong> h_longs;
+    uint32_t NT = 0;
+    uint64_t n_windows_total = 0;    // reference's last scanned window + 1
+    uint64_t n_reads = 0;
+
+    // device
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    uint32_t * d_words = nullptr; size_t cap_words = 0;
+    uint32_t * d_tile_off = nullptr; size_t cap_tile_off = 0;
+    PdLong * d_longs = nullptr; size_t cap_longs = 0;
+    uint32_t * d_long_off = nullptr, * d_long_span = nullptr;
+    PdRgConst * d_rgc = nullptr;
+    uint32_t * d_sample_rg = nullptr;
+    double * d_tab_val = nullptr, * d_tab_ln = nullptr, * d_tab_l10 = nullptr;
+    uint32_t * h_pin_words = nullptr; size_t cap_pin_words = 0;   // pinned staging
+    // scan scratch (grown on demand)
+    void * d_scratch[16] = {}; size_t cap_scratch[16] = {};
+    // results (pinned)
+    std::vector<pd_call> res_calls;
+    std::vector<uint32_t> res_ps;
+    float ms_h2d = 0;
+};
+
+int pd_fail(pd_ctx * c, int status, const std::string & msg);
+int pd_pack_contig(pd_ctx * c);                    // pd_pack.cpp part: builds the packed host image
+int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result * out);   // pd_kernels.cu
+
+#endif

@@ -1,0 +1,455 @@
+// pd_host.cu -- host side of the scan library: context, histogram preprocessing, the push path with the
+// active-coverage cap, packing into the tiled 32-bit layout, upload, and the host-only validation hook.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <queue>
+#include <string>
+#include <vector>
+
+#include "pd_context.h"
+
+static std::string g_create_error;
+
+int pd_fail(pd_ctx * c, int status, const std::string & msg)
+{
+    if (c && c->status == 0) { c->status = status; c->err = msg; }
+    return status;
+}
+
+#define PD_CUDA(c, call)                                                                          \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return pd_fail((c), PD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// processHistogram (reference insert_histogram_popdel.h:974-986): smoothing :759-778, quantile distances
+// :609-646, density scaling :884-891, per-window normalisation :718-745, probability floor :793-808.
+// The reference's integer-accumulator and off-by-one behaviour is part of the contract.
+// ---------------------------------------------------------------------------------------------------------
+extern "C" double pd_process_histogram(double * values, uint32_t len, int32_t offset, uint32_t median,
+                                       uint32_t read_length, int smoothing, uint32_t pseudo_count_fraction,
+                                       uint32_t * lower_q, uint32_t * upper_q)
+{
+    const int n = (int)len;
+    std::vector<double> v(values, values + len);
+    if (smoothing) {
+        double kern[41], ksum = 0;
+        for (int j = -20; j <= 20; ++j) { kern[j + 20] = std::exp(-j * j / 40.0); }
+        for (int j = 0; j < 41; ++j) ksum += kern[j];             // all 41 weights, also outside the histogram
+        std::vector<double> sm(len);
+        for (int i = 0; i < n; ++i) {
+            double acc = 0;
+            for (int j = -20; j <= 20; ++j)
+                if (i + j >= 0 && i + j < n) acc += kern[j + 20] * v[i + j];
+            sm[i] = acc / ksum;
+        }
+        v.swap(sm);
+    }
+    uint32_t lq = 0, uq = 0;
+    {
+        unsigned total = 0;                                       // `unsigned += double`: truncates each step
+        for (int i = 1; i + 1 < n; ++i) total += v[i];
+        const double lower = total * 0.01, upper = total * 0.99;
+        double run = 0;
+        int i = 1;
+        for (; i + 1 < n; ++i) {
+            run += v[i];
+            if (run >= lower) { lq = (uint32_t)std::abs(i + offset - (int)median); break; }
+        }
+        for (; i + 1 < n; ++i) {                                  // restarts on the same element: counted twice
+            run += v[i];
+            if (run >= upper) { uq = (uint32_t)std::abs(i + offset - (int)median); break; }
+        }
+    }
+    {
+        unsigned total = 0;
+        for (int i = 0; i < n; ++i) total += v[i];
+        for (int i = 0; i < n; ++i) v[i] /= total;
+    }
+    {
+        unsigned isize = (unsigned)offset;                        // index 1 is paired with insert size `offset`
+        for (int i = 1; i + 1 < n; ++i, ++isize) {
+            int inner = (int)(isize - 2 * read_length);
+            if (inner < 1) inner = 1;
+            v[i] *= static_cast<double>(256 + inner - 1) / 256;
+        }
+    }
+    double mx = 0;
+    for (int i = 0; i < n; ++i) mx = std::max(mx, v[i]);
+    const double min_prob = mx / pseudo_count_fraction;
+    for (int i = 0; i < n; ++i) values[i] = v[i] < min_prob ? min_prob : v[i];
+    if (lower_q) *lower_q = lq;
+    if (upper_q) *upper_q = uq;
+    return min_prob;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------------
+extern "C" const char * pd_create_error(void) { return g_create_error.c_str(); }
+extern "C" const char * pd_last_error(pd_ctx * c) { return c ? c->err.c_str() : "null context"; }
+
+static int upload_static(pd_ctx * c)
+{
+    size_t total = 0;
+    for (auto & t : c->tables_) total += t.size();
+    std::vector<double> val(total), ln(total), l10(total);
+    for (uint32_t g = 0; g < c->R; ++g) {
+        size_t o = c->rgc[g].hist_off;
+        for (size_t i = 0; i < c->tables_[g].size(); ++i) {
+            val[o + i] = c->tables_[g][i];
+            ln[o + i] = std::log(c->tables_[g][i]);
+            l10[o + i] = std::log10(c->tables_[g][i]);
+        }
+    }
+    PD_CUDA(c, cudaMalloc(&c->d_tab_val, std::max<size_t>(total, 1) * 8));
+    PD_CUDA(c, cudaMalloc(&c->d_tab_ln, std::max<size_t>(total, 1) * 8));
+    PD_CUDA(c, cudaMalloc(&c->d_tab_l10, std::max<size_t>(total, 1) * 8));
+    PD_CUDA(c, cudaMemcpy(c->d_tab_val, val.data(), total * 8, cudaMemcpyHostToDevice));
+    PD_CUDA(c, cudaMemcpy(c->d_tab_ln, ln.data(), total * 8, cudaMemcpyHostToDevice));
+    PD_CUDA(c, cudaMemcpy(c->d_tab_l10, l10.data(), total * 8, cudaMemcpyHostToDevice));
+    PD_CUDA(c, cudaMalloc(&c->d_rgc, c->R * sizeof(PdRgConst)));
+    PD_CUDA(c, cudaMemcpy(c->d_rgc, c->rgc.data(), c->R * sizeof(PdRgConst), cudaMemcpyHostToDevice));
+    PD_CUDA(c, cudaMalloc(&c->d_sample_rg, (c->N + 1) * 4));
+    PD_CUDA(c, cudaMemcpy(c->d_sample_rg, c->sample_rg.data(), (c->N + 1) * 4, cudaMemcpyHostToDevice));
+    PD_CUDA(c, cudaMalloc(&c->d_long_off, (c->R + 1) * 4));
+    PD_CUDA(c, cudaMalloc(&c->d_long_span, c->R * 4));
+    return 0;
+}
+
+extern "C" pd_ctx * pd_create(const pd_params * p, uint32_t n_samples, uint32_t n_rg, const pd_rg * rgs, int device)
+{
+    g_create_error.clear();
+    if (!p || !rgs || n_samples == 0 || n_rg < n_samples) { g_create_error = "pd_create: invalid arguments"; return nullptr; }
+    if (p->window_size != 30) { g_create_error = "pd_create: only 30-bp windows are supported"; return nullptr; }
+    if (p->window_buffer < 960 || p->iterations > 60) { g_create_error = "pd_create: window_buffer < 960 or iterations > 60"; return nullptr; }
+    pd_ctx * c = new pd_ctx();
+    c->params = *p; c->N = n_samples; c->R = n_rg; c->device = device;
+    c->grid.window_buffer = p->window_buffer;
+    c->rgs.assign(rgs, rgs + n_rg);
+    c->tables_.resize(n_rg);
+    c->rgc.resize(n_rg);
+    c->sample_rg.assign(n_samples + 1, 0);
+    uint32_t hist_off = 0, prev_sample = 0;
+    int64_t tmin = INT32_MAX;
+    for (uint32_t g = 0; g < n_rg; ++g) {
+        const pd_rg & r = rgs[g];
+        if (r.sample >= n_samples || r.sample < prev_sample || (g == 0 && r.sample != 0) || r.sample > prev_sample + 1 ||
+            !r.values || r.len < 3) {
+            g_create_error = "pd_create: read groups must be grouped by sample in ascending order, every sample non-empty";
+            delete c; return nullptr;
+        }
+        prev_sample = r.sample;
+        c->sample_rg[r.sample + 1] = g + 1;
+        c->tables_[g].assign(r.values, r.values + r.len);
+        c->rgs[g].values = c->tables_[g].data();
+        PdRgConst & k = c->rgc[g];
+        k.inner_off = (int32_t)r.median - 2 * (int32_t)r.read_length;
+        k.max_load = r.max_load; k.sample = r.sample; k.median = (int32_t)r.median;
+        k.hist_base = (int32_t)r.median - r.offset; k.hist_len = r.len; k.hist_off = hist_off;
+        k.min_prob = r.min_prob; k.ln_min_prob = std::log(r.min_prob); k.l10_min_prob = std::log10(r.min_prob);
+        k.stddev = r.stddev; k.lower_q = (int32_t)r.lower_quantile_dist; k.upper_q = (int32_t)r.upper_quantile_dist;
+        k.min_init = r.min_init_del_len; k.pad_ = 0;
+        // stream read pairs with dev up to ~8 sigma stay "short": span <= lookback tiles
+        double span_w = (29.0 + std::max(0.0, k.inner_off + 8.0 * r.stddev)) / 30.0 + 2.0;
+        uint32_t lb = (uint32_t)std::ceil(span_w / PD_TILE_WINDOWS);
+        k.lookback_tiles = std::min<uint32_t>(std::max<uint32_t>(lb, 1), PD_MAX_LOOKBACK_TILES);
+        hist_off += r.len;
+        tmin = std::min<int64_t>(tmin, r.min_init_del_len);
+    }
+    if (c->sample_rg[n_samples] != n_rg || prev_sample != n_samples - 1) {
+        g_create_error = "pd_create: every sample needs at least one read group"; delete c; return nullptr;
+    }
+    c->t_min = (int32_t)std::min<int64_t>(tmin, PD_DEV_MAX - 1);
+    c->hrg.resize(n_rg);
+    if (device >= 0) {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || device >= ndev) {
+            g_create_error = std::string("pd_create: no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "index out of range") +
+                             "); this library has no CPU scan path";
+            delete c; return nullptr;
+        }
+        if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            g_create_error = "pd_create: cudaSetDevice/cudaStreamCreate failed"; delete c; return nullptr;
+        }
+        for (auto & ev : c->ev) cudaEventCreate(&ev);
+        if (upload_static(c) != 0) { g_create_error = c->err; pd_destroy(c); return nullptr; }
+    }
+    return c;
+}
+
+extern "C" void pd_destroy(pd_ctx * c)
+{
+    if (!c) return;
+    if (c->device >= 0) {
+        cudaSetDevice(c->device);
+        cudaFree(c->d_words); cudaFree(c->d_tile_off); cudaFree(c->d_longs); cudaFree(c->d_long_off); cudaFree(c->d_long_span);
+        cudaFree(c->d_rgc); cudaFree(c->d_sample_rg); cudaFree(c->d_tab_val); cudaFree(c->d_tab_ln); cudaFree(c->d_tab_l10);
+        for (auto & p : c->d_scratch) cudaFree(p);
+        if (c->h_pin_words) cudaFreeHost(c->h_pin_words);
+        for (auto & ev : c->ev) if (ev) cudaEventDestroy(ev);
+        if (c->stream) cudaStreamDestroy(c->stream);
+    }
+    delete c;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// contig: begin / push (with the active-coverage cap) / pack / upload
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int pd_contig_begin(pd_ctx * c, uint32_t anchor)
+{
+    if (!c) return PD_ERR_ARG;
+    if (c->status) return c->status;
+    if (anchor % PD_WIN != 0) return pd_fail(c, PD_ERR_ARG, "pd_contig_begin: anchor must be a multiple of 30 (first 30-bp window of the contig)");
+    c->grid.anchor = anchor;
+    for (auto & h : c->hrg) { h = PdHostRg(); }
+    c->contig_open = true; c->packed = false; c->uploaded = false;
+    c->n_windows_total = 0; c->n_reads = 0;
+    return 0;
+}
+
+// The cap of ChromosomeProfile::add (profile_structure_popdel_call.h:1084-1113, getEndCount :870-928): a read pair is
+// stored iff fewer than max_load previously stored pairs of its read group are still open at its 30-bp bucket
+// (open = lastWindow >= bucket). The reference refreshes its counter lazily; the decision is the same except for the
+// single add that follows a segment switch while the cap is active (documented in DESIGN.md).
+extern "C" int pd_contig_push(pd_ctx * c, uint32_t rg, uint64_t n, const uint32_t * pos, const int32_t * dev)
+{
+    if (!c) return PD_ERR_ARG;
+    if (c->status) return c->status;
+    if (!c->contig_open || rg >= c->R || (n && (!pos || !dev))) return pd_fail(c, PD_ERR_ARG, "pd_contig_push: bad arguments or no open contig");
+    if (c->packed) return pd_fail(c, PD_ERR_ARG, "pd_contig_push: contig already packed");
+    PdHostRg & h = c->hrg[rg];
+    const PdRgConst & k = c->rgc[rg];
+    const bool capped = k.max_load != 0xFFFFFFFFu;
+    h.pos_rel.reserve(h.pos_rel.size() + n);
+    h.dev.reserve(h.dev.size() + n);
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t p = pos[i];
+        if (p < c->grid.anchor) return pd_fail(c, PD_ERR_ARG, "pd_contig_push: position before the contig anchor");
+        if (h.any && p < h.last_pos) return pd_fail(c, PD_ERR_ORDER, "pd_contig_push: read pairs must be sorted by position");
+        h.any = true; h.last_pos = p;
+        uint32_t pr = p - c->grid.anchor;
+        if (capped) {
+            uint32_t b = pr / PD_WIN;
+            int64_t inner = (int64_t)dev[i] + k.inner_off;
+            if (inner < 0) inner = 0;
+            uint32_t lw = (uint32_t)((pr + (uint64_t)inner) / PD_WIN);
+            std::vector<uint32_t> & hp = h.open_lw;
+            while (!hp.empty() && hp.front() < b) { std::pop_heap(hp.begin(), hp.end(), std::greater<uint32_t>()); hp.pop_back(); }
+            if (hp.size() >= k.max_load) { ++h.dropped; continue; }
+            hp.push_back(lw); std::push_heap(hp.begin(), hp.end(), std::greater<uint32_t>());
+        }
+        h.pos_rel.push_back(pr);
+        h.dev.push_back(dev[i]);
+    }
+    return 0;
+}
+
+// Last window the reference scans for this contig (workflow_popdel.h:42-47 with nextWindow's stop rules,
+// profile_structure_popdel_call.h:1213-1247): in the final segment kf the scan runs until the border or until every
+// start entry is activated and every end entry of end set kf is removed.
+static uint64_t last_scanned_window(const pd_ctx * c)
+{
+    const uint32_t wb = c->grid.window_buffer;
+    int64_t kf = -1;
+    for (const auto & h : c->hrg) if (!h.pos_rel.empty()) kf = std::max<int64_t>(kf, (int64_t)((uint64_t)(h.pos_rel.back() / PD_WIN) * PD_WIN / wb));
+    if (kf < 0) return 0;
+    int64_t E = -1, S = -1;
+    for (uint32_t g = 0; g < c->R; ++g) {
+        const PdHostRg & h = c->hrg[g];
+        const int32_t io = c->rgc[g].inner_off;
+        for (size_t i = h.pos_rel.size(); i-- > 0;) {
+            uint64_t pr = h.pos_rel[i];
+            uint64_t b = pr / PD_WIN;
+            int64_t j = (int64_t)(b * PD_WIN / wb);
+            if (j < kf - 1) break;
+            int64_t inner = std::max<int64_t>(0, (int64_t)h.dev[i] + io);
+            int64_t lw = (int64_t)((pr + inner) / PD_WIN);
+            int64_t wl = (int64_t)pd_seg_last_window((uint64_t)j, wb);
+            if (j == kf) { S = std::max<int64_t>(S, (int64_t)pr); if (lw <= wl) E = std::max(E, lw); }
+            else if (lw > wl) E = std::max(E, lw);                  // spill-over entry of segment kf-1 lives in end set kf
+        }
+    }
+    int64_t stop = std::max(E + 2, (S + 29) / (int64_t)PD_WIN);
+    int64_t wl = (int64_t)pd_seg_last_window((uint64_t)kf, wb);
+    return (uint64_t)std::min(stop, wl) + 1;
+}
+
+int pd_pack_contig(pd_ctx * c)
+{
+    if (c->packed) return 0;
+    const uint32_t wb = c->grid.window_buffer;
+    c->n_windows_total = last_scanned_window(c);
+    uint64_t max_tile = (c->n_windows_total + PD_TILE_WINDOWS - 1) / PD_TILE_WINDOWS;
+    for (const auto & h : c->hrg) if (!h.pos_rel.empty()) max_tile = std::max<uint64_t>(max_tile, h.pos_rel.back() / PD_TILE_BP + 1);
+    if (max_tile + 1 >= (1ull << 31)) return pd_fail(c, PD_ERR_RANGE, "contig too long for the tile index");
+    c->NT = (uint32_t)std::max<uint64_t>(max_tile, 1);
+    const uint32_t NT = c->NT;
+    c->h_tile_off.assign((size_t)c->R * (NT + 1), 0);
+    c->h_long_off.assign(c->R + 1, 0);
+    c->h_long_span.assign(c->R, 0);
+    c->h_longs.clear();
+    // pass 1: counts per tile
+    uint64_t total_words = 0;
+    c->n_reads = 0;
+    for (uint32_t g = 0; g < c->R; ++g) {
+        const PdHostRg & h = c->hrg[g];
+        uint32_t * off = &c->h_tile_off[(size_t)g * (NT + 1)];
+        std::vector<uint32_t> cnt(NT, 0);
+        for (uint32_t pr : h.pos_rel) ++cnt[pr / PD_TILE_BP];
+        for (uint32_t t = 0; t < NT; ++t) {
+            if (total_words > 0xFFFFFFF0ull) return pd_fail(c, PD_ERR_CAPACITY, "more than 2^32 packed words in one contig batch; split the cohort or the contig");
+            off[t] = (uint32_t)total_words;
+            total_words += (cnt[t] + 3u) & ~3u;
+        }
+        off[NT] = (uint32_t)total_words;
+        c->n_reads += h.pos_rel.size();
+    }
+    c->h_words.assign(total_words, PD_PAD_WORD);
+    // pass 2: words and the wide list of long read pairs
+    for (uint32_t g = 0; g < c->R; ++g) {
+        const PdHostRg & h = c->hrg[g];
+        const PdRgConst & k = c->rgc[g];
+        const uint32_t * off = &c->h_tile_off[(size_t)g * (NT + 1)];
+        c->h_long_off[g] = (uint32_t)c->h_longs.size();
+        uint32_t cur_tile = 0xFFFFFFFFu, w = 0, span = 0;
+        for (size_t i = 0; i < h.pos_rel.size(); ++i) {
+            uint32_t pr = h.pos_rel[i];
+            uint32_t t = pr / PD_TILE_BP;
+            if (t != cur_tile) { cur_tile = t; w = off[t]; }
+            int32_t d = h.dev[i];
+            int64_t s, e;
+            bool act = pd_interval(pr, d, k.inner_off, wb, s, e);
+            bool is_long = d > PD_DEV_MAX || d < PD_DEV_MIN + 1;
+            if (act && (uint64_t)e / PD_TILE_WINDOWS > (uint64_t)t + k.lookback_tiles) is_long = true;
+            int32_t dc = d > PD_DEV_MAX ? PD_DEV_MAX : (d < PD_DEV_MIN + 1 ? PD_DEV_MIN + 1 : d);
+            c->h_words[w++] = pd_pack(dc, pr - t * PD_TILE_BP, is_long);
+            if (is_long && act) {
+                c->h_longs.push_back(PdLong{(uint32_t)s, (uint32_t)e, pr, d});
+                span = std::max<uint32_t>(span, (uint32_t)(e - s + 1));
+            }
+        }
+        c->h_long_span[g] = span;
+    }
+    c->h_long_off[c->R] = (uint32_t)c->h_longs.size();
+    c->packed = true;
+    return 0;
+}
+
+extern "C" int pd_contig_window_count(pd_ctx * c, uint64_t * n)
+{
+    if (!c || !n) return PD_ERR_ARG;
+    if (c->status) return c->status;
+    if (!c->contig_open) return pd_fail(c, PD_ERR_ARG, "no open contig");
+    int rc = pd_pack_contig(c);
+    if (rc) return rc;
+    *n = c->n_windows_total;
+    return 0;
+}
+
+template <typename T>
+static int grow(pd_ctx * c, T *& p, size_t & cap, size_t need)
+{
+    if (need <= cap && p) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = std::max<size_t>(need + need / 8, 1024);
+    PD_CUDA(c, cudaMalloc(&p, want * sizeof(T)));
+    cap = want;
+    return 0;
+}
+
+extern "C" int pd_contig_upload(pd_ctx * c)
+{
+    if (!c) return PD_ERR_ARG;
+    if (c->status) return c->status;
+    if (c->device < 0) return pd_fail(c, PD_ERR_CUDA, "pd_contig_upload: host-only context (device = -1); the scan needs a CUDA device");
+    if (!c->contig_open) return pd_fail(c, PD_ERR_ARG, "no open contig");
+    if (c->uploaded) return 0;
+    int rc = pd_pack_contig(c);
+    if (rc) return rc;
+    PD_CUDA(c, cudaSetDevice(c->device));
+    if (grow(c, c->d_words, c->cap_words, c->h_words.size() + 4)) return c->status;
+    if (grow(c, c->d_tile_off, c->cap_tile_off, c->h_tile_off.size())) return c->status;
+    if (grow(c, c->d_longs, c->cap_longs, c->h_longs.size() + 1)) return c->status;
+    // pinned staging for the big stream
+    if (c->cap_pin_words < c->h_words.size()) {
+        if (c->h_pin_words) cudaFreeHost(c->h_pin_words);
+        c->h_pin_words = nullptr; c->cap_pin_words = 0;
+        size_t want = c->h_words.size() + c->h_words.size() / 8 + 1024;
+        PD_CUDA(c, cudaMallocHost(&c->h_pin_words, want * 4));
+        c->cap_pin_words = want;
+    }
+    PD_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    // chunked copy: fill pinned staging in pieces so the H2D of chunk i overlaps the memcpy of chunk i+1
+    const size_t chunk = 16u << 20;   // words
+    for (size_t o = 0; o < c->h_words.size(); o += chunk) {
+        size_t m = std::min(chunk, c->h_words.size() - o);
+        memcpy(c->h_pin_words + o, c->h_words.data() + o, m * 4);
+        PD_CUDA(c, cudaMemcpyAsync(c->d_words + o, c->h_pin_words + o, m * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    PD_CUDA(c, cudaMemcpyAsync(c->d_tile_off, c->h_tile_off.data(), c->h_tile_off.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    if (!c->h_longs.empty())
+        PD_CUDA(c, cudaMemcpyAsync(c->d_longs, c->h_longs.data(), c->h_longs.size() * sizeof(PdLong), cudaMemcpyHostToDevice, c->stream));
+    PD_CUDA(c, cudaMemcpyAsync(c->d_long_off, c->h_long_off.data(), (c->R + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    PD_CUDA(c, cudaMemcpyAsync(c->d_long_span, c->h_long_span.data(), c->R * 4, cudaMemcpyHostToDevice, c->stream));
+    PD_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    PD_CUDA(c, cudaStreamSynchronize(c->stream));
+    PD_CUDA(c, cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]));
+    c->uploaded = true;
+    return 0;
+}
+
+extern "C" int pd_contig_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result * out)
+{
+    if (!c || !out) return PD_ERR_ARG;
+    if (c->status) return c->status;
+    if (c->device < 0) return pd_fail(c, PD_ERR_CUDA, "pd_contig_scan: host-only context (device = -1); the scan runs on a CUDA device only");
+    float h2d = 0;
+    if (!c->uploaded) { int rc = pd_contig_upload(c); if (rc) return rc; h2d = c->ms_h2d; }
+    int rc = pd_run_scan(c, first_window, n_windows, out);
+    if (rc == 0) { out->ms_h2d = h2d; out->ms_total += h2d; }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-only validation hook: per-window sums from the PACKED image with the closed-form rule
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int pd_debug_host_window_sums(pd_ctx * c, uint32_t rg, uint64_t first_window, uint64_t n_windows, int64_t * out)
+{
+    if (!c || !out || rg >= c->R) return PD_ERR_ARG;
+    if (c->status) return c->status;
+    if (!c->contig_open) return pd_fail(c, PD_ERR_ARG, "no open contig");
+    int rc = pd_pack_contig(c);
+    if (rc) return rc;
+    memset(out, 0, sizeof(int64_t) * 3 * n_windows);
+    const PdRgConst & k = c->rgc[rg];
+    const uint32_t * off = &c->h_tile_off[(size_t)rg * (c->NT + 1)];
+    auto add = [&](int64_t s, int64_t e, int32_t d, uint64_t pr) {
+        for (int64_t w = std::max<int64_t>(s, (int64_t)first_window); w <= e && w < (int64_t)(first_window + n_windows); ++w) {
+            int64_t * o = out + 3 * (w - first_window);
+            o[0] += 1; o[1] += d; o[2] += (int64_t)(pr + c->grid.anchor);
+        }
+    };
+    for (uint32_t t = 0; t < c->NT; ++t)
+        for (uint32_t i = off[t]; i < off[t + 1]; ++i) {
+            uint32_t w = c->h_words[i];
+            if (pd_word_long(w)) continue;                         // pads and long read pairs
+            uint64_t pr = (uint64_t)t * PD_TILE_BP + pd_word_pit(w);
+            int64_t s, e;
+            if (pd_interval(pr, pd_word_dev(w), k.inner_off, c->grid.window_buffer, s, e)) add(s, e, pd_word_dev(w), pr);
+        }
+    for (uint32_t i = c->h_long_off[rg]; i < c->h_long_off[rg + 1]; ++i) {
+        const PdLong & L = c->h_longs[i];
+        add(L.s, L.e, L.dev, L.pos_rel);
+    }
+    return 0;
+}
+
+// pd_contig_synthesize is implemented in pd_synth.cu

@@ -1,0 +1,957 @@
+// pd_kernels.cu -- sm_100a kernels of the `popdel call` window scan and their orchestration.
+//
+//   k_screen      (K1, HBM-bound)  every (sample, window): streams the packed read-pair words once, counts the
+//                                   active read pairs and those above the smallest initial-length threshold, and flags
+//                                   windows in which some sample's upper-half median CAN exceed that threshold
+//                                   (exact necessary condition for initialize_deletion_lengths to return a candidate,
+//                                   reference genotype_deletion_popdel_call.h:33-87).
+//   k_gather      (K2a)            flagged windows only: exact active sets per (window, read group), coverage /
+//                                   high-coverage state and the per-sample Q3 (upperHalfMedian, :15-27).
+//   k_candidates  (K2b)            per flagged window: sort Q3s over samples, gap-50 clustering, rank-indexed
+//                                   thresholds -> candidate initial lengths (:58-86).
+//   k_em          (K3-K5)          per (window, initial length): allele-frequency initialisation (:93-133), EM over
+//                                   deletion length / reference shifts / allele frequency (:556-664), final genotype
+//                                   likelihoods, LAD/DAD/FL, supporting read percentiles, LR test, PL (:665-727).
+// No tensor cores: the path is lookup-and-reduce (BASELINE.json north_star).
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "pd_context.h"
+
+#define PD_CUDA(c, call)                                                                          \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return pd_fail((c), PD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+namespace {
+
+constexpr uint32_t FULL = 0xFFFFFFFFu;
+constexpr double LN2_D = 0.693147180559945309417232121458;       // the reference evaluates log(2.0) in double
+constexpr double LOG10_2_D = 0.301029995663981195213738894724;
+// expl() underflows to 0 below ln(2^-16446): the reference's `res == 0` test on long double (:240, :324)
+constexpr double LD_EXP_ZERO = -11399.4985314888605;
+
+enum { CNT_JOBS = 0, CNT_PAIRS = 1, CNT_POOL = 2, CNT_CALLS = 3, CNT_FLAGS = 4, CNT_ERR = 5 };
+
+struct PoolEntry { uint32_t pos_rel; int32_t dev; };
+struct PdPair { uint32_t job; int32_t L0; };
+
+// ------------------------------------------------------------------------------------------------------------------
+// interval of a stream word, with the per-tile segment constants hoisted (pd_common.h holds the plain version)
+// ------------------------------------------------------------------------------------------------------------------
+struct TileSeg { uint32_t base_bp; uint32_t nb; int32_t wlA, wlB, wlC; };
+
+__device__ __forceinline__ TileSeg tile_seg(uint32_t tile, uint32_t wb)
+{
+    TileSeg t;
+    uint64_t base = (uint64_t)tile * PD_TILE_BP;
+    uint64_t j0 = base / wb;
+    uint64_t nb = (j0 + 1) * wb;
+    t.base_bp = (uint32_t)base;
+    t.nb = (uint32_t)nb;
+    t.wlA = (int32_t)((nb - 1) / PD_WIN);
+    t.wlB = (int32_t)((nb + wb - 1) / PD_WIN);
+    t.wlC = (int32_t)((nb + 2ull * wb - 1) / PD_WIN);
+    return t;
+}
+
+// returns false for pads / long read pairs / never-active read pairs
+__device__ __forceinline__ bool word_interval(uint32_t w, const TileSeg & ts, int32_t inner_off, int32_t & s, int32_t & e,
+                                              int32_t & dev, uint32_t & pos_rel)
+{
+    if (w & PD_LONG_BIT) return false;
+    dev = (int32_t)w >> 11;
+    pos_rel = ts.base_bp + (w & 0x3FFu);
+    uint32_t b = pos_rel / PD_WIN;
+    uint32_t bp = b * PD_WIN;
+    int32_t inner = dev + inner_off;
+    inner = inner < 0 ? 0 : inner;
+    int32_t lw = (int32_t)((pos_rel + (uint32_t)inner) / PD_WIN);
+    bool next = bp >= ts.nb;
+    int32_t wl = next ? ts.wlB : ts.wlA;
+    int32_t wl2 = next ? ts.wlC : ts.wlB;
+    s = (int32_t)b + (pos_rel != bp ? 1 : 0);
+    e = lw + 1;
+    int32_t cap = lw <= wl ? wl : wl2;
+    e = e < cap ? e : cap;
+    return s <= wl;
+}
+
+__device__ __forceinline__ uint32_t lower_bound_long(const PdLong * L, uint32_t lo, uint32_t hi, int64_t key_s)
+{
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if ((int64_t)L[mid].s < key_s) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K1: screen. One warp = one tile (32 windows) of one sample; lane = window.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_screen(PdDev a, uint32_t tile_begin, uint32_t tile_end, uint32_t * __restrict__ flags,
+                                                uint32_t * __restrict__ jobs, uint32_t * __restrict__ counters)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t tile = tile_begin + blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (tile >= tile_end) return;
+    const uint32_t smp = blockIdx.y;
+    const uint32_t g0 = a.sample_rg[smp], g1 = a.sample_rg[smp + 1];
+    const int32_t w0 = (int32_t)(tile * PD_TILE_WINDOWS), w = w0 + lane;
+    const int32_t thr = (int32_t)(((uint32_t)a.t_min << 11) | 0x7FFu);      // (int)word > thr  <=>  dev > t_min
+
+    // ---- phase A: is there any read pair above the threshold that can be active in this tile?
+    bool any = false;
+    for (uint32_t g = g0; g < g1; ++g) {
+        const uint32_t * toff = a.tile_off + (size_t)g * (a.NT + 1);
+        const uint32_t lb = a.rgc[g].lookback_tiles;
+        const uint32_t t_lo = tile > lb ? tile - lb : 0;
+        const uint32_t r0 = toff[t_lo], r1 = toff[tile + 1];
+        for (uint32_t i = r0 + lane * 4; i < r1; i += 128) {
+            uint4 v = __ldg(reinterpret_cast<const uint4 *>(a.words + i));
+            any |= ((int32_t)v.x > thr) | ((int32_t)v.y > thr) | ((int32_t)v.z > thr) | ((int32_t)v.w > thr);
+        }
+        const uint32_t l0 = a.long_off[g], l1 = a.long_off[g + 1];
+        if (l1 > l0) {
+            uint32_t lo = lower_bound_long(a.longs, l0, l1, (int64_t)w0 - (int64_t)a.long_span[g]);
+            for (uint32_t i = lo + lane; i < l1; i += 32) {
+                PdLong L = a.longs[i];
+                if ((int64_t)L.s > (int64_t)w0 + 31) break;
+                any |= ((int64_t)L.e >= w0);
+            }
+        }
+    }
+    if (!__any_sync(FULL, any)) return;
+
+    // ---- phase B: exact counts per window (lane) for every read group of the sample
+    uint32_t cov = 0, n = 0, x = 0;
+    for (uint32_t g = g0; g < g1; ++g) {
+        const uint32_t * toff = a.tile_off + (size_t)g * (a.NT + 1);
+        const PdRgConst k = a.rgc[g];
+        const uint32_t t_lo = tile > k.lookback_tiles ? tile - k.lookback_tiles : 0;
+        uint32_t n_g = 0, x_g = 0;
+        for (uint32_t tt = t_lo; tt <= tile; ++tt) {
+            const TileSeg ts = tile_seg(tt, a.window_buffer);
+            const uint32_t r_lo = toff[tt], r_hi = toff[tt + 1];
+            for (uint32_t base = r_lo; base < r_hi; base += 32) {
+                const uint32_t i = base + lane;
+                const uint32_t word = i < r_hi ? __ldg(a.words + i) : PD_PAD_WORD;
+                int32_t s = 0, e = 0, dev = 0; uint32_t pr;
+                bool valid = word_interval(word, ts, k.inner_off, s, e, dev, pr);
+                valid = valid && e >= w0 && s <= w0 + 31;
+                uint32_t pk = (uint32_t)e | (dev > a.t_min ? 0x80000000u : 0u);
+                uint32_t mask = __ballot_sync(FULL, valid);
+                while (mask) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int32_t ss = __shfl_sync(FULL, s, src);
+                    const uint32_t ee = __shfl_sync(FULL, pk, src);
+                    const bool hit = ss <= w && w <= (int32_t)(ee & 0x7FFFFFFFu);
+                    n_g += hit;
+                    x_g += hit & (ee >> 31);
+                }
+            }
+        }
+        const uint32_t l0 = a.long_off[g], l1 = a.long_off[g + 1];
+        if (l1 > l0) {
+            uint32_t lo = lower_bound_long(a.longs, l0, l1, (int64_t)w0 - (int64_t)a.long_span[g]);
+            for (uint32_t base = lo; base < l1; base += 32) {
+                const uint32_t i = base + lane;
+                PdLong L = i < l1 ? a.longs[i] : PdLong{0xFFFFFFFFu, 0, 0, 0};
+                bool beyond = (int64_t)L.s > (int64_t)w0 + 31;
+                bool valid = i < l1 && !beyond && (int64_t)L.e >= w0;
+                uint32_t pk = L.e | (L.dev > a.t_min ? 0x80000000u : 0u);
+                uint32_t mask = __ballot_sync(FULL, valid);
+                while (mask) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int32_t ss = (int32_t)__shfl_sync(FULL, L.s, src);
+                    const uint32_t ee = __shfl_sync(FULL, pk, src);
+                    const bool hit = ss <= w && w <= (int32_t)(ee & 0x7FFFFFFFu);
+                    n_g += hit;
+                    x_g += hit & (ee >> 31);
+                }
+                if (__all_sync(FULL, beyond || i >= l1)) break;
+            }
+        }
+        cov += n_g;
+        if (n_g < k.max_load) { n += n_g; x += x_g; }
+    }
+    const bool in_range = (uint32_t)w >= a.w_begin && (uint32_t)w < a.w_end;
+    const bool pass = in_range && cov >= 2 && n >= 1 && x >= pd_q3_need(n);
+    if (pass) {
+        const uint32_t wi = (uint32_t)w - a.w_begin;
+        if (flags[wi] == 0 && atomicExch(&flags[wi], 1u) == 0) {
+            uint32_t slot = atomicAdd(&counters[CNT_JOBS], 1u);
+            jobs[slot] = (uint32_t)w;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K2a: gather. One warp = one (flagged window, sample).
+// ------------------------------------------------------------------------------------------------------------------
+struct GatherArgs {
+    const uint32_t * jobs; uint32_t job0, njobs;
+    PoolEntry * pool; uint32_t pool_cap;
+    uint32_t * counters;
+    uint32_t * act_off, * act_cnt;       // [njobs][R]
+    int32_t * q3; uint8_t * sstat;       // [njobs][N]   sstat: 0 = low coverage, 1 = no usable values, 2 = Q3 valid
+};
+
+// calls f(valid, pos_rel, dev) for every 32-wide batch of read pairs of read group g that may be active at window w;
+// `valid` marks lanes whose read pair IS active at w. Batches preserve stream order (stream first, then long list).
+template <typename F>
+__device__ __forceinline__ void for_active_batches(const PdDev & a, uint32_t g, const PdRgConst & k, int32_t w, int lane, F f)
+{
+    const uint32_t * toff = a.tile_off + (size_t)g * (a.NT + 1);
+    const uint32_t tile = (uint32_t)w / PD_TILE_WINDOWS;
+    const uint32_t t_lo = tile > k.lookback_tiles ? tile - k.lookback_tiles : 0;
+    for (uint32_t tt = t_lo; tt <= tile; ++tt) {
+        const TileSeg ts = tile_seg(tt, a.window_buffer);
+        const uint32_t r_lo = toff[tt], r_hi = toff[tt + 1];
+        for (uint32_t base = r_lo; base < r_hi; base += 32) {
+            const uint32_t i = base + lane;
+            const uint32_t word = i < r_hi ? __ldg(a.words + i) : PD_PAD_WORD;
+            int32_t s = 0, e = 0, dev = 0; uint32_t pr = 0;
+            bool valid = word_interval(word, ts, k.inner_off, s, e, dev, pr);
+            valid = valid && s <= w && w <= e;
+            f(valid, pr, dev);
+        }
+    }
+    const uint32_t l0 = a.long_off[g], l1 = a.long_off[g + 1];
+    if (l1 > l0) {
+        uint32_t lo = lower_bound_long(a.longs, l0, l1, (int64_t)w - (int64_t)a.long_span[g]);
+        for (uint32_t base = lo; base < l1; base += 32) {
+            const uint32_t i = base + lane;
+            PdLong L = i < l1 ? a.longs[i] : PdLong{0xFFFFFFFFu, 0, 0, 0};
+            bool beyond = (int64_t)L.s > (int64_t)w;
+            bool valid = i < l1 && !beyond && (int64_t)L.e >= w;
+            f(valid, L.pos_rel, L.dev);
+            if (__all_sync(FULL, beyond || i >= l1)) break;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_gather(PdDev a, GatherArgs ga)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t job = blockIdx.x;
+    const uint32_t smp = blockIdx.y * 4 + (threadIdx.x >> 5);
+    if (smp >= a.N) return;
+    const int32_t w = (int32_t)ga.jobs[ga.job0 + job];
+    const uint32_t g0 = a.sample_rg[smp], g1 = a.sample_rg[smp + 1];
+    uint32_t * cnt = ga.act_cnt + (size_t)job * a.R;
+    uint32_t * off = ga.act_off + (size_t)job * a.R;
+
+    // pass 1: counts
+    uint32_t cov = 0, nvals = 0;
+    for (uint32_t g = g0; g < g1; ++g) {
+        const PdRgConst k = a.rgc[g];
+        uint32_t n_g = 0;
+        for_active_batches(a, g, k, w, lane, [&](bool valid, uint32_t, int32_t) { n_g += __popc(__ballot_sync(FULL, valid)); });
+        if (lane == 0) cnt[g] = n_g;
+        cov += n_g;
+        if (n_g < k.max_load) nvals += n_g;
+    }
+    uint32_t base = 0;
+    if (lane == 0 && nvals) base = atomicAdd(&ga.counters[CNT_POOL], nvals);
+    base = __shfl_sync(FULL, base, 0);
+    const bool fits = (uint64_t)base + nvals <= ga.pool_cap;
+    // pass 2: entries (stream order)
+    uint32_t cur = base;
+    for (uint32_t g = g0; g < g1; ++g) {
+        const PdRgConst k = a.rgc[g];
+        if (lane == 0) off[g] = cur;
+        const uint32_t n_g = __shfl_sync(FULL, lane == 0 ? cnt[g] : 0u, 0);
+        if (n_g >= k.max_load || !fits) continue;
+        for_active_batches(a, g, k, w, lane, [&](bool valid, uint32_t pr, int32_t dev) {
+            uint32_t mask = __ballot_sync(FULL, valid);
+            if (valid) ga.pool[cur + __popc(mask & ((1u << lane) - 1u))] = PoolEntry{pr, dev};
+            cur += __popc(mask);
+        });
+    }
+    __syncwarp();
+    // coverage state and Q3
+    uint8_t st; int32_t q = 0;
+    if (cov < 2u) st = 0;
+    else if (nvals == 0 || !fits) st = 1;
+    else {
+        st = 2;
+        const volatile PoolEntry * v = ga.pool + base;
+        const uint32_t nn = nvals;
+        int32_t lo_v = 0, hi_v = 0;            // order statistics l and l+1
+        uint32_t l;
+        double r = 0;
+        if (nn < 4) { l = nn - 1; }
+        else { double pos = (3.0 * nn + 2.0 + (nn % 2)) / 4.0 - 1.0; l = (uint32_t)pos; r = pos - l; }
+        const uint32_t l2 = (l + 1 < nn) ? l + 1 : l;
+        for (uint32_t i0 = 0; i0 < nn; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            int32_t vi = i < nn ? v[i].dev : INT_MAX;
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < nn; ++j) { int32_t vj = v[j].dev; rank += (vj < vi) || (vj == vi && j < i); }
+            uint32_t m1 = __ballot_sync(FULL, i < nn && rank == l);
+            uint32_t m2 = __ballot_sync(FULL, i < nn && rank == l2);
+            if (m1) lo_v = __shfl_sync(FULL, vi, __ffs(m1) - 1);
+            if (m2) hi_v = __shfl_sync(FULL, vi, __ffs(m2) - 1);
+        }
+        if (nn < 4) q = (int32_t)floor((double)lo_v + 0.5);
+        else q = (int32_t)floor((1 - r) * lo_v + r * hi_v + 0.5);
+    }
+    if (lane == 0) { ga.q3[(size_t)job * a.N + smp] = q; ga.sstat[(size_t)job * a.N + smp] = st; }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K2b: candidates. One block per flagged window.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_candidates(PdDev a, const int32_t * __restrict__ q3, const uint8_t * __restrict__ sstat,
+                                                    uint32_t job0, uint32_t * counters, PdPair * pairs, uint32_t pair_cap, uint32_t npad)
+{
+    extern __shared__ int32_t sv[];
+    __shared__ uint32_t s_n;
+    const uint32_t job = blockIdx.x;
+    if (threadIdx.x == 0) s_n = 0;
+    for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) sv[i] = INT_MAX;
+    __syncthreads();
+    for (uint32_t s = threadIdx.x; s < a.N; s += blockDim.x)
+        if (sstat[(size_t)job * a.N + s] == 2) sv[atomicAdd(&s_n, 1u)] = q3[(size_t)job * a.N + s];
+    __syncthreads();
+    const uint32_t nv = s_n;
+    if (nv == 0) return;
+    for (uint32_t k = 2; k <= npad; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) {
+                uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    int32_t x = sv[i], y = sv[ixj];
+                    bool up = (i & k) == 0;
+                    if ((x > y) == up) { sv[i] = y; sv[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    if (threadIdx.x == 0) {
+        // genotype_deletion_popdel_call.h:62-84; thresholds are indexed by RANK in the sorted array (quirk)
+        int sum = sv[0], n = 1;
+        uint32_t thr = a.rgc[0].min_init;
+        auto emit = [&](int mean) {
+            uint32_t slot = atomicAdd(&counters[CNT_PAIRS], 1u);
+            if (slot < pair_cap) pairs[slot] = PdPair{job0 + job, mean};
+        };
+        for (uint32_t i = 1; i < nv; ++i) {
+            if (sv[i - 1] + 50 > sv[i]) { sum += sv[i]; ++n; thr = min(thr, a.rgc[i].min_init); }
+            else { if (sum / n > (int)thr) emit(sum / n); sum = sv[i]; n = 1; thr = a.rgc[i].min_init; }
+        }
+        if (sum / n > (int)thr) emit(sum / n);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K3-K5: EM + final pass. One block per (flagged window, initial length); thread = sample (strided).
+// ------------------------------------------------------------------------------------------------------------------
+struct EmArgs {
+    const uint32_t * jobs; const PdPair * pairs; uint32_t pair0, npairs, job_base;   // pairs[].job is absolute; scratch uses job - job_base
+    const PoolEntry * pool; const uint32_t * act_off, * act_cnt; const uint8_t * sstat;
+    double * dlx;            // [block][N][3]   data likelihoods, log domain, max = 0
+    int32_t * shifts;        // [block][R]
+    uint32_t * ps;           // [block][N][13]
+    uint32_t * counters;
+    pd_call * out_calls; uint32_t * out_ps; uint32_t out_cap;
+    uint32_t iterations, min_len; double min_lr, min_sample_fraction; int somatic, window_wise; uint32_t anchor;
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+// deterministic block sum of two doubles (fixed shuffle tree, then warps in index order); result on all threads
+__device__ __forceinline__ void block_sum2(double & a, double & b, double * red)
+{
+    a = warp_sum(a); b = warp_sum(b);
+    const int wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { red[2 * wid] = a; red[2 * wid + 1] = b; }
+    __syncthreads();
+    double sa = 0, sb = 0;
+    for (int i = 0; i < nw; ++i) { sa += red[2 * i]; sb += red[2 * i + 1]; }
+    a = sa; b = sb;
+}
+__device__ __forceinline__ void block_sum2u(unsigned long long & a, unsigned long long & b, unsigned long long * red)
+{
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(FULL, a, o); b += __shfl_xor_sync(FULL, b, o); }
+    const int wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { red[2 * wid] = a; red[2 * wid + 1] = b; }
+    __syncthreads();
+    unsigned long long sa = 0, sb = 0;
+    for (int i = 0; i < nw; ++i) { sa += red[2 * i]; sb += red[2 * i + 1]; }
+    a = sa; b = sb;
+}
+
+__device__ __forceinline__ double hist_at(const double * __restrict__ tab, const PdRgConst & k, int dev, double floor_v)
+{
+    int i = dev + k.hist_base;                        // I(), insert_histogram_popdel.h:1157-1163
+    if (i <= 0 || i + 1 >= (int)k.hist_len) return floor_v;
+    return __ldg(tab + k.hist_off + i);
+}
+
+struct Gt { double a, b, c; };
+__device__ __forceinline__ Gt gt_prior(double f, int somatic)       // :343-380
+{
+    const double ps = 0.0000000001;
+    Gt g;
+    if (!somatic) { g.a = fmax((1 - f) * (1 - f), ps); g.b = fmax(2 * f * (1 - f), ps); g.c = fmax(f * f, ps); }
+    else if (f <= 0.4) { g.a = fmax(1 - 2 * f + ps, ps); g.b = fmax(2 * f - 2 * ps, ps); g.c = ps; }
+    else if (f < 0.75) { g.a = ps; g.b = 1.; g.c = ps; }
+    else { g.a = ps; g.b = ps; g.c = 1.; }
+    return g;
+}
+
+struct EmShared {
+    double red[64];
+    unsigned long long redu[64];
+    double rgw[3];                     // log-domain per-RG likelihoods of read group 0 (quirk: drives all reference shifts)
+    double freq, prevFreq, lr, plr;
+    Gt gt, prevGt;
+    double ea0Rg, ea1Rg;
+    uint32_t len, prevLen, it;
+    int visited_len[64]; double visited_freq[64]; int nvisited;
+    int stop;
+};
+
+// data likelihoods of every sample for (L, shifts) -> dlx; compute_data_likelihoods (EM overload) :179-253
+__device__ void compute_dl(const PdDev & a, const EmArgs & e, EmShared & sh, const uint32_t * cnt, const uint32_t * off,
+                           double * dlx, const int32_t * shifts, bool zero_shifts, uint32_t L)
+{
+    for (uint32_t s = threadIdx.x; s < a.N; s += blockDim.x) {
+        double l0 = 0, l1 = 0, l2 = 0;
+        for (uint32_t g = a.sample_rg[s]; g < a.sample_rg[s + 1]; ++g) {
+            const PdRgConst k = a.rgc[g];
+            const uint32_t n = cnt[g];
+            double w0 = 0, w1 = 0, w2 = 0;
+            const bool high = n >= k.max_load;
+            if (!high) {
+                const int shift = zero_shifts ? 0 : shifts[g];
+                const PoolEntry * p = e.pool + off[g];
+                for (uint32_t i = 0; i < n; ++i) {
+                    const int d = p[i].dev;
+                    const double ref = hist_at(a.tab_val, k, d - shift, k.min_prob);
+                    const double del = hist_at(a.tab_val, k, d - (int)L, k.min_prob);
+                    const double g0 = hist_at(a.tab_ln, k, d - shift, k.ln_min_prob);
+                    const double g2 = hist_at(a.tab_ln, k, d - (int)L, k.ln_min_prob);
+                    const double g1 = log(ref + del) - LN2_D;
+                    w0 += g0; w1 += g1; w2 += g2;
+                    l0 += g0; l1 += g1; l2 += g2;
+                }
+            }
+            if (g == 0) {
+                if (high) { sh.rgw[0] = sh.rgw[1] = sh.rgw[2] = -INFINITY; }     // Triple(0,0,0) in the reference
+                else { double m = fmax(fmax(w0, w1), w2); sh.rgw[0] = w0 - m; sh.rgw[1] = w1 - m; sh.rgw[2] = w2 - m; }
+            }
+        }
+        const double m = fmax(fmax(l0, l1), l2);
+        double x0 = l0 - m, x1 = l1 - m, x2 = l2 - m;
+        const double LN1E10 = log(0.0000000001);
+        if (x0 < LD_EXP_ZERO || x1 < LD_EXP_ZERO || x2 < LD_EXP_ZERO) { x0 = 0; x1 = LN1E10; x2 = LN1E10; }
+        if (x0 == x1 && x0 == x2) { x0 = 0; x1 = LN1E10; x2 = LN1E10; }
+        dlx[3 * s] = x0; dlx[3 * s + 1] = x1; dlx[3 * s + 2] = x2;
+    }
+    __syncthreads();
+}
+
+// deletion_likelihood_ratio :490-508 (block-wide; result on all threads)
+__device__ double block_lr(const PdDev & a, EmShared & sh, const double * dlx, const Gt gt)
+{
+    double del = 0, nodel = 0;
+    for (uint32_t s = threadIdx.x; s < a.N; s += blockDim.x) {
+        const double x0 = dlx[3 * s], A = exp(x0), B = exp(dlx[3 * s + 1]), C = exp(dlx[3 * s + 2]);
+        const double p0 = A * gt.a, p1 = B * gt.b, p2 = C * gt.c, pAll = p0 + p1 + p2;
+        const double a0 = p0 / pAll, a1 = p1 / pAll, a2 = p2 / pAll;
+        del += log(a0 * A + a1 * B + a2 * C);
+        nodel += x0;
+    }
+    block_sum2(del, nodel, sh.red);
+    return del - nodel;
+}
+
+__global__ void __launch_bounds__(256) k_em(PdDev a, EmArgs e)
+{
+    __shared__ EmShared sh;
+    const uint32_t pi = e.pair0 + blockIdx.x;
+    const PdPair pr = e.pairs[pi];
+    const uint32_t job = pr.job - e.job_base;
+    const uint32_t L0 = (uint32_t)pr.L0;
+    const uint32_t w = e.jobs[pr.job];
+    const uint32_t * cnt = e.act_cnt + (size_t)job * a.R;
+    const uint32_t * off = e.act_off + (size_t)job * a.R;
+    const uint8_t * sstat = e.sstat + (size_t)job * a.N;
+    double * dlx = e.dlx + (size_t)blockIdx.x * 3 * a.N;
+    int32_t * shifts = e.shifts + (size_t)blockIdx.x * a.R;
+    uint32_t * ps = e.ps + (size_t)blockIdx.x * 13 * a.N;
+    const int tid = threadIdx.x;
+
+    for (uint32_t g = tid; g < a.R; g += blockDim.x) shifts[g] = 0;
+
+    // ---- initialize_allele_frequency :93-133
+    {
+        unsigned long long c = 0, t = 0;
+        for (uint32_t g = tid; g < a.R; g += blockDim.x) {
+            const PdRgConst k = a.rgc[g];
+            const uint32_t n = cnt[g];
+            if (n == 0 || n >= k.max_load) continue;
+            t += n;
+            const int wb = max((int)L0 / 2, (int)floor((double)L0 - 2 * k.stddev + 0.5));
+            const int we = (int)((double)L0 + 2 * k.stddev);
+            const PoolEntry * p = e.pool + off[g];
+            for (uint32_t i = 0; i < n; ++i) { const int d = p[i].dev; c += (d > wb && d < we); }
+        }
+        block_sum2u(c, t, sh.redu);
+        if (tid == 0) {
+            sh.freq = t == 0 ? 0.0 : (double)c / (double)t;
+            sh.len = L0; sh.it = 0; sh.nvisited = 0; sh.stop = 0;
+        }
+        __syncthreads();
+    }
+    if (sh.freq == 0) return;
+    compute_dl(a, e, sh, cnt, off, dlx, shifts, false, L0);
+    if (tid == 0) { sh.gt = gt_prior(sh.freq, e.somatic); sh.prevFreq = sh.freq; sh.prevLen = sh.len; sh.prevGt = sh.gt; }
+    __syncthreads();
+
+    // ---- EM loop :598-660
+    while (true) {
+        const bool cont = sh.len >= e.min_len && sh.it < e.iterations;
+        __syncthreads();                      // everyone has evaluated the loop condition before thread 0 touches it
+        if (!cont) break;
+        if (tid == 0) {
+            ++sh.it;
+            int key = (int)sh.len, f = -1;
+            for (int i = 0; i < sh.nvisited; ++i) if (sh.visited_len[i] == key) f = i;
+            if (f < 0) { f = sh.nvisited++; sh.visited_len[f] = key; }
+            sh.visited_freq[f] = sh.freq;
+            sh.prevLen = sh.len; sh.prevFreq = sh.freq; sh.prevGt = sh.gt;
+            // weights of read group 0 (rgDlIt is never advanced, :401,424-431)
+            const double r0 = exp(sh.rgw[0]), r1 = exp(sh.rgw[1]), r2 = exp(sh.rgw[2]);
+            const double aSumRg = r0 * sh.gt.a + r1 * sh.gt.b + r2 * sh.gt.c;
+            const double a0Rg = sh.rgw[0] + log(sh.gt.a) - log(aSumRg);
+            const double a1Rg = sh.rgw[1] + log(sh.gt.b) - log(aSumRg);
+            sh.ea0Rg = exp(a0Rg); sh.ea1Rg = exp(a1Rg);
+        }
+        __syncthreads();
+        // update_deletion_length :388-462
+        const Gt gt = sh.gt;
+        const int L = (int)sh.len;
+        const double ea0Rg = sh.ea0Rg, ea1Rg = sh.ea1Rg;
+        double sumDel = 0, wDel = 0;
+        for (uint32_t s = tid; s < a.N; s += blockDim.x) {
+            const double x1 = dlx[3 * s + 1], x2 = dlx[3 * s + 2];
+            const double aSum = exp(dlx[3 * s]) * gt.a + exp(x1) * gt.b + exp(x2) * gt.c;
+            const double a1 = x1 + log(gt.b) - log(aSum);
+            const double a2 = x2 + log(gt.c) - log(aSum);
+            const double ea1 = exp(a1), ea2 = exp(a2);
+            for (uint32_t g = a.sample_rg[s]; g < a.sample_rg[s + 1]; ++g) {
+                const PdRgConst k = a.rgc[g];
+                const uint32_t n = cnt[g];
+                if (n >= k.max_load) continue;
+                double sumRef = 0, wRef = 0;
+                const int shift = shifts[g];
+                const PoolEntry * p = e.pool + off[g];
+                for (uint32_t i = 0; i < n; ++i) {
+                    const int d = p[i].dev;
+                    const double del = hist_at(a.tab_val, k, d - L, k.min_prob);
+                    const double nod = hist_at(a.tab_val, k, d - shift, k.min_prob);
+                    const double pd = ea1 * del / (del + nod) + ea2;
+                    const double prf = ea1Rg * nod / (del + nod) + ea0Rg;
+                    sumDel += pd; sumRef += prf;
+                    wDel += pd * d; wRef += prf * d;
+                }
+                const double q = wRef / sumRef;
+                int sft = (q != q) ? 0 : (q >= 2147483647.0 ? INT_MAX : (q <= -2147483648.0 ? INT_MIN : (int)q));
+                if (sft > k.stddev || sft < -1 * k.stddev) sft = 0;
+                shifts[g] = sft;
+            }
+        }
+        block_sum2(sumDel, wDel, sh.red);
+        if (tid == 0) {
+            uint32_t nl;
+            if (sumDel == 0) nl = 0;
+            else { double len = wDel / sumDel; nl = len < 0 ? 0u : (uint32_t)round(len); }
+            sh.len = nl;
+        }
+        __syncthreads();
+        compute_dl(a, e, sh, cnt, off, dlx, shifts, false, sh.len);
+        // update_allele_frequency :467-485 (with the genotype priors of the previous iteration)
+        double fs = 0, dummy = 0;
+        for (uint32_t s = tid; s < a.N; s += blockDim.x) {
+            const double p0 = exp(dlx[3 * s]) * gt.a, p1 = exp(dlx[3 * s + 1]) * gt.b, p2 = exp(dlx[3 * s + 2]) * gt.c;
+            fs += (p1 + 2 * p2) / (p0 + p1 + p2);
+        }
+        block_sum2(fs, dummy, sh.red);
+        if (tid == 0) {
+            sh.freq = fs / 2.0 / a.N;
+            sh.stop = 0;
+            if (sh.freq == 0) sh.stop = 1;
+            else {
+                sh.gt = gt_prior(sh.freq, e.somatic);
+                int key = (int)sh.len;
+                for (int i = 0; i < sh.nvisited; ++i)
+                    if (sh.visited_len[i] == key && fabs(sh.visited_freq[i] - sh.freq) <= 0.0001) sh.stop = 2;
+            }
+        }
+        __syncthreads();
+        if (sh.stop == 1) break;
+        if (sh.stop == 2) {
+            // convergence :632-658: compare with the previous estimate evaluated with the initial (zero) shifts
+            const double lr = block_lr(a, sh, dlx, sh.gt);
+            compute_dl(a, e, sh, cnt, off, dlx, shifts, true, sh.prevLen);
+            const double plr = block_lr(a, sh, dlx, sh.prevGt);
+            __syncthreads();
+            if (plr > lr) {
+                if (tid == 0) { sh.len = sh.prevLen; sh.freq = sh.prevFreq; }
+                for (uint32_t g = tid; g < a.R; g += blockDim.x) shifts[g] = 0;
+            }
+            __syncthreads();
+            break;
+        }
+    }
+    __syncthreads();
+    if (sh.freq < 0.0000000001 || sh.len < e.min_len) return;
+
+    // ---- final pass :665-727 (compute_data_likelihoods final overload :255-337)
+    const int len = (int)sh.len;
+    unsigned long long supp = 0, ndata = 0;
+    uint32_t smin = 0xFFFFFFFFu, smax = 0, lmin = 0xFFFFFFFFu, lmax = 0;   // ranges of supporting starts / ends
+    for (uint32_t s = tid; s < a.N; s += blockDim.x) {
+        uint32_t lad[3] = {0, 0, 0}, dad[5] = {0, 0, 0, 0, 0};
+        uint32_t fl_min = 0xFFFFFFFFu, fl_max = 0;
+        double l0 = 0, l1 = 0, l2 = 0, t0 = 0, t1 = 0, t2 = 0;
+        int delLower = INT_MAX, delUpper = 0;
+        const uint32_t g0 = a.sample_rg[s], g1 = a.sample_rg[s + 1];
+        for (uint32_t g = g0; g < g1; ++g) {
+            const PdRgConst k = a.rgc[g];
+            const uint32_t n = cnt[g];
+            if (n >= k.max_load) continue;
+            const int shift = shifts[g];
+            delLower = len - k.lower_q; delUpper = len + k.upper_q;
+            const PoolEntry * p = e.pool + off[g];
+            for (uint32_t i = 0; i < n; ++i) {
+                const int d = p[i].dev;
+                if (d > k.upper_q) { if (d < delLower) ++dad[2]; else if (d <= delUpper) ++dad[3]; else ++dad[4]; }
+                else { if (d < delUpper) ++dad[0]; else ++dad[1]; }
+                const double ref = hist_at(a.tab_val, k, d - shift, k.min_prob);
+                const double del = hist_at(a.tab_val, k, d - len, k.min_prob);
+                if (ref >= 2 * del) ++lad[0]; else if (del >= 2 * ref) ++lad[2]; else ++lad[1];
+                l0 += hist_at(a.tab_ln, k, d - shift, k.ln_min_prob);
+                t0 += hist_at(a.tab_l10, k, d - shift, k.l10_min_prob);
+                l1 += log(ref + del) - LN2_D;
+                t1 += log10(ref + del) - LOG10_2_D;
+                l2 += hist_at(a.tab_ln, k, d - len, k.ln_min_prob);
+                t2 += hist_at(a.tab_l10, k, d - len, k.l10_min_prob);
+                const uint32_t first = p[i].pos_rel + e.anchor;
+                const int isz = max(0, d + k.inner_off);
+                const uint32_t last = first + (uint32_t)isz;
+                fl_min = min(fl_min, first); fl_max = max(fl_max, last);
+            }
+        }
+        // supporting read pairs: borders of the LAST usable read group apply to all of the sample's read groups (quirk)
+        for (uint32_t g = g0; g < g1; ++g) {
+            const PdRgConst k = a.rgc[g];
+            const uint32_t n = cnt[g];
+            if (n >= k.max_load) continue;
+            const PoolEntry * p = e.pool + off[g];
+            for (uint32_t i = 0; i < n; ++i) {
+                const int d = p[i].dev;
+                if (d >= delLower && d <= delUpper) {
+                    const uint32_t first = p[i].pos_rel + e.anchor;
+                    const uint32_t last = first + (uint32_t)max(0, d + k.inner_off);
+                    ++supp; smin = min(smin, first); smax = max(smax, first); lmin = min(lmin, last); lmax = max(lmax, last);
+                }
+            }
+        }
+        if (fl_min == 0xFFFFFFFFu) fl_min = 0;
+        double x0, x1, x2, g0l = t0, g1l = t1, g2l = t2;
+        const double LN1E10 = log(0.0000000001);
+        if (t0 + t1 + t2 == 0.0) { x0 = 0; x1 = LN1E10; x2 = LN1E10; }
+        else {
+            const double mg = fmax(fmax(t0, t1), t2), md = fmax(fmax(l0, l1), l2);
+            g0l -= mg; g1l -= mg; g2l -= mg;
+            if (g0l == g1l && g0l == g2l) { g0l = 0; g1l = -10; g2l = -10; }
+            x0 = l0 - md; x1 = l1 - md; x2 = l2 - md;
+            if (x0 < LD_EXP_ZERO || x1 < LD_EXP_ZERO || x2 < LD_EXP_ZERO) { x0 = 0; x1 = LN1E10; x2 = LN1E10; }
+            if (x0 == x1 && x0 == x2) { x0 = 0; x1 = LN1E10; x2 = LN1E10; }
+        }
+        dlx[3 * s] = x0; dlx[3 * s + 1] = x1; dlx[3 * s + 2] = x2;
+        // calculatePhredGL utils_popdel.h:1511-1528
+        const double gTot = log10(exp(g0l) + exp(g1l) + exp(g2l));
+        const double q0 = -10 * (g0l - gTot), q1 = -10 * (g1l - gTot), q2 = -10 * (g2l - gTot);
+        const double mn = fmin(fmin(q0, q1), q2);
+        uint32_t * o = ps + 13 * s;
+        const bool low = sstat[s] == 0;
+        o[0] = low ? 0u : (uint32_t)round(q0 - mn);
+        o[1] = low ? 0u : (uint32_t)round(q1 - mn);
+        o[2] = low ? 0u : (uint32_t)round(q2 - mn);
+        o[3] = lad[0]; o[4] = lad[1]; o[5] = lad[2];
+        o[6] = dad[0]; o[7] = dad[1]; o[8] = dad[2]; o[9] = dad[3]; o[10] = dad[4];
+        o[11] = fl_min; o[12] = fl_max;
+        if (!low) ++ndata;
+    }
+    __syncthreads();
+    block_sum2u(supp, ndata, sh.redu);
+    if (supp == 0) return;
+    // percentiles of the supporting starts (80th) and ends (20th): getSuppFirstLast :514-529, by value bisection
+    uint32_t sF, sL;
+    {
+        // block-wide min/max of the supporting positions (shuffles, then warps in index order)
+        for (int o = 16; o > 0; o >>= 1) {
+            smin = min(smin, __shfl_xor_sync(FULL, smin, o)); smax = max(smax, __shfl_xor_sync(FULL, smax, o));
+            lmin = min(lmin, __shfl_xor_sync(FULL, lmin, o)); lmax = max(lmax, __shfl_xor_sync(FULL, lmax, o));
+        }
+        uint32_t * r32 = reinterpret_cast<uint32_t *>(sh.redu);
+        const int wid = tid >> 5, nw = (blockDim.x + 31) >> 5;
+        __syncthreads();
+        if ((tid & 31) == 0) { r32[4 * wid] = smin; r32[4 * wid + 1] = smax; r32[4 * wid + 2] = lmin; r32[4 * wid + 3] = lmax; }
+        __syncthreads();
+        for (int i = 0; i < nw; ++i) { smin = min(smin, r32[4 * i]); smax = max(smax, r32[4 * i + 1]); lmin = min(lmin, r32[4 * i + 2]); lmax = max(lmax, r32[4 * i + 3]); }
+        __syncthreads();
+        const unsigned long long kF = (unsigned long long)round((double)(supp - 1) * 0.8);
+        const unsigned long long kL = (unsigned long long)round((double)(supp - 1) * (1 - 0.8));
+        uint32_t loF = smin, hiF = smax, loL = lmin, hiL = lmax;
+        while (loF < hiF || loL < hiL) {
+            const uint32_t midF = loF + (hiF - loF) / 2, midL = loL + (hiL - loL) / 2;
+            unsigned long long cF = 0, cL = 0;
+            for (uint32_t s = tid; s < a.N; s += blockDim.x) {
+                int delLower = INT_MAX, delUpper = 0;
+                const uint32_t g0 = a.sample_rg[s], g1 = a.sample_rg[s + 1];
+                for (uint32_t g = g0; g < g1; ++g) { const PdRgConst k = a.rgc[g]; if (cnt[g] >= k.max_load) continue; delLower = len - k.lower_q; delUpper = len + k.upper_q; }
+                for (uint32_t g = g0; g < g1; ++g) {
+                    const PdRgConst k = a.rgc[g];
+                    const uint32_t n = cnt[g];
+                    if (n >= k.max_load) continue;
+                    const PoolEntry * p = e.pool + off[g];
+                    for (uint32_t i = 0; i < n; ++i) {
+                        const int d = p[i].dev;
+                        if (d >= delLower && d <= delUpper) {
+                            const uint32_t first = p[i].pos_rel + e.anchor;
+                            const uint32_t last = first + (uint32_t)max(0, d + k.inner_off);
+                            cF += first <= midF; cL += last <= midL;
+                        }
+                    }
+                }
+            }
+            block_sum2u(cF, cL, sh.redu);
+            if (loF < hiF) { if (cF >= kF + 1) hiF = midF; else loF = midF + 1; }
+            if (loL < hiL) { if (cL >= kL + 1) hiL = midL; else loL = midL + 1; }
+        }
+        sF = loF; sL = loL;
+    }
+    if (sF == 0 && sL == 0) return;
+    const double lr = block_lr(a, sh, dlx, sh.gt);
+    __shared__ uint32_t s_slot;
+    if (tid == 0) {
+        s_slot = 0xFFFFFFFFu;
+        if (lr >= e.min_lr) {
+            const uint32_t slot = atomicAdd(&e.counters[CNT_CALLS], 1u);
+            if (slot < e.out_cap) {
+                s_slot = slot;
+                pd_call c;
+                c.initial_length = L0; c.iterations = sh.it; c.deletion_length = sh.len;
+                c.filter = ((double)ndata / a.N >= e.min_sample_fraction) ? 0u : 4u;
+                c.lr = lr; c.frequency = sh.freq;
+                const uint32_t cur = e.anchor + w * PD_WIN;
+                c.window_position = cur - 1;
+                c.position = e.window_wise ? cur - 1 : sF;
+                c.end_position = e.window_wise ? 0u : sL;
+                c.segment = (uint32_t)(((uint64_t)w * PD_WIN) / a.window_buffer);
+                e.out_calls[slot] = c;
+            }
+        }
+    }
+    __syncthreads();
+    if (s_slot != 0xFFFFFFFFu) {
+        uint32_t * dst = e.out_ps + (size_t)s_slot * 13 * a.N;
+        for (uint32_t i = tid; i < 13 * a.N; i += blockDim.x) dst[i] = ps[i];
+    }
+}
+
+template <typename T>
+int grow_scratch(pd_ctx * c, int slot, T *& p, size_t need)
+{
+    size_t bytes = need * sizeof(T);
+    if (bytes > c->cap_scratch[slot] || !c->d_scratch[slot]) {
+        if (c->d_scratch[slot]) cudaFree(c->d_scratch[slot]);
+        c->d_scratch[slot] = nullptr; c->cap_scratch[slot] = 0;
+        size_t want = std::max<size_t>(bytes + bytes / 4, 4096);
+        PD_CUDA(c, cudaMalloc(&c->d_scratch[slot], want));
+        c->cap_scratch[slot] = want;
+    }
+    p = reinterpret_cast<T *>(c->d_scratch[slot]);
+    return 0;
+}
+
+}  // namespace
+
+int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result * out)
+{
+    PD_CUDA(c, cudaSetDevice(c->device));
+    memset(out, 0, sizeof(*out));
+    const uint64_t total = c->n_windows_total;
+    uint64_t w_begin = std::min<uint64_t>(first_window, total);
+    uint64_t w_end = n_windows ? std::min<uint64_t>(first_window + n_windows, total) : total;
+    c->res_calls.clear(); c->res_ps.clear();
+    out->n_reads = c->n_reads;
+    out->algorithmic_bytes = 4ull * c->n_reads;
+    if (w_end <= w_begin) { out->calls = c->res_calls.data(); out->per_sample = c->res_ps.data(); return 0; }
+    const uint32_t N = c->N, R = c->R;
+    const uint32_t W = (uint32_t)(w_end - w_begin);
+
+    PdDev a;
+    a.words = c->d_words; a.tile_off = c->d_tile_off; a.longs = c->d_longs; a.long_off = c->d_long_off; a.long_span = c->d_long_span;
+    a.rgc = c->d_rgc; a.sample_rg = c->d_sample_rg; a.tab_val = c->d_tab_val; a.tab_ln = c->d_tab_ln; a.tab_l10 = c->d_tab_l10;
+    a.NT = c->NT; a.N = N; a.R = R; a.window_buffer = c->grid.window_buffer; a.t_min = c->t_min;
+    a.w_begin = (uint32_t)w_begin; a.w_end = (uint32_t)w_end;
+
+    uint32_t * d_flags, * d_jobs, * d_counters;
+    if (grow_scratch(c, 0, d_flags, (size_t)W)) return c->status;
+    if (grow_scratch(c, 1, d_jobs, (size_t)W)) return c->status;
+    if (grow_scratch(c, 2, d_counters, (size_t)16)) return c->status;
+    cudaStream_t st = c->stream;
+    PD_CUDA(c, cudaEventRecord(c->ev[2], st));
+    PD_CUDA(c, cudaMemsetAsync(d_flags, 0, (size_t)W * 4, st));
+    PD_CUDA(c, cudaMemsetAsync(d_counters, 0, 16 * 4, st));
+    const uint32_t tile_begin = (uint32_t)(w_begin / PD_TILE_WINDOWS);
+    const uint32_t tile_end = (uint32_t)std::min<uint64_t>((w_end + PD_TILE_WINDOWS - 1) / PD_TILE_WINDOWS, c->NT);
+    PD_CUDA(c, cudaEventRecord(c->ev[3], st));
+    {
+        dim3 grid((tile_end - tile_begin + 7) / 8, N);
+        k_screen<<<grid, 256, 0, st>>>(a, tile_begin, tile_end, d_flags, d_jobs, d_counters);
+        PD_CUDA(c, cudaGetLastError());
+    }
+    PD_CUDA(c, cudaEventRecord(c->ev[4], st));
+    uint32_t h_cnt[16];
+    PD_CUDA(c, cudaMemcpyAsync(h_cnt, d_counters, 16 * 4, cudaMemcpyDeviceToHost, st));
+    PD_CUDA(c, cudaStreamSynchronize(st));
+    const uint32_t n_jobs = h_cnt[CNT_JOBS];
+    out->n_windows = W;
+    out->n_flagged_windows = n_jobs;
+
+    std::vector<uint32_t> h_jobs(n_jobs);
+    if (n_jobs) {
+        PD_CUDA(c, cudaMemcpyAsync(h_jobs.data(), d_jobs, (size_t)n_jobs * 4, cudaMemcpyDeviceToHost, st));
+        PD_CUDA(c, cudaStreamSynchronize(st));
+        std::sort(h_jobs.begin(), h_jobs.end());
+        PD_CUDA(c, cudaMemcpyAsync(d_jobs, h_jobs.data(), (size_t)n_jobs * 4, cudaMemcpyHostToDevice, st));
+    }
+
+    // ---- genotyping stage, in batches of flagged windows
+    const size_t job_bytes = 8ull * R + 5ull * N + 400ull * N;
+    const uint32_t JB = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(3000000000ull / job_bytes, 64), 16384);
+    const size_t pair_bytes = 24ull * N + 4ull * R + 52ull * N + 52ull * N;
+    const uint32_t PB = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(2000000000ull / pair_bytes, 64), 8192);
+    uint32_t npad = 1; while (npad < N) npad <<= 1;
+    if ((size_t)npad * 4 > 200 * 1024) return pd_fail(c, PD_ERR_CAPACITY, "more than 51200 samples per context: candidate sort does not fit shared memory (shard by sample)");
+    if ((size_t)npad * 4 > 48 * 1024)
+        PD_CUDA(c, cudaFuncSetAttribute(k_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(npad * 4)));
+    const uint32_t em_threads = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    uint64_t n_pairs_total = 0;
+    size_t pool_cap = std::max<size_t>((size_t)std::min<uint32_t>(JB, std::max(n_jobs, 1u)) * R * 40, 1u << 20);
+
+    for (uint32_t job0 = 0; job0 < n_jobs; job0 += JB) {
+        const uint32_t nj = std::min(JB, n_jobs - job0);
+        uint32_t * d_act_off, * d_act_cnt; int32_t * d_q3; uint8_t * d_sstat; PoolEntry * d_pool; PdPair * d_pairs;
+        if (grow_scratch(c, 3, d_act_off, (size_t)nj * R)) return c->status;
+        if (grow_scratch(c, 4, d_act_cnt, (size_t)nj * R)) return c->status;
+        if (grow_scratch(c, 5, d_q3, (size_t)nj * N)) return c->status;
+        if (grow_scratch(c, 6, d_sstat, (size_t)nj * N)) return c->status;
+        const uint32_t pair_cap = nj * 8 + 1024;
+        if (grow_scratch(c, 8, d_pairs, (size_t)pair_cap)) return c->status;
+        uint32_t pool_used = 0;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            if (pool_cap > 0xFFFFFFF0ull) pool_cap = 0xFFFFFFF0ull;
+            if (grow_scratch(c, 7, d_pool, pool_cap)) return c->status;
+            PD_CUDA(c, cudaMemsetAsync(d_counters + CNT_PAIRS, 0, 2 * 4, st));      // pairs + pool cursor
+            GatherArgs ga{d_jobs, job0, nj, d_pool, (uint32_t)pool_cap, d_counters, d_act_off, d_act_cnt, d_q3, d_sstat};
+            k_gather<<<dim3(nj, (N + 3) / 4), 128, 0, st>>>(a, ga);
+            PD_CUDA(c, cudaGetLastError());
+            PD_CUDA(c, cudaMemcpyAsync(h_cnt, d_counters, 16 * 4, cudaMemcpyDeviceToHost, st));
+            PD_CUDA(c, cudaStreamSynchronize(st));
+            pool_used = h_cnt[CNT_POOL];
+            if (pool_used <= pool_cap) break;
+            if (attempt == 1) return pd_fail(c, PD_ERR_CAPACITY, "active read-pair pool overflow");
+            pool_cap = (size_t)pool_used + 1024;
+        }
+        k_candidates<<<nj, 256, npad * 4, st>>>(a, d_q3, d_sstat, job0, d_counters, d_pairs, pair_cap, npad);
+        PD_CUDA(c, cudaGetLastError());
+        PD_CUDA(c, cudaMemcpyAsync(h_cnt, d_counters, 16 * 4, cudaMemcpyDeviceToHost, st));
+        PD_CUDA(c, cudaStreamSynchronize(st));
+        const uint32_t n_pairs = h_cnt[CNT_PAIRS];
+        if (n_pairs > pair_cap) return pd_fail(c, PD_ERR_CAPACITY, "more than 8 candidate lengths per flagged window on average");
+        n_pairs_total += n_pairs;
+        for (uint32_t p0 = 0; p0 < n_pairs; p0 += PB) {
+            const uint32_t np = std::min(PB, n_pairs - p0);
+            double * d_dlx; int32_t * d_shifts; uint32_t * d_ps; pd_call * d_out_calls; uint32_t * d_out_ps;
+            if (grow_scratch(c, 9, d_dlx, (size_t)np * 3 * N)) return c->status;
+            if (grow_scratch(c, 10, d_shifts, (size_t)np * R)) return c->status;
+            if (grow_scratch(c, 11, d_ps, (size_t)np * 13 * N)) return c->status;
+            if (grow_scratch(c, 12, d_out_calls, (size_t)np)) return c->status;
+            if (grow_scratch(c, 13, d_out_ps, (size_t)np * 13 * N)) return c->status;
+            PD_CUDA(c, cudaMemsetAsync(d_counters + CNT_CALLS, 0, 4, st));
+            EmArgs e;
+            e.jobs = d_jobs; e.pairs = d_pairs; e.pair0 = p0; e.npairs = np; e.job_base = job0;
+            e.pool = d_pool; e.act_off = d_act_off; e.act_cnt = d_act_cnt; e.sstat = d_sstat;
+            e.dlx = d_dlx; e.shifts = d_shifts; e.ps = d_ps; e.counters = d_counters;
+            e.out_calls = d_out_calls; e.out_ps = d_out_ps; e.out_cap = np;
+            e.iterations = c->params.iterations; e.min_len = c->params.min_len; e.min_lr = c->params.min_lr;
+            e.min_sample_fraction = c->params.min_sample_fraction; e.somatic = c->params.somatic; e.window_wise = c->params.window_wise;
+            e.anchor = c->grid.anchor;
+            k_em<<<np, em_threads, 0, st>>>(a, e);
+            PD_CUDA(c, cudaGetLastError());
+            PD_CUDA(c, cudaMemcpyAsync(h_cnt, d_counters, 16 * 4, cudaMemcpyDeviceToHost, st));
+            PD_CUDA(c, cudaStreamSynchronize(st));
+            const uint32_t nc = h_cnt[CNT_CALLS];
+            if (nc) {
+                size_t o = c->res_calls.size();
+                c->res_calls.resize(o + nc);
+                c->res_ps.resize((o + nc) * 13ull * N);
+                PD_CUDA(c, cudaMemcpyAsync(c->res_calls.data() + o, d_out_calls, (size_t)nc * sizeof(pd_call), cudaMemcpyDeviceToHost, st));
+                PD_CUDA(c, cudaMemcpyAsync(c->res_ps.data() + o * 13ull * N, d_out_ps, (size_t)nc * 13 * N * 4, cudaMemcpyDeviceToHost, st));
+                PD_CUDA(c, cudaStreamSynchronize(st));
+            }
+        }
+    }
+    PD_CUDA(c, cudaEventRecord(c->ev[5], st));
+    PD_CUDA(c, cudaStreamSynchronize(st));
+    // order: (window, initial length) = the reference's emission order
+    {
+        const size_t nc = c->res_calls.size();
+        std::vector<uint32_t> idx(nc);
+        std::iota(idx.begin(), idx.end(), 0u);
+        std::sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) {
+            const pd_call & p = c->res_calls[x], & q = c->res_calls[y];
+            if (p.window_position != q.window_position) return p.window_position < q.window_position;
+            return p.initial_length < q.initial_length;
+        });
+        std::vector<pd_call> sc(nc);
+        std::vector<uint32_t> sp(nc * 13ull * N);
+        for (size_t i = 0; i < nc; ++i) {
+            sc[i] = c->res_calls[idx[i]];
+            memcpy(&sp[i * 13ull * N], &c->res_ps[(size_t)idx[i] * 13ull * N], 13ull * N * 4);
+        }
+        c->res_calls.swap(sc); c->res_ps.swap(sp);
+    }
+    out->n_calls = c->res_calls.size();
+    out->calls = c->res_calls.data();
+    out->per_sample = c->res_ps.data();
+    out->n_candidates = n_pairs_total;
+    PD_CUDA(c, cudaEventElapsedTime(&out->ms_screen, c->ev[3], c->ev[4]));
+    PD_CUDA(c, cudaEventElapsedTime(&out->ms_genotype, c->ev[4], c->ev[5]));
+    PD_CUDA(c, cudaEventElapsedTime(&out->ms_total, c->ev[2], c->ev[5]));
+    out->ms_d2h = 0;
+    return 0;
+}

@@ -60,8 +60,10 @@ class Oracle:
             raise RuntimeError(f"orc_call_files failed ({rc})")
         return nw.value
 
-    def scan_contig(self, params, rgs, rg_off, pos, dev, n_samples, max_calls=100000):
-        """params: dict; rgs: list of dicts (with 'values' ndarray). Returns (calls ndarray, per_sample, n_windows)."""
+    def scan_contig(self, params, rgs, rg_off, pos, dev, n_samples, max_calls=100000, window_sums=False, max_windows=0):
+        """params: dict; rgs: list of dicts (with 'values' ndarray). Returns (calls ndarray, per_sample, n_windows)
+        or, with window_sums=True, additionally an int64 array [n_windows, 1 + R, 3] of per-window
+        {pos, ncalls, 0} and per read group {active count, sum dev, sum pos}."""
         p = OrcParams(**params)
         keep = []
         arr = (OrcRg * len(rgs))()
@@ -77,10 +79,15 @@ class Oracle:
         calls = (OrcCall * max_calls)()
         per = np.zeros(13 * n_samples * max_calls, dtype=np.uint32)
         nw = C.c_int64(0)
+        wd, wcap = None, 0
+        if window_sums:
+            wcap = int(max_windows) * (1 + len(rgs))
+            wbuf = np.zeros(3 * wcap, dtype=np.int64)
+            wd = wbuf.ctypes.data_as(C.POINTER(C.c_int64))
         n = self.lib.orc_scan_contig(C.byref(p), n_samples, len(rgs), arr, rg_off.ctypes.data_as(C.POINTER(C.c_uint64)),
                                      pos.ctypes.data_as(C.POINTER(C.c_uint32)), dev.ctypes.data_as(C.POINTER(C.c_int32)),
                                      0, 0xFFFFFFFF, calls, per.ctypes.data_as(C.POINTER(C.c_uint32)), max_calls,
-                                     None, 0, C.byref(nw))
+                                     wd, wcap, C.byref(nw))
         if n < 0:
             raise RuntimeError("call buffer too small")
         dt = np.dtype([("initial_length", "u4"), ("iterations", "u4"), ("deletion_length", "u4"), ("_pad", "u4"),
@@ -88,7 +95,10 @@ class Oracle:
                        ("end_position", "u4"), ("filter", "u4"), ("segment", "u4"), ("_pad2", "u4")])
         assert dt.itemsize == C.sizeof(OrcCall), (dt.itemsize, C.sizeof(OrcCall))
         out = np.frombuffer(calls, dtype=dt, count=n).copy()
-        return out, per[:13 * n_samples * n].reshape(n, n_samples, 13).copy(), nw.value
+        ps = per[:13 * n_samples * n].reshape(n, n_samples, 13).copy()
+        if window_sums:
+            return out, ps, nw.value, wbuf[:3 * nw.value * (1 + len(rgs))].reshape(nw.value, 1 + len(rgs), 3).copy()
+        return out, ps, nw.value
 
 
 def load(so):

@@ -1,0 +1,97 @@
+"""CPU-only tests of the product's host logic: the C ABI loads and exports what include/popdel_b200.h declares,
+histogram preprocessing equals the oracle, and the packed tile layout + closed-form activity rule reproduce the
+oracle's (= the reference's) per-window active sets. No scan is run here: the scan has no CPU path."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from popdel_b200 import api, simulate
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = api.load_library()
+    header = open(os.path.join(ROOT, "include", "popdel_b200.h")).read()
+    declared = set(re.findall(r"\b(pd_[a-z_]+)\s*\(", header)) - {"pd_ctx"}
+    assert declared == set(api.EXPORTS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_process_histogram_equals_oracle(oracle_lib):
+    rng = np.random.default_rng(3)
+    for mu, sd, rl in [(500, 50, 150), (350, 30, 100), (550, 80, 150), (300, 100, 125)]:
+        isz = np.rint(rng.normal(mu, sd, size=200000)).astype(np.int64)
+        med = int(np.median(isz))
+        lo, hi = max(1, int(np.floor(med - 3 * sd))), int(np.ceil(med + 3 * sd)) + 1
+        counts = np.bincount(isz[(isz >= lo) & (isz < hi)] - lo, minlength=hi - lo).astype(np.float64)
+        for smoothing in (True, False):
+            a = api.process_histogram(counts, lo, med, rl, smoothing, 500)
+            b = oracle_lib.process_histogram(counts, lo, med, rl, smoothing, 500)
+            assert np.array_equal(a[0], b[0]) and a[1:] == b[1:]
+
+
+def _cohort(kind):
+    if kind == "basic":
+        return simulate.simulate_cohort(seed=21, n_samples=3, contig_len=430_000, n_dels=2)[0], api.CallParameters()
+    if kind == "mixedrg":
+        specs = simulate.mixed_rg_specs(4, 4)
+        return simulate.simulate_cohort(seed=22, n_samples=4, contig_len=260_000, n_dels=2, rg_specs=specs)[0], api.CallParameters()
+    if kind == "gap":
+        samples, _ = simulate.simulate_cohort(seed=23, n_samples=3, contig_len=800_000, n_dels=1)
+        for k, s in enumerate(samples):
+            for rg in s.read_groups:
+                keep = ~((rg.pos >= 150_000) & (rg.pos < 610_000))
+                if k == 0:
+                    keep &= ~((rg.pos >= 20_000) & (rg.pos < 60_000))
+                rg.pos, rg.isize = rg.pos[keep], rg.isize[keep]
+        return samples, api.CallParameters()
+    if kind == "highcov":
+        samples, _ = simulate.simulate_cohort(seed=24, n_samples=2, contig_len=230_000, n_dels=1)
+        spec = simulate.ReadGroupSpec(name="burst", coverage=400.0)
+        extra, _ = simulate.simulate_cohort(seed=25, n_samples=1, contig_len=230_000, n_dels=0, rg_specs=[[spec]])
+        e = extra[0].read_groups[0]
+        m = (e.pos >= 90_000) & (e.pos < 120_000)
+        rg = samples[0].read_groups[0]
+        p, i = np.concatenate([rg.pos, e.pos[m]]), np.concatenate([rg.isize, e.isize[m]])
+        o = np.lexsort((i, p))
+        rg.pos, rg.isize = p[o], i[o]
+        return samples, api.CallParameters()
+    if kind == "longspan":
+        # a large deletion (long read pairs in the wide list) crossing a segment border
+        dels = [simulate.Deletion(196_000, 9000, np.array([1, 2, 1]))]
+        return simulate.simulate_cohort(seed=26, n_samples=3, contig_len=260_000, n_dels=0, dels=dels)[0], api.CallParameters()
+    raise KeyError(kind)
+
+
+@pytest.mark.parametrize("kind", ["basic", "mixedrg", "gap", "highcov", "longspan"])
+def test_packed_layout_reproduces_active_sets(kind, oracle_lib):
+    from parity import run_oracle
+    samples, params = _cohort(kind)
+    headers = [[dict(name=rg.spec.name, median=rg.median, stddev=rg.stddev, read_length=rg.spec.read_length,
+                     hist_start=rg.hist_start, hist_end=rg.hist_end, hist_counts=rg.hist_counts)
+                for rg in s.read_groups] for s in samples]
+    rgs = api.read_groups_from_headers(headers, params)
+    sc = api.Scanner(params, rgs, len(samples), device=-1)        # host-only context
+    anchor = api.cohort_anchor(samples)
+    sc.begin_contig(anchor)
+    g = 0
+    for s in samples:
+        for rg in s.read_groups:
+            sc.push(g, rg.pos, rg.dev)
+            g += 1
+    n_windows = sc.window_count()
+    _, _, n_ref, wins = run_oracle(samples, params, rgs, oracle_lib, window_sums=True, max_windows=n_windows + 10)
+    assert n_windows == n_ref
+    assert np.array_equal(wins[:, 0, 0], anchor + 30 * np.arange(n_ref))       # contiguous grid from the anchor
+    for g in range(len(rgs)):
+        got = sc.debug_host_window_sums(g, 0, n_windows)
+        ref = wins[:, 1 + g, :]
+        bad = np.nonzero((got != ref).any(axis=1))[0]
+        assert bad.size == 0, f"rg {g}: first mismatch at window {bad[0]} (pos {anchor + 30 * bad[0]}): {got[bad[0]]} vs {ref[bad[0]]}"
+    with pytest.raises(api.ScanError):
+        sc.scan()                                                              # no CPU scan path
+    sc.close()

@@ -1,0 +1,63 @@
+"""GPU parity tests: the CUDA scan, called through the C ABI, against the CPU oracle on the same seeded cohorts.
+Integer outputs (window positions, candidate and final lengths, iterations, PL/LAD/DAD/FL, filters, segments)
+must be bit-exact; LR and allele frequency within 1e-6 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from popdel_b200 import api, simulate
+from parity import assert_calls_equal, compare_scan_with_oracle, run_oracle
+from test_host_logic import _cohort
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("kind", ["basic", "mixedrg", "gap", "highcov", "longspan"])
+def test_scan_matches_oracle(kind, oracle_lib):
+    samples, params = _cohort(kind)
+    stats = compare_scan_with_oracle(samples, oracle_lib, params)
+    assert stats["n_calls"] > 0
+    assert stats["n_flagged"] < stats["n_windows"] // 4        # the screen prunes the bulk of the windows
+
+
+def test_scan_window_wise_and_user_thresholds(oracle_lib):
+    samples, _ = simulate.simulate_cohort(seed=31, n_samples=5, contig_len=240_000, n_dels=2)
+    params = api.CallParameters(window_wise=True, min_init_len=150, min_len=120)
+    stats = compare_scan_with_oracle(samples, oracle_lib, params)
+    assert stats["n_calls"] > 0
+
+
+def test_scan_somatic_and_iterations(oracle_lib):
+    samples, _ = simulate.simulate_cohort(seed=32, n_samples=4, contig_len=210_000, n_dels=2)
+    params = api.CallParameters(somatic=True, iterations=4)
+    compare_scan_with_oracle(samples, oracle_lib, params)
+
+
+def test_scan_no_deletions_and_empty_sample(oracle_lib):
+    samples, _ = simulate.simulate_cohort(seed=33, n_samples=3, contig_len=120_000, n_dels=0)
+    rg = samples[2].read_groups[0]
+    rg.pos, rg.isize = rg.pos[:0], rg.isize[:0]                 # a sample without any read pair
+    stats = compare_scan_with_oracle(samples, oracle_lib)
+    assert stats["n_calls"] == 0
+
+
+def test_scan_window_ranges_partition_the_contig(oracle_lib):
+    """Window-range sharding: scanning disjoint ranges yields exactly the calls of the full scan."""
+    samples, _ = simulate.simulate_cohort(seed=34, n_samples=4, contig_len=450_000, n_dels=4)
+    params = api.CallParameters()
+    full, rgs = api.scan_cohort(samples, params)
+    n = full["n_windows"]
+    cuts = [0, 6667, 9000, n]
+    parts = [api.scan_cohort(samples, params, first_window=a, n_windows=b - a)[0] for a, b in zip(cuts[:-1], cuts[1:])]
+    calls = np.concatenate([p["calls"] for p in parts])
+    ps = np.concatenate([p["per_sample"] for p in parts])
+    assert sum(p["n_windows"] for p in parts) == n
+    assert_calls_equal(calls, ps, full["calls"], full["per_sample"], rtol=0)
+    ref_calls, ref_ps, _ = run_oracle(samples, params, rgs, oracle_lib)
+    assert_calls_equal(full["calls"], full["per_sample"], ref_calls, ref_ps)
+
+
+def test_larger_cohort(oracle_lib):
+    """40 samples x 300 kbp: more samples than one warp, several candidates per window."""
+    samples, _ = simulate.simulate_cohort(seed=35, n_samples=40, contig_len=300_000, n_dels=4)
+    stats = compare_scan_with_oracle(samples, oracle_lib)
+    assert stats["n_calls"] > 100
