@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- `popdel call` window scan throughput (sample x window genotype evaluations per second).
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): 100 synthetic profiles, chr21 (46,709,983 bp -> 1.56e6 windows of 30 bp), one
+read group each (30x, 2x150 bp, insert ~ N(500, 50^2)), planted deletions; per GPU one such window range (weak
+scaling over contiguous window ranges, no data-path collective). A step = one pass of the scan over the range.
+  value : evaluations/s with the packed read pairs already resident in HBM (all kernels + result copy-back)
+  e2e   : evaluations/s through the C ABI from host arrays: push (pack into pinned memory) + H2D + scan + D2H
+  roofline : k_screen, algorithmic bytes = 4 B per resident read pair, CUDA-event duration
+  cpu_baseline : the CPU oracle port (1 core) on a bounded slice of the same cohort
+The reference arm times the reference's own `popdel call` (oracle/_ref/popdel_ref, built from /root/reference by
+oracle/Makefile) on profile files of a bounded slice of the same workload, one process per host core over contiguous
+regions (-r), like BASELINE.md section 3.
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CHR21_LEN = 46_709_983
+METRIC = "sample x window genotype evaluations per second (popdel call window scan)"
+UNIT = "evals/s"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# synthetic cohort (host arrays)
+# ----------------------------------------------------------------------------------------------------------------
+def plant(seed, n_samples, length, per_mbp):
+    rng = np.random.default_rng([seed, 911])
+    n = max(1, int(round(length / 1e6 * per_mbp)))
+    slot = (length - 40_000) // n
+    starts, lens, gts = [], [], []
+    for k in range(n):
+        L = int(np.exp(rng.uniform(np.log(300), np.log(10000))))
+        s = 20_000 + k * slot + int(rng.integers(0, max(1, slot - L - 2000)))
+        af = float(rng.choice([0.1, 0.3, 0.5]))
+        g = rng.binomial(2, af, size=n_samples).astype(np.uint8)
+        if g.sum() == 0:
+            g[int(rng.integers(0, n_samples))] = 1
+        starts.append(s), lens.append(L), gts.append(g)
+    return np.array(starts, np.uint32), np.array(lens, np.uint32), np.stack(gts)
+
+
+def make_cohort(seed, n_samples, length, per_mbp, threads):
+    from popdel_b200 import api
+    ds, dl, gt = plant(seed, n_samples, length, per_mbp)
+
+    def one(s):
+        pos, isz = api.synth_read_group(seed, s, 500.0, 50.0, 150, 0.1, 0, length, ds, dl, gt[:, s])
+        med = 500
+        lo, hi = max(1, int(np.floor(med - 150))), int(np.ceil(med + 150)) + 1
+        sel = isz[(isz >= lo) & (isz < hi)]
+        counts = np.bincount(sel - lo, minlength=hi - lo).astype(np.float64)
+        hdr = dict(name=f"rg{s}", median=med, stddev=50.0, read_length=150, hist_start=lo, hist_end=hi, hist_counts=counts)
+        dev = isz - np.int32(med)
+        return pos, isz, dev, hdr
+
+    with ThreadPoolExecutor(threads) as ex:
+        out = list(ex.map(one, range(n_samples)))
+    return out, (ds, dl, gt)
+
+
+class ClockSampler:
+    def __init__(self, dev):
+        self.dev, self.proc, self.lines = dev, None, []
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            t = [x.strip() for x in ln.split(",")]
+            if len(t) < 6:
+                continue
+            try:
+                sm.append(float(t[0])), (mx := float(t[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, t[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons))
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from popdel_b200 import api
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    threads = max(1, (os.cpu_count() or 8) // max(world, 1))
+    N, L = args.samples, args.length
+    t0 = time.time()
+    cohort, dels = make_cohort(args.seed + rank, N, L, args.dels_per_mbp, threads)     # rank r = window range r
+    t_gen = time.time() - t0
+    params = api.CallParameters()
+    rgs = api.read_groups_from_headers([[c[3]] for c in cohort], params)
+    sc = api.Scanner(params, rgs, N, device=local_rank)
+    anchor = (min(int(c[0][0]) for c in cohort) // 30) * 30
+
+    def push_all():
+        sc.begin_contig(anchor)
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(lambda s: sc.push(s, cohort[s][0], cohort[s][2]), range(N)))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-input throughput
+    push_all()
+    sc.upload()
+    res = sc.scan()
+    evals = int(res["n_windows"]) * N
+    for _ in range(args.warmup):
+        res = sc.scan()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    barrier()
+    t0 = time.perf_counter()
+    ms_screen, ms_dev, launches = [], [], 0
+    for _ in range(args.steps):
+        res = sc.scan()
+        ms_screen.append(res["ms_screen"]), ms_dev.append(res["ms_total"])
+        launches += int(res["n_kernel_launches"])
+    barrier()
+    dt = time.perf_counter() - t0
+    clk = clocks.stop()
+    if dist is not None:
+        tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        ev = torch.tensor([evals], device="cuda", dtype=torch.float64)
+        dist.all_reduce(ev, op=dist.ReduceOp.SUM)
+        evals_all = float(ev.item())
+    else:
+        evals_all = float(evals)
+    value = evals_all * args.steps / dt
+
+    # ---- end to end through the C ABI from host arrays (pack -> pinned -> H2D -> scan -> D2H)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    push_all()
+    r2 = sc.scan()                                                  # warm-up (pinned buffers exist afterwards)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        push_all()
+        r2 = sc.scan()
+    barrier()
+    dt2 = time.perf_counter() - t0
+    if dist is not None:
+        tt = torch.tensor([dt2], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt2 = float(tt.item())
+    e2e = evals_all * e2e_steps / dt2
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak_gbs()
+    ms_s = float(np.mean(ms_screen))
+    achieved = res["algorithmic_bytes"] / (ms_s * 1e-3) / 1e9
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32 (screen) / f64 (likelihoods)", "data": "synthetic",
+        "config": {"workload": f"{N} synthetic profiles x chr21-sized window range ({L} bp, {res['n_windows']} windows of 30 bp) "
+                               f"per GPU, single read group each, 30x, planted deletions {args.dels_per_mbp}/Mbp",
+                   "samples": N, "windows_per_gpu": int(res["n_windows"]), "read_pairs_per_gpu": int(res["n_reads"]),
+                   "parallelism": f"window-range x{world}", "l2": "inputs (%.2f GB packed words) larger than the 126 MB L2" % (res["algorithmic_bytes"] / 1e9),
+                   "calls_per_step": int(len(res["calls"])), "flagged_windows": int(res["n_flagged_windows"]),
+                   "candidates": int(res["n_candidates"])},
+        "clocks": clk,
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(r2["h2d_bytes"]), "d2h_bytes_per_step": int(r2["d2h_bytes"]),
+                "steps": e2e_steps, "ms_per_step": dt2 / e2e_steps * 1e3},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "k_screen", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "bytes_per_eval": res["algorithmic_bytes"] / evals,
+                     "ms_kernel": ms_s, "ms_device_per_step": float(np.mean(ms_dev)),
+                     "frac_at_survey_20B_per_eval": evals * 20 / (ms_s * 1e-3) / 1e9 / peak},
+        "setup_s": {"generate": t_gen},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, cohort, params, rgs)
+    print(json.dumps(out), flush=True)
+
+
+def cpu_baseline(args, cohort, params, rgs):
+    """The CPU oracle (restatement of the reference, 1 core) on the first `slice` bp of the same cohort."""
+    import oracle_api
+    so = os.path.join(ROOT, "oracle", "liboracle.so")
+    if not os.path.exists(so):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, stdout=subprocess.DEVNULL)
+    orc = oracle_api.load(so)
+    N = len(cohort)
+    slice_bp = int(args.cpu_slice)
+    pos, dev, off = [], [], [0]
+    for c in cohort:
+        n = int(np.searchsorted(c[0], slice_bp))
+        pos.append(c[0][:n]), dev.append(c[2][:n]), off.append(off[-1] + n)
+    t0 = time.perf_counter()
+    calls, _, nwin = orc.scan_contig(params.as_dict(), [r.as_dict() for r in rgs], np.array(off, np.uint64),
+                                     np.concatenate(pos), np.concatenate(dev), N, max_calls=200000)
+    dt = time.perf_counter() - t0
+    return {"value": nwin * N / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"first {slice_bp} bp of the same cohort: {nwin} windows x {N} samples in {dt:.1f} s ({len(calls)} window calls)"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from popdel_b200 import profile_format as pf
+    binary = os.path.join(ROOT, "oracle", "_ref", "popdel_ref")
+    cores = os.cpu_count() or 1
+    N = args.samples
+    slice_bp = int(min(args.ref_slice_per_core * cores, args.length, 24_000_000))
+    cohort, _ = make_cohort(args.seed, N, slice_bp, args.dels_per_mbp, cores)
+    tmp = tempfile.mkdtemp(prefix="popdel_ref_bench_")
+    try:
+        contigs = [("chr21", CHR21_LEN)]
+
+        def write(s):
+            p = os.path.join(tmp, f"s{s:05d}.profile")
+            pf.write_profile_single_rg(p, cohort[s][3], contigs, 0, cohort[s][0], cohort[s][1], compressed=True)
+            return p
+
+        with ThreadPoolExecutor(cores) as ex:
+            paths = list(ex.map(write, range(N)))
+        lst = os.path.join(tmp, "profiles.txt")
+        open(lst, "w").write("\n".join(paths) + "\n")
+        kind = "reference"
+        if not os.path.exists(binary):
+            kind = "port"
+        regions = np.linspace(0, slice_bp, cores + 1).astype(int)
+
+        def step():
+            t0 = time.perf_counter()
+            if kind == "reference":
+                procs = [subprocess.Popen([binary, "call", lst, "-r", f"chr21:{regions[i] + 1}-{regions[i + 1]}", "-o",
+                                           os.path.join(tmp, f"out{i}.vcf")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                         for i in range(cores)]
+                rc = [p.wait() for p in procs]
+                assert all(r == 0 for r in rc), rc
+            else:
+                import oracle_api
+                orc = oracle_api.load(os.path.join(ROOT, "oracle", "liboracle.so"))
+                orc.call_files(paths, os.path.join(tmp, "dump.txt"))
+            return time.perf_counter() - t0
+
+        for _ in range(min(args.warmup, 1)):
+            step()
+        times = [step() for _ in range(args.steps)]
+        dt = float(np.sum(times))
+        evals = N * (slice_bp // 30)
+        value = evals * args.steps / dt
+        used = cores if kind == "reference" else 1
+        out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "long double (x87)", "data": "synthetic",
+               "config": {"workload": f"{N} synthetic profiles x chr21, bounded sample: first {slice_bp} bp "
+                                      f"({slice_bp // 30} windows), gzip profile files on local disk", "samples": N},
+               "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind,
+                                "sample": f"{N} samples x first {slice_bp} bp, {used} processes over contiguous -r regions"},
+               "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(out), flush=True)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--samples", type=int, default=100)
+    ap.add_argument("--length", type=int, default=CHR21_LEN)
+    ap.add_argument("--dels-per-mbp", type=float, default=2.0)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-slice", type=int, default=1_500_000)
+    ap.add_argument("--ref-slice-per-core", type=int, default=300_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -78,6 +78,8 @@ typedef struct {
     uint64_t n_candidates;         /* (window, initial length) pairs run through the EM */
     uint64_t n_reads;              /* read pairs resident on the device for this contig */
     uint64_t algorithmic_bytes;    /* bytes the screen kernel must move: 4 per resident read-pair word */
+    uint64_t h2d_bytes, d2h_bytes; /* bytes copied host->device for this contig / device->host for this scan */
+    uint64_t n_kernel_launches;    /* kernels of this library launched by this scan */
     float    ms_h2d, ms_screen, ms_genotype, ms_d2h, ms_total;   /* CUDA-event times on the library's stream */
 } pd_result;
 
@@ -113,12 +115,16 @@ int pd_contig_scan(pd_ctx * ctx, uint64_t first_window, uint64_t n_windows, pd_r
 /* Number of grid windows the reference would scan for the pushed contig (last scanned window index + 1). */
 int pd_contig_window_count(pd_ctx * ctx, uint64_t * n_windows);
 
-/* Synthetic cohort generated ON THE DEVICE directly in the packed layout (cfg3-5 cannot be
- * materialised on the host): per read group Poisson(density*30) read pairs per 30-bp bucket, insert size
- * round(N(median, stddev^2)); `n_dels` planted deletions with per-sample genotypes. Replaces push+upload. */
-int pd_contig_synthesize(pd_ctx * ctx, uint64_t seed, uint64_t n_windows, double pairs_per_bp,
-                         uint32_t n_dels, const uint32_t * del_start, const uint32_t * del_len,
-                         const uint8_t * del_genotypes /* n_dels x n_samples, 0/1/2 */);
+/* Synthetic read pairs of ONE read group, generated on the host with a counter-based RNG: per 30-bp
+ * bucket and haplotype Poisson(pairs_per_bp*30/2) read pairs, insert size round(N(mu, sigma^2)) clipped to
+ * (2*read_length, 20000); planted deletions are applied per haplotype (genotype 0/1/2): pairs whose forward read lies
+ * in the deleted segment do not exist, pairs spanning the breakpoint get isize += length. Output sorted by
+ * (pos, isize) like a profile. Returns the number of read pairs written (<= capacity) or a negative pd_status.
+ * Thread-safe (no context); used by bench.py and the tests to build cohorts of BASELINE.json's sizes quickly. */
+int64_t pd_synth_read_group(uint64_t seed, uint32_t rg_index, double mu, double sigma, uint32_t read_length,
+                            double pairs_per_bp, uint32_t first_pos, uint32_t end_pos,
+                            uint32_t n_dels, const uint32_t * del_start, const uint32_t * del_len,
+                            const uint8_t * del_genotype, uint32_t * pos, int32_t * isize, uint64_t capacity);
 
 /* Host-side validation hook for the packed layout (NOT used by the scan): per-window active read-pair count,
  * sum of deviations and sum of positions of read group `rg`, computed from the packed words with the same

@@ -40,6 +40,7 @@ class PdResult(C.Structure):
     _fields_ = [("n_calls", C.c_uint64), ("calls", C.c_void_p), ("per_sample", C.POINTER(C.c_uint32)),
                 ("n_windows", C.c_uint64), ("n_flagged_windows", C.c_uint64), ("n_candidates", C.c_uint64),
                 ("n_reads", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_kernel_launches", C.c_uint64),
                 ("ms_h2d", C.c_float), ("ms_screen", C.c_float), ("ms_genotype", C.c_float), ("ms_d2h", C.c_float),
                 ("ms_total", C.c_float)]
 
@@ -49,7 +50,7 @@ CALL_DTYPE = np.dtype([("initial_length", "<u4"), ("iterations", "<u4"), ("delet
                        ("end_position", "<u4"), ("segment", "<u4")])
 
 EXPORTS = ["pd_process_histogram", "pd_create", "pd_create_error", "pd_destroy", "pd_last_error", "pd_contig_begin",
-           "pd_contig_push", "pd_contig_upload", "pd_contig_scan", "pd_contig_window_count", "pd_contig_synthesize",
+           "pd_contig_push", "pd_contig_upload", "pd_contig_scan", "pd_contig_window_count", "pd_synth_read_group",
            "pd_debug_host_window_sums"]
 
 _lib = None
@@ -78,8 +79,11 @@ def load_library(path: str = LIB_PATH):
     lib.pd_contig_upload.argtypes = [C.c_void_p]
     lib.pd_contig_scan.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(PdResult)]
     lib.pd_contig_window_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
-    lib.pd_contig_synthesize.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_double, C.c_uint32,
-                                         C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)]
+    lib.pd_synth_read_group.restype = C.c_int64
+    lib.pd_synth_read_group.argtypes = [C.c_uint64, C.c_uint32, C.c_double, C.c_double, C.c_uint32, C.c_double,
+                                        C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32),
+                                        C.POINTER(C.c_uint32), C.POINTER(C.c_uint8), C.POINTER(C.c_uint32),
+                                        C.POINTER(C.c_int32), C.c_uint64]
     lib.pd_debug_host_window_sums.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(C.c_int64)]
     _lib = lib
     return lib
@@ -228,22 +232,34 @@ class Scanner:
             C.memmove(per.ctypes.data, res.per_sample, per.nbytes)
         return dict(calls=calls, per_sample=per, n_windows=res.n_windows, n_flagged_windows=res.n_flagged_windows,
                     n_candidates=res.n_candidates, n_reads=res.n_reads, algorithmic_bytes=res.algorithmic_bytes,
+                    h2d_bytes=res.h2d_bytes, d2h_bytes=res.d2h_bytes, n_kernel_launches=res.n_kernel_launches,
                     ms_h2d=res.ms_h2d, ms_screen=res.ms_screen, ms_genotype=res.ms_genotype, ms_total=res.ms_total)
-
-    def synthesize(self, seed: int, n_windows: int, pairs_per_bp: float, del_start=(), del_len=(), genotypes=None):
-        ds = np.ascontiguousarray(del_start, dtype=np.uint32)
-        dl = np.ascontiguousarray(del_len, dtype=np.uint32)
-        gt = np.ascontiguousarray(genotypes if genotypes is not None else np.zeros((0, self.n_samples)), dtype=np.uint8)
-        self._check(self.lib.pd_contig_synthesize(self.ctx, int(seed), int(n_windows), float(pairs_per_bp), ds.size,
-                                                  ds.ctypes.data_as(C.POINTER(C.c_uint32)),
-                                                  dl.ctypes.data_as(C.POINTER(C.c_uint32)),
-                                                  gt.ctypes.data_as(C.POINTER(C.c_uint8))))
 
     def debug_host_window_sums(self, rg: int, first_window: int, n_windows: int) -> np.ndarray:
         out = np.zeros((int(n_windows), 3), dtype=np.int64)
         self._check(self.lib.pd_debug_host_window_sums(self.ctx, int(rg), int(first_window), int(n_windows),
                                                        out.ctypes.data_as(C.POINTER(C.c_int64))))
         return out
+
+
+def synth_read_group(seed: int, rg_index: int, mu: float, sigma: float, read_length: int, pairs_per_bp: float,
+                     first_pos: int, end_pos: int, del_start=(), del_len=(), del_genotype=()):
+    """pd_synth_read_group: returns (pos uint32, isize int32), sorted by (pos, isize). Releases the GIL."""
+    lib = load_library()
+    ds = np.ascontiguousarray(del_start, dtype=np.uint32)
+    dl = np.ascontiguousarray(del_len, dtype=np.uint32)
+    dg = np.ascontiguousarray(del_genotype, dtype=np.uint8)
+    span = int(end_pos) - int(first_pos)
+    cap = int(span * pairs_per_bp * 1.05) + 100000
+    pos = np.empty(cap, dtype=np.uint32)
+    isz = np.empty(cap, dtype=np.int32)
+    n = lib.pd_synth_read_group(int(seed), int(rg_index), float(mu), float(sigma), int(read_length), float(pairs_per_bp),
+                                int(first_pos), int(end_pos), ds.size, ds.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                dl.ctypes.data_as(C.POINTER(C.c_uint32)), dg.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                pos.ctypes.data_as(C.POINTER(C.c_uint32)), isz.ctypes.data_as(C.POINTER(C.c_int32)), cap)
+    if n < 0:
+        raise ScanError(f"pd_synth_read_group failed ({n})")
+    return pos[:n], isz[:n]
 
 
 def cohort_anchor(samples) -> int:

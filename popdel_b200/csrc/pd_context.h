@@ -31,14 +31,22 @@ struct PdDev {
     uint32_t w_begin, w_end;         // windows to scan [w_begin, w_end)
 };
 
-struct PdHostRg {                    // host staging of one read group of the current contig
-    std::vector<uint32_t> pos_rel;   // after the active-coverage cap
-    std::vector<int32_t> dev;
+struct PdHostRg {                    // host staging of one read group of the current contig (filled by pd_contig_push)
+    uint32_t * words = nullptr;      // packed stream (pinned when the context has a device); tiles padded to 4 words
+    size_t n_words = 0, cap_words = 0;
+    std::vector<uint32_t> tile_rel;  // tile_rel[t] = first word of tile t (relative to this read group), size = tiles seen + 1
+    std::vector<PdLong> longs;
+    uint32_t long_span = 0;
+    uint32_t cur_tile = 0;           // tile being appended
+    uint64_t n_reads = 0, dropped = 0;
     // active-coverage cap state (ChromosomeProfile::add, profile_structure :1084-1113)
     std::vector<uint32_t> open_lw;   // min-heap of last-window indices of read pairs still open
-    uint64_t dropped = 0;
     uint32_t last_pos = 0;
     bool any = false;
+    // bookkeeping for the reference's last scanned window: per segment (current, previous)
+    int64_t seg = -1;                // segment of the most recent read pair
+    int64_t S = -1, E_own = -1, E_spill = -1;         // current segment: max pos, max lw <= wl(seg), max lw > wl(seg)
+    int64_t prev_seg = -1, prev_E_spill = -1;         // previous non-empty segment
 };
 
 struct pd_ctx {
@@ -57,9 +65,10 @@ struct pd_ctx {
     bool contig_open = false, packed = false, uploaded = false;
     PdGrid grid{0, 200000};
     std::vector<PdHostRg> hrg;
-    // packed host image
-    std::vector<uint32_t> h_words, h_tile_off, h_long_off, h_long_span;
-    std::vector<PdLong> h_longs;
+    // packed host image (offset tables; the words stay in the per-read-group staging vectors)
+    std::vector<uint32_t> h_tile_off, h_long_off, h_long_span;
+    std::vector<uint64_t> h_word_base;   // first word of each read group in the device stream
+    uint64_t total_words = 0, total_longs = 0;
     uint32_t NT = 0;
     uint64_t n_windows_total = 0;    // reference's last scanned window + 1
     uint64_t n_reads = 0;
@@ -74,17 +83,17 @@ struct pd_ctx {
     PdRgConst * d_rgc = nullptr;
     uint32_t * d_sample_rg = nullptr;
     double * d_tab_val = nullptr, * d_tab_ln = nullptr, * d_tab_l10 = nullptr;
-    uint32_t * h_pin_words = nullptr; size_t cap_pin_words = 0;   // pinned staging
     // scan scratch (grown on demand)
     void * d_scratch[16] = {}; size_t cap_scratch[16] = {};
     // results (pinned)
     std::vector<pd_call> res_calls;
     std::vector<uint32_t> res_ps;
     float ms_h2d = 0;
+    uint64_t h2d_bytes = 0;
 };
 
 int pd_fail(pd_ctx * c, int status, const std::string & msg);
-int pd_pack_contig(pd_ctx * c);                    // pd_pack.cpp part: builds the packed host image
+int pd_pack_contig(pd_ctx * c);                    // finalises the offset tables of the packed image
 int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result * out);   // pd_kernels.cu
 
 #endif

@@ -12,6 +12,7 @@
 #include "pd_context.h"
 
 static std::string g_create_error;
+static void free_words(pd_ctx * c, PdHostRg & h);
 
 int pd_fail(pd_ctx * c, int status, const std::string & msg)
 {
@@ -192,23 +193,48 @@ extern "C" void pd_destroy(pd_ctx * c)
         cudaFree(c->d_words); cudaFree(c->d_tile_off); cudaFree(c->d_longs); cudaFree(c->d_long_off); cudaFree(c->d_long_span);
         cudaFree(c->d_rgc); cudaFree(c->d_sample_rg); cudaFree(c->d_tab_val); cudaFree(c->d_tab_ln); cudaFree(c->d_tab_l10);
         for (auto & p : c->d_scratch) cudaFree(p);
-        if (c->h_pin_words) cudaFreeHost(c->h_pin_words);
         for (auto & ev : c->ev) if (ev) cudaEventDestroy(ev);
         if (c->stream) cudaStreamDestroy(c->stream);
     }
+    for (auto & h : c->hrg) free_words(c, h);
     delete c;
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// contig: begin / push (with the active-coverage cap) / pack / upload
+// contig: begin / push (active-coverage cap + packing in one pass) / finalise / upload
 // ---------------------------------------------------------------------------------------------------------
+static void free_words(pd_ctx * c, PdHostRg & h)
+{
+    if (h.words) { if (c->device >= 0) cudaFreeHost(h.words); else free(h.words); }
+    h.words = nullptr; h.n_words = h.cap_words = 0;
+}
+
+static bool reserve_words(pd_ctx * c, PdHostRg & h, size_t need)
+{
+    if (need <= h.cap_words) return true;
+    size_t want = std::max<size_t>(need + need / 4, 4096);
+    uint32_t * p = nullptr;
+    if (c->device >= 0) { if (cudaMallocHost(&p, want * 4) != cudaSuccess) return false; }
+    else { p = (uint32_t *)malloc(want * 4); if (!p) return false; }
+    if (h.n_words) memcpy(p, h.words, h.n_words * 4);
+    uint32_t * old = h.words;
+    h.words = p; h.cap_words = want;
+    if (old) { if (c->device >= 0) cudaFreeHost(old); else free(old); }
+    return true;
+}
+
 extern "C" int pd_contig_begin(pd_ctx * c, uint32_t anchor)
 {
     if (!c) return PD_ERR_ARG;
     if (c->status) return c->status;
     if (anchor % PD_WIN != 0) return pd_fail(c, PD_ERR_ARG, "pd_contig_begin: anchor must be a multiple of 30 (first 30-bp window of the contig)");
     c->grid.anchor = anchor;
-    for (auto & h : c->hrg) { h = PdHostRg(); }
+    for (auto & h : c->hrg) {
+        uint32_t * w = h.words; size_t cap = h.cap_words;      // keep the (pinned) buffer across contigs
+        h = PdHostRg();
+        h.words = w; h.cap_words = cap;
+        h.tile_rel.assign(1, 0u);
+    }
     c->contig_open = true; c->packed = false; c->uploaded = false;
     c->n_windows_total = 0; c->n_reads = 0;
     return 0;
@@ -218,6 +244,7 @@ extern "C" int pd_contig_begin(pd_ctx * c, uint32_t anchor)
 // stored iff fewer than max_load previously stored pairs of its read group are still open at its 30-bp bucket
 // (open = lastWindow >= bucket). The reference refreshes its counter lazily; the decision is the same except for the
 // single add that follows a segment switch while the cap is active (documented in DESIGN.md).
+// Thread-compatible: may run concurrently for DIFFERENT read groups of one context.
 extern "C" int pd_contig_push(pd_ctx * c, uint32_t rg, uint64_t n, const uint32_t * pos, const int32_t * dev)
 {
     if (!c) return PD_ERR_ARG;
@@ -227,117 +254,125 @@ extern "C" int pd_contig_push(pd_ctx * c, uint32_t rg, uint64_t n, const uint32_
     PdHostRg & h = c->hrg[rg];
     const PdRgConst & k = c->rgc[rg];
     const bool capped = k.max_load != 0xFFFFFFFFu;
-    h.pos_rel.reserve(h.pos_rel.size() + n);
-    h.dev.reserve(h.dev.size() + n);
+    const uint32_t wb = c->grid.window_buffer, anchor = c->grid.anchor;
+    if (!reserve_words(c, h, h.n_words + n + n / 8 + 64)) return pd_fail(c, PD_ERR_CUDA, "pd_contig_push: out of (pinned) host memory");
+    uint64_t seg_end_bp = h.seg < 0 ? 0 : (uint64_t)(h.seg + 1) * wb;
+    int64_t wl = h.seg < 0 ? -1 : (int64_t)pd_seg_last_window((uint64_t)h.seg, wb);
+    int64_t wl2 = h.seg < 0 ? -1 : (int64_t)pd_seg_last_window((uint64_t)h.seg + 1, wb);
+    uint32_t * words = h.words;
+    size_t nw = h.n_words;
     for (uint64_t i = 0; i < n; ++i) {
-        uint32_t p = pos[i];
-        if (p < c->grid.anchor) return pd_fail(c, PD_ERR_ARG, "pd_contig_push: position before the contig anchor");
+        const uint32_t p = pos[i];
+        if (p < anchor) return pd_fail(c, PD_ERR_ARG, "pd_contig_push: position before the contig anchor");
         if (h.any && p < h.last_pos) return pd_fail(c, PD_ERR_ORDER, "pd_contig_push: read pairs must be sorted by position");
         h.any = true; h.last_pos = p;
-        uint32_t pr = p - c->grid.anchor;
+        const uint32_t pr = p - anchor;
+        const uint32_t b = pr / PD_WIN, bp = b * PD_WIN;
+        const int32_t d = dev[i];
+        int64_t inner = (int64_t)d + k.inner_off;
+        if (inner < 0) inner = 0;
+        const int64_t lw = (int64_t)((pr + (uint64_t)inner) / PD_WIN);
         if (capped) {
-            uint32_t b = pr / PD_WIN;
-            int64_t inner = (int64_t)dev[i] + k.inner_off;
-            if (inner < 0) inner = 0;
-            uint32_t lw = (uint32_t)((pr + (uint64_t)inner) / PD_WIN);
             std::vector<uint32_t> & hp = h.open_lw;
             while (!hp.empty() && hp.front() < b) { std::pop_heap(hp.begin(), hp.end(), std::greater<uint32_t>()); hp.pop_back(); }
             if (hp.size() >= k.max_load) { ++h.dropped; continue; }
-            hp.push_back(lw); std::push_heap(hp.begin(), hp.end(), std::greater<uint32_t>());
+            hp.push_back((uint32_t)std::min<int64_t>(lw, 0xFFFFFFFF)); std::push_heap(hp.begin(), hp.end(), std::greater<uint32_t>());
         }
-        h.pos_rel.push_back(pr);
-        h.dev.push_back(dev[i]);
+        if (h.seg < 0 || bp >= seg_end_bp) {                       // first read pair of a new segment
+            const int64_t j = (int64_t)((uint64_t)bp / wb);
+            if (h.seg >= 0) { h.prev_seg = h.seg; h.prev_E_spill = h.E_spill; }
+            h.seg = j; h.S = h.E_own = h.E_spill = -1;
+            seg_end_bp = (uint64_t)(j + 1) * wb;
+            wl = (int64_t)pd_seg_last_window((uint64_t)j, wb);
+            wl2 = (int64_t)pd_seg_last_window((uint64_t)j + 1, wb);
+        }
+        h.S = std::max<int64_t>(h.S, pr);
+        if (lw <= wl) h.E_own = std::max(h.E_own, lw); else h.E_spill = std::max(h.E_spill, lw);
+        const int64_t s = (int64_t)b + (pr != bp ? 1 : 0);
+        int64_t e = lw + 1;
+        const bool act = s <= wl;
+        if (act) { const int64_t cap = lw <= wl ? wl : wl2; if (e > cap) e = cap; }
+        const uint32_t t = pr / PD_TILE_BP;
+        if (t != h.cur_tile) {
+            while (nw & 3) words[nw++] = PD_PAD_WORD;
+            while (h.cur_tile < t) { ++h.cur_tile; h.tile_rel.push_back((uint32_t)nw); }
+        }
+        bool is_long = d > PD_DEV_MAX || d < PD_DEV_MIN + 1;
+        if (act && (uint64_t)e / PD_TILE_WINDOWS > (uint64_t)t + k.lookback_tiles) is_long = true;
+        const int32_t dc = d > PD_DEV_MAX ? PD_DEV_MAX : (d < PD_DEV_MIN + 1 ? PD_DEV_MIN + 1 : d);
+        if (nw + 8 > h.cap_words) {                                 // padding can outgrow the reservation
+            h.n_words = nw;
+            if (!reserve_words(c, h, nw + (n - i) + (n - i) / 8 + 64)) return pd_fail(c, PD_ERR_CUDA, "pd_contig_push: out of (pinned) host memory");
+            words = h.words;
+        }
+        words[nw++] = pd_pack(dc, pr - t * PD_TILE_BP, is_long);
+        if (is_long && act) {
+            h.longs.push_back(PdLong{(uint32_t)s, (uint32_t)e, pr, d});
+            h.long_span = std::max<uint32_t>(h.long_span, (uint32_t)(e - s + 1));
+        }
+        ++h.n_reads;
+        if (nw > 0xFFFFFFF0ull) return pd_fail(c, PD_ERR_CAPACITY, "more than 2^32 packed words in one read group");
     }
+    h.n_words = nw;
     return 0;
 }
 
 // Last window the reference scans for this contig (workflow_popdel.h:42-47 with nextWindow's stop rules,
 // profile_structure_popdel_call.h:1213-1247): in the final segment kf the scan runs until the border or until every
-// start entry is activated and every end entry of end set kf is removed.
+// start entry is activated and every end entry of end set kf (own entries ending before the border, spill-over
+// entries of segment kf-1) is removed.
 static uint64_t last_scanned_window(const pd_ctx * c)
 {
     const uint32_t wb = c->grid.window_buffer;
     int64_t kf = -1;
-    for (const auto & h : c->hrg) if (!h.pos_rel.empty()) kf = std::max<int64_t>(kf, (int64_t)((uint64_t)(h.pos_rel.back() / PD_WIN) * PD_WIN / wb));
+    for (const auto & h : c->hrg) kf = std::max(kf, h.seg);
     if (kf < 0) return 0;
     int64_t E = -1, S = -1;
-    for (uint32_t g = 0; g < c->R; ++g) {
-        const PdHostRg & h = c->hrg[g];
-        const int32_t io = c->rgc[g].inner_off;
-        for (size_t i = h.pos_rel.size(); i-- > 0;) {
-            uint64_t pr = h.pos_rel[i];
-            uint64_t b = pr / PD_WIN;
-            int64_t j = (int64_t)(b * PD_WIN / wb);
-            if (j < kf - 1) break;
-            int64_t inner = std::max<int64_t>(0, (int64_t)h.dev[i] + io);
-            int64_t lw = (int64_t)((pr + inner) / PD_WIN);
-            int64_t wl = (int64_t)pd_seg_last_window((uint64_t)j, wb);
-            if (j == kf) { S = std::max<int64_t>(S, (int64_t)pr); if (lw <= wl) E = std::max(E, lw); }
-            else if (lw > wl) E = std::max(E, lw);                  // spill-over entry of segment kf-1 lives in end set kf
-        }
+    for (const auto & h : c->hrg) {
+        if (h.seg == kf) { S = std::max(S, h.S); E = std::max(E, h.E_own); if (h.prev_seg == kf - 1) E = std::max(E, h.prev_E_spill); }
+        else if (h.seg == kf - 1) E = std::max(E, h.E_spill);
     }
-    int64_t stop = std::max(E + 2, (S + 29) / (int64_t)PD_WIN);
-    int64_t wl = (int64_t)pd_seg_last_window((uint64_t)kf, wb);
+    const int64_t stop = std::max(E + 2, (S + 29) / (int64_t)PD_WIN);
+    const int64_t wl = (int64_t)pd_seg_last_window((uint64_t)kf, wb);
     return (uint64_t)std::min(stop, wl) + 1;
 }
 
 int pd_pack_contig(pd_ctx * c)
 {
     if (c->packed) return 0;
-    const uint32_t wb = c->grid.window_buffer;
     c->n_windows_total = last_scanned_window(c);
     uint64_t max_tile = (c->n_windows_total + PD_TILE_WINDOWS - 1) / PD_TILE_WINDOWS;
-    for (const auto & h : c->hrg) if (!h.pos_rel.empty()) max_tile = std::max<uint64_t>(max_tile, h.pos_rel.back() / PD_TILE_BP + 1);
+    for (auto & h : c->hrg) {
+        if (!reserve_words(c, h, h.n_words + 4)) return pd_fail(c, PD_ERR_CUDA, "out of (pinned) host memory");
+        while (h.n_words & 3) h.words[h.n_words++] = PD_PAD_WORD;
+        if (h.n_reads) max_tile = std::max<uint64_t>(max_tile, (uint64_t)h.cur_tile + 1);
+    }
     if (max_tile + 1 >= (1ull << 31)) return pd_fail(c, PD_ERR_RANGE, "contig too long for the tile index");
     c->NT = (uint32_t)std::max<uint64_t>(max_tile, 1);
     const uint32_t NT = c->NT;
     c->h_tile_off.assign((size_t)c->R * (NT + 1), 0);
     c->h_long_off.assign(c->R + 1, 0);
     c->h_long_span.assign(c->R, 0);
-    c->h_longs.clear();
-    // pass 1: counts per tile
-    uint64_t total_words = 0;
+    c->h_word_base.assign(c->R + 1, 0);
+    uint64_t total = 0, nlong = 0;
     c->n_reads = 0;
     for (uint32_t g = 0; g < c->R; ++g) {
         const PdHostRg & h = c->hrg[g];
+        c->h_word_base[g] = total;
+        if (total + h.n_words > 0xFFFFFFF0ull)
+            return pd_fail(c, PD_ERR_CAPACITY, "more than 2^32 packed words in one contig batch; split the cohort or the contig");
         uint32_t * off = &c->h_tile_off[(size_t)g * (NT + 1)];
-        std::vector<uint32_t> cnt(NT, 0);
-        for (uint32_t pr : h.pos_rel) ++cnt[pr / PD_TILE_BP];
-        for (uint32_t t = 0; t < NT; ++t) {
-            if (total_words > 0xFFFFFFF0ull) return pd_fail(c, PD_ERR_CAPACITY, "more than 2^32 packed words in one contig batch; split the cohort or the contig");
-            off[t] = (uint32_t)total_words;
-            total_words += (cnt[t] + 3u) & ~3u;
-        }
-        off[NT] = (uint32_t)total_words;
-        c->n_reads += h.pos_rel.size();
+        const size_t seen = h.tile_rel.size();
+        for (uint32_t t = 0; t <= NT; ++t) off[t] = (uint32_t)(total + (t < seen ? h.tile_rel[t] : h.n_words));
+        total += h.n_words;
+        c->h_long_off[g] = (uint32_t)nlong;
+        nlong += h.longs.size();
+        c->h_long_span[g] = h.long_span;
+        c->n_reads += h.n_reads;
     }
-    c->h_words.assign(total_words, PD_PAD_WORD);
-    // pass 2: words and the wide list of long read pairs
-    for (uint32_t g = 0; g < c->R; ++g) {
-        const PdHostRg & h = c->hrg[g];
-        const PdRgConst & k = c->rgc[g];
-        const uint32_t * off = &c->h_tile_off[(size_t)g * (NT + 1)];
-        c->h_long_off[g] = (uint32_t)c->h_longs.size();
-        uint32_t cur_tile = 0xFFFFFFFFu, w = 0, span = 0;
-        for (size_t i = 0; i < h.pos_rel.size(); ++i) {
-            uint32_t pr = h.pos_rel[i];
-            uint32_t t = pr / PD_TILE_BP;
-            if (t != cur_tile) { cur_tile = t; w = off[t]; }
-            int32_t d = h.dev[i];
-            int64_t s, e;
-            bool act = pd_interval(pr, d, k.inner_off, wb, s, e);
-            bool is_long = d > PD_DEV_MAX || d < PD_DEV_MIN + 1;
-            if (act && (uint64_t)e / PD_TILE_WINDOWS > (uint64_t)t + k.lookback_tiles) is_long = true;
-            int32_t dc = d > PD_DEV_MAX ? PD_DEV_MAX : (d < PD_DEV_MIN + 1 ? PD_DEV_MIN + 1 : d);
-            c->h_words[w++] = pd_pack(dc, pr - t * PD_TILE_BP, is_long);
-            if (is_long && act) {
-                c->h_longs.push_back(PdLong{(uint32_t)s, (uint32_t)e, pr, d});
-                span = std::max<uint32_t>(span, (uint32_t)(e - s + 1));
-            }
-        }
-        c->h_long_span[g] = span;
-    }
-    c->h_long_off[c->R] = (uint32_t)c->h_longs.size();
+    c->h_word_base[c->R] = total;
+    c->h_long_off[c->R] = (uint32_t)nlong;
+    c->total_words = total; c->total_longs = nlong;
     c->packed = true;
     return 0;
 }
@@ -375,30 +410,22 @@ extern "C" int pd_contig_upload(pd_ctx * c)
     int rc = pd_pack_contig(c);
     if (rc) return rc;
     PD_CUDA(c, cudaSetDevice(c->device));
-    if (grow(c, c->d_words, c->cap_words, c->h_words.size() + 4)) return c->status;
+    if (grow(c, c->d_words, c->cap_words, c->total_words + 4)) return c->status;
     if (grow(c, c->d_tile_off, c->cap_tile_off, c->h_tile_off.size())) return c->status;
-    if (grow(c, c->d_longs, c->cap_longs, c->h_longs.size() + 1)) return c->status;
-    // pinned staging for the big stream
-    if (c->cap_pin_words < c->h_words.size()) {
-        if (c->h_pin_words) cudaFreeHost(c->h_pin_words);
-        c->h_pin_words = nullptr; c->cap_pin_words = 0;
-        size_t want = c->h_words.size() + c->h_words.size() / 8 + 1024;
-        PD_CUDA(c, cudaMallocHost(&c->h_pin_words, want * 4));
-        c->cap_pin_words = want;
-    }
+    if (grow(c, c->d_longs, c->cap_longs, c->total_longs + 1)) return c->status;
     PD_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
-    // chunked copy: fill pinned staging in pieces so the H2D of chunk i overlaps the memcpy of chunk i+1
-    const size_t chunk = 16u << 20;   // words
-    for (size_t o = 0; o < c->h_words.size(); o += chunk) {
-        size_t m = std::min(chunk, c->h_words.size() - o);
-        memcpy(c->h_pin_words + o, c->h_words.data() + o, m * 4);
-        PD_CUDA(c, cudaMemcpyAsync(c->d_words + o, c->h_pin_words + o, m * 4, cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes = 0;
+    for (uint32_t g = 0; g < c->R; ++g) {                         // straight from the pinned per-read-group buffers
+        const PdHostRg & h = c->hrg[g];
+        if (h.n_words) PD_CUDA(c, cudaMemcpyAsync(c->d_words + c->h_word_base[g], h.words, h.n_words * 4, cudaMemcpyHostToDevice, c->stream));
+        if (!h.longs.empty())
+            PD_CUDA(c, cudaMemcpyAsync(c->d_longs + c->h_long_off[g], h.longs.data(), h.longs.size() * sizeof(PdLong), cudaMemcpyHostToDevice, c->stream));
+        c->h2d_bytes += h.n_words * 4 + h.longs.size() * sizeof(PdLong);
     }
     PD_CUDA(c, cudaMemcpyAsync(c->d_tile_off, c->h_tile_off.data(), c->h_tile_off.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    if (!c->h_longs.empty())
-        PD_CUDA(c, cudaMemcpyAsync(c->d_longs, c->h_longs.data(), c->h_longs.size() * sizeof(PdLong), cudaMemcpyHostToDevice, c->stream));
     PD_CUDA(c, cudaMemcpyAsync(c->d_long_off, c->h_long_off.data(), (c->R + 1) * 4, cudaMemcpyHostToDevice, c->stream));
     PD_CUDA(c, cudaMemcpyAsync(c->d_long_span, c->h_long_span.data(), c->R * 4, cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += c->h_tile_off.size() * 4 + (2 * c->R + 1) * 4;
     PD_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     PD_CUDA(c, cudaStreamSynchronize(c->stream));
     PD_CUDA(c, cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]));
@@ -430,7 +457,9 @@ extern "C" int pd_debug_host_window_sums(pd_ctx * c, uint32_t rg, uint64_t first
     if (rc) return rc;
     memset(out, 0, sizeof(int64_t) * 3 * n_windows);
     const PdRgConst & k = c->rgc[rg];
+    const PdHostRg & h = c->hrg[rg];
     const uint32_t * off = &c->h_tile_off[(size_t)rg * (c->NT + 1)];
+    const uint64_t base = c->h_word_base[rg];
     auto add = [&](int64_t s, int64_t e, int32_t d, uint64_t pr) {
         for (int64_t w = std::max<int64_t>(s, (int64_t)first_window); w <= e && w < (int64_t)(first_window + n_windows); ++w) {
             int64_t * o = out + 3 * (w - first_window);
@@ -438,18 +467,13 @@ extern "C" int pd_debug_host_window_sums(pd_ctx * c, uint32_t rg, uint64_t first
         }
     };
     for (uint32_t t = 0; t < c->NT; ++t)
-        for (uint32_t i = off[t]; i < off[t + 1]; ++i) {
-            uint32_t w = c->h_words[i];
+        for (uint64_t i = off[t] - base; i < off[t + 1] - base; ++i) {
+            uint32_t w = h.words[i];
             if (pd_word_long(w)) continue;                         // pads and long read pairs
             uint64_t pr = (uint64_t)t * PD_TILE_BP + pd_word_pit(w);
             int64_t s, e;
             if (pd_interval(pr, pd_word_dev(w), k.inner_off, c->grid.window_buffer, s, e)) add(s, e, pd_word_dev(w), pr);
         }
-    for (uint32_t i = c->h_long_off[rg]; i < c->h_long_off[rg + 1]; ++i) {
-        const PdLong & L = c->h_longs[i];
-        add(L.s, L.e, L.dev, L.pos_rel);
-    }
+    for (const PdLong & L : h.longs) add(L.s, L.e, L.dev, L.pos_rel);
     return 0;
 }
-
-// pd_contig_synthesize is implemented in pd_synth.cu

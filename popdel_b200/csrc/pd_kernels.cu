@@ -807,6 +807,7 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
     c->res_calls.clear(); c->res_ps.clear();
     out->n_reads = c->n_reads;
     out->algorithmic_bytes = 4ull * c->n_reads;
+    out->h2d_bytes = c->h2d_bytes;
     if (w_end <= w_begin) { out->calls = c->res_calls.data(); out->per_sample = c->res_ps.data(); return 0; }
     const uint32_t N = c->N, R = c->R;
     const uint32_t W = (uint32_t)(w_end - w_begin);
@@ -831,6 +832,7 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
     {
         dim3 grid((tile_end - tile_begin + 7) / 8, N);
         k_screen<<<grid, 256, 0, st>>>(a, tile_begin, tile_end, d_flags, d_jobs, d_counters);
+        ++out->n_kernel_launches;
         PD_CUDA(c, cudaGetLastError());
     }
     PD_CUDA(c, cudaEventRecord(c->ev[4], st));
@@ -878,6 +880,7 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
             PD_CUDA(c, cudaMemsetAsync(d_counters + CNT_PAIRS, 0, 2 * 4, st));      // pairs + pool cursor
             GatherArgs ga{d_jobs, job0, nj, d_pool, (uint32_t)pool_cap, d_counters, d_act_off, d_act_cnt, d_q3, d_sstat};
             k_gather<<<dim3(nj, (N + 3) / 4), 128, 0, st>>>(a, ga);
+            ++out->n_kernel_launches;
             PD_CUDA(c, cudaGetLastError());
             PD_CUDA(c, cudaMemcpyAsync(h_cnt, d_counters, 16 * 4, cudaMemcpyDeviceToHost, st));
             PD_CUDA(c, cudaStreamSynchronize(st));
@@ -887,6 +890,7 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
             pool_cap = (size_t)pool_used + 1024;
         }
         k_candidates<<<nj, 256, npad * 4, st>>>(a, d_q3, d_sstat, job0, d_counters, d_pairs, pair_cap, npad);
+        ++out->n_kernel_launches;
         PD_CUDA(c, cudaGetLastError());
         PD_CUDA(c, cudaMemcpyAsync(h_cnt, d_counters, 16 * 4, cudaMemcpyDeviceToHost, st));
         PD_CUDA(c, cudaStreamSynchronize(st));
@@ -911,6 +915,7 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
             e.min_sample_fraction = c->params.min_sample_fraction; e.somatic = c->params.somatic; e.window_wise = c->params.window_wise;
             e.anchor = c->grid.anchor;
             k_em<<<np, em_threads, 0, st>>>(a, e);
+            ++out->n_kernel_launches;
             PD_CUDA(c, cudaGetLastError());
             PD_CUDA(c, cudaMemcpyAsync(h_cnt, d_counters, 16 * 4, cudaMemcpyDeviceToHost, st));
             PD_CUDA(c, cudaStreamSynchronize(st));
@@ -922,6 +927,7 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
                 PD_CUDA(c, cudaMemcpyAsync(c->res_calls.data() + o, d_out_calls, (size_t)nc * sizeof(pd_call), cudaMemcpyDeviceToHost, st));
                 PD_CUDA(c, cudaMemcpyAsync(c->res_ps.data() + o * 13ull * N, d_out_ps, (size_t)nc * 13 * N * 4, cudaMemcpyDeviceToHost, st));
                 PD_CUDA(c, cudaStreamSynchronize(st));
+                out->d2h_bytes += (uint64_t)nc * (sizeof(pd_call) + 13ull * N * 4);
             }
         }
     }

@@ -205,3 +205,67 @@ def read_profile(path: str, compressed: bool = True):
                            np.concatenate(dev[chrom][r]) if dev[chrom][r] else np.zeros(0, np.int32))
                           for r in range(n_rg)]
     return meta, contigs, records, dict(index_region_size=irs, index=index)
+
+
+def write_profile_single_rg(path: str, meta: dict, contigs: Sequence[Tuple[str, int]], chrom: int,
+                            pos: np.ndarray, isize: np.ndarray, compressed: bool = True) -> None:
+    """Vectorised writer for the common case of one read group on one contig (same bytes as write_profile)."""
+    pos = np.asarray(pos, dtype=np.int64)
+    n = pos.size
+    n_regions = sum(l // INDEX_REGION_SIZE + 1 for _, l in contigs)
+    head = bytearray()
+    head += MAGIC
+    head += struct.pack("<II", INDEX_REGION_SIZE, n_regions)
+    index_pos = len(head)
+    head += b"\0" * (8 * n_regions)
+    head += struct.pack("<I", 1)
+    name = meta["name"].encode()
+    head += struct.pack("<I", len(name) + 1) + name + b"\0"
+    head += struct.pack("<IdIII", int(meta["median"]), float(meta["stddev"]), int(meta["read_length"]),
+                        int(meta["hist_start"]), int(meta["hist_end"]))
+    head += np.asarray(meta["hist_counts"], dtype="<f8").tobytes()
+    head += struct.pack("<I", len(contigs))
+    for cname, length in contigs:
+        nb = cname.encode()
+        head += struct.pack("<I", len(nb) + 1) + nb + b"\0" + struct.pack("<i", int(length))
+    base = len(head)
+    win = pos // PROFILE_WINDOW
+    first = np.flatnonzero(np.r_[True, win[1:] != win[:-1]]) if n else np.zeros(0, dtype=np.int64)
+    counts = np.diff(np.r_[first, n])
+    wbegin = win[first] * PROFILE_WINDOW
+    wstart = np.r_[0, np.cumsum(12 + 5 * counts)]                 # byte offset of each window record
+    body = np.zeros(int(wstart[-1]), dtype=np.uint8)
+    hdr = np.zeros(first.size, dtype=np.dtype([("c", "<u4"), ("b", "<u4"), ("n", "<u4")]))
+    hdr["c"], hdr["b"], hdr["n"] = chrom, wbegin, counts
+    hb = hdr.view(np.uint8).reshape(-1, 12)
+    for k in range(12):
+        body[wstart[:-1] + k] = hb[:, k]
+    rec = np.zeros(n, dtype=np.dtype([("o", "u1"), ("d", "<i4")]))
+    wi = np.repeat(np.arange(first.size), counts)
+    rec["o"] = (pos - wbegin[wi]).astype(np.uint8)
+    rec["d"] = (np.asarray(isize, dtype=np.int64) - int(meta["median"])).astype(np.int32)
+    rb = rec.view(np.uint8).reshape(-1, 5)
+    roff = wstart[:-1][wi] + 12 + 5 * (np.arange(n) - first[wi])
+    for k in range(5):
+        body[roff + k] = rb[:, k]
+    region = wbegin // INDEX_REGION_SIZE
+    rfirst = np.flatnonzero(np.r_[True, region[1:] != region[:-1]]) if first.size else np.zeros(0, dtype=np.int64)
+    bounds = np.r_[wstart[:-1][rfirst], wstart[-1]]
+    index = [[0] * (l // INDEX_REGION_SIZE + 1) for _, l in contigs]
+    out = bytearray()
+    raw = body.tobytes()
+    for k in range(rfirst.size):
+        index[chrom][int(region[rfirst[k]])] = base + len(out)
+        blk = raw[int(bounds[k]):int(bounds[k + 1])]
+        out += _gzip_member(blk) if compressed else blk
+    prev = base + len(out)
+    for i in range(len(index) - 1, -1, -1):
+        for j in range(len(index[i]) - 1, -1, -1):
+            if index[i][j] == 0:
+                index[i][j] = prev
+            else:
+                prev = index[i][j]
+    head[index_pos:index_pos + 8 * n_regions] = struct.pack("<%dQ" % n_regions, *[o for c in index for o in c])
+    with open(path, "wb") as fh:
+        fh.write(bytes(head))
+        fh.write(bytes(out))

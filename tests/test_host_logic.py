@@ -41,7 +41,8 @@ def _cohort(kind):
         specs = simulate.mixed_rg_specs(4, 4)
         return simulate.simulate_cohort(seed=22, n_samples=4, contig_len=260_000, n_dels=2, rg_specs=specs)[0], api.CallParameters()
     if kind == "gap":
-        samples, _ = simulate.simulate_cohort(seed=23, n_samples=3, contig_len=800_000, n_dels=1)
+        dels = [simulate.Deletion(100_000, 1800, np.array([1, 2, 1])), simulate.Deletion(700_000, 900, np.array([2, 0, 1]))]
+        samples, _ = simulate.simulate_cohort(seed=23, n_samples=3, contig_len=800_000, n_dels=0, dels=dels)
         for k, s in enumerate(samples):
             for rg in s.read_groups:
                 keep = ~((rg.pos >= 150_000) & (rg.pos < 610_000))
