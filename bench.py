@@ -153,17 +153,17 @@ def run_ours(args, rank, world, local_rank):
     # ---- resident-input throughput
     push_all()
     sc.upload()
-    res = sc.scan()
+    res = sc.scan(copy=False)
     evals = int(res["n_windows"]) * N
     for _ in range(args.warmup):
-        res = sc.scan()
+        res = sc.scan(copy=False)
     clocks = ClockSampler(local_rank)
     clocks.start()
     barrier()
     t0 = time.perf_counter()
     ms_screen, ms_dev, launches = [], [], 0
     for _ in range(args.steps):
-        res = sc.scan()
+        res = sc.scan(copy=False)
         ms_screen.append(res["ms_screen"]), ms_dev.append(res["ms_total"])
         launches += int(res["n_kernel_launches"])
     barrier()
@@ -183,12 +183,12 @@ def run_ours(args, rank, world, local_rank):
     # ---- end to end through the C ABI from host arrays (pack -> pinned -> H2D -> scan -> D2H)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     push_all()
-    r2 = sc.scan()                                                  # warm-up (pinned buffers exist afterwards)
+    r2 = sc.scan(copy=False)                                        # warm-up (pinned buffers exist afterwards)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         push_all()
-        r2 = sc.scan()
+        r2 = sc.scan(copy=False)
     barrier()
     dt2 = time.perf_counter() - t0
     if dist is not None:

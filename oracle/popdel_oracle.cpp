@@ -476,6 +476,10 @@ unsigned updateLength(const Ctx & cx, const Profile & pr, const std::vector<T3> 
             if (shifts[g] > h.stddev || shifts[g] < -1 * h.stddev) shifts[g] = 0;
         }
     }
+    if (getenv("ORC_DEBUG_POS") && (uint32_t)atoi(getenv("ORC_DEBUG_POS")) == pr.currentPos)
+        fprintf(stderr, "ORC pos %u L %d sumDel %.17g wDel %.17g rgw %.6Lg %.6Lg %.6Lg shifts %d %d %d gt %.6g %.6g %.6g dl0 %.6Lg %.6Lg %.6Lg dl1 %.6Lg %.6Lg %.6Lg dl2 %.6Lg %.6Lg %.6Lg\n", pr.currentPos, L, sumDel, wDel,
+                logl(r0.a), logl(r0.b), logl(r0.c), shifts[0], shifts[1], shifts[2], gt.a, gt.b, gt.c,
+                logl(dl[0].a), logl(dl[0].b), logl(dl[0].c), logl(dl[1].a), logl(dl[1].b), logl(dl[1].c), logl(dl[2].a), logl(dl[2].b), logl(dl[2].c));
     if (sumDel == 0) return 0;
     double len = wDel / sumDel;
     if (len < 0) return 0;

@@ -221,15 +221,21 @@ class Scanner:
         self._check(self.lib.pd_contig_window_count(self.ctx, C.byref(n)))
         return n.value
 
-    def scan(self, first_window: int = 0, n_windows: int = 0) -> dict:
+    def scan(self, first_window: int = 0, n_windows: int = 0, copy: bool = True) -> dict:
+        """Runs the scan. With copy=False `calls` / `per_sample` are views of library-owned (pinned) memory that stay
+        valid until the next call on this scanner."""
         res = PdResult()
         self._check(self.lib.pd_contig_scan(self.ctx, int(first_window), int(n_windows), C.byref(res)))
         n = res.n_calls
-        calls = np.zeros(n, dtype=CALL_DTYPE)
-        per = np.zeros((n, self.n_samples, 13), dtype=np.uint32)
-        if n:
-            C.memmove(calls.ctypes.data, res.calls, n * CALL_DTYPE.itemsize)
-            C.memmove(per.ctypes.data, res.per_sample, per.nbytes)
+        if n and not copy:
+            calls = np.frombuffer((C.c_char * (n * CALL_DTYPE.itemsize)).from_address(res.calls), dtype=CALL_DTYPE)
+            per = np.ctypeslib.as_array(res.per_sample, shape=(n, self.n_samples, 13))
+        else:
+            calls = np.zeros(n, dtype=CALL_DTYPE)
+            per = np.zeros((n, self.n_samples, 13), dtype=np.uint32)
+            if n:
+                C.memmove(calls.ctypes.data, res.calls, n * CALL_DTYPE.itemsize)
+                C.memmove(per.ctypes.data, res.per_sample, per.nbytes)
         return dict(calls=calls, per_sample=per, n_windows=res.n_windows, n_flagged_windows=res.n_flagged_windows,
                     n_candidates=res.n_candidates, n_reads=res.n_reads, algorithmic_bytes=res.algorithmic_bytes,
                     h2d_bytes=res.h2d_bytes, d2h_bytes=res.d2h_bytes, n_kernel_launches=res.n_kernel_launches,

@@ -47,7 +47,7 @@ struct PdRgConst {                  // per read group, device-resident
     int32_t  median;
     int32_t  hist_base;             // median - offset: table index = dev + hist_base
     uint32_t hist_len;
-    uint32_t hist_off;              // start of this read group's tables in the table arrays
+    uint32_t hist_off;              // index of this read group's FLOOR entry in the table array; values follow at hist_off+1+i
     double   min_prob, ln_min_prob, l10_min_prob;
     double   stddev;
     int32_t  lower_q, upper_q;
@@ -91,6 +91,45 @@ PD_HD bool pd_interval(uint64_t pos_rel, int32_t dev, int32_t inner_off, uint32_
     if (lw <= wl) { if ((uint64_t)e > wl) e = (int64_t)wl; }
     else { uint64_t wl2 = pd_seg_last_window(j + 1, window_buffer); if ((uint64_t)e > wl2) e = (int64_t)wl2; }
     return true;
+}
+
+// Same rule with the per-tile segment constants hoisted (what the kernels evaluate per stream word).
+struct TileSeg { uint32_t base_bp; uint32_t nb; int32_t wlA, wlB, wlC; };
+
+PD_HD TileSeg tile_seg(uint32_t tile, uint32_t wb)
+{
+    TileSeg t;
+    uint64_t base = (uint64_t)tile * PD_TILE_BP;
+    uint64_t j0 = base / wb;
+    uint64_t nb = (j0 + 1) * wb;
+    t.base_bp = (uint32_t)base;
+    t.nb = (uint32_t)nb;
+    t.wlA = (int32_t)((nb - 1) / PD_WIN);
+    t.wlB = (int32_t)((nb + wb - 1) / PD_WIN);
+    t.wlC = (int32_t)((nb + 2ull * wb - 1) / PD_WIN);
+    return t;
+}
+
+// returns false for pads / long read pairs / never-active read pairs
+PD_HD bool word_interval(uint32_t w, const TileSeg & ts, int32_t inner_off, int32_t & s, int32_t & e,
+                                              int32_t & dev, uint32_t & pos_rel)
+{
+    if (w & PD_LONG_BIT) return false;
+    dev = (int32_t)w >> 11;
+    pos_rel = ts.base_bp + (w & 0x3FFu);
+    uint32_t b = pos_rel / PD_WIN;
+    uint32_t bp = b * PD_WIN;
+    int32_t inner = dev + inner_off;
+    inner = inner < 0 ? 0 : inner;
+    int32_t lw = (int32_t)((pos_rel + (uint32_t)inner) / PD_WIN);
+    bool next = bp >= ts.nb;
+    int32_t wl = next ? ts.wlB : ts.wlA;
+    int32_t wl2 = next ? ts.wlC : ts.wlB;
+    s = (int32_t)b + (pos_rel != bp ? 1 : 0);
+    e = lw + 1;
+    int32_t cap = lw <= wl ? wl : wl2;
+    e = e < cap ? e : cap;
+    return s <= wl;
 }
 
 // Smallest number of values above T among n sorted values such that the upper-half median (Q3) can exceed T

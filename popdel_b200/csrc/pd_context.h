@@ -11,19 +11,28 @@
 #include "pd_common.h"
 
 struct PdLong { uint32_t s, e, pos_rel; int32_t dev; };      // wide entry of a long read pair (16 B)
+// tile table entry: first stream word of the tile and the range of wide-list entries that can be active in it
+struct PdTile { uint32_t off, long_lo, long_hi, pad; };
+// interleaved likelihood tables, one entry per histogram index (and one floor entry per read group)
+struct PdTab {
+    double val;     // processed histogram value I()
+    double ln;      // ln(val)
+    double l10;     // log10(val)
+    double lnp;     // ln(val + min_prob) - ln2_d          (g1 when the other hypothesis sits on the floor)
+    double l10p;    // log10(val + min_prob) - log10(2)_d
+    double fr;      // min_prob / (min_prob + val)
+    double fd;      // val / (min_prob + val)
+    double pad;
+};
 
 // Device view handed to the kernels by value.
 struct PdDev {
     const uint32_t * words;          // packed read-pair stream, all read groups
-    const uint32_t * tile_off;       // [R][NT+1] word offsets (multiples of 4)
+    const PdTile *   tiles;          // [R][NT+1] tile table (word offsets are multiples of 4)
     const PdLong *   longs;          // wide list of long read pairs, all read groups, sorted by s per read group
-    const uint32_t * long_off;       // [R+1]
-    const uint32_t * long_span;      // [R] max (e - s + 1)
     const PdRgConst * rgc;           // [R]
     const uint32_t * sample_rg;      // [N+1] read groups of sample s = sample_rg[s] .. sample_rg[s+1]
-    const double * tab_val;          // processed histogram values, all read groups
-    const double * tab_ln;           // ln(values)
-    const double * tab_l10;          // log10(values)
+    const PdTab * tab;               // likelihood tables of all read groups; entry hist_off-1+... see PdRgConst
     uint32_t NT;                     // tiles per read group
     uint32_t N, R;
     uint32_t window_buffer;
@@ -31,6 +40,7 @@ struct PdDev {
     uint32_t w_begin, w_end;         // windows to scan [w_begin, w_end)
 };
 
+#define PD_CAP_RING 4096u
 struct PdHostRg {                    // host staging of one read group of the current contig (filled by pd_contig_push)
     uint32_t * words = nullptr;      // packed stream (pinned when the context has a device); tiles padded to 4 words
     size_t n_words = 0, cap_words = 0;
@@ -40,7 +50,9 @@ struct PdHostRg {                    // host staging of one read group of the cu
     uint32_t cur_tile = 0;           // tile being appended
     uint64_t n_reads = 0, dropped = 0;
     // active-coverage cap state (ChromosomeProfile::add, profile_structure :1084-1113)
-    std::vector<uint32_t> open_lw;   // min-heap of last-window indices of read pairs still open
+    std::vector<uint32_t> ring;      // ring[lw % PD_CAP_RING] = stored read pairs whose last window is lw (lw >= ring_b)
+    std::vector<uint32_t> far;       // min-heap of last windows beyond the ring
+    uint32_t ring_b = 0, open = 0;   // open = stored read pairs with last window >= ring_b
     uint32_t last_pos = 0;
     bool any = false;
     // bookkeeping for the reference's last scanned window: per segment (current, previous)
@@ -66,7 +78,8 @@ struct pd_ctx {
     PdGrid grid{0, 200000};
     std::vector<PdHostRg> hrg;
     // packed host image (offset tables; the words stay in the per-read-group staging vectors)
-    std::vector<uint32_t> h_tile_off, h_long_off, h_long_span;
+    std::vector<PdTile> h_tiles;
+    std::vector<uint32_t> h_long_off;
     std::vector<uint64_t> h_word_base;   // first word of each read group in the device stream
     uint64_t total_words = 0, total_longs = 0;
     uint32_t NT = 0;
@@ -77,17 +90,16 @@ struct pd_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
     uint32_t * d_words = nullptr; size_t cap_words = 0;
-    uint32_t * d_tile_off = nullptr; size_t cap_tile_off = 0;
+    PdTile * d_tiles = nullptr; size_t cap_tiles = 0;
     PdLong * d_longs = nullptr; size_t cap_longs = 0;
-    uint32_t * d_long_off = nullptr, * d_long_span = nullptr;
     PdRgConst * d_rgc = nullptr;
     uint32_t * d_sample_rg = nullptr;
-    double * d_tab_val = nullptr, * d_tab_ln = nullptr, * d_tab_l10 = nullptr;
+    PdTab * d_tab = nullptr;
     // scan scratch (grown on demand)
     void * d_scratch[16] = {}; size_t cap_scratch[16] = {};
-    // results (pinned)
+    // results
     std::vector<pd_call> res_calls;
-    std::vector<uint32_t> res_ps;
+    uint32_t * res_ps = nullptr; size_t cap_res_ps = 0;    // pinned
     float ms_h2d = 0;
     uint64_t h2d_bytes = 0;
 };

@@ -97,29 +97,28 @@ extern "C" const char * pd_last_error(pd_ctx * c) { return c ? c->err.c_str() : 
 
 static int upload_static(pd_ctx * c)
 {
+    // the reference evaluates log(2.0) / log10(2.0) in double (genotype_deletion_popdel_call.h:212,298)
+    const double LN2_D = std::log(2.0), L10_2_D = std::log10(2.0);
     size_t total = 0;
-    for (auto & t : c->tables_) total += t.size();
-    std::vector<double> val(total), ln(total), l10(total);
+    for (auto & t : c->tables_) total += t.size() + 1;
+    std::vector<PdTab> tab(total);
     for (uint32_t g = 0; g < c->R; ++g) {
+        const double mp = c->rgc[g].min_prob;
+        auto fill = [&](PdTab & e, double v) {
+            e.val = v; e.ln = std::log(v); e.l10 = std::log10(v);
+            e.lnp = std::log(v + mp) - LN2_D; e.l10p = std::log10(v + mp) - L10_2_D;
+            e.fr = mp / (mp + v); e.fd = v / (mp + v); e.pad = 0;
+        };
         size_t o = c->rgc[g].hist_off;
-        for (size_t i = 0; i < c->tables_[g].size(); ++i) {
-            val[o + i] = c->tables_[g][i];
-            ln[o + i] = std::log(c->tables_[g][i]);
-            l10[o + i] = std::log10(c->tables_[g][i]);
-        }
+        fill(tab[o], mp);                                           // floor entry
+        for (size_t i = 0; i < c->tables_[g].size(); ++i) fill(tab[o + 1 + i], c->tables_[g][i]);
     }
-    PD_CUDA(c, cudaMalloc(&c->d_tab_val, std::max<size_t>(total, 1) * 8));
-    PD_CUDA(c, cudaMalloc(&c->d_tab_ln, std::max<size_t>(total, 1) * 8));
-    PD_CUDA(c, cudaMalloc(&c->d_tab_l10, std::max<size_t>(total, 1) * 8));
-    PD_CUDA(c, cudaMemcpy(c->d_tab_val, val.data(), total * 8, cudaMemcpyHostToDevice));
-    PD_CUDA(c, cudaMemcpy(c->d_tab_ln, ln.data(), total * 8, cudaMemcpyHostToDevice));
-    PD_CUDA(c, cudaMemcpy(c->d_tab_l10, l10.data(), total * 8, cudaMemcpyHostToDevice));
+    PD_CUDA(c, cudaMalloc(&c->d_tab, std::max<size_t>(total, 1) * sizeof(PdTab)));
+    PD_CUDA(c, cudaMemcpy(c->d_tab, tab.data(), total * sizeof(PdTab), cudaMemcpyHostToDevice));
     PD_CUDA(c, cudaMalloc(&c->d_rgc, c->R * sizeof(PdRgConst)));
     PD_CUDA(c, cudaMemcpy(c->d_rgc, c->rgc.data(), c->R * sizeof(PdRgConst), cudaMemcpyHostToDevice));
     PD_CUDA(c, cudaMalloc(&c->d_sample_rg, (c->N + 1) * 4));
     PD_CUDA(c, cudaMemcpy(c->d_sample_rg, c->sample_rg.data(), (c->N + 1) * 4, cudaMemcpyHostToDevice));
-    PD_CUDA(c, cudaMalloc(&c->d_long_off, (c->R + 1) * 4));
-    PD_CUDA(c, cudaMalloc(&c->d_long_span, c->R * 4));
     return 0;
 }
 
@@ -160,7 +159,7 @@ extern "C" pd_ctx * pd_create(const pd_params * p, uint32_t n_samples, uint32_t 
         double span_w = (29.0 + std::max(0.0, k.inner_off + 8.0 * r.stddev)) / 30.0 + 2.0;
         uint32_t lb = (uint32_t)std::ceil(span_w / PD_TILE_WINDOWS);
         k.lookback_tiles = std::min<uint32_t>(std::max<uint32_t>(lb, 1), PD_MAX_LOOKBACK_TILES);
-        hist_off += r.len;
+        hist_off += r.len + 1;
         tmin = std::min<int64_t>(tmin, r.min_init_del_len);
     }
     if (c->sample_rg[n_samples] != n_rg || prev_sample != n_samples - 1) {
@@ -190,8 +189,9 @@ extern "C" void pd_destroy(pd_ctx * c)
     if (!c) return;
     if (c->device >= 0) {
         cudaSetDevice(c->device);
-        cudaFree(c->d_words); cudaFree(c->d_tile_off); cudaFree(c->d_longs); cudaFree(c->d_long_off); cudaFree(c->d_long_span);
-        cudaFree(c->d_rgc); cudaFree(c->d_sample_rg); cudaFree(c->d_tab_val); cudaFree(c->d_tab_ln); cudaFree(c->d_tab_l10);
+        cudaFree(c->d_words); cudaFree(c->d_tiles); cudaFree(c->d_longs);
+        cudaFree(c->d_rgc); cudaFree(c->d_sample_rg); cudaFree(c->d_tab);
+        if (c->res_ps) cudaFreeHost(c->res_ps);
         for (auto & p : c->d_scratch) cudaFree(p);
         for (auto & ev : c->ev) if (ev) cudaEventDestroy(ev);
         if (c->stream) cudaStreamDestroy(c->stream);
@@ -273,10 +273,18 @@ extern "C" int pd_contig_push(pd_ctx * c, uint32_t rg, uint64_t n, const uint32_
         if (inner < 0) inner = 0;
         const int64_t lw = (int64_t)((pr + (uint64_t)inner) / PD_WIN);
         if (capped) {
-            std::vector<uint32_t> & hp = h.open_lw;
-            while (!hp.empty() && hp.front() < b) { std::pop_heap(hp.begin(), hp.end(), std::greater<uint32_t>()); hp.pop_back(); }
-            if (hp.size() >= k.max_load) { ++h.dropped; continue; }
-            hp.push_back((uint32_t)std::min<int64_t>(lw, 0xFFFFFFFF)); std::push_heap(hp.begin(), hp.end(), std::greater<uint32_t>());
+            if (h.ring.empty()) { h.ring.assign(PD_CAP_RING, 0u); h.ring_b = b; h.open = 0; }
+            if (b - h.ring_b >= PD_CAP_RING) {                      // everything in the ring is closed
+                std::fill(h.ring.begin(), h.ring.end(), 0u);
+                h.open = (uint32_t)h.far.size(); h.ring_b = b;
+            }
+            while (h.ring_b < b) { uint32_t & c0 = h.ring[h.ring_b % PD_CAP_RING]; h.open -= c0; c0 = 0; ++h.ring_b; }
+            while (!h.far.empty() && h.far.front() < b) { std::pop_heap(h.far.begin(), h.far.end(), std::greater<uint32_t>()); h.far.pop_back(); --h.open; }
+            if (h.open >= k.max_load) { ++h.dropped; continue; }
+            const uint32_t lwc = (uint32_t)std::min<int64_t>(lw, 0xFFFFFFFF);
+            if (lwc - b < PD_CAP_RING) ++h.ring[lwc % PD_CAP_RING];
+            else { h.far.push_back(lwc); std::push_heap(h.far.begin(), h.far.end(), std::greater<uint32_t>()); }
+            ++h.open;
         }
         if (h.seg < 0 || bp >= seg_end_bp) {                       // first read pair of a new segment
             const int64_t j = (int64_t)((uint64_t)bp / wb);
@@ -350,9 +358,8 @@ int pd_pack_contig(pd_ctx * c)
     if (max_tile + 1 >= (1ull << 31)) return pd_fail(c, PD_ERR_RANGE, "contig too long for the tile index");
     c->NT = (uint32_t)std::max<uint64_t>(max_tile, 1);
     const uint32_t NT = c->NT;
-    c->h_tile_off.assign((size_t)c->R * (NT + 1), 0);
+    c->h_tiles.assign((size_t)c->R * (NT + 1), PdTile{0, 0, 0, 0});
     c->h_long_off.assign(c->R + 1, 0);
-    c->h_long_span.assign(c->R, 0);
     c->h_word_base.assign(c->R + 1, 0);
     uint64_t total = 0, nlong = 0;
     c->n_reads = 0;
@@ -361,13 +368,22 @@ int pd_pack_contig(pd_ctx * c)
         c->h_word_base[g] = total;
         if (total + h.n_words > 0xFFFFFFF0ull)
             return pd_fail(c, PD_ERR_CAPACITY, "more than 2^32 packed words in one contig batch; split the cohort or the contig");
-        uint32_t * off = &c->h_tile_off[(size_t)g * (NT + 1)];
+        PdTile * tl = &c->h_tiles[(size_t)g * (NT + 1)];
         const size_t seen = h.tile_rel.size();
-        for (uint32_t t = 0; t <= NT; ++t) off[t] = (uint32_t)(total + (t < seen ? h.tile_rel[t] : h.n_words));
+        // wide-list range per tile: entries are sorted by s; [lo, hi) = first entry still alive (e >= 32t) .. first with s > 32t+31
+        size_t lo = 0, hi = 0;
+        const size_t nl = h.longs.size();
+        for (uint32_t t = 0; t <= NT; ++t) {
+            tl[t].off = (uint32_t)(total + (t < seen ? h.tile_rel[t] : h.n_words));
+            const uint64_t w0 = (uint64_t)t * PD_TILE_WINDOWS;
+            while (hi < nl && h.longs[hi].s <= w0 + PD_TILE_WINDOWS - 1) ++hi;
+            while (lo < hi && h.longs[lo].e < w0) ++lo;
+            tl[t].long_lo = (uint32_t)(nlong + lo);
+            tl[t].long_hi = (uint32_t)(nlong + hi);
+        }
         total += h.n_words;
         c->h_long_off[g] = (uint32_t)nlong;
-        nlong += h.longs.size();
-        c->h_long_span[g] = h.long_span;
+        nlong += nl;
         c->n_reads += h.n_reads;
     }
     c->h_word_base[c->R] = total;
@@ -411,7 +427,7 @@ extern "C" int pd_contig_upload(pd_ctx * c)
     if (rc) return rc;
     PD_CUDA(c, cudaSetDevice(c->device));
     if (grow(c, c->d_words, c->cap_words, c->total_words + 4)) return c->status;
-    if (grow(c, c->d_tile_off, c->cap_tile_off, c->h_tile_off.size())) return c->status;
+    if (grow(c, c->d_tiles, c->cap_tiles, c->h_tiles.size())) return c->status;
     if (grow(c, c->d_longs, c->cap_longs, c->total_longs + 1)) return c->status;
     PD_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
     c->h2d_bytes = 0;
@@ -422,10 +438,8 @@ extern "C" int pd_contig_upload(pd_ctx * c)
             PD_CUDA(c, cudaMemcpyAsync(c->d_longs + c->h_long_off[g], h.longs.data(), h.longs.size() * sizeof(PdLong), cudaMemcpyHostToDevice, c->stream));
         c->h2d_bytes += h.n_words * 4 + h.longs.size() * sizeof(PdLong);
     }
-    PD_CUDA(c, cudaMemcpyAsync(c->d_tile_off, c->h_tile_off.data(), c->h_tile_off.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    PD_CUDA(c, cudaMemcpyAsync(c->d_long_off, c->h_long_off.data(), (c->R + 1) * 4, cudaMemcpyHostToDevice, c->stream));
-    PD_CUDA(c, cudaMemcpyAsync(c->d_long_span, c->h_long_span.data(), c->R * 4, cudaMemcpyHostToDevice, c->stream));
-    c->h2d_bytes += c->h_tile_off.size() * 4 + (2 * c->R + 1) * 4;
+    PD_CUDA(c, cudaMemcpyAsync(c->d_tiles, c->h_tiles.data(), c->h_tiles.size() * sizeof(PdTile), cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += c->h_tiles.size() * sizeof(PdTile);
     PD_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     PD_CUDA(c, cudaStreamSynchronize(c->stream));
     PD_CUDA(c, cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]));
@@ -458,7 +472,7 @@ extern "C" int pd_debug_host_window_sums(pd_ctx * c, uint32_t rg, uint64_t first
     memset(out, 0, sizeof(int64_t) * 3 * n_windows);
     const PdRgConst & k = c->rgc[rg];
     const PdHostRg & h = c->hrg[rg];
-    const uint32_t * off = &c->h_tile_off[(size_t)rg * (c->NT + 1)];
+    const PdTile * off = &c->h_tiles[(size_t)rg * (c->NT + 1)];
     const uint64_t base = c->h_word_base[rg];
     auto add = [&](int64_t s, int64_t e, int32_t d, uint64_t pr) {
         for (int64_t w = std::max<int64_t>(s, (int64_t)first_window); w <= e && w < (int64_t)(first_window + n_windows); ++w) {
@@ -467,7 +481,7 @@ extern "C" int pd_debug_host_window_sums(pd_ctx * c, uint32_t rg, uint64_t first
         }
     };
     for (uint32_t t = 0; t < c->NT; ++t)
-        for (uint64_t i = off[t] - base; i < off[t + 1] - base; ++i) {
+        for (uint64_t i = off[t].off - base; i < off[t + 1].off - base; ++i) {
             uint32_t w = h.words[i];
             if (pd_word_long(w)) continue;                         // pads and long read pairs
             uint64_t pr = (uint64_t)t * PD_TILE_BP + pd_word_pit(w);

@@ -1,10 +1,12 @@
 // pd_kernels.cu -- sm_100a kernels of the `popdel call` window scan and their orchestration.
 //
-//   k_screen      (K1, HBM-bound)  every (sample, window): streams the packed read-pair words once, counts the
-//                                   active read pairs and those above the smallest initial-length threshold, and flags
-//                                   windows in which some sample's upper-half median CAN exceed that threshold
-//                                   (exact necessary condition for initialize_deletion_lengths to return a candidate,
-//                                   reference genotype_deletion_popdel_call.h:33-87).
+//   k_screen      (K1, HBM-bound)  every (sample, window): streams the packed read-pair words once with 128-bit
+//                                   loads (one warp = 8 tiles = 256 windows of one sample), and only where a read pair
+//                                   above the smallest initial-length threshold can be active counts, per window, the
+//                                   active read pairs and those above the threshold; flags windows in which some
+//                                   sample's upper-half median CAN exceed the threshold (exact necessary condition
+//                                   for initialize_deletion_lengths to return a candidate, reference
+//                                   genotype_deletion_popdel_call.h:33-87).
 //   k_gather      (K2a)            flagged windows only: exact active sets per (window, read group), coverage /
 //                                   high-coverage state and the per-sample Q3 (upperHalfMedian, :15-27).
 //   k_candidates  (K2b)            per flagged window: sort Q3s over samples, gap-50 clustering, rank-indexed
@@ -12,12 +14,14 @@
 //   k_em          (K3-K5)          per (window, initial length): allele-frequency initialisation (:93-133), EM over
 //                                   deletion length / reference shifts / allele frequency (:556-664), final genotype
 //                                   likelihoods, LAD/DAD/FL, supporting read percentiles, LR test, PL (:665-727).
+//   k_compact                      gathers the per-sample rows of the emitted calls into one contiguous buffer.
 // No tensor cores: the path is lookup-and-reduce (BASELINE.json north_star).
 #include <algorithm>
 #include <cfloat>
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -35,161 +39,162 @@
 namespace {
 
 constexpr uint32_t FULL = 0xFFFFFFFFu;
+constexpr int SCREEN_TPW = 8;                                     // tiles per warp in k_screen
 constexpr double LN2_D = 0.693147180559945309417232121458;       // the reference evaluates log(2.0) in double
 constexpr double LOG10_2_D = 0.301029995663981195213738894724;
+// The reference accumulates in long double and subtracts the DOUBLE constants log(2.0) / log10(2.0) from
+// logl(ref+del) / log10l(ref+del). For a read pair with ref == del this leaves ln2 - fl(ln2) (resp. the log10
+// analogue) per read pair, so three otherwise identical sums are NOT equal there and the "all equal -> assume
+// reference" overrides (:246-251, :314-319, :330-335) do not fire. We keep such read pairs out of the double
+// sums and re-apply the residue as a tie-break.
+constexpr double LN2_RESIDUE = 2.3190468138462996e-17;            // ln 2 - fl64(ln 2)
+constexpr double LOG10_2_RESIDUE = -2.8037281277851704e-18;       // log10 2 - fl64(log10 2)
 // expl() underflows to 0 below ln(2^-16446): the reference's `res == 0` test on long double (:240, :324)
 constexpr double LD_EXP_ZERO = -11399.4985314888605;
+constexpr double LN1E10 = -23.025850929940457;                    // ln(1e-10)
 
-enum { CNT_JOBS = 0, CNT_PAIRS = 1, CNT_POOL = 2, CNT_CALLS = 3, CNT_FLAGS = 4, CNT_ERR = 5 };
+enum { CNT_JOBS = 0, CNT_PAIRS = 1, CNT_POOL = 2 };
 
 struct PoolEntry { uint32_t pos_rel; int32_t dev; };
 struct PdPair { uint32_t job; int32_t L0; };
 
-// ------------------------------------------------------------------------------------------------------------------
-// interval of a stream word, with the per-tile segment constants hoisted (pd_common.h holds the plain version)
-// ------------------------------------------------------------------------------------------------------------------
-struct TileSeg { uint32_t base_bp; uint32_t nb; int32_t wlA, wlB, wlC; };
-
-__device__ __forceinline__ TileSeg tile_seg(uint32_t tile, uint32_t wb)
+__device__ __forceinline__ PdTile load_tile(const PdTile * p)
 {
-    TileSeg t;
-    uint64_t base = (uint64_t)tile * PD_TILE_BP;
-    uint64_t j0 = base / wb;
-    uint64_t nb = (j0 + 1) * wb;
-    t.base_bp = (uint32_t)base;
-    t.nb = (uint32_t)nb;
-    t.wlA = (int32_t)((nb - 1) / PD_WIN);
-    t.wlB = (int32_t)((nb + wb - 1) / PD_WIN);
-    t.wlC = (int32_t)((nb + 2ull * wb - 1) / PD_WIN);
-    return t;
-}
-
-// returns false for pads / long read pairs / never-active read pairs
-__device__ __forceinline__ bool word_interval(uint32_t w, const TileSeg & ts, int32_t inner_off, int32_t & s, int32_t & e,
-                                              int32_t & dev, uint32_t & pos_rel)
-{
-    if (w & PD_LONG_BIT) return false;
-    dev = (int32_t)w >> 11;
-    pos_rel = ts.base_bp + (w & 0x3FFu);
-    uint32_t b = pos_rel / PD_WIN;
-    uint32_t bp = b * PD_WIN;
-    int32_t inner = dev + inner_off;
-    inner = inner < 0 ? 0 : inner;
-    int32_t lw = (int32_t)((pos_rel + (uint32_t)inner) / PD_WIN);
-    bool next = bp >= ts.nb;
-    int32_t wl = next ? ts.wlB : ts.wlA;
-    int32_t wl2 = next ? ts.wlC : ts.wlB;
-    s = (int32_t)b + (pos_rel != bp ? 1 : 0);
-    e = lw + 1;
-    int32_t cap = lw <= wl ? wl : wl2;
-    e = e < cap ? e : cap;
-    return s <= wl;
-}
-
-__device__ __forceinline__ uint32_t lower_bound_long(const PdLong * L, uint32_t lo, uint32_t hi, int64_t key_s)
-{
-    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if ((int64_t)L[mid].s < key_s) lo = mid + 1; else hi = mid; }
-    return lo;
+    const uint4 q = __ldg(reinterpret_cast<const uint4 *>(p));
+    return PdTile{q.x, q.y, q.z, q.w};
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// K1: screen. One warp = one tile (32 windows) of one sample; lane = window.
+// K1 phase B: lane = window of `tile`; adds to n_g the active read pairs of read group g and to x_g those with
+// dev > t_min (stream words of the look-back tiles, then the wide list of long read pairs).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void count_tile(const PdDev & a, uint32_t g, const PdRgConst & k, uint32_t tile, int lane,
+                                           uint32_t & n_g, uint32_t & x_g)
+{
+    const PdTile * tl = a.tiles + (size_t)g * (a.NT + 1);
+    const int32_t w0 = (int32_t)(tile * PD_TILE_WINDOWS), w = w0 + lane;
+    const uint32_t t_lo = tile > k.lookback_tiles ? tile - k.lookback_tiles : 0;
+    for (uint32_t tt = t_lo; tt <= tile; ++tt) {
+        const TileSeg ts = tile_seg(tt, a.window_buffer);
+        const uint32_t r_lo = tl[tt].off, r_hi = tl[tt + 1].off;
+        for (uint32_t base = r_lo; base < r_hi; base += 32) {
+            const uint32_t i = base + lane;
+            const uint32_t word = i < r_hi ? __ldg(a.words + i) : PD_PAD_WORD;
+            int32_t s = 0, e = 0, dev = 0; uint32_t pr;
+            bool valid = word_interval(word, ts, k.inner_off, s, e, dev, pr);
+            valid = valid && e >= w0 && s <= w0 + 31;
+            const uint32_t pk = (uint32_t)e | (dev > a.t_min ? 0x80000000u : 0u);
+            uint32_t mask = __ballot_sync(FULL, valid);
+            while (mask) {
+                const int src = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int32_t ss = __shfl_sync(FULL, s, src);
+                const uint32_t ee = __shfl_sync(FULL, pk, src);
+                const bool hit = ss <= w && w <= (int32_t)(ee & 0x7FFFFFFFu);
+                n_g += hit;
+                x_g += hit & (ee >> 31);
+            }
+        }
+    }
+    const uint32_t l_lo = tl[tile].long_lo, l_hi = tl[tile].long_hi;
+    for (uint32_t base = l_lo; base < l_hi; base += 32) {
+        const uint32_t i = base + lane;
+        PdLong L = i < l_hi ? a.longs[i] : PdLong{0xFFFFFFFFu, 0, 0, 0};
+        const bool valid = i < l_hi && (int64_t)L.e >= w0;
+        const uint32_t pk = L.e | (L.dev > a.t_min ? 0x80000000u : 0u);
+        uint32_t mask = __ballot_sync(FULL, valid);
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int32_t ss = (int32_t)__shfl_sync(FULL, L.s, src);
+            const uint32_t ee = __shfl_sync(FULL, pk, src);
+            const bool hit = ss <= w && w <= (int32_t)(ee & 0x7FFFFFFFu);
+            n_g += hit;
+            x_g += hit & (ee >> 31);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K1: screen. One warp = SCREEN_TPW consecutive tiles of one sample.
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_screen(PdDev a, uint32_t tile_begin, uint32_t tile_end, uint32_t * __restrict__ flags,
                                                 uint32_t * __restrict__ jobs, uint32_t * __restrict__ counters)
 {
     const int lane = threadIdx.x & 31;
-    const uint32_t tile = tile_begin + blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (tile >= tile_end) return;
+    const uint32_t T0 = tile_begin + (blockIdx.x * 8 + (threadIdx.x >> 5)) * SCREEN_TPW;
+    if (T0 >= tile_end) return;
+    const uint32_t T1 = min(T0 + SCREEN_TPW, tile_end);          // exclusive
     const uint32_t smp = blockIdx.y;
     const uint32_t g0 = a.sample_rg[smp], g1 = a.sample_rg[smp + 1];
-    const int32_t w0 = (int32_t)(tile * PD_TILE_WINDOWS), w = w0 + lane;
     const int32_t thr = (int32_t)(((uint32_t)a.t_min << 11) | 0x7FFu);      // (int)word > thr  <=>  dev > t_min
 
-    // ---- phase A: is there any read pair above the threshold that can be active in this tile?
-    bool any = false;
+    // ---- phase A: stream every word once; which of my tiles can see a read pair above the threshold?
+    uint32_t tmask = 0;                                           // bit i: tile T0+i needs exact counts
     for (uint32_t g = g0; g < g1; ++g) {
-        const uint32_t * toff = a.tile_off + (size_t)g * (a.NT + 1);
-        const uint32_t lb = a.rgc[g].lookback_tiles;
-        const uint32_t t_lo = tile > lb ? tile - lb : 0;
-        const uint32_t r0 = toff[t_lo], r1 = toff[tile + 1];
-        for (uint32_t i = r0 + lane * 4; i < r1; i += 128) {
-            uint4 v = __ldg(reinterpret_cast<const uint4 *>(a.words + i));
-            any |= ((int32_t)v.x > thr) | ((int32_t)v.y > thr) | ((int32_t)v.z > thr) | ((int32_t)v.w > thr);
-        }
-        const uint32_t l0 = a.long_off[g], l1 = a.long_off[g + 1];
-        if (l1 > l0) {
-            uint32_t lo = lower_bound_long(a.longs, l0, l1, (int64_t)w0 - (int64_t)a.long_span[g]);
-            for (uint32_t i = lo + lane; i < l1; i += 32) {
-                PdLong L = a.longs[i];
-                if ((int64_t)L.s > (int64_t)w0 + 31) break;
-                any |= ((int64_t)L.e >= w0);
+        const PdTile * tl = a.tiles + (size_t)g * (a.NT + 1);
+        const uint32_t lb = a.rgc[g].lookback_tiles;              // <= PD_MAX_LOOKBACK_TILES
+        const uint32_t t_lo = T0 > lb ? T0 - lb : 0;
+        // lanes hold the tile table entries t_lo .. T1 (at most 8 + 8 + 1 = 17)
+        const uint32_t te = t_lo + lane;
+        const bool have = te <= T1;
+        PdTile my = PdTile{0xFFFFFFFFu, 0, 0, 0};
+        if (have) my = load_tile(tl + te);
+        const uint32_t r0 = __shfl_sync(FULL, my.off, 0), r1 = __shfl_sync(FULL, my.off, (int)(T1 - t_lo));
+        // long read pairs: any of my tiles with a non-empty wide-list range
+        const uint32_t lmask = __ballot_sync(FULL, have && te >= T0 && te < T1 && my.long_lo < my.long_hi);
+        tmask |= (lmask >> (T0 - t_lo)) & ((1u << SCREEN_TPW) - 1u);
+        for (uint32_t i0 = r0; i0 < r1; i0 += 128 * 4) {
+            bool ex[4]; uint32_t idx[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                idx[u] = i0 + u * 128 + lane * 4;
+                ex[u] = false;
+                if (idx[u] < r1) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(a.words + idx[u]));
+                    ex[u] = ((int32_t)v.x > thr) | ((int32_t)v.y > thr) | ((int32_t)v.z > thr) | ((int32_t)v.w > thr);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                uint32_t m = __ballot_sync(FULL, ex[u]);
+                while (m) {                                       // rare: find the tile of the exceeding word
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t wi = __shfl_sync(FULL, idx[u], src);
+                    // tile index = (number of table entries with off <= wi) - 1
+                    const uint32_t nle = __popc(__ballot_sync(FULL, have && my.off <= wi));
+                    const int32_t rel = (int32_t)(t_lo + nle - 1) - (int32_t)T0;     // negative: look-back tile
+                    const int32_t lo = rel < 0 ? 0 : rel, hi = min(rel + (int32_t)lb, SCREEN_TPW - 1);
+                    if (hi >= lo) tmask |= ((1u << (hi + 1)) - 1u) & ~((1u << lo) - 1u);
+                }
             }
         }
     }
-    if (!__any_sync(FULL, any)) return;
+    if (tmask == 0) return;
 
-    // ---- phase B: exact counts per window (lane) for every read group of the sample
-    uint32_t cov = 0, n = 0, x = 0;
-    for (uint32_t g = g0; g < g1; ++g) {
-        const uint32_t * toff = a.tile_off + (size_t)g * (a.NT + 1);
-        const PdRgConst k = a.rgc[g];
-        const uint32_t t_lo = tile > k.lookback_tiles ? tile - k.lookback_tiles : 0;
-        uint32_t n_g = 0, x_g = 0;
-        for (uint32_t tt = t_lo; tt <= tile; ++tt) {
-            const TileSeg ts = tile_seg(tt, a.window_buffer);
-            const uint32_t r_lo = toff[tt], r_hi = toff[tt + 1];
-            for (uint32_t base = r_lo; base < r_hi; base += 32) {
-                const uint32_t i = base + lane;
-                const uint32_t word = i < r_hi ? __ldg(a.words + i) : PD_PAD_WORD;
-                int32_t s = 0, e = 0, dev = 0; uint32_t pr;
-                bool valid = word_interval(word, ts, k.inner_off, s, e, dev, pr);
-                valid = valid && e >= w0 && s <= w0 + 31;
-                uint32_t pk = (uint32_t)e | (dev > a.t_min ? 0x80000000u : 0u);
-                uint32_t mask = __ballot_sync(FULL, valid);
-                while (mask) {
-                    const int src = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const int32_t ss = __shfl_sync(FULL, s, src);
-                    const uint32_t ee = __shfl_sync(FULL, pk, src);
-                    const bool hit = ss <= w && w <= (int32_t)(ee & 0x7FFFFFFFu);
-                    n_g += hit;
-                    x_g += hit & (ee >> 31);
-                }
-            }
+    // ---- phase B: exact counts per window (lane) for the tiles in tmask
+    for (uint32_t ti = 0; ti < (uint32_t)SCREEN_TPW; ++ti) {
+        if (!((tmask >> ti) & 1u)) continue;
+        const uint32_t tile = T0 + ti;
+        if (tile >= T1) break;
+        uint32_t cov = 0, n = 0, x = 0;
+        for (uint32_t g = g0; g < g1; ++g) {
+            const PdRgConst k = a.rgc[g];
+            uint32_t n_g = 0, x_g = 0;
+            count_tile(a, g, k, tile, lane, n_g, x_g);
+            cov += n_g;
+            if (n_g < k.max_load) { n += n_g; x += x_g; }
         }
-        const uint32_t l0 = a.long_off[g], l1 = a.long_off[g + 1];
-        if (l1 > l0) {
-            uint32_t lo = lower_bound_long(a.longs, l0, l1, (int64_t)w0 - (int64_t)a.long_span[g]);
-            for (uint32_t base = lo; base < l1; base += 32) {
-                const uint32_t i = base + lane;
-                PdLong L = i < l1 ? a.longs[i] : PdLong{0xFFFFFFFFu, 0, 0, 0};
-                bool beyond = (int64_t)L.s > (int64_t)w0 + 31;
-                bool valid = i < l1 && !beyond && (int64_t)L.e >= w0;
-                uint32_t pk = L.e | (L.dev > a.t_min ? 0x80000000u : 0u);
-                uint32_t mask = __ballot_sync(FULL, valid);
-                while (mask) {
-                    const int src = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const int32_t ss = (int32_t)__shfl_sync(FULL, L.s, src);
-                    const uint32_t ee = __shfl_sync(FULL, pk, src);
-                    const bool hit = ss <= w && w <= (int32_t)(ee & 0x7FFFFFFFu);
-                    n_g += hit;
-                    x_g += hit & (ee >> 31);
-                }
-                if (__all_sync(FULL, beyond || i >= l1)) break;
+        const uint32_t w = tile * PD_TILE_WINDOWS + lane;
+        const bool in_range = w >= a.w_begin && w < a.w_end;
+        const bool pass = in_range && cov >= 2 && n >= 1 && x >= pd_q3_need(n);
+        if (pass) {
+            const uint32_t wi = w - a.w_begin;
+            if (flags[wi] == 0 && atomicExch(&flags[wi], 1u) == 0) {
+                uint32_t slot = atomicAdd(&counters[CNT_JOBS], 1u);
+                jobs[slot] = w;
             }
-        }
-        cov += n_g;
-        if (n_g < k.max_load) { n += n_g; x += x_g; }
-    }
-    const bool in_range = (uint32_t)w >= a.w_begin && (uint32_t)w < a.w_end;
-    const bool pass = in_range && cov >= 2 && n >= 1 && x >= pd_q3_need(n);
-    if (pass) {
-        const uint32_t wi = (uint32_t)w - a.w_begin;
-        if (flags[wi] == 0 && atomicExch(&flags[wi], 1u) == 0) {
-            uint32_t slot = atomicAdd(&counters[CNT_JOBS], 1u);
-            jobs[slot] = (uint32_t)w;
         }
     }
 }
@@ -206,16 +211,16 @@ struct GatherArgs {
 };
 
 // calls f(valid, pos_rel, dev) for every 32-wide batch of read pairs of read group g that may be active at window w;
-// `valid` marks lanes whose read pair IS active at w. Batches preserve stream order (stream first, then long list).
+// `valid` marks lanes whose read pair IS active at w. Batches preserve stream order (stream first, then wide list).
 template <typename F>
 __device__ __forceinline__ void for_active_batches(const PdDev & a, uint32_t g, const PdRgConst & k, int32_t w, int lane, F f)
 {
-    const uint32_t * toff = a.tile_off + (size_t)g * (a.NT + 1);
+    const PdTile * tl = a.tiles + (size_t)g * (a.NT + 1);
     const uint32_t tile = (uint32_t)w / PD_TILE_WINDOWS;
     const uint32_t t_lo = tile > k.lookback_tiles ? tile - k.lookback_tiles : 0;
     for (uint32_t tt = t_lo; tt <= tile; ++tt) {
         const TileSeg ts = tile_seg(tt, a.window_buffer);
-        const uint32_t r_lo = toff[tt], r_hi = toff[tt + 1];
+        const uint32_t r_lo = tl[tt].off, r_hi = tl[tt + 1].off;
         for (uint32_t base = r_lo; base < r_hi; base += 32) {
             const uint32_t i = base + lane;
             const uint32_t word = i < r_hi ? __ldg(a.words + i) : PD_PAD_WORD;
@@ -225,17 +230,12 @@ __device__ __forceinline__ void for_active_batches(const PdDev & a, uint32_t g, 
             f(valid, pr, dev);
         }
     }
-    const uint32_t l0 = a.long_off[g], l1 = a.long_off[g + 1];
-    if (l1 > l0) {
-        uint32_t lo = lower_bound_long(a.longs, l0, l1, (int64_t)w - (int64_t)a.long_span[g]);
-        for (uint32_t base = lo; base < l1; base += 32) {
-            const uint32_t i = base + lane;
-            PdLong L = i < l1 ? a.longs[i] : PdLong{0xFFFFFFFFu, 0, 0, 0};
-            bool beyond = (int64_t)L.s > (int64_t)w;
-            bool valid = i < l1 && !beyond && (int64_t)L.e >= w;
-            f(valid, L.pos_rel, L.dev);
-            if (__all_sync(FULL, beyond || i >= l1)) break;
-        }
+    const uint32_t l_lo = tl[tile].long_lo, l_hi = tl[tile].long_hi;
+    for (uint32_t base = l_lo; base < l_hi; base += 32) {
+        const uint32_t i = base + lane;
+        PdLong L = i < l_hi ? a.longs[i] : PdLong{0xFFFFFFFFu, 0, 0, 0};
+        const bool valid = i < l_hi && (int64_t)L.s <= w && (int64_t)L.e >= w;
+        f(valid, L.pos_rel, L.dev);
     }
 }
 
@@ -264,43 +264,64 @@ __global__ void __launch_bounds__(128) k_gather(PdDev a, GatherArgs ga)
     if (lane == 0 && nvals) base = atomicAdd(&ga.counters[CNT_POOL], nvals);
     base = __shfl_sync(FULL, base, 0);
     const bool fits = (uint64_t)base + nvals <= ga.pool_cap;
-    // pass 2: entries (stream order)
+    // pass 2: entries (stream order); the first 32 values also stay in registers (lane i holds value i) for the Q3
     uint32_t cur = base;
+    int32_t myval = INT_MAX;
     for (uint32_t g = g0; g < g1; ++g) {
         const PdRgConst k = a.rgc[g];
         if (lane == 0) off[g] = cur;
         const uint32_t n_g = __shfl_sync(FULL, lane == 0 ? cnt[g] : 0u, 0);
         if (n_g >= k.max_load || !fits) continue;
         for_active_batches(a, g, k, w, lane, [&](bool valid, uint32_t pr, int32_t dev) {
-            uint32_t mask = __ballot_sync(FULL, valid);
-            if (valid) ga.pool[cur + __popc(mask & ((1u << lane) - 1u))] = PoolEntry{pr, dev};
+            const uint32_t mask = __ballot_sync(FULL, valid);
+            const uint32_t slot = cur - base + __popc(mask & ((1u << lane) - 1u));
+            if (valid) ga.pool[base + slot] = PoolEntry{pr, dev};
+            uint32_t m = mask;
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t sl = __shfl_sync(FULL, slot, src);
+                const int32_t dv = __shfl_sync(FULL, dev, src);
+                if (sl == (uint32_t)lane) myval = dv;
+            }
             cur += __popc(mask);
         });
     }
     __syncwarp();
-    // coverage state and Q3
+    // coverage state and Q3 (upperHalfMedian :15-27: n<4 -> maximum; else interpolate at (3n+2+n%2)/4-1)
     uint8_t st; int32_t q = 0;
     if (cov < 2u) st = 0;
     else if (nvals == 0 || !fits) st = 1;
     else {
         st = 2;
-        const volatile PoolEntry * v = ga.pool + base;
         const uint32_t nn = nvals;
-        int32_t lo_v = 0, hi_v = 0;            // order statistics l and l+1
-        uint32_t l;
-        double r = 0;
+        uint32_t l; double r = 0;
         if (nn < 4) { l = nn - 1; }
         else { double pos = (3.0 * nn + 2.0 + (nn % 2)) / 4.0 - 1.0; l = (uint32_t)pos; r = pos - l; }
         const uint32_t l2 = (l + 1 < nn) ? l + 1 : l;
-        for (uint32_t i0 = 0; i0 < nn; i0 += 32) {
-            const uint32_t i = i0 + lane;
-            int32_t vi = i < nn ? v[i].dev : INT_MAX;
+        int32_t lo_v = 0, hi_v = 0;
+        if (nn <= 32) {
             uint32_t rank = 0;
-            for (uint32_t j = 0; j < nn; ++j) { int32_t vj = v[j].dev; rank += (vj < vi) || (vj == vi && j < i); }
-            uint32_t m1 = __ballot_sync(FULL, i < nn && rank == l);
-            uint32_t m2 = __ballot_sync(FULL, i < nn && rank == l2);
-            if (m1) lo_v = __shfl_sync(FULL, vi, __ffs(m1) - 1);
-            if (m2) hi_v = __shfl_sync(FULL, vi, __ffs(m2) - 1);
+            for (int j = 0; j < 32; ++j) {
+                const int32_t vj = __shfl_sync(FULL, myval, j);
+                rank += ((uint32_t)j < nn) && ((vj < myval) || (vj == myval && j < lane));
+            }
+            const uint32_t m1 = __ballot_sync(FULL, (uint32_t)lane < nn && rank == l);
+            const uint32_t m2 = __ballot_sync(FULL, (uint32_t)lane < nn && rank == l2);
+            lo_v = __shfl_sync(FULL, myval, __ffs(m1) - 1);
+            hi_v = __shfl_sync(FULL, myval, __ffs(m2) - 1);
+        } else {
+            const volatile PoolEntry * v = ga.pool + base;
+            for (uint32_t i0 = 0; i0 < nn; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                const int32_t vi = i < nn ? v[i].dev : INT_MAX;
+                uint32_t rank = 0;
+                for (uint32_t j = 0; j < nn; ++j) { const int32_t vj = v[j].dev; rank += (vj < vi) || (vj == vi && j < i); }
+                const uint32_t m1 = __ballot_sync(FULL, i < nn && rank == l);
+                const uint32_t m2 = __ballot_sync(FULL, i < nn && rank == l2);
+                if (m1) lo_v = __shfl_sync(FULL, vi, __ffs(m1) - 1);
+                if (m2) hi_v = __shfl_sync(FULL, vi, __ffs(m2) - 1);
+            }
         }
         if (nn < 4) q = (int32_t)floor((double)lo_v + 0.5);
         else q = (int32_t)floor((1 - r) * lo_v + r * hi_v + 0.5);
@@ -325,9 +346,10 @@ __global__ void __launch_bounds__(256) k_candidates(PdDev a, const int32_t * __r
     __syncthreads();
     const uint32_t nv = s_n;
     if (nv == 0) return;
-    for (uint32_t k = 2; k <= npad; k <<= 1)
+    uint32_t np2 = 1; while (np2 < nv) np2 <<= 1;                 // sort only the occupied power of two
+    for (uint32_t k = 2; k <= np2; k <<= 1)
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) {
+            for (uint32_t i = threadIdx.x; i < np2; i += blockDim.x) {
                 uint32_t ixj = i ^ j;
                 if (ixj > i) {
                     int32_t x = sv[i], y = sv[ixj];
@@ -361,10 +383,12 @@ struct EmArgs {
     const PoolEntry * pool; const uint32_t * act_off, * act_cnt; const uint8_t * sstat;
     double * dlx;            // [block][N][3]   data likelihoods, log domain, max = 0
     int32_t * shifts;        // [block][R]
-    uint32_t * ps;           // [block][N][13]
-    uint32_t * counters;
-    pd_call * out_calls; uint32_t * out_ps; uint32_t out_cap;
+    uint32_t * ps;           // [block][N][13]  per-sample output rows (pair-indexed)
+    pd_call * calls;         // [block]         call headers (pair-indexed)
+    uint8_t * valid;         // [block]
     uint32_t iterations, min_len; double min_lr, min_sample_fraction; int somatic, window_wise; uint32_t anchor;
+    uint32_t * dbg;          // optional [npairs][4]: reason, len, iterations, supp (PD_DEBUG)
+    int dbg_window;          // device printf of the EM trajectory of this window (PD_DEBUG_WINDOW), -1 = off
 };
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -396,11 +420,12 @@ __device__ __forceinline__ void block_sum2u(unsigned long long & a, unsigned lon
     a = sa; b = sb;
 }
 
-__device__ __forceinline__ double hist_at(const double * __restrict__ tab, const PdRgConst & k, int dev, double floor_v)
+// table entry of insert-size deviation `dev` (I(), insert_histogram_popdel.h:1157-1163): floor entry outside the table
+__device__ __forceinline__ const PdTab * tab_at(const PdTab * __restrict__ tab, const PdRgConst & k, int dev)
 {
-    int i = dev + k.hist_base;                        // I(), insert_histogram_popdel.h:1157-1163
-    if (i <= 0 || i + 1 >= (int)k.hist_len) return floor_v;
-    return __ldg(tab + k.hist_off + i);
+    const int i = dev + k.hist_base;
+    const bool in = i > 0 && i + 1 < (int)k.hist_len;
+    return tab + k.hist_off + (in ? i + 1 : 0);
 }
 
 struct Gt { double a, b, c; };
@@ -419,7 +444,7 @@ struct EmShared {
     double red[64];
     unsigned long long redu[64];
     double rgw[3];                     // log-domain per-RG likelihoods of read group 0 (quirk: drives all reference shifts)
-    double freq, prevFreq, lr, plr;
+    double freq, prevFreq;
     Gt gt, prevGt;
     double ea0Rg, ea1Rg;
     uint32_t len, prevLen, it;
@@ -427,12 +452,28 @@ struct EmShared {
     int stop;
 };
 
+// Normalises three log-likelihood sums like the reference (:235-251): subtract the maximum, apply the long-double
+// tie-break of `ndeg` read pairs with ref == del to the heterozygous sum, then the two overrides.
+__device__ __forceinline__ void finish_triple(double l0, double l1, double l2, uint32_t ndeg, double & x0, double & x1, double & x2)
+{
+    const double m = fmax(fmax(l0, l1), l2);
+    x0 = l0 - m; x1 = l1 - m; x2 = l2 - m;
+    if (ndeg) {
+        x1 += ndeg * LN2_RESIDUE;
+        const double m2 = fmax(fmax(x0, x1), x2);
+        x0 -= m2; x1 -= m2; x2 -= m2;
+    }
+    if (x0 < LD_EXP_ZERO || x1 < LD_EXP_ZERO || x2 < LD_EXP_ZERO) { x0 = 0; x1 = LN1E10; x2 = LN1E10; }
+    if (x0 == x1 && x0 == x2) { x0 = 0; x1 = LN1E10; x2 = LN1E10; }
+}
+
 // data likelihoods of every sample for (L, shifts) -> dlx; compute_data_likelihoods (EM overload) :179-253
 __device__ void compute_dl(const PdDev & a, const EmArgs & e, EmShared & sh, const uint32_t * cnt, const uint32_t * off,
                            double * dlx, const int32_t * shifts, bool zero_shifts, uint32_t L)
 {
     for (uint32_t s = threadIdx.x; s < a.N; s += blockDim.x) {
         double l0 = 0, l1 = 0, l2 = 0;
+        uint32_t ndeg = 0;
         for (uint32_t g = a.sample_rg[s]; g < a.sample_rg[s + 1]; ++g) {
             const PdRgConst k = a.rgc[g];
             const uint32_t n = cnt[g];
@@ -443,11 +484,15 @@ __device__ void compute_dl(const PdDev & a, const EmArgs & e, EmShared & sh, con
                 const PoolEntry * p = e.pool + off[g];
                 for (uint32_t i = 0; i < n; ++i) {
                     const int d = p[i].dev;
-                    const double ref = hist_at(a.tab_val, k, d - shift, k.min_prob);
-                    const double del = hist_at(a.tab_val, k, d - (int)L, k.min_prob);
-                    const double g0 = hist_at(a.tab_ln, k, d - shift, k.ln_min_prob);
-                    const double g2 = hist_at(a.tab_ln, k, d - (int)L, k.ln_min_prob);
-                    const double g1 = log(ref + del) - LN2_D;
+                    const PdTab * tr = tab_at(a.tab, k, d - shift);
+                    const PdTab * td = tab_at(a.tab, k, d - (int)L);
+                    const double ref = tr->val, del = td->val;
+                    const double g0 = tr->ln, g2 = td->ln;
+                    double g1;
+                    if (ref == del) { g1 = g0; ++ndeg; }                 // + LN2_RESIDUE, applied in finish_triple
+                    else if (del == k.min_prob) g1 = tr->lnp;            // ln(ref + min_prob) - ln2_d
+                    else if (ref == k.min_prob) g1 = td->lnp;
+                    else g1 = log(ref + del) - LN2_D;
                     w0 += g0; w1 += g1; w2 += g2;
                     l0 += g0; l1 += g1; l2 += g2;
                 }
@@ -457,11 +502,8 @@ __device__ void compute_dl(const PdDev & a, const EmArgs & e, EmShared & sh, con
                 else { double m = fmax(fmax(w0, w1), w2); sh.rgw[0] = w0 - m; sh.rgw[1] = w1 - m; sh.rgw[2] = w2 - m; }
             }
         }
-        const double m = fmax(fmax(l0, l1), l2);
-        double x0 = l0 - m, x1 = l1 - m, x2 = l2 - m;
-        const double LN1E10 = log(0.0000000001);
-        if (x0 < LD_EXP_ZERO || x1 < LD_EXP_ZERO || x2 < LD_EXP_ZERO) { x0 = 0; x1 = LN1E10; x2 = LN1E10; }
-        if (x0 == x1 && x0 == x2) { x0 = 0; x1 = LN1E10; x2 = LN1E10; }
+        double x0, x1, x2;
+        finish_triple(l0, l1, l2, ndeg, x0, x1, x2);
         dlx[3 * s] = x0; dlx[3 * s + 1] = x1; dlx[3 * s + 2] = x2;
     }
     __syncthreads();
@@ -482,7 +524,7 @@ __device__ double block_lr(const PdDev & a, EmShared & sh, const double * dlx, c
     return del - nodel;
 }
 
-__global__ void __launch_bounds__(256) k_em(PdDev a, EmArgs e)
+__global__ void __launch_bounds__(256, 2) k_em(PdDev a, EmArgs e)
 {
     __shared__ EmShared sh;
     const uint32_t pi = e.pair0 + blockIdx.x;
@@ -497,6 +539,12 @@ __global__ void __launch_bounds__(256) k_em(PdDev a, EmArgs e)
     int32_t * shifts = e.shifts + (size_t)blockIdx.x * a.R;
     uint32_t * ps = e.ps + (size_t)blockIdx.x * 13 * a.N;
     const int tid = threadIdx.x;
+    auto reject = [&](uint32_t reason) {
+        if (tid == 0) {
+            e.valid[blockIdx.x] = 0;
+            if (e.dbg) { e.dbg[4 * blockIdx.x] = reason; e.dbg[4 * blockIdx.x + 1] = sh.len; e.dbg[4 * blockIdx.x + 2] = sh.it; }
+        }
+    };
 
     for (uint32_t g = tid; g < a.R; g += blockDim.x) shifts[g] = 0;
 
@@ -520,7 +568,7 @@ __global__ void __launch_bounds__(256) k_em(PdDev a, EmArgs e)
         }
         __syncthreads();
     }
-    if (sh.freq == 0) return;
+    if (sh.freq == 0) { reject(1); return; }
     compute_dl(a, e, sh, cnt, off, dlx, shifts, false, L0);
     if (tid == 0) { sh.gt = gt_prior(sh.freq, e.somatic); sh.prevFreq = sh.freq; sh.prevLen = sh.len; sh.prevGt = sh.gt; }
     __syncthreads();
@@ -565,8 +613,8 @@ __global__ void __launch_bounds__(256) k_em(PdDev a, EmArgs e)
                 const PoolEntry * p = e.pool + off[g];
                 for (uint32_t i = 0; i < n; ++i) {
                     const int d = p[i].dev;
-                    const double del = hist_at(a.tab_val, k, d - L, k.min_prob);
-                    const double nod = hist_at(a.tab_val, k, d - shift, k.min_prob);
+                    const double del = tab_at(a.tab, k, d - L)->val;
+                    const double nod = tab_at(a.tab, k, d - shift)->val;
                     const double pd = ea1 * del / (del + nod) + ea2;
                     const double prf = ea1Rg * nod / (del + nod) + ea0Rg;
                     sumDel += pd; sumRef += prf;
@@ -579,6 +627,8 @@ __global__ void __launch_bounds__(256) k_em(PdDev a, EmArgs e)
             }
         }
         block_sum2(sumDel, wDel, sh.red);
+        if (tid == 0 && (int)w == e.dbg_window)
+            printf("GPU w %u L0 %u it %u len %u freq %.17g sumDel %.17g wDel %.17g\n", w, L0, sh.it, sh.len, sh.freq, sumDel, wDel);
         if (tid == 0) {
             uint32_t nl;
             if (sumDel == 0) nl = 0;
@@ -622,7 +672,7 @@ __global__ void __launch_bounds__(256) k_em(PdDev a, EmArgs e)
         }
     }
     __syncthreads();
-    if (sh.freq < 0.0000000001 || sh.len < e.min_len) return;
+    if (sh.freq < 0.0000000001 || sh.len < e.min_len) { reject(2); return; }
 
     // ---- final pass :665-727 (compute_data_likelihoods final overload :255-337)
     const int len = (int)sh.len;
@@ -630,7 +680,7 @@ __global__ void __launch_bounds__(256) k_em(PdDev a, EmArgs e)
     uint32_t smin = 0xFFFFFFFFu, smax = 0, lmin = 0xFFFFFFFFu, lmax = 0;   // ranges of supporting starts / ends
     for (uint32_t s = tid; s < a.N; s += blockDim.x) {
         uint32_t lad[3] = {0, 0, 0}, dad[5] = {0, 0, 0, 0, 0};
-        uint32_t fl_min = 0xFFFFFFFFu, fl_max = 0;
+        uint32_t fl_min = 0xFFFFFFFFu, fl_max = 0, ndeg = 0;
         double l0 = 0, l1 = 0, l2 = 0, t0 = 0, t1 = 0, t2 = 0;
         int delLower = INT_MAX, delUpper = 0;
         const uint32_t g0 = a.sample_rg[s], g1 = a.sample_rg[s + 1];
@@ -645,15 +695,16 @@ __global__ void __launch_bounds__(256) k_em(PdDev a, EmArgs e)
                 const int d = p[i].dev;
                 if (d > k.upper_q) { if (d < delLower) ++dad[2]; else if (d <= delUpper) ++dad[3]; else ++dad[4]; }
                 else { if (d < delUpper) ++dad[0]; else ++dad[1]; }
-                const double ref = hist_at(a.tab_val, k, d - shift, k.min_prob);
-                const double del = hist_at(a.tab_val, k, d - len, k.min_prob);
+                const PdTab * tr = tab_at(a.tab, k, d - shift);
+                const PdTab * td = tab_at(a.tab, k, d - len);
+                const double ref = tr->val, del = td->val;
                 if (ref >= 2 * del) ++lad[0]; else if (del >= 2 * ref) ++lad[2]; else ++lad[1];
-                l0 += hist_at(a.tab_ln, k, d - shift, k.ln_min_prob);
-                t0 += hist_at(a.tab_l10, k, d - shift, k.l10_min_prob);
-                l1 += log(ref + del) - LN2_D;
-                t1 += log10(ref + del) - LOG10_2_D;
-                l2 += hist_at(a.tab_ln, k, d - len, k.ln_min_prob);
-                t2 += hist_at(a.tab_l10, k, d - len, k.l10_min_prob);
+                l0 += tr->ln; t0 += tr->l10;
+                l2 += td->ln; t2 += td->l10;
+                if (ref == del) { l1 += tr->ln; t1 += tr->l10; ++ndeg; }              // residues applied below
+                else if (del == k.min_prob) { l1 += tr->lnp; t1 += tr->l10p; }
+                else if (ref == k.min_prob) { l1 += td->lnp; t1 += td->l10p; }
+                else { l1 += log(ref + del) - LN2_D; t1 += log10(ref + del) - LOG10_2_D; }
                 const uint32_t first = p[i].pos_rel + e.anchor;
                 const int isz = max(0, d + k.inner_off);
                 const uint32_t last = first + (uint32_t)isz;
@@ -677,15 +728,13 @@ __global__ void __launch_bounds__(256) k_em(PdDev a, EmArgs e)
         }
         if (fl_min == 0xFFFFFFFFu) fl_min = 0;
         double x0, x1, x2, g0l = t0, g1l = t1, g2l = t2;
-        const double LN1E10 = log(0.0000000001);
-        if (t0 + t1 + t2 == 0.0) { x0 = 0; x1 = LN1E10; x2 = LN1E10; }
+        if (t0 + t1 + t2 == 0.0) { x0 = 0; x1 = LN1E10; x2 = LN1E10; }       // sum(gtLogs) == 0 :307-308
         else {
-            const double mg = fmax(fmax(t0, t1), t2), md = fmax(fmax(l0, l1), l2);
+            const double mg = fmax(fmax(t0, t1), t2);
             g0l -= mg; g1l -= mg; g2l -= mg;
+            if (ndeg) { g1l += ndeg * LOG10_2_RESIDUE; const double m2 = fmax(fmax(g0l, g1l), g2l); g0l -= m2; g1l -= m2; g2l -= m2; }
             if (g0l == g1l && g0l == g2l) { g0l = 0; g1l = -10; g2l = -10; }
-            x0 = l0 - md; x1 = l1 - md; x2 = l2 - md;
-            if (x0 < LD_EXP_ZERO || x1 < LD_EXP_ZERO || x2 < LD_EXP_ZERO) { x0 = 0; x1 = LN1E10; x2 = LN1E10; }
-            if (x0 == x1 && x0 == x2) { x0 = 0; x1 = LN1E10; x2 = LN1E10; }
+            finish_triple(l0, l1, l2, ndeg, x0, x1, x2);
         }
         dlx[3 * s] = x0; dlx[3 * s + 1] = x1; dlx[3 * s + 2] = x2;
         // calculatePhredGL utils_popdel.h:1511-1528
@@ -704,7 +753,7 @@ __global__ void __launch_bounds__(256) k_em(PdDev a, EmArgs e)
     }
     __syncthreads();
     block_sum2u(supp, ndata, sh.redu);
-    if (supp == 0) return;
+    if (supp == 0) { reject(3); return; }
     // percentiles of the supporting starts (80th) and ends (20th): getSuppFirstLast :514-529, by value bisection
     uint32_t sF, sL;
     {
@@ -751,33 +800,34 @@ __global__ void __launch_bounds__(256) k_em(PdDev a, EmArgs e)
         }
         sF = loF; sL = loL;
     }
-    if (sF == 0 && sL == 0) return;
+    if (sF == 0 && sL == 0) { reject(4); return; }
     const double lr = block_lr(a, sh, dlx, sh.gt);
-    __shared__ uint32_t s_slot;
     if (tid == 0) {
-        s_slot = 0xFFFFFFFFu;
-        if (lr >= e.min_lr) {
-            const uint32_t slot = atomicAdd(&e.counters[CNT_CALLS], 1u);
-            if (slot < e.out_cap) {
-                s_slot = slot;
-                pd_call c;
-                c.initial_length = L0; c.iterations = sh.it; c.deletion_length = sh.len;
-                c.filter = ((double)ndata / a.N >= e.min_sample_fraction) ? 0u : 4u;
-                c.lr = lr; c.frequency = sh.freq;
-                const uint32_t cur = e.anchor + w * PD_WIN;
-                c.window_position = cur - 1;
-                c.position = e.window_wise ? cur - 1 : sF;
-                c.end_position = e.window_wise ? 0u : sL;
-                c.segment = (uint32_t)(((uint64_t)w * PD_WIN) / a.window_buffer);
-                e.out_calls[slot] = c;
-            }
+        const bool ok = lr >= e.min_lr;
+        e.valid[blockIdx.x] = ok ? 1 : 0;
+        if (e.dbg) { e.dbg[4 * blockIdx.x] = ok ? 0 : 5; e.dbg[4 * blockIdx.x + 1] = sh.len; e.dbg[4 * blockIdx.x + 2] = sh.it; e.dbg[4 * blockIdx.x + 3] = (uint32_t)supp; }
+        if (ok) {
+            pd_call c;
+            c.initial_length = L0; c.iterations = sh.it; c.deletion_length = sh.len;
+            c.filter = ((double)ndata / a.N >= e.min_sample_fraction) ? 0u : 4u;
+            c.lr = lr; c.frequency = sh.freq;
+            const uint32_t cur = e.anchor + w * PD_WIN;
+            c.window_position = cur - 1;
+            c.position = e.window_wise ? cur - 1 : sF;
+            c.end_position = e.window_wise ? 0u : sL;
+            c.segment = (uint32_t)(((uint64_t)w * PD_WIN) / a.window_buffer);
+            e.calls[blockIdx.x] = c;
         }
     }
-    __syncthreads();
-    if (s_slot != 0xFFFFFFFFu) {
-        uint32_t * dst = e.out_ps + (size_t)s_slot * 13 * a.N;
-        for (uint32_t i = tid; i < 13 * a.N; i += blockDim.x) dst[i] = ps[i];
-    }
+}
+
+// gathers the per-sample rows of the valid pairs: out[k] = ps[idx[k]]
+__global__ void __launch_bounds__(256) k_compact(const uint32_t * __restrict__ ps, const uint32_t * __restrict__ idx,
+                                                 uint32_t * __restrict__ out, uint32_t row_words)
+{
+    const uint32_t * src = ps + (size_t)idx[blockIdx.x] * row_words;
+    uint32_t * dst = out + (size_t)blockIdx.x * row_words;
+    for (uint32_t i = threadIdx.x; i < row_words; i += blockDim.x) dst[i] = src[i];
 }
 
 template <typename T>
@@ -804,17 +854,19 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
     const uint64_t total = c->n_windows_total;
     uint64_t w_begin = std::min<uint64_t>(first_window, total);
     uint64_t w_end = n_windows ? std::min<uint64_t>(first_window + n_windows, total) : total;
-    c->res_calls.clear(); c->res_ps.clear();
+    c->res_calls.clear();
     out->n_reads = c->n_reads;
     out->algorithmic_bytes = 4ull * c->n_reads;
     out->h2d_bytes = c->h2d_bytes;
-    if (w_end <= w_begin) { out->calls = c->res_calls.data(); out->per_sample = c->res_ps.data(); return 0; }
+    out->calls = c->res_calls.data(); out->per_sample = c->res_ps;
+    if (w_end <= w_begin) return 0;
     const uint32_t N = c->N, R = c->R;
     const uint32_t W = (uint32_t)(w_end - w_begin);
+    const size_t row = 13ull * N;
 
     PdDev a;
-    a.words = c->d_words; a.tile_off = c->d_tile_off; a.longs = c->d_longs; a.long_off = c->d_long_off; a.long_span = c->d_long_span;
-    a.rgc = c->d_rgc; a.sample_rg = c->d_sample_rg; a.tab_val = c->d_tab_val; a.tab_ln = c->d_tab_ln; a.tab_l10 = c->d_tab_l10;
+    a.words = c->d_words; a.tiles = c->d_tiles; a.longs = c->d_longs;
+    a.rgc = c->d_rgc; a.sample_rg = c->d_sample_rg; a.tab = c->d_tab;
     a.NT = c->NT; a.N = N; a.R = R; a.window_buffer = c->grid.window_buffer; a.t_min = c->t_min;
     a.w_begin = (uint32_t)w_begin; a.w_end = (uint32_t)w_end;
 
@@ -830,7 +882,8 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
     const uint32_t tile_end = (uint32_t)std::min<uint64_t>((w_end + PD_TILE_WINDOWS - 1) / PD_TILE_WINDOWS, c->NT);
     PD_CUDA(c, cudaEventRecord(c->ev[3], st));
     {
-        dim3 grid((tile_end - tile_begin + 7) / 8, N);
+        const uint32_t tiles_per_block = 8 * SCREEN_TPW;
+        dim3 grid((tile_end - tile_begin + tiles_per_block - 1) / tiles_per_block, N);
         k_screen<<<grid, 256, 0, st>>>(a, tile_begin, tile_end, d_flags, d_jobs, d_counters);
         ++out->n_kernel_launches;
         PD_CUDA(c, cudaGetLastError());
@@ -855,105 +908,119 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
     const size_t job_bytes = 8ull * R + 5ull * N + 400ull * N;
     const uint32_t JB = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(3000000000ull / job_bytes, 64), 16384);
     const size_t pair_bytes = 24ull * N + 4ull * R + 52ull * N + 52ull * N;
-    const uint32_t PB = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(2000000000ull / pair_bytes, 64), 8192);
+    const uint32_t PB = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(3000000000ull / pair_bytes, 64), 32768);
     uint32_t npad = 1; while (npad < N) npad <<= 1;
     if ((size_t)npad * 4 > 200 * 1024) return pd_fail(c, PD_ERR_CAPACITY, "more than 51200 samples per context: candidate sort does not fit shared memory (shard by sample)");
     if ((size_t)npad * 4 > 48 * 1024)
         PD_CUDA(c, cudaFuncSetAttribute(k_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(npad * 4)));
     const uint32_t em_threads = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
-    uint64_t n_pairs_total = 0;
+    uint64_t n_pairs_total = 0, n_calls = 0;
     size_t pool_cap = std::max<size_t>((size_t)std::min<uint32_t>(JB, std::max(n_jobs, 1u)) * R * 40, 1u << 20);
+    const bool dbg = getenv("PD_DEBUG") != nullptr;
+    const int dbg_window = getenv("PD_DEBUG_WINDOW") ? atoi(getenv("PD_DEBUG_WINDOW")) : -1;
 
     for (uint32_t job0 = 0; job0 < n_jobs; job0 += JB) {
         const uint32_t nj = std::min(JB, n_jobs - job0);
-        uint32_t * d_act_off, * d_act_cnt; int32_t * d_q3; uint8_t * d_sstat; PoolEntry * d_pool; PdPair * d_pairs;
+        uint32_t * d_act_off, * d_act_cnt; int32_t * d_q3; uint8_t * d_sstat; PoolEntry * d_pool = nullptr; PdPair * d_pairs;
         if (grow_scratch(c, 3, d_act_off, (size_t)nj * R)) return c->status;
         if (grow_scratch(c, 4, d_act_cnt, (size_t)nj * R)) return c->status;
         if (grow_scratch(c, 5, d_q3, (size_t)nj * N)) return c->status;
         if (grow_scratch(c, 6, d_sstat, (size_t)nj * N)) return c->status;
         const uint32_t pair_cap = nj * 8 + 1024;
         if (grow_scratch(c, 8, d_pairs, (size_t)pair_cap)) return c->status;
-        uint32_t pool_used = 0;
-        for (int attempt = 0; attempt < 2; ++attempt) {
+        uint32_t n_pairs = 0;
+        for (int attempt = 0; ; ++attempt) {
             if (pool_cap > 0xFFFFFFF0ull) pool_cap = 0xFFFFFFF0ull;
             if (grow_scratch(c, 7, d_pool, pool_cap)) return c->status;
             PD_CUDA(c, cudaMemsetAsync(d_counters + CNT_PAIRS, 0, 2 * 4, st));      // pairs + pool cursor
             GatherArgs ga{d_jobs, job0, nj, d_pool, (uint32_t)pool_cap, d_counters, d_act_off, d_act_cnt, d_q3, d_sstat};
             k_gather<<<dim3(nj, (N + 3) / 4), 128, 0, st>>>(a, ga);
-            ++out->n_kernel_launches;
+            k_candidates<<<nj, 256, npad * 4, st>>>(a, d_q3, d_sstat, job0, d_counters, d_pairs, pair_cap, npad);
+            out->n_kernel_launches += 2;
             PD_CUDA(c, cudaGetLastError());
             PD_CUDA(c, cudaMemcpyAsync(h_cnt, d_counters, 16 * 4, cudaMemcpyDeviceToHost, st));
             PD_CUDA(c, cudaStreamSynchronize(st));
-            pool_used = h_cnt[CNT_POOL];
-            if (pool_used <= pool_cap) break;
+            if (h_cnt[CNT_POOL] <= pool_cap) { n_pairs = h_cnt[CNT_PAIRS]; break; }
             if (attempt == 1) return pd_fail(c, PD_ERR_CAPACITY, "active read-pair pool overflow");
-            pool_cap = (size_t)pool_used + 1024;
+            pool_cap = (size_t)h_cnt[CNT_POOL] + 1024;                              // exact size known now: run again
         }
-        k_candidates<<<nj, 256, npad * 4, st>>>(a, d_q3, d_sstat, job0, d_counters, d_pairs, pair_cap, npad);
-        ++out->n_kernel_launches;
-        PD_CUDA(c, cudaGetLastError());
-        PD_CUDA(c, cudaMemcpyAsync(h_cnt, d_counters, 16 * 4, cudaMemcpyDeviceToHost, st));
-        PD_CUDA(c, cudaStreamSynchronize(st));
-        const uint32_t n_pairs = h_cnt[CNT_PAIRS];
         if (n_pairs > pair_cap) return pd_fail(c, PD_ERR_CAPACITY, "more than 8 candidate lengths per flagged window on average");
+        // deterministic order: (window, initial length)
+        std::vector<PdPair> h_pairs(n_pairs);
+        if (n_pairs) {
+            PD_CUDA(c, cudaMemcpyAsync(h_pairs.data(), d_pairs, (size_t)n_pairs * sizeof(PdPair), cudaMemcpyDeviceToHost, st));
+            PD_CUDA(c, cudaStreamSynchronize(st));
+            std::sort(h_pairs.begin(), h_pairs.end(), [](const PdPair & x, const PdPair & y) { return x.job != y.job ? x.job < y.job : x.L0 < y.L0; });
+            PD_CUDA(c, cudaMemcpyAsync(d_pairs, h_pairs.data(), (size_t)n_pairs * sizeof(PdPair), cudaMemcpyHostToDevice, st));
+        }
         n_pairs_total += n_pairs;
         for (uint32_t p0 = 0; p0 < n_pairs; p0 += PB) {
             const uint32_t np = std::min(PB, n_pairs - p0);
-            double * d_dlx; int32_t * d_shifts; uint32_t * d_ps; pd_call * d_out_calls; uint32_t * d_out_ps;
+            double * d_dlx; int32_t * d_shifts; uint32_t * d_ps, * d_idx, * d_out_ps; pd_call * d_calls; uint8_t * d_valid;
             if (grow_scratch(c, 9, d_dlx, (size_t)np * 3 * N)) return c->status;
             if (grow_scratch(c, 10, d_shifts, (size_t)np * R)) return c->status;
-            if (grow_scratch(c, 11, d_ps, (size_t)np * 13 * N)) return c->status;
-            if (grow_scratch(c, 12, d_out_calls, (size_t)np)) return c->status;
-            if (grow_scratch(c, 13, d_out_ps, (size_t)np * 13 * N)) return c->status;
-            PD_CUDA(c, cudaMemsetAsync(d_counters + CNT_CALLS, 0, 4, st));
+            if (grow_scratch(c, 11, d_ps, (size_t)np * row)) return c->status;
+            if (grow_scratch(c, 12, d_calls, (size_t)np)) return c->status;
+            if (grow_scratch(c, 13, d_out_ps, (size_t)np * row)) return c->status;
+            if (grow_scratch(c, 15, d_idx, (size_t)np)) return c->status;
+            if (grow_scratch(c, 14, d_valid, (size_t)np + (dbg ? (size_t)np * 16 : 0))) return c->status;
             EmArgs e;
             e.jobs = d_jobs; e.pairs = d_pairs; e.pair0 = p0; e.npairs = np; e.job_base = job0;
             e.pool = d_pool; e.act_off = d_act_off; e.act_cnt = d_act_cnt; e.sstat = d_sstat;
-            e.dlx = d_dlx; e.shifts = d_shifts; e.ps = d_ps; e.counters = d_counters;
-            e.out_calls = d_out_calls; e.out_ps = d_out_ps; e.out_cap = np;
+            e.dlx = d_dlx; e.shifts = d_shifts; e.ps = d_ps; e.calls = d_calls; e.valid = d_valid;
             e.iterations = c->params.iterations; e.min_len = c->params.min_len; e.min_lr = c->params.min_lr;
             e.min_sample_fraction = c->params.min_sample_fraction; e.somatic = c->params.somatic; e.window_wise = c->params.window_wise;
             e.anchor = c->grid.anchor;
+            e.dbg = nullptr; e.dbg_window = dbg_window;
+            if (dbg) {
+                e.dbg = reinterpret_cast<uint32_t *>(d_valid + (((size_t)np + 15) & ~(size_t)15) - 0);
+                if ((((size_t)np + 15) & ~(size_t)15) + (size_t)np * 16 > c->cap_scratch[14]) e.dbg = nullptr;
+                else PD_CUDA(c, cudaMemsetAsync(e.dbg, 0xFF, (size_t)np * 16, st));
+            }
             k_em<<<np, em_threads, 0, st>>>(a, e);
             ++out->n_kernel_launches;
             PD_CUDA(c, cudaGetLastError());
-            PD_CUDA(c, cudaMemcpyAsync(h_cnt, d_counters, 16 * 4, cudaMemcpyDeviceToHost, st));
+            std::vector<uint8_t> h_valid(np);
+            std::vector<pd_call> h_calls(np);
+            PD_CUDA(c, cudaMemcpyAsync(h_valid.data(), d_valid, np, cudaMemcpyDeviceToHost, st));
+            PD_CUDA(c, cudaMemcpyAsync(h_calls.data(), d_calls, (size_t)np * sizeof(pd_call), cudaMemcpyDeviceToHost, st));
             PD_CUDA(c, cudaStreamSynchronize(st));
-            const uint32_t nc = h_cnt[CNT_CALLS];
+            if (e.dbg) {
+                std::vector<uint32_t> hd((size_t)np * 4);
+                cudaMemcpy(hd.data(), e.dbg, (size_t)np * 16, cudaMemcpyDeviceToHost);
+                for (uint32_t i = 0; i < np; ++i)
+                    fprintf(stderr, "PD_DEBUG pair window %u L0 %d reason %u len %u it %u supp %u\n", h_jobs[h_pairs[p0 + i].job], h_pairs[p0 + i].L0, hd[4 * i], hd[4 * i + 1], hd[4 * i + 2], hd[4 * i + 3]);
+            }
+            std::vector<uint32_t> idx;
+            idx.reserve(np);
+            for (uint32_t i = 0; i < np; ++i) if (h_valid[i]) { idx.push_back(i); c->res_calls.push_back(h_calls[i]); }
+            const uint32_t nc = (uint32_t)idx.size();
             if (nc) {
-                size_t o = c->res_calls.size();
-                c->res_calls.resize(o + nc);
-                c->res_ps.resize((o + nc) * 13ull * N);
-                PD_CUDA(c, cudaMemcpyAsync(c->res_calls.data() + o, d_out_calls, (size_t)nc * sizeof(pd_call), cudaMemcpyDeviceToHost, st));
-                PD_CUDA(c, cudaMemcpyAsync(c->res_ps.data() + o * 13ull * N, d_out_ps, (size_t)nc * 13 * N * 4, cudaMemcpyDeviceToHost, st));
+                const size_t need = (n_calls + nc) * row;
+                if (need > c->cap_res_ps) {                       // grow the pinned result buffer
+                    size_t want = std::max<size_t>(need + need / 2, 1u << 20);
+                    uint32_t * p = nullptr;
+                    PD_CUDA(c, cudaMallocHost(&p, want * 4));
+                    if (n_calls) memcpy(p, c->res_ps, n_calls * row * 4);
+                    if (c->res_ps) cudaFreeHost(c->res_ps);
+                    c->res_ps = p; c->cap_res_ps = want;
+                }
+                PD_CUDA(c, cudaMemcpyAsync(d_idx, idx.data(), (size_t)nc * 4, cudaMemcpyHostToDevice, st));
+                k_compact<<<nc, 256, 0, st>>>(d_ps, d_idx, d_out_ps, (uint32_t)row);
+                ++out->n_kernel_launches;
+                PD_CUDA(c, cudaGetLastError());
+                PD_CUDA(c, cudaMemcpyAsync(c->res_ps + n_calls * row, d_out_ps, (size_t)nc * row * 4, cudaMemcpyDeviceToHost, st));
                 PD_CUDA(c, cudaStreamSynchronize(st));
-                out->d2h_bytes += (uint64_t)nc * (sizeof(pd_call) + 13ull * N * 4);
+                out->d2h_bytes += (uint64_t)nc * (sizeof(pd_call) + row * 4);
+                n_calls += nc;
             }
         }
     }
     PD_CUDA(c, cudaEventRecord(c->ev[5], st));
     PD_CUDA(c, cudaStreamSynchronize(st));
-    // order: (window, initial length) = the reference's emission order
-    {
-        const size_t nc = c->res_calls.size();
-        std::vector<uint32_t> idx(nc);
-        std::iota(idx.begin(), idx.end(), 0u);
-        std::sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) {
-            const pd_call & p = c->res_calls[x], & q = c->res_calls[y];
-            if (p.window_position != q.window_position) return p.window_position < q.window_position;
-            return p.initial_length < q.initial_length;
-        });
-        std::vector<pd_call> sc(nc);
-        std::vector<uint32_t> sp(nc * 13ull * N);
-        for (size_t i = 0; i < nc; ++i) {
-            sc[i] = c->res_calls[idx[i]];
-            memcpy(&sp[i * 13ull * N], &c->res_ps[(size_t)idx[i] * 13ull * N], 13ull * N * 4);
-        }
-        c->res_calls.swap(sc); c->res_ps.swap(sp);
-    }
     out->n_calls = c->res_calls.size();
     out->calls = c->res_calls.data();
-    out->per_sample = c->res_ps.data();
+    out->per_sample = c->res_ps;
     out->n_candidates = n_pairs_total;
     PD_CUDA(c, cudaEventElapsedTime(&out->ms_screen, c->ev[3], c->ev[4]));
     PD_CUDA(c, cudaEventElapsedTime(&out->ms_genotype, c->ev[4], c->ev[5]));
