@@ -122,7 +122,7 @@ def measured_peak_gbs():
 # ----------------------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
     import torch
-    from popdel_b200 import api
+    from popdel_b200 import api, sharding
     dist = None
     if world > 1:
         import torch.distributed as dist_
@@ -169,15 +169,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     dt = time.perf_counter() - t0
     clk = clocks.stop()
-    if dist is not None:
-        tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        ev = torch.tensor([evals], device="cuda", dtype=torch.float64)
-        dist.all_reduce(ev, op=dist.ReduceOp.SUM)
-        evals_all = float(ev.item())
-    else:
-        evals_all = float(evals)
+    dt, evals_all = sharding.reduce_timing(dt, float(evals), dist, "cuda")      # max over ranks / sum over ranks
     value = evals_all * args.steps / dt
 
     # ---- end to end through the C ABI from host arrays (pack -> pinned -> H2D -> scan -> D2H)
@@ -191,10 +183,7 @@ def run_ours(args, rank, world, local_rank):
         r2 = sc.scan(copy=False)
     barrier()
     dt2 = time.perf_counter() - t0
-    if dist is not None:
-        tt = torch.tensor([dt2], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt2 = float(tt.item())
+    dt2, _ = sharding.reduce_timing(dt2, float(evals), dist, "cuda")
     e2e = evals_all * e2e_steps / dt2
 
     if rank != 0:

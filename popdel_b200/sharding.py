@@ -1,0 +1,51 @@
+"""Window-range sharding of the scan across ranks: contiguous ranges cut at the reference's segment
+borders, so every `processSegment` group of calls lives on exactly one rank and `unifyCalls` behaves as in a
+single-process run. No data-path collective: ranks only exchange their (small) call lists and timing scalars."""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import numpy as np
+
+
+def segment_last_window(j: int, window_buffer: int) -> int:
+    """Last window index of segment j (largest w with 30*w < (j+1)*window_buffer); = pd_seg_last_window."""
+    return ((j + 1) * window_buffer - 1) // 30
+
+
+def segment_aligned_ranges(n_windows: int, window_buffer: int, world: int) -> List[Tuple[int, int]]:
+    """Splits windows [0, n_windows) into `world` contiguous (first_window, count) ranges whose cuts fall on
+    segment borders; segments are dealt out as evenly as possible (rank r gets segments [r*S/world, (r+1)*S/world))."""
+    if n_windows <= 0:
+        return [(0, 0)] * world
+    n_seg = (30 * (n_windows - 1)) // window_buffer + 1
+    out = []
+    for r in range(world):
+        s0, s1 = (r * n_seg) // world, ((r + 1) * n_seg) // world
+        w0 = 0 if s0 == 0 else segment_last_window(s0 - 1, window_buffer) + 1
+        w1 = n_windows if s1 >= n_seg else min(n_windows, segment_last_window(s1 - 1, window_buffer) + 1)
+        out.append((w0, max(0, w1 - w0)) if s1 > s0 else (w0, 0))
+    return out
+
+
+def gather_calls(calls: np.ndarray, per_sample: np.ndarray, rank: int, world: int, dist=None):
+    """Host-side merge of the per-rank call lists on rank 0, in genomic order (ranks hold ascending ranges)."""
+    if world == 1 or dist is None:
+        return calls, per_sample
+    objs = [None] * world if rank == 0 else None
+    dist.gather_object((calls, per_sample), objs, dst=0)
+    if rank != 0:
+        return None, None
+    return np.concatenate([o[0] for o in objs]), np.concatenate([o[1] for o in objs])
+
+
+def reduce_timing(elapsed_s: float, evaluations: float, dist=None, device=None):
+    """(max elapsed over ranks, sum of evaluations over ranks) -- the bench contract's whole-job aggregate."""
+    if dist is None:
+        return elapsed_s, evaluations
+    import torch
+    t = torch.tensor([elapsed_s], dtype=torch.float64, device=device)
+    e = torch.tensor([evaluations], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(e, op=dist.ReduceOp.SUM)
+    return float(t.item()), float(e.item())

@@ -46,8 +46,14 @@ def test_scan_window_ranges_partition_the_contig(oracle_lib):
     params = api.CallParameters()
     full, rgs = api.scan_cohort(samples, params)
     n = full["n_windows"]
-    cuts = [0, 6667, 9000, n]
-    parts = [api.scan_cohort(samples, params, first_window=a, n_windows=b - a)[0] for a, b in zip(cuts[:-1], cuts[1:])]
+    from popdel_b200.sharding import segment_aligned_ranges
+    ranges = segment_aligned_ranges(n, params.window_buffer, 3)           # segment-aligned shards of 3 ranks
+    assert [r[0] for r in ranges] == [0, 6667, 13334]
+    parts = [api.scan_cohort(samples, params, first_window=a, n_windows=c)[0] for a, c in ranges]
+    odd = [(0, 5000), (5000, 4000), (9000, n - 9000)]                     # arbitrary cuts work too
+    parts2 = [api.scan_cohort(samples, params, first_window=a, n_windows=c)[0] for a, c in odd]
+    assert_calls_equal(np.concatenate([p["calls"] for p in parts2]), np.concatenate([p["per_sample"] for p in parts2]),
+                       full["calls"], full["per_sample"], rtol=0)
     calls = np.concatenate([p["calls"] for p in parts])
     ps = np.concatenate([p["per_sample"] for p in parts])
     assert sum(p["n_windows"] for p in parts) == n

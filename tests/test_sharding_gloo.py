@@ -1,0 +1,62 @@
+"""Multi-process host logic on CPU (gloo, world_size 2): segment-aligned window ranges partition the contig, the
+per-rank call lists merge into the single-process order, and the timing reduction is max / sum."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from popdel_b200 import api, sharding
+
+
+def test_ranges_cover_and_align():
+    for n_windows, wb, world in [(1557014, 200000, 8), (8659, 200000, 2), (6667, 200000, 4), (100, 960, 3), (0, 200000, 2)]:
+        r = sharding.segment_aligned_ranges(n_windows, wb, world)
+        assert len(r) == world and sum(c for _, c in r) == n_windows
+        pos = 0
+        for w0, c in r:
+            if c:
+                assert w0 == pos
+                pos += c
+                if pos < n_windows:                      # every cut is the first window of a segment
+                    assert (30 * pos) // wb == (30 * (pos - 1)) // wb + 1
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_windows, wb, N = 20000, 200000, 3
+    ranges = sharding.segment_aligned_ranges(n_windows, wb, world)
+    rng = np.random.default_rng(7)
+    win = np.sort(rng.choice(n_windows, size=200, replace=False))
+    calls = np.zeros(win.size, dtype=api.CALL_DTYPE)
+    calls["window_position"] = 30 * win + 29
+    calls["segment"] = (30 * win) // wb
+    ps = rng.integers(0, 50, size=(win.size, N, 13)).astype(np.uint32)
+    w0, c = ranges[rank]
+    mine = (win >= w0) & (win < w0 + c)
+    got_c, got_p = sharding.gather_calls(calls[mine], ps[mine], rank, world, dist)
+    t, e = sharding.reduce_timing(1.0 + rank, float(c * N), dist)
+    if rank == 0:
+        q.put((np.array_equal(got_c, calls), np.array_equal(got_p, ps), t, e, n_windows * N))
+    dist.destroy_process_group()
+
+
+def test_gather_and_reduce_world2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    same_calls, same_ps, t, e, total = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert same_calls and same_ps
+    assert t == 2.0 and e == total
