@@ -186,6 +186,9 @@ def run_ours(args, rank, world, local_rank):
     dt2, _ = sharding.reduce_timing(dt2, float(evals), dist, "cuda")
     e2e = evals_all * e2e_steps / dt2
 
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peak, peak_src = measured_peak_gbs()

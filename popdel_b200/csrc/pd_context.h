@@ -87,7 +87,8 @@ struct pd_ctx {
     uint64_t n_reads = 0;
 
     // device
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: result compaction + D2H, overlapped with the EM
+    std::vector<uint32_t> idx_stage[2];
     cudaEvent_t ev[8] = {};
     uint32_t * d_words = nullptr; size_t cap_words = 0;
     PdTile * d_tiles = nullptr; size_t cap_tiles = 0;
@@ -96,7 +97,7 @@ struct pd_ctx {
     uint32_t * d_sample_rg = nullptr;
     PdTab * d_tab = nullptr;
     // scan scratch (grown on demand)
-    void * d_scratch[16] = {}; size_t cap_scratch[16] = {};
+    void * d_scratch[24] = {}; size_t cap_scratch[24] = {};
     // results
     std::vector<pd_call> res_calls;
     uint32_t * res_ps = nullptr; size_t cap_res_ps = 0;    // pinned

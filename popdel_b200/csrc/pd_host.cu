@@ -175,7 +175,8 @@ extern "C" pd_ctx * pd_create(const pd_params * p, uint32_t n_samples, uint32_t 
                              "); this library has no CPU scan path";
             delete c; return nullptr;
         }
-        if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) {
             g_create_error = "pd_create: cudaSetDevice/cudaStreamCreate failed"; delete c; return nullptr;
         }
         for (auto & ev : c->ev) cudaEventCreate(&ev);
@@ -195,6 +196,7 @@ extern "C" void pd_destroy(pd_ctx * c)
         for (auto & p : c->d_scratch) cudaFree(p);
         for (auto & ev : c->ev) if (ev) cudaEventDestroy(ev);
         if (c->stream) cudaStreamDestroy(c->stream);
+        if (c->stream2) cudaStreamDestroy(c->stream2);
     }
     for (auto & h : c->hrg) free_words(c, h);
     delete c;
@@ -260,67 +262,79 @@ extern "C" int pd_contig_push(pd_ctx * c, uint32_t rg, uint64_t n, const uint32_
     int64_t wl = h.seg < 0 ? -1 : (int64_t)pd_seg_last_window((uint64_t)h.seg, wb);
     int64_t wl2 = h.seg < 0 ? -1 : (int64_t)pd_seg_last_window((uint64_t)h.seg + 1, wb);
     uint32_t * words = h.words;
-    size_t nw = h.n_words;
+    size_t nw = h.n_words, cap = h.cap_words;
+    const int32_t inner_off = k.inner_off;
+    const uint32_t lookback = k.lookback_tiles, max_load = k.max_load;
+    if (capped && h.ring.empty()) { h.ring.assign(PD_CAP_RING, 0u); h.ring_b = 0; h.open = 0; }
+    uint32_t * ring = capped ? h.ring.data() : nullptr;
+    uint32_t ring_b = h.ring_b, open = h.open, cur_tile = h.cur_tile, last_pos = h.last_pos;
+    int64_t S = h.S, E_own = h.E_own, E_spill = h.E_spill;
+    uint64_t n_reads = h.n_reads, dropped = h.dropped;
+    bool any = h.any;
+    int rc = 0;
     for (uint64_t i = 0; i < n; ++i) {
         const uint32_t p = pos[i];
-        if (p < anchor) return pd_fail(c, PD_ERR_ARG, "pd_contig_push: position before the contig anchor");
-        if (h.any && p < h.last_pos) return pd_fail(c, PD_ERR_ORDER, "pd_contig_push: read pairs must be sorted by position");
-        h.any = true; h.last_pos = p;
+        if (p < anchor) { rc = pd_fail(c, PD_ERR_ARG, "pd_contig_push: position before the contig anchor"); break; }
+        if (any && p < last_pos) { rc = pd_fail(c, PD_ERR_ORDER, "pd_contig_push: read pairs must be sorted by position"); break; }
+        any = true; last_pos = p;
         const uint32_t pr = p - anchor;
         const uint32_t b = pr / PD_WIN, bp = b * PD_WIN;
         const int32_t d = dev[i];
-        int64_t inner = (int64_t)d + k.inner_off;
+        int64_t inner = (int64_t)d + inner_off;
         if (inner < 0) inner = 0;
-        const int64_t lw = (int64_t)((pr + (uint64_t)inner) / PD_WIN);
+        const uint64_t endp = (uint64_t)pr + (uint64_t)inner;
+        const int64_t lw = endp < 0xFFFFFFFFull ? (int64_t)((uint32_t)endp / PD_WIN) : (int64_t)(endp / PD_WIN);
         if (capped) {
-            if (h.ring.empty()) { h.ring.assign(PD_CAP_RING, 0u); h.ring_b = b; h.open = 0; }
-            if (b - h.ring_b >= PD_CAP_RING) {                      // everything in the ring is closed
-                std::fill(h.ring.begin(), h.ring.end(), 0u);
-                h.open = (uint32_t)h.far.size(); h.ring_b = b;
+            if (b - ring_b >= PD_CAP_RING) {                        // everything in the ring is closed
+                if (open != h.far.size()) std::fill(ring, ring + PD_CAP_RING, 0u);
+                open = (uint32_t)h.far.size(); ring_b = b;
             }
-            while (h.ring_b < b) { uint32_t & c0 = h.ring[h.ring_b % PD_CAP_RING]; h.open -= c0; c0 = 0; ++h.ring_b; }
-            while (!h.far.empty() && h.far.front() < b) { std::pop_heap(h.far.begin(), h.far.end(), std::greater<uint32_t>()); h.far.pop_back(); --h.open; }
-            if (h.open >= k.max_load) { ++h.dropped; continue; }
+            while (ring_b < b) { uint32_t & c0 = ring[ring_b & (PD_CAP_RING - 1)]; open -= c0; c0 = 0; ++ring_b; }
+            while (!h.far.empty() && h.far.front() < b) { std::pop_heap(h.far.begin(), h.far.end(), std::greater<uint32_t>()); h.far.pop_back(); --open; }
+            if (open >= max_load) { ++dropped; continue; }
             const uint32_t lwc = (uint32_t)std::min<int64_t>(lw, 0xFFFFFFFF);
-            if (lwc - b < PD_CAP_RING) ++h.ring[lwc % PD_CAP_RING];
+            if (lwc - b < PD_CAP_RING) ++ring[lwc & (PD_CAP_RING - 1)];
             else { h.far.push_back(lwc); std::push_heap(h.far.begin(), h.far.end(), std::greater<uint32_t>()); }
-            ++h.open;
+            ++open;
         }
-        if (h.seg < 0 || bp >= seg_end_bp) {                       // first read pair of a new segment
+        if (bp >= seg_end_bp || h.seg < 0) {                        // first read pair of a new segment
             const int64_t j = (int64_t)((uint64_t)bp / wb);
-            if (h.seg >= 0) { h.prev_seg = h.seg; h.prev_E_spill = h.E_spill; }
-            h.seg = j; h.S = h.E_own = h.E_spill = -1;
+            if (h.seg >= 0) { h.prev_seg = h.seg; h.prev_E_spill = E_spill; }
+            h.seg = j; S = E_own = E_spill = -1;
             seg_end_bp = (uint64_t)(j + 1) * wb;
             wl = (int64_t)pd_seg_last_window((uint64_t)j, wb);
             wl2 = (int64_t)pd_seg_last_window((uint64_t)j + 1, wb);
         }
-        h.S = std::max<int64_t>(h.S, pr);
-        if (lw <= wl) h.E_own = std::max(h.E_own, lw); else h.E_spill = std::max(h.E_spill, lw);
+        S = pr;                                                     // positions are sorted
+        if (lw <= wl) { if (lw > E_own) E_own = lw; } else if (lw > E_spill) E_spill = lw;
         const int64_t s = (int64_t)b + (pr != bp ? 1 : 0);
         int64_t e = lw + 1;
         const bool act = s <= wl;
-        if (act) { const int64_t cap = lw <= wl ? wl : wl2; if (e > cap) e = cap; }
-        const uint32_t t = pr / PD_TILE_BP;
-        if (t != h.cur_tile) {
+        if (act) { const int64_t capw = lw <= wl ? wl : wl2; if (e > capw) e = capw; }
+        const uint32_t t = b / PD_TILE_WINDOWS;
+        if (t != cur_tile) {
             while (nw & 3) words[nw++] = PD_PAD_WORD;
-            while (h.cur_tile < t) { ++h.cur_tile; h.tile_rel.push_back((uint32_t)nw); }
+            while (cur_tile < t) { ++cur_tile; h.tile_rel.push_back((uint32_t)nw); }
         }
         bool is_long = d > PD_DEV_MAX || d < PD_DEV_MIN + 1;
-        if (act && (uint64_t)e / PD_TILE_WINDOWS > (uint64_t)t + k.lookback_tiles) is_long = true;
+        if (act && (uint64_t)e / PD_TILE_WINDOWS > (uint64_t)t + lookback) is_long = true;
         const int32_t dc = d > PD_DEV_MAX ? PD_DEV_MAX : (d < PD_DEV_MIN + 1 ? PD_DEV_MIN + 1 : d);
-        if (nw + 8 > h.cap_words) {                                 // padding can outgrow the reservation
+        if (nw + 8 > cap) {                                         // padding can outgrow the reservation
             h.n_words = nw;
-            if (!reserve_words(c, h, nw + (n - i) + (n - i) / 8 + 64)) return pd_fail(c, PD_ERR_CUDA, "pd_contig_push: out of (pinned) host memory");
-            words = h.words;
+            if (!reserve_words(c, h, nw + (n - i) + (n - i) / 8 + 64)) { rc = pd_fail(c, PD_ERR_CUDA, "pd_contig_push: out of (pinned) host memory"); break; }
+            words = h.words; cap = h.cap_words;
         }
         words[nw++] = pd_pack(dc, pr - t * PD_TILE_BP, is_long);
         if (is_long && act) {
             h.longs.push_back(PdLong{(uint32_t)s, (uint32_t)e, pr, d});
             h.long_span = std::max<uint32_t>(h.long_span, (uint32_t)(e - s + 1));
         }
-        ++h.n_reads;
-        if (nw > 0xFFFFFFF0ull) return pd_fail(c, PD_ERR_CAPACITY, "more than 2^32 packed words in one read group");
+        ++n_reads;
+        if (nw > 0xFFFFFFF0ull) { rc = pd_fail(c, PD_ERR_CAPACITY, "more than 2^32 packed words in one read group"); break; }
     }
+    h.ring_b = ring_b; h.open = open; h.cur_tile = cur_tile; h.last_pos = last_pos; h.any = any;
+    h.S = S; h.E_own = E_own; h.E_spill = E_spill; h.n_reads = n_reads; h.dropped = dropped;
+    if (rc) { h.n_words = nw; return rc; }
     h.n_words = nw;
     return 0;
 }

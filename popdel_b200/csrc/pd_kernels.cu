@@ -239,61 +239,69 @@ __device__ __forceinline__ void for_active_batches(const PdDev & a, uint32_t g, 
     }
 }
 
+constexpr int GATHER_STAGE = 96;                                   // staged read pairs per warp (shared memory)
+
 __global__ void __launch_bounds__(128) k_gather(PdDev a, GatherArgs ga)
 {
-    const int lane = threadIdx.x & 31;
+    __shared__ PoolEntry stage[4][GATHER_STAGE];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t job = blockIdx.x;
-    const uint32_t smp = blockIdx.y * 4 + (threadIdx.x >> 5);
+    const uint32_t smp = blockIdx.y * 4 + wib;
     if (smp >= a.N) return;
     const int32_t w = (int32_t)ga.jobs[ga.job0 + job];
     const uint32_t g0 = a.sample_rg[smp], g1 = a.sample_rg[smp + 1];
     uint32_t * cnt = ga.act_cnt + (size_t)job * a.R;
     uint32_t * off = ga.act_off + (size_t)job * a.R;
+    PoolEntry * st = stage[wib];
 
-    // pass 1: counts
+    // single pass: count per read group and stage the usable read pairs in shared memory (stream order)
     uint32_t cov = 0, nvals = 0;
+    bool overflow = false;
     for (uint32_t g = g0; g < g1; ++g) {
+        const uint32_t max_load = __ldg(&a.rgc[g].max_load);
         const PdRgConst k = a.rgc[g];
         uint32_t n_g = 0;
-        for_active_batches(a, g, k, w, lane, [&](bool valid, uint32_t, int32_t) { n_g += __popc(__ballot_sync(FULL, valid)); });
-        if (lane == 0) cnt[g] = n_g;
+        const uint32_t start = nvals;
+        for_active_batches(a, g, k, w, lane, [&](bool valid, uint32_t pr, int32_t dev) {
+            const uint32_t mask = __ballot_sync(FULL, valid);
+            const uint32_t slot = start + n_g + __popc(mask & ((1u << lane) - 1u));
+            if (valid && slot < (uint32_t)GATHER_STAGE) st[slot] = PoolEntry{pr, dev};
+            n_g += __popc(mask);
+        });
+        if (lane == 0) { cnt[g] = n_g; off[g] = start; }                 // off = offset inside the sample's segment for now
         cov += n_g;
-        if (n_g < k.max_load) nvals += n_g;
+        if (n_g < max_load) { nvals += n_g; if (nvals > (uint32_t)GATHER_STAGE) overflow = true; }
     }
     uint32_t base = 0;
     if (lane == 0 && nvals) base = atomicAdd(&ga.counters[CNT_POOL], nvals);
     base = __shfl_sync(FULL, base, 0);
     const bool fits = (uint64_t)base + nvals <= ga.pool_cap;
-    // pass 2: entries (stream order); the first 32 values also stay in registers (lane i holds value i) for the Q3
-    uint32_t cur = base;
-    int32_t myval = INT_MAX;
-    for (uint32_t g = g0; g < g1; ++g) {
-        const PdRgConst k = a.rgc[g];
-        if (lane == 0) off[g] = cur;
-        const uint32_t n_g = __shfl_sync(FULL, lane == 0 ? cnt[g] : 0u, 0);
-        if (n_g >= k.max_load || !fits) continue;
-        for_active_batches(a, g, k, w, lane, [&](bool valid, uint32_t pr, int32_t dev) {
-            const uint32_t mask = __ballot_sync(FULL, valid);
-            const uint32_t slot = cur - base + __popc(mask & ((1u << lane) - 1u));
-            if (valid) ga.pool[base + slot] = PoolEntry{pr, dev};
-            uint32_t m = mask;
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const uint32_t sl = __shfl_sync(FULL, slot, src);
-                const int32_t dv = __shfl_sync(FULL, dev, src);
-                if (sl == (uint32_t)lane) myval = dv;
+    __syncwarp();
+    if (lane == 0) for (uint32_t g = g0; g < g1; ++g) off[g] += base;
+    if (fits) {
+        if (!overflow) {
+            for (uint32_t i = lane; i < nvals; i += 32) ga.pool[base + i] = st[i];
+        } else {                                                         // rare: more usable pairs than the stage holds
+            uint32_t cur = base;
+            for (uint32_t g = g0; g < g1; ++g) {
+                const PdRgConst k = a.rgc[g];
+                const uint32_t n_g = __shfl_sync(FULL, lane == 0 ? cnt[g] : 0u, 0);
+                if (n_g >= k.max_load) continue;
+                for_active_batches(a, g, k, w, lane, [&](bool valid, uint32_t pr, int32_t dev) {
+                    const uint32_t mask = __ballot_sync(FULL, valid);
+                    if (valid) ga.pool[cur + __popc(mask & ((1u << lane) - 1u))] = PoolEntry{pr, dev};
+                    cur += __popc(mask);
+                });
             }
-            cur += __popc(mask);
-        });
+        }
     }
     __syncwarp();
     // coverage state and Q3 (upperHalfMedian :15-27: n<4 -> maximum; else interpolate at (3n+2+n%2)/4-1)
-    uint8_t st; int32_t q = 0;
-    if (cov < 2u) st = 0;
-    else if (nvals == 0 || !fits) st = 1;
+    uint8_t stt; int32_t q = 0;
+    if (cov < 2u) stt = 0;
+    else if (nvals == 0 || !fits) stt = 1;
     else {
-        st = 2;
+        stt = 2;
         const uint32_t nn = nvals;
         uint32_t l; double r = 0;
         if (nn < 4) { l = nn - 1; }
@@ -301,17 +309,18 @@ __global__ void __launch_bounds__(128) k_gather(PdDev a, GatherArgs ga)
         const uint32_t l2 = (l + 1 < nn) ? l + 1 : l;
         int32_t lo_v = 0, hi_v = 0;
         if (nn <= 32) {
+            const int32_t myval = (uint32_t)lane < nn ? st[lane].dev : INT_MAX;
             uint32_t rank = 0;
-            for (int j = 0; j < 32; ++j) {
-                const int32_t vj = __shfl_sync(FULL, myval, j);
-                rank += ((uint32_t)j < nn) && ((vj < myval) || (vj == myval && j < lane));
+            for (uint32_t j = 0; j < nn; ++j) {
+                const int32_t vj = __shfl_sync(FULL, myval, (int)j);
+                rank += (vj < myval) || (vj == myval && (int)j < lane);
             }
             const uint32_t m1 = __ballot_sync(FULL, (uint32_t)lane < nn && rank == l);
             const uint32_t m2 = __ballot_sync(FULL, (uint32_t)lane < nn && rank == l2);
             lo_v = __shfl_sync(FULL, myval, __ffs(m1) - 1);
             hi_v = __shfl_sync(FULL, myval, __ffs(m2) - 1);
         } else {
-            const volatile PoolEntry * v = ga.pool + base;
+            const volatile PoolEntry * v = ga.pool + base;              // written above by this warp
             for (uint32_t i0 = 0; i0 < nn; i0 += 32) {
                 const uint32_t i = i0 + lane;
                 const int32_t vi = i < nn ? v[i].dev : INT_MAX;
@@ -326,7 +335,7 @@ __global__ void __launch_bounds__(128) k_gather(PdDev a, GatherArgs ga)
         if (nn < 4) q = (int32_t)floor((double)lo_v + 0.5);
         else q = (int32_t)floor((1 - r) * lo_v + r * hi_v + 0.5);
     }
-    if (lane == 0) { ga.q3[(size_t)job * a.N + smp] = q; ga.sstat[(size_t)job * a.N + smp] = st; }
+    if (lane == 0) { ga.q3[(size_t)job * a.N + smp] = q; ga.sstat[(size_t)job * a.N + smp] = stt; }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -467,44 +476,85 @@ __device__ __forceinline__ void finish_triple(double l0, double l1, double l2, u
     if (x0 == x1 && x0 == x2) { x0 = 0; x1 = LN1E10; x2 = LN1E10; }
 }
 
-// data likelihoods of every sample for (L, shifts) -> dlx; compute_data_likelihoods (EM overload) :179-253
-__device__ void compute_dl(const PdDev & a, const EmArgs & e, EmShared & sh, const uint32_t * cnt, const uint32_t * off,
-                           double * dlx, const int32_t * shifts, bool zero_shifts, uint32_t L)
+struct RgLite { int hist_base; uint32_t hist_len, hist_off, max_load; double min_prob; };
+__device__ __forceinline__ RgLite rg_lite(const PdRgConst * r)
 {
-    for (uint32_t s = threadIdx.x; s < a.N; s += blockDim.x) {
-        double l0 = 0, l1 = 0, l2 = 0;
-        uint32_t ndeg = 0;
+    RgLite k;
+    k.hist_base = __ldg(&r->hist_base); k.hist_len = __ldg(&r->hist_len); k.hist_off = __ldg(&r->hist_off);
+    k.max_load = __ldg(&r->max_load); k.min_prob = __ldg(&r->min_prob);
+    return k;
+}
+__device__ __forceinline__ const PdTab * tab_at(const PdTab * __restrict__ tab, const RgLite & k, int dev)
+{
+    const int i = dev + k.hist_base;
+    const bool in = i > 0 && i + 1 < (int)k.hist_len;
+    return tab + k.hist_off + (in ? i + 1 : 0);
+}
+
+// EM state handed from k_em to k_final
+struct EmState { uint32_t len, it, alive, pad; double freq; double gt[3]; };
+
+// ------------------------------------------------------------------------------------------------------------------
+// EM kernel: LPS lanes cooperate on one sample (read pairs strided over the lanes, fixed-order shuffle reduction);
+// the two table values of every read pair computed by the data-likelihood pass are cached in shared memory for the
+// length update of the next iteration (same deletion length and reference shifts -> identical look-ups).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int EM_CACHE_SLOTS = 8;
+
+template <int LPS>
+__device__ __forceinline__ double group_sum(double v, uint32_t gmask)
+{
+#pragma unroll
+    for (int o = LPS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+    return v;
+}
+
+// data likelihoods of every sample for (L, shifts) -> dlx; compute_data_likelihoods (EM overload) :179-253
+template <int LPS>
+__device__ void compute_dl(const PdDev & a, const EmArgs & e, EmShared & sh, const uint32_t * cnt, const uint32_t * off,
+                           double * dlx, const int32_t * shifts, bool zero_shifts, uint32_t L, double * cache, bool fill_cache)
+{
+    const int tid = threadIdx.x, sub = tid % LPS, grp = tid / LPS, ngrp = blockDim.x / LPS;
+    const uint32_t gmask = (LPS == 32) ? FULL : (((1u << LPS) - 1u) << ((tid & 31) & ~(LPS - 1)));
+    for (uint32_t s = grp; s < a.N; s += ngrp) {
+        double l0 = 0, l1 = 0, l2 = 0, w0 = 0, w1 = 0, w2 = 0, nd = 0;
+        int slot = 0;
+        bool high0 = false;
         for (uint32_t g = a.sample_rg[s]; g < a.sample_rg[s + 1]; ++g) {
-            const PdRgConst k = a.rgc[g];
+            const RgLite k = rg_lite(a.rgc + g);
             const uint32_t n = cnt[g];
-            double w0 = 0, w1 = 0, w2 = 0;
-            const bool high = n >= k.max_load;
-            if (!high) {
-                const int shift = zero_shifts ? 0 : shifts[g];
-                const PoolEntry * p = e.pool + off[g];
-                for (uint32_t i = 0; i < n; ++i) {
-                    const int d = p[i].dev;
-                    const PdTab * tr = tab_at(a.tab, k, d - shift);
-                    const PdTab * td = tab_at(a.tab, k, d - (int)L);
-                    const double ref = tr->val, del = td->val;
-                    const double g0 = tr->ln, g2 = td->ln;
-                    double g1;
-                    if (ref == del) { g1 = g0; ++ndeg; }                 // + LN2_RESIDUE, applied in finish_triple
-                    else if (del == k.min_prob) g1 = tr->lnp;            // ln(ref + min_prob) - ln2_d
-                    else if (ref == k.min_prob) g1 = td->lnp;
-                    else g1 = log(ref + del) - LN2_D;
-                    w0 += g0; w1 += g1; w2 += g2;
-                    l0 += g0; l1 += g1; l2 += g2;
-                }
-            }
-            if (g == 0) {
-                if (high) { sh.rgw[0] = sh.rgw[1] = sh.rgw[2] = -INFINITY; }     // Triple(0,0,0) in the reference
-                else { double m = fmax(fmax(w0, w1), w2); sh.rgw[0] = w0 - m; sh.rgw[1] = w1 - m; sh.rgw[2] = w2 - m; }
+            if (n >= k.max_load) { if (g == 0) high0 = true; continue; }
+            const int shift = zero_shifts ? 0 : shifts[g];
+            const PoolEntry * p = e.pool + off[g];
+            for (uint32_t i = sub; i < n; i += LPS, ++slot) {
+                const int d = __ldg(&p[i].dev);
+                const PdTab * tr = tab_at(a.tab, k, d - shift);
+                const PdTab * td = tab_at(a.tab, k, d - (int)L);
+                const double ref = __ldg(&tr->val), del = __ldg(&td->val);
+                const double g0 = __ldg(&tr->ln), g2 = __ldg(&td->ln);
+                double g1;
+                if (ref == del) { g1 = g0; nd += 1; }                    // + LN2_RESIDUE, applied in finish_triple
+                else if (del == k.min_prob) g1 = __ldg(&tr->lnp);        // ln(ref + min_prob) - ln2_d
+                else if (ref == k.min_prob) g1 = __ldg(&td->lnp);
+                else g1 = log(ref + del) - LN2_D;
+                if (fill_cache && slot < EM_CACHE_SLOTS) { cache[(2 * slot) * blockDim.x + tid] = del; cache[(2 * slot + 1) * blockDim.x + tid] = ref; }
+                l0 += g0; l1 += g1; l2 += g2;
+                if (g == 0) { w0 += g0; w1 += g1; w2 += g2; }
             }
         }
-        double x0, x1, x2;
-        finish_triple(l0, l1, l2, ndeg, x0, x1, x2);
-        dlx[3 * s] = x0; dlx[3 * s + 1] = x1; dlx[3 * s + 2] = x2;
+        l0 = group_sum<LPS>(l0, gmask); l1 = group_sum<LPS>(l1, gmask); l2 = group_sum<LPS>(l2, gmask); nd = group_sum<LPS>(nd, gmask);
+        if (s == a.rgc[0].sample) {                                      // read group 0 belongs to this sample
+            w0 = group_sum<LPS>(w0, gmask); w1 = group_sum<LPS>(w1, gmask); w2 = group_sum<LPS>(w2, gmask);
+            if (sub == 0) {
+                if (high0) { sh.rgw[0] = sh.rgw[1] = sh.rgw[2] = -INFINITY; }        // Triple(0,0,0) in the reference
+                else { const double m = fmax(fmax(w0, w1), w2); sh.rgw[0] = w0 - m; sh.rgw[1] = w1 - m; sh.rgw[2] = w2 - m; }
+            }
+        }
+        if (sub == 0) {
+            double x0, x1, x2;
+            finish_triple(l0, l1, l2, (uint32_t)nd, x0, x1, x2);
+            dlx[3 * s] = x0; dlx[3 * s + 1] = x1; dlx[3 * s + 2] = x2;
+        }
     }
     __syncthreads();
 }
@@ -524,9 +574,11 @@ __device__ double block_lr(const PdDev & a, EmShared & sh, const double * dlx, c
     return del - nodel;
 }
 
-__global__ void __launch_bounds__(256, 2) k_em(PdDev a, EmArgs e)
+template <int LPS>
+__global__ void __launch_bounds__(512, 2) k_em(PdDev a, EmArgs e, EmState * states)
 {
     __shared__ EmShared sh;
+    extern __shared__ double cache[];                 // [2 * EM_CACHE_SLOTS][blockDim.x]
     const uint32_t pi = e.pair0 + blockIdx.x;
     const PdPair pr = e.pairs[pi];
     const uint32_t job = pr.job - e.job_base;
@@ -534,15 +586,19 @@ __global__ void __launch_bounds__(256, 2) k_em(PdDev a, EmArgs e)
     const uint32_t w = e.jobs[pr.job];
     const uint32_t * cnt = e.act_cnt + (size_t)job * a.R;
     const uint32_t * off = e.act_off + (size_t)job * a.R;
-    const uint8_t * sstat = e.sstat + (size_t)job * a.N;
     double * dlx = e.dlx + (size_t)blockIdx.x * 3 * a.N;
     int32_t * shifts = e.shifts + (size_t)blockIdx.x * a.R;
-    uint32_t * ps = e.ps + (size_t)blockIdx.x * 13 * a.N;
-    const int tid = threadIdx.x;
-    auto reject = [&](uint32_t reason) {
+    const int tid = threadIdx.x, sub = tid % LPS, grp = tid / LPS, ngrp = blockDim.x / LPS;
+    const uint32_t gmask = (LPS == 32) ? FULL : (((1u << LPS) - 1u) << ((tid & 31) & ~(LPS - 1)));
+    auto finish = [&](uint32_t alive, uint32_t reason) {
         if (tid == 0) {
-            e.valid[blockIdx.x] = 0;
-            if (e.dbg) { e.dbg[4 * blockIdx.x] = reason; e.dbg[4 * blockIdx.x + 1] = sh.len; e.dbg[4 * blockIdx.x + 2] = sh.it; }
+            EmState st; st.len = sh.len; st.it = sh.it; st.alive = alive; st.pad = 0; st.freq = sh.freq;
+            st.gt[0] = sh.gt.a; st.gt[1] = sh.gt.b; st.gt[2] = sh.gt.c;
+            states[blockIdx.x] = st;
+            if (!alive) {
+                e.valid[blockIdx.x] = 0;
+                if (e.dbg) { e.dbg[4 * blockIdx.x] = reason; e.dbg[4 * blockIdx.x + 1] = sh.len; e.dbg[4 * blockIdx.x + 2] = sh.it; }
+            }
         }
     };
 
@@ -552,12 +608,12 @@ __global__ void __launch_bounds__(256, 2) k_em(PdDev a, EmArgs e)
     {
         unsigned long long c = 0, t = 0;
         for (uint32_t g = tid; g < a.R; g += blockDim.x) {
-            const PdRgConst k = a.rgc[g];
             const uint32_t n = cnt[g];
-            if (n == 0 || n >= k.max_load) continue;
+            if (n == 0 || n >= __ldg(&a.rgc[g].max_load)) continue;
             t += n;
-            const int wb = max((int)L0 / 2, (int)floor((double)L0 - 2 * k.stddev + 0.5));
-            const int we = (int)((double)L0 + 2 * k.stddev);
+            const double sd = __ldg(&a.rgc[g].stddev);
+            const int wb = max((int)L0 / 2, (int)floor((double)L0 - 2 * sd + 0.5));
+            const int we = (int)((double)L0 + 2 * sd);
             const PoolEntry * p = e.pool + off[g];
             for (uint32_t i = 0; i < n; ++i) { const int d = p[i].dev; c += (d > wb && d < we); }
         }
@@ -565,12 +621,13 @@ __global__ void __launch_bounds__(256, 2) k_em(PdDev a, EmArgs e)
         if (tid == 0) {
             sh.freq = t == 0 ? 0.0 : (double)c / (double)t;
             sh.len = L0; sh.it = 0; sh.nvisited = 0; sh.stop = 0;
+            sh.gt = gt_prior(sh.freq, e.somatic);
         }
         __syncthreads();
     }
-    if (sh.freq == 0) { reject(1); return; }
-    compute_dl(a, e, sh, cnt, off, dlx, shifts, false, L0);
-    if (tid == 0) { sh.gt = gt_prior(sh.freq, e.somatic); sh.prevFreq = sh.freq; sh.prevLen = sh.len; sh.prevGt = sh.gt; }
+    if (sh.freq == 0) { finish(0, 1); return; }
+    compute_dl<LPS>(a, e, sh, cnt, off, dlx, shifts, false, L0, cache, true);
+    if (tid == 0) { sh.prevFreq = sh.freq; sh.prevLen = sh.len; sh.prevGt = sh.gt; }
     __syncthreads();
 
     // ---- EM loop :598-660
@@ -593,37 +650,43 @@ __global__ void __launch_bounds__(256, 2) k_em(PdDev a, EmArgs e)
             sh.ea0Rg = exp(a0Rg); sh.ea1Rg = exp(a1Rg);
         }
         __syncthreads();
-        // update_deletion_length :388-462
+        // update_deletion_length :388-462 (table values of (len, shifts) come from the cache filled by compute_dl)
         const Gt gt = sh.gt;
         const int L = (int)sh.len;
         const double ea0Rg = sh.ea0Rg, ea1Rg = sh.ea1Rg;
         double sumDel = 0, wDel = 0;
-        for (uint32_t s = tid; s < a.N; s += blockDim.x) {
+        for (uint32_t s = grp; s < a.N; s += ngrp) {
             const double x1 = dlx[3 * s + 1], x2 = dlx[3 * s + 2];
             const double aSum = exp(dlx[3 * s]) * gt.a + exp(x1) * gt.b + exp(x2) * gt.c;
             const double a1 = x1 + log(gt.b) - log(aSum);
             const double a2 = x2 + log(gt.c) - log(aSum);
             const double ea1 = exp(a1), ea2 = exp(a2);
+            int slot = 0;
             for (uint32_t g = a.sample_rg[s]; g < a.sample_rg[s + 1]; ++g) {
-                const PdRgConst k = a.rgc[g];
+                const RgLite k = rg_lite(a.rgc + g);
                 const uint32_t n = cnt[g];
                 if (n >= k.max_load) continue;
                 double sumRef = 0, wRef = 0;
                 const int shift = shifts[g];
                 const PoolEntry * p = e.pool + off[g];
-                for (uint32_t i = 0; i < n; ++i) {
-                    const int d = p[i].dev;
-                    const double del = tab_at(a.tab, k, d - L)->val;
-                    const double nod = tab_at(a.tab, k, d - shift)->val;
+                for (uint32_t i = sub; i < n; i += LPS, ++slot) {
+                    const int d = __ldg(&p[i].dev);
+                    double del, nod;
+                    if (slot < EM_CACHE_SLOTS) { del = cache[(2 * slot) * blockDim.x + tid]; nod = cache[(2 * slot + 1) * blockDim.x + tid]; }
+                    else { del = __ldg(&tab_at(a.tab, k, d - L)->val); nod = __ldg(&tab_at(a.tab, k, d - shift)->val); }
                     const double pd = ea1 * del / (del + nod) + ea2;
                     const double prf = ea1Rg * nod / (del + nod) + ea0Rg;
                     sumDel += pd; sumRef += prf;
                     wDel += pd * d; wRef += prf * d;
                 }
-                const double q = wRef / sumRef;
-                int sft = (q != q) ? 0 : (q >= 2147483647.0 ? INT_MAX : (q <= -2147483648.0 ? INT_MIN : (int)q));
-                if (sft > k.stddev || sft < -1 * k.stddev) sft = 0;
-                shifts[g] = sft;
+                sumRef = group_sum<LPS>(sumRef, gmask); wRef = group_sum<LPS>(wRef, gmask);
+                if (sub == 0) {
+                    const double q = wRef / sumRef;
+                    int sft = (q != q) ? 0 : (q >= 2147483647.0 ? INT_MAX : (q <= -2147483648.0 ? INT_MIN : (int)q));
+                    const double sd = __ldg(&a.rgc[g].stddev);
+                    if (sft > sd || sft < -1 * sd) sft = 0;
+                    shifts[g] = sft;
+                }
             }
         }
         block_sum2(sumDel, wDel, sh.red);
@@ -636,7 +699,7 @@ __global__ void __launch_bounds__(256, 2) k_em(PdDev a, EmArgs e)
             sh.len = nl;
         }
         __syncthreads();
-        compute_dl(a, e, sh, cnt, off, dlx, shifts, false, sh.len);
+        compute_dl<LPS>(a, e, sh, cnt, off, dlx, shifts, false, sh.len, cache, true);
         // update_allele_frequency :467-485 (with the genotype priors of the previous iteration)
         double fs = 0, dummy = 0;
         for (uint32_t s = tid; s < a.N; s += blockDim.x) {
@@ -660,7 +723,7 @@ __global__ void __launch_bounds__(256, 2) k_em(PdDev a, EmArgs e)
         if (sh.stop == 2) {
             // convergence :632-658: compare with the previous estimate evaluated with the initial (zero) shifts
             const double lr = block_lr(a, sh, dlx, sh.gt);
-            compute_dl(a, e, sh, cnt, off, dlx, shifts, true, sh.prevLen);
+            compute_dl<LPS>(a, e, sh, cnt, off, dlx, shifts, true, sh.prevLen, cache, false);
             const double plr = block_lr(a, sh, dlx, sh.prevGt);
             __syncthreads();
             if (plr > lr) {
@@ -672,8 +735,38 @@ __global__ void __launch_bounds__(256, 2) k_em(PdDev a, EmArgs e)
         }
     }
     __syncthreads();
-    if (sh.freq < 0.0000000001 || sh.len < e.min_len) { reject(2); return; }
+    const bool alive = !(sh.freq < 0.0000000001 || sh.len < e.min_len);
+    finish(alive ? 1u : 0u, 2);
+}
 
+// ------------------------------------------------------------------------------------------------------------------
+// final pass: one block per (window, initial length) that survived the EM; thread = sample (strided)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_final(PdDev a, EmArgs e, const EmState * states)
+{
+    __shared__ EmShared sh;
+    const EmState stt = states[blockIdx.x];
+    if (!stt.alive) return;
+    const uint32_t pi = e.pair0 + blockIdx.x;
+    const PdPair pr = e.pairs[pi];
+    const uint32_t job = pr.job - e.job_base;
+    const uint32_t L0 = (uint32_t)pr.L0;
+    const uint32_t w = e.jobs[pr.job];
+    const uint32_t * cnt = e.act_cnt + (size_t)job * a.R;
+    const uint32_t * off = e.act_off + (size_t)job * a.R;
+    const uint8_t * sstat = e.sstat + (size_t)job * a.N;
+    double * dlx = e.dlx + (size_t)blockIdx.x * 3 * a.N;
+    const int32_t * shifts = e.shifts + (size_t)blockIdx.x * a.R;
+    uint32_t * ps = e.ps + (size_t)blockIdx.x * 13 * a.N;
+    const int tid = threadIdx.x;
+    if (tid == 0) { sh.len = stt.len; sh.it = stt.it; sh.freq = stt.freq; sh.gt = Gt{stt.gt[0], stt.gt[1], stt.gt[2]}; }
+    __syncthreads();
+    auto reject = [&](uint32_t reason) {
+        if (tid == 0) {
+            e.valid[blockIdx.x] = 0;
+            if (e.dbg) { e.dbg[4 * blockIdx.x] = reason; e.dbg[4 * blockIdx.x + 1] = sh.len; e.dbg[4 * blockIdx.x + 2] = sh.it; }
+        }
+    };
     // ---- final pass :665-727 (compute_data_likelihoods final overload :255-337)
     const int len = (int)sh.len;
     unsigned long long supp = 0, ndata = 0;
@@ -913,7 +1006,7 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
     if ((size_t)npad * 4 > 200 * 1024) return pd_fail(c, PD_ERR_CAPACITY, "more than 51200 samples per context: candidate sort does not fit shared memory (shard by sample)");
     if ((size_t)npad * 4 > 48 * 1024)
         PD_CUDA(c, cudaFuncSetAttribute(k_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(npad * 4)));
-    const uint32_t em_threads = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    const uint32_t em_threads = N <= 64 ? 64 : 128;                 // k_final: thread = sample (strided)
     uint64_t n_pairs_total = 0, n_calls = 0;
     size_t pool_cap = std::max<size_t>((size_t)std::min<uint32_t>(JB, std::max(n_jobs, 1u)) * R * 40, 1u << 20);
     const bool dbg = getenv("PD_DEBUG") != nullptr;
@@ -954,16 +1047,23 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
             PD_CUDA(c, cudaMemcpyAsync(d_pairs, h_pairs.data(), (size_t)n_pairs * sizeof(PdPair), cudaMemcpyHostToDevice, st));
         }
         n_pairs_total += n_pairs;
-        for (uint32_t p0 = 0; p0 < n_pairs; p0 += PB) {
-            const uint32_t np = std::min(PB, n_pairs - p0);
-            double * d_dlx; int32_t * d_shifts; uint32_t * d_ps, * d_idx, * d_out_ps; pd_call * d_calls; uint8_t * d_valid;
+        // pairs in chunks: the row compaction + D2H of chunk k (stream2) overlaps the EM of chunk k+1 (stream)
+        const uint32_t CH = std::min<uint32_t>(PB, std::max<uint32_t>(2048, (n_pairs + 3) / 4));
+        uint32_t chunk_no = 0;
+        for (uint32_t p0 = 0; p0 < n_pairs; p0 += CH, ++chunk_no) {
+            const uint32_t np = std::min(CH, n_pairs - p0);
+            const int par = (int)(chunk_no & 1);
+            double * d_dlx; int32_t * d_shifts; uint32_t * d_ps, * d_idx, * d_out_ps; pd_call * d_calls; uint8_t * d_valid; EmState * d_states;
             if (grow_scratch(c, 9, d_dlx, (size_t)np * 3 * N)) return c->status;
             if (grow_scratch(c, 10, d_shifts, (size_t)np * R)) return c->status;
-            if (grow_scratch(c, 11, d_ps, (size_t)np * row)) return c->status;
+            // double-buffered: read by stream2 while the next chunk is computed
+            PD_CUDA(c, cudaEventSynchronize(c->ev[6 + par]));                      // chunk k-2 has left these buffers
+            if (grow_scratch(c, 11 + 8 * par, d_ps, (size_t)CH * row)) return c->status;            // slots 11 / 19
+            if (grow_scratch(c, 13 + 8 * par, d_out_ps, (size_t)CH * row)) return c->status;        // slots 13 / 21
+            if (grow_scratch(c, 15 + 8 * par, d_idx, (size_t)CH)) return c->status;                 // slots 15 / 23
             if (grow_scratch(c, 12, d_calls, (size_t)np)) return c->status;
-            if (grow_scratch(c, 13, d_out_ps, (size_t)np * row)) return c->status;
-            if (grow_scratch(c, 15, d_idx, (size_t)np)) return c->status;
-            if (grow_scratch(c, 14, d_valid, (size_t)np + (dbg ? (size_t)np * 16 : 0))) return c->status;
+            if (grow_scratch(c, 14, d_valid, (size_t)np + 16 + (dbg ? (size_t)np * 16 : 0))) return c->status;
+            if (grow_scratch(c, 16, d_states, (size_t)np)) return c->status;
             EmArgs e;
             e.jobs = d_jobs; e.pairs = d_pairs; e.pair0 = p0; e.npairs = np; e.job_base = job0;
             e.pool = d_pool; e.act_off = d_act_off; e.act_cnt = d_act_cnt; e.sstat = d_sstat;
@@ -973,12 +1073,24 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
             e.anchor = c->grid.anchor;
             e.dbg = nullptr; e.dbg_window = dbg_window;
             if (dbg) {
-                e.dbg = reinterpret_cast<uint32_t *>(d_valid + (((size_t)np + 15) & ~(size_t)15) - 0);
-                if ((((size_t)np + 15) & ~(size_t)15) + (size_t)np * 16 > c->cap_scratch[14]) e.dbg = nullptr;
-                else PD_CUDA(c, cudaMemsetAsync(e.dbg, 0xFF, (size_t)np * 16, st));
+                e.dbg = reinterpret_cast<uint32_t *>(d_valid + (((size_t)np + 15) & ~(size_t)15));
+                PD_CUDA(c, cudaMemsetAsync(e.dbg, 0xFF, (size_t)np * 16, st));
             }
-            k_em<<<np, em_threads, 0, st>>>(a, e);
-            ++out->n_kernel_launches;
+            {
+                const uint32_t lps = N * 8 <= 512 ? 8 : (N * 4 <= 512 ? 4 : (N * 2 <= 512 ? 2 : 1));
+                const uint32_t T = std::min<uint32_t>(512, ((N * lps + 31) / 32) * 32);
+                const size_t smem = (size_t)2 * EM_CACHE_SLOTS * T * sizeof(double);
+                auto launch = [&](auto kern) -> cudaError_t {
+                    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (err != cudaSuccess) return err;
+                    kern<<<np, T, smem, st>>>(a, e, d_states);
+                    return cudaGetLastError();
+                };
+                cudaError_t err = lps == 8 ? launch(k_em<8>) : lps == 4 ? launch(k_em<4>) : lps == 2 ? launch(k_em<2>) : launch(k_em<1>);
+                if (err != cudaSuccess) return pd_fail(c, PD_ERR_CUDA, std::string("k_em launch: ") + cudaGetErrorString(err));
+                k_final<<<np, em_threads, 0, st>>>(a, e, d_states);
+            }
+            out->n_kernel_launches += 2;
             PD_CUDA(c, cudaGetLastError());
             std::vector<uint8_t> h_valid(np);
             std::vector<pd_call> h_calls(np);
@@ -991,13 +1103,14 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
                 for (uint32_t i = 0; i < np; ++i)
                     fprintf(stderr, "PD_DEBUG pair window %u L0 %d reason %u len %u it %u supp %u\n", h_jobs[h_pairs[p0 + i].job], h_pairs[p0 + i].L0, hd[4 * i], hd[4 * i + 1], hd[4 * i + 2], hd[4 * i + 3]);
             }
-            std::vector<uint32_t> idx;
-            idx.reserve(np);
+            std::vector<uint32_t> & idx = c->idx_stage[par];                       // must outlive the async H2D below
+            idx.clear();
             for (uint32_t i = 0; i < np; ++i) if (h_valid[i]) { idx.push_back(i); c->res_calls.push_back(h_calls[i]); }
             const uint32_t nc = (uint32_t)idx.size();
             if (nc) {
                 const size_t need = (n_calls + nc) * row;
-                if (need > c->cap_res_ps) {                       // grow the pinned result buffer
+                if (need > c->cap_res_ps) {                       // grow the pinned result buffer (rare; drains stream2 first)
+                    PD_CUDA(c, cudaStreamSynchronize(c->stream2));
                     size_t want = std::max<size_t>(need + need / 2, 1u << 20);
                     uint32_t * p = nullptr;
                     PD_CUDA(c, cudaMallocHost(&p, want * 4));
@@ -1005,17 +1118,20 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
                     if (c->res_ps) cudaFreeHost(c->res_ps);
                     c->res_ps = p; c->cap_res_ps = want;
                 }
-                PD_CUDA(c, cudaMemcpyAsync(d_idx, idx.data(), (size_t)nc * 4, cudaMemcpyHostToDevice, st));
-                k_compact<<<nc, 256, 0, st>>>(d_ps, d_idx, d_out_ps, (uint32_t)row);
+                cudaStream_t s2 = c->stream2;
+                PD_CUDA(c, cudaMemcpyAsync(d_idx, idx.data(), (size_t)nc * 4, cudaMemcpyHostToDevice, s2));
+                k_compact<<<nc, 256, 0, s2>>>(d_ps, d_idx, d_out_ps, (uint32_t)row);
                 ++out->n_kernel_launches;
                 PD_CUDA(c, cudaGetLastError());
-                PD_CUDA(c, cudaMemcpyAsync(c->res_ps + n_calls * row, d_out_ps, (size_t)nc * row * 4, cudaMemcpyDeviceToHost, st));
-                PD_CUDA(c, cudaStreamSynchronize(st));
+                PD_CUDA(c, cudaMemcpyAsync(c->res_ps + n_calls * row, d_out_ps, (size_t)nc * row * 4, cudaMemcpyDeviceToHost, s2));
+                PD_CUDA(c, cudaEventRecord(c->ev[6 + par], s2));
                 out->d2h_bytes += (uint64_t)nc * (sizeof(pd_call) + row * 4);
                 n_calls += nc;
             }
         }
+        PD_CUDA(c, cudaStreamSynchronize(c->stream2));
     }
+    PD_CUDA(c, cudaStreamSynchronize(c->stream2));
     PD_CUDA(c, cudaEventRecord(c->ev[5], st));
     PD_CUDA(c, cudaStreamSynchronize(st));
     out->n_calls = c->res_calls.size();
