@@ -1,0 +1,583 @@
+// popdel_b200_call -- host shell of the B200 scan: a drop-in for `popdel call` (reference workflow_popdel.h:256-371).
+//
+// Host side (this file, plain C++17): command line, profile headers and histogram preprocessing, parameter
+// calculation, the segment loader (which read pairs the reference loads in which segment), the segment-level merge
+// (unifyCalls) and the VCF writer. Device side: every window of the scan, through the C ABI of libpopdel_b200.so
+// (include/popdel_b200.h). There is no CPU path for the scan: without a CUDA device the program stops with an error.
+//
+// Usage: popdel_b200_call [options] PROFILE-LIST-FILE | PROFILE1 PROFILE2 [...]
+//   -o FILE  output VCF (popdel.vcf)        -n  window-wise output, no merging       -F  also write failed calls
+//   -l NUM   min initial deletion length    -m NUM  min deletion length              -a NUM  active-coverage cap (100)
+//   -b NUM   segment length in bp (200000)  -t NUM  EM iterations (15)               -p NUM  prior (1e-4)
+//   -s NUM   min sample fraction (0.1)      -c NUM  min relative window cover (0.5)  -f NUM  pseudo-count fraction (500)
+//   -u       unsmoothed histograms          -x  uncompressed profiles                -C  cell-population priors
+//   -g NUM   CUDA device (0)
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <set>
+#include <sstream>
+#include <string>
+#include <vector>
+#include <zlib.h>
+
+#include "../../include/popdel_b200.h"
+
+namespace {
+
+[[noreturn]] void die(const std::string & msg) { std::cerr << "[popdel_b200] " << msg << std::endl; exit(1); }
+inline int rnd(double d) { return (int)std::floor(d + 0.5); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// profile files (format: reference insert_histogram_popdel.h:334-525 header, window_podel.h:211-251 records)
+// ---------------------------------------------------------------------------------------------------------------
+struct Rec { uint32_t pos; int32_t dev; };
+struct Win { int32_t chrom; uint32_t begin; std::vector<std::vector<Rec>> rg; };
+struct RgHeader { std::string name; uint32_t median, readLength; double stddev; int32_t offset; std::vector<double> counts; };
+struct Profile {
+    std::string path;
+    uint32_t indexRegionSize = 10000;
+    std::vector<RgHeader> rgs;
+    std::vector<std::string> contigNames;
+    std::vector<int32_t> contigLengths;
+    std::vector<Win> wins;                                   // file order
+    std::vector<size_t> contigFirst;                         // first window of each contig (wins.size() if none)
+};
+
+template <typename T> T get(const std::vector<unsigned char> & d, size_t & o)
+{
+    if (o + sizeof(T) > d.size()) die("truncated profile");
+    T v; memcpy(&v, d.data() + o, sizeof(T)); o += sizeof(T); return v;
+}
+
+void inflateMembers(const std::vector<unsigned char> & in, size_t off, std::vector<unsigned char> & out)
+{
+    z_stream zs; memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, 31) != Z_OK) die("zlib init failed");
+    zs.next_in = const_cast<unsigned char *>(in.data() + off);
+    zs.avail_in = (uInt)(in.size() - off);
+    std::vector<unsigned char> buf(4u << 20);
+    while (zs.avail_in > 0) {
+        zs.next_out = buf.data(); zs.avail_out = (uInt)buf.size();
+        int rc = inflate(&zs, Z_NO_FLUSH);
+        out.insert(out.end(), buf.data(), buf.data() + (buf.size() - zs.avail_out));
+        if (rc == Z_STREAM_END) { if (zs.avail_in == 0) break; inflateReset(&zs); }
+        else if (rc != Z_OK) die("corrupt gzip block in profile");
+    }
+    inflateEnd(&zs);
+}
+
+void loadProfile(const std::string & path, bool uncompressed, Profile & p)
+{
+    std::ifstream f(path, std::ios::binary);
+    if (!f.good()) die("cannot open profile '" + path + "'");
+    std::vector<unsigned char> d((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    if (d.size() < 15 || memcmp(d.data(), "POPDEL\1", 7) != 0) die("'" + path + "' is not a PopDel profile (magic string)");
+    p.path = path;
+    size_t o = 7;
+    p.indexRegionSize = get<uint32_t>(d, o);
+    uint32_t nRegions = get<uint32_t>(d, o);
+    o += 8ull * nRegions;
+    uint32_t nrg = get<uint32_t>(d, o);
+    if (nrg == 0) die("profile without read groups");
+    for (uint32_t i = 0; i < nrg; ++i) {
+        RgHeader h;
+        uint32_t nl = get<uint32_t>(d, o);
+        h.name.assign((const char *)d.data() + o, nl - 1); o += nl;
+        h.median = get<uint32_t>(d, o); h.stddev = get<double>(d, o); h.readLength = get<uint32_t>(d, o);
+        h.offset = (int32_t)get<uint32_t>(d, o);
+        uint32_t end = get<uint32_t>(d, o);
+        h.counts.resize(end - h.offset);
+        for (double & v : h.counts) v = get<double>(d, o);
+        p.rgs.push_back(h);
+    }
+    uint32_t nc = get<uint32_t>(d, o);
+    for (uint32_t i = 0; i < nc; ++i) {
+        uint32_t nl = get<uint32_t>(d, o);
+        p.contigNames.emplace_back((const char *)d.data() + o, nl - 1); o += nl;
+        p.contigLengths.push_back(get<int32_t>(d, o));
+    }
+    std::vector<unsigned char> body;
+    if (uncompressed) body.assign(d.begin() + o, d.end());
+    else if (o < d.size()) inflateMembers(d, o, body);
+    size_t b = 0;
+    while (b + 8 <= body.size()) {
+        Win w; w.chrom = (int32_t)get<uint32_t>(body, b); w.begin = get<uint32_t>(body, b);
+        w.rg.resize(nrg);
+        for (uint32_t g = 0; g < nrg; ++g) {
+            uint32_t n = get<uint32_t>(body, b);
+            if (b + 5ull * n > body.size()) die("truncated window record in '" + path + "'");
+            w.rg[g].resize(n);
+            for (uint32_t i = 0; i < n; ++i) {
+                uint8_t offc = body[b]; b += 1;
+                int32_t dv; memcpy(&dv, body.data() + b, 4); b += 4;
+                w.rg[g][i] = Rec{w.begin + offc, dv};
+            }
+        }
+        p.wins.push_back(std::move(w));
+    }
+    p.contigFirst.assign(nc + 1, p.wins.size());
+    for (size_t i = p.wins.size(); i-- > 0;) if (p.wins[i].chrom >= 0 && (uint32_t)p.wins[i].chrom < nc) p.contigFirst[p.wins[i].chrom] = i;
+    for (size_t c = nc; c-- > 0;) if (p.contigFirst[c] == p.wins.size()) p.contigFirst[c] = p.contigFirst[c + 1];
+}
+
+// first window (file order) whose (contig, index region) is >= (c, region): what the index seek lands on
+// (reference insert_histogram_popdel.h:531-562; empty index entries are back-filled with the next offset :298-328)
+size_t indexSeek(const Profile & p, int32_t c, uint32_t pos)
+{
+    const uint32_t region = pos / p.indexRegionSize;
+    size_t lo = p.contigFirst[c], hi = p.contigFirst[c + 1];
+    while (lo < hi) { size_t mid = (lo + hi) / 2; if (p.wins[mid].begin / p.indexRegionSize < region) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// 30-bp buckets of a 256-bp window, ascending (reference window_podel.h:314-418): anchored at the window's first read pair
+struct Bucket { uint32_t begin; std::vector<std::vector<Rec>> rg; };
+void convertWindow(const Win & w, std::vector<Bucket> & out)
+{
+    out.clear();
+    uint32_t first = 0xFFFFFFFFu;
+    for (const auto & r : w.rg) if (!r.empty()) first = std::min(first, r[0].pos);
+    if (first == 0xFFFFFFFFu) return;
+    const uint32_t base = (first / 30) * 30;
+    std::map<uint32_t, size_t> slot;
+    for (const auto & r : w.rg) for (const Rec & x : r) slot[(x.pos - base) / 30] = 0;
+    size_t k = 0;
+    for (auto & kv : slot) kv.second = k++;
+    out.resize(slot.size());
+    for (auto & kv : slot) { out[kv.second].begin = base + kv.first * 30; out[kv.second].rg.resize(w.rg.size()); }
+    for (size_t g = 0; g < w.rg.size(); ++g) for (const Rec & x : w.rg[g]) out[slot[(x.pos - base) / 30]].rg[g].push_back(x);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// calls, segment-level merge (reference utils_popdel.h:237-654) and VCF (vcfout_popdel_call.h)
+// ---------------------------------------------------------------------------------------------------------------
+struct Call {
+    uint32_t initialLength = 0, iterations = 0, deletionLength = 0, filter = 0;
+    double lr = 0, frequency = 0;
+    uint32_t windowPosition = 0, position = 0, endPosition = 0, significantWindows = 0;
+    std::vector<uint32_t> ps;                                // 13 per sample: PL[3] LAD[3] DAD[5] FL[2]
+};
+inline bool allPass(const Call & c) { return (c.filter & 31u) == 0; }
+inline void invalidate(Call & c) { c.filter = 255; }
+
+bool sizeSimilar(unsigned a, unsigned b, double sd)
+{
+    const unsigned l = std::min(a, b), r = std::max(a, b);
+    return (l + 2 * sd >= r) || (l >= 0.5 * r);
+}
+bool similarCalls(Call & a, Call & b, double sd)
+{
+    if (!sizeSimilar(a.deletionLength, b.deletionLength, sd)) return false;
+    const unsigned aSpan = a.endPosition - a.position, bSpan = b.endPosition - b.position;
+    const unsigned minLen = std::min(aSpan, bSpan);
+    const unsigned left = std::max(a.position, b.position), right = std::min(a.position + aSpan, b.position + bSpan);
+    const int overlap = (int)(right - left);
+    if (overlap >= 0.25 * minLen || overlap + 2 * sd >= minLen) return true;
+    // checkAndExtend: one of the spans is shorter than its deletion and the starts are close enough
+    if ((aSpan < a.deletionLength || bSpan < b.deletionLength) &&
+        (b.position - a.position < (std::min(a.deletionLength, b.deletionLength) + 4 * sd))) { a.endPosition = b.endPosition; return true; }
+    return false;
+}
+
+struct Merger {
+    std::vector<std::vector<uint32_t>> lists;                // per sample x 8 (LAD 3 + DAD 5)
+    std::vector<uint32_t> plSum;                             // per sample x 3
+    std::vector<unsigned> starts, sizes;
+    long double lr = 0;
+    unsigned callCount = 1, winCount = 1, sigWin = 1;
+
+    void mergeRange(std::vector<Call> & calls, size_t start, size_t last, double minCover)
+    {
+        Call & st = calls[start];
+        std::sort(starts.begin(), starts.end()); st.position = starts[starts.size() / 2]; starts.clear();
+        std::sort(sizes.begin(), sizes.end()); st.deletionLength = sizes[sizes.size() / 2]; sizes.clear();
+        st.lr = (double)(lr / winCount);
+        const size_t N = st.ps.size() / 13;
+        unsigned inRange = 0;
+        for (size_t k = start; k < last; ++k) {
+            const Call & g = calls[k];
+            if (g.windowPosition > st.position && g.windowPosition - 30 < st.position + st.deletionLength) {
+                for (size_t s = 0; s < N; ++s) {
+                    for (int j = 0; j < 3; ++j) plSum[3 * s + j] += g.ps[13 * s + j];
+                    for (int j = 0; j < 8; ++j) lists[8 * s + j].push_back(g.ps[13 * s + 3 + j]);
+                }
+                ++inRange;
+            }
+        }
+        if (inRange == 0) { invalidate(st); return; }
+        unsigned alleles = 0;
+        for (size_t s = 0; s < N; ++s) {
+            uint32_t * g = &plSum[3 * s];
+            const double mn = std::min(std::min(g[0], g[1]), g[2]);
+            const double ref = static_cast<double>(g[0] - mn) / inRange, het = static_cast<double>(g[1] - mn) / inRange,
+                         hom = static_cast<double>(g[2] - mn) / inRange;
+            g[0] = g[1] = g[2] = 0;
+            uint32_t * o = &st.ps[13 * s];
+            o[0] = (uint32_t)std::round(ref); o[1] = (uint32_t)std::round(het); o[2] = (uint32_t)std::round(hom);
+            for (int j = 0; j < 8; ++j) {
+                std::vector<uint32_t> & v = lists[8 * s + j];
+                std::sort(v.begin(), v.end());
+                o[3 + j] = v[v.size() / 2];
+                v.clear();
+            }
+            if (o[1] == o[2]) { if (het > hom) ++o[1]; else ++o[2]; }
+            else if (o[0] == o[1]) { if (ref > het) ++o[0]; else ++o[1]; }
+            if (o[0] == 0) continue;
+            alleles += (o[1] == 0) ? 1 : 2;
+        }
+        st.frequency = static_cast<double>(alleles) / (N * 2);
+        st.significantWindows = sigWin;
+        if (30.0 * sigWin / st.deletionLength < minCover) st.filter |= 16;
+        winCount = 1; sigWin = 1; lr = 0.0; ++callCount;
+    }
+};
+
+bool unifySegment(std::vector<Call> & calls, double meanStddev, double minCover, bool outputFailed)
+{
+    if (calls.size() <= 1) return false;
+    std::stable_sort(calls.begin(), calls.end(), [](const Call & l, const Call & r) {
+        if (l.position != r.position) return l.position < r.position;
+        if (l.deletionLength != r.deletionLength) return l.deletionLength < r.deletionLength;
+        return l.lr > r.lr;
+    });
+    size_t cur = 0;
+    const size_t last = calls.size() - 1;
+    if (!outputFailed) {
+        while (!allPass(calls[cur])) { if (cur == last) return false; ++cur; }
+        if (cur == last) return false;
+    }
+    const size_t first = cur;
+    const size_t N = calls[cur].ps.size() / 13;
+    Merger m;
+    m.lists.resize(8 * N); m.plSum.assign(3 * N, 0);
+    m.starts.push_back(calls[cur].position); m.sizes.push_back(calls[cur].deletionLength);
+    m.lr = calls[cur].lr;
+    size_t it = first + 1;
+    while (true) {
+        if (similarCalls(calls[cur], calls[it], meanStddev)) {
+            if (allPass(calls[it])) { m.starts.push_back(calls[it].position); m.sizes.push_back(calls[it].deletionLength); ++m.sigWin; }
+            ++m.winCount;
+            m.lr += calls[it].lr;
+            invalidate(calls[it]);
+            if (it == last) { if (!m.starts.empty()) m.mergeRange(calls, cur, it, minCover); break; }
+        } else {
+            if (m.winCount != 1 && !m.starts.empty()) m.mergeRange(calls, cur, it, minCover);
+            else invalidate(calls[cur]);
+            cur = it;
+        }
+        if (it != last) ++it;
+        else { if (m.winCount == 1) { --m.callCount; invalidate(calls[cur]); } break; }
+    }
+    std::vector<Call> keep;
+    for (size_t k = first; k <= last; ++k) if (calls[k].filter != 255) keep.push_back(std::move(calls[k]));
+    calls.swap(keep);
+    return true;
+}
+
+// LR -> QUAL (reference QuantileMap, parameter_parsing_popdel_call.h:14-136, always built with prior 1e-4):
+// keys qchisq(1-10^(-i/10), df=1)/2 - ln(prior/(1-prior)), i = 1..100; QUAL = i of the largest key <= LR.
+struct QualMap {
+    std::vector<double> keys;
+    QualMap()
+    {
+        const double p = std::log(0.0001 / (1 - 0.0001));
+        for (int i = 1; i <= 100; ++i) {
+            const long double q = std::pow(10.0L, -i / 10.0L);           // upper tail of chi^2_1 = erfc(sqrt(x/2))
+            long double z = std::sqrt(-2.0L * std::log(q)), prev = 0;     // solve erfc(z/sqrt2) = q by Newton
+            for (int k = 0; k < 100 && std::fabs((double)(z - prev)) > 1e-17L * (double)z; ++k) {
+                prev = z;
+                const long double fz = erfcl(z / sqrtl(2.0L)) - q;
+                const long double dfz = -sqrtl(2.0L / 3.14159265358979323846264338327950288L) * expl(-z * z / 2);
+                z -= fz / dfz;
+            }
+            keys.push_back((double)(z * z) / 2 - p);
+        }
+    }
+    int qual(double lr) const
+    {
+        if (lr < 0) return 0;
+        int i = (int)(std::upper_bound(keys.begin(), keys.end(), lr) - keys.begin());     // number of keys <= lr
+        return i >= 100 ? 100 : i;                                 // beyond the last key the reference prints 100 as well
+    }
+};
+
+std::string sampleName(const std::string & path)                  // reference utils_popdel.h:1469-1489
+{
+    size_t lastDelim = 0, lastDot = path.size();
+    for (size_t i = 0; i < path.size(); ++i) { if (path[i] == '/' || path[i] == '\\') lastDelim = i; else if (path[i] == '.') lastDot = i; }
+    if (lastDelim == 0) return path.substr(0, lastDot);
+    if (lastDot < lastDelim) return path.substr(lastDelim + 1);
+    return path.substr(lastDelim + 1, lastDot - lastDelim - 1);
+}
+
+void writeHeader(std::ostream & out, const Profile & first, const std::vector<std::string> & files)
+{
+    time_t now = time(nullptr); char buf[32];
+    strftime(buf, sizeof(buf), "[%Y%m%d] ", localtime(&now));
+    out << "##fileformat=VCFv4.3\n##fileDate=" << buf << "\n##source=PopDel-V1.5.0\n";
+    for (size_t i = 0; i < first.contigNames.size(); ++i)
+        out << "##contig=<ID=" << first.contigNames[i] << ",length=" << first.contigLengths[i] << ">\n";
+    out << "##INFO=<ID=AF,Number=A,Type=Float,Description=\"Allele Frequency\">\n"
+           "##INFO=<ID=IMPRECISE,Number=0,Type=Flag,Description=\"Imprecise structural variation\">\n"
+           "##INFO=<ID=SVLEN,Number=.,Type=Integer,Description=\"Difference in length between REF and ALT alleles\">\n"
+           "##INFO=<ID=SVTYPE,Number=1,Type=String,Description=\"Type of structural variant\">\n"
+           "##INFO=<ID=END,Number=1,Type=Integer,Description=\"End position of the structural variant\">\n"
+           "##INFO=<ID=SVMETHOD,Number=1,Type=String,Description=\"Approach used to detect the structural variant\">\n"
+           "##INFO=<ID=LR,Number=1,Type=String,Description=\"Log-Likelihood ratio that the test is correct\">\n"
+           "##INFO=<ID=YIELD,Number=1,Type=Float,Description=\"Fraction of genotyped samples\">\n"
+           "##INFO=<ID=SWIN,Number=1,Type=Integer,Description=\"Number of significant windows merged into this variant\">\n"
+           "##FILTER=<ID=LowLR,Description=\"Likelihood ratio below threshold\">\n"
+           "##FILTER=<ID=missingSamples,Description=\"Too many samples not genotyped\">\n"
+           "##FILTER=<ID=allRefGT,Description=\"All samples genotyped as homozygous reference\">\n"
+           "##FILTER=<ID=CSWin,Description=\"Low fraction of significant windows\">\n"
+           "##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n"
+           "##FORMAT=<ID=PL,Number=G,Type=Integer,Description=\"Phred-scaled genotype likelihoods rounded to the closest integer\">\n"
+           "##FORMAT=<ID=GQ,Number=1,Type=Integer,Description=\"Genotype quality. Difference of the best and second-best PL\">\n"
+           "##FORMAT=<ID=LAD,Number=3,Type=Integer,Description=\"Likelihood derived allelic depth: Count of read-pairs supporting REF, ambiguous, ALT\">\n"
+           "##FORMAT=<ID=DAD,Number=5,Type=Integer,Description=\"Distribution derived allelic depth: Count of read-pairs supporting REF only, REF and ALT, neither(between the histograms), ALT only, bigger than ALT\">\n"
+           "##FORMAT=<ID=FL,Number=2,Type=Integer,Description=\"Window of the first and last read active in this window\">\n"
+           "##FORMAT=<ID=FLD,Number=1,Type=Integer,Description=\"Distance between first and last window\">\n";
+    out << "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT";
+    for (const std::string & f : files) out << "\t" << sampleName(f);
+    out << "\n";
+}
+
+void writeRecord(std::ostream & out, const std::string & chrom, const Call & c, const QualMap & qm)
+{
+    const size_t N = c.ps.size() / 13;
+    unsigned genotyped = (unsigned)N;
+    for (size_t s = 0; s < N; ++s) if (c.ps[13 * s] + c.ps[13 * s + 1] + c.ps[13 * s + 2] == 0) --genotyped;
+    std::string filter;
+    if (allPass(c)) filter = "PASS";
+    else {
+        auto add = [&](const char * t) { if (!filter.empty()) filter += ';'; filter += t; };
+        if (c.filter & 1) add("lowLR");
+        if (c.filter & 2) add("highCov");
+        if (c.filter & 4) add("missingSamples");
+        if (c.filter & 8) add("allRefGT");
+        if (c.filter & 16) add("CSWin");
+    }
+    std::ostringstream info;                                       // default stream precision (6), like the reference
+    info << "IMPRECISE;SVLEN=" << -static_cast<int>(c.deletionLength) << ";END=" << c.position + c.deletionLength
+         << ";SVTYPE=DEL;AF=" << c.frequency << ";LR=" << c.lr << ";SVMETHOD=PopDelv1.5.0;YIELD="
+         << (double)genotyped / N << ";SWIN=" << c.significantWindows;
+    const uint32_t pos = c.position > 1 ? c.position - 1 : c.position;           // record.beginPos (0-based)
+    out << chrom << "\t" << pos + 1 << "\t.\tN\t<DEL>\t" << qm.qual(c.lr) << "\t" << filter << "\t" << info.str()
+        << "\tGT:PL:GQ:LAD:DAD:FL:FLD";
+    for (size_t s = 0; s < N; ++s) {
+        const uint32_t * o = &c.ps[13 * s];
+        unsigned gq = 0;
+        if (o[0] + o[1] + o[2] != 0) gq = o[0] == 0 ? std::min(o[1], o[2]) : (o[1] == 0 ? std::min(o[0], o[2]) : std::min(o[0], o[1]));
+        gq = std::min(gq, 255u);
+        out << "\t";
+        if (gq == 0) out << "./.:0,0,0";
+        else out << (o[2] == 0 ? "1" : "0") << "/" << (o[0] != 0 ? "1" : "0") << ":" << std::min(o[0], 255u) << "," << std::min(o[1], 255u) << "," << std::min(o[2], 255u);
+        out << ":" << gq << ":" << o[3] << "," << o[4] << "," << o[5] << ":" << o[6] << "," << o[7] << "," << o[8] << "," << o[9] << "," << o[10]
+            << ":" << o[11] << "," << o[12] << ":" << o[12] - o[11];
+    }
+    out << "\n";
+}
+
+struct Options {
+    std::vector<std::string> files;
+    std::string out = "popdel.vcf";
+    bool windowWise = false, outputFailed = false, smoothing = true, uncompressed = false, somatic = false;
+    long minInit = -1, minLen = -1;
+    unsigned maxLoad = 100, buffer = 200000, iterations = 15, pseudo = 500;
+    double prior = 0.0001, minSampleFraction = 0.1, minCover = 0.5;
+    int device = 0;
+};
+
+}  // namespace
+
+int main(int argc, char ** argv)
+{
+    Options opt;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        auto val = [&]() -> std::string { if (i + 1 >= argc) die("missing value for " + a); return argv[++i]; };
+        if (a == "-o" || a == "--out") opt.out = val();
+        else if (a == "-n" || a == "--no-regenotyping") opt.windowWise = true;
+        else if (a == "-F" || a == "--output-failed") opt.outputFailed = true;
+        else if (a == "-u" || a == "--unsmoothed") opt.smoothing = false;
+        else if (a == "-x" || a == "--uncompressed-in") opt.uncompressed = true;
+        else if (a == "-C" || a == "--cell-population") opt.somatic = true;
+        else if (a == "-l" || a == "--min-init-length") opt.minInit = atol(val().c_str());
+        else if (a == "-m" || a == "--min-length") opt.minLen = atol(val().c_str());
+        else if (a == "-a" || a == "--active-coverage") opt.maxLoad = (unsigned)atol(val().c_str());
+        else if (a == "-b" || a == "--buffer-size") opt.buffer = (unsigned)atol(val().c_str());
+        else if (a == "-t" || a == "--iterations") opt.iterations = (unsigned)atol(val().c_str());
+        else if (a == "-f" || a == "--pseudocount-fraction") opt.pseudo = (unsigned)atol(val().c_str());
+        else if (a == "-p" || a == "--prior-probability") opt.prior = atof(val().c_str());
+        else if (a == "-s" || a == "--min-sample-fraction") opt.minSampleFraction = atof(val().c_str());
+        else if (a == "-c" || a == "--min-relative-window-cover") opt.minCover = atof(val().c_str());
+        else if (a == "-g" || a == "--gpu") opt.device = atoi(val().c_str());
+        else if (a == "-r" || a == "-R" || a == "-A" || a == "-e" || a == "-d") die("option " + a + " is not supported by this build (whole contigs, default read-group handling)");
+        else if (!a.empty() && a[0] == '-') die("unknown option " + a);
+        else opt.files.push_back(a);
+    }
+    if (opt.files.empty()) die("usage: popdel_b200_call [options] PROFILE-LIST-FILE | PROFILE1 PROFILE2 ...");
+    if (opt.files.size() == 1) {                                     // a list of profile paths, one per line
+        std::ifstream lf(opt.files[0]);
+        if (!lf.good()) die("cannot open '" + opt.files[0] + "'");
+        std::string first7(7, '\0');
+        lf.read(&first7[0], 7);
+        if (first7 != std::string("POPDEL\1", 7)) {
+            lf.clear(); lf.seekg(0);
+            std::vector<std::string> listed; std::string line;
+            while (std::getline(lf, line)) if (!line.empty()) listed.push_back(line);
+            opt.files = listed;
+        }
+    }
+    const size_t N = opt.files.size();
+    std::vector<Profile> profiles(N);
+    for (size_t i = 0; i < N; ++i) loadProfile(opt.files[i], opt.uncompressed, profiles[i]);
+
+    // ---- histograms and parameters (reference parameter_calculation_popdel_call.h:160-204)
+    std::vector<pd_rg> rgs;
+    std::vector<std::vector<double>> tables;
+    std::vector<std::vector<uint32_t>> sampleRgs(N);
+    std::set<std::string> seen;
+    for (size_t i = 0; i < N; ++i)
+        for (const RgHeader & h : profiles[i].rgs) {
+            if (!seen.insert(h.name).second) die("duplicate read group '" + h.name + "' (use unique read-group IDs)");
+            tables.push_back(h.counts);
+            pd_rg r; memset(&r, 0, sizeof(r));
+            r.sample = (uint32_t)i; r.median = h.median; r.read_length = h.readLength; r.stddev = h.stddev; r.offset = h.offset;
+            r.len = (uint32_t)h.counts.size();
+            r.min_prob = pd_process_histogram(tables.back().data(), r.len, r.offset, r.median, r.read_length, opt.smoothing, opt.pseudo,
+                                              &r.lower_quantile_dist, &r.upper_quantile_dist);
+            sampleRgs[i].push_back((uint32_t)rgs.size());
+            rgs.push_back(r);
+        }
+    const size_t R = rgs.size();
+    double meanStddev = 0;
+    for (size_t g = 0; g < R; ++g) { rgs[g].values = tables[g].data(); meanStddev += rgs[g].stddev; }
+    meanStddev /= R;
+    std::vector<unsigned> minInit(R);
+    for (size_t g = 0; g < R; ++g) {
+        minInit[g] = opt.minInit >= 0 ? (unsigned)opt.minInit : (unsigned)rnd(4 * rgs[g].stddev);
+        rgs[g].min_init_del_len = minInit[g];
+        rgs[g].max_load = opt.maxLoad == 0 ? 0xFFFFFFFFu : opt.maxLoad;
+    }
+    pd_params prm; memset(&prm, 0, sizeof(prm));
+    {
+        std::vector<unsigned> v = minInit;
+        std::sort(v.begin(), v.end());
+        const unsigned n = (unsigned)v.size();
+        const unsigned j = (unsigned)std::floor(n * 0.95);
+        const unsigned pct = (j != n * 0.95) ? v[j] : v[j - 1];
+        prm.min_len = opt.minLen >= 0 ? (uint32_t)opt.minLen : (uint32_t)rnd(1.0 * pct);
+    }
+    prm.iterations = opt.iterations;
+    prm.min_lr = (6.6349 / 2.0) - std::log(opt.prior / (1 - opt.prior));
+    prm.min_sample_fraction = opt.minSampleFraction;
+    prm.window_size = 30; prm.window_buffer = opt.buffer;
+    prm.somatic = opt.somatic; prm.window_wise = opt.windowWise;
+
+    pd_ctx * ctx = pd_create(&prm, (uint32_t)N, (uint32_t)R, rgs.data(), opt.device);
+    if (!ctx) die(std::string("cannot create the scan context: ") + pd_create_error());
+    auto check = [&](int rc) { if (rc != 0) die(std::string("scan library: ") + pd_last_error(ctx)); };
+
+    std::ofstream out(opt.out);
+    if (!out.good()) die("cannot open output '" + opt.out + "'");
+    writeHeader(out, profiles[0], opt.files);
+    const QualMap qm;
+    const uint32_t WB = opt.buffer;
+    uint64_t totalWindows = 0, totalCalls = 0;
+
+    // ---- regions of interest = the contigs of the first profile, in order (reference load_profile_popdel_call.h:108-157)
+    for (int32_t c = 0; c < (int32_t)profiles[0].contigNames.size(); ++c) {
+        // first 30-bp window of the contig over all samples (getFirstWindowCoordinate, load_profile :291-350)
+        bool found = false; uint32_t anchor = 0xFFFFFFFFu;
+        std::vector<Bucket> buckets;
+        for (size_t i = 0; i < N; ++i) {
+            const Profile & p = profiles[i];
+            if ((size_t)c >= p.contigNames.size()) continue;
+            size_t w = indexSeek(p, c, 0);
+            if (w >= p.contigFirst[c + 1]) continue;
+            convertWindow(p.wins[w], buckets);
+            if (buckets.empty()) continue;
+            found = true; anchor = std::min(anchor, buckets[0].begin);
+        }
+        if (!found) continue;
+        check(pd_contig_begin(ctx, anchor));
+
+        // segment loader: which read pairs does the reference load in which iteration of its segment loop
+        // (workflow_popdel.h:297-366, readSegment load_profile :526-587). Iteration t accepts buckets below
+        // R = anchor + (t+1)*buffer; every sample re-enters through the index at the smallest bucket any sample
+        // stopped at, so read pairs between that position and the next 10-kbp index boundary of a straddling
+        // 256-bp window are never loaded.
+        std::vector<std::vector<uint32_t>> ppos(R);
+        std::vector<std::vector<int32_t>> pdev(R);
+        std::vector<uint32_t> cand(N, anchor);
+        std::vector<bool> fin(N, false);
+        uint32_t rb = anchor;
+        uint64_t Rt = (uint64_t)anchor + WB;
+        while (true) {
+            uint32_t nextRead = 0xFFFFFFFFu;
+            bool allFin = true;
+            for (size_t i = 0; i < N; ++i) {
+                if (fin[i]) continue;
+                if ((uint64_t)cand[i] >= Rt) { allFin = false; continue; }            // sits out this iteration
+                const Profile & p = profiles[i];
+                if ((size_t)c >= p.contigNames.size()) { fin[i] = true; continue; }
+                size_t w = indexSeek(p, c, rb);
+                bool stopped = false;
+                for (; !stopped; ++w) {
+                    if (w >= p.contigFirst[c + 1]) { fin[i] = true; break; }         // next contig or end of file
+                    const Win & win = p.wins[w];
+                    if ((uint64_t)win.begin + 255 < rb) continue;
+                    convertWindow(win, buckets);
+                    for (const Bucket & b : buckets) {
+                        if (b.begin < rb) continue;
+                        if ((uint64_t)b.begin >= Rt) { cand[i] = b.begin; nextRead = std::min(nextRead, b.begin); stopped = true; break; }
+                        for (size_t r = 0; r < b.rg.size(); ++r)
+                            for (const Rec & x : b.rg[r]) { ppos[sampleRgs[i][r]].push_back(x.pos); pdev[sampleRgs[i][r]].push_back(x.dev); }
+                    }
+                }
+                if (!fin[i]) allFin = false;
+            }
+            if (allFin) break;
+            if (nextRead != 0xFFFFFFFFu) rb = nextRead;
+            Rt += WB;
+        }
+        for (size_t g = 0; g < R; ++g) check(pd_contig_push(ctx, (uint32_t)g, ppos[g].size(), ppos[g].data(), pdev[g].data()));
+
+        pd_result res;
+        check(pd_contig_scan(ctx, 0, 0, &res));
+        totalWindows += res.n_windows;
+        // calls of one processSegment() call = calls with the same segment index
+        const std::string & chrom = profiles[0].contigNames[c];
+        size_t k = 0;
+        while (k < res.n_calls) {
+            std::vector<Call> seg;
+            const uint32_t sidx = res.calls[k].segment;
+            for (; k < res.n_calls && res.calls[k].segment == sidx; ++k) {
+                const pd_call & pc = res.calls[k];
+                Call cl;
+                cl.initialLength = pc.initial_length; cl.iterations = pc.iterations; cl.deletionLength = pc.deletion_length;
+                cl.filter = pc.filter; cl.lr = pc.lr; cl.frequency = pc.frequency; cl.windowPosition = pc.window_position;
+                cl.position = pc.position; cl.endPosition = pc.end_position;
+                cl.ps.assign(res.per_sample + k * 13ull * N, res.per_sample + (k + 1) * 13ull * N);
+                seg.push_back(std::move(cl));
+            }
+            if (!opt.windowWise && !unifySegment(seg, meanStddev, opt.minCover, opt.outputFailed)) continue;
+            for (const Call & cl : seg)
+                if (cl.iterations != 0 && (opt.outputFailed || allPass(cl))) { writeRecord(out, chrom, cl, qm); ++totalCalls; }
+            out.flush();
+        }
+    }
+    pd_destroy(ctx);
+    std::cout << "[popdel_b200] scanned " << totalWindows << " windows x " << N << " samples, wrote " << totalCalls
+              << " records to '" << opt.out << "'" << std::endl;
+    return 0;
+}
