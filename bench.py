@@ -145,6 +145,17 @@ def run_ours(args, rank, world, local_rank):
         with ThreadPoolExecutor(threads) as ex:
             list(ex.map(lambda s: sc.push(s, cohort[s][0], cohort[s][2]), range(N)))
 
+    # page-locked copies of the host arrays for the end-to-end path (pd_contig_push_pinned packs on the device)
+    def pin(a):
+        t = torch.from_numpy(a.view(np.int32)).pin_memory()
+        return t, t.numpy().view(a.dtype)
+    pinned = [(pin(np.ascontiguousarray(c[0], dtype=np.uint32)), pin(np.ascontiguousarray(c[2], dtype=np.int32))) for c in cohort]
+
+    def push_all_pinned():
+        sc.begin_contig(anchor)
+        for s in range(N):
+            sc.push_pinned(s, pinned[s][0][1], pinned[s][1][1])
+
     def barrier():
         if dist is not None:
             dist.barrier()
@@ -174,17 +185,28 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- end to end through the C ABI from host arrays (pack -> pinned -> H2D -> scan -> D2H)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    push_all()
-    r2 = sc.scan(copy=False)                                        # warm-up (pinned buffers exist afterwards)
+    push_all_pinned()
+    r2 = sc.scan(copy=False)                                        # warm-up (device buffers exist afterwards)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        push_all()
+        push_all_pinned()
         r2 = sc.scan(copy=False)
     barrier()
     dt2 = time.perf_counter() - t0
     dt2, _ = sharding.reduce_timing(dt2, float(evals), dist, "cuda")
     e2e = evals_all * e2e_steps / dt2
+    assert int(r2["n_calls_check"]) == len(res["calls"]) if "n_calls_check" in r2 else len(r2["calls"]) == len(res["calls"])
+    # the same through pd_contig_push (sequential host packer, one thread per read group)
+    push_all()
+    r3 = sc.scan(copy=False)
+    barrier()
+    t0 = time.perf_counter()
+    push_all()
+    r3 = sc.scan(copy=False)
+    barrier()
+    dt3 = time.perf_counter() - t0
+    dt3, _ = sharding.reduce_timing(dt3, float(evals), dist, "cuda")
 
     if dist is not None:
         dist.barrier()
@@ -206,7 +228,8 @@ def run_ours(args, rank, world, local_rank):
                    "candidates": int(res["n_candidates"])},
         "clocks": clk,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(r2["h2d_bytes"]), "d2h_bytes_per_step": int(r2["d2h_bytes"]),
-                "steps": e2e_steps, "ms_per_step": dt2 / e2e_steps * 1e3},
+                "steps": e2e_steps, "ms_per_step": dt2 / e2e_steps * 1e3, "path": "pd_contig_push_pinned (device-side packing)",
+                "host_packer_value": evals_all / dt3, "host_packer_ms_per_step": dt3 * 1e3, "host_packer_h2d_bytes": int(r3["h2d_bytes"])},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "k_screen", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "bytes_per_eval": res["algorithmic_bytes"] / evals,

@@ -104,6 +104,14 @@ int pd_contig_begin(pd_ctx * ctx, uint32_t anchor);
  * May be called several times per read group (positions must keep increasing). Host buffers are reusable on return. */
 int pd_contig_push(pd_ctx * ctx, uint32_t rg, uint64_t n, const uint32_t * pos, const int32_t * dev);
 
+/* Fast path of pd_contig_push for PAGE-LOCKED host arrays (cudaHostAlloc / cudaHostRegister / torch pin_memory):
+ * the library only records the pointers; pd_contig_upload copies the raw arrays to the device and packs them THERE
+ * (tile search, scan, words, wide list). The arrays must stay valid and unchanged until pd_contig_upload (or the
+ * first pd_contig_scan) returns. One call per read group and contig; cannot be mixed with pd_contig_push. Same
+ * results as pd_contig_push: the active-coverage cap is checked exactly on the device and, if it would drop a read
+ * pair, the contig is transparently re-packed by the sequential host path. */
+int pd_contig_push_pinned(pd_ctx * ctx, uint32_t rg, uint64_t n, const uint32_t * pos, const int32_t * dev);
+
 /* Packs what was pushed and copies it to the device (pinned staging, async on the context's stream). */
 int pd_contig_upload(pd_ctx * ctx);
 

@@ -50,7 +50,7 @@ CALL_DTYPE = np.dtype([("initial_length", "<u4"), ("iterations", "<u4"), ("delet
                        ("end_position", "<u4"), ("segment", "<u4")])
 
 EXPORTS = ["pd_process_histogram", "pd_create", "pd_create_error", "pd_destroy", "pd_last_error", "pd_contig_begin",
-           "pd_contig_push", "pd_contig_upload", "pd_contig_scan", "pd_contig_window_count", "pd_synth_read_group",
+           "pd_contig_push", "pd_contig_push_pinned", "pd_contig_upload", "pd_contig_scan", "pd_contig_window_count", "pd_synth_read_group",
            "pd_debug_host_window_sums"]
 
 _lib = None
@@ -76,6 +76,7 @@ def load_library(path: str = LIB_PATH):
     lib.pd_last_error.argtypes = [C.c_void_p]
     lib.pd_contig_begin.argtypes = [C.c_void_p, C.c_uint32]
     lib.pd_contig_push.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
+    lib.pd_contig_push_pinned.argtypes = lib.pd_contig_push.argtypes
     lib.pd_contig_upload.argtypes = [C.c_void_p]
     lib.pd_contig_scan.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(PdResult)]
     lib.pd_contig_window_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
@@ -213,6 +214,16 @@ class Scanner:
         self._check(self.lib.pd_contig_push(self.ctx, int(rg), pos.size, pos.ctypes.data_as(C.POINTER(C.c_uint32)),
                                             dev.ctypes.data_as(C.POINTER(C.c_int32))))
 
+    def push_pinned(self, rg: int, pos: np.ndarray, dev: np.ndarray):
+        """pd_contig_push_pinned: `pos` (uint32) / `dev` (int32) must be C-contiguous views of page-locked memory and
+        stay alive and unchanged until upload()/scan() returns."""
+        assert pos.dtype == np.uint32 and dev.dtype == np.int32 and pos.flags.c_contiguous and dev.flags.c_contiguous
+        assert pos.size == dev.size
+        self._pinned_keep = getattr(self, "_pinned_keep", {})
+        self._pinned_keep[rg] = (pos, dev)
+        self._check(self.lib.pd_contig_push_pinned(self.ctx, int(rg), pos.size, pos.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                   dev.ctypes.data_as(C.POINTER(C.c_int32))))
+
     def upload(self):
         self._check(self.lib.pd_contig_upload(self.ctx))
 
@@ -274,7 +285,8 @@ def cohort_anchor(samples) -> int:
     return (min(first) // 30) * 30
 
 
-def scan_cohort(samples, params: CallParameters, device: int = 0, first_window: int = 0, n_windows: int = 0):
+def scan_cohort(samples, params: CallParameters, device: int = 0, first_window: int = 0, n_windows: int = 0,
+                pinned: bool = False):
     """Convenience: whole in-memory cohort (popdel_b200.simulate objects) -> window calls of one contig."""
     rgs = read_groups_from_headers([[dict(name=rg.spec.name, median=rg.median, stddev=rg.stddev,
                                           read_length=rg.spec.read_length, hist_start=rg.hist_start,
@@ -286,7 +298,10 @@ def scan_cohort(samples, params: CallParameters, device: int = 0, first_window: 
         g = 0
         for s in samples:
             for rg in s.read_groups:
-                sc.push(g, rg.pos, rg.dev)
+                if pinned:
+                    sc.push_pinned(g, np.ascontiguousarray(rg.pos, dtype=np.uint32), np.ascontiguousarray(rg.dev, dtype=np.int32))
+                else:
+                    sc.push(g, rg.pos, rg.dev)
                 g += 1
         return sc.scan(first_window, n_windows), rgs
     finally:

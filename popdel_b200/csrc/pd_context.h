@@ -61,6 +61,8 @@ struct PdHostRg {                    // host staging of one read group of the cu
     int64_t prev_seg = -1, prev_E_spill = -1;         // previous non-empty segment
 };
 
+struct PdRawRg { const uint32_t * pos = nullptr; const int32_t * dev = nullptr; uint64_t n = 0; };   // pd_contig_push_pinned
+
 struct pd_ctx {
     pd_params params;
     uint32_t N = 0, R = 0;
@@ -77,6 +79,8 @@ struct pd_ctx {
     bool contig_open = false, packed = false, uploaded = false;
     PdGrid grid{0, 200000};
     std::vector<PdHostRg> hrg;
+    std::vector<PdRawRg> raw;            // caller-owned page-locked arrays (device-side packing)
+    bool dev_mode = false, host_mode = false;
     // packed host image (offset tables; the words stay in the per-read-group staging vectors)
     std::vector<PdTile> h_tiles;
     std::vector<uint32_t> h_long_off;
@@ -98,6 +102,7 @@ struct pd_ctx {
     PdTab * d_tab = nullptr;
     // scan scratch (grown on demand)
     void * d_scratch[24] = {}; size_t cap_scratch[24] = {};
+    void * d_pack[8] = {}; size_t cap_pack[8] = {};          // device packer scratch (raw arrays, tile firsts, ...)
     // results
     std::vector<pd_call> res_calls;
     uint32_t * res_ps = nullptr; size_t cap_res_ps = 0;    // pinned
@@ -107,6 +112,7 @@ struct pd_ctx {
 
 int pd_fail(pd_ctx * c, int status, const std::string & msg);
 int pd_pack_contig(pd_ctx * c);                    // finalises the offset tables of the packed image
+int pd_pack_on_device(pd_ctx * c);                // pd_pack.cu: 0 ok, 1 = use the host packer, <0 error
 int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result * out);   // pd_kernels.cu
 
 #endif

@@ -167,6 +167,7 @@ extern "C" pd_ctx * pd_create(const pd_params * p, uint32_t n_samples, uint32_t 
     }
     c->t_min = (int32_t)std::min<int64_t>(tmin, PD_DEV_MAX - 1);
     c->hrg.resize(n_rg);
+    c->raw.resize(n_rg);
     if (device >= 0) {
         int ndev = 0;
         cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -194,6 +195,7 @@ extern "C" void pd_destroy(pd_ctx * c)
         cudaFree(c->d_rgc); cudaFree(c->d_sample_rg); cudaFree(c->d_tab);
         if (c->res_ps) cudaFreeHost(c->res_ps);
         for (auto & p : c->d_scratch) cudaFree(p);
+        for (auto & p : c->d_pack) cudaFree(p);
         for (auto & ev : c->ev) if (ev) cudaEventDestroy(ev);
         if (c->stream) cudaStreamDestroy(c->stream);
         if (c->stream2) cudaStreamDestroy(c->stream2);
@@ -237,6 +239,8 @@ extern "C" int pd_contig_begin(pd_ctx * c, uint32_t anchor)
         h.words = w; h.cap_words = cap;
         h.tile_rel.assign(1, 0u);
     }
+    for (auto & r : c->raw) r = PdRawRg();
+    c->dev_mode = c->host_mode = false;
     c->contig_open = true; c->packed = false; c->uploaded = false;
     c->n_windows_total = 0; c->n_reads = 0;
     return 0;
@@ -253,6 +257,8 @@ extern "C" int pd_contig_push(pd_ctx * c, uint32_t rg, uint64_t n, const uint32_
     if (c->status) return c->status;
     if (!c->contig_open || rg >= c->R || (n && (!pos || !dev))) return pd_fail(c, PD_ERR_ARG, "pd_contig_push: bad arguments or no open contig");
     if (c->packed) return pd_fail(c, PD_ERR_ARG, "pd_contig_push: contig already packed");
+    if (c->dev_mode) return pd_fail(c, PD_ERR_ARG, "pd_contig_push: cannot be mixed with pd_contig_push_pinned in one contig");
+    c->host_mode = true;
     PdHostRg & h = c->hrg[rg];
     const PdRgConst & k = c->rgc[rg];
     const bool capped = k.max_load != 0xFFFFFFFFu;
@@ -407,11 +413,26 @@ int pd_pack_contig(pd_ctx * c)
     return 0;
 }
 
+extern "C" int pd_contig_push_pinned(pd_ctx * c, uint32_t rg, uint64_t n, const uint32_t * pos, const int32_t * dev)
+{
+    if (!c) return PD_ERR_ARG;
+    if (c->status) return c->status;
+    if (!c->contig_open || rg >= c->R || (n && (!pos || !dev))) return pd_fail(c, PD_ERR_ARG, "pd_contig_push_pinned: bad arguments or no open contig");
+    if (c->device < 0) return pd_fail(c, PD_ERR_CUDA, "pd_contig_push_pinned: host-only context");
+    if (c->host_mode || c->packed) return pd_fail(c, PD_ERR_ARG, "pd_contig_push_pinned: cannot be mixed with pd_contig_push / contig already packed");
+    if (c->raw[rg].n) return pd_fail(c, PD_ERR_ARG, "pd_contig_push_pinned: one call per read group and contig");
+    c->dev_mode = true;
+    c->raw[rg] = PdRawRg{pos, dev, n};
+    return 0;
+}
+
 extern "C" int pd_contig_window_count(pd_ctx * c, uint64_t * n)
 {
     if (!c || !n) return PD_ERR_ARG;
     if (c->status) return c->status;
     if (!c->contig_open) return pd_fail(c, PD_ERR_ARG, "no open contig");
+    if (c->dev_mode && !c->uploaded) { int rc0 = pd_contig_upload(c); if (rc0) return rc0; }
+    if (c->dev_mode) { *n = c->n_windows_total; return 0; }
     int rc = pd_pack_contig(c);
     if (rc) return rc;
     *n = c->n_windows_total;
@@ -437,6 +458,18 @@ extern "C" int pd_contig_upload(pd_ctx * c)
     if (c->device < 0) return pd_fail(c, PD_ERR_CUDA, "pd_contig_upload: host-only context (device = -1); the scan needs a CUDA device");
     if (!c->contig_open) return pd_fail(c, PD_ERR_ARG, "no open contig");
     if (c->uploaded) return 0;
+    if (c->dev_mode) {
+        int prc = pd_pack_on_device(c);
+        if (prc < 0) return prc;
+        if (prc == 0) { c->packed = true; c->uploaded = true; return 0; }
+        // the active-coverage cap would drop read pairs (or a span exceeds the device look-back): sequential host path
+        c->dev_mode = false;
+        for (uint32_t g = 0; g < c->R; ++g) {
+            const PdRawRg r = c->raw[g];
+            int hrc = pd_contig_push(c, g, r.n, r.pos, r.dev);
+            if (hrc) return hrc;
+        }
+    }
     int rc = pd_pack_contig(c);
     if (rc) return rc;
     PD_CUDA(c, cudaSetDevice(c->device));
@@ -481,6 +514,7 @@ extern "C" int pd_debug_host_window_sums(pd_ctx * c, uint32_t rg, uint64_t first
     if (!c || !out || rg >= c->R) return PD_ERR_ARG;
     if (c->status) return c->status;
     if (!c->contig_open) return pd_fail(c, PD_ERR_ARG, "no open contig");
+    if (c->dev_mode) return pd_fail(c, PD_ERR_ARG, "validation hook works on host-packed contigs only");
     int rc = pd_pack_contig(c);
     if (rc) return rc;
     memset(out, 0, sizeof(int64_t) * 3 * n_windows);

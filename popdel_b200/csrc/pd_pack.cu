@@ -1,0 +1,444 @@
+// pd_pack.cu -- device-side packer: raw (pos, dev) arrays -> tiled 32-bit stream, tile table and wide list.
+//
+// Used by pd_contig_push_pinned(): the host only enqueues the H2D copies of the caller's page-locked arrays; tile
+// boundaries (binary search), padded tile offsets (scan), the packed words, the wide list of long read pairs and its
+// per-tile ranges are produced by the kernels below, with the same closed-form rule (pd_common.h) as the host packer.
+// The active-coverage cap (ChromosomeProfile::add, profile_structure_popdel_call.h:1084-1113) is checked exactly on
+// the device (open pairs at every read pair = i - #{lastWindow < bucket}); if it would drop anything, or a read pair
+// spans more than the supported look-back, the contig is re-packed by the sequential host path instead.
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pd_context.h"
+
+#define PD_CUDA(c, call)                                                                          \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return pd_fail((c), PD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+namespace {
+
+constexpr int CAP_CHUNK_TILES = 32;
+constexpr int CAP_MAX_LOOKBACK = 64;                       // tiles; beyond that the host path is used
+constexpr int CAP_BINS = (CAP_MAX_LOOKBACK + CAP_CHUNK_TILES) * 32 + 32;
+
+struct PackArgs {
+    const uint32_t * pos; const int32_t * dev;             // raw arrays, all read groups
+    const uint64_t * rg_start;                             // [R+1]
+    const PdRgConst * rgc;
+    uint32_t R, NT, anchor, window_buffer;
+    uint32_t * tfirst;                                     // [R][NT+1] first read pair (RG-relative) of each tile
+    uint32_t * flags;                                      // [0] unsorted, [1] cap would drop, [2] position before anchor
+    uint32_t * span_tiles;                                 // [R] max (tile of last window - tile of the read pair)
+};
+
+__global__ void k_tile_first(PackArgs a)
+{
+    const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t per = (uint64_t)a.NT + 1;
+    if (id >= per * a.R) return;
+    const uint32_t g = (uint32_t)(id / per), t = (uint32_t)(id % per);
+    const uint32_t * p = a.pos + a.rg_start[g];
+    const uint64_t n = a.rg_start[g + 1] - a.rg_start[g];
+    const uint64_t key = (uint64_t)a.anchor + (uint64_t)t * PD_TILE_BP;
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if ((uint64_t)p[mid] < key) lo = mid + 1; else hi = mid; }
+    a.tfirst[id] = (uint32_t)lo;
+}
+
+// per read pair: order check and the largest tile span per read group
+__global__ void k_check_span(PackArgs a, uint64_t total)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    // read group of i: R is small, linear search over the (cached) starts
+    uint32_t g = 0;
+    while (g + 1 < a.R && i >= a.rg_start[g + 1]) ++g;
+    const uint32_t p = a.pos[i];
+    if (p < a.anchor) { atomicOr(&a.flags[2], 1u); return; }
+    if (i > a.rg_start[g] && a.pos[i - 1] > p) atomicOr(&a.flags[0], 1u);
+    const uint32_t pr = p - a.anchor;
+    int64_t inner = (int64_t)a.dev[i] + a.rgc[g].inner_off;
+    if (inner < 0) inner = 0;
+    const uint64_t lw = ((uint64_t)pr + (uint64_t)inner) / PD_WIN;
+    const uint32_t span = (uint32_t)min((uint64_t)0xFFFFu, (lw + 1) / PD_TILE_WINDOWS - pr / PD_TILE_BP);
+    if (span > a.rgc[g].lookback_tiles) atomicMax(&a.span_tiles[g], span);
+}
+
+// exact check of the active-coverage cap: one block per (read group, chunk of 32 tiles)
+__global__ void __launch_bounds__(1024) k_cap_check(PackArgs a, uint32_t chunks_per_rg)
+{
+    __shared__ uint32_t hist[CAP_BINS + 1];
+    __shared__ uint32_t wsum[32];
+    const uint32_t g = blockIdx.x / chunks_per_rg, ch = blockIdx.x % chunks_per_rg;
+    const uint32_t max_load = a.rgc[g].max_load;
+    if (max_load == 0xFFFFFFFFu) return;
+    const uint32_t kl = max(a.span_tiles[g], a.rgc[g].lookback_tiles);
+    if (kl > CAP_MAX_LOOKBACK) return;                                    // host path decides (flagged by the caller)
+    const uint32_t t0 = ch * CAP_CHUNK_TILES;
+    if (t0 >= a.NT) return;
+    const uint32_t t1 = min(t0 + CAP_CHUNK_TILES, a.NT);
+    const uint32_t tl = t0 > kl ? t0 - kl : 0;
+    const uint32_t * tf = a.tfirst + (size_t)g * (a.NT + 1);
+    const uint32_t i_lo = tf[tl], i_mid = tf[t0], i_hi = tf[t1];
+    if (i_hi - i_lo < max_load) return;                                   // cannot reach the cap at all
+    const uint32_t * p = a.pos + a.rg_start[g];
+    const int32_t * d = a.dev + a.rg_start[g];
+    const int32_t inner_off = a.rgc[g].inner_off;
+    const uint32_t w_lo = tl * PD_TILE_WINDOWS;
+    const uint32_t nbins = (t1 - tl) * PD_TILE_WINDOWS + 1;              // last bin: last window beyond the chunk
+    for (uint32_t b = threadIdx.x; b <= nbins; b += blockDim.x) hist[b] = 0;
+    __syncthreads();
+    for (uint32_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+        const uint32_t pr = p[i] - a.anchor;
+        int64_t inner = (int64_t)d[i] + inner_off;
+        if (inner < 0) inner = 0;
+        const uint64_t lw = ((uint64_t)pr + (uint64_t)inner) / PD_WIN;
+        const uint32_t bin = (uint32_t)min((uint64_t)(nbins - 1), lw - w_lo);
+        atomicAdd(&hist[bin], 1u);
+    }
+    __syncthreads();
+    // exclusive prefix sum over the bins: C[x] = number of read pairs in range with last window < w_lo + x
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < nbins; base += blockDim.x) {
+        const uint32_t b = base + threadIdx.x;
+        uint32_t v = b < nbins ? hist[b] : 0, inc = v;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, o); if ((threadIdx.x & 31) >= o) inc += n; }
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t s = wsum[threadIdx.x], si = s;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t n = __shfl_up_sync(0xFFFFFFFFu, si, o); if (threadIdx.x >= o) si += n; }
+            wsum[threadIdx.x] = si - s;
+        }
+        __syncthreads();
+        const uint32_t excl = carry + wsum[threadIdx.x >> 5] + inc - v;
+        __syncthreads();
+        if (b < nbins) hist[b] = excl;
+        // total of this round
+        if (threadIdx.x == blockDim.x - 1) wsum[0] = excl + v;
+        __syncthreads();
+        carry = wsum[0];
+        __syncthreads();
+    }
+    bool bad = false;
+    for (uint32_t i = i_mid + threadIdx.x; i < i_hi; i += blockDim.x) {
+        const uint32_t b = (p[i] - a.anchor) / PD_WIN;
+        const uint32_t open = (i - i_lo) - hist[b - w_lo];
+        bad |= open >= max_load;
+    }
+    if (bad) atomicOr(&a.flags[1], 1u);
+}
+
+// padded tile sizes -> tile offsets (relative to the read group); one block per read group, sequential chunks
+__global__ void __launch_bounds__(1024) k_tile_offsets(PackArgs a, uint32_t * rel_off /*[R][NT+1]*/, uint64_t * rg_words /*[R]*/)
+{
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t s_carry;
+    const uint32_t g = blockIdx.x;
+    const uint32_t * tf = a.tfirst + (size_t)g * (a.NT + 1);
+    uint32_t * ro = rel_off + (size_t)g * (a.NT + 1);
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < a.NT; base += blockDim.x) {
+        const uint32_t t = base + threadIdx.x;
+        const uint32_t v = t < a.NT ? ((tf[t + 1] - tf[t] + 3u) & ~3u) : 0u;
+        uint32_t inc = v;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, o); if ((threadIdx.x & 31) >= o) inc += n; }
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t s = wsum[threadIdx.x], si = s;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t n = __shfl_up_sync(0xFFFFFFFFu, si, o); if (threadIdx.x >= o) si += n; }
+            wsum[threadIdx.x] = si - s;
+        }
+        __syncthreads();
+        const uint32_t excl = s_carry + wsum[threadIdx.x >> 5] + inc - v;
+        if (t < a.NT) ro[t] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { ro[a.NT] = s_carry; rg_words[g] = s_carry; }
+}
+
+struct WriteArgs {
+    uint32_t * words; PdTile * tiles; PdLong * longs;
+    const uint32_t * rel_off; const uint64_t * word_base;          // [R]
+    uint32_t * lcount;                                              // [R][NT+1] long read pairs per tile -> offsets
+    const uint64_t * long_base;                                     // [R]
+    uint32_t * pmax;                                                // prefix max of e over the wide list
+};
+
+// one thread per (read group, tile): words, pads, count of long read pairs (pass 0) / wide entries (pass 1)
+__global__ void k_pack_tiles(PackArgs a, WriteArgs w, int pass)
+{
+    const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t per = (uint64_t)a.NT + 1;
+    if (id >= per * a.R) return;
+    const uint32_t g = (uint32_t)(id / per), t = (uint32_t)(id % per);
+    if (t >= a.NT) { if (pass == 0) w.lcount[id] = 0; return; }
+    const PdRgConst k = a.rgc[g];
+    const uint32_t * tf = a.tfirst + (size_t)g * per;
+    const uint32_t * p = a.pos + a.rg_start[g];
+    const int32_t * d = a.dev + a.rg_start[g];
+    const uint32_t i0 = tf[t], i1 = tf[t + 1];
+    uint32_t * out = w.words + w.word_base[g] + w.rel_off[id];
+    PdLong * lout = pass == 1 ? w.longs + w.long_base[g] + w.lcount[id] : nullptr;
+    uint32_t nl = 0;
+    for (uint32_t i = i0; i < i1; ++i) {
+        const uint32_t pr = p[i] - a.anchor;
+        const int32_t dv = d[i];
+        int64_t s, e;
+        const bool act = pd_interval(pr, dv, k.inner_off, a.window_buffer, s, e);
+        bool is_long = dv > PD_DEV_MAX || dv < PD_DEV_MIN + 1;
+        if (act && (uint64_t)e / PD_TILE_WINDOWS > (uint64_t)t + k.lookback_tiles) is_long = true;
+        if (pass == 0) {
+            const int32_t dc = dv > PD_DEV_MAX ? PD_DEV_MAX : (dv < PD_DEV_MIN + 1 ? PD_DEV_MIN + 1 : dv);
+            out[i - i0] = pd_pack(dc, pr - t * PD_TILE_BP, is_long);
+        } else if (is_long && act) {
+            lout[nl] = PdLong{(uint32_t)s, (uint32_t)e, pr, dv};
+        }
+        nl += (is_long && act);
+    }
+    if (pass == 0) {
+        for (uint32_t i = i1 - i0; i & 3; ++i) out[i] = PD_PAD_WORD;
+        w.lcount[id] = nl;
+    }
+}
+
+// exclusive scan of lcount per read group (in place) and totals; one block per read group
+__global__ void __launch_bounds__(1024) k_long_offsets(PackArgs a, uint32_t * lcount, uint64_t * rg_longs)
+{
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t s_carry;
+    const uint32_t g = blockIdx.x;
+    uint32_t * lc = lcount + (size_t)g * (a.NT + 1);
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base <= a.NT; base += blockDim.x) {
+        const uint32_t t = base + threadIdx.x;
+        const uint32_t v = t <= a.NT ? lc[t] : 0u;
+        uint32_t inc = v;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, o); if ((threadIdx.x & 31) >= o) inc += n; }
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t s = wsum[threadIdx.x], si = s;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t n = __shfl_up_sync(0xFFFFFFFFu, si, o); if (threadIdx.x >= o) si += n; }
+            wsum[threadIdx.x] = si - s;
+        }
+        __syncthreads();
+        const uint32_t excl = s_carry + wsum[threadIdx.x >> 5] + inc - v;
+        if (t <= a.NT) lc[t] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) rg_longs[g] = s_carry;
+}
+
+// prefix maximum of e over each read group's wide list (lists are short: one thread per read group)
+__global__ void k_long_pmax(PackArgs a, WriteArgs w, const uint64_t * rg_longs)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.R) return;
+    const PdLong * L = w.longs + w.long_base[g];
+    uint32_t * pm = w.pmax + w.long_base[g];
+    uint32_t m = 0;
+    for (uint64_t i = 0; i < rg_longs[g]; ++i) { m = max(m, L[i].e); pm[i] = m; }
+}
+
+// tile table: word offset and the range [lo, hi) of wide entries that can be active in the tile
+__global__ void k_tile_table(PackArgs a, WriteArgs w, const uint64_t * rg_longs)
+{
+    const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t per = (uint64_t)a.NT + 1;
+    if (id >= per * a.R) return;
+    const uint32_t g = (uint32_t)(id / per), t = (uint32_t)(id % per);
+    const PdLong * L = w.longs + w.long_base[g];
+    const uint32_t * pm = w.pmax + w.long_base[g];
+    const uint64_t n = rg_longs[g];
+    const uint64_t w0 = (uint64_t)t * PD_TILE_WINDOWS;
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if ((uint64_t)L[mid].s <= w0 + PD_TILE_WINDOWS - 1) lo = mid + 1; else hi = mid; }
+    const uint64_t hi_t = lo;
+    lo = 0; hi = hi_t;
+    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if ((uint64_t)pm[mid] < w0) lo = mid + 1; else hi = mid; }
+    PdTile tl;
+    tl.off = (uint32_t)(w.word_base[g] + w.rel_off[id]);
+    tl.long_lo = (uint32_t)(w.long_base[g] + lo);
+    tl.long_hi = (uint32_t)(w.long_base[g] + hi_t);
+    tl.pad = 0;
+    w.tiles[id] = tl;
+}
+
+template <typename T>
+int grow_dev(pd_ctx * c, int slot, T *& p, size_t need)
+{
+    size_t bytes = std::max<size_t>(need, 1) * sizeof(T);
+    if (bytes > c->cap_pack[slot] || !c->d_pack[slot]) {
+        if (c->d_pack[slot]) cudaFree(c->d_pack[slot]);
+        c->d_pack[slot] = nullptr; c->cap_pack[slot] = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        PD_CUDA(c, cudaMalloc(&c->d_pack[slot], want));
+        c->cap_pack[slot] = want;
+    }
+    p = reinterpret_cast<T *>(c->d_pack[slot]);
+    return 0;
+}
+
+}  // namespace
+
+// Last window the reference scans (see last_scanned_window in pd_host.cu), from the tails of the raw host arrays.
+static uint64_t last_window_from_raw(const pd_ctx * c)
+{
+    const uint32_t wb = c->grid.window_buffer, anchor = c->grid.anchor;
+    int64_t kf = -1;
+    for (uint32_t g = 0; g < c->R; ++g) {
+        const PdRawRg & r = c->raw[g];
+        if (r.n) kf = std::max<int64_t>(kf, (int64_t)((uint64_t)((r.pos[r.n - 1] - anchor) / PD_WIN) * PD_WIN / wb));
+    }
+    if (kf < 0) return 0;
+    int64_t E = -1, S = -1;
+    for (uint32_t g = 0; g < c->R; ++g) {
+        const PdRawRg & r = c->raw[g];
+        const int32_t io = c->rgc[g].inner_off;
+        for (uint64_t i = r.n; i-- > 0;) {
+            const uint64_t pr = r.pos[i] - anchor;
+            const uint64_t b = pr / PD_WIN;
+            const int64_t j = (int64_t)(b * PD_WIN / wb);
+            if (j < kf - 1) break;
+            const int64_t inner = std::max<int64_t>(0, (int64_t)r.dev[i] + io);
+            const int64_t lw = (int64_t)((pr + inner) / PD_WIN);
+            const int64_t wl = (int64_t)pd_seg_last_window((uint64_t)j, wb);
+            if (j == kf) { S = std::max<int64_t>(S, (int64_t)pr); if (lw <= wl) E = std::max(E, lw); }
+            else if (lw > wl) E = std::max(E, lw);
+        }
+    }
+    const int64_t stop = std::max(E + 2, (S + 29) / (int64_t)PD_WIN);
+    const int64_t wl = (int64_t)pd_seg_last_window((uint64_t)kf, wb);
+    return (uint64_t)std::min(stop, wl) + 1;
+}
+
+// returns 0 on success, 1 when the contig must be packed by the host path instead, <0 on error
+int pd_pack_on_device(pd_ctx * c)
+{
+    PD_CUDA(c, cudaSetDevice(c->device));
+    const uint32_t R = c->R;
+    std::vector<uint64_t> rg_start(R + 1, 0);
+    uint32_t max_pos_rel = 0; bool any = false;
+    for (uint32_t g = 0; g < R; ++g) {
+        const PdRawRg & r = c->raw[g];
+        rg_start[g + 1] = rg_start[g] + r.n;
+        if (r.n) {
+            if (r.pos[0] < c->grid.anchor) return pd_fail(c, PD_ERR_ARG, "pd_contig_push_pinned: position before the contig anchor");
+            max_pos_rel = std::max(max_pos_rel, r.pos[r.n - 1] - c->grid.anchor); any = true;
+        }
+    }
+    const uint64_t total = rg_start[R];
+    if (total > 0xFFFFFFF0ull) return pd_fail(c, PD_ERR_CAPACITY, "more than 2^32 read pairs in one contig batch");
+    c->n_windows_total = any ? last_window_from_raw(c) : 0;
+    const uint32_t NT = (uint32_t)std::max<uint64_t>(std::max<uint64_t>((c->n_windows_total + PD_TILE_WINDOWS - 1) / PD_TILE_WINDOWS,
+                                                                        any ? (uint64_t)max_pos_rel / PD_TILE_BP + 1 : 0), 1);
+    c->NT = NT;
+    cudaStream_t st = c->stream;
+    uint32_t * d_pos; int32_t * d_dev; uint64_t * d_u64; uint32_t * d_tfirst, * d_rel, * d_lcount, * d_small, * d_pmax;
+    const size_t per = (size_t)NT + 1;
+    if (grow_dev(c, 0, d_pos, total)) return c->status;
+    if (grow_dev(c, 1, d_dev, total)) return c->status;
+    if (grow_dev(c, 2, d_u64, (size_t)5 * (R + 1))) return c->status;        // rg_start | rg_words | word_base | rg_longs | long_base
+    if (grow_dev(c, 3, d_tfirst, per * R)) return c->status;
+    if (grow_dev(c, 4, d_rel, per * R)) return c->status;
+    if (grow_dev(c, 5, d_lcount, per * R)) return c->status;
+    if (grow_dev(c, 6, d_small, (size_t)R + 16)) return c->status;           // flags[4] | span_tiles[R]
+    uint64_t * d_rg_start = d_u64, * d_rg_words = d_u64 + (R + 1), * d_word_base = d_u64 + 2 * (R + 1),
+             * d_rg_longs = d_u64 + 3 * (R + 1), * d_long_base = d_u64 + 4 * (R + 1);
+    PD_CUDA(c, cudaEventRecord(c->ev[0], st));
+    for (uint32_t g = 0; g < R; ++g) {
+        const PdRawRg & r = c->raw[g];
+        if (!r.n) continue;
+        PD_CUDA(c, cudaMemcpyAsync(d_pos + rg_start[g], r.pos, r.n * 4, cudaMemcpyHostToDevice, st));
+        PD_CUDA(c, cudaMemcpyAsync(d_dev + rg_start[g], r.dev, r.n * 4, cudaMemcpyHostToDevice, st));
+    }
+    PD_CUDA(c, cudaMemcpyAsync(d_rg_start, rg_start.data(), (R + 1) * 8, cudaMemcpyHostToDevice, st));
+    PD_CUDA(c, cudaMemsetAsync(d_small, 0, ((size_t)R + 16) * 4, st));
+    c->h2d_bytes = total * 8 + (R + 1) * 8;
+
+    PackArgs a;
+    a.pos = d_pos; a.dev = d_dev; a.rg_start = d_rg_start; a.rgc = c->d_rgc; a.R = R; a.NT = NT;
+    a.anchor = c->grid.anchor; a.window_buffer = c->grid.window_buffer; a.tfirst = d_tfirst; a.flags = d_small; a.span_tiles = d_small + 16;
+    const uint64_t ntile = per * R;
+    if (total) k_check_span<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, total);
+    k_tile_first<<<(unsigned)((ntile + 255) / 256), 256, 0, st>>>(a);
+    const uint32_t chunks = (NT + CAP_CHUNK_TILES - 1) / CAP_CHUNK_TILES;
+    k_cap_check<<<R * chunks, 1024, 0, st>>>(a, chunks);
+    k_tile_offsets<<<R, 1024, 0, st>>>(a, d_rel, d_rg_words);
+    PD_CUDA(c, cudaGetLastError());
+    std::vector<uint32_t> h_small((size_t)R + 16);
+    std::vector<uint64_t> h_words(R);
+    PD_CUDA(c, cudaMemcpyAsync(h_small.data(), d_small, h_small.size() * 4, cudaMemcpyDeviceToHost, st));
+    PD_CUDA(c, cudaMemcpyAsync(h_words.data(), d_rg_words, R * 8, cudaMemcpyDeviceToHost, st));
+    PD_CUDA(c, cudaStreamSynchronize(st));
+    if (h_small[2]) return pd_fail(c, PD_ERR_ARG, "pd_contig_push_pinned: position before the contig anchor");
+    if (h_small[0]) return pd_fail(c, PD_ERR_ORDER, "pd_contig_push_pinned: read pairs must be sorted by position");
+    bool fallback = h_small[1] != 0;
+    for (uint32_t g = 0; g < R; ++g)
+        if (c->rgc[g].max_load != 0xFFFFFFFFu && std::max(h_small[16 + g], c->rgc[g].lookback_tiles) > (uint32_t)CAP_MAX_LOOKBACK) fallback = true;
+    if (fallback) return 1;
+
+    std::vector<uint64_t> base(R + 1, 0);
+    for (uint32_t g = 0; g < R; ++g) base[g + 1] = base[g] + h_words[g];
+    if (base[R] > 0xFFFFFFF0ull) return pd_fail(c, PD_ERR_CAPACITY, "more than 2^32 packed words in one contig batch; split the cohort or the contig");
+    c->total_words = base[R];
+    c->n_reads = total;
+    PD_CUDA(c, cudaMemcpyAsync(d_word_base, base.data(), (R + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (c->total_words + 4 > c->cap_words || !c->d_words) {
+        if (c->d_words) cudaFree(c->d_words);
+        c->d_words = nullptr; c->cap_words = 0;
+        size_t want = c->total_words + c->total_words / 8 + 1024;
+        PD_CUDA(c, cudaMalloc(&c->d_words, want * 4));
+        c->cap_words = want;
+    }
+    if (ntile > c->cap_tiles || !c->d_tiles) {
+        if (c->d_tiles) cudaFree(c->d_tiles);
+        c->d_tiles = nullptr; c->cap_tiles = 0;
+        size_t want = ntile + ntile / 8 + 64;
+        PD_CUDA(c, cudaMalloc(&c->d_tiles, want * sizeof(PdTile)));
+        c->cap_tiles = want;
+    }
+    WriteArgs w;
+    w.words = c->d_words; w.tiles = c->d_tiles; w.longs = nullptr; w.rel_off = d_rel; w.word_base = d_word_base;
+    w.lcount = d_lcount; w.long_base = d_long_base; w.pmax = nullptr;
+    k_pack_tiles<<<(unsigned)((ntile + 127) / 128), 128, 0, st>>>(a, w, 0);
+    k_long_offsets<<<R, 1024, 0, st>>>(a, d_lcount, d_rg_longs);
+    PD_CUDA(c, cudaGetLastError());
+    std::vector<uint64_t> h_longs(R);
+    PD_CUDA(c, cudaMemcpyAsync(h_longs.data(), d_rg_longs, R * 8, cudaMemcpyDeviceToHost, st));
+    PD_CUDA(c, cudaStreamSynchronize(st));
+    std::vector<uint64_t> lbase(R + 1, 0);
+    for (uint32_t g = 0; g < R; ++g) lbase[g + 1] = lbase[g] + h_longs[g];
+    c->total_longs = lbase[R];
+    PD_CUDA(c, cudaMemcpyAsync(d_long_base, lbase.data(), (R + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (c->total_longs + 1 > c->cap_longs || !c->d_longs) {
+        if (c->d_longs) cudaFree(c->d_longs);
+        c->d_longs = nullptr; c->cap_longs = 0;
+        size_t want = c->total_longs + c->total_longs / 8 + 1024;
+        PD_CUDA(c, cudaMalloc(&c->d_longs, want * sizeof(PdLong)));
+        c->cap_longs = want;
+    }
+    if (grow_dev(c, 7, d_pmax, (size_t)c->total_longs + 1)) return c->status;
+    w.longs = c->d_longs; w.pmax = d_pmax;
+    k_pack_tiles<<<(unsigned)((ntile + 127) / 128), 128, 0, st>>>(a, w, 1);
+    k_long_pmax<<<(R + 63) / 64, 64, 0, st>>>(a, w, d_rg_longs);
+    k_tile_table<<<(unsigned)((ntile + 255) / 256), 256, 0, st>>>(a, w, d_rg_longs);
+    PD_CUDA(c, cudaGetLastError());
+    PD_CUDA(c, cudaEventRecord(c->ev[1], st));
+    PD_CUDA(c, cudaStreamSynchronize(st));
+    PD_CUDA(c, cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]));
+    return 0;
+}

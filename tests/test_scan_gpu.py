@@ -67,3 +67,23 @@ def test_larger_cohort(oracle_lib):
     samples, _ = simulate.simulate_cohort(seed=35, n_samples=40, contig_len=300_000, n_dels=4)
     stats = compare_scan_with_oracle(samples, oracle_lib)
     assert stats["n_calls"] > 100
+
+
+@pytest.mark.parametrize("kind", ["basic", "mixedrg", "gap", "highcov", "longspan"])
+def test_device_packer_equals_host_packer(kind):
+    """pd_contig_push_pinned (device-side packing; host fallback when the coverage cap bites) == pd_contig_push."""
+    samples, params = _cohort(kind)
+    a, _ = api.scan_cohort(samples, params)
+    b, _ = api.scan_cohort(samples, params, pinned=True)
+    assert a["n_windows"] == b["n_windows"] and a["n_flagged_windows"] == b["n_flagged_windows"]
+    assert a["n_reads"] == b["n_reads"]
+    assert_calls_equal(b["calls"], b["per_sample"], a["calls"], a["per_sample"], rtol=0)
+
+
+@pytest.mark.parametrize("n_samples,contig_len", [(150, 90_000), (300, 70_000)])
+def test_many_samples(n_samples, contig_len, oracle_lib):
+    """More samples than one EM block handles with several lanes per sample (exercises the 2- and 1-lane variants)."""
+    dels = [simulate.Deletion(30_000, 1200, np.random.default_rng(5).binomial(2, 0.3, size=n_samples))]
+    samples, _ = simulate.simulate_cohort(seed=36, n_samples=n_samples, contig_len=contig_len, n_dels=0, dels=dels)
+    stats = compare_scan_with_oracle(samples, oracle_lib)
+    assert stats["n_calls"] > 20
