@@ -56,22 +56,33 @@ def plant(seed, n_samples, length, per_mbp):
     return np.array(starts, np.uint32), np.array(lens, np.uint32), np.stack(gts)
 
 
-def make_cohort(seed, n_samples, length, per_mbp, threads):
+def make_cohort(seed, n_samples, length, per_mbp, threads, mixed=False):
+    """Returns (list of read groups [pos, isize, dev, header, sample], deletions). One read group per sample, or with
+    `mixed` 1-3 read groups per sample with mu in {350,450,550} and sigma in {30,50,80} (BASELINE.json configs[2])."""
     from popdel_b200 import api
     ds, dl, gt = plant(seed, n_samples, length, per_mbp)
+    rng = np.random.default_rng([seed, 77])
+    specs = []
+    for s in range(n_samples):
+        k = int(rng.integers(1, 4)) if mixed else 1
+        for j in range(k):
+            mu = float(rng.choice([350, 450, 550])) if mixed else 500.0
+            sd = float(rng.choice([30, 50, 80])) if mixed else 50.0
+            specs.append((s, len(specs), mu, sd, 0.1 / k))
 
-    def one(s):
-        pos, isz = api.synth_read_group(seed, s, 500.0, 50.0, 150, 0.1, 0, length, ds, dl, gt[:, s])
-        med = 500
-        lo, hi = max(1, int(np.floor(med - 150))), int(np.ceil(med + 150)) + 1
+    def one(spec):
+        s, g, mu, sd, dens = spec
+        pos, isz = api.synth_read_group(seed, g, mu, sd, 150, dens, 0, length, ds, dl, gt[:, s])
+        med = int(mu)
+        lo, hi = max(1, int(np.floor(med - 3 * sd))), int(np.ceil(med + 3 * sd)) + 1
         sel = isz[(isz >= lo) & (isz < hi)]
         counts = np.bincount(sel - lo, minlength=hi - lo).astype(np.float64)
-        hdr = dict(name=f"rg{s}", median=med, stddev=50.0, read_length=150, hist_start=lo, hist_end=hi, hist_counts=counts)
+        hdr = dict(name=f"rg{g}", median=med, stddev=sd, read_length=150, hist_start=lo, hist_end=hi, hist_counts=counts)
         dev = isz - np.int32(med)
-        return pos, isz, dev, hdr
+        return pos, isz, dev, hdr, s
 
     with ThreadPoolExecutor(threads) as ex:
-        out = list(ex.map(one, range(n_samples)))
+        out = list(ex.map(one, specs))
     return out, (ds, dl, gt)
 
 
@@ -133,17 +144,18 @@ def run_ours(args, rank, world, local_rank):
     threads = max(1, (os.cpu_count() or 8) // max(world, 1))
     N, L = args.samples, args.length
     t0 = time.time()
-    cohort, dels = make_cohort(args.seed + rank, N, L, args.dels_per_mbp, threads)     # rank r = window range r
+    cohort, dels = make_cohort(args.seed + rank, N, L, args.dels_per_mbp, threads, args.mixed)     # rank r = window range r
     t_gen = time.time() - t0
     params = api.CallParameters()
-    rgs = api.read_groups_from_headers([[c[3]] for c in cohort], params)
+    rgs = api.read_groups_from_headers([[c[3] for c in cohort if c[4] == s] for s in range(N)], params)
+    R = len(cohort)
     sc = api.Scanner(params, rgs, N, device=local_rank)
     anchor = (min(int(c[0][0]) for c in cohort) // 30) * 30
 
     def push_all():
         sc.begin_contig(anchor)
         with ThreadPoolExecutor(threads) as ex:
-            list(ex.map(lambda s: sc.push(s, cohort[s][0], cohort[s][2]), range(N)))
+            list(ex.map(lambda g: sc.push(g, cohort[g][0], cohort[g][2]), range(R)))
 
     # page-locked copies of the host arrays for the end-to-end path (pd_contig_push_pinned packs on the device)
     def pin(a):
@@ -153,8 +165,8 @@ def run_ours(args, rank, world, local_rank):
 
     def push_all_pinned():
         sc.begin_contig(anchor)
-        for s in range(N):
-            sc.push_pinned(s, pinned[s][0][1], pinned[s][1][1])
+        for g in range(R):
+            sc.push_pinned(g, pinned[g][0][1], pinned[g][1][1])
 
     def barrier():
         if dist is not None:
@@ -222,7 +234,7 @@ def run_ours(args, rank, world, local_rank):
         "dtype": "int32 (screen) / f64 (likelihoods)", "data": "synthetic",
         "config": {"workload": f"{N} synthetic profiles x chr21-sized window range ({L} bp, {res['n_windows']} windows of 30 bp) "
                                f"per GPU, single read group each, 30x, planted deletions {args.dels_per_mbp}/Mbp",
-                   "samples": N, "windows_per_gpu": int(res["n_windows"]), "read_pairs_per_gpu": int(res["n_reads"]),
+                   "samples": N, "read_groups": R, "windows_per_gpu": int(res["n_windows"]), "read_pairs_per_gpu": int(res["n_reads"]),
                    "parallelism": f"window-range x{world}", "l2": "inputs (%.2f GB packed words) larger than the 126 MB L2" % (res["algorithmic_bytes"] / 1e9),
                    "calls_per_step": int(len(res["calls"])), "flagged_windows": int(res["n_flagged_windows"]),
                    "candidates": int(res["n_candidates"])},
@@ -249,7 +261,7 @@ def cpu_baseline(args, cohort, params, rgs):
     if not os.path.exists(so):
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, stdout=subprocess.DEVNULL)
     orc = oracle_api.load(so)
-    N = len(cohort)
+    N = args.samples
     slice_bp = int(args.cpu_slice)
     pos, dev, off = [], [], [0]
     for c in cohort:
@@ -341,6 +353,7 @@ def main():
     ap.add_argument("--cpu-slice", type=int, default=1_500_000)
     ap.add_argument("--ref-slice-per-core", type=int, default=300_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mixed", action="store_true", help="1-3 read groups per sample with mixed insert-size histograms")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -510,10 +510,13 @@ __device__ __forceinline__ double group_sum(double v, uint32_t gmask)
 }
 
 // data likelihoods of every sample for (L, shifts) -> dlx; compute_data_likelihoods (EM overload) :179-253
+// Returns this thread's part of update_allele_frequency's sum (:467-485) under the genotype priors `gtf`.
 template <int LPS>
-__device__ void compute_dl(const PdDev & a, const EmArgs & e, EmShared & sh, const uint32_t * cnt, const uint32_t * off,
-                           double * dlx, const int32_t * shifts, bool zero_shifts, uint32_t L, double * cache, bool fill_cache)
+__device__ double compute_dl(const PdDev & a, const EmArgs & e, EmShared & sh, const uint32_t * cnt, const uint32_t * off,
+                             double * dlx, const int32_t * shifts, bool zero_shifts, uint32_t L, double * cache, bool fill_cache,
+                             const Gt gtf)
 {
+    double fs = 0;
     const int tid = threadIdx.x, sub = tid % LPS, grp = tid / LPS, ngrp = blockDim.x / LPS;
     const uint32_t gmask = (LPS == 32) ? FULL : (((1u << LPS) - 1u) << ((tid & 31) & ~(LPS - 1)));
     for (uint32_t s = grp; s < a.N; s += ngrp) {
@@ -554,9 +557,12 @@ __device__ void compute_dl(const PdDev & a, const EmArgs & e, EmShared & sh, con
             double x0, x1, x2;
             finish_triple(l0, l1, l2, (uint32_t)nd, x0, x1, x2);
             dlx[3 * s] = x0; dlx[3 * s + 1] = x1; dlx[3 * s + 2] = x2;
+            const double p0 = exp(x0) * gtf.a, p1 = exp(x1) * gtf.b, p2 = exp(x2) * gtf.c;
+            fs += (p1 + 2 * p2) / (p0 + p1 + p2);
         }
     }
     __syncthreads();
+    return fs;
 }
 
 // deletion_likelihood_ratio :490-508 (block-wide; result on all threads)
@@ -575,7 +581,7 @@ __device__ double block_lr(const PdDev & a, EmShared & sh, const double * dlx, c
 }
 
 template <int LPS>
-__global__ void __launch_bounds__(512, 2) k_em(PdDev a, EmArgs e, EmState * states)
+__global__ void __launch_bounds__(LPS >= 8 ? 1024 : 512, LPS >= 8 ? 1 : 2) k_em(PdDev a, EmArgs e, EmState * states)
 {
     __shared__ EmShared sh;
     extern __shared__ double cache[];                 // [2 * EM_CACHE_SLOTS][blockDim.x]
@@ -626,7 +632,7 @@ __global__ void __launch_bounds__(512, 2) k_em(PdDev a, EmArgs e, EmState * stat
         __syncthreads();
     }
     if (sh.freq == 0) { finish(0, 1); return; }
-    compute_dl<LPS>(a, e, sh, cnt, off, dlx, shifts, false, L0, cache, true);
+    compute_dl<LPS>(a, e, sh, cnt, off, dlx, shifts, false, L0, cache, true, sh.gt);
     if (tid == 0) { sh.prevFreq = sh.freq; sh.prevLen = sh.len; sh.prevGt = sh.gt; }
     __syncthreads();
 
@@ -699,13 +705,8 @@ __global__ void __launch_bounds__(512, 2) k_em(PdDev a, EmArgs e, EmState * stat
             sh.len = nl;
         }
         __syncthreads();
-        compute_dl<LPS>(a, e, sh, cnt, off, dlx, shifts, false, sh.len, cache, true);
-        // update_allele_frequency :467-485 (with the genotype priors of the previous iteration)
-        double fs = 0, dummy = 0;
-        for (uint32_t s = tid; s < a.N; s += blockDim.x) {
-            const double p0 = exp(dlx[3 * s]) * gt.a, p1 = exp(dlx[3 * s + 1]) * gt.b, p2 = exp(dlx[3 * s + 2]) * gt.c;
-            fs += (p1 + 2 * p2) / (p0 + p1 + p2);
-        }
+        // data likelihoods at the new length + update_allele_frequency :467-485 (priors of the previous iteration)
+        double fs = compute_dl<LPS>(a, e, sh, cnt, off, dlx, shifts, false, sh.len, cache, true, gt), dummy = 0;
         block_sum2(fs, dummy, sh.red);
         if (tid == 0) {
             sh.freq = fs / 2.0 / a.N;
@@ -723,7 +724,7 @@ __global__ void __launch_bounds__(512, 2) k_em(PdDev a, EmArgs e, EmState * stat
         if (sh.stop == 2) {
             // convergence :632-658: compare with the previous estimate evaluated with the initial (zero) shifts
             const double lr = block_lr(a, sh, dlx, sh.gt);
-            compute_dl<LPS>(a, e, sh, cnt, off, dlx, shifts, true, sh.prevLen, cache, false);
+            compute_dl<LPS>(a, e, sh, cnt, off, dlx, shifts, true, sh.prevLen, cache, false, sh.prevGt);
             const double plr = block_lr(a, sh, dlx, sh.prevGt);
             __syncthreads();
             if (plr > lr) {
@@ -744,9 +745,13 @@ __global__ void __launch_bounds__(512, 2) k_em(PdDev a, EmArgs e, EmState * stat
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_final(PdDev a, EmArgs e, const EmState * states)
 {
+    constexpr uint32_t SUPP_CAP = 1536;               // supporting read pairs kept in shared memory for the percentiles
     __shared__ EmShared sh;
+    __shared__ uint32_t s_first[SUPP_CAP], s_last[SUPP_CAP];
+    __shared__ uint32_t s_nsupp;
     const EmState stt = states[blockIdx.x];
     if (!stt.alive) return;
+    if (threadIdx.x == 0) s_nsupp = 0;
     const uint32_t pi = e.pair0 + blockIdx.x;
     const PdPair pr = e.pairs[pi];
     const uint32_t job = pr.job - e.job_base;
@@ -816,6 +821,8 @@ __global__ void __launch_bounds__(128) k_final(PdDev a, EmArgs e, const EmState 
                     const uint32_t first = p[i].pos_rel + e.anchor;
                     const uint32_t last = first + (uint32_t)max(0, d + k.inner_off);
                     ++supp; smin = min(smin, first); smax = max(smax, first); lmin = min(lmin, last); lmax = max(lmax, last);
+                    const uint32_t slot = atomicAdd(&s_nsupp, 1u);
+                    if (slot < SUPP_CAP) { s_first[slot] = first; s_last[slot] = last; }
                 }
             }
         }
@@ -868,6 +875,9 @@ __global__ void __launch_bounds__(128) k_final(PdDev a, EmArgs e, const EmState 
         while (loF < hiF || loL < hiL) {
             const uint32_t midF = loF + (hiF - loF) / 2, midL = loL + (hiL - loL) / 2;
             unsigned long long cF = 0, cL = 0;
+            if (supp <= SUPP_CAP) {
+                for (uint32_t i = tid; i < (uint32_t)supp; i += blockDim.x) { cF += s_first[i] <= midF; cL += s_last[i] <= midL; }
+            } else
             for (uint32_t s = tid; s < a.N; s += blockDim.x) {
                 int delLower = INT_MAX, delUpper = 0;
                 const uint32_t g0 = a.sample_rg[s], g1 = a.sample_rg[s + 1];
@@ -1077,8 +1087,9 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
                 PD_CUDA(c, cudaMemsetAsync(e.dbg, 0xFF, (size_t)np * 16, st));
             }
             {
-                const uint32_t lps = N * 8 <= 512 ? 8 : (N * 4 <= 512 ? 4 : (N * 2 <= 512 ? 2 : 1));
-                const uint32_t T = std::min<uint32_t>(512, ((N * lps + 31) / 32) * 32);
+                uint32_t lps = N * 8 <= 512 ? 8 : (N * 4 <= 512 ? 4 : (N * 2 <= 512 ? 2 : 1));
+                if (getenv("PD_EM_LPS")) lps = (uint32_t)atoi(getenv("PD_EM_LPS"));          // tuning knob
+                const uint32_t T = std::min<uint32_t>(lps >= 8 ? 1024 : 512, ((N * lps + 31) / 32) * 32);
                 const size_t smem = (size_t)2 * EM_CACHE_SLOTS * T * sizeof(double);
                 auto launch = [&](auto kern) -> cudaError_t {
                     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
