@@ -81,6 +81,7 @@ typedef struct {
     uint64_t h2d_bytes, d2h_bytes; /* bytes copied host->device for this contig / device->host for this scan */
     uint64_t n_kernel_launches;    /* kernels of this library launched by this scan */
     float    ms_h2d, ms_screen, ms_genotype, ms_d2h, ms_total;   /* CUDA-event times on the library's stream */
+    float    ms_stream;            /* the HBM-bound streaming kernel of the screen alone (k_stream) */
 } pd_result;
 
 /* Host: processHistogram(hist, 256, smoothing, pseudoCountFraction), insert_histogram_popdel.h:974-986, in place.

@@ -42,7 +42,7 @@ class PdResult(C.Structure):
                 ("n_reads", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_kernel_launches", C.c_uint64),
                 ("ms_h2d", C.c_float), ("ms_screen", C.c_float), ("ms_genotype", C.c_float), ("ms_d2h", C.c_float),
-                ("ms_total", C.c_float)]
+                ("ms_total", C.c_float), ("ms_stream", C.c_float)]
 
 
 CALL_DTYPE = np.dtype([("initial_length", "<u4"), ("iterations", "<u4"), ("deletion_length", "<u4"), ("filter", "<u4"),
@@ -250,7 +250,8 @@ class Scanner:
         return dict(calls=calls, per_sample=per, n_windows=res.n_windows, n_flagged_windows=res.n_flagged_windows,
                     n_candidates=res.n_candidates, n_reads=res.n_reads, algorithmic_bytes=res.algorithmic_bytes,
                     h2d_bytes=res.h2d_bytes, d2h_bytes=res.d2h_bytes, n_kernel_launches=res.n_kernel_launches,
-                    ms_h2d=res.ms_h2d, ms_screen=res.ms_screen, ms_genotype=res.ms_genotype, ms_total=res.ms_total)
+                    ms_h2d=res.ms_h2d, ms_screen=res.ms_screen, ms_genotype=res.ms_genotype, ms_total=res.ms_total,
+                    ms_stream=res.ms_stream)
 
     def debug_host_window_sums(self, rg: int, first_window: int, n_windows: int) -> np.ndarray:
         out = np.zeros((int(n_windows), 3), dtype=np.int64)

@@ -15,14 +15,15 @@ struct PdLong { uint32_t s, e, pos_rel; int32_t dev; };      // wide entry of a 
 struct PdTile { uint32_t off, long_lo, long_hi, pad; };
 // interleaved likelihood tables, one entry per histogram index (and one floor entry per read group)
 struct PdTab {
+    // first 32 bytes = everything the EM loop touches (one sector, two 128-bit loads)
     double val;     // processed histogram value I()
     double ln;      // ln(val)
-    double l10;     // log10(val)
     double lnp;     // ln(val + min_prob) - ln2_d          (g1 when the other hypothesis sits on the floor)
+    double fr;      // min_prob / (min_prob + val)         (weight of the floor hypothesis)
+    // final pass only
+    double l10;     // log10(val)
     double l10p;    // log10(val + min_prob) - log10(2)_d
-    double fr;      // min_prob / (min_prob + val)
-    double fd;      // val / (min_prob + val)
-    double pad;
+    double pad[2];
 };
 
 // Device view handed to the kernels by value.
@@ -92,8 +93,7 @@ struct pd_ctx {
 
     // device
     cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: result compaction + D2H, overlapped with the EM
-    std::vector<uint32_t> idx_stage[2];
-    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev[12] = {};
     uint32_t * d_words = nullptr; size_t cap_words = 0;
     PdTile * d_tiles = nullptr; size_t cap_tiles = 0;
     PdLong * d_longs = nullptr; size_t cap_longs = 0;
@@ -101,11 +101,17 @@ struct pd_ctx {
     uint32_t * d_sample_rg = nullptr;
     PdTab * d_tab = nullptr;
     // scan scratch (grown on demand)
-    void * d_scratch[24] = {}; size_t cap_scratch[24] = {};
+    void * d_scratch[40] = {}; size_t cap_scratch[40] = {};
     void * d_pack[8] = {}; size_t cap_pack[8] = {};          // device packer scratch (raw arrays, tile firsts, ...)
     // results
-    std::vector<pd_call> res_calls;
-    uint32_t * res_ps = nullptr; size_t cap_res_ps = 0;    // pinned
+    pd_call * res_calls = nullptr; size_t cap_res_calls = 0;   // page-locked, mapped: written by the device (k_emit_rows)
+    uint32_t * res_ps = nullptr; size_t cap_res_ps = 0;        // page-locked, mapped
+    uint32_t * res_count = nullptr;                            // page-locked, mapped: [0] = number of calls
+    // word -> tile index of the current upload (k_stream's slow path) and wide-list ranges per read group
+    bool index_built = false;
+    uint32_t * d_gran_off = nullptr, * d_gran_tile = nullptr, * d_long_off = nullptr; size_t cap_gran = 0;
+    uint32_t max_rg_words = 0;
+    size_t pool_cap = 0;                                       // active read-pair pool capacity (persists across scans)
     float ms_h2d = 0;
     uint64_t h2d_bytes = 0;
 };

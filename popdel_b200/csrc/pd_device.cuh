@@ -1,0 +1,162 @@
+// pd_device.cuh -- device-side helpers and the kernel-launch interface shared by the scan's translation units
+// (pd_screen.cu, pd_gather.cu, pd_em.cu, pd_scan.cu). Internal.
+#ifndef PD_DEVICE_CUH_
+#define PD_DEVICE_CUH_
+
+#include <climits>
+#include <string>
+
+#include "pd_context.h"
+
+#define PD_CUDA(c, call)                                                                          \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return pd_fail((c), PD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+constexpr uint32_t PD_FULL = 0xFFFFFFFFu;
+constexpr uint32_t PD_GRAN = 1024;                  // words per warp in k_stream; granule of the word -> tile index
+constexpr int PD_CAND_INLINE = 6;                   // candidate lengths kept inline per window job
+
+// device counters of one scan (uint32 each)
+enum { CNT_TJOBS = 0, CNT_JOBS = 1, CNT_PAIRS = 2, CNT_POOL = 3, CNT_CALLS = 4, CNT_N = 16 };
+
+struct PdPair { uint32_t job; int32_t L0; };                         // (window job, initial deletion length)
+struct EmState { uint32_t len, it, alive, pad; double freq; double gt[3]; };   // handed from k_em to k_final
+
+// ---- screen (pd_screen.cu) ------------------------------------------------------------------------------------
+struct ScreenArgs {
+    uint32_t tile_begin, tile_end;      // tiles intersecting the window range
+    uint32_t tb_al;                     // tile_begin rounded down to a multiple of 32
+    uint32_t need_stride;               // words of the need bitmap per sample
+    uint32_t * need;                    // [N][need_stride] bit = (sample, tile) can see a read pair above the threshold
+    uint32_t * tile_flags;              // [tile_end - tile_begin] bit = window of the tile passed the exact screen
+    const uint32_t * gran_off;          // [R+1] first entry of read group g in gran_tile
+    const uint32_t * gran_tile;         // tile that contains word (first word of g) + j * PD_GRAN
+    const uint32_t * long_off;          // [R+1] wide-list ranges per read group
+    uint32_t total_longs;
+};
+struct JobArgs {
+    const uint32_t * tile_flags; uint32_t n_tiles, tile_begin;
+    uint32_t * tj_tile, * tj_mask, * tj_wbase;      // flagged tiles in ascending order, window mask, first window job
+    uint32_t * job_window;                           // window of every window job (ascending)
+    uint32_t * counters;
+    unsigned long long * block_sums;                // scratch of the two-level scan
+};
+void pd_launch_gran_index(const PdDev & a, uint32_t * gran_tile, const uint32_t * gran_off, cudaStream_t st);
+void pd_launch_screen(const PdDev & a, const ScreenArgs & s, uint32_t max_rg_words, cudaStream_t st, cudaEvent_t after_stream, uint64_t * launches);
+void pd_launch_tile_jobs(const JobArgs & j, cudaStream_t st, uint64_t * launches);
+
+// ---- gather + candidates (pd_gather.cu) -----------------------------------------------------------------------
+struct GatherArgs {
+    const uint32_t * tj_tile, * tj_mask, * tj_wbase; uint32_t tj0, ntj;      // tile jobs [tj0, tj0 + ntj)
+    uint32_t job_base;                  // first window job of this batch (scratch rows are relative to it)
+    uint32_t * pool_pos; int32_t * pool_dev; uint32_t pool_cap;              // active read pairs, SoA
+    uint32_t * counters;
+    uint32_t * act_off, * act_cnt;      // [jobs][R]
+    int32_t * q3; uint8_t * sstat;      // [jobs][N]   sstat: 0 = low coverage, 1 = no usable values, 2 = Q3 valid
+    int32_t * dmax;                     // [jobs][N]   largest deviation among the sample's usable active read pairs (INT_MIN: none)
+};
+struct CandArgs {
+    const int32_t * q3; const uint8_t * sstat; uint32_t njobs, job_base;
+    uint32_t * cand_cnt;                // [njobs]
+    int32_t * cand_inline;              // [njobs][PD_CAND_INLINE]
+    uint32_t * cand_off;                // [njobs] exclusive scan of cand_cnt
+    PdPair * pairs; uint32_t pair_cap;
+    uint32_t * counters; unsigned long long * block_sums;
+    uint32_t npad;
+};
+void pd_launch_gather(const PdDev & a, const GatherArgs & g, cudaStream_t st, uint64_t * launches);
+int  pd_launch_candidates(pd_ctx * c, const PdDev & a, const CandArgs & ca, cudaStream_t st, uint64_t * launches);
+
+// ---- EM + final pass (pd_em.cu) -------------------------------------------------------------------------------
+struct EmArgs {
+    const uint32_t * job_window; const PdPair * pairs; uint32_t pair0, npairs, job_base;   // pairs[].job is absolute
+    const uint32_t * pool_pos; const int32_t * pool_dev; const uint32_t * act_off, * act_cnt; const uint8_t * sstat;
+    const int32_t * dmax;    // [job][N]
+    double * dlx;            // [pair][N][3]   data likelihoods, log domain, max = 0
+    double * dle;            // [pair][N][3]   exp(dlx)
+    int32_t * shifts;        // [pair][R]
+    uint32_t * ps;           // [pair][N][13]  per-sample output rows
+    pd_call * calls;         // [pair]
+    uint8_t * valid;         // [pair]
+    EmState * states;        // [pair]
+    uint32_t iterations, min_len; double min_lr, min_sample_fraction; int somatic, window_wise; uint32_t anchor;
+    uint32_t * dbg;          // optional [npairs][4]: reason, len, iterations, supp (PD_DEBUG)
+    int dbg_window;          // device printf of the EM trajectory of this window (PD_DEBUG_WINDOW), -1 = off
+    int sort_samples;        // fused kernel: order the samples by largest deviation and skip unchanged likelihood passes
+};
+struct EmitArgs {
+    const uint8_t * valid; const pd_call * calls; const uint32_t * ps; uint32_t npairs, row_words;
+    uint32_t * counters;                // CNT_CALLS = calls emitted so far
+    uint32_t * chunk_base;              // device scalar: first output slot of this chunk
+    pd_call * out_calls; uint32_t * out_ps; uint32_t * out_count;   // mapped page-locked host memory
+};
+int  pd_launch_em(pd_ctx * c, const PdDev & a, const EmArgs & e, cudaStream_t st, uint64_t * launches);
+void pd_launch_emit_count(const EmitArgs & m, cudaStream_t st, uint64_t * launches);
+void pd_launch_emit_rows(const EmitArgs & m, cudaStream_t st, uint64_t * launches);
+
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ PdTile load_tile(const PdTile * p)
+{
+    const uint4 q = __ldg(reinterpret_cast<const uint4 *>(p));
+    return PdTile{q.x, q.y, q.z, q.w};
+}
+
+// block-wide exclusive scan of one 64-bit value per thread (blockDim.x multiple of 32, <= 1024); returns the
+// exclusive prefix, `total` = sum over the block. `ws` = 33 values of shared memory.
+__device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long v, unsigned long long * ws, unsigned long long & total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long n = __shfl_up_sync(PD_FULL, inc, o); if (lane >= o) inc += n; }
+    __syncthreads();                                    // ws may still be read from a previous call
+    if (lane == 31) ws[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned long long s = lane < nw ? ws[lane] : 0ull, si = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long n = __shfl_up_sync(PD_FULL, si, o); if (lane >= o) si += n; }
+        if (lane < nw) ws[lane] = si - s;
+        if (lane == 31) ws[32] = si;
+    }
+    __syncthreads();
+    total = ws[32];
+    return ws[wid] + inc - v;
+}
+
+// calls f(valid, s, e, pos_rel, dev) for every 32-wide batch of read pairs of read group g whose active interval can
+// intersect the windows of `tile` (stream words of the look-back tiles in stream order, then the wide list).
+// `valid` marks lanes holding a real, ever-active read pair; the caller tests the interval.
+template <typename F>
+__device__ __forceinline__ void for_tile_batches(const PdDev & a, uint32_t g, const PdRgConst & k, uint32_t tile, int lane, F f)
+{
+    const PdTile * tl = a.tiles + (size_t)g * (a.NT + 1);
+    const uint32_t t_lo = tile > k.lookback_tiles ? tile - k.lookback_tiles : 0;
+    for (uint32_t tt = t_lo; tt <= tile; ++tt) {
+        const TileSeg ts = tile_seg(tt, a.window_buffer);
+        const uint32_t r_lo = __ldg(&tl[tt].off), r_hi = __ldg(&tl[tt + 1].off);
+        for (uint32_t base = r_lo; base < r_hi; base += 32) {
+            const uint32_t i = base + lane;
+            const uint32_t word = i < r_hi ? __ldg(a.words + i) : PD_PAD_WORD;
+            int32_t s = 0, e = 0, dev = 0; uint32_t pr = 0;
+            const bool valid = word_interval(word, ts, k.inner_off, s, e, dev, pr);
+            f(valid, s, e, pr, dev);
+        }
+    }
+    const uint32_t l_lo = __ldg(&tl[tile].long_lo), l_hi = __ldg(&tl[tile].long_hi);
+    for (uint32_t base = l_lo; base < l_hi; base += 32) {
+        const uint32_t i = base + lane;
+        PdLong L = PdLong{0xFFFFFFFFu, 0, 0, 0};
+        if (i < l_hi) L = a.longs[i];
+        f(i < l_hi, (int32_t)L.s, (int32_t)L.e, L.pos_rel, L.dev);
+    }
+}
+#endif  // __CUDACC__
+
+#endif

@@ -107,7 +107,7 @@ static int upload_static(pd_ctx * c)
         auto fill = [&](PdTab & e, double v) {
             e.val = v; e.ln = std::log(v); e.l10 = std::log10(v);
             e.lnp = std::log(v + mp) - LN2_D; e.l10p = std::log10(v + mp) - L10_2_D;
-            e.fr = mp / (mp + v); e.fd = v / (mp + v); e.pad = 0;
+            e.fr = mp / (mp + v); e.pad[0] = e.pad[1] = 0;
         };
         size_t o = c->rgc[g].hist_off;
         fill(tab[o], mp);                                           // floor entry
@@ -194,6 +194,9 @@ extern "C" void pd_destroy(pd_ctx * c)
         cudaFree(c->d_words); cudaFree(c->d_tiles); cudaFree(c->d_longs);
         cudaFree(c->d_rgc); cudaFree(c->d_sample_rg); cudaFree(c->d_tab);
         if (c->res_ps) cudaFreeHost(c->res_ps);
+        if (c->res_calls) cudaFreeHost(c->res_calls);
+        if (c->res_count) cudaFreeHost(c->res_count);
+        cudaFree(c->d_gran_off); cudaFree(c->d_gran_tile); cudaFree(c->d_long_off);
         for (auto & p : c->d_scratch) cudaFree(p);
         for (auto & p : c->d_pack) cudaFree(p);
         for (auto & ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -241,7 +244,7 @@ extern "C" int pd_contig_begin(pd_ctx * c, uint32_t anchor)
     }
     for (auto & r : c->raw) r = PdRawRg();
     c->dev_mode = c->host_mode = false;
-    c->contig_open = true; c->packed = false; c->uploaded = false;
+    c->contig_open = true; c->packed = false; c->uploaded = false; c->index_built = false;
     c->n_windows_total = 0; c->n_reads = 0;
     return 0;
 }
@@ -461,7 +464,7 @@ extern "C" int pd_contig_upload(pd_ctx * c)
     if (c->dev_mode) {
         int prc = pd_pack_on_device(c);
         if (prc < 0) return prc;
-        if (prc == 0) { c->packed = true; c->uploaded = true; return 0; }
+        if (prc == 0) { c->packed = true; c->uploaded = true; c->index_built = false; return 0; }
         // the active-coverage cap would drop read pairs (or a span exceeds the device look-back): sequential host path
         c->dev_mode = false;
         for (uint32_t g = 0; g < c->R; ++g) {
@@ -490,7 +493,7 @@ extern "C" int pd_contig_upload(pd_ctx * c)
     PD_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     PD_CUDA(c, cudaStreamSynchronize(c->stream));
     PD_CUDA(c, cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]));
-    c->uploaded = true;
+    c->uploaded = true; c->index_built = false;
     return 0;
 }
 

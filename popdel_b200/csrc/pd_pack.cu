@@ -395,6 +395,7 @@ int pd_pack_on_device(pd_ctx * c)
     for (uint32_t g = 0; g < R; ++g) base[g + 1] = base[g] + h_words[g];
     if (base[R] > 0xFFFFFFF0ull) return pd_fail(c, PD_ERR_CAPACITY, "more than 2^32 packed words in one contig batch; split the cohort or the contig");
     c->total_words = base[R];
+    c->h_word_base = base;
     c->n_reads = total;
     PD_CUDA(c, cudaMemcpyAsync(d_word_base, base.data(), (R + 1) * 8, cudaMemcpyHostToDevice, st));
     if (c->total_words + 4 > c->cap_words || !c->d_words) {
@@ -423,6 +424,9 @@ int pd_pack_on_device(pd_ctx * c)
     std::vector<uint64_t> lbase(R + 1, 0);
     for (uint32_t g = 0; g < R; ++g) lbase[g + 1] = lbase[g] + h_longs[g];
     c->total_longs = lbase[R];
+    if (c->total_longs > 0xFFFFFFF0ull) return pd_fail(c, PD_ERR_CAPACITY, "more than 2^32 long read pairs in one contig batch");
+    c->h_long_off.assign(R + 1, 0);
+    for (uint32_t g = 0; g <= R; ++g) c->h_long_off[g] = (uint32_t)lbase[g];
     PD_CUDA(c, cudaMemcpyAsync(d_long_base, lbase.data(), (R + 1) * 8, cudaMemcpyHostToDevice, st));
     if (c->total_longs + 1 > c->cap_longs || !c->d_longs) {
         if (c->d_longs) cudaFree(c->d_longs);

@@ -1,0 +1,319 @@
+// pd_scan.cu -- orchestration of one window-range scan (pd_contig_scan): screen -> tile jobs -> gather ->
+// candidates -> EM / final pass in chunks -> ordered emission into mapped host memory.
+//
+// Host synchronisations per scan: one after the screen (number of flagged tiles / windows, to size the scratch), one
+// per job batch after the candidates (number of (window, length) pairs), one at the end. Everything else is
+// stream-ordered: the EM chunks run on `stream`, the emission of chunk k (k_emit_*, writing call headers and per-sample
+// rows over PCIe) runs on `stream2` and overlaps the EM of chunk k+1.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "pd_device.cuh"
+
+namespace {
+
+enum Slot {                                     // d_scratch slots
+    S_NEED = 0, S_TFLAGS, S_COUNTERS, S_TJ_TILE, S_TJ_MASK, S_TJ_WBASE, S_JOBWIN, S_BSUMS,
+    S_ACT_OFF, S_ACT_CNT, S_Q3, S_SSTAT, S_CAND_CNT, S_CAND_INL, S_CAND_OFF, S_PAIRS, S_POOL_POS, S_POOL_DEV,
+    S_DLX, S_DLE, S_SHIFTS, S_STATES, S_PS0, S_PS1, S_CALLS0, S_CALLS1, S_VALID0, S_VALID1, S_CHUNK_BASE, S_DBG, S_DMAX
+};
+
+template <typename T>
+int grow_scratch(pd_ctx * c, int slot, T *& p, size_t need)
+{
+    const size_t bytes = std::max<size_t>(need, 1) * sizeof(T);
+    if (bytes > c->cap_scratch[slot] || !c->d_scratch[slot]) {
+        if (c->d_scratch[slot]) cudaFree(c->d_scratch[slot]);
+        c->d_scratch[slot] = nullptr; c->cap_scratch[slot] = 0;
+        const size_t want = std::max<size_t>(bytes + bytes / 4, 4096);
+        PD_CUDA(c, cudaMalloc(&c->d_scratch[slot], want));
+        c->cap_scratch[slot] = want;
+    }
+    p = reinterpret_cast<T *>(c->d_scratch[slot]);
+    return 0;
+}
+
+// word -> tile index and wide-list ranges of the current upload (built once per upload)
+int build_index(pd_ctx * c, const PdDev & a)
+{
+    const uint32_t R = c->R;
+    std::vector<uint32_t> goff(R + 1, 0);
+    uint32_t max_words = 0;
+    for (uint32_t g = 0; g < R; ++g) {
+        const uint64_t nw = c->h_word_base[g + 1] - c->h_word_base[g];
+        goff[g + 1] = goff[g] + (uint32_t)((nw + PD_GRAN - 1) / PD_GRAN) + 1;
+        max_words = (uint32_t)std::max<uint64_t>(max_words, nw);
+    }
+    c->max_rg_words = max_words;
+    const size_t need = (size_t)goff[R] + 1;
+    if (need > c->cap_gran || !c->d_gran_tile) {
+        cudaFree(c->d_gran_tile); cudaFree(c->d_gran_off); cudaFree(c->d_long_off);
+        c->d_gran_tile = c->d_gran_off = c->d_long_off = nullptr; c->cap_gran = 0;
+        PD_CUDA(c, cudaMalloc(&c->d_gran_tile, (need + need / 8) * 4));
+        PD_CUDA(c, cudaMalloc(&c->d_gran_off, ((size_t)R + 1) * 4));
+        PD_CUDA(c, cudaMalloc(&c->d_long_off, ((size_t)R + 1) * 4));
+        c->cap_gran = need + need / 8;
+    }
+    PD_CUDA(c, cudaMemcpyAsync(c->d_gran_off, goff.data(), ((size_t)R + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    PD_CUDA(c, cudaMemcpyAsync(c->d_long_off, c->h_long_off.data(), ((size_t)R + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    PD_CUDA(c, cudaMemsetAsync(c->d_gran_tile, 0, need * 4, c->stream));
+    pd_launch_gran_index(a, c->d_gran_tile, c->d_gran_off, c->stream);
+    PD_CUDA(c, cudaGetLastError());
+    PD_CUDA(c, cudaStreamSynchronize(c->stream));                    // goff (host vector) is read by the async copy
+    c->index_built = true;
+    return 0;
+}
+
+// mapped, page-locked result buffers: grown so that `need_calls` calls fit; existing contents are preserved
+int ensure_results(pd_ctx * c, size_t need_calls, size_t row, size_t keep_calls)
+{
+    if (!c->res_count) {
+        PD_CUDA(c, cudaHostAlloc(&c->res_count, 256, cudaHostAllocMapped));      // [0] calls emitted; [16..31] counter read-back
+        c->res_count[0] = 0;
+    }
+    if (need_calls > c->cap_res_calls || !c->res_calls) {
+        const size_t want = std::max<size_t>(need_calls + need_calls / 2, 1024);
+        pd_call * p = nullptr;
+        PD_CUDA(c, cudaHostAlloc(&p, want * sizeof(pd_call), cudaHostAllocMapped));
+        if (keep_calls) memcpy(p, c->res_calls, keep_calls * sizeof(pd_call));
+        if (c->res_calls) cudaFreeHost(c->res_calls);
+        c->res_calls = p; c->cap_res_calls = want;
+    }
+    if (need_calls * row > c->cap_res_ps || !c->res_ps) {
+        const size_t want = std::max<size_t>((need_calls + need_calls / 2) * row, 1u << 18);
+        uint32_t * p = nullptr;
+        if (cudaHostAlloc(&p, want * 4, cudaHostAllocMapped) != cudaSuccess) {
+            cudaGetLastError();
+            return pd_fail(c, PD_ERR_CAPACITY, "cannot page-lock the result buffer for this many calls x samples; scan a smaller window range");
+        }
+        if (keep_calls) memcpy(p, c->res_ps, keep_calls * row * 4);
+        if (c->res_ps) cudaFreeHost(c->res_ps);
+        c->res_ps = p; c->cap_res_ps = want;
+    }
+    return 0;
+}
+
+}  // namespace
+
+int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result * out)
+{
+    PD_CUDA(c, cudaSetDevice(c->device));
+    memset(out, 0, sizeof(*out));
+    const uint64_t total = c->n_windows_total;
+    const uint64_t w_begin = std::min<uint64_t>(first_window, total);
+    const uint64_t w_end = n_windows ? std::min<uint64_t>(first_window + n_windows, total) : total;
+    const uint32_t N = c->N, R = c->R;
+    const size_t row = 13ull * N;
+    if (ensure_results(c, 1, row, 0)) return c->status;
+    c->res_count[0] = 0;
+    out->n_reads = c->n_reads;
+    out->algorithmic_bytes = 4ull * c->n_reads;
+    out->h2d_bytes = c->h2d_bytes;
+    out->calls = c->res_calls; out->per_sample = c->res_ps;
+    if (w_end <= w_begin) return 0;
+    const uint32_t W = (uint32_t)(w_end - w_begin);
+    out->n_windows = W;
+
+    PdDev a;
+    a.words = c->d_words; a.tiles = c->d_tiles; a.longs = c->d_longs;
+    a.rgc = c->d_rgc; a.sample_rg = c->d_sample_rg; a.tab = c->d_tab;
+    a.NT = c->NT; a.N = N; a.R = R; a.window_buffer = c->grid.window_buffer; a.t_min = c->t_min;
+    a.w_begin = (uint32_t)w_begin; a.w_end = (uint32_t)w_end;
+    if (!c->index_built && build_index(c, a)) return c->status;
+
+    cudaStream_t st = c->stream, st2 = c->stream2;
+    uint64_t * nl = &out->n_kernel_launches;
+    const bool dbg = getenv("PD_DEBUG") != nullptr;
+    const int dbg_window = getenv("PD_DEBUG_WINDOW") ? atoi(getenv("PD_DEBUG_WINDOW")) : -1;
+
+    // ---- screen
+    ScreenArgs s;
+    s.tile_begin = (uint32_t)(w_begin / PD_TILE_WINDOWS);
+    s.tile_end = (uint32_t)std::min<uint64_t>((w_end + PD_TILE_WINDOWS - 1) / PD_TILE_WINDOWS, c->NT);
+    s.tb_al = s.tile_begin & ~31u;
+    s.need_stride = (s.tile_end - s.tb_al + 31) / 32;
+    s.gran_off = c->d_gran_off; s.gran_tile = c->d_gran_tile; s.long_off = c->d_long_off;
+    s.total_longs = (uint32_t)c->total_longs;
+    const uint32_t n_tiles = s.tile_end - s.tile_begin;
+    uint32_t * d_counters; unsigned long long * d_bsums;
+    if (grow_scratch(c, S_NEED, s.need, (size_t)N * s.need_stride)) return c->status;
+    if (grow_scratch(c, S_TFLAGS, s.tile_flags, (size_t)n_tiles)) return c->status;
+    if (grow_scratch(c, S_COUNTERS, d_counters, (size_t)CNT_N)) return c->status;
+    JobArgs j;
+    j.tile_flags = s.tile_flags; j.n_tiles = n_tiles; j.tile_begin = s.tile_begin; j.counters = d_counters;
+    if (grow_scratch(c, S_TJ_TILE, j.tj_tile, (size_t)n_tiles)) return c->status;
+    if (grow_scratch(c, S_TJ_MASK, j.tj_mask, (size_t)n_tiles)) return c->status;
+    if (grow_scratch(c, S_TJ_WBASE, j.tj_wbase, (size_t)n_tiles)) return c->status;
+    if (grow_scratch(c, S_JOBWIN, j.job_window, (size_t)n_tiles * PD_TILE_WINDOWS)) return c->status;
+    if (grow_scratch(c, S_BSUMS, d_bsums, (size_t)std::max<uint64_t>((n_tiles * (uint64_t)PD_TILE_WINDOWS + 1023) / 1024, 1) + 1)) return c->status;
+    j.block_sums = d_bsums;
+    PD_CUDA(c, cudaEventRecord(c->ev[2], st));
+    PD_CUDA(c, cudaMemsetAsync(s.need, 0, (size_t)N * s.need_stride * 4, st));
+    PD_CUDA(c, cudaMemsetAsync(s.tile_flags, 0, (size_t)n_tiles * 4, st));
+    PD_CUDA(c, cudaMemsetAsync(d_counters, 0, CNT_N * 4, st));
+    PD_CUDA(c, cudaEventRecord(c->ev[3], st));
+    if (n_tiles) {
+        pd_launch_screen(a, s, c->max_rg_words, st, c->ev[10], nl);
+        PD_CUDA(c, cudaGetLastError());
+    }
+    PD_CUDA(c, cudaEventRecord(c->ev[4], st));
+    if (n_tiles) pd_launch_tile_jobs(j, st, nl);
+    PD_CUDA(c, cudaGetLastError());
+    uint32_t * h_cnt = c->res_count + 16;                            // page-locked: the read-back is a plain DMA
+    PD_CUDA(c, cudaMemcpyAsync(h_cnt, d_counters, CNT_N * 4, cudaMemcpyDeviceToHost, st));
+    PD_CUDA(c, cudaStreamSynchronize(st));
+    const uint32_t n_tj = h_cnt[CNT_TJOBS], n_jobs = h_cnt[CNT_JOBS];
+    out->n_flagged_windows = n_jobs;
+
+    // ---- genotyping stage, in batches of tile jobs
+    const size_t job_bytes = 8ull * R + 5ull * N + 8ull * (PD_CAND_INLINE + 2) + 400ull * N;
+    const uint32_t JB = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(4000000000ull / job_bytes, 64), 1u << 20);
+    std::vector<uint32_t> h_wbase;
+    if (n_jobs > JB) {
+        h_wbase.resize(n_tj);
+        PD_CUDA(c, cudaMemcpyAsync(h_wbase.data(), j.tj_wbase, (size_t)n_tj * 4, cudaMemcpyDeviceToHost, st));
+        PD_CUDA(c, cudaStreamSynchronize(st));
+    }
+    uint32_t npad = 1; while (npad < N) npad <<= 1;
+    if ((size_t)npad * 4 > 200 * 1024) return pd_fail(c, PD_ERR_CAPACITY, "more than 51200 samples per context: candidate sort does not fit shared memory (shard by sample)");
+    const size_t pair_bytes = 48ull * N + 4ull * R + 2 * 52ull * N + 128;
+    const uint32_t CH = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(2000000000ull / pair_bytes, 64), getenv("PD_EM_CHUNK") ? atoi(getenv("PD_EM_CHUNK")) : 8192);
+    uint64_t n_pairs_total = 0;
+    uint32_t chunk_no = 0;
+    std::vector<uint32_t> h_jobwin; std::vector<PdPair> h_pairs;
+    if (dbg && n_jobs) {
+        h_jobwin.resize(n_jobs);
+        PD_CUDA(c, cudaMemcpy(h_jobwin.data(), j.job_window, (size_t)n_jobs * 4, cudaMemcpyDeviceToHost));
+    }
+    uint32_t * d_chunk_base;
+    if (grow_scratch(c, S_CHUNK_BASE, d_chunk_base, (size_t)4)) return c->status;
+
+    for (uint32_t tj0 = 0; tj0 < n_tj;) {
+        // batch = tile jobs [tj0, tj1) with at most JB window jobs
+        uint32_t tj1 = n_tj, job_base = 0, nj = n_jobs;
+        if (!h_wbase.empty()) {
+            job_base = h_wbase[tj0];
+            tj1 = tj0 + 1;
+            while (tj1 < n_tj && h_wbase[tj1] - job_base <= JB - PD_TILE_WINDOWS) ++tj1;
+            nj = (tj1 < n_tj ? h_wbase[tj1] : n_jobs) - job_base;
+        }
+        GatherArgs ga;
+        ga.tj_tile = j.tj_tile; ga.tj_mask = j.tj_mask; ga.tj_wbase = j.tj_wbase; ga.tj0 = tj0; ga.ntj = tj1 - tj0;
+        ga.job_base = job_base; ga.counters = d_counters;
+        if (grow_scratch(c, S_ACT_OFF, ga.act_off, (size_t)nj * R)) return c->status;
+        if (grow_scratch(c, S_ACT_CNT, ga.act_cnt, (size_t)nj * R)) return c->status;
+        if (grow_scratch(c, S_Q3, ga.q3, (size_t)nj * N)) return c->status;
+        if (grow_scratch(c, S_SSTAT, ga.sstat, (size_t)nj * N)) return c->status;
+        if (grow_scratch(c, S_DMAX, ga.dmax, (size_t)nj * N)) return c->status;
+        CandArgs ca;
+        ca.q3 = ga.q3; ca.sstat = ga.sstat; ca.njobs = nj; ca.job_base = job_base; ca.counters = d_counters; ca.block_sums = d_bsums; ca.npad = npad;
+        if (grow_scratch(c, S_CAND_CNT, ca.cand_cnt, (size_t)nj)) return c->status;
+        if (grow_scratch(c, S_CAND_INL, ca.cand_inline, (size_t)nj * PD_CAND_INLINE)) return c->status;
+        if (grow_scratch(c, S_CAND_OFF, ca.cand_off, (size_t)nj)) return c->status;
+        size_t pair_cap = std::max<size_t>(c->cap_scratch[S_PAIRS] / sizeof(PdPair), (size_t)nj * 2 + 1024);
+        uint32_t n_pairs = 0;
+        if (c->pool_cap == 0) c->pool_cap = std::max<size_t>((size_t)std::min<uint32_t>(nj, 16384) * R * 40, 1u << 20);
+        bool gathered = false;
+        for (int attempt = 0; ; ++attempt) {
+            if (c->pool_cap > 0xFFFFFFF0ull) c->pool_cap = 0xFFFFFFF0ull;
+            if (grow_scratch(c, S_POOL_POS, ga.pool_pos, c->pool_cap)) return c->status;
+            if (grow_scratch(c, S_POOL_DEV, ga.pool_dev, c->pool_cap)) return c->status;
+            if (grow_scratch(c, S_PAIRS, ca.pairs, pair_cap)) return c->status;
+            ga.pool_cap = (uint32_t)c->pool_cap; ca.pair_cap = (uint32_t)std::min<size_t>(pair_cap, 0xFFFFFFF0ull);
+            if (!gathered) {
+                PD_CUDA(c, cudaMemsetAsync(d_counters + CNT_POOL, 0, 4, st));
+                pd_launch_gather(a, ga, st, nl);
+                PD_CUDA(c, cudaGetLastError());
+            }
+            if (pd_launch_candidates(c, a, ca, st, nl)) return c->status;
+            PD_CUDA(c, cudaMemcpyAsync(h_cnt, d_counters, CNT_N * 4, cudaMemcpyDeviceToHost, st));
+            PD_CUDA(c, cudaStreamSynchronize(st));
+            const bool pool_ok = h_cnt[CNT_POOL] <= c->pool_cap, pairs_ok = h_cnt[CNT_PAIRS] <= pair_cap;
+            if (pool_ok && pairs_ok) { n_pairs = h_cnt[CNT_PAIRS]; break; }
+            if (attempt == 2) return pd_fail(c, PD_ERR_CAPACITY, "active read-pair pool / candidate list overflow");
+            if (!pool_ok) c->pool_cap = (size_t)h_cnt[CNT_POOL] + (size_t)h_cnt[CNT_POOL] / 8 + 1024;      // exact size known now: run again
+            else gathered = true;
+            if (!pairs_ok) pair_cap = (size_t)h_cnt[CNT_PAIRS] + 1024;
+        }
+        n_pairs_total += n_pairs;
+        if (dbg && n_pairs) {
+            h_pairs.resize(n_pairs);
+            PD_CUDA(c, cudaMemcpy(h_pairs.data(), ca.pairs, (size_t)n_pairs * sizeof(PdPair), cudaMemcpyDeviceToHost));
+        }
+
+        // ---- pairs in chunks: the emission of chunk k (stream2) overlaps the EM of chunk k+1 (stream)
+        for (uint32_t p0 = 0; p0 < n_pairs; p0 += CH, ++chunk_no) {
+            const uint32_t np = std::min(CH, n_pairs - p0);
+            const int par = (int)(chunk_no & 1);
+            EmArgs e;
+            if (grow_scratch(c, S_DLX, e.dlx, (size_t)CH * 3 * N)) return c->status;
+            if (grow_scratch(c, S_DLE, e.dle, (size_t)CH * 3 * N)) return c->status;
+            if (grow_scratch(c, S_SHIFTS, e.shifts, (size_t)CH * R)) return c->status;
+            if (grow_scratch(c, S_STATES, e.states, (size_t)CH)) return c->status;
+            // double-buffered: read by stream2 while the next chunk is computed
+            if (chunk_no >= 2) PD_CUDA(c, cudaStreamWaitEvent(st, c->ev[8 + par], 0));          // chunk k-2 has been emitted
+            const size_t had = c->cap_scratch[S_PS0 + par];
+            if (grow_scratch(c, S_PS0 + par, e.ps, (size_t)CH * row)) return c->status;
+            if (grow_scratch(c, S_CALLS0 + par, e.calls, (size_t)CH)) return c->status;
+            if (grow_scratch(c, S_VALID0 + par, e.valid, (size_t)CH + 16)) return c->status;
+            (void)had;
+            e.job_window = j.job_window; e.pairs = ca.pairs; e.pair0 = p0; e.npairs = np; e.job_base = job_base;
+            e.pool_pos = ga.pool_pos; e.pool_dev = ga.pool_dev; e.act_off = ga.act_off; e.act_cnt = ga.act_cnt; e.sstat = ga.sstat; e.dmax = ga.dmax;
+            e.iterations = c->params.iterations; e.min_len = c->params.min_len; e.min_lr = c->params.min_lr;
+            e.min_sample_fraction = c->params.min_sample_fraction; e.somatic = c->params.somatic; e.window_wise = c->params.window_wise;
+            e.anchor = c->grid.anchor;
+            e.dbg = nullptr; e.dbg_window = dbg_window;
+            e.sort_samples = getenv("PD_EM_SORT") ? atoi(getenv("PD_EM_SORT")) : 1;
+            if (dbg) {
+                if (grow_scratch(c, S_DBG, e.dbg, (size_t)CH * 4)) return c->status;
+                PD_CUDA(c, cudaMemsetAsync(e.dbg, 0xFF, (size_t)np * 16, st));
+            }
+            PD_CUDA(c, cudaMemsetAsync(e.valid, 0, np, st));
+            if (pd_launch_em(c, a, e, st, nl)) return c->status;
+            PD_CUDA(c, cudaEventRecord(c->ev[6 + par], st));
+            if (dbg) {
+                std::vector<uint32_t> hd((size_t)np * 4);
+                PD_CUDA(c, cudaMemcpyAsync(hd.data(), e.dbg, (size_t)np * 16, cudaMemcpyDeviceToHost, st));
+                PD_CUDA(c, cudaStreamSynchronize(st));
+                for (uint32_t i = 0; i < np; ++i)
+                    fprintf(stderr, "PD_DEBUG pair window %u L0 %d reason %u len %u it %u supp %u\n", h_jobwin[h_pairs[p0 + i].job],
+                            h_pairs[p0 + i].L0, hd[4 * i], hd[4 * i + 1], hd[4 * i + 2], hd[4 * i + 3]);
+            }
+            // result capacity: upper bound = calls emitted so far (exact once stream2 is drained) + this chunk
+            if ((size_t)(n_pairs_total - n_pairs + p0 + np) > c->cap_res_calls || (size_t)(n_pairs_total - n_pairs + p0 + np) * row > c->cap_res_ps) {
+                PD_CUDA(c, cudaStreamSynchronize(st2));
+                const size_t have = c->res_count[0];
+                if (ensure_results(c, have + np, row, have)) return c->status;
+            }
+            EmitArgs m;
+            m.valid = e.valid; m.calls = e.calls; m.ps = e.ps; m.npairs = np; m.row_words = (uint32_t)row;
+            m.counters = d_counters; m.chunk_base = d_chunk_base;
+            m.out_calls = c->res_calls; m.out_ps = c->res_ps; m.out_count = c->res_count;
+            PD_CUDA(c, cudaStreamWaitEvent(st2, c->ev[6 + par], 0));
+            pd_launch_emit_count(m, st2, nl);
+            pd_launch_emit_rows(m, st2, nl);
+            PD_CUDA(c, cudaGetLastError());
+            PD_CUDA(c, cudaEventRecord(c->ev[8 + par], st2));
+        }
+        // the next batch overwrites the pool / active-set tables that k_final of this batch reads: stream order
+        // on `stream` covers that; the pair list is only read by k_em / k_final as well.
+        tj0 = tj1;
+    }
+    PD_CUDA(c, cudaEventRecord(c->ev[5], st));
+    PD_CUDA(c, cudaStreamSynchronize(st));
+    PD_CUDA(c, cudaStreamSynchronize(st2));
+    out->n_calls = c->res_count[0];
+    out->calls = c->res_calls;
+    out->per_sample = c->res_ps;
+    out->n_candidates = n_pairs_total;
+    out->d2h_bytes = out->n_calls * (sizeof(pd_call) + row * 4);
+    PD_CUDA(c, cudaEventElapsedTime(&out->ms_screen, c->ev[3], c->ev[4]));
+    if (n_tiles) PD_CUDA(c, cudaEventElapsedTime(&out->ms_stream, c->ev[3], c->ev[10]));
+    PD_CUDA(c, cudaEventElapsedTime(&out->ms_genotype, c->ev[4], c->ev[5]));
+    PD_CUDA(c, cudaEventElapsedTime(&out->ms_total, c->ev[2], c->ev[5]));
+    out->ms_d2h = 0;
+    return 0;
+}
