@@ -20,7 +20,7 @@ constexpr uint32_t PD_GRAN = 1024;                  // words per warp in k_strea
 constexpr int PD_CAND_INLINE = 6;                   // candidate lengths kept inline per window job
 
 // device counters of one scan (uint32 each)
-enum { CNT_TJOBS = 0, CNT_JOBS = 1, CNT_PAIRS = 2, CNT_POOL = 3, CNT_CALLS = 4, CNT_N = 16 };
+enum { CNT_TJOBS = 0, CNT_JOBS = 1, CNT_PAIRS = 2, CNT_POOL = 3, CNT_CALLS = 4, CNT_CJOBS = 5, CNT_N = 16 };
 
 struct PdPair { uint32_t job; int32_t L0; };                         // (window job, initial deletion length)
 struct EmState { uint32_t len, it, alive, pad; double freq; double gt[3]; };   // handed from k_em to k_final
@@ -52,21 +52,29 @@ void pd_launch_tile_jobs(const JobArgs & j, cudaStream_t st, uint64_t * launches
 struct GatherArgs {
     const uint32_t * tj_tile, * tj_mask, * tj_wbase; uint32_t tj0, ntj;      // tile jobs [tj0, tj0 + ntj)
     uint32_t job_base;                  // first window job of this batch (scratch rows are relative to it)
-    uint32_t * pool_pos; int32_t * pool_dev; uint32_t pool_cap;              // active read pairs, SoA
-    uint32_t * counters;
-    uint32_t * act_off, * act_cnt;      // [jobs][R]
+    // Q3 pass (k_tile_q3): every flagged window
     int32_t * q3; uint8_t * sstat;      // [jobs][N]   sstat: 0 = low coverage, 1 = no usable values, 2 = Q3 valid
     int32_t * dmax;                     // [jobs][N]   largest deviation among the sample's usable active read pairs (INT_MIN: none)
+    // pool pass (k_tile_gather): windows with candidate lengths ("candidate jobs", numbered in window order per batch)
+    const uint32_t * tj_cmask, * tj_cfirst;      // [ntj] candidate windows of the tile / candidate job of the first of them
+    uint32_t cj_base, cj_end;           // this launch handles the tiles whose first candidate job lies in [cj_base, cj_end)
+    uint32_t * pool_pos; int32_t * pool_dev; uint32_t pool_cap;              // active read pairs, SoA
+    uint32_t * counters;
+    uint32_t * act_off, * act_cnt;      // [candidate jobs - cj_base][R]
+    uint32_t debug_flags;               // tests: bit 0 = generic path in k_tile_q3, bit 1 = generic path in k_tile_gather
 };
 struct CandArgs {
     const int32_t * q3; const uint8_t * sstat; uint32_t njobs, job_base;
     uint32_t * cand_cnt;                // [njobs]
     int32_t * cand_inline;              // [njobs][PD_CAND_INLINE]
     uint32_t * cand_off;                // [njobs] exclusive scan of cand_cnt
+    uint32_t * cjob_of;                 // [njobs] number of earlier windows of the batch with candidates (= candidate job)
     PdPair * pairs; uint32_t pair_cap;
     uint32_t * counters; unsigned long long * block_sums;
     uint32_t npad;
 };
+void pd_launch_q3(const PdDev & a, const GatherArgs & g, cudaStream_t st, uint64_t * launches);
+void pd_launch_cmask(const GatherArgs & g, const CandArgs & ca, uint32_t * tj_cmask, uint32_t * tj_cfirst, cudaStream_t st, uint64_t * launches);
 void pd_launch_gather(const PdDev & a, const GatherArgs & g, cudaStream_t st, uint64_t * launches);
 int  pd_launch_candidates(pd_ctx * c, const PdDev & a, const CandArgs & ca, cudaStream_t st, uint64_t * launches);
 
@@ -75,6 +83,7 @@ struct EmArgs {
     const uint32_t * job_window; const PdPair * pairs; uint32_t pair0, npairs, job_base;   // pairs[].job is absolute
     const uint32_t * pool_pos; const int32_t * pool_dev; const uint32_t * act_off, * act_cnt; const uint8_t * sstat;
     const int32_t * dmax;    // [job][N]
+    const uint32_t * cjob_of; uint32_t cj_base;      // act_off / act_cnt rows: cjob_of[job] - cj_base
     double * dlx;            // [pair][N][3]   data likelihoods, log domain, max = 0
     double * dle;            // [pair][N][3]   exp(dlx)
     int32_t * shifts;        // [pair][R]

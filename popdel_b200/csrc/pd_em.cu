@@ -117,8 +117,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_em(PdDev a, EmArgs e)
     const uint32_t job = pr.job - e.job_base;
     const int L0 = pr.L0;
     const uint32_t w = e.job_window[pr.job];
-    const uint32_t * cnt = e.act_cnt + (size_t)job * a.R;
-    const uint32_t * off = e.act_off + (size_t)job * a.R;
+    const uint32_t cj = e.cjob_of[job] - e.cj_base;
+    const uint32_t * cnt = e.act_cnt + (size_t)cj * a.R;
+    const uint32_t * off = e.act_off + (size_t)cj * a.R;
     double * dlx = e.dlx + (size_t)blockIdx.x * 3 * a.N;
     double * dle = e.dle + (size_t)blockIdx.x * 3 * a.N;
     int32_t * shifts = e.shifts + (size_t)blockIdx.x * a.R;
@@ -272,8 +273,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_final(PdDev a, EmArgs e)
     const uint32_t job = pr.job - e.job_base;
     const uint32_t L0 = (uint32_t)pr.L0;
     const uint32_t w = e.job_window[pr.job];
-    const uint32_t * cnt = e.act_cnt + (size_t)job * a.R;
-    const uint32_t * off = e.act_off + (size_t)job * a.R;
+    const uint32_t cj = e.cjob_of[job] - e.cj_base;
+    const uint32_t * cnt = e.act_cnt + (size_t)cj * a.R;
+    const uint32_t * off = e.act_off + (size_t)cj * a.R;
     const uint8_t * sstat = e.sstat + (size_t)job * a.N;
     double * dlx = e.dlx + (size_t)blockIdx.x * 3 * a.N;
     double * dle = e.dle + (size_t)blockIdx.x * 3 * a.N;
@@ -578,10 +580,11 @@ __global__ void __launch_bounds__(MAXT, MINB) k_em_one(PdDev a, EmArgs e)
     const PdRgConst * rg = a.rgc + (has ? s : 0);
     RgOne k;
     k.fl = a.tab + __ldg(&rg->hist_off); k.hist_base = __ldg(&rg->hist_base); k.hist_len = __ldg(&rg->hist_len); k.min_prob = __ldg(&rg->min_prob); k.ln_min_prob = __ldg(&rg->ln_min_prob);
-    const uint32_t n_all = has ? e.act_cnt[(size_t)job * a.R + s] : 0u;
+    const uint32_t cj = e.cjob_of[job] - e.cj_base;
+    const uint32_t n_all = has ? e.act_cnt[(size_t)cj * a.R + s] : 0u;
     const bool usable = has && n_all < __ldg(&rg->max_load);
     const uint32_t n = usable ? n_all : 0u;
-    const uint32_t poff = has ? e.act_off[(size_t)job * a.R + s] : 0u;
+    const uint32_t poff = has ? e.act_off[(size_t)cj * a.R + s] : 0u;
     const int32_t * pd = e.pool_dev + poff;
     const int nl = n > (uint32_t)sub ? (int)((n - sub + LPS - 1) / LPS) : 0;
     const double dn = (double)n;

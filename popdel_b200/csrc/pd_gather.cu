@@ -1,9 +1,13 @@
 // pd_gather.cu -- K2: active sets, per-sample upper-half medians and candidate deletion lengths of the flagged windows.
 //
-//   k_tile_gather  one warp = (flagged tile, sample): the read pairs that can be active anywhere in the tile are decoded
-//                  ONCE into shared memory (interval, position, deviation); every flagged window of the tile then only
-//                  filters that staged list: active read pairs -> pool (structure of arrays), coverage state, and the
-//                  sample's Q3 (upperHalfMedian, genotype_deletion_popdel_call.h:15-27) by a warp bitonic sort.
+//   k_tile_q3      one warp = (flagged tile, sample), one LANE = one window of the tile: the read pairs that can be active
+//                  in the tile are staged read group by read group in shared memory and scattered into per-window
+//                  value lists; every lane then selects its window's Q3 (upperHalfMedian,
+//                  genotype_deletion_popdel_call.h:15-27) by bisection on the value. Writes Q3, coverage state and the
+//                  largest deviation per (window, sample) -- nothing else, so windows without candidates cost no pool.
+//   k_tile_cmask   per flagged tile: the windows that got at least one candidate length, and their first row.
+//   k_tile_gather  one warp = (tile with candidates, sample): active read pairs of the candidate windows -> pool
+//                  (structure of arrays) + per read group offsets / counts, read by the EM kernels.
 //   k_candidates   one block per flagged window: sort the Q3s over samples, gap-50 clustering with rank-indexed
 //                  thresholds (:58-86) -> candidate initial lengths, kept inline per window.
 //   k_cand_*       exclusive scan of the candidate counts -> (window, initial length) pairs in reference order.
@@ -38,29 +42,198 @@ __device__ __forceinline__ int32_t q3_value(uint32_t nn, double r, int32_t lo_v,
     return (int32_t)floor((1 - r) * lo_v + r * hi_v + 0.5);
 }
 
-// ascending bitonic sort of one value per lane
-__device__ __forceinline__ int32_t warp_sort(int32_t v, int lane)
+// ------------------------------------------------------------------------------------------------------------------
+// K2a: Q3 of every (flagged window, sample)
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int TQ_WARPS = 4;
+constexpr int TQ_STAGE = 320;                                       // staged read pairs per read group and tile
+constexpr int TQ_ACT = 48;                                          // usable active read pairs per (window, sample), fast path
+
+struct alignas(16) WarpQ3 {
+    uint32_t se[TQ_STAGE];                                          // first | last << 8 window of the tile the pair is active in
+    int32_t dev[TQ_STAGE];
+    int32_t val[TQ_ACT][32];                                        // [slot][window]: deviations of the window's usable active pairs
+    uint32_t cnt[32];
+};
+
+__device__ __forceinline__ void write_q3(const GatherArgs & ga, uint32_t N, uint32_t job, uint32_t smp, uint32_t cov, uint32_t n,
+                                         int32_t q, int32_t mx)
 {
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1)
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            const int32_t o = __shfl_xor_sync(PD_FULL, v, j);
-            const bool up = ((lane & k) == 0) == ((lane & j) == 0);      // keep the minimum
-            v = up ? min(v, o) : max(v, o);
-        }
-    return v;
+    const size_t o = (size_t)job * N + smp;
+    ga.q3[o] = (cov >= 2u && n) ? q : 0;
+    ga.sstat[o] = cov < 2u ? 0 : (n == 0 ? 1 : 2);
+    ga.dmax[o] = n ? mx : INT_MIN;
 }
 
-// Generic (slow) path of one (window, sample): streams the read groups twice, no shared memory. Used when the staged
-// list or the active set does not fit the fast path.
-__device__ __noinline__ void gather_window_slow(const PdDev & a, const GatherArgs & ga, uint32_t smp, int32_t w, uint32_t job, int lane)
+// Generic path of one (window, sample): no shared memory, any number of read pairs / read groups. The order
+// statistics are found by bisection on the value, one pass over the read groups' tile batches per step.
+__device__ __noinline__ void q3_window_slow(const PdDev & a, const GatherArgs & ga, uint32_t smp, int32_t w, uint32_t job, int lane)
 {
     const uint32_t g0 = a.sample_rg[smp], g1 = a.sample_rg[smp + 1];
-    uint32_t * cnt = ga.act_cnt + (size_t)job * a.R;
-    uint32_t * off = ga.act_off + (size_t)job * a.R;
     const uint32_t tile = (uint32_t)w / PD_TILE_WINDOWS;
-    uint32_t cov = 0, nvals = 0;
+    // counts how many usable active deviations are <= t; also the smallest one above t
+    auto pass = [&](int32_t t, uint32_t & cov, uint32_t & nvals, int32_t & mn, int32_t & mx, int32_t & above) {
+        uint32_t c = 0;
+        cov = 0; nvals = 0; mn = INT_MAX; mx = INT_MIN; above = INT_MAX;
+        for (uint32_t g = g0; g < g1; ++g) {
+            const PdRgConst k = a.rgc[g];
+            uint32_t n_g = 0, c_g = 0; int32_t mn_g = INT_MAX, mx_g = INT_MIN, ab_g = INT_MAX;
+            for_tile_batches(a, g, k, tile, lane, [&](bool valid, int32_t s, int32_t e, uint32_t, int32_t dev) {
+                valid = valid && s <= w && w <= e;
+                n_g += __popc(__ballot_sync(PD_FULL, valid));
+                c_g += __popc(__ballot_sync(PD_FULL, valid && dev <= t));
+                if (valid) { mn_g = min(mn_g, dev); mx_g = max(mx_g, dev); if (dev > t) ab_g = min(ab_g, dev); }
+            });
+            cov += n_g;
+            if (n_g < k.max_load) { nvals += n_g; c += c_g; mn = min(mn, mn_g); mx = max(mx, mx_g); above = min(above, ab_g); }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = min(mn, __shfl_xor_sync(PD_FULL, mn, o)); mx = max(mx, __shfl_xor_sync(PD_FULL, mx, o));
+            above = min(above, __shfl_xor_sync(PD_FULL, above, o));
+        }
+        return c;
+    };
+    uint32_t cov, n; int32_t mn, mx, above;
+    pass(INT_MAX, cov, n, mn, mx, above);
+    int32_t q = 0;
+    if (cov >= 2u && n) {
+        uint32_t l, l2; double r;
+        q3_position(n, l, l2, r);
+        int32_t lo_v = mx, hi_v = mx;
+        if (n >= 4) {
+            int32_t lo = mn, hi = mx;
+            uint32_t cov2, n2; int32_t a2, b2, ab2;
+            while (lo < hi) {
+                const int32_t mid = lo + (int32_t)(((uint32_t)hi - (uint32_t)lo) >> 1);
+                if (pass(mid, cov2, n2, a2, b2, ab2) >= l + 1) hi = mid; else lo = mid + 1;
+            }
+            lo_v = lo;
+            hi_v = pass(lo_v, cov2, n2, a2, b2, ab2) >= l2 + 1 ? lo_v : ab2;
+        }
+        q = q3_value(n, r, lo_v, hi_v);
+    }
+    if (lane == 0) write_q3(ga, a.N, job, smp, cov, n, q, mx);
+}
+
+__global__ void __launch_bounds__(TQ_WARPS * 32) k_tile_q3(PdDev a, GatherArgs ga)
+{
+    __shared__ WarpQ3 sh_all[TQ_WARPS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t smp = blockIdx.y * TQ_WARPS + wib;
+    if (smp >= a.N) return;
+    const uint32_t tj = ga.tj0 + blockIdx.x;
+    const uint32_t tile = ga.tj_tile[tj], wmask = ga.tj_mask[tj];
+    const uint32_t job_first = ga.tj_wbase[tj] - ga.job_base;            // scratch row of the tile's first flagged window
+    const uint32_t g0 = a.sample_rg[smp], g1 = a.sample_rg[smp + 1];
+    WarpQ3 & sh = sh_all[wib];
+    const int32_t w0 = (int32_t)(tile * PD_TILE_WINDOWS);
+    const uint32_t lane_bit = 1u << lane;
+    const uint32_t my_job = job_first + __popc(wmask & (lane_bit - 1u));
+
+    sh.cnt[lane] = 0;
+    uint32_t cov = 0;
+    bool slow = (ga.debug_flags & 1u) != 0;
+    __syncwarp();
+    for (uint32_t g = g0; g < g1 && !slow; ++g) {
+        const PdRgConst k = a.rgc[g];
+        // ---- stage this read group's pairs whose interval meets a flagged window of the tile
+        uint32_t total = 0;
+        for_tile_batches(a, g, k, tile, lane, [&](bool valid, int32_t s, int32_t e, uint32_t, int32_t dev) {
+            uint32_t m = 0, sr = 0, er = 0;
+            if (valid && e >= w0 && s <= w0 + 31) {
+                sr = (uint32_t)max(s - w0, 0); er = (uint32_t)min(e - w0, 31);
+                m = wmask & (er == 31u ? 0xFFFFFFFFu : ((1u << (er + 1)) - 1u)) & ~((1u << sr) - 1u);
+            }
+            const uint32_t mask = __ballot_sync(PD_FULL, m != 0);
+            const uint32_t slot = total + __popc(mask & (lane_bit - 1u));
+            if (m && slot < (uint32_t)TQ_STAGE) { sh.se[slot] = sr | (er << 8); sh.dev[slot] = dev; }
+            total += __popc(mask);
+        });
+        if (total > (uint32_t)TQ_STAGE) { slow = true; break; }
+        const uint32_t before = sh.cnt[lane];
+        __syncwarp();
+        // ---- scatter: every pair appends its deviation to the lists of the flagged windows it is active in
+        for (uint32_t i = lane; i < total; i += 32) {
+            const uint32_t se = sh.se[i], sr = se & 0xFFu, er = se >> 8;
+            const int32_t dev = sh.dev[i];
+            uint32_t m = wmask & (er == 31u ? 0xFFFFFFFFu : ((1u << (er + 1)) - 1u)) & ~((1u << sr) - 1u);
+            while (m) {
+                const int w = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t slot = atomicAdd(&sh.cnt[w], 1u);
+                if (slot < (uint32_t)TQ_ACT) sh.val[slot][w] = dev;
+            }
+        }
+        __syncwarp();
+        const uint32_t n_g = sh.cnt[lane] - before;
+        cov += n_g;
+        if (n_g >= k.max_load) sh.cnt[lane] = before;                    // a high-coverage read group is left out (:1443-1478)
+        __syncwarp();
+    }
+    const bool flagged = (wmask & lane_bit) != 0;
+    const uint32_t n = sh.cnt[lane];
+    const uint32_t over = __ballot_sync(PD_FULL, flagged && n > (uint32_t)TQ_ACT);
+    uint32_t slow_mask = slow ? wmask : over;
+    if (!slow && flagged && n <= (uint32_t)TQ_ACT) {
+        int32_t q = 0, mx = INT_MIN;
+        if (cov >= 2u && n) {
+            int32_t mn = INT_MAX;
+            for (uint32_t i = 0; i < n; ++i) { const int32_t v = sh.val[i][lane]; mn = min(mn, v); mx = max(mx, v); }
+            uint32_t l, l2; double r;
+            q3_position(n, l, l2, r);
+            int32_t lo_v = mx, hi_v = mx;
+            if (n >= 4) {
+                int32_t lo = mn, hi = mx;
+                while (lo < hi) {                                        // smallest v with #{x <= v} >= l + 1
+                    const int32_t mid = lo + (int32_t)(((uint32_t)hi - (uint32_t)lo) >> 1);
+                    uint32_t c = 0;
+                    for (uint32_t i = 0; i < n; ++i) c += sh.val[i][lane] <= mid;
+                    if (c >= l + 1) hi = mid; else lo = mid + 1;
+                }
+                lo_v = lo;
+                uint32_t c = 0; int32_t above = INT_MAX;
+                for (uint32_t i = 0; i < n; ++i) { const int32_t v = sh.val[i][lane]; c += v <= lo_v; if (v > lo_v) above = min(above, v); }
+                hi_v = c >= l2 + 1 ? lo_v : above;
+            }
+            q = q3_value(n, r, lo_v, hi_v);
+        } else if (n) {
+            for (uint32_t i = 0; i < n; ++i) mx = max(mx, sh.val[i][lane]);
+        }
+        write_q3(ga, a.N, my_job, smp, cov, n, q, mx);
+    }
+    __syncwarp();
+    for (; slow_mask; slow_mask &= slow_mask - 1) {
+        const int wl = __ffs(slow_mask) - 1;
+        q3_window_slow(a, ga, smp, w0 + wl, job_first + __popc(wmask & ((1u << wl) - 1u)), lane);
+    }
+}
+
+// candidate windows of every flagged tile (after the candidate counts are known)
+__global__ void __launch_bounds__(256) k_tile_cmask(GatherArgs ga, const uint32_t * __restrict__ cand_cnt, const uint32_t * __restrict__ cjob_of,
+                                                    uint32_t * __restrict__ tj_cmask, uint32_t * __restrict__ tj_cfirst)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ga.ntj) return;
+    const uint32_t tj = ga.tj0 + i;
+    const uint32_t first = ga.tj_wbase[tj] - ga.job_base;
+    uint32_t cm = 0, cf = 0xFFFFFFFFu, r = 0;
+    for (uint32_t m = ga.tj_mask[tj]; m; m &= m - 1, ++r)
+        if (cand_cnt[first + r]) { cm |= m & (0u - m); if (cf == 0xFFFFFFFFu) cf = cjob_of[first + r]; }
+    tj_cmask[i] = cm; tj_cfirst[i] = cf;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K2c: active sets of the candidate windows -> pool
+// ------------------------------------------------------------------------------------------------------------------
+// Generic (slow) path of one (window, sample): streams the read groups twice, no shared memory. Used when the staged
+// list or the active set does not fit the fast path.
+__device__ __noinline__ void gather_window_slow(const PdDev & a, const GatherArgs & ga, uint32_t smp, int32_t w, uint32_t row, int lane)
+{
+    const uint32_t g0 = a.sample_rg[smp], g1 = a.sample_rg[smp + 1];
+    uint32_t * cnt = ga.act_cnt + (size_t)row * a.R;
+    uint32_t * off = ga.act_off + (size_t)row * a.R;
+    const uint32_t tile = (uint32_t)w / PD_TILE_WINDOWS;
+    uint32_t nvals = 0;
     for (uint32_t g = g0; g < g1; ++g) {
         const PdRgConst k = a.rgc[g];
         uint32_t n_g = 0;
@@ -68,7 +241,6 @@ __device__ __noinline__ void gather_window_slow(const PdDev & a, const GatherArg
             n_g += __popc(__ballot_sync(PD_FULL, valid && s <= w && w <= e));
         });
         if (lane == 0) { cnt[g] = n_g; off[g] = nvals; }
-        cov += n_g;
         if (n_g < k.max_load) nvals += n_g;
     }
     uint32_t base = 0;
@@ -92,33 +264,6 @@ __device__ __noinline__ void gather_window_slow(const PdDev & a, const GatherArg
         }
     }
     __syncwarp();
-    uint8_t stt; int32_t q = 0, dmx = INT_MIN;
-    if (cov < 2u) stt = 0;
-    else if (nvals == 0 || !fits) stt = 1;
-    else {
-        stt = 2;
-        uint32_t l, l2; double r;
-        q3_position(nvals, l, l2, r);
-        int32_t lo_v = 0, hi_v = 0;
-        const volatile int32_t * v = ga.pool_dev + base;                 // written above by this warp
-        for (uint32_t i0 = 0; i0 < nvals; i0 += 32) {
-            const uint32_t i = i0 + lane;
-            const int32_t vi = i < nvals ? v[i] : INT_MAX;
-            uint32_t rank = 0;
-            for (uint32_t j = 0; j < nvals; ++j) { const int32_t vj = v[j]; rank += (vj < vi) || (vj == vi && j < i); }
-            const uint32_t m1 = __ballot_sync(PD_FULL, i < nvals && rank == l);
-            const uint32_t m2 = __ballot_sync(PD_FULL, i < nvals && rank == l2);
-            if (m1) lo_v = __shfl_sync(PD_FULL, vi, __ffs(m1) - 1);
-            if (m2) hi_v = __shfl_sync(PD_FULL, vi, __ffs(m2) - 1);
-        }
-        q = q3_value(nvals, r, lo_v, hi_v);
-    }
-    if (fits && nvals) {
-        const volatile int32_t * v = ga.pool_dev + base;
-        for (uint32_t i = lane; i < nvals; i += 32) dmx = max(dmx, v[i]);
-        for (int o = 16; o > 0; o >>= 1) dmx = max(dmx, __shfl_xor_sync(PD_FULL, dmx, o));
-    }
-    if (lane == 0) { ga.q3[(size_t)job * a.N + smp] = q; ga.sstat[(size_t)job * a.N + smp] = stt; ga.dmax[(size_t)job * a.N + smp] = dmx; }
 }
 
 __global__ void __launch_bounds__(TG_WARPS * 32) k_tile_gather(PdDev a, GatherArgs ga)
@@ -127,16 +272,18 @@ __global__ void __launch_bounds__(TG_WARPS * 32) k_tile_gather(PdDev a, GatherAr
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t smp = blockIdx.y * TG_WARPS + wib;
     if (smp >= a.N) return;
-    const uint32_t tj = ga.tj0 + blockIdx.x;
-    const uint32_t tile = ga.tj_tile[tj], wmask = ga.tj_mask[tj];
-    const uint32_t job_first = ga.tj_wbase[tj] - ga.job_base;            // scratch row of the tile's first flagged window
+    const uint32_t wmask = ga.tj_cmask[blockIdx.x];                       // windows of the tile with candidate lengths
+    const uint32_t cfirst = ga.tj_cfirst[blockIdx.x];
+    if (wmask == 0 || cfirst < ga.cj_base || cfirst >= ga.cj_end) return;
+    const uint32_t tile = ga.tj_tile[ga.tj0 + blockIdx.x];
+    const uint32_t row_first = cfirst - ga.cj_base;                       // scratch row of the tile's first candidate window
     const uint32_t g0 = a.sample_rg[smp], g1 = a.sample_rg[smp + 1], nrg = g1 - g0;
     WarpStage & st = stage_all[wib];
     const int32_t w0 = (int32_t)(tile * PD_TILE_WINDOWS);
 
     // ---- stage every read pair whose interval intersects the tile (per read group, stream order)
     uint32_t total = 0;
-    bool fast = nrg <= (uint32_t)TG_MAXRG;
+    bool fast = nrg <= (uint32_t)TG_MAXRG && !(ga.debug_flags & 2u);
     if (fast) {
         for (uint32_t g = g0; g < g1; ++g) {
             if (lane == 0) st.rg_first[g - g0] = total;
@@ -154,8 +301,8 @@ __global__ void __launch_bounds__(TG_WARPS * 32) k_tile_gather(PdDev a, GatherAr
     }
     __syncwarp();
 
-    // one pool reservation per (tile, sample): the staged read pairs' active windows among the flagged ones (an upper
-    // bound of what is written: a high-coverage read group is left out of the pool)
+    // one pool reservation per (tile, sample): the staged read pairs' active windows among the candidate ones (an
+    // upper bound of what is written: a high-coverage read group is left out of the pool)
     uint32_t tile_base = 0; bool tile_fits = true;
     if (fast) {
         uint32_t tot = 0;
@@ -173,11 +320,11 @@ __global__ void __launch_bounds__(TG_WARPS * 32) k_tile_gather(PdDev a, GatherAr
     uint32_t rank = 0;
     for (uint32_t m = wmask; m; m &= m - 1, ++rank) {
         const int32_t w = w0 + (__ffs(m) - 1);
-        const uint32_t job = job_first + rank;
-        if (!fast) { gather_window_slow(a, ga, smp, w, job, lane); continue; }
-        uint32_t * cnt = ga.act_cnt + (size_t)job * a.R;
-        uint32_t * off = ga.act_off + (size_t)job * a.R;
-        uint32_t cov = 0, nvals = 0;
+        const uint32_t row = row_first + rank;
+        if (!fast) { gather_window_slow(a, ga, smp, w, row, lane); continue; }
+        uint32_t * cnt = ga.act_cnt + (size_t)row * a.R;
+        uint32_t * off = ga.act_off + (size_t)row * a.R;
+        uint32_t nvals = 0;
         for (uint32_t gi = 0; gi < nrg; ++gi) {
             const uint32_t i_lo = st.rg_first[gi], i_hi = st.rg_first[gi + 1];
             uint32_t n_g = 0;
@@ -191,50 +338,18 @@ __global__ void __launch_bounds__(TG_WARPS * 32) k_tile_gather(PdDev a, GatherAr
                 n_g += __popc(mask);
             }
             if (lane == 0) { cnt[g0 + gi] = n_g; off[g0 + gi] = nvals; }
-            cov += n_g;
             if (n_g < __ldg(&a.rgc[g0 + gi].max_load)) nvals += n_g;          // a high-coverage read group is left out
         }
-        if (nvals > (uint32_t)TG_ACT) { gather_window_slow(a, ga, smp, w, job, lane); continue; }
+        if (nvals > (uint32_t)TG_ACT) { gather_window_slow(a, ga, smp, w, row, lane); continue; }
         const uint32_t base = tile_base;
-        const bool fits = tile_fits;
         tile_base += nvals;
         __syncwarp();
         if ((uint32_t)lane < nrg) off[g0 + lane] += base;
-        int32_t dmx = INT_MIN;
-        for (uint32_t i = lane; i < nvals; i += 32) {
-            const StagePair p = st.pair[st.act[i]];
-            dmx = max(dmx, p.dev);
-            if (fits) { ga.pool_pos[base + i] = p.pos; ga.pool_dev[base + i] = p.dev; }
-        }
-        for (int o = 16; o > 0; o >>= 1) dmx = max(dmx, __shfl_xor_sync(PD_FULL, dmx, o));
-        uint8_t stt; int32_t q = 0;
-        if (cov < 2u) stt = 0;
-        else if (nvals == 0 || !fits) stt = 1;
-        else {
-            stt = 2;
-            uint32_t l, l2; double r;
-            q3_position(nvals, l, l2, r);
-            int32_t lo_v, hi_v;
-            if (nvals <= 32) {
-                const int32_t v = warp_sort((uint32_t)lane < nvals ? st.pair[st.act[lane]].dev : INT_MAX, lane);
-                lo_v = __shfl_sync(PD_FULL, v, (int)l);
-                hi_v = __shfl_sync(PD_FULL, v, (int)l2);
-            } else {                                                      // 33..TG_ACT values: rank counting in shared memory
-                lo_v = hi_v = 0;
-                for (uint32_t i0 = 0; i0 < nvals; i0 += 32) {
-                    const uint32_t i = i0 + lane;
-                    const int32_t vi = i < nvals ? st.pair[st.act[i]].dev : INT_MAX;
-                    uint32_t rk = 0;
-                    for (uint32_t j = 0; j < nvals; ++j) { const int32_t vj = st.pair[st.act[j]].dev; rk += (vj < vi) || (vj == vi && j < i); }
-                    const uint32_t m1 = __ballot_sync(PD_FULL, i < nvals && rk == l);
-                    const uint32_t m2 = __ballot_sync(PD_FULL, i < nvals && rk == l2);
-                    if (m1) lo_v = __shfl_sync(PD_FULL, vi, __ffs(m1) - 1);
-                    if (m2) hi_v = __shfl_sync(PD_FULL, vi, __ffs(m2) - 1);
-                }
+        if (tile_fits)
+            for (uint32_t i = lane; i < nvals; i += 32) {
+                const StagePair p = st.pair[st.act[i]];
+                ga.pool_pos[base + i] = p.pos; ga.pool_dev[base + i] = p.dev;
             }
-            q = q3_value(nvals, r, lo_v, hi_v);
-        }
-        if (lane == 0) { ga.q3[(size_t)job * a.N + smp] = q; ga.sstat[(size_t)job * a.N + smp] = stt; ga.dmax[(size_t)job * a.N + smp] = dmx; }
         __syncwarp();                                                     // st.act is rewritten by the next window
     }
 }
@@ -290,13 +405,17 @@ __global__ void __launch_bounds__(256) k_candidates(PdDev a, CandArgs ca, int mo
     }
 }
 
-// exclusive scan of cand_cnt -> cand_off, total -> counters[CNT_PAIRS]; inline candidates -> pairs
+// exclusive scan of cand_cnt -> cand_off, total -> counters[CNT_PAIRS]; inline candidates -> pairs. The same scan numbers
+// the windows that have candidates (cjob_of, total -> counters[CNT_CJOBS]): value = pairs (low 40 bits) | windows << 40.
+__device__ __forceinline__ unsigned long long cand_value(uint32_t c) { return c ? ((1ull << 40) | c) : 0ull; }
+constexpr unsigned long long CAND_LOW = (1ull << 40) - 1;
+
 __global__ void __launch_bounds__(1024) k_cand_sums(CandArgs ca)
 {
     __shared__ unsigned long long ws[33];
     const uint32_t i = blockIdx.x * 1024 + threadIdx.x;
     unsigned long long total;
-    block_excl_scan(i < ca.njobs ? ca.cand_cnt[i] : 0u, ws, total);
+    block_excl_scan(cand_value(i < ca.njobs ? ca.cand_cnt[i] : 0u), ws, total);
     if (threadIdx.x == 0) ca.block_sums[blockIdx.x] = total;
 }
 __global__ void __launch_bounds__(1024) k_cand_offsets(CandArgs ca, uint32_t nb)
@@ -310,7 +429,10 @@ __global__ void __launch_bounds__(1024) k_cand_offsets(CandArgs ca, uint32_t nb)
         if (b < nb) ca.block_sums[b] = carry + ex;
         carry += total;
     }
-    if (threadIdx.x == 0) ca.counters[CNT_PAIRS] = (uint32_t)min(carry, 0xFFFFFFFFull);
+    if (threadIdx.x == 0) {
+        ca.counters[CNT_PAIRS] = (uint32_t)min(carry & CAND_LOW, 0xFFFFFFFFull);
+        ca.counters[CNT_CJOBS] = (uint32_t)(carry >> 40);
+    }
 }
 __global__ void __launch_bounds__(1024) k_cand_write(CandArgs ca)
 {
@@ -318,15 +440,29 @@ __global__ void __launch_bounds__(1024) k_cand_write(CandArgs ca)
     const uint32_t i = blockIdx.x * 1024 + threadIdx.x;
     const uint32_t c = i < ca.njobs ? ca.cand_cnt[i] : 0u;
     unsigned long long total;
-    const uint32_t o = (uint32_t)(block_excl_scan(c, ws, total) + ca.block_sums[blockIdx.x]);
+    const unsigned long long ex = block_excl_scan(cand_value(c), ws, total) + ca.block_sums[blockIdx.x];
     if (i >= ca.njobs) return;
+    const uint32_t o = (uint32_t)min(ex & CAND_LOW, 0xFFFFFFFFull);
     ca.cand_off[i] = o;
+    ca.cjob_of[i] = (uint32_t)(ex >> 40);
     if (c <= (uint32_t)PD_CAND_INLINE)
         for (uint32_t k = 0; k < c; ++k)
             if (o + k < ca.pair_cap) ca.pairs[o + k] = PdPair{ca.job_base + i, ca.cand_inline[(size_t)i * PD_CAND_INLINE + k]};
 }
 
 }  // namespace
+
+void pd_launch_q3(const PdDev & a, const GatherArgs & g, cudaStream_t st, uint64_t * launches)
+{
+    k_tile_q3<<<dim3(g.ntj, (a.N + TQ_WARPS - 1) / TQ_WARPS), TQ_WARPS * 32, 0, st>>>(a, g);
+    ++*launches;
+}
+
+void pd_launch_cmask(const GatherArgs & g, const CandArgs & ca, uint32_t * tj_cmask, uint32_t * tj_cfirst, cudaStream_t st, uint64_t * launches)
+{
+    k_tile_cmask<<<(g.ntj + 255) / 256, 256, 0, st>>>(g, ca.cand_cnt, ca.cjob_of, tj_cmask, tj_cfirst);
+    ++*launches;
+}
 
 void pd_launch_gather(const PdDev & a, const GatherArgs & g, cudaStream_t st, uint64_t * launches)
 {

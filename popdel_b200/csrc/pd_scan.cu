@@ -17,7 +17,7 @@ namespace {
 
 enum Slot {                                     // d_scratch slots
     S_NEED = 0, S_TFLAGS, S_COUNTERS, S_TJ_TILE, S_TJ_MASK, S_TJ_WBASE, S_JOBWIN, S_BSUMS,
-    S_ACT_OFF, S_ACT_CNT, S_Q3, S_SSTAT, S_CAND_CNT, S_CAND_INL, S_CAND_OFF, S_PAIRS, S_POOL_POS, S_POOL_DEV,
+    S_ACT_OFF, S_ACT_CNT, S_Q3, S_SSTAT, S_CAND_CNT, S_CAND_INL, S_CAND_OFF, S_CJOB_OF, S_TJ_CMASK, S_TJ_CFIRST, S_PAIRS, S_POOL_POS, S_POOL_DEV,
     S_DLX, S_DLE, S_SHIFTS, S_STATES, S_PS0, S_PS1, S_CALLS0, S_CALLS1, S_VALID0, S_VALID1, S_CHUNK_BASE, S_DBG, S_DMAX
 };
 
@@ -168,9 +168,15 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
     const uint32_t n_tj = h_cnt[CNT_TJOBS], n_jobs = h_cnt[CNT_JOBS];
     out->n_flagged_windows = n_jobs;
 
-    // ---- genotyping stage, in batches of tile jobs
-    const size_t job_bytes = 8ull * R + 5ull * N + 8ull * (PD_CAND_INLINE + 2) + 400ull * N;
-    const uint32_t JB = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(4000000000ull / job_bytes, 64), 1u << 20);
+    // ---- genotyping stage. Level 1: batches of tile jobs (Q3 of every flagged window, candidates). Level 2: the windows
+    // with candidates ("candidate jobs") in sub-batches of whole tiles (active-set pool, EM, final pass, emission).
+    const size_t job_bytes = 9ull * N + 4ull * (PD_CAND_INLINE + 3) + 8;
+    uint32_t JB = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(3000000000ull / job_bytes, 64), 1u << 20);
+    if (getenv("PD_JOB_BATCH")) JB = std::max<uint32_t>((uint32_t)atoi(getenv("PD_JOB_BATCH")), 64);           // test knobs
+    const uint32_t rows_env = getenv("PD_CJOB_ROWS") ? std::max<uint32_t>((uint32_t)atoi(getenv("PD_CJOB_ROWS")), 1) : 0;
+    const uint32_t slow_env = getenv("PD_FORCE_SLOW") ? (uint32_t)atoi(getenv("PD_FORCE_SLOW")) : 0;
+    const size_t cjob_bytes = 8ull * R + 400ull * N;
+    const uint32_t JB2 = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(4000000000ull / cjob_bytes, 64), 1u << 20);
     std::vector<uint32_t> h_wbase;
     if (n_jobs > JB) {
         h_wbase.resize(n_tj);
@@ -181,9 +187,10 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
     if ((size_t)npad * 4 > 200 * 1024) return pd_fail(c, PD_ERR_CAPACITY, "more than 51200 samples per context: candidate sort does not fit shared memory (shard by sample)");
     const size_t pair_bytes = 48ull * N + 4ull * R + 2 * 52ull * N + 128;
     const uint32_t CH = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(2000000000ull / pair_bytes, 64), getenv("PD_EM_CHUNK") ? atoi(getenv("PD_EM_CHUNK")) : 8192);
-    uint64_t n_pairs_total = 0;
+    uint64_t n_pairs_total = 0, n_cjobs_total = 0;
     uint32_t chunk_no = 0;
     std::vector<uint32_t> h_jobwin; std::vector<PdPair> h_pairs;
+    std::vector<uint32_t> h_cfirst, h_cmask, h_tjw, h_cand_off;
     if (dbg && n_jobs) {
         h_jobwin.resize(n_jobs);
         PD_CUDA(c, cudaMemcpy(h_jobwin.data(), j.job_window, (size_t)n_jobs * 4, cudaMemcpyDeviceToHost));
@@ -200,106 +207,157 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
             while (tj1 < n_tj && h_wbase[tj1] - job_base <= JB - PD_TILE_WINDOWS) ++tj1;
             nj = (tj1 < n_tj ? h_wbase[tj1] : n_jobs) - job_base;
         }
+        const uint32_t ntj = tj1 - tj0;
         GatherArgs ga;
-        ga.tj_tile = j.tj_tile; ga.tj_mask = j.tj_mask; ga.tj_wbase = j.tj_wbase; ga.tj0 = tj0; ga.ntj = tj1 - tj0;
+        memset(&ga, 0, sizeof(ga));
+        ga.tj_tile = j.tj_tile; ga.tj_mask = j.tj_mask; ga.tj_wbase = j.tj_wbase; ga.tj0 = tj0; ga.ntj = ntj;
         ga.job_base = job_base; ga.counters = d_counters;
-        if (grow_scratch(c, S_ACT_OFF, ga.act_off, (size_t)nj * R)) return c->status;
-        if (grow_scratch(c, S_ACT_CNT, ga.act_cnt, (size_t)nj * R)) return c->status;
         if (grow_scratch(c, S_Q3, ga.q3, (size_t)nj * N)) return c->status;
         if (grow_scratch(c, S_SSTAT, ga.sstat, (size_t)nj * N)) return c->status;
         if (grow_scratch(c, S_DMAX, ga.dmax, (size_t)nj * N)) return c->status;
+        uint32_t * d_cmask, * d_cfirst;
+        if (grow_scratch(c, S_TJ_CMASK, d_cmask, (size_t)ntj)) return c->status;
+        if (grow_scratch(c, S_TJ_CFIRST, d_cfirst, (size_t)ntj)) return c->status;
+        ga.tj_cmask = d_cmask; ga.tj_cfirst = d_cfirst;
         CandArgs ca;
         ca.q3 = ga.q3; ca.sstat = ga.sstat; ca.njobs = nj; ca.job_base = job_base; ca.counters = d_counters; ca.block_sums = d_bsums; ca.npad = npad;
         if (grow_scratch(c, S_CAND_CNT, ca.cand_cnt, (size_t)nj)) return c->status;
         if (grow_scratch(c, S_CAND_INL, ca.cand_inline, (size_t)nj * PD_CAND_INLINE)) return c->status;
         if (grow_scratch(c, S_CAND_OFF, ca.cand_off, (size_t)nj)) return c->status;
+        if (grow_scratch(c, S_CJOB_OF, ca.cjob_of, (size_t)nj)) return c->status;
+        uint32_t rows_cap = std::min<uint32_t>(std::min<uint32_t>(nj, JB2), (uint32_t)std::max<uint64_t>(1000000000ull / (8ull * R), 64));
+        if (rows_env) rows_cap = std::min(rows_cap, rows_env);
+        ga.debug_flags = slow_env;
+        if (grow_scratch(c, S_ACT_OFF, ga.act_off, (size_t)(rows_cap + PD_TILE_WINDOWS) * R)) return c->status;
+        if (grow_scratch(c, S_ACT_CNT, ga.act_cnt, (size_t)(rows_cap + PD_TILE_WINDOWS) * R)) return c->status;
         size_t pair_cap = std::max<size_t>(c->cap_scratch[S_PAIRS] / sizeof(PdPair), (size_t)nj * 2 + 1024);
-        uint32_t n_pairs = 0;
         if (c->pool_cap == 0) c->pool_cap = std::max<size_t>((size_t)std::min<uint32_t>(nj, 16384) * R * 40, 1u << 20);
-        bool gathered = false;
-        for (int attempt = 0; ; ++attempt) {
+
+        pd_launch_q3(a, ga, st, nl);
+        PD_CUDA(c, cudaGetLastError());
+        // candidates, then (optimistically) the pool of the first sub-batch; one synchronisation validates both
+        auto run_gather = [&](uint32_t cj_lo) -> int {
             if (c->pool_cap > 0xFFFFFFF0ull) c->pool_cap = 0xFFFFFFF0ull;
             if (grow_scratch(c, S_POOL_POS, ga.pool_pos, c->pool_cap)) return c->status;
             if (grow_scratch(c, S_POOL_DEV, ga.pool_dev, c->pool_cap)) return c->status;
+            ga.pool_cap = (uint32_t)c->pool_cap; ga.cj_base = cj_lo; ga.cj_end = cj_lo + rows_cap;
+            PD_CUDA(c, cudaMemsetAsync(d_counters + CNT_POOL, 0, 4, st));
+            pd_launch_gather(a, ga, st, nl);
+            PD_CUDA(c, cudaGetLastError());
+            return 0;
+        };
+        uint32_t n_pairs = 0, n_cj = 0;
+        bool cand_done = false;
+        for (int attempt = 0; ; ++attempt) {
             if (grow_scratch(c, S_PAIRS, ca.pairs, pair_cap)) return c->status;
-            ga.pool_cap = (uint32_t)c->pool_cap; ca.pair_cap = (uint32_t)std::min<size_t>(pair_cap, 0xFFFFFFF0ull);
-            if (!gathered) {
-                PD_CUDA(c, cudaMemsetAsync(d_counters + CNT_POOL, 0, 4, st));
-                pd_launch_gather(a, ga, st, nl);
-                PD_CUDA(c, cudaGetLastError());
+            ca.pair_cap = (uint32_t)std::min<size_t>(pair_cap, 0xFFFFFFF0ull);
+            if (!cand_done) {
+                if (pd_launch_candidates(c, a, ca, st, nl)) return c->status;
+                pd_launch_cmask(ga, ca, d_cmask, d_cfirst, st, nl);
             }
-            if (pd_launch_candidates(c, a, ca, st, nl)) return c->status;
+            if (run_gather(0)) return c->status;
             PD_CUDA(c, cudaMemcpyAsync(h_cnt, d_counters, CNT_N * 4, cudaMemcpyDeviceToHost, st));
             PD_CUDA(c, cudaStreamSynchronize(st));
             const bool pool_ok = h_cnt[CNT_POOL] <= c->pool_cap, pairs_ok = h_cnt[CNT_PAIRS] <= pair_cap;
-            if (pool_ok && pairs_ok) { n_pairs = h_cnt[CNT_PAIRS]; break; }
-            if (attempt == 2) return pd_fail(c, PD_ERR_CAPACITY, "active read-pair pool / candidate list overflow");
+            if (pool_ok && pairs_ok) { n_pairs = h_cnt[CNT_PAIRS]; n_cj = h_cnt[CNT_CJOBS]; break; }
+            if (attempt == 3) return pd_fail(c, PD_ERR_CAPACITY, "active read-pair pool / candidate list overflow");
             if (!pool_ok) c->pool_cap = (size_t)h_cnt[CNT_POOL] + (size_t)h_cnt[CNT_POOL] / 8 + 1024;      // exact size known now: run again
-            else gathered = true;
-            if (!pairs_ok) pair_cap = (size_t)h_cnt[CNT_PAIRS] + 1024;
+            if (pairs_ok) cand_done = true;
+            else pair_cap = (size_t)h_cnt[CNT_PAIRS] + 1024;
         }
-        n_pairs_total += n_pairs;
+        n_pairs_total += n_pairs; n_cjobs_total += n_cj;
         if (dbg && n_pairs) {
             h_pairs.resize(n_pairs);
             PD_CUDA(c, cudaMemcpy(h_pairs.data(), ca.pairs, (size_t)n_pairs * sizeof(PdPair), cudaMemcpyDeviceToHost));
         }
-
-        // ---- pairs in chunks: the emission of chunk k (stream2) overlaps the EM of chunk k+1 (stream)
-        for (uint32_t p0 = 0; p0 < n_pairs; p0 += CH, ++chunk_no) {
-            const uint32_t np = std::min(CH, n_pairs - p0);
-            const int par = (int)(chunk_no & 1);
-            EmArgs e;
-            if (grow_scratch(c, S_DLX, e.dlx, (size_t)CH * 3 * N)) return c->status;
-            if (grow_scratch(c, S_DLE, e.dle, (size_t)CH * 3 * N)) return c->status;
-            if (grow_scratch(c, S_SHIFTS, e.shifts, (size_t)CH * R)) return c->status;
-            if (grow_scratch(c, S_STATES, e.states, (size_t)CH)) return c->status;
-            // double-buffered: read by stream2 while the next chunk is computed
-            if (chunk_no >= 2) PD_CUDA(c, cudaStreamWaitEvent(st, c->ev[8 + par], 0));          // chunk k-2 has been emitted
-            const size_t had = c->cap_scratch[S_PS0 + par];
-            if (grow_scratch(c, S_PS0 + par, e.ps, (size_t)CH * row)) return c->status;
-            if (grow_scratch(c, S_CALLS0 + par, e.calls, (size_t)CH)) return c->status;
-            if (grow_scratch(c, S_VALID0 + par, e.valid, (size_t)CH + 16)) return c->status;
-            (void)had;
-            e.job_window = j.job_window; e.pairs = ca.pairs; e.pair0 = p0; e.npairs = np; e.job_base = job_base;
-            e.pool_pos = ga.pool_pos; e.pool_dev = ga.pool_dev; e.act_off = ga.act_off; e.act_cnt = ga.act_cnt; e.sstat = ga.sstat; e.dmax = ga.dmax;
-            e.iterations = c->params.iterations; e.min_len = c->params.min_len; e.min_lr = c->params.min_lr;
-            e.min_sample_fraction = c->params.min_sample_fraction; e.somatic = c->params.somatic; e.window_wise = c->params.window_wise;
-            e.anchor = c->grid.anchor;
-            e.dbg = nullptr; e.dbg_window = dbg_window;
-            e.sort_samples = getenv("PD_EM_SORT") ? atoi(getenv("PD_EM_SORT")) : 1;
-            if (dbg) {
-                if (grow_scratch(c, S_DBG, e.dbg, (size_t)CH * 4)) return c->status;
-                PD_CUDA(c, cudaMemsetAsync(e.dbg, 0xFF, (size_t)np * 16, st));
-            }
-            PD_CUDA(c, cudaMemsetAsync(e.valid, 0, np, st));
-            if (pd_launch_em(c, a, e, st, nl)) return c->status;
-            PD_CUDA(c, cudaEventRecord(c->ev[6 + par], st));
-            if (dbg) {
-                std::vector<uint32_t> hd((size_t)np * 4);
-                PD_CUDA(c, cudaMemcpyAsync(hd.data(), e.dbg, (size_t)np * 16, cudaMemcpyDeviceToHost, st));
-                PD_CUDA(c, cudaStreamSynchronize(st));
-                for (uint32_t i = 0; i < np; ++i)
-                    fprintf(stderr, "PD_DEBUG pair window %u L0 %d reason %u len %u it %u supp %u\n", h_jobwin[h_pairs[p0 + i].job],
-                            h_pairs[p0 + i].L0, hd[4 * i], hd[4 * i + 1], hd[4 * i + 2], hd[4 * i + 3]);
-            }
-            // result capacity: upper bound = calls emitted so far (exact once stream2 is drained) + this chunk
-            if ((size_t)(n_pairs_total - n_pairs + p0 + np) > c->cap_res_calls || (size_t)(n_pairs_total - n_pairs + p0 + np) * row > c->cap_res_ps) {
-                PD_CUDA(c, cudaStreamSynchronize(st2));
-                const size_t have = c->res_count[0];
-                if (ensure_results(c, have + np, row, have)) return c->status;
-            }
-            EmitArgs m;
-            m.valid = e.valid; m.calls = e.calls; m.ps = e.ps; m.npairs = np; m.row_words = (uint32_t)row;
-            m.counters = d_counters; m.chunk_base = d_chunk_base;
-            m.out_calls = c->res_calls; m.out_ps = c->res_ps; m.out_count = c->res_count;
-            PD_CUDA(c, cudaStreamWaitEvent(st2, c->ev[6 + par], 0));
-            pd_launch_emit_count(m, st2, nl);
-            pd_launch_emit_rows(m, st2, nl);
-            PD_CUDA(c, cudaGetLastError());
-            PD_CUDA(c, cudaEventRecord(c->ev[8 + par], st2));
+        const bool multi = n_cj > rows_cap;
+        if (multi) {                    // sub-batch borders need the tiles' candidate-job numbering on the host
+            h_cfirst.resize(ntj); h_cmask.resize(ntj); h_tjw.resize(ntj); h_cand_off.resize(nj);
+            PD_CUDA(c, cudaMemcpyAsync(h_cfirst.data(), d_cfirst, (size_t)ntj * 4, cudaMemcpyDeviceToHost, st));
+            PD_CUDA(c, cudaMemcpyAsync(h_cmask.data(), d_cmask, (size_t)ntj * 4, cudaMemcpyDeviceToHost, st));
+            PD_CUDA(c, cudaMemcpyAsync(h_tjw.data(), j.tj_wbase + tj0, (size_t)ntj * 4, cudaMemcpyDeviceToHost, st));
+            PD_CUDA(c, cudaMemcpyAsync(h_cand_off.data(), ca.cand_off, (size_t)nj * 4, cudaMemcpyDeviceToHost, st));
+            PD_CUDA(c, cudaStreamSynchronize(st));
         }
-        // the next batch overwrites the pool / active-set tables that k_final of this batch reads: stream order
-        // on `stream` covers that; the pair list is only read by k_em / k_final as well.
+        // first pair of the first tile whose first candidate job is >= cj
+        auto pair_at = [&](uint32_t cj) -> uint32_t {
+            for (uint32_t t = 0; t < ntj; ++t)           // (sub-batches are few; a linear scan is fine)
+                if (h_cmask[t] && h_cfirst[t] >= cj) return h_cand_off[h_tjw[t] - job_base];
+            return n_pairs;
+        };
+
+        for (uint32_t cj_lo = 0; cj_lo < std::max<uint32_t>(n_cj, 1) && n_pairs; cj_lo += rows_cap) {
+            uint32_t pA = 0, pB = n_pairs;
+            if (multi) {
+                pA = pair_at(cj_lo); pB = pair_at(cj_lo + rows_cap);
+                if (cj_lo > 0) {
+                    for (int attempt = 0; ; ++attempt) {
+                        if (run_gather(cj_lo)) return c->status;
+                        PD_CUDA(c, cudaMemcpyAsync(h_cnt, d_counters, CNT_N * 4, cudaMemcpyDeviceToHost, st));
+                        PD_CUDA(c, cudaStreamSynchronize(st));
+                        if (h_cnt[CNT_POOL] <= c->pool_cap) break;
+                        if (attempt == 2) return pd_fail(c, PD_ERR_CAPACITY, "active read-pair pool overflow");
+                        c->pool_cap = (size_t)h_cnt[CNT_POOL] + (size_t)h_cnt[CNT_POOL] / 8 + 1024;
+                    }
+                }
+            }
+            // ---- pairs in chunks: the emission of chunk k (stream2) overlaps the EM of chunk k+1 (stream)
+            for (uint32_t p0 = pA; p0 < pB; p0 += CH, ++chunk_no) {
+                const uint32_t np = std::min(CH, pB - p0);
+                const int par = (int)(chunk_no & 1);
+                EmArgs e;
+                if (grow_scratch(c, S_DLX, e.dlx, (size_t)CH * 3 * N)) return c->status;
+                if (grow_scratch(c, S_DLE, e.dle, (size_t)CH * 3 * N)) return c->status;
+                if (grow_scratch(c, S_SHIFTS, e.shifts, (size_t)CH * R)) return c->status;
+                if (grow_scratch(c, S_STATES, e.states, (size_t)CH)) return c->status;
+                // double-buffered: read by stream2 while the next chunk is computed
+                if (chunk_no >= 2) PD_CUDA(c, cudaStreamWaitEvent(st, c->ev[8 + par], 0));          // chunk k-2 has been emitted
+                if (grow_scratch(c, S_PS0 + par, e.ps, (size_t)CH * row)) return c->status;
+                if (grow_scratch(c, S_CALLS0 + par, e.calls, (size_t)CH)) return c->status;
+                if (grow_scratch(c, S_VALID0 + par, e.valid, (size_t)CH + 16)) return c->status;
+                e.job_window = j.job_window; e.pairs = ca.pairs; e.pair0 = p0; e.npairs = np; e.job_base = job_base;
+                e.pool_pos = ga.pool_pos; e.pool_dev = ga.pool_dev; e.act_off = ga.act_off; e.act_cnt = ga.act_cnt; e.sstat = ga.sstat; e.dmax = ga.dmax;
+                e.cjob_of = ca.cjob_of; e.cj_base = cj_lo;
+                e.iterations = c->params.iterations; e.min_len = c->params.min_len; e.min_lr = c->params.min_lr;
+                e.min_sample_fraction = c->params.min_sample_fraction; e.somatic = c->params.somatic; e.window_wise = c->params.window_wise;
+                e.anchor = c->grid.anchor;
+                e.dbg = nullptr; e.dbg_window = dbg_window;
+                e.sort_samples = getenv("PD_EM_SORT") ? atoi(getenv("PD_EM_SORT")) : 1;
+                if (dbg) {
+                    if (grow_scratch(c, S_DBG, e.dbg, (size_t)CH * 4)) return c->status;
+                    PD_CUDA(c, cudaMemsetAsync(e.dbg, 0xFF, (size_t)np * 16, st));
+                }
+                PD_CUDA(c, cudaMemsetAsync(e.valid, 0, np, st));
+                if (pd_launch_em(c, a, e, st, nl)) return c->status;
+                PD_CUDA(c, cudaEventRecord(c->ev[6 + par], st));
+                if (dbg) {
+                    std::vector<uint32_t> hd((size_t)np * 4);
+                    PD_CUDA(c, cudaMemcpyAsync(hd.data(), e.dbg, (size_t)np * 16, cudaMemcpyDeviceToHost, st));
+                    PD_CUDA(c, cudaStreamSynchronize(st));
+                    for (uint32_t i = 0; i < np; ++i)
+                        fprintf(stderr, "PD_DEBUG pair window %u L0 %d reason %u len %u it %u supp %u\n", h_jobwin[h_pairs[p0 + i].job],
+                                h_pairs[p0 + i].L0, hd[4 * i], hd[4 * i + 1], hd[4 * i + 2], hd[4 * i + 3]);
+                }
+                // result capacity: upper bound = calls emitted so far (exact once stream2 is drained) + this chunk
+                const size_t upper = (size_t)(n_pairs_total - n_pairs + p0 + np);
+                if (upper > c->cap_res_calls || upper * row > c->cap_res_ps) {
+                    PD_CUDA(c, cudaStreamSynchronize(st2));
+                    const size_t have = c->res_count[0];
+                    if (ensure_results(c, have + np, row, have)) return c->status;
+                }
+                EmitArgs m;
+                m.valid = e.valid; m.calls = e.calls; m.ps = e.ps; m.npairs = np; m.row_words = (uint32_t)row;
+                m.counters = d_counters; m.chunk_base = d_chunk_base;
+                m.out_calls = c->res_calls; m.out_ps = c->res_ps; m.out_count = c->res_count;
+                PD_CUDA(c, cudaStreamWaitEvent(st2, c->ev[6 + par], 0));
+                pd_launch_emit_count(m, st2, nl);
+                pd_launch_emit_rows(m, st2, nl);
+                PD_CUDA(c, cudaGetLastError());
+                PD_CUDA(c, cudaEventRecord(c->ev[8 + par], st2));
+            }
+        }
+        // the next batch overwrites the Q3 / pool / active-set tables that the EM kernels of this batch read: stream
+        // order on `stream` covers that; the pair list is only read by the EM kernels as well.
         tj0 = tj1;
     }
     PD_CUDA(c, cudaEventRecord(c->ev[5], st));

@@ -87,3 +87,15 @@ def test_many_samples(n_samples, contig_len, oracle_lib):
     samples, _ = simulate.simulate_cohort(seed=36, n_samples=n_samples, contig_len=contig_len, n_dels=0, dels=dels)
     stats = compare_scan_with_oracle(samples, oracle_lib)
     assert stats["n_calls"] > 20
+
+
+@pytest.mark.parametrize("env", [{"PD_FORCE_SLOW": "3"}, {"PD_JOB_BATCH": "64", "PD_CJOB_ROWS": "7"}, {"PD_CJOB_ROWS": "1", "PD_EM_CHUNK": "5"},
+                                 {"PD_EM_GENERAL": "1"}])
+@pytest.mark.parametrize("kind", ["basic", "mixedrg", "highcov"])
+def test_scan_generic_paths_and_batching(kind, env, oracle_lib, monkeypatch):
+    """The generic (no shared memory) Q3 / pool paths, small job batches, candidate-job sub-batches and EM chunks, and
+    the general EM kernel give the same calls as the default configuration (all knobs are read per scan)."""
+    samples, params = _cohort(kind)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    compare_scan_with_oracle(samples, oracle_lib, params)
