@@ -121,6 +121,38 @@ int pd_contig_upload(pd_ctx * ctx);
  * window calls. Uploads first if needed. `out` stays valid until the next call on this context. */
 int pd_contig_scan(pd_ctx * ctx, uint64_t first_window, uint64_t n_windows, pd_result * out);
 
+/* Sizes the tile tables of the open contig for at least `n_windows` windows (call between pd_contig_begin and the
+ * upload). Needed by sample-sharded cohorts, whose ranks must cover the COHORT's window range (normally contig length
+ * / 30 + 2) although their own samples' read pairs may end earlier. */
+int pd_contig_reserve_windows(pd_ctx * ctx, uint64_t n_windows);
+
+/* ---- Sample sharding (BASELINE.json: "only the largest-cohort config additionally shards by sample") ----
+ * Every rank creates its context with ITS samples / read groups only (pd_create) and attaches it to the cohort:
+ * the screen threshold, the rank-indexed initial-length thresholds (initialize_deletion_lengths,
+ * genotype_deletion_popdel_call.h:58-86), the sample count of update_allele_frequency (:467-485) and of the
+ * sample-fraction filter become the cohort's; read group 0 of the COHORT drives every reference shift (:401,424-431).
+ * pd_contig_scan is then a COLLECTIVE: all ranks call it with the same window range after pushing their read pairs
+ * (and pd_contig_reserve_windows). It all-gathers the screen's tile flags, the per-window Q3 values and the contig
+ * tail, and exchanges the EM's per-iteration sufficient statistics inside the EM kernels through peer memory
+ * (NVLink). Every rank returns the same calls; per_sample holds the rows of the rank's own samples. */
+typedef struct {
+    uint32_t rank, world;                  /* world = 2..8 */
+    uint32_t n_samples_global;
+    uint32_t n_rg_global;
+    const uint32_t * min_init_global;      /* [n_rg_global] minInitDelLengths of all read groups, cohort order */
+    const uint32_t * samples_per_rank;     /* [world]; rank r holds the samples after those of ranks < r */
+} pd_shard_info;
+
+/* One process per GPU: NCCL (all-gathers) + CUDA IPC (exchange slots). Rank 0 makes the 128-byte id, the launcher
+ * distributes it (e.g. torch.distributed.broadcast), every rank attaches (collective). libnccl.so.2 is dlopen'ed. */
+int pd_shard_unique_id(uint8_t * out128);
+int pd_shard_attach_nccl(pd_ctx * ctx, const pd_shard_info * info, const uint8_t * id128);
+
+/* Several contexts of ONE process (on one GPU or on peer-accessible GPUs): infos[r] describes rank r.
+ * pd_shard_group_scan runs the collective scan with one host thread per context. */
+int pd_shard_attach_group(pd_ctx ** ctxs, uint32_t n, const pd_shard_info * infos);
+int pd_shard_group_scan(pd_ctx ** ctxs, uint32_t n, uint64_t first_window, uint64_t n_windows, pd_result * outs);
+
 /* Number of grid windows the reference would scan for the pushed contig (last scanned window index + 1). */
 int pd_contig_window_count(pd_ctx * ctx, uint64_t * n_windows);
 

@@ -51,9 +51,15 @@ CALL_DTYPE = np.dtype([("initial_length", "<u4"), ("iterations", "<u4"), ("delet
 
 EXPORTS = ["pd_process_histogram", "pd_create", "pd_create_error", "pd_destroy", "pd_last_error", "pd_contig_begin",
            "pd_contig_push", "pd_contig_push_pinned", "pd_contig_upload", "pd_contig_scan", "pd_contig_window_count", "pd_synth_read_group",
-           "pd_debug_host_window_sums"]
+           "pd_debug_host_window_sums", "pd_contig_reserve_windows", "pd_shard_unique_id", "pd_shard_attach_nccl",
+           "pd_shard_attach_group", "pd_shard_group_scan"]
 
 _lib = None
+
+
+class PdShardInfo(C.Structure):
+    _fields_ = [("rank", C.c_uint32), ("world", C.c_uint32), ("n_samples_global", C.c_uint32), ("n_rg_global", C.c_uint32),
+                ("min_init_global", C.POINTER(C.c_uint32)), ("samples_per_rank", C.POINTER(C.c_uint32))]
 
 
 def load_library(path: str = LIB_PATH):
@@ -86,6 +92,11 @@ def load_library(path: str = LIB_PATH):
                                         C.POINTER(C.c_uint32), C.POINTER(C.c_uint8), C.POINTER(C.c_uint32),
                                         C.POINTER(C.c_int32), C.c_uint64]
     lib.pd_debug_host_window_sums.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(C.c_int64)]
+    lib.pd_contig_reserve_windows.argtypes = [C.c_void_p, C.c_uint64]
+    lib.pd_shard_unique_id.argtypes = [C.POINTER(C.c_uint8)]
+    lib.pd_shard_attach_nccl.argtypes = [C.c_void_p, C.POINTER(PdShardInfo), C.POINTER(C.c_uint8)]
+    lib.pd_shard_attach_group.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(PdShardInfo)]
+    lib.pd_shard_group_scan.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(PdResult)]
     _lib = lib
     return lib
 
@@ -253,6 +264,31 @@ class Scanner:
                     ms_h2d=res.ms_h2d, ms_screen=res.ms_screen, ms_genotype=res.ms_genotype, ms_total=res.ms_total,
                     ms_stream=res.ms_stream)
 
+    def reserve_windows(self, n_windows: int):
+        self._check(self.lib.pd_contig_reserve_windows(self.ctx, int(n_windows)))
+
+    def _result_dict(self, res, copy=True) -> dict:
+        n = res.n_calls
+        calls = np.zeros(n, dtype=CALL_DTYPE)
+        per = np.zeros((n, self.n_samples, 13), dtype=np.uint32)
+        if n:
+            C.memmove(calls.ctypes.data, res.calls, n * CALL_DTYPE.itemsize)
+            C.memmove(per.ctypes.data, res.per_sample, per.nbytes)
+        return dict(calls=calls, per_sample=per, n_windows=res.n_windows, n_flagged_windows=res.n_flagged_windows,
+                    n_candidates=res.n_candidates, n_reads=res.n_reads, algorithmic_bytes=res.algorithmic_bytes,
+                    h2d_bytes=res.h2d_bytes, d2h_bytes=res.d2h_bytes, n_kernel_launches=res.n_kernel_launches,
+                    ms_h2d=res.ms_h2d, ms_screen=res.ms_screen, ms_genotype=res.ms_genotype, ms_total=res.ms_total,
+                    ms_stream=res.ms_stream)
+
+    def attach_nccl(self, rank: int, world: int, samples_per_rank, min_init_global, unique_id: bytes):
+        """Sample sharding, one process per GPU (pd_shard_attach_nccl; collective)."""
+        self._shard_keep = (np.ascontiguousarray(min_init_global, dtype=np.uint32), np.ascontiguousarray(samples_per_rank, dtype=np.uint32),
+                            (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id)))
+        mi, spr, uid = self._shard_keep
+        info = PdShardInfo(int(rank), int(world), int(spr.sum()), mi.size, mi.ctypes.data_as(C.POINTER(C.c_uint32)),
+                           spr.ctypes.data_as(C.POINTER(C.c_uint32)))
+        self._check(self.lib.pd_shard_attach_nccl(self.ctx, C.byref(info), uid))
+
     def debug_host_window_sums(self, rg: int, first_window: int, n_windows: int) -> np.ndarray:
         out = np.zeros((int(n_windows), 3), dtype=np.int64)
         self._check(self.lib.pd_debug_host_window_sums(self.ctx, int(rg), int(first_window), int(n_windows),
@@ -307,3 +343,74 @@ def scan_cohort(samples, params: CallParameters, device: int = 0, first_window: 
         return sc.scan(first_window, n_windows), rgs
     finally:
         sc.close()
+
+
+def shard_unique_id() -> bytes:
+    """ncclUniqueId for pd_shard_attach_nccl (make it on rank 0, broadcast it)."""
+    buf = (C.c_uint8 * 128)()
+    rc = load_library().pd_shard_unique_id(buf)
+    if rc != 0:
+        raise ScanError(f"pd_shard_unique_id failed ({rc}): libnccl.so.2 not loadable?")
+    return bytes(buf)
+
+
+def split_samples(n_samples: int, world: int):
+    """Contiguous sample blocks per rank (sizes differ by at most one)."""
+    base, extra = divmod(int(n_samples), int(world))
+    return [base + (1 if r < extra else 0) for r in range(world)]
+
+
+def cohort_headers(samples):
+    return [[dict(name=rg.spec.name, median=rg.median, stddev=rg.stddev, read_length=rg.spec.read_length,
+                  hist_start=rg.hist_start, hist_end=rg.hist_end, hist_counts=rg.hist_counts) for rg in s.read_groups] for s in samples]
+
+
+def scan_cohort_sample_sharded(samples, params: CallParameters, world: int, devices=None, first_window: int = 0, n_windows: int = 0,
+                               contig_len: int = 0):
+    """Sample-sharded scan of an in-memory cohort with `world` contexts of THIS process (pd_shard_attach_group /
+    pd_shard_group_scan; devices[r] = GPU of rank r, default all on GPU 0). Returns the merged result (calls of rank 0,
+    per-sample rows concatenated in cohort order) and the read groups of the whole cohort."""
+    lib = load_library()
+    rgs = read_groups_from_headers(cohort_headers(samples), params)                 # parameters of the WHOLE cohort
+    spr = split_samples(len(samples), world)
+    devices = list(devices) if devices is not None else [0] * world
+    mi = np.array([r.min_init_del_len for r in rgs], dtype=np.uint32)
+    sprs = np.array(spr, dtype=np.uint32)
+    anchor = cohort_anchor(samples)
+    if not contig_len:
+        contig_len = max(int(rg.pos[-1]) + 25000 for s in samples for rg in s.read_groups if rg.pos.size)
+    scanners, s0 = [], 0
+    try:
+        for r in range(world):
+            mine = [g for g in rgs if s0 <= g.sample < s0 + spr[r]]
+            local = [ReadGroup(**{**g.__dict__, "sample": g.sample - s0}) for g in mine]
+            sc = Scanner(params, local, spr[r], devices[r])
+            scanners.append(sc)
+            sc.begin_contig(anchor)
+            sc.reserve_windows((contig_len - anchor) // 30 + 2)
+            gi = 0
+            for s in samples[s0:s0 + spr[r]]:
+                for rg in s.read_groups:
+                    sc.push(gi, rg.pos, rg.dev)
+                    gi += 1
+            s0 += spr[r]
+        ctxs = (C.c_void_p * world)(*[sc.ctx for sc in scanners])
+        infos = (PdShardInfo * world)(*[PdShardInfo(r, world, len(samples), mi.size, mi.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                    sprs.ctypes.data_as(C.POINTER(C.c_uint32))) for r in range(world)])
+        rc = lib.pd_shard_attach_group(ctxs, world, infos)
+        if rc != 0:
+            raise ScanError(f"[{rc}] pd_shard_attach_group: " + "; ".join(lib.pd_last_error(sc.ctx).decode() for sc in scanners))
+        outs = (PdResult * world)()
+        rc = lib.pd_shard_group_scan(ctxs, world, int(first_window), int(n_windows), outs)
+        if rc != 0:
+            raise ScanError(f"[{rc}] pd_shard_group_scan: " + "; ".join(lib.pd_last_error(sc.ctx).decode() for sc in scanners))
+        parts = [sc._result_dict(outs[r]) for r, sc in enumerate(scanners)]
+        for p in parts[1:]:
+            assert np.array_equal(p["calls"], parts[0]["calls"]), "ranks disagree on the calls"
+        merged = dict(parts[0])
+        merged["per_sample"] = np.concatenate([p["per_sample"] for p in parts], axis=1)
+        merged["parts"] = parts
+        return merged, rgs
+    finally:
+        for sc in scanners:
+            sc.close()

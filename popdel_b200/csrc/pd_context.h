@@ -62,6 +62,11 @@ struct PdHostRg {                    // host staging of one read group of the cu
     int64_t prev_seg = -1, prev_E_spill = -1;         // previous non-empty segment
 };
 
+// what the last scanned window of a contig depends on (last_scanned_window): final segment kf of the pushed read
+// pairs, max start position S and max last window E of end set kf, max spill-over last window of segment kf's own pairs
+struct PdTail { int64_t kf = -1, S = -1, E = -1, E_spill = -1; };
+struct PdShard;                      // sample sharding state (pd_shard.cu)
+
 struct PdRawRg { const uint32_t * pos = nullptr; const int32_t * dev = nullptr; uint64_t n = 0; };   // pd_contig_push_pinned
 
 struct pd_ctx {
@@ -89,6 +94,8 @@ struct pd_ctx {
     uint64_t total_words = 0, total_longs = 0;
     uint32_t NT = 0;
     uint64_t n_windows_total = 0;    // reference's last scanned window + 1
+    PdTail tail;                     // inputs of n_windows_total (combined over the ranks of a sample-sharded cohort)
+    uint64_t min_windows = 0;        // pd_contig_reserve_windows: the tile tables cover at least this many windows
     uint64_t n_reads = 0;
 
     // device
@@ -100,6 +107,8 @@ struct pd_ctx {
     PdRgConst * d_rgc = nullptr;
     uint32_t * d_sample_rg = nullptr;
     PdTab * d_tab = nullptr;
+    uint32_t * d_min_init = nullptr; // [R] minInitDelLengths (of the whole cohort when sharded by sample)
+    PdShard * shard = nullptr;
     // scan scratch (grown on demand)
     void * d_scratch[40] = {}; size_t cap_scratch[40] = {};
     void * d_pack[8] = {}; size_t cap_pack[8] = {};          // device packer scratch (raw arrays, tile firsts, ...)
@@ -119,6 +128,8 @@ struct pd_ctx {
 int pd_fail(pd_ctx * c, int status, const std::string & msg);
 int pd_pack_contig(pd_ctx * c);                    // finalises the offset tables of the packed image
 int pd_pack_on_device(pd_ctx * c);                // pd_pack.cu: 0 ok, 1 = use the host packer, <0 error
-int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result * out);   // pd_kernels.cu
+int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result * out);   // pd_scan.cu
+uint64_t pd_tail_windows(const PdTail & t, uint32_t window_buffer);
+void pd_shard_release(pd_ctx * c);                // pd_shard.cu
 
 #endif

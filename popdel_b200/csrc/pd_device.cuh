@@ -15,6 +15,7 @@
             return pd_fail((c), PD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
+#define PD_MAX_WORLD 8                              /* ranks of a sample-sharded cohort */
 constexpr uint32_t PD_FULL = 0xFFFFFFFFu;
 constexpr uint32_t PD_GRAN = 1024;                  // words per warp in k_stream; granule of the word -> tile index
 constexpr int PD_CAND_INLINE = 6;                   // candidate lengths kept inline per window job
@@ -64,7 +65,10 @@ struct GatherArgs {
     uint32_t debug_flags;               // tests: bit 0 = generic path in k_tile_q3, bit 1 = generic path in k_tile_gather
 };
 struct CandArgs {
-    const int32_t * q3; const uint8_t * sstat; uint32_t njobs, job_base;
+    // Q3 / state of every (window job, sample): nparts blocks [njobs][part_n[p]] (one per rank when sharded by sample)
+    uint32_t nparts; const int32_t * q3[PD_MAX_WORLD]; const uint8_t * sstat[PD_MAX_WORLD]; uint32_t part_n[PD_MAX_WORLD];
+    const uint32_t * min_init;          // [read groups of the whole cohort] minInitDelLengths, indexed by RANK (quirk)
+    uint32_t njobs, job_base;
     uint32_t * cand_cnt;                // [njobs]
     int32_t * cand_inline;              // [njobs][PD_CAND_INLINE]
     uint32_t * cand_off;                // [njobs] exclusive scan of cand_cnt
@@ -77,6 +81,23 @@ void pd_launch_q3(const PdDev & a, const GatherArgs & g, cudaStream_t st, uint64
 void pd_launch_cmask(const GatherArgs & g, const CandArgs & ca, uint32_t * tj_cmask, uint32_t * tj_cfirst, cudaStream_t st, uint64_t * launches);
 void pd_launch_gather(const PdDev & a, const GatherArgs & g, cudaStream_t st, uint64_t * launches);
 int  pd_launch_candidates(pd_ctx * c, const PdDev & a, const CandArgs & ca, cudaStream_t st, uint64_t * launches);
+
+// ---- sample sharding (pd_shard.cu): cross-rank exchange inside the EM kernels --------------------------------------
+// One slot = the four 64-bit values one rank contributes to one reduction of one (window, length) pair. Every rank
+// owns an array [2 launches][pairs][2 reductions][world ranks]; rank r WRITES slot [..][r] of every rank's array
+// (peer memory over NVLink, or plain device memory for in-process groups) and POLLS its own array.
+struct XrSlot { unsigned long long v[4]; unsigned long long seq; unsigned long long pad[3]; };
+struct XrArgs {
+    uint32_t world, rank;               // world <= 1: not sharded
+    XrSlot * peer[PD_MAX_WORLD];        // rank r's slot array
+    uint32_t pairs_cap;                 // pairs per launch the arrays hold
+    unsigned long long epoch;           // launch number, identical on every rank (sequence numbers = epoch << 16 | k)
+    uint32_t * ticket;                  // pair numbering of the persistent launch
+    uint32_t * err;                     // set when a peer did not answer in time (the scan then fails)
+    uint32_t n_global;                  // samples of the whole cohort
+    uint32_t owns_rg0;                  // this rank holds read group 0 of the cohort (its posterior drives every reference shift)
+    uint32_t grid_cap;                  // blocks of the persistent launch
+};
 
 // ---- EM + final pass (pd_em.cu) -------------------------------------------------------------------------------
 struct EmArgs {
@@ -95,6 +116,7 @@ struct EmArgs {
     uint32_t * dbg;          // optional [npairs][4]: reason, len, iterations, supp (PD_DEBUG)
     int dbg_window;          // device printf of the EM trajectory of this window (PD_DEBUG_WINDOW), -1 = off
     int sort_samples;        // fused kernel: order the samples by largest deviation and skip unchanged likelihood passes
+    XrArgs xr;               // sample sharding: cross-rank reductions (world <= 1: none)
 };
 struct EmitArgs {
     const uint8_t * valid; const pd_call * calls; const uint32_t * ps; uint32_t npairs, row_words;
@@ -103,6 +125,7 @@ struct EmitArgs {
     pd_call * out_calls; uint32_t * out_ps; uint32_t * out_count;   // mapped page-locked host memory
 };
 int  pd_launch_em(pd_ctx * c, const PdDev & a, const EmArgs & e, cudaStream_t st, uint64_t * launches);
+int  pd_em_preload_xr(pd_ctx * c);
 void pd_launch_emit_count(const EmitArgs & m, cudaStream_t st, uint64_t * launches);
 void pd_launch_emit_rows(const EmitArgs & m, cudaStream_t st, uint64_t * launches);
 

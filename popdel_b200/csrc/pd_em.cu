@@ -11,6 +11,7 @@
 //   k_emit_*  ordered compaction of the emitted calls and their per-sample rows straight into mapped host memory.
 // Floating point: double. The two places where the reference's x87 long double is observable are emulated
 // (finish_triple): exp() underflow at -11399.5 and the ln2 - fl64(ln2) residue of read pairs with ref == del.
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
@@ -26,7 +27,7 @@ namespace {
 template <int LPS, int SLOTS>
 __device__ __forceinline__ double compute_dl(const PdDev & a, const EmArgs & e, EmShared & sh, const uint32_t * cnt, const uint32_t * off,
                                              double * dlx, double * dle, const int32_t * shifts, bool zero_shifts, int L,
-                                             double * cache_r, const int32_t * cache_d, bool fill_cache, const Gt gtf)
+                                             double * cache_r, const int32_t * cache_d, bool fill_cache, const Gt gtf, const bool own0)
 {
     double fs = 0;
     const int tid = threadIdx.x, T = blockDim.x, sub = tid % LPS, grp = tid / LPS, ngrp = T / LPS;
@@ -39,7 +40,7 @@ __device__ __forceinline__ double compute_dl(const PdDev & a, const EmArgs & e, 
             const RgLite k = rg_lite(a.rgc + g);
             const uint32_t n = cnt[g];
             if (n >= k.max_load) {
-                if (g == 0 && sub == 0) sh.rgw[0] = sh.rgw[1] = sh.rgw[2] = 0;      // Triple(0,0,0) in the reference
+                if (g == 0 && own0 && sub == 0) sh.rgw[0] = sh.rgw[1] = sh.rgw[2] = 0;      // Triple(0,0,0) in the reference
                 continue;
             }
             const int shift = zero_shifts ? 0 : shifts[g];
@@ -65,7 +66,7 @@ __device__ __forceinline__ double compute_dl(const PdDev & a, const EmArgs & e, 
                 if (fill_cache && slot < SLOTS) cache_r[slot * T + tid] = r;
                 l0 += rr.b; l1 += g1; l2 += g2;
             }
-            if (g == 0) {                                                // read group 0 = first read group of sample 0
+            if (g == 0 && own0) {                                        // read group 0 = first read group of sample 0 of the cohort
                 const double w0 = group_sum<LPS>(l0, gmask), w1 = group_sum<LPS>(l1, gmask), w2 = group_sum<LPS>(l2, gmask);
                 if (sub == 0) { const double m = fmax(fmax(w0, w1), w2); sh.rgw[0] = exp(w0 - m); sh.rgw[1] = exp(w1 - m); sh.rgw[2] = exp(w2 - m); }
             }
@@ -91,7 +92,8 @@ __device__ __forceinline__ double compute_dl(const PdDev & a, const EmArgs & e, 
 }
 
 // deletion_likelihood_ratio :490-508 (block-wide; result on all threads)
-__device__ __forceinline__ double block_lr(const PdDev & a, EmShared & sh, const double * dlx, const double * dle, const Gt gt, int & par)
+template <bool XR>
+__device__ __forceinline__ double block_lr(const PdDev & a, const EmArgs & e, XrBlock & xb, EmShared & sh, const double * dlx, const double * dle, const Gt gt, int & par)
 {
     double del = 0, nodel = 0;
     for (uint32_t s = threadIdx.x; s < a.N; s += blockDim.x) {
@@ -102,17 +104,16 @@ __device__ __forceinline__ double block_lr(const PdDev & a, EmShared & sh, const
         nodel += dlx[3 * s];
     }
     block_sum2(del, nodel, sh.red, par);
+    if (XR) xr_sum2(e.xr, xb, sh, del, nodel);
     return del - nodel;
 }
 
-template <int LPS, int SLOTS, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) k_em(PdDev a, EmArgs e)
+template <int LPS, int SLOTS, bool XR>
+__device__ __forceinline__ void em_body(const PdDev & a, const EmArgs & e, EmShared & sh, double * cache_r, const uint32_t bid)
 {
-    __shared__ EmShared sh;
-    extern __shared__ double cache_r[];                 // [SLOTS][T] weights, then [SLOTS][T] deviations (int32)
     const int tid = threadIdx.x, T = blockDim.x, sub = tid % LPS, grp = tid / LPS, ngrp = T / LPS;
     int32_t * cache_d = reinterpret_cast<int32_t *>(cache_r + (size_t)SLOTS * T);
-    const uint32_t pi = e.pair0 + blockIdx.x;
+    const uint32_t pi = e.pair0 + bid;
     const PdPair pr = e.pairs[pi];
     const uint32_t job = pr.job - e.job_base;
     const int L0 = pr.L0;
@@ -120,11 +121,14 @@ __global__ void __launch_bounds__(MAXT, MINB) k_em(PdDev a, EmArgs e)
     const uint32_t cj = e.cjob_of[job] - e.cj_base;
     const uint32_t * cnt = e.act_cnt + (size_t)cj * a.R;
     const uint32_t * off = e.act_off + (size_t)cj * a.R;
-    double * dlx = e.dlx + (size_t)blockIdx.x * 3 * a.N;
-    double * dle = e.dle + (size_t)blockIdx.x * 3 * a.N;
-    int32_t * shifts = e.shifts + (size_t)blockIdx.x * a.R;
+    double * dlx = e.dlx + (size_t)bid * 3 * a.N;
+    double * dle = e.dle + (size_t)bid * 3 * a.N;
+    int32_t * shifts = e.shifts + (size_t)bid * a.R;
     const uint32_t gmask = group_mask<LPS>();
     int par = 0;
+    XrBlock xb{bid, e.xr.epoch << 16};
+    const bool own0 = !XR || e.xr.owns_rg0;             // read group 0 of the cohort lives on this rank
+    const double n_cohort = XR ? (double)e.xr.n_global : (double)a.N;
     // loop state, identical on every thread
     uint32_t len = (uint32_t)L0, it = 0;
     double freq = 0;
@@ -133,10 +137,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_em(PdDev a, EmArgs e)
         if (tid == 0) {
             EmState st; st.len = len; st.it = it; st.alive = alive; st.pad = 0; st.freq = freq;
             st.gt[0] = gt.a; st.gt[1] = gt.b; st.gt[2] = gt.c;
-            e.states[blockIdx.x] = st;
+            e.states[bid] = st;
             if (!alive) {
-                e.valid[blockIdx.x] = 0;
-                if (e.dbg) { e.dbg[4 * blockIdx.x] = reason; e.dbg[4 * blockIdx.x + 1] = len; e.dbg[4 * blockIdx.x + 2] = it; }
+                e.valid[bid] = 0;
+                if (e.dbg) { e.dbg[4 * bid] = reason; e.dbg[4 * bid + 1] = len; e.dbg[4 * bid + 2] = it; }
             }
         }
     };
@@ -164,12 +168,19 @@ __global__ void __launch_bounds__(MAXT, MINB) k_em(PdDev a, EmArgs e)
                 }
             }
         block_sum2u(c, t, sh.redu);
+        if (XR) xr_sum2u(e.xr, xb, sh, c, t);
         freq = t == 0 ? 0.0 : (double)c / (double)t;
         gt = gt_prior(freq, e.somatic);
     }
     if (freq == 0) { finish(0, 1); return; }
-    compute_dl<LPS, SLOTS>(a, e, sh, cnt, off, dlx, dle, shifts, true, L0, cache_r, cache_d, true, gt);
+    compute_dl<LPS, SLOTS>(a, e, sh, cnt, off, dlx, dle, shifts, true, L0, cache_r, cache_d, true, gt, own0);
     __syncthreads();
+    if (XR) {                                           // read group 0's likelihood triple comes from its owner
+        double z = 0, r0 = own0 ? sh.rgw[0] : 0.0, r1 = own0 ? sh.rgw[1] : 0.0, r2 = own0 ? sh.rgw[2] : 0.0;
+        xr_sum4(e.xr, xb, sh, z, r0, r1, r2);
+        if (tid == 0) { sh.rgw[0] = r0; sh.rgw[1] = r1; sh.rgw[2] = r2; }
+        __syncthreads();
+    }
 
     // ---- EM loop :598-660
     uint32_t prevLen = len; double prevFreq = freq;
@@ -216,6 +227,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_em(PdDev a, EmArgs e)
             }
         }
         block_sum2(sumDel, wDel, sh.red, par);
+        if (XR) xr_sum2(e.xr, xb, sh, sumDel, wDel);
         if (tid == 0) {                                   // visited[prevLen] = prevFreq (:600); read after the next barrier
             int f = -1;
             for (int i = 0; i < sh.nvisited; ++i) if (sh.visited_len[i] == (int)prevLen) f = i;
@@ -227,20 +239,26 @@ __global__ void __launch_bounds__(MAXT, MINB) k_em(PdDev a, EmArgs e)
         if (sumDel == 0) len = 0;
         else { const double nl = wDel / sumDel; len = nl < 0 ? 0u : (uint32_t)round(nl); }
         // data likelihoods at the new length + update_allele_frequency :467-485 (priors of the previous iteration)
-        double fs = compute_dl<LPS, SLOTS>(a, e, sh, cnt, off, dlx, dle, shifts, false, (int)len, cache_r, cache_d, true, gt), dummy = 0;
+        double fs = compute_dl<LPS, SLOTS>(a, e, sh, cnt, off, dlx, dle, shifts, false, (int)len, cache_r, cache_d, true, gt, own0), dummy = 0;
         block_sum2(fs, dummy, sh.red, par);
-        freq = fs / 2.0 / a.N;
+        if (XR) {
+            double r0 = own0 ? sh.rgw[0] : 0.0, r1 = own0 ? sh.rgw[1] : 0.0, r2 = own0 ? sh.rgw[2] : 0.0;
+            xr_sum4(e.xr, xb, sh, fs, r0, r1, r2);
+            if (tid == 0) { sh.rgw[0] = r0; sh.rgw[1] = r1; sh.rgw[2] = r2; }
+            __syncthreads();
+        }
+        freq = fs / 2.0 / n_cohort;
         if (freq == 0) { stop = 1; break; }
         gt = gt_prior(freq, e.somatic);
         for (int i = 0; i < sh.nvisited; ++i)
             if (sh.visited_len[i] == (int)len && fabs(sh.visited_freq[i] - freq) <= 0.0001) stop = 2;
         if (stop == 2) {
             // convergence :632-658: compare with the previous estimate evaluated with the initial (zero) shifts
-            const double lr = block_lr(a, sh, dlx, dle, gt, par);
+            const double lr = block_lr<XR>(a, e, xb, sh, dlx, dle, gt, par);
             const Gt prevGt = gt_prior(prevFreq, e.somatic);          // the priors the previous estimate was made with
-            compute_dl<LPS, SLOTS>(a, e, sh, cnt, off, dlx, dle, shifts, true, (int)prevLen, cache_r, cache_d, false, prevGt);
+            compute_dl<LPS, SLOTS>(a, e, sh, cnt, off, dlx, dle, shifts, true, (int)prevLen, cache_r, cache_d, false, prevGt, own0);
             __syncthreads();
-            const double plr = block_lr(a, sh, dlx, dle, prevGt, par);
+            const double plr = block_lr<XR>(a, e, xb, sh, dlx, dle, prevGt, par);
             if (plr > lr) {
                 len = prevLen; freq = prevFreq;
                 for (uint32_t g = tid; g < a.R; g += T) shifts[g] = 0;
@@ -252,23 +270,54 @@ __global__ void __launch_bounds__(MAXT, MINB) k_em(PdDev a, EmArgs e)
     finish(alive ? 1u : 0u, 2);
 }
 
+template <int LPS, int SLOTS, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_em(PdDev a, EmArgs e)
+{
+    __shared__ EmShared sh;
+    extern __shared__ double cache_r[];                 // [SLOTS][T] weights, then [SLOTS][T] deviations (int32)
+    em_body<LPS, SLOTS, false>(a, e, sh, cache_r, blockIdx.x);
+}
+// sample-sharded cohort: persistent blocks take the pairs in ticket order, so that the pairs in flight are the same
+// (lowest unfinished) ones on every rank and the in-kernel exchanges cannot wait for a block that is not resident
+template <int LPS, int SLOTS, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_em_xr(PdDev a, EmArgs e)
+{
+    __shared__ EmShared sh;
+    __shared__ uint32_t s_bid;
+    extern __shared__ double cache_r[];
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_bid = atomicAdd(e.xr.ticket, 1u);
+        __syncthreads();
+        const uint32_t bid = s_bid;
+        if (bid >= e.npairs) return;
+        em_body<LPS, SLOTS, true>(a, e, sh, cache_r, bid);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // final pass: one block per (window, initial length) that survived the EM
 // ------------------------------------------------------------------------------------------------------------------
 constexpr uint32_t SUPP_CAP = 1536;                    // supporting read pairs kept in shared memory for the percentiles
 
-template <int LPS, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) k_final(PdDev a, EmArgs e)
+template <int LPS, bool XR>
+__device__ __forceinline__ void final_body(const PdDev & a, const EmArgs & e, EmShared & sh, uint32_t * s_first, uint32_t * s_last, uint32_t & s_nsupp,
+                                           const uint32_t bid)
 {
-    __shared__ EmShared sh;
-    __shared__ uint32_t s_first[SUPP_CAP], s_last[SUPP_CAP];
-    __shared__ uint32_t s_nsupp;
-    const EmState stt = e.states[blockIdx.x];
+    const EmState stt = e.states[bid];
+    XrBlock xb{bid, e.xr.epoch << 16};
+    if (XR && bid == 0) {
+        // one exchange per launch even when no pair survived the EM: a rank that has passed this launch then knows that
+        // every peer has left the previous one, whose slots the next launch reuses
+        unsigned long long z0 = 0, z1 = 0;
+        xr_sum2u(e.xr, xb, sh, z0, z1);
+    }
     if (!stt.alive) return;
+    const double n_cohort = XR ? (double)e.xr.n_global : (double)a.N;
     const int tid = threadIdx.x, T = blockDim.x, sub = tid % LPS, grp = tid / LPS, ngrp = T / LPS;
     const uint32_t gmask = group_mask<LPS>();
     if (tid == 0) s_nsupp = 0;
-    const uint32_t pi = e.pair0 + blockIdx.x;
+    const uint32_t pi = e.pair0 + bid;
     const PdPair pr = e.pairs[pi];
     const uint32_t job = pr.job - e.job_base;
     const uint32_t L0 = (uint32_t)pr.L0;
@@ -277,18 +326,18 @@ __global__ void __launch_bounds__(MAXT, MINB) k_final(PdDev a, EmArgs e)
     const uint32_t * cnt = e.act_cnt + (size_t)cj * a.R;
     const uint32_t * off = e.act_off + (size_t)cj * a.R;
     const uint8_t * sstat = e.sstat + (size_t)job * a.N;
-    double * dlx = e.dlx + (size_t)blockIdx.x * 3 * a.N;
-    double * dle = e.dle + (size_t)blockIdx.x * 3 * a.N;
-    const int32_t * shifts = e.shifts + (size_t)blockIdx.x * a.R;
-    uint32_t * ps = e.ps + (size_t)blockIdx.x * 13 * a.N;
+    double * dlx = e.dlx + (size_t)bid * 3 * a.N;
+    double * dle = e.dle + (size_t)bid * 3 * a.N;
+    const int32_t * shifts = e.shifts + (size_t)bid * a.R;
+    uint32_t * ps = e.ps + (size_t)bid * 13 * a.N;
     const int len = (int)stt.len;
     const Gt gt = Gt{stt.gt[0], stt.gt[1], stt.gt[2]};
     int par = 0;
     __syncthreads();
     auto reject = [&](uint32_t reason) {
         if (tid == 0) {
-            e.valid[blockIdx.x] = 0;
-            if (e.dbg) { e.dbg[4 * blockIdx.x] = reason; e.dbg[4 * blockIdx.x + 1] = stt.len; e.dbg[4 * blockIdx.x + 2] = stt.it; }
+            e.valid[bid] = 0;
+            if (e.dbg) { e.dbg[4 * bid] = reason; e.dbg[4 * bid + 1] = stt.len; e.dbg[4 * bid + 2] = stt.it; }
         }
     };
     // ---- final pass :665-727 (compute_data_likelihoods final overload :255-337)
@@ -383,12 +432,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k_final(PdDev a, EmArgs e)
     }
     __syncthreads();
     block_sum2u(supp, ndata, sh.redu);
+    if (XR) xr_sum2u(e.xr, xb, sh, supp, ndata);
     if (supp == 0) { reject(3); return; }
     // percentiles of the supporting starts (80th) and ends (20th): getSuppFirstLast :514-529, by value bisection
     uint32_t sF, sL;
     const unsigned long long kF = (unsigned long long)round((double)(supp - 1) * 0.8);
     const unsigned long long kL = (unsigned long long)round((double)(supp - 1) * (1 - 0.8));
-    if (supp <= SUPP_CAP) {
+    if (!XR && supp <= SUPP_CAP) {
         // the usual case: the supporting read pairs sit in shared memory and one warp bisects without block barriers
         if (tid < 32) {
             const uint32_t n = (uint32_t)supp;
@@ -423,6 +473,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_final(PdDev a, EmArgs e)
         __syncthreads();
         for (int i = 0; i < nw; ++i) { smin = min(smin, r32[4 * i]); smax = max(smax, r32[4 * i + 1]); lmin = min(lmin, r32[4 * i + 2]); lmax = max(lmax, r32[4 * i + 3]); }
         __syncthreads();
+        if (XR) xr_minmax(e.xr, xb, sh, smin, smax, lmin, lmax);
         uint32_t loF = smin, hiF = smax, loL = lmin, hiL = lmax;
         while (loF < hiF || loL < hiL) {
             const uint32_t midF = loF + (hiF - loF) / 2, midL = loL + (hiL - loL) / 2;
@@ -448,29 +499,54 @@ __global__ void __launch_bounds__(MAXT, MINB) k_final(PdDev a, EmArgs e)
                 }
             }
             block_sum2u(cF, cL, sh.redu);
+            if (XR) xr_sum2u(e.xr, xb, sh, cF, cL);
             if (loF < hiF) { if (cF >= kF + 1) hiF = midF; else loF = midF + 1; }
             if (loL < hiL) { if (cL >= kL + 1) hiL = midL; else loL = midL + 1; }
         }
         sF = loF; sL = loL;
     }
     if (sF == 0 && sL == 0) { reject(4); return; }
-    const double lr = block_lr(a, sh, dlx, dle, gt, par);
+    const double lr = block_lr<XR>(a, e, xb, sh, dlx, dle, gt, par);
     if (tid == 0) {
         const bool ok = lr >= e.min_lr;
-        e.valid[blockIdx.x] = ok ? 1 : 0;
-        if (e.dbg) { e.dbg[4 * blockIdx.x] = ok ? 0 : 5; e.dbg[4 * blockIdx.x + 1] = stt.len; e.dbg[4 * blockIdx.x + 2] = stt.it; e.dbg[4 * blockIdx.x + 3] = (uint32_t)supp; }
+        e.valid[bid] = ok ? 1 : 0;
+        if (e.dbg) { e.dbg[4 * bid] = ok ? 0 : 5; e.dbg[4 * bid + 1] = stt.len; e.dbg[4 * bid + 2] = stt.it; e.dbg[4 * bid + 3] = (uint32_t)supp; }
         if (ok) {
             pd_call c;
             c.initial_length = L0; c.iterations = stt.it; c.deletion_length = stt.len;
-            c.filter = ((double)ndata / a.N >= e.min_sample_fraction) ? 0u : 4u;
+            c.filter = ((double)ndata / n_cohort >= e.min_sample_fraction) ? 0u : 4u;
             c.lr = lr; c.frequency = stt.freq;
             const uint32_t cur = e.anchor + w * PD_WIN;
             c.window_position = cur - 1;
             c.position = e.window_wise ? cur - 1 : sF;
             c.end_position = e.window_wise ? 0u : sL;
             c.segment = (uint32_t)(((uint64_t)w * PD_WIN) / a.window_buffer);
-            e.calls[blockIdx.x] = c;
+            e.calls[bid] = c;
         }
+    }
+}
+
+template <int LPS, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_final(PdDev a, EmArgs e)
+{
+    __shared__ EmShared sh;
+    __shared__ uint32_t s_first[SUPP_CAP], s_last[SUPP_CAP];
+    __shared__ uint32_t s_nsupp;
+    final_body<LPS, false>(a, e, sh, s_first, s_last, s_nsupp, blockIdx.x);
+}
+template <int LPS, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_final_xr(PdDev a, EmArgs e)
+{
+    __shared__ EmShared sh;
+    __shared__ uint32_t s_first[SUPP_CAP], s_last[SUPP_CAP];
+    __shared__ uint32_t s_nsupp, s_bid;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_bid = atomicAdd(e.xr.ticket + 1, 1u);
+        __syncthreads();
+        const uint32_t bid = s_bid;
+        if (bid >= e.npairs) return;
+        final_body<LPS, true>(a, e, sh, s_first, s_last, s_nsupp, bid);
     }
 }
 
@@ -894,6 +970,23 @@ cudaError_t launch_em_t(const PdDev & a, const EmArgs & e, uint32_t T, cudaStrea
     return cudaGetLastError();
 }
 
+template <int LPS, int SLOTS, int MAXT, int MINB>
+cudaError_t launch_xr_t(const PdDev & a, const EmArgs & e, uint32_t T, cudaStream_t st)
+{
+    const size_t smem = (size_t)SLOTS * T * (sizeof(double) + sizeof(int32_t));
+    cudaError_t err = cudaFuncSetAttribute(k_em_xr<LPS, SLOTS, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    err = cudaMemsetAsync(e.xr.ticket, 0, 8, st);
+    if (err != cudaSuccess) return err;
+    const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(e.npairs, e.xr.grid_cap));
+    EmArgs e2 = e;
+    e2.xr.epoch = 2 * e.xr.epoch;
+    k_em_xr<LPS, SLOTS, MAXT, MINB><<<grid, T, smem, st>>>(a, e2);
+    e2.xr.epoch = 2 * e.xr.epoch + 1;
+    k_final_xr<LPS, MAXT, MINB><<<grid, T, 0, st>>>(a, e2);
+    return cudaGetLastError();
+}
+
 template <int LPS, int SLOTS, bool PREF, int MAXT, int MINB>
 cudaError_t launch_one_t(const PdDev & a, const EmArgs & e, uint32_t T, cudaStream_t st)
 {
@@ -904,8 +997,32 @@ cudaError_t launch_one_t(const PdDev & a, const EmArgs & e, uint32_t T, cudaStre
 
 }  // namespace
 
+// CUDA loads kernels lazily, and loading may wait for running kernels: a sharded rank whose first k_final_xr launch had
+// to load the kernel while its k_em_xr blocks spin on a peer (whose launch sits behind the same lock) would never
+// return. Load the cross-rank kernels up front (pd_shard_attach_*).
+int pd_em_preload_xr(pd_ctx * c)
+{
+    cudaFuncAttributes fa;
+    PD_CUDA(c, cudaFuncGetAttributes(&fa, k_em_xr<4, 8, 512, 2>));
+    PD_CUDA(c, cudaFuncGetAttributes(&fa, k_em_xr<2, 16, 512, 2>));
+    PD_CUDA(c, cudaFuncGetAttributes(&fa, k_final_xr<4, 512, 2>));
+    PD_CUDA(c, cudaFuncGetAttributes(&fa, k_final_xr<2, 512, 2>));
+    PD_CUDA(c, cudaFuncGetAttributes(&fa, k_emit_count));
+    PD_CUDA(c, cudaFuncGetAttributes(&fa, k_emit_rows));
+    return 0;
+}
+
 int pd_launch_em(pd_ctx * c, const PdDev & a, const EmArgs & e, cudaStream_t st, uint64_t * launches)
 {
+    if (e.xr.world > 1) {
+        // sample-sharded cohort: general kernels with in-kernel cross-rank reductions, persistent blocks (2 per SM at most)
+        const uint32_t lpsx = a.N <= 112 ? 4 : (a.N <= 224 ? 2 : 4);
+        const uint32_t Tx = std::min<uint32_t>(512, ((a.N * lpsx + 31) / 32) * 32);
+        const cudaError_t errx = lpsx == 4 ? launch_xr_t<4, 8, 512, 2>(a, e, Tx, st) : launch_xr_t<2, 16, 512, 2>(a, e, Tx, st);
+        if (errx != cudaSuccess) return pd_fail(c, PD_ERR_CUDA, std::string("k_em_xr/k_final_xr launch: ") + cudaGetErrorString(errx));
+        *launches += 2;
+        return 0;
+    }
     // one read group per sample and the cohort fits one block: fused EM + final pass with per-sample state in registers
     if (a.R == a.N && a.N <= 256 && !getenv("PD_EM_GENERAL")) {
         uint32_t lps1 = a.N <= 256 ? 1 : 2;

@@ -40,6 +40,7 @@ struct EmShared {
     double rgw[3];                     // read group 0's likelihood triple, exp domain (quirk: drives all reference shifts)
     int visited_len[64]; double visited_freq[64]; int nvisited;
     uint32_t sel[2];                   // supporting start / end percentiles (k_final)
+    unsigned long long xr_in[PD_MAX_WORLD][4];    // values received from every rank (sample sharding)
 };
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -73,6 +74,91 @@ __device__ __forceinline__ void block_sum2u(unsigned long long & a, unsigned lon
     unsigned long long sa = 0, sb = 0;
     for (int i = 0; i < nw; ++i) { sa += red[2 * i]; sb += red[2 * i + 1]; }
     a = sa; b = sb;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Cross-rank reductions of the sample-sharded scan: every rank runs the SAME (window, length) pair in a
+// co-resident block; the per-pair sufficient statistics are exchanged through peer memory inside the kernel -- rank r
+// stores its four values and a sequence number into slot [pair][reduction parity][r] of EVERY rank's array (NVLink
+// stores, release at system scope) and polls its own array (acquire) -- and are then combined in rank order, so every
+// rank holds bit-identical results and takes identical branches. `v*` must be block-uniform on entry.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long * p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long * p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long * p, unsigned long long v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long * p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct XrBlock { uint32_t pair; unsigned long long seq; };          // per block: pair slot and reduction counter
+
+// exchanges four raw 64-bit values; afterwards sh.xr_in[r][i] = value i of rank r (all threads may read it)
+__device__ __forceinline__ void xr_exchange(const XrArgs & x, XrBlock & xb, EmShared & sh, unsigned long long v0, unsigned long long v1,
+                                            unsigned long long v2, unsigned long long v3)
+{
+    ++xb.seq;
+    __syncthreads();                                              // earlier readers of sh.xr_in are done
+    const uint32_t tid = threadIdx.x;
+    if (tid < x.world) {
+        const size_t base = ((((size_t)(x.epoch & 1) * x.pairs_cap + xb.pair) * 2 + (xb.seq & 1)) * x.world);
+        XrSlot * dst = x.peer[tid] + base + x.rank;
+        st_relaxed_sys(&dst->v[0], v0); st_relaxed_sys(&dst->v[1], v1); st_relaxed_sys(&dst->v[2], v2); st_relaxed_sys(&dst->v[3], v3);
+        st_release_sys(&dst->seq, xb.seq);
+        const XrSlot * src = x.peer[x.rank] + base + tid;
+        const long long t0 = clock64();
+        bool ok = true;
+        while (ld_acquire_sys(&src->seq) != xb.seq) {
+            if (*(volatile uint32_t *)x.err) { ok = false; break; }
+            if (clock64() - t0 > 6000000000ll) { atomicExch(x.err, 1u); ok = false; break; }     // ~3 s: a peer is gone
+            __nanosleep(40);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sh.xr_in[tid][i] = ok ? ld_relaxed_sys(&src->v[i]) : 0ull;
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void xr_sum4(const XrArgs & x, XrBlock & xb, EmShared & sh, double & a, double & b, double & c, double & d)
+{
+    xr_exchange(x, xb, sh, __double_as_longlong(a), __double_as_longlong(b), __double_as_longlong(c), __double_as_longlong(d));
+    a = b = c = d = 0;
+    for (uint32_t r = 0; r < x.world; ++r) {
+        a += __longlong_as_double(sh.xr_in[r][0]); b += __longlong_as_double(sh.xr_in[r][1]);
+        c += __longlong_as_double(sh.xr_in[r][2]); d += __longlong_as_double(sh.xr_in[r][3]);
+    }
+}
+__device__ __forceinline__ void xr_sum2(const XrArgs & x, XrBlock & xb, EmShared & sh, double & a, double & b)
+{
+    double c = 0, d = 0;
+    xr_sum4(x, xb, sh, a, b, c, d);
+}
+__device__ __forceinline__ void xr_sum2u(const XrArgs & x, XrBlock & xb, EmShared & sh, unsigned long long & a, unsigned long long & b)
+{
+    xr_exchange(x, xb, sh, a, b, 0ull, 0ull);
+    a = b = 0;
+    for (uint32_t r = 0; r < x.world; ++r) { a += sh.xr_in[r][0]; b += sh.xr_in[r][1]; }
+}
+// minima of (a, c) and maxima of (b, d) over the ranks
+__device__ __forceinline__ void xr_minmax(const XrArgs & x, XrBlock & xb, EmShared & sh, uint32_t & a, uint32_t & b, uint32_t & c, uint32_t & d)
+{
+    xr_exchange(x, xb, sh, a, b, c, d);
+    for (uint32_t r = 0; r < x.world; ++r) {
+        a = min(a, (uint32_t)sh.xr_in[r][0]); b = max(b, (uint32_t)sh.xr_in[r][1]);
+        c = min(c, (uint32_t)sh.xr_in[r][2]); d = max(d, (uint32_t)sh.xr_in[r][3]);
+    }
 }
 
 // Normalises three log-likelihood sums like the reference (:235-251): subtract the maximum, apply the long-double

@@ -366,8 +366,13 @@ __global__ void __launch_bounds__(256) k_candidates(PdDev a, CandArgs ca, int mo
     if (mode == 1 && ca.cand_cnt[job] <= (uint32_t)PD_CAND_INLINE) return;
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
-    for (uint32_t s = threadIdx.x; s < a.N; s += blockDim.x)
-        if (ca.sstat[(size_t)job * a.N + s] == 2) sv[atomicAdd(&s_n, 1u)] = ca.q3[(size_t)job * a.N + s];
+    for (uint32_t p = 0; p < ca.nparts; ++p) {
+        const uint32_t np = ca.part_n[p];
+        const uint8_t * ss = ca.sstat[p] + (size_t)job * np;
+        const int32_t * qq = ca.q3[p] + (size_t)job * np;
+        for (uint32_t s = threadIdx.x; s < np; s += blockDim.x)
+            if (ss[s] == 2) sv[atomicAdd(&s_n, 1u)] = qq[s];
+    }
     __syncthreads();
     const uint32_t nv = s_n;
     if (nv == 0) { if (threadIdx.x == 0 && mode == 0) ca.cand_cnt[job] = 0; return; }
@@ -389,7 +394,7 @@ __global__ void __launch_bounds__(256) k_candidates(PdDev a, CandArgs ca, int mo
     if (threadIdx.x == 0) {
         // genotype_deletion_popdel_call.h:62-84; thresholds are indexed by RANK in the sorted array (quirk)
         int sum = sv[0], n = 1;
-        uint32_t thr = a.rgc[0].min_init, nc = 0;
+        uint32_t thr = ca.min_init[0], nc = 0;
         const uint32_t pair0 = mode == 1 ? ca.cand_off[job] : 0;
         auto emit = [&](int mean) {
             if (mode == 0) { if (nc < (uint32_t)PD_CAND_INLINE) ca.cand_inline[(size_t)job * PD_CAND_INLINE + nc] = mean; }
@@ -397,8 +402,8 @@ __global__ void __launch_bounds__(256) k_candidates(PdDev a, CandArgs ca, int mo
             ++nc;
         };
         for (uint32_t i = 1; i < nv; ++i) {
-            if (sv[i - 1] + 50 > sv[i]) { sum += sv[i]; ++n; thr = min(thr, a.rgc[i].min_init); }
-            else { if (sum / n > (int)thr) emit(sum / n); sum = sv[i]; n = 1; thr = a.rgc[i].min_init; }
+            if (sv[i - 1] + 50 > sv[i]) { sum += sv[i]; ++n; thr = min(thr, ca.min_init[i]); }
+            else { if (sum / n > (int)thr) emit(sum / n); sum = sv[i]; n = 1; thr = ca.min_init[i]; }
         }
         if (sum / n > (int)thr) emit(sum / n);
         if (mode == 0) ca.cand_cnt[job] = nc;

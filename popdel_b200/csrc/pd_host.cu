@@ -117,6 +117,12 @@ static int upload_static(pd_ctx * c)
     PD_CUDA(c, cudaMemcpy(c->d_tab, tab.data(), total * sizeof(PdTab), cudaMemcpyHostToDevice));
     PD_CUDA(c, cudaMalloc(&c->d_rgc, c->R * sizeof(PdRgConst)));
     PD_CUDA(c, cudaMemcpy(c->d_rgc, c->rgc.data(), c->R * sizeof(PdRgConst), cudaMemcpyHostToDevice));
+    {
+        std::vector<uint32_t> mi(c->R);
+        for (uint32_t g = 0; g < c->R; ++g) mi[g] = c->rgc[g].min_init;
+        PD_CUDA(c, cudaMalloc(&c->d_min_init, c->R * 4));
+        PD_CUDA(c, cudaMemcpy(c->d_min_init, mi.data(), c->R * 4, cudaMemcpyHostToDevice));
+    }
     PD_CUDA(c, cudaMalloc(&c->d_sample_rg, (c->N + 1) * 4));
     PD_CUDA(c, cudaMemcpy(c->d_sample_rg, c->sample_rg.data(), (c->N + 1) * 4, cudaMemcpyHostToDevice));
     return 0;
@@ -192,7 +198,8 @@ extern "C" void pd_destroy(pd_ctx * c)
     if (c->device >= 0) {
         cudaSetDevice(c->device);
         cudaFree(c->d_words); cudaFree(c->d_tiles); cudaFree(c->d_longs);
-        cudaFree(c->d_rgc); cudaFree(c->d_sample_rg); cudaFree(c->d_tab);
+        pd_shard_release(c);
+        cudaFree(c->d_rgc); cudaFree(c->d_sample_rg); cudaFree(c->d_tab); cudaFree(c->d_min_init);
         if (c->res_ps) cudaFreeHost(c->res_ps);
         if (c->res_calls) cudaFreeHost(c->res_calls);
         if (c->res_count) cudaFreeHost(c->res_count);
@@ -245,7 +252,7 @@ extern "C" int pd_contig_begin(pd_ctx * c, uint32_t anchor)
     for (auto & r : c->raw) r = PdRawRg();
     c->dev_mode = c->host_mode = false;
     c->contig_open = true; c->packed = false; c->uploaded = false; c->index_built = false;
-    c->n_windows_total = 0; c->n_reads = 0;
+    c->n_windows_total = 0; c->n_reads = 0; c->min_windows = 0; c->tail = PdTail();
     return 0;
 }
 
@@ -352,27 +359,33 @@ extern "C" int pd_contig_push(pd_ctx * c, uint32_t rg, uint64_t n, const uint32_
 // profile_structure_popdel_call.h:1213-1247): in the final segment kf the scan runs until the border or until every
 // start entry is activated and every end entry of end set kf (own entries ending before the border, spill-over
 // entries of segment kf-1) is removed.
-static uint64_t last_scanned_window(const pd_ctx * c)
+uint64_t pd_tail_windows(const PdTail & t, uint32_t wb)
 {
-    const uint32_t wb = c->grid.window_buffer;
-    int64_t kf = -1;
-    for (const auto & h : c->hrg) kf = std::max(kf, h.seg);
-    if (kf < 0) return 0;
-    int64_t E = -1, S = -1;
-    for (const auto & h : c->hrg) {
-        if (h.seg == kf) { S = std::max(S, h.S); E = std::max(E, h.E_own); if (h.prev_seg == kf - 1) E = std::max(E, h.prev_E_spill); }
-        else if (h.seg == kf - 1) E = std::max(E, h.E_spill);
-    }
-    const int64_t stop = std::max(E + 2, (S + 29) / (int64_t)PD_WIN);
-    const int64_t wl = (int64_t)pd_seg_last_window((uint64_t)kf, wb);
+    if (t.kf < 0) return 0;
+    const int64_t stop = std::max(t.E + 2, (t.S + 29) / (int64_t)PD_WIN);
+    const int64_t wl = (int64_t)pd_seg_last_window((uint64_t)t.kf, wb);
     return (uint64_t)std::min(stop, wl) + 1;
+}
+static uint64_t last_scanned_window(pd_ctx * c)
+{
+    PdTail t;
+    for (const auto & h : c->hrg) t.kf = std::max(t.kf, h.seg);
+    if (t.kf >= 0)
+        for (const auto & h : c->hrg) {
+            if (h.seg == t.kf) {
+                t.S = std::max(t.S, h.S); t.E = std::max(t.E, h.E_own); t.E_spill = std::max(t.E_spill, h.E_spill);
+                if (h.prev_seg == t.kf - 1) t.E = std::max(t.E, h.prev_E_spill);
+            } else if (h.seg == t.kf - 1) t.E = std::max(t.E, h.E_spill);
+        }
+    c->tail = t;
+    return pd_tail_windows(t, c->grid.window_buffer);
 }
 
 int pd_pack_contig(pd_ctx * c)
 {
     if (c->packed) return 0;
     c->n_windows_total = last_scanned_window(c);
-    uint64_t max_tile = (c->n_windows_total + PD_TILE_WINDOWS - 1) / PD_TILE_WINDOWS;
+    uint64_t max_tile = (std::max(c->n_windows_total, c->min_windows) + PD_TILE_WINDOWS - 1) / PD_TILE_WINDOWS;
     for (auto & h : c->hrg) {
         if (!reserve_words(c, h, h.n_words + 4)) return pd_fail(c, PD_ERR_CUDA, "out of (pinned) host memory");
         while (h.n_words & 3) h.words[h.n_words++] = PD_PAD_WORD;
@@ -426,6 +439,15 @@ extern "C" int pd_contig_push_pinned(pd_ctx * c, uint32_t rg, uint64_t n, const 
     if (c->raw[rg].n) return pd_fail(c, PD_ERR_ARG, "pd_contig_push_pinned: one call per read group and contig");
     c->dev_mode = true;
     c->raw[rg] = PdRawRg{pos, dev, n};
+    return 0;
+}
+
+extern "C" int pd_contig_reserve_windows(pd_ctx * c, uint64_t n_windows)
+{
+    if (!c) return PD_ERR_ARG;
+    if (c->status) return c->status;
+    if (!c->contig_open || c->packed || c->uploaded) return pd_fail(c, PD_ERR_ARG, "pd_contig_reserve_windows: call between pd_contig_begin and the upload");
+    c->min_windows = n_windows;
     return 0;
 }
 

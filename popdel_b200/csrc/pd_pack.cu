@@ -295,16 +295,17 @@ int grow_dev(pd_ctx * c, int slot, T *& p, size_t need)
 }  // namespace
 
 // Last window the reference scans (see last_scanned_window in pd_host.cu), from the tails of the raw host arrays.
-static uint64_t last_window_from_raw(const pd_ctx * c)
+static uint64_t last_window_from_raw(pd_ctx * c)
 {
     const uint32_t wb = c->grid.window_buffer, anchor = c->grid.anchor;
+    c->tail = PdTail();
     int64_t kf = -1;
     for (uint32_t g = 0; g < c->R; ++g) {
         const PdRawRg & r = c->raw[g];
         if (r.n) kf = std::max<int64_t>(kf, (int64_t)((uint64_t)((r.pos[r.n - 1] - anchor) / PD_WIN) * PD_WIN / wb));
     }
     if (kf < 0) return 0;
-    int64_t E = -1, S = -1;
+    int64_t E = -1, S = -1, Esp = -1;
     for (uint32_t g = 0; g < c->R; ++g) {
         const PdRawRg & r = c->raw[g];
         const int32_t io = c->rgc[g].inner_off;
@@ -316,13 +317,12 @@ static uint64_t last_window_from_raw(const pd_ctx * c)
             const int64_t inner = std::max<int64_t>(0, (int64_t)r.dev[i] + io);
             const int64_t lw = (int64_t)((pr + inner) / PD_WIN);
             const int64_t wl = (int64_t)pd_seg_last_window((uint64_t)j, wb);
-            if (j == kf) { S = std::max<int64_t>(S, (int64_t)pr); if (lw <= wl) E = std::max(E, lw); }
+            if (j == kf) { S = std::max<int64_t>(S, (int64_t)pr); if (lw <= wl) E = std::max(E, lw); else Esp = std::max(Esp, lw); }
             else if (lw > wl) E = std::max(E, lw);
         }
     }
-    const int64_t stop = std::max(E + 2, (S + 29) / (int64_t)PD_WIN);
-    const int64_t wl = (int64_t)pd_seg_last_window((uint64_t)kf, wb);
-    return (uint64_t)std::min(stop, wl) + 1;
+    c->tail.kf = kf; c->tail.S = S; c->tail.E = E; c->tail.E_spill = Esp;
+    return pd_tail_windows(c->tail, wb);
 }
 
 // returns 0 on success, 1 when the contig must be packed by the host path instead, <0 on error
@@ -343,7 +343,7 @@ int pd_pack_on_device(pd_ctx * c)
     const uint64_t total = rg_start[R];
     if (total > 0xFFFFFFF0ull) return pd_fail(c, PD_ERR_CAPACITY, "more than 2^32 read pairs in one contig batch");
     c->n_windows_total = any ? last_window_from_raw(c) : 0;
-    const uint32_t NT = (uint32_t)std::max<uint64_t>(std::max<uint64_t>((c->n_windows_total + PD_TILE_WINDOWS - 1) / PD_TILE_WINDOWS,
+    const uint32_t NT = (uint32_t)std::max<uint64_t>(std::max<uint64_t>((std::max(c->n_windows_total, c->min_windows) + PD_TILE_WINDOWS - 1) / PD_TILE_WINDOWS,
                                                                         any ? (uint64_t)max_pos_rel / PD_TILE_BP + 1 : 0), 1);
     c->NT = NT;
     cudaStream_t st = c->stream;

@@ -12,13 +12,14 @@
 #include <vector>
 
 #include "pd_device.cuh"
+#include "pd_shard.h"
 
 namespace {
 
 enum Slot {                                     // d_scratch slots
     S_NEED = 0, S_TFLAGS, S_COUNTERS, S_TJ_TILE, S_TJ_MASK, S_TJ_WBASE, S_JOBWIN, S_BSUMS,
     S_ACT_OFF, S_ACT_CNT, S_Q3, S_SSTAT, S_CAND_CNT, S_CAND_INL, S_CAND_OFF, S_CJOB_OF, S_TJ_CMASK, S_TJ_CFIRST, S_PAIRS, S_POOL_POS, S_POOL_DEV,
-    S_DLX, S_DLE, S_SHIFTS, S_STATES, S_PS0, S_PS1, S_CALLS0, S_CALLS1, S_VALID0, S_VALID1, S_CHUNK_BASE, S_DBG, S_DMAX
+    S_DLX, S_DLE, S_SHIFTS, S_STATES, S_PS0, S_PS1, S_CALLS0, S_CALLS1, S_VALID0, S_VALID1, S_CHUNK_BASE, S_DBG, S_DMAX, S_ALL_Q3, S_ALL_SS
 };
 
 template <typename T>
@@ -102,10 +103,18 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
 {
     PD_CUDA(c, cudaSetDevice(c->device));
     memset(out, 0, sizeof(*out));
-    const uint64_t total = c->n_windows_total;
+    PdShard * sh = c->shard;                                          // sample-sharded cohort: this scan is a collective
+    uint64_t total = c->n_windows_total;
+    if (sh) {
+        if (pd_shard_window_total(c, &total)) return c->status;
+        if ((total + PD_TILE_WINDOWS - 1) / PD_TILE_WINDOWS > c->NT)
+            return pd_fail(c, PD_ERR_ARG, "sample-sharded scan: the cohort's window range exceeds this rank's tile tables; call pd_contig_reserve_windows(contig length / 30 + 2) before the upload");
+    }
     const uint64_t w_begin = std::min<uint64_t>(first_window, total);
     const uint64_t w_end = n_windows ? std::min<uint64_t>(first_window + n_windows, total) : total;
     const uint32_t N = c->N, R = c->R;
+    // sizes that decide the batching must be the same on every rank of a sharded cohort
+    const uint32_t Nb = sh ? sh->n_local_max : N, Rb = sh ? sh->r_global : R, Ng = sh ? sh->n_global : N;
     const size_t row = 13ull * N;
     if (ensure_results(c, 1, row, 0)) return c->status;
     c->res_count[0] = 0;
@@ -159,6 +168,7 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
         pd_launch_screen(a, s, c->max_rg_words, st, c->ev[10], nl);
         PD_CUDA(c, cudaGetLastError());
     }
+    if (sh && n_tiles && pd_shard_or_flags(c, s.tile_flags, n_tiles, st)) return c->status;      // a window is flagged if ANY rank flags it
     PD_CUDA(c, cudaEventRecord(c->ev[4], st));
     if (n_tiles) pd_launch_tile_jobs(j, st, nl);
     PD_CUDA(c, cudaGetLastError());
@@ -170,12 +180,12 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
 
     // ---- genotyping stage. Level 1: batches of tile jobs (Q3 of every flagged window, candidates). Level 2: the windows
     // with candidates ("candidate jobs") in sub-batches of whole tiles (active-set pool, EM, final pass, emission).
-    const size_t job_bytes = 9ull * N + 4ull * (PD_CAND_INLINE + 3) + 8;
+    const size_t job_bytes = 9ull * Nb * (sh ? sh->world + 1 : 1) + 4ull * (PD_CAND_INLINE + 3) + 8;
     uint32_t JB = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(3000000000ull / job_bytes, 64), 1u << 20);
     if (getenv("PD_JOB_BATCH")) JB = std::max<uint32_t>((uint32_t)atoi(getenv("PD_JOB_BATCH")), 64);           // test knobs
     const uint32_t rows_env = getenv("PD_CJOB_ROWS") ? std::max<uint32_t>((uint32_t)atoi(getenv("PD_CJOB_ROWS")), 1) : 0;
     const uint32_t slow_env = getenv("PD_FORCE_SLOW") ? (uint32_t)atoi(getenv("PD_FORCE_SLOW")) : 0;
-    const size_t cjob_bytes = 8ull * R + 400ull * N;
+    const size_t cjob_bytes = 8ull * Rb + 400ull * Nb;
     const uint32_t JB2 = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(4000000000ull / cjob_bytes, 64), 1u << 20);
     std::vector<uint32_t> h_wbase;
     if (n_jobs > JB) {
@@ -183,10 +193,19 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
         PD_CUDA(c, cudaMemcpyAsync(h_wbase.data(), j.tj_wbase, (size_t)n_tj * 4, cudaMemcpyDeviceToHost, st));
         PD_CUDA(c, cudaStreamSynchronize(st));
     }
-    uint32_t npad = 1; while (npad < N) npad <<= 1;
+    uint32_t npad = 1; while (npad < Ng) npad <<= 1;
     if ((size_t)npad * 4 > 200 * 1024) return pd_fail(c, PD_ERR_CAPACITY, "more than 51200 samples per context: candidate sort does not fit shared memory (shard by sample)");
-    const size_t pair_bytes = 48ull * N + 4ull * R + 2 * 52ull * N + 128;
+    const size_t pair_bytes = 48ull * Nb + 4ull * Rb + 2 * 52ull * Nb + 128;
     const uint32_t CH = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(2000000000ull / pair_bytes, 64), getenv("PD_EM_CHUNK") ? atoi(getenv("PD_EM_CHUNK")) : 8192);
+    XrArgs xr;
+    memset(&xr, 0, sizeof(xr));
+    if (sh) {
+        xr.world = sh->world; xr.rank = sh->rank; xr.pairs_cap = sh->xr_pairs_cap; xr.ticket = sh->d_ticket; xr.err = sh->d_err;
+        xr.n_global = sh->n_global; xr.owns_rg0 = sh->sample_offset == 0; xr.grid_cap = sh->grid_cap;
+        for (uint32_t r = 0; r < sh->world; ++r) xr.peer[r] = sh->xr_peer[r];
+        if (CH > sh->xr_pairs_cap) return pd_fail(c, PD_ERR_ARG, "EM chunk larger than the exchange slots");
+        PD_CUDA(c, cudaMemsetAsync(sh->d_err, 0, 4, st));
+    }
     uint64_t n_pairs_total = 0, n_cjobs_total = 0;
     uint32_t chunk_no = 0;
     std::vector<uint32_t> h_jobwin; std::vector<PdPair> h_pairs;
@@ -212,20 +231,31 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
         memset(&ga, 0, sizeof(ga));
         ga.tj_tile = j.tj_tile; ga.tj_mask = j.tj_mask; ga.tj_wbase = j.tj_wbase; ga.tj0 = tj0; ga.ntj = ntj;
         ga.job_base = job_base; ga.counters = d_counters;
-        if (grow_scratch(c, S_Q3, ga.q3, (size_t)nj * N)) return c->status;
-        if (grow_scratch(c, S_SSTAT, ga.sstat, (size_t)nj * N)) return c->status;
+        if (grow_scratch(c, S_Q3, ga.q3, (size_t)nj * Nb)) return c->status;         // (sharded: all-gather blocks of equal size)
+        if (grow_scratch(c, S_SSTAT, ga.sstat, (size_t)nj * Nb)) return c->status;
         if (grow_scratch(c, S_DMAX, ga.dmax, (size_t)nj * N)) return c->status;
         uint32_t * d_cmask, * d_cfirst;
         if (grow_scratch(c, S_TJ_CMASK, d_cmask, (size_t)ntj)) return c->status;
         if (grow_scratch(c, S_TJ_CFIRST, d_cfirst, (size_t)ntj)) return c->status;
         ga.tj_cmask = d_cmask; ga.tj_cfirst = d_cfirst;
         CandArgs ca;
-        ca.q3 = ga.q3; ca.sstat = ga.sstat; ca.njobs = nj; ca.job_base = job_base; ca.counters = d_counters; ca.block_sums = d_bsums; ca.npad = npad;
+        memset(&ca, 0, sizeof(ca));
+        ca.nparts = 1; ca.q3[0] = ga.q3; ca.sstat[0] = ga.sstat; ca.part_n[0] = N; ca.min_init = c->d_min_init;
+        ca.njobs = nj; ca.job_base = job_base; ca.counters = d_counters; ca.block_sums = d_bsums; ca.npad = npad;
+        int32_t * all_q3 = nullptr; uint8_t * all_ss = nullptr;
+        if (sh) {
+            if (grow_scratch(c, S_ALL_Q3, all_q3, (size_t)nj * Nb * sh->world)) return c->status;
+            if (grow_scratch(c, S_ALL_SS, all_ss, (size_t)nj * Nb * sh->world)) return c->status;
+            ca.nparts = sh->world;
+            for (uint32_t r = 0; r < sh->world; ++r) {
+                ca.q3[r] = all_q3 + (size_t)r * nj * Nb; ca.sstat[r] = all_ss + (size_t)r * nj * Nb; ca.part_n[r] = sh->part_n[r];
+            }
+        }
         if (grow_scratch(c, S_CAND_CNT, ca.cand_cnt, (size_t)nj)) return c->status;
         if (grow_scratch(c, S_CAND_INL, ca.cand_inline, (size_t)nj * PD_CAND_INLINE)) return c->status;
         if (grow_scratch(c, S_CAND_OFF, ca.cand_off, (size_t)nj)) return c->status;
         if (grow_scratch(c, S_CJOB_OF, ca.cjob_of, (size_t)nj)) return c->status;
-        uint32_t rows_cap = std::min<uint32_t>(std::min<uint32_t>(nj, JB2), (uint32_t)std::max<uint64_t>(1000000000ull / (8ull * R), 64));
+        uint32_t rows_cap = std::min<uint32_t>(std::min<uint32_t>(nj, JB2), (uint32_t)std::max<uint64_t>(1000000000ull / (8ull * Rb), 64));
         if (rows_env) rows_cap = std::min(rows_cap, rows_env);
         ga.debug_flags = slow_env;
         if (grow_scratch(c, S_ACT_OFF, ga.act_off, (size_t)(rows_cap + PD_TILE_WINDOWS) * R)) return c->status;
@@ -235,6 +265,10 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
 
         pd_launch_q3(a, ga, st, nl);
         PD_CUDA(c, cudaGetLastError());
+        if (sh) {                                                   // every rank derives the candidates from ALL samples' Q3
+            if (pd_shard_allgather(c, ga.q3, all_q3, (size_t)nj * Nb * 4, st)) return c->status;
+            if (pd_shard_allgather(c, ga.sstat, all_ss, (size_t)nj * Nb, st)) return c->status;
+        }
         // candidates, then (optimistically) the pool of the first sub-batch; one synchronisation validates both
         auto run_gather = [&](uint32_t cj_lo) -> int {
             if (c->pool_cap > 0xFFFFFFF0ull) c->pool_cap = 0xFFFFFFF0ull;
@@ -318,6 +352,8 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
                 e.job_window = j.job_window; e.pairs = ca.pairs; e.pair0 = p0; e.npairs = np; e.job_base = job_base;
                 e.pool_pos = ga.pool_pos; e.pool_dev = ga.pool_dev; e.act_off = ga.act_off; e.act_cnt = ga.act_cnt; e.sstat = ga.sstat; e.dmax = ga.dmax;
                 e.cjob_of = ca.cjob_of; e.cj_base = cj_lo;
+                e.xr = xr;
+                if (sh) e.xr.epoch = sh->epoch++;
                 e.iterations = c->params.iterations; e.min_len = c->params.min_len; e.min_lr = c->params.min_lr;
                 e.min_sample_fraction = c->params.min_sample_fraction; e.somatic = c->params.somatic; e.window_wise = c->params.window_wise;
                 e.anchor = c->grid.anchor;
@@ -328,6 +364,7 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
                     PD_CUDA(c, cudaMemsetAsync(e.dbg, 0xFF, (size_t)np * 16, st));
                 }
                 PD_CUDA(c, cudaMemsetAsync(e.valid, 0, np, st));
+                if (sh && pd_shard_prelaunch(c)) return c->status;
                 if (pd_launch_em(c, a, e, st, nl)) return c->status;
                 PD_CUDA(c, cudaEventRecord(c->ev[6 + par], st));
                 if (dbg) {
@@ -363,6 +400,11 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
     PD_CUDA(c, cudaEventRecord(c->ev[5], st));
     PD_CUDA(c, cudaStreamSynchronize(st));
     PD_CUDA(c, cudaStreamSynchronize(st2));
+    if (sh) {
+        uint32_t xerr = 0;
+        PD_CUDA(c, cudaMemcpy(&xerr, sh->d_err, 4, cudaMemcpyDeviceToHost));
+        if (xerr) return pd_fail(c, PD_ERR_CUDA, "sample-sharded scan: a peer rank did not answer an in-kernel exchange in time");
+    }
     out->n_calls = c->res_count[0];
     out->calls = c->res_calls;
     out->per_sample = c->res_ps;

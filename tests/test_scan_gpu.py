@@ -99,3 +99,34 @@ def test_scan_generic_paths_and_batching(kind, env, oracle_lib, monkeypatch):
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     compare_scan_with_oracle(samples, oracle_lib, params)
+
+
+@pytest.mark.parametrize("kind,world", [("basic", 2), ("mixedrg", 2), ("mixedrg", 3), ("highcov", 2), ("longspan", 3)])
+def test_sample_sharded_scan_equals_single_context(kind, world, oracle_lib):
+    """Sample sharding: `world` contexts of one process, each holding a block of the samples,
+    exchange tile flags, Q3 values and the EM's per-iteration statistics (in-kernel, through peer memory). The merged
+    result must equal the oracle and the single-context scan: integers bit-exact, LR / AF within 1e-6 relative (the
+    cross-rank sums are taken in rank order, not in the single-context order)."""
+    samples, params = _cohort(kind)
+    merged, rgs = api.scan_cohort_sample_sharded(samples, params, world)
+    single, _ = api.scan_cohort(samples, params)
+    assert merged["n_windows"] == single["n_windows"] and merged["n_flagged_windows"] == single["n_flagged_windows"]
+    assert_calls_equal(merged["calls"], merged["per_sample"], single["calls"], single["per_sample"])
+    ref_calls, ref_ps, _ = run_oracle(samples, params, rgs, oracle_lib)
+    assert_calls_equal(merged["calls"], merged["per_sample"], ref_calls, ref_ps)
+    assert len(merged["calls"]) > 0
+
+
+def test_sample_sharded_larger_cohort(oracle_lib):
+    """40 samples over 4 contexts, several candidates per window, EM chunks of 16 pairs (several launches per scan)."""
+    import os
+    samples, _ = simulate.simulate_cohort(seed=35, n_samples=40, contig_len=300_000, n_dels=4)
+    params = api.CallParameters()
+    os.environ["PD_EM_CHUNK"] = "16"
+    try:
+        merged, rgs = api.scan_cohort_sample_sharded(samples, params, 4)
+    finally:
+        del os.environ["PD_EM_CHUNK"]
+    ref_calls, ref_ps, _ = run_oracle(samples, params, rgs, oracle_lib)
+    assert_calls_equal(merged["calls"], merged["per_sample"], ref_calls, ref_ps)
+    assert len(merged["calls"]) > 100
