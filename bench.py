@@ -57,11 +57,8 @@ def plant(seed, n_samples, length, per_mbp):
     return np.array(starts, np.uint32), np.array(lens, np.uint32), np.stack(gts)
 
 
-def make_cohort(seed, n_samples, length, per_mbp, threads, mixed=False):
-    """Returns (list of read groups [pos, isize, dev, header, sample], deletions). One read group per sample, or with
-    `mixed` 1-3 read groups per sample with mu in {350,450,550} and sigma in {30,50,80} (BASELINE.json configs[2])."""
-    from popdel_b200 import api
-    ds, dl, gt = plant(seed, n_samples, length, per_mbp)
+def cohort_specs(seed, n_samples, mixed=False):
+    """(sample, read group, mu, sigma, read pairs per bp) of every read group of the cohort."""
     rng = np.random.default_rng([seed, 77])
     specs = []
     for s in range(n_samples):
@@ -70,6 +67,18 @@ def make_cohort(seed, n_samples, length, per_mbp, threads, mixed=False):
             mu = float(rng.choice([350, 450, 550])) if mixed else 500.0
             sd = float(rng.choice([30, 50, 80])) if mixed else 50.0
             specs.append((s, len(specs), mu, sd, 0.1 / k))
+    return specs
+
+
+def make_cohort(seed, n_samples, length, per_mbp, threads, mixed=False, sample_range=None):
+    """Returns (list of read groups [pos, isize, dev, header, sample], deletions). One read group per sample, or with
+    `mixed` 1-3 read groups per sample with mu in {350,450,550} and sigma in {30,50,80} (BASELINE.json configs[2]).
+    sample_range = (s0, s1): only the read groups of these samples of the cohort are generated (sample sharding)."""
+    from popdel_b200 import api
+    ds, dl, gt = plant(seed, n_samples, length, per_mbp)
+    specs = cohort_specs(seed, n_samples, mixed)
+    if sample_range is not None:
+        specs = [sp for sp in specs if sample_range[0] <= sp[0] < sample_range[1]]
 
     def one(spec):
         s, g, mu, sd, dens = spec
@@ -277,6 +286,103 @@ def cpu_baseline(args, cohort, params, rgs):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# sample-sharded cohort (BASELINE.json configs[4] style): every rank holds samples/world samples of the SAME window range
+# ----------------------------------------------------------------------------------------------------------------
+def run_sample_sharded(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from popdel_b200 import api
+    assert world >= 2, "--shard-samples needs torchrun with >= 2 ranks"
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    threads = max(1, (os.cpu_count() or 8) // world)
+    N, L = args.samples, args.length
+    spr = api.split_samples(N, world)
+    s0 = sum(spr[:rank])
+    cohort, dels = make_cohort(args.seed, N, L, args.dels_per_mbp, threads, args.mixed, sample_range=(s0, s0 + spr[rank]))
+    params = api.CallParameters()
+    # call parameters of the WHOLE cohort (only sigma of the other ranks' read groups is needed)
+    specs = cohort_specs(args.seed, N, args.mixed)
+    every = [api.ReadGroup(sample=sp[0], median=int(sp[2]), read_length=150, stddev=sp[3], offset=0, values=np.zeros(3), min_prob=0.0,
+                           lower_quantile_dist=0, upper_quantile_dist=0) for sp in specs]
+    params.finalize(every)
+    min_init = np.array([r.min_init_del_len for r in every], dtype=np.uint32)
+    p_local = api.CallParameters(min_len=params.min_len)
+    rgs = api.read_groups_from_headers([[c[3] for c in cohort if c[4] == s] for s in range(s0, s0 + spr[rank])], p_local)
+    assert [r.min_init_del_len for r in rgs] == [int(min_init[sp[1]]) for sp in specs if s0 <= sp[0] < s0 + spr[rank]]
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(api.shard_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    sc = api.Scanner(params, rgs, spr[rank], device=local_rank)
+    sc.attach_nccl(rank, world, spr, min_init, bytes(uid.cpu().numpy()))
+    sc.begin_contig(0)
+    sc.reserve_windows(L // 30 + 2)
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(lambda g: sc.push(g, cohort[g][0], cohort[g][2]), range(len(cohort))))
+    sc.upload()
+    res = sc.scan(copy=True)
+    evals = int(res["n_windows"]) * N
+    check = None
+    if args.check:                      # merged result against the CPU oracle (small cohorts only)
+        parts = [None] * world
+        dist.all_gather_object(parts, dict(calls=res["calls"], per_sample=res["per_sample"], pos=[c[0] for c in cohort], dev=[c[2] for c in cohort],
+                                           rgs=[r.as_dict() for r in rgs]))
+        if rank == 0:
+            import oracle_api
+            from parity import assert_calls_equal
+            orc = oracle_api.load(os.path.join(ROOT, "oracle", "liboracle.so"))
+            for p in parts[1:]:
+                assert np.array_equal(p["calls"], parts[0]["calls"]), "ranks disagree on the calls"
+            per = np.concatenate([p["per_sample"] for p in parts], axis=1)
+            pos = [a for p in parts for a in p["pos"]]
+            dev = [a for p in parts for a in p["dev"]]
+            rg_all, base = [], 0
+            for r, p in enumerate(parts):
+                for d in p["rgs"]:
+                    rg_all.append({**d, "sample": d["sample"] + base})
+                base += spr[r]
+            off = np.concatenate([[0], np.cumsum([a.size for a in pos])]).astype(np.uint64)
+            ref_calls, ref_ps, nwin = orc.scan_contig(params.as_dict(), rg_all, off, np.concatenate(pos), np.concatenate(dev), N, max_calls=400000)
+            assert nwin == res["n_windows"], (nwin, res["n_windows"])
+            assert_calls_equal(parts[0]["calls"], per, ref_calls, ref_ps)
+            check = f"merged calls of {world} ranks == CPU oracle ({len(ref_calls)} window calls, integers bit-exact, LR/AF 1e-6)"
+    for _ in range(args.warmup):
+        sc.scan(copy=False)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    launches, ms_dev = 0, []
+    for _ in range(args.steps):
+        r2 = sc.scan(copy=False)
+        launches += int(r2["n_kernel_launches"]); ms_dev.append(r2["ms_total"])
+    dist.barrier(); torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    clk = clocks.stop()
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    n_calls = len(r2["calls"])
+    sc.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank != 0:
+        return
+    out = {"metric": METRIC, "value": evals * args.steps / dt, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "int32 (screen) / f64 (likelihoods)", "data": "synthetic",
+           "config": {"workload": f"{N} synthetic profiles sharded BY SAMPLE over {world} GPUs ({spr[0]} per GPU), one window range of {L} bp "
+                                  f"({res['n_windows']} windows), {'mixed read groups' if args.mixed else 'single read group each'}, 30x, "
+                                  f"planted deletions {args.dels_per_mbp}/Mbp; exchanges: NCCL all-gather (tile flags, Q3), in-kernel peer-memory "
+                                  f"reductions of the EM statistics over NVLink", "samples": N, "windows": int(res["n_windows"]),
+                      "parallelism": f"sample-sharded x{world}", "calls_per_step": int(n_calls), "flagged_windows": int(res["n_flagged_windows"]),
+                      "candidates": int(res["n_candidates"]), "parity_check": check},
+           "clocks": clk, "gpu_launches": launches, "ms_device_per_step_rank0": float(np.mean(ms_dev))}
+    print(json.dumps(out), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # reference arm
 # ----------------------------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
@@ -354,6 +460,8 @@ def main():
     ap.add_argument("--cpu-slice", type=int, default=1_500_000)
     ap.add_argument("--ref-slice-per-core", type=int, default=300_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard-samples", action="store_true", help="sample-sharded cohort over the ranks (config 5 style) instead of window ranges")
+    ap.add_argument("--check", action="store_true", help="--shard-samples: compare the merged calls with the CPU oracle (small cohorts)")
     ap.add_argument("--mixed", action="store_true", help="1-3 read groups per sample with mixed insert-size histograms")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -362,6 +470,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.shard_samples:
+        run_sample_sharded(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

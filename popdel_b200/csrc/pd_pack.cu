@@ -50,23 +50,34 @@ __global__ void k_tile_first(PackArgs a)
     a.tfirst[id] = (uint32_t)lo;
 }
 
-// per read pair: order check and the largest tile span per read group
-__global__ void k_check_span(PackArgs a, uint64_t total)
+// per read pair: order check and the largest tile span per read group. grid = (chunks of 1024 read pairs, read group)
+__global__ void __launch_bounds__(256) k_check_span(PackArgs a)
 {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    // read group of i: R is small, linear search over the (cached) starts
-    uint32_t g = 0;
-    while (g + 1 < a.R && i >= a.rg_start[g + 1]) ++g;
-    const uint32_t p = a.pos[i];
-    if (p < a.anchor) { atomicOr(&a.flags[2], 1u); return; }
-    if (i > a.rg_start[g] && a.pos[i - 1] > p) atomicOr(&a.flags[0], 1u);
-    const uint32_t pr = p - a.anchor;
-    int64_t inner = (int64_t)a.dev[i] + a.rgc[g].inner_off;
-    if (inner < 0) inner = 0;
-    const uint64_t lw = ((uint64_t)pr + (uint64_t)inner) / PD_WIN;
-    const uint32_t span = (uint32_t)min((uint64_t)0xFFFFu, (lw + 1) / PD_TILE_WINDOWS - pr / PD_TILE_BP);
-    if (span > a.rgc[g].lookback_tiles) atomicMax(&a.span_tiles[g], span);
+    const uint32_t g = blockIdx.y;
+    const uint64_t r0 = a.rg_start[g], n = a.rg_start[g + 1] - r0;
+    const uint64_t first = (uint64_t)blockIdx.x * 1024;
+    if (first >= n) return;
+    const uint32_t * p = a.pos + r0;
+    const int32_t * d = a.dev + r0;
+    const int32_t inner_off = a.rgc[g].inner_off;
+    const uint32_t lookback = a.rgc[g].lookback_tiles;
+    uint32_t bad_order = 0, bad_anchor = 0, span_max = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const uint64_t i = first + (uint64_t)u * 256 + threadIdx.x;
+        if (i >= n) break;
+        const uint32_t pi = __ldcs(p + i);
+        if (pi < a.anchor) { bad_anchor = 1; continue; }
+        if (i > 0 && __ldg(p + i - 1) > pi) bad_order = 1;
+        const uint32_t pr = pi - a.anchor;
+        int64_t inner = (int64_t)__ldcs(d + i) + inner_off;
+        if (inner < 0) inner = 0;
+        const uint64_t lw = ((uint64_t)pr + (uint64_t)inner) / PD_WIN;
+        span_max = max(span_max, (uint32_t)min((uint64_t)0xFFFFu, (lw + 1) / PD_TILE_WINDOWS - pr / PD_TILE_BP));
+    }
+    if (bad_anchor) atomicOr(&a.flags[2], 1u);
+    if (bad_order) atomicOr(&a.flags[0], 1u);
+    if (span_max > lookback) atomicMax(&a.span_tiles[g], span_max);
 }
 
 // exact check of the active-coverage cap: one block per (read group, chunk of 32 tiles)
@@ -174,14 +185,17 @@ struct WriteArgs {
     uint32_t * pmax;                                                // prefix max of e over the wide list
 };
 
-// one thread per (read group, tile): words, pads, count of long read pairs (pass 0) / wide entries (pass 1)
-__global__ void k_pack_tiles(PackArgs a, WriteArgs w, int pass)
+// one WARP per (read group, tile), lanes over the tile's read pairs (coalesced reads of the raw arrays, coalesced
+// writes of the words): words, pads, count of long read pairs (pass 0) / wide entries in read order (pass 1)
+__global__ void __launch_bounds__(256) k_pack_tiles(PackArgs a, WriteArgs w, int pass)
 {
-    const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t id = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     const uint64_t per = (uint64_t)a.NT + 1;
     if (id >= per * a.R) return;
     const uint32_t g = (uint32_t)(id / per), t = (uint32_t)(id % per);
-    if (t >= a.NT) { if (pass == 0) w.lcount[id] = 0; return; }
+    if (t >= a.NT) { if (pass == 0 && lane == 0) w.lcount[id] = 0; return; }
+    if (pass == 1 && w.lcount[id + 1] == w.lcount[id]) return;            // no wide entries in this tile (the usual case)
     const PdRgConst k = a.rgc[g];
     const uint32_t * tf = a.tfirst + (size_t)g * per;
     const uint32_t * p = a.pos + a.rg_start[g];
@@ -190,24 +204,30 @@ __global__ void k_pack_tiles(PackArgs a, WriteArgs w, int pass)
     uint32_t * out = w.words + w.word_base[g] + w.rel_off[id];
     PdLong * lout = pass == 1 ? w.longs + w.long_base[g] + w.lcount[id] : nullptr;
     uint32_t nl = 0;
-    for (uint32_t i = i0; i < i1; ++i) {
-        const uint32_t pr = p[i] - a.anchor;
-        const int32_t dv = d[i];
-        int64_t s, e;
-        const bool act = pd_interval(pr, dv, k.inner_off, a.window_buffer, s, e);
-        bool is_long = dv > PD_DEV_MAX || dv < PD_DEV_MIN + 1;
-        if (act && (uint64_t)e / PD_TILE_WINDOWS > (uint64_t)t + k.lookback_tiles) is_long = true;
-        if (pass == 0) {
-            const int32_t dc = dv > PD_DEV_MAX ? PD_DEV_MAX : (dv < PD_DEV_MIN + 1 ? PD_DEV_MIN + 1 : dv);
-            out[i - i0] = pd_pack(dc, pr - t * PD_TILE_BP, is_long);
-        } else if (is_long && act) {
-            lout[nl] = PdLong{(uint32_t)s, (uint32_t)e, pr, dv};
+    for (uint32_t base = i0; base < i1; base += 32) {
+        const uint32_t i = base + lane;
+        bool lng = false;
+        uint32_t pr = 0; int32_t dv = 0; int64_t s = 0, e = 0;
+        if (i < i1) {
+            pr = __ldcs(p + i) - a.anchor;
+            dv = __ldcs(d + i);
+            const bool act = pd_interval(pr, dv, k.inner_off, a.window_buffer, s, e);
+            bool is_long = dv > PD_DEV_MAX || dv < PD_DEV_MIN + 1;
+            if (act && (uint64_t)e / PD_TILE_WINDOWS > (uint64_t)t + k.lookback_tiles) is_long = true;
+            if (pass == 0) {
+                const int32_t dc = dv > PD_DEV_MAX ? PD_DEV_MAX : (dv < PD_DEV_MIN + 1 ? PD_DEV_MIN + 1 : dv);
+                out[i - i0] = pd_pack(dc, pr - t * PD_TILE_BP, is_long);
+            }
+            lng = is_long && act;
         }
-        nl += (is_long && act);
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, lng);
+        if (pass == 1 && lng) lout[nl + __popc(m & ((1u << lane) - 1u))] = PdLong{(uint32_t)s, (uint32_t)e, pr, dv};
+        nl += __popc(m);
     }
     if (pass == 0) {
-        for (uint32_t i = i1 - i0; i & 3; ++i) out[i] = PD_PAD_WORD;
-        w.lcount[id] = nl;
+        const uint32_t cnt = i1 - i0, padded = (cnt + 3u) & ~3u;
+        if (cnt + lane < padded) out[cnt + lane] = PD_PAD_WORD;
+        if (lane == 0) w.lcount[id] = nl;
     }
 }
 
@@ -373,7 +393,9 @@ int pd_pack_on_device(pd_ctx * c)
     a.pos = d_pos; a.dev = d_dev; a.rg_start = d_rg_start; a.rgc = c->d_rgc; a.R = R; a.NT = NT;
     a.anchor = c->grid.anchor; a.window_buffer = c->grid.window_buffer; a.tfirst = d_tfirst; a.flags = d_small; a.span_tiles = d_small + 16;
     const uint64_t ntile = per * R;
-    if (total) k_check_span<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, total);
+    uint64_t max_n = 0;
+    for (uint32_t g = 0; g < R; ++g) max_n = std::max<uint64_t>(max_n, c->raw[g].n);
+    if (total) k_check_span<<<dim3((unsigned)((max_n + 1023) / 1024), R), 256, 0, st>>>(a);
     k_tile_first<<<(unsigned)((ntile + 255) / 256), 256, 0, st>>>(a);
     const uint32_t chunks = (NT + CAP_CHUNK_TILES - 1) / CAP_CHUNK_TILES;
     k_cap_check<<<R * chunks, 1024, 0, st>>>(a, chunks);
@@ -415,7 +437,7 @@ int pd_pack_on_device(pd_ctx * c)
     WriteArgs w;
     w.words = c->d_words; w.tiles = c->d_tiles; w.longs = nullptr; w.rel_off = d_rel; w.word_base = d_word_base;
     w.lcount = d_lcount; w.long_base = d_long_base; w.pmax = nullptr;
-    k_pack_tiles<<<(unsigned)((ntile + 127) / 128), 128, 0, st>>>(a, w, 0);
+    k_pack_tiles<<<(unsigned)((ntile + 7) / 8), 256, 0, st>>>(a, w, 0);
     k_long_offsets<<<R, 1024, 0, st>>>(a, d_lcount, d_rg_longs);
     PD_CUDA(c, cudaGetLastError());
     std::vector<uint64_t> h_longs(R);
@@ -437,7 +459,7 @@ int pd_pack_on_device(pd_ctx * c)
     }
     if (grow_dev(c, 7, d_pmax, (size_t)c->total_longs + 1)) return c->status;
     w.longs = c->d_longs; w.pmax = d_pmax;
-    k_pack_tiles<<<(unsigned)((ntile + 127) / 128), 128, 0, st>>>(a, w, 1);
+    k_pack_tiles<<<(unsigned)((ntile + 7) / 8), 256, 0, st>>>(a, w, 1);
     k_long_pmax<<<(R + 63) / 64, 64, 0, st>>>(a, w, d_rg_longs);
     k_tile_table<<<(unsigned)((ntile + 255) / 256), 256, 0, st>>>(a, w, d_rg_longs);
     PD_CUDA(c, cudaGetLastError());

@@ -49,3 +49,47 @@ def reduce_timing(elapsed_s: float, evaluations: float, dist=None, device=None):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(e, op=dist.ReduceOp.SUM)
     return float(t.item()), float(e.item())
+
+
+# ---- sample sharding (config 5): every rank holds a contiguous block of the samples of the SAME window range ------------
+def sample_blocks(n_samples: int, world: int) -> List[Tuple[int, int]]:
+    """(first sample, count) per rank; sizes differ by at most one (= api.split_samples)."""
+    base, extra = divmod(int(n_samples), int(world))
+    out, s0 = [], 0
+    for r in range(world):
+        n = base + (1 if r < extra else 0)
+        out.append((s0, n))
+        s0 += n
+    return out
+
+
+def combine_tails(tails, window_buffer: int) -> int:
+    """Number of windows the reference scans for the cohort's contig from the ranks' tail summaries (kf, S, E, E_spill)
+    -- the host restatement of pd_shard_window_total (pd_shard.cu): kf = final segment of the rank's read pairs, S =
+    largest start position in it, E = largest last window of end set kf, E_spill = largest spill-over last window."""
+    kf = max(t[0] for t in tails)
+    if kf < 0:
+        return 0
+    S = E = -1
+    for t in tails:
+        if t[0] == kf:
+            S, E = max(S, t[1]), max(E, t[2])
+        elif t[0] == kf - 1 and t[0] >= 0:
+            E = max(E, t[3])
+    stop = max(E + 2, (S + 29) // 30)
+    return min(stop, segment_last_window(kf, window_buffer)) + 1
+
+
+def merge_sample_shards(parts, rank: int, world: int, dist=None):
+    """Every rank returns the same calls and the per-sample rows of ITS samples: rank 0 concatenates the rows along
+    the sample axis in rank (= cohort) order. parts = (calls, per_sample) of this rank."""
+    if world == 1 or dist is None:
+        return parts
+    objs = [None] * world if rank == 0 else None
+    dist.gather_object(parts, objs, dst=0)
+    if rank != 0:
+        return None, None
+    for o in objs[1:]:
+        if not np.array_equal(o[0], objs[0][0]):
+            raise RuntimeError("sample-sharded ranks disagree on the window calls")
+    return objs[0][0], np.concatenate([o[1] for o in objs], axis=1)

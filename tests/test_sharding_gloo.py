@@ -44,6 +44,51 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _worker_samples(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    N = 7
+    rng = np.random.default_rng(11)
+    calls = np.zeros(50, dtype=api.CALL_DTYPE)
+    calls["window_position"] = 30 * np.sort(rng.choice(5000, size=50, replace=False)) + 29
+    ps = rng.integers(0, 50, size=(50, N, 13)).astype(np.uint32)
+    s0, n = sharding.sample_blocks(N, world)[rank]
+    got_c, got_p = sharding.merge_sample_shards((calls, ps[:, s0:s0 + n]), rank, world, dist)
+    if rank == 0:
+        q.put((np.array_equal(got_c, calls), np.array_equal(got_p, ps)))
+    dist.destroy_process_group()
+
+
+def test_sample_blocks_and_tail_combination():
+    assert sharding.sample_blocks(7, 2) == [(0, 4), (4, 3)] and sharding.sample_blocks(50000, 8)[7] == (43750, 6250)
+    assert [n for _, n in sharding.sample_blocks(10, 4)] == api.split_samples(10, 4)
+    wb = 200000
+    # one rank: stop = max(E + 2, ceil(S / 30)) capped at the last window of the final segment
+    assert sharding.combine_tails([(0, 150000, 5010, -1)], wb) == 5013
+    assert sharding.combine_tails([(0, 199990, 6660, 6700)], wb) == 6667              # capped by the segment border
+    # a rank whose read pairs end one segment earlier only contributes its spill-over entries
+    assert sharding.combine_tails([(1, 200100, 6690, -1), (0, 199000, 6650, 6700)], wb) == 6703
+    assert sharding.combine_tails([(1, 200100, 6690, -1), (-1, -1, -1, -1)], wb) == 6693
+    assert sharding.combine_tails([(-1, -1, -1, -1)] * 2, wb) == 0
+
+
+def test_merge_sample_shards_world2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_samples, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    same_calls, same_ps = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert same_calls and same_ps
+
+
 def test_gather_and_reduce_world2():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
