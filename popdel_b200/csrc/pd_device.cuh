@@ -76,6 +76,7 @@ struct CandArgs {
     PdPair * pairs; uint32_t pair_cap;
     uint32_t * counters; unsigned long long * block_sums;
     uint32_t npad;
+    uint32_t force_sort;                // tests: always take the sorting path of k_candidates
 };
 void pd_launch_q3(const PdDev & a, const GatherArgs & g, cudaStream_t st, uint64_t * launches);
 void pd_launch_cmask(const GatherArgs & g, const CandArgs & ca, uint32_t * tj_cmask, uint32_t * tj_cfirst, cudaStream_t st, uint64_t * launches);

@@ -358,25 +358,113 @@ __global__ void __launch_bounds__(TG_WARPS * 32) k_tile_gather(PdDev a, GatherAr
 // K2b: candidates. One block per flagged window. mode 0: count + inline list; mode 1: windows with more than
 // PD_CAND_INLINE candidates write their pairs directly (after the scan of the counts).
 // ------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t CAND_BITS = 1u << 16;                     // value range the presence bitmap covers
+constexpr uint32_t CAND_TOPS = 1024;                         // clusters per window via the bitmap path
+
+struct CandEmit {
+    const CandArgs & ca; uint32_t job; int mode; uint32_t pair0, nc;
+    __device__ void operator()(int mean)
+    {
+        if (mode == 0) { if (nc < (uint32_t)PD_CAND_INLINE) ca.cand_inline[(size_t)job * PD_CAND_INLINE + nc] = mean; }
+        else if (pair0 + nc < ca.pair_cap) ca.pairs[pair0 + nc] = PdPair{ca.job_base + job, mean};
+        ++nc;
+    }
+};
+
+// any value present in [lo, hi] (bit positions, hi - lo < 64)?
+__device__ __forceinline__ bool bits_any(const uint32_t * bits, uint32_t lo, uint32_t hi)
+{
+    const uint32_t w0 = lo >> 5, w1 = hi >> 5;
+    const uint32_t m0 = 0xFFFFFFFFu << (lo & 31u), m1 = 0xFFFFFFFFu >> (31u - (hi & 31u));
+    if (w0 == w1) return (bits[w0] & m0 & m1) != 0;
+    uint32_t r = (bits[w0] & m0) | (bits[w1] & m1);
+    for (uint32_t w = w0 + 1; w < w1; ++w) r |= bits[w];
+    return r != 0;
+}
+
+// One block per flagged window: initialize_deletion_lengths (genotype_deletion_popdel_call.h:58-86) WITHOUT sorting the
+// Q3 values. The chain clusters (sorted neighbours closer than 50) are the maximal runs of a presence bitmap over the
+// value range whose gaps are shorter than 50: a value is the top of a cluster iff none of the next 49 values is
+// present. Per cluster: sum and count by shared-memory atomics; the ranks of its members in the sorted array are
+// [number of smaller values, + count), which is all the rank-indexed thresholds need (quirk, :65,72,80). Falls back to
+// the bitonic sort for value ranges beyond 65 536 or more than 1 024 clusters.
 __global__ void __launch_bounds__(256) k_candidates(PdDev a, CandArgs ca, int mode)
 {
     extern __shared__ int32_t sv[];
-    __shared__ uint32_t s_n;
+    __shared__ uint32_t s_bits[CAND_BITS / 32 + 4];
+    __shared__ int32_t s_top[CAND_TOPS], s_sorted[CAND_TOPS], s_sum[CAND_TOPS];
+    __shared__ uint32_t s_cnt[CAND_TOPS];
+    __shared__ uint32_t s_n, s_ntop, s_thr;
+    __shared__ int32_t s_min, s_max;
     const uint32_t job = blockIdx.x;
     if (mode == 1 && ca.cand_cnt[job] <= (uint32_t)PD_CAND_INLINE) return;
-    if (threadIdx.x == 0) s_n = 0;
+    if (threadIdx.x == 0) { s_n = 0; s_ntop = 0; s_min = INT_MAX; s_max = INT_MIN; }
     __syncthreads();
     for (uint32_t p = 0; p < ca.nparts; ++p) {
         const uint32_t np = ca.part_n[p];
         const uint8_t * ss = ca.sstat[p] + (size_t)job * np;
         const int32_t * qq = ca.q3[p] + (size_t)job * np;
         for (uint32_t s = threadIdx.x; s < np; s += blockDim.x)
-            if (ss[s] == 2) sv[atomicAdd(&s_n, 1u)] = qq[s];
+            if (ss[s] == 2) { const int32_t v = qq[s]; sv[atomicAdd(&s_n, 1u)] = v; atomicMin(&s_min, v); atomicMax(&s_max, v); }
     }
     __syncthreads();
     const uint32_t nv = s_n;
     if (nv == 0) { if (threadIdx.x == 0 && mode == 0) ca.cand_cnt[job] = 0; return; }
-    uint32_t np2 = 1; while (np2 < nv) np2 <<= 1;                 // sort only the occupied power of two
+    CandEmit emit{ca, job, mode, mode == 1 ? ca.cand_off[job] : 0u, 0u};
+    const int32_t mn = s_min;
+    const uint32_t range = (uint32_t)(s_max - mn) + 1u;
+    bool sorted_path = ca.force_sort || range > CAND_BITS;
+    if (!sorted_path) {
+        const uint32_t nwords = (range + 31) / 32;
+        for (uint32_t w = threadIdx.x; w < nwords + 3; w += blockDim.x) s_bits[w] = 0;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nv; i += blockDim.x) { const uint32_t b = (uint32_t)(sv[i] - mn); atomicOr(&s_bits[b >> 5], 1u << (b & 31u)); }
+        __syncthreads();
+        for (uint32_t w = threadIdx.x; w < nwords; w += blockDim.x)
+            for (uint32_t m = s_bits[w]; m; m &= m - 1) {
+                const uint32_t b = w * 32 + (__ffs(m) - 1);
+                if (!bits_any(s_bits, b + 1, b + 49)) { const uint32_t slot = atomicAdd(&s_ntop, 1u); if (slot < CAND_TOPS) s_top[slot] = (int32_t)b; }
+            }
+        __syncthreads();
+        sorted_path = s_ntop > CAND_TOPS;
+    }
+    if (!sorted_path) {
+        const uint32_t K = s_ntop;
+        for (uint32_t t = threadIdx.x; t < K; t += blockDim.x) {
+            const int32_t v = s_top[t];
+            uint32_t r = 0;
+            for (uint32_t u = 0; u < K; ++u) r += s_top[u] < v;
+            s_sorted[r] = v; s_sum[t] = 0; s_cnt[t] = 0;
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nv; i += blockDim.x) {
+            const int32_t b = sv[i] - mn;
+            uint32_t lo = 0, hi = K - 1;                               // smallest k with top_k >= b
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (s_sorted[mid] >= b) hi = mid; else lo = mid + 1; }
+            atomicAdd(&s_sum[lo], sv[i]); atomicAdd(&s_cnt[lo], 1u);
+        }
+        __syncthreads();
+        uint32_t r0 = 0;
+        for (uint32_t k = 0; k < K; ++k) {
+            const uint32_t n = s_cnt[k];
+            const int mean = s_sum[k] / (int)n;
+            if (mean > a.t_min) {                                       // else it cannot exceed any threshold (t_min = their minimum)
+                if (threadIdx.x == 0) s_thr = 0xFFFFFFFFu;
+                __syncthreads();
+                uint32_t t = 0xFFFFFFFFu;
+                for (uint32_t i = r0 + threadIdx.x; i < r0 + n; i += blockDim.x) t = min(t, ca.min_init[i]);
+                if (t != 0xFFFFFFFFu) atomicMin(&s_thr, t);
+                __syncthreads();
+                if (threadIdx.x == 0 && mean > (int)s_thr) emit(mean);
+                __syncthreads();
+            }
+            r0 += n;
+        }
+        if (threadIdx.x == 0 && mode == 0) ca.cand_cnt[job] = emit.nc;
+        return;
+    }
+    // ---- fallback: bitonic sort of the occupied power of two, then the reference's linear pass
+    uint32_t np2 = 1; while (np2 < nv) np2 <<= 1;
     for (uint32_t i = nv + threadIdx.x; i < np2; i += blockDim.x) sv[i] = INT_MAX;
     __syncthreads();
     for (uint32_t k = 2; k <= np2; k <<= 1)
@@ -394,19 +482,13 @@ __global__ void __launch_bounds__(256) k_candidates(PdDev a, CandArgs ca, int mo
     if (threadIdx.x == 0) {
         // genotype_deletion_popdel_call.h:62-84; thresholds are indexed by RANK in the sorted array (quirk)
         int sum = sv[0], n = 1;
-        uint32_t thr = ca.min_init[0], nc = 0;
-        const uint32_t pair0 = mode == 1 ? ca.cand_off[job] : 0;
-        auto emit = [&](int mean) {
-            if (mode == 0) { if (nc < (uint32_t)PD_CAND_INLINE) ca.cand_inline[(size_t)job * PD_CAND_INLINE + nc] = mean; }
-            else if (pair0 + nc < ca.pair_cap) ca.pairs[pair0 + nc] = PdPair{ca.job_base + job, mean};
-            ++nc;
-        };
+        uint32_t thr = ca.min_init[0];
         for (uint32_t i = 1; i < nv; ++i) {
             if (sv[i - 1] + 50 > sv[i]) { sum += sv[i]; ++n; thr = min(thr, ca.min_init[i]); }
             else { if (sum / n > (int)thr) emit(sum / n); sum = sv[i]; n = 1; thr = ca.min_init[i]; }
         }
         if (sum / n > (int)thr) emit(sum / n);
-        if (mode == 0) ca.cand_cnt[job] = nc;
+        if (mode == 0) ca.cand_cnt[job] = emit.nc;
     }
 }
 

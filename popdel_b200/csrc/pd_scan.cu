@@ -242,6 +242,7 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
         memset(&ca, 0, sizeof(ca));
         ca.nparts = 1; ca.q3[0] = ga.q3; ca.sstat[0] = ga.sstat; ca.part_n[0] = N; ca.min_init = c->d_min_init;
         ca.njobs = nj; ca.job_base = job_base; ca.counters = d_counters; ca.block_sums = d_bsums; ca.npad = npad;
+        ca.force_sort = (slow_env >> 2) & 1u;
         int32_t * all_q3 = nullptr; uint8_t * all_ss = nullptr;
         if (sh) {
             if (grow_scratch(c, S_ALL_Q3, all_q3, (size_t)nj * Nb * sh->world)) return c->status;

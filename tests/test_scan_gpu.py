@@ -89,7 +89,7 @@ def test_many_samples(n_samples, contig_len, oracle_lib):
     assert stats["n_calls"] > 20
 
 
-@pytest.mark.parametrize("env", [{"PD_FORCE_SLOW": "3"}, {"PD_JOB_BATCH": "64", "PD_CJOB_ROWS": "7"}, {"PD_CJOB_ROWS": "1", "PD_EM_CHUNK": "5"},
+@pytest.mark.parametrize("env", [{"PD_FORCE_SLOW": "7"}, {"PD_JOB_BATCH": "64", "PD_CJOB_ROWS": "7"}, {"PD_CJOB_ROWS": "1", "PD_EM_CHUNK": "5"},
                                  {"PD_EM_GENERAL": "1"}])
 @pytest.mark.parametrize("kind", ["basic", "mixedrg", "highcov"])
 def test_scan_generic_paths_and_batching(kind, env, oracle_lib, monkeypatch):
