@@ -248,7 +248,8 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32 (screen) / f64 (likelihoods)", "data": "synthetic",
         "config": {"workload": f"{N} synthetic profiles x chr21-sized window range ({L} bp, {res['n_windows']} windows of 30 bp) "
-                               f"per GPU, single read group each, 30x, planted deletions {args.dels_per_mbp}/Mbp",
+                               f"per GPU, {'1-3 read groups per sample with mixed insert-size histograms' if args.mixed else 'single read group each'}, "
+                               f"30x, planted deletions {args.dels_per_mbp}/Mbp",
                    "samples": N, "read_groups": R, "windows_per_gpu": int(res["n_windows"]), "read_pairs_per_gpu": int(res["n_reads"]),
                    "parallelism": f"window-range x{world}", "l2": "inputs (%.2f GB packed words) larger than the 126 MB L2" % (res["algorithmic_bytes"] / 1e9),
                    "calls_per_step": int(len(res["calls"])), "flagged_windows": int(res["n_flagged_windows"]),

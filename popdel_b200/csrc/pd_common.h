@@ -98,11 +98,13 @@ struct TileSeg { uint32_t base_bp; uint32_t nb; int32_t wlA, wlB, wlC; };
 
 PD_HD TileSeg tile_seg(uint32_t tile, uint32_t wb)
 {
+    // positions are 32-bit, so tile * 960 fits 32 bits and the only division by a run-time value is a 32-bit one
+    // (this runs once per (warp, read group, tile) in the gather / count kernels)
     TileSeg t;
-    uint64_t base = (uint64_t)tile * PD_TILE_BP;
-    uint64_t j0 = base / wb;
-    uint64_t nb = (j0 + 1) * wb;
-    t.base_bp = (uint32_t)base;
+    uint32_t base = tile * PD_TILE_BP;
+    uint32_t j0 = base / wb;
+    uint64_t nb = ((uint64_t)j0 + 1) * wb;
+    t.base_bp = base;
     t.nb = (uint32_t)nb;
     t.wlA = (int32_t)((nb - 1) / PD_WIN);
     t.wlB = (int32_t)((nb + wb - 1) / PD_WIN);

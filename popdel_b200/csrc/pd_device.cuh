@@ -21,7 +21,7 @@ constexpr uint32_t PD_GRAN = 1024;                  // words per warp in k_strea
 constexpr int PD_CAND_INLINE = 6;                   // candidate lengths kept inline per window job
 
 // device counters of one scan (uint32 each)
-enum { CNT_TJOBS = 0, CNT_JOBS = 1, CNT_PAIRS = 2, CNT_POOL = 3, CNT_CALLS = 4, CNT_CJOBS = 5, CNT_N = 16 };
+enum { CNT_TJOBS = 0, CNT_JOBS = 1, CNT_PAIRS = 2, CNT_POOL = 3, CNT_CALLS = 4, CNT_CJOBS = 5, CNT_ERR = 6, CNT_N = 16 };
 
 struct PdPair { uint32_t job; int32_t L0; };                         // (window job, initial deletion length)
 struct EmState { uint32_t len, it, alive, pad; double freq; double gt[3]; };   // handed from k_em to k_final
@@ -112,6 +112,7 @@ struct EmArgs {
     uint32_t * ps;           // [pair][N][13]  per-sample output rows
     pd_call * calls;         // [pair]
     uint8_t * valid;         // [pair]
+    uint32_t * done;         // [pair] set (release) when valid / calls / ps of the pair are final
     EmState * states;        // [pair]
     uint32_t iterations, min_len; double min_lr, min_sample_fraction; int somatic, window_wise; uint32_t anchor;
     uint32_t * dbg;          // optional [npairs][4]: reason, len, iterations, supp (PD_DEBUG)
@@ -121,14 +122,14 @@ struct EmArgs {
 };
 struct EmitArgs {
     const uint8_t * valid; const pd_call * calls; const uint32_t * ps; uint32_t npairs, row_words;
-    uint32_t * counters;                // CNT_CALLS = calls emitted so far
-    uint32_t * chunk_base;              // device scalar: first output slot of this chunk
+    const uint32_t * done;              // [pair] published by the EM kernels
+    uint32_t * counters;                // CNT_CALLS = calls emitted so far, CNT_ERR = the emitter gave up waiting
+    uint32_t * emit_blocks_done;        // device scalar (0 between launches)
     pd_call * out_calls; uint32_t * out_ps; uint32_t * out_count;   // mapped page-locked host memory
 };
 int  pd_launch_em(pd_ctx * c, const PdDev & a, const EmArgs & e, cudaStream_t st, uint64_t * launches);
 int  pd_em_preload_xr(pd_ctx * c);
-void pd_launch_emit_count(const EmitArgs & m, cudaStream_t st, uint64_t * launches);
-void pd_launch_emit_rows(const EmitArgs & m, cudaStream_t st, uint64_t * launches);
+void pd_launch_emit(const EmitArgs & m, cudaStream_t st, uint64_t * launches);
 
 #if defined(__CUDACC__)
 // ---------------------------------------------------------------------------------------------------------------
@@ -165,24 +166,40 @@ __device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long
 
 // calls f(valid, s, e, pos_rel, dev) for every 32-wide batch of read pairs of read group g whose active interval can
 // intersect the windows of `tile` (stream words of the look-back tiles in stream order, then the wide list).
-// `valid` marks lanes holding a real, ever-active read pair; the caller tests the interval.
+// `valid` marks lanes holding a real, ever-active read pair; the caller tests the interval. Must be called by all 32
+// lanes. The look-back tiles are contiguous in the stream: lane j holds the table entry and segment constants of tile
+// t_lo + j (ONE load phase instead of one per tile), the words are walked as one flat range with the next batch
+// already in flight, and every lane finds the tile of its word among the <= 9 tile borders by shuffles.
 template <typename F>
 __device__ __forceinline__ void for_tile_batches(const PdDev & a, uint32_t g, const PdRgConst & k, uint32_t tile, int lane, F f)
 {
     const PdTile * tl = a.tiles + (size_t)g * (a.NT + 1);
     const uint32_t t_lo = tile > k.lookback_tiles ? tile - k.lookback_tiles : 0;
-    for (uint32_t tt = t_lo; tt <= tile; ++tt) {
-        const TileSeg ts = tile_seg(tt, a.window_buffer);
-        const uint32_t r_lo = __ldg(&tl[tt].off), r_hi = __ldg(&tl[tt + 1].off);
-        for (uint32_t base = r_lo; base < r_hi; base += 32) {
-            const uint32_t i = base + lane;
-            const uint32_t word = i < r_hi ? __ldg(a.words + i) : PD_PAD_WORD;
-            int32_t s = 0, e = 0, dev = 0; uint32_t pr = 0;
-            const bool valid = word_interval(word, ts, k.inner_off, s, e, dev, pr);
-            f(valid, s, e, pr, dev);
-        }
+    const uint32_t nt = tile - t_lo + 1;                              // <= PD_MAX_LOOKBACK_TILES + 1
+    PdTile mine = PdTile{0xFFFFFFFFu, 0, 0, 0};
+    if ((uint32_t)lane <= nt) mine = load_tile(&tl[t_lo + lane]);
+    const uint32_t r_lo = __shfl_sync(PD_FULL, mine.off, 0), r_hi = __shfl_sync(PD_FULL, mine.off, (int)nt);
+    const uint32_t l_lo = __shfl_sync(PD_FULL, mine.long_lo, (int)nt - 1), l_hi = __shfl_sync(PD_FULL, mine.long_hi, (int)nt - 1);
+    // borders 1..3 in registers (warp-uniform); 0xFFFFFFFF beyond the look-back
+    const uint32_t b1 = nt > 1 ? __shfl_sync(PD_FULL, mine.off, 1) : 0xFFFFFFFFu;
+    const uint32_t b2 = nt > 2 ? __shfl_sync(PD_FULL, mine.off, 2) : 0xFFFFFFFFu;
+    const uint32_t b3 = nt > 3 ? __shfl_sync(PD_FULL, mine.off, 3) : 0xFFFFFFFFu;
+    // the segment constants of the look-back tiles differ only in base_bp unless a segment border lies between them
+    const TileSeg ts_lo = tile_seg(t_lo, a.window_buffer), ts_hi = nt > 1 ? tile_seg(tile, a.window_buffer) : ts_lo;
+    const bool one_seg = ts_lo.nb == ts_hi.nb;
+    uint32_t next = (r_lo + lane) < r_hi ? __ldg(a.words + r_lo + lane) : PD_PAD_WORD;
+    for (uint32_t base = r_lo; base < r_hi; base += 32) {
+        const uint32_t i = base + lane, word = next;
+        if (base + 32 < r_hi) next = (i + 32) < r_hi ? __ldg(a.words + i + 32) : PD_PAD_WORD;
+        uint32_t kk = (uint32_t)(i >= b1) + (uint32_t)(i >= b2) + (uint32_t)(i >= b3);      // tile of word i = t_lo + borders <= i
+        for (uint32_t j = 4; j < nt; ++j) kk += __shfl_sync(PD_FULL, mine.off, (int)j) <= i;
+        TileSeg ts = ts_hi;
+        if (one_seg) ts.base_bp = (t_lo + kk) * PD_TILE_BP;
+        else ts = tile_seg(t_lo + kk, a.window_buffer);
+        int32_t s = 0, e = 0, dev = 0; uint32_t pr = 0;
+        const bool valid = word_interval(word, ts, k.inner_off, s, e, dev, pr);
+        f(valid, s, e, pr, dev);
     }
-    const uint32_t l_lo = __ldg(&tl[tile].long_lo), l_hi = __ldg(&tl[tile].long_hi);
     for (uint32_t base = l_lo; base < l_hi; base += 32) {
         const uint32_t i = base + lane;
         PdLong L = PdLong{0xFFFFFFFFu, 0, 0, 0};

@@ -533,6 +533,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_final(PdDev a, EmArgs e)
     __shared__ uint32_t s_first[SUPP_CAP], s_last[SUPP_CAP];
     __shared__ uint32_t s_nsupp;
     final_body<LPS, false>(a, e, sh, s_first, s_last, s_nsupp, blockIdx.x);
+    publish_done(e, blockIdx.x);
 }
 template <int LPS, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_final_xr(PdDev a, EmArgs e)
@@ -547,6 +548,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_final_xr(PdDev a, EmArgs e)
         const uint32_t bid = s_bid;
         if (bid >= e.npairs) return;
         final_body<LPS, true>(a, e, sh, s_first, s_last, s_nsupp, bid);
+        publish_done(e, bid);
     }
 }
 
@@ -619,14 +621,10 @@ __device__ __forceinline__ void dl_one(const RgOne & k, const int32_t * cache_d,
     }
 }
 
-template <int LPS, int SLOTS, int BATCH, bool PREF, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) k_em_one(PdDev a, EmArgs e)
+template <int LPS, int SLOTS, int BATCH, bool PREF>
+__device__ __forceinline__ void em_one_body(const PdDev & a, const EmArgs & e, EmShared & sh, uint32_t * s_first, uint32_t * s_last,
+                                            uint32_t & s_nsupp, uint16_t * s_perm, int32_t * cache_dev)
 {
-    __shared__ EmShared sh;
-    __shared__ uint32_t s_first[SUPP_CAP], s_last[SUPP_CAP];
-    __shared__ uint32_t s_nsupp;
-    __shared__ uint16_t s_perm[256];
-    extern __shared__ int32_t cache_dev[];              // [SLOTS][T] deviations of this block's read pairs
     const int tid = threadIdx.x, T = blockDim.x, sub = tid % LPS;
     const uint32_t gmask = group_mask<LPS>();
     const uint32_t pi = e.pair0 + blockIdx.x;
@@ -928,35 +926,95 @@ __global__ void __launch_bounds__(MAXT, MINB) k_em_one(PdDev a, EmArgs e)
     }
 }
 
+template <int LPS, int SLOTS, int BATCH, bool PREF, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_em_one(PdDev a, EmArgs e)
+{
+    __shared__ EmShared sh;
+    __shared__ uint32_t s_first[SUPP_CAP], s_last[SUPP_CAP];
+    __shared__ uint32_t s_nsupp;
+    __shared__ uint16_t s_perm[256];
+    extern __shared__ int32_t cache_dev[];              // [SLOTS][T] deviations of this block's read pairs
+    em_one_body<LPS, SLOTS, BATCH, PREF>(a, e, sh, s_first, s_last, s_nsupp, s_perm, cache_dev);
+    publish_done(e, blockIdx.x);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // emission: calls of a chunk in pair order -> mapped host memory
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_emit_count(EmitArgs m, uint32_t * out_count)
+// One kernel per EM chunk on the second stream, CONCURRENT with the chunk's EM launch: a few blocks walk the pairs in
+// order in batches of one pair per warp, wait until every pair up to the end of their batch has published `done`
+// (acquire), number the valid pairs in pair order (= the reference's call order) and copy call header + per-sample
+// row into mapped host memory over PCIe while the EM of later pairs is still running. The last block to finish
+// advances the call counter for the next chunk.
+constexpr int EMIT_BLOCKS = 12, EMIT_WARPS = 16;
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t * p)
 {
-    __shared__ unsigned long long ws[33];
-    unsigned long long v = 0, total;
-    for (uint32_t i = threadIdx.x; i < m.npairs; i += 1024) v += m.valid[i] != 0;
-    block_excl_scan(v, ws, total);
-    if (threadIdx.x == 0) {
-        const uint32_t base = m.counters[CNT_CALLS];
-        *m.chunk_base = base;
-        m.counters[CNT_CALLS] = base + (uint32_t)total;
-        *out_count = base + (uint32_t)total;
-    }
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
-__global__ void __launch_bounds__(256) k_emit_rows(EmitArgs m)
+
+__global__ void __launch_bounds__(EMIT_WARPS * 32) k_emit_stream(EmitArgs m)
 {
-    __shared__ unsigned long long ws[33];
-    const uint32_t b = blockIdx.x;
-    if (!m.valid[b]) return;
-    unsigned long long v = 0, total;
-    for (uint32_t i = threadIdx.x; i < b; i += 256) v += m.valid[i] != 0;
-    block_excl_scan(v, ws, total);
-    const size_t slot = (size_t)*m.chunk_base + (size_t)total;
-    if (threadIdx.x == 0) m.out_calls[slot] = m.calls[b];
-    const uint32_t * src = m.ps + (size_t)b * m.row_words;
-    uint32_t * dst = m.out_ps + slot * m.row_words;
-    for (uint32_t i = threadIdx.x; i < m.row_words; i += 256) dst[i] = src[i];
+    __shared__ uint32_t s_cnt[EMIT_WARPS];
+    __shared__ uint32_t s_last;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t base0 = m.counters[CNT_CALLS];            // calls emitted by the earlier chunks (advanced by the LAST block only)
+    uint32_t ready = 0, counted = 0, below = 0;              // pairs known done / pairs counted / valid pairs among the counted
+    for (uint32_t lo = blockIdx.x * EMIT_WARPS; lo < m.npairs; lo += gridDim.x * EMIT_WARPS) {
+        const uint32_t hi = min(lo + (uint32_t)EMIT_WARPS, m.npairs);
+        // ---- wait until pairs [0, hi) are final
+        const long long t0 = clock64();
+        for (;;) {
+            bool ok = true;
+            for (uint32_t i = ready + tid; i < hi; i += blockDim.x) ok = ok && ld_acquire_gpu(m.done + i) != 0;
+            if (__syncthreads_and(ok)) break;
+            const bool bad = *(volatile uint32_t *)(m.counters + CNT_ERR) != 0 || clock64() - t0 > 20000000000ll;     // ~10 s: EM kernel gone
+            if (__syncthreads_or(bad)) { if (tid == 0) atomicExch(m.counters + CNT_ERR, 1u); return; }
+            __nanosleep(200);
+        }
+        ready = hi;
+        // ---- valid pairs below the batch
+        uint32_t c = 0;
+        for (uint32_t i = counted + tid; i < lo; i += blockDim.x) c += m.valid[i] != 0;
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(PD_FULL, c, o);
+        __syncthreads();
+        if (lane == 0) s_cnt[wid] = c;
+        __syncthreads();
+        for (int w = 0; w < EMIT_WARPS; ++w) below += s_cnt[w];
+        counted = lo;
+        // ---- one warp per pair of the batch
+        const uint32_t b = lo + wid;
+        uint32_t before = 0;
+        for (uint32_t i = lo; i < min(b, hi); ++i) before += m.valid[i] != 0;
+        if (b < hi && m.valid[b]) {
+            const size_t slot = (size_t)base0 + below + before;
+            if (lane == 0) m.out_calls[slot] = m.calls[b];
+            const uint4 * src = reinterpret_cast<const uint4 *>(m.ps + (size_t)b * m.row_words);
+            uint32_t * dst = m.out_ps + slot * m.row_words;
+            const uint32_t n4 = ((size_t)b * m.row_words % 4 == 0 && (slot * m.row_words) % 4 == 0) ? m.row_words / 4 : 0;
+            for (uint32_t i = lane; i < n4; i += 32) reinterpret_cast<uint4 *>(dst)[i] = src[i];
+            for (uint32_t i = n4 * 4 + lane; i < m.row_words; i += 32) dst[i] = m.ps[(size_t)b * m.row_words + i];
+        }
+    }
+    // ---- the last block to finish publishes the new total (every block has read base0 by then)
+    __syncthreads();
+    if (tid == 0) { __threadfence(); s_last = atomicAdd(m.emit_blocks_done, 1u) == gridDim.x - 1; }
+    __syncthreads();
+    if (!s_last) return;
+    uint32_t c = 0;
+    for (uint32_t i = tid; i < m.npairs; i += blockDim.x) c += m.valid[i] != 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(PD_FULL, c, o);
+    if (lane == 0) s_cnt[wid] = c;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < EMIT_WARPS; ++w) tot += s_cnt[w];
+        m.counters[CNT_CALLS] = base0 + tot;
+        *m.out_count = base0 + tot;
+        *m.emit_blocks_done = 0;
+    }
 }
 
 template <int LPS, int SLOTS, int MAXT, int MINB>
@@ -1007,8 +1065,7 @@ int pd_em_preload_xr(pd_ctx * c)
     PD_CUDA(c, cudaFuncGetAttributes(&fa, k_em_xr<2, 16, 512, 2>));
     PD_CUDA(c, cudaFuncGetAttributes(&fa, k_final_xr<4, 512, 2>));
     PD_CUDA(c, cudaFuncGetAttributes(&fa, k_final_xr<2, 512, 2>));
-    PD_CUDA(c, cudaFuncGetAttributes(&fa, k_emit_count));
-    PD_CUDA(c, cudaFuncGetAttributes(&fa, k_emit_rows));
+    PD_CUDA(c, cudaFuncGetAttributes(&fa, k_emit_stream));
     return 0;
 }
 
@@ -1063,13 +1120,9 @@ int pd_launch_em(pd_ctx * c, const PdDev & a, const EmArgs & e, cudaStream_t st,
     return 0;
 }
 
-void pd_launch_emit_count(const EmitArgs & m, cudaStream_t st, uint64_t * launches)
+void pd_launch_emit(const EmitArgs & m, cudaStream_t st, uint64_t * launches)
 {
-    k_emit_count<<<1, 1024, 0, st>>>(m, m.out_count);
-    ++*launches;
-}
-void pd_launch_emit_rows(const EmitArgs & m, cudaStream_t st, uint64_t * launches)
-{
-    k_emit_rows<<<m.npairs, 256, 0, st>>>(m);
+    const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(EMIT_BLOCKS, (m.npairs + EMIT_WARPS - 1) / EMIT_WARPS));
+    k_emit_stream<<<grid, EMIT_WARPS * 32, 0, st>>>(m);
     ++*launches;
 }

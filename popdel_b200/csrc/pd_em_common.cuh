@@ -161,6 +161,15 @@ __device__ __forceinline__ void xr_minmax(const XrArgs & x, XrBlock & xb, EmShar
     }
 }
 
+// every exit of the EM / final-pass bodies leaves valid / calls / ps of the pair final: publish that to the concurrent
+// emitter (k_emit_stream)
+__device__ __forceinline__ void publish_done(const EmArgs & e, uint32_t bid)
+{
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(e.done + bid), "r"(1u) : "memory");
+}
+
 // Normalises three log-likelihood sums like the reference (:235-251): subtract the maximum, apply the long-double
 // tie-break of `ndeg` read pairs with ref == del to the heterozygous sum, then the two overrides.
 __device__ __forceinline__ void finish_triple(double l0, double l1, double l2, uint32_t ndeg, double & x0, double & x1, double & x2)

@@ -46,12 +46,9 @@ __device__ __forceinline__ int32_t q3_value(uint32_t nn, double r, int32_t lo_v,
 // K2a: Q3 of every (flagged window, sample)
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int TQ_WARPS = 4;
-constexpr int TQ_STAGE = 320;                                       // staged read pairs per read group and tile
 constexpr int TQ_ACT = 48;                                          // usable active read pairs per (window, sample), fast path
 
 struct alignas(16) WarpQ3 {
-    uint32_t se[TQ_STAGE];                                          // first | last << 8 window of the tile the pair is active in
-    int32_t dev[TQ_STAGE];
     int32_t val[TQ_ACT][32];                                        // [slot][window]: deviations of the window's usable active pairs
     uint32_t cnt[32];
 };
@@ -115,7 +112,7 @@ __device__ __noinline__ void q3_window_slow(const PdDev & a, const GatherArgs & 
     if (lane == 0) write_q3(ga, a.N, job, smp, cov, n, q, mx);
 }
 
-__global__ void __launch_bounds__(TQ_WARPS * 32) k_tile_q3(PdDev a, GatherArgs ga)
+__global__ void __launch_bounds__(TQ_WARPS * 32, 9) k_tile_q3(PdDev a, GatherArgs ga)
 {
     __shared__ WarpQ3 sh_all[TQ_WARPS];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -132,38 +129,25 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) k_tile_q3(PdDev a, GatherArgs g
 
     sh.cnt[lane] = 0;
     uint32_t cov = 0;
-    bool slow = (ga.debug_flags & 1u) != 0;
+    const bool slow = (ga.debug_flags & 1u) != 0;
     __syncwarp();
     for (uint32_t g = g0; g < g1 && !slow; ++g) {
         const PdRgConst k = a.rgc[g];
-        // ---- stage this read group's pairs whose interval meets a flagged window of the tile
-        uint32_t total = 0;
-        for_tile_batches(a, g, k, tile, lane, [&](bool valid, int32_t s, int32_t e, uint32_t, int32_t dev) {
-            uint32_t m = 0, sr = 0, er = 0;
-            if (valid && e >= w0 && s <= w0 + 31) {
-                sr = (uint32_t)max(s - w0, 0); er = (uint32_t)min(e - w0, 31);
-                m = wmask & (er == 31u ? 0xFFFFFFFFu : ((1u << (er + 1)) - 1u)) & ~((1u << sr) - 1u);
-            }
-            const uint32_t mask = __ballot_sync(PD_FULL, m != 0);
-            const uint32_t slot = total + __popc(mask & (lane_bit - 1u));
-            if (m && slot < (uint32_t)TQ_STAGE) { sh.se[slot] = sr | (er << 8); sh.dev[slot] = dev; }
-            total += __popc(mask);
-        });
-        if (total > (uint32_t)TQ_STAGE) { slow = true; break; }
         const uint32_t before = sh.cnt[lane];
         __syncwarp();
-        // ---- scatter: every pair appends its deviation to the lists of the flagged windows it is active in
-        for (uint32_t i = lane; i < total; i += 32) {
-            const uint32_t se = sh.se[i], sr = se & 0xFFu, er = se >> 8;
-            const int32_t dev = sh.dev[i];
-            uint32_t m = wmask & (er == 31u ? 0xFFFFFFFFu : ((1u << (er + 1)) - 1u)) & ~((1u << sr) - 1u);
-            while (m) {
-                const int w = __ffs(m) - 1;
-                m &= m - 1;
-                const uint32_t slot = atomicAdd(&sh.cnt[w], 1u);
-                if (slot < (uint32_t)TQ_ACT) sh.val[slot][w] = dev;
+        // every read pair appends its deviation to the lists of the flagged windows it is active in
+        for_tile_batches(a, g, k, tile, lane, [&](bool valid, int32_t s, int32_t e, uint32_t, int32_t dev) {
+            if (valid && e >= w0 && s <= w0 + 31) {
+                const uint32_t sr = (uint32_t)max(s - w0, 0), er = (uint32_t)min(e - w0, 31);
+                uint32_t m = wmask & (er == 31u ? 0xFFFFFFFFu : ((1u << (er + 1)) - 1u)) & ~((1u << sr) - 1u);
+                while (m) {
+                    const int w = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t slot = atomicAdd(&sh.cnt[w], 1u);
+                    if (slot < (uint32_t)TQ_ACT) sh.val[slot][w] = dev;
+                }
             }
-        }
+        });
         __syncwarp();
         const uint32_t n_g = sh.cnt[lane] - before;
         cov += n_g;

@@ -128,6 +128,16 @@ static int upload_static(pd_ctx * c)
     return 0;
 }
 
+// stream2 carries the result emitter, which runs concurrently with the EM kernels: its few blocks should get an SM as
+// soon as one has room
+static cudaError_t create_priority_stream(cudaStream_t * s)
+{
+    int lo = 0, hi = 0;
+    cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (e != cudaSuccess) return e;
+    return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, hi);
+}
+
 extern "C" pd_ctx * pd_create(const pd_params * p, uint32_t n_samples, uint32_t n_rg, const pd_rg * rgs, int device)
 {
     g_create_error.clear();
@@ -183,7 +193,7 @@ extern "C" pd_ctx * pd_create(const pd_params * p, uint32_t n_samples, uint32_t 
             delete c; return nullptr;
         }
         if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) {
+            create_priority_stream(&c->stream2) != cudaSuccess) {
             g_create_error = "pd_create: cudaSetDevice/cudaStreamCreate failed"; delete c; return nullptr;
         }
         for (auto & ev : c->ev) cudaEventCreate(&ev);

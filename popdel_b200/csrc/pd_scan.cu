@@ -19,7 +19,7 @@ namespace {
 enum Slot {                                     // d_scratch slots
     S_NEED = 0, S_TFLAGS, S_COUNTERS, S_TJ_TILE, S_TJ_MASK, S_TJ_WBASE, S_JOBWIN, S_BSUMS,
     S_ACT_OFF, S_ACT_CNT, S_Q3, S_SSTAT, S_CAND_CNT, S_CAND_INL, S_CAND_OFF, S_CJOB_OF, S_TJ_CMASK, S_TJ_CFIRST, S_PAIRS, S_POOL_POS, S_POOL_DEV,
-    S_DLX, S_DLE, S_SHIFTS, S_STATES, S_PS0, S_PS1, S_CALLS0, S_CALLS1, S_VALID0, S_VALID1, S_CHUNK_BASE, S_DBG, S_DMAX, S_ALL_Q3, S_ALL_SS
+    S_DLX, S_DLE, S_SHIFTS, S_STATES, S_PS0, S_PS1, S_CALLS0, S_CALLS1, S_VALID0, S_VALID1, S_DONE0, S_DONE1, S_CHUNK_BASE, S_DBG, S_DMAX, S_ALL_Q3, S_ALL_SS
 };
 
 template <typename T>
@@ -196,7 +196,9 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
     uint32_t npad = 1; while (npad < Ng) npad <<= 1;
     if ((size_t)npad * 4 > 200 * 1024) return pd_fail(c, PD_ERR_CAPACITY, "more than 51200 samples per context: candidate sort does not fit shared memory (shard by sample)");
     const size_t pair_bytes = 48ull * Nb + 4ull * Rb + 2 * 52ull * Nb + 128;
-    const uint32_t CH = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(2000000000ull / pair_bytes, 64), getenv("PD_EM_CHUNK") ? atoi(getenv("PD_EM_CHUNK")) : 8192);
+    const uint32_t CH = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(2000000000ull / pair_bytes, 64), getenv("PD_EM_CHUNK") ? atoi(getenv("PD_EM_CHUNK")) : 16384);
+    // (measured on B200, 100 samples x chr21: tapering costs more in small EM launches than it saves in the tail -> off by default)
+    const uint32_t taper_min = std::min<uint32_t>(CH, getenv("PD_EM_TAPER") ? std::max(1, atoi(getenv("PD_EM_TAPER"))) : CH);
     XrArgs xr;
     memset(&xr, 0, sizeof(xr));
     if (sh) {
@@ -214,8 +216,9 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
         h_jobwin.resize(n_jobs);
         PD_CUDA(c, cudaMemcpy(h_jobwin.data(), j.job_window, (size_t)n_jobs * 4, cudaMemcpyDeviceToHost));
     }
-    uint32_t * d_chunk_base;
-    if (grow_scratch(c, S_CHUNK_BASE, d_chunk_base, (size_t)4)) return c->status;
+    uint32_t * d_emit_state;
+    if (grow_scratch(c, S_CHUNK_BASE, d_emit_state, (size_t)4)) return c->status;
+    PD_CUDA(c, cudaMemsetAsync(d_emit_state, 0, 16, st));
 
     for (uint32_t tj0 = 0; tj0 < n_tj;) {
         // batch = tile jobs [tj0, tj1) with at most JB window jobs
@@ -337,8 +340,11 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
                 }
             }
             // ---- pairs in chunks: the emission of chunk k (stream2) overlaps the EM of chunk k+1 (stream)
-            for (uint32_t p0 = pA; p0 < pB; p0 += CH, ++chunk_no) {
-                const uint32_t np = std::min(CH, pB - p0);
+            // Optional (PD_EM_TAPER): chunk sizes taper off (3/4 of what is left) so that the emission of the LAST chunk,
+            // which no EM launch hides, is small. Deterministic in (pairs, CH): identical on every rank.
+            for (uint32_t p0 = pA, np = 0; p0 < pB; p0 += np, ++chunk_no) {
+                const uint32_t left = pB - p0;
+                np = std::min(CH, left <= taper_min + taper_min / 2 ? left : std::max(taper_min, (uint32_t)((uint64_t)left * 3 / 4 / taper_min * taper_min)));
                 const int par = (int)(chunk_no & 1);
                 EmArgs e;
                 if (grow_scratch(c, S_DLX, e.dlx, (size_t)CH * 3 * N)) return c->status;
@@ -350,6 +356,7 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
                 if (grow_scratch(c, S_PS0 + par, e.ps, (size_t)CH * row)) return c->status;
                 if (grow_scratch(c, S_CALLS0 + par, e.calls, (size_t)CH)) return c->status;
                 if (grow_scratch(c, S_VALID0 + par, e.valid, (size_t)CH + 16)) return c->status;
+                if (grow_scratch(c, S_DONE0 + par, e.done, (size_t)CH)) return c->status;
                 e.job_window = j.job_window; e.pairs = ca.pairs; e.pair0 = p0; e.npairs = np; e.job_base = job_base;
                 e.pool_pos = ga.pool_pos; e.pool_dev = ga.pool_dev; e.act_off = ga.act_off; e.act_cnt = ga.act_cnt; e.sstat = ga.sstat; e.dmax = ga.dmax;
                 e.cjob_of = ca.cjob_of; e.cj_base = cj_lo;
@@ -365,9 +372,29 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
                     PD_CUDA(c, cudaMemsetAsync(e.dbg, 0xFF, (size_t)np * 16, st));
                 }
                 PD_CUDA(c, cudaMemsetAsync(e.valid, 0, np, st));
-                if (sh && pd_shard_prelaunch(c)) return c->status;
-                if (pd_launch_em(c, a, e, st, nl)) return c->status;
+                PD_CUDA(c, cudaMemsetAsync(e.done, 0, (size_t)np * 4, st));
+                // result capacity: upper bound = calls emitted so far (exact once stream2 is drained) + this chunk
+                const size_t upper = (size_t)(n_pairs_total - n_pairs + p0 + np);
+                if (upper > c->cap_res_calls || upper * row > c->cap_res_ps) {
+                    PD_CUDA(c, cudaStreamSynchronize(st2));
+                    const size_t have = c->res_count[0];
+                    if (ensure_results(c, have + np, row, have)) return c->status;
+                }
+                // the emitter of this chunk starts on stream2 as soon as the flags are cleared and runs CONCURRENTLY with
+                // the EM launch below, copying finished pairs to the host in pair order while later pairs are computed
                 PD_CUDA(c, cudaEventRecord(c->ev[6 + par], st));
+                EmitArgs m;
+                m.valid = e.valid; m.calls = e.calls; m.ps = e.ps; m.npairs = np; m.row_words = (uint32_t)row; m.done = e.done;
+                m.counters = d_counters; m.emit_blocks_done = d_emit_state;
+                m.out_calls = c->res_calls; m.out_ps = c->res_ps; m.out_count = c->res_count;
+                if (sh && pd_shard_prelaunch(c)) return c->status;
+                // (EM first: CUDA loads kernels lazily and a first-time load may wait for running kernels -- the emitter,
+                // which only waits for ev[6], must never be the one that is running while the EM kernel is being loaded)
+                if (pd_launch_em(c, a, e, st, nl)) return c->status;
+                PD_CUDA(c, cudaStreamWaitEvent(st2, c->ev[6 + par], 0));
+                pd_launch_emit(m, st2, nl);
+                PD_CUDA(c, cudaGetLastError());
+                PD_CUDA(c, cudaEventRecord(c->ev[8 + par], st2));
                 if (dbg) {
                     std::vector<uint32_t> hd((size_t)np * 4);
                     PD_CUDA(c, cudaMemcpyAsync(hd.data(), e.dbg, (size_t)np * 16, cudaMemcpyDeviceToHost, st));
@@ -376,22 +403,6 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
                         fprintf(stderr, "PD_DEBUG pair window %u L0 %d reason %u len %u it %u supp %u\n", h_jobwin[h_pairs[p0 + i].job],
                                 h_pairs[p0 + i].L0, hd[4 * i], hd[4 * i + 1], hd[4 * i + 2], hd[4 * i + 3]);
                 }
-                // result capacity: upper bound = calls emitted so far (exact once stream2 is drained) + this chunk
-                const size_t upper = (size_t)(n_pairs_total - n_pairs + p0 + np);
-                if (upper > c->cap_res_calls || upper * row > c->cap_res_ps) {
-                    PD_CUDA(c, cudaStreamSynchronize(st2));
-                    const size_t have = c->res_count[0];
-                    if (ensure_results(c, have + np, row, have)) return c->status;
-                }
-                EmitArgs m;
-                m.valid = e.valid; m.calls = e.calls; m.ps = e.ps; m.npairs = np; m.row_words = (uint32_t)row;
-                m.counters = d_counters; m.chunk_base = d_chunk_base;
-                m.out_calls = c->res_calls; m.out_ps = c->res_ps; m.out_count = c->res_count;
-                PD_CUDA(c, cudaStreamWaitEvent(st2, c->ev[6 + par], 0));
-                pd_launch_emit_count(m, st2, nl);
-                pd_launch_emit_rows(m, st2, nl);
-                PD_CUDA(c, cudaGetLastError());
-                PD_CUDA(c, cudaEventRecord(c->ev[8 + par], st2));
             }
         }
         // the next batch overwrites the Q3 / pool / active-set tables that the EM kernels of this batch read: stream
@@ -401,6 +412,8 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
     PD_CUDA(c, cudaEventRecord(c->ev[5], st));
     PD_CUDA(c, cudaStreamSynchronize(st));
     PD_CUDA(c, cudaStreamSynchronize(st2));
+    PD_CUDA(c, cudaMemcpy(h_cnt, d_counters, CNT_N * 4, cudaMemcpyDeviceToHost));
+    if (h_cnt[CNT_ERR]) return pd_fail(c, PD_ERR_CUDA, "the result emitter gave up waiting for the EM kernels");
     if (sh) {
         uint32_t xerr = 0;
         PD_CUDA(c, cudaMemcpy(&xerr, sh->d_err, 4, cudaMemcpyDeviceToHost));

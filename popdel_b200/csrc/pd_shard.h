@@ -4,7 +4,7 @@
 
 #include "pd_device.cuh"
 
-#define PD_XR_PAIRS 8192u             /* pairs per EM launch the exchange slots hold (= largest EM chunk) */
+#define PD_XR_PAIRS 16384u            /* pairs per EM launch the exchange slots hold (= largest EM chunk) */
 
 struct PdGroup;
 struct PdShard {
