@@ -13,6 +13,7 @@
 //   -u       unsmoothed histograms          -x  uncompressed profiles                -C  cell-population priors
 //   -g NUM   CUDA device (0)
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -25,6 +26,7 @@
 #include <set>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 #include <zlib.h>
 
@@ -439,7 +441,15 @@ int main(int argc, char ** argv)
     }
     const size_t N = opt.files.size();
     std::vector<Profile> profiles(N);
-    for (size_t i = 0; i < N; ++i) loadProfile(opt.files[i], opt.uncompressed, profiles[i]);
+    {   // decode the profiles with all host cores (one file per task; SURVEY.md 8f rank 2: the reference re-opens and
+        // inflates every file per 200-kbp segment, single-threaded)
+        std::atomic<size_t> next{0};
+        const unsigned nthreads = (unsigned)std::max<size_t>(1, std::min<size_t>(N, std::thread::hardware_concurrency()));
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nthreads; ++t)
+            pool.emplace_back([&] { for (size_t i; (i = next.fetch_add(1)) < N;) loadProfile(opt.files[i], opt.uncompressed, profiles[i]); });
+        for (auto & th : pool) th.join();
+    }
 
     // ---- histograms and parameters (reference parameter_calculation_popdel_call.h:160-204)
     std::vector<pd_rg> rgs;

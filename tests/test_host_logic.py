@@ -96,3 +96,47 @@ def test_packed_layout_reproduces_active_sets(kind, oracle_lib):
     with pytest.raises(api.ScanError):
         sc.scan()                                                              # no CPU scan path
     sc.close()
+
+
+def _tiny_scanner(device):
+    samples, _ = simulate.simulate_cohort(seed=41, n_samples=2, contig_len=60_000, n_dels=0)
+    params = api.CallParameters()
+    rgs = api.read_groups_from_headers(api.cohort_headers(samples), params)
+    return api.Scanner(params, rgs, len(samples), device=device), samples
+
+
+def test_error_behaviour_of_the_c_abi_without_a_gpu():
+    """Errors are return codes with a sticky message, never exceptions or exits; a host-only context (device = -1) packs
+    and validates but refuses to scan -- there is no CPU fallback for the scan."""
+    sc, samples = _tiny_scanner(device=-1)
+    rg = samples[0].read_groups[0]
+    with pytest.raises(api.ScanError, match="no open contig"):
+        sc.push(0, rg.pos, rg.dev)
+    sc2, _ = _tiny_scanner(device=-1)
+    sc2.begin_contig(api.cohort_anchor(samples))
+    with pytest.raises(api.ScanError, match="sorted"):
+        sc2.push(0, rg.pos[::-1].copy(), rg.dev[::-1].copy())                  # PD_ERR_ORDER
+    with pytest.raises(api.ScanError, match="sorted"):
+        sc2.begin_contig(0)                                                     # sticky: the context stays failed
+    sc3, _ = _tiny_scanner(device=-1)
+    sc3.begin_contig(api.cohort_anchor(samples))
+    sc3.push(0, rg.pos, rg.dev)
+    sc3.reserve_windows(5000)
+    assert sc3.window_count() > 1000
+    with pytest.raises(api.ScanError, match="host-only context"):
+        sc3.scan()
+    with pytest.raises(api.ScanError, match="no usable CUDA device|out of range"):
+        _tiny_scanner(device=99)
+
+
+def test_shard_attach_rejects_bad_arguments():
+    import ctypes as C
+    lib = api.load_library()
+    sc, _ = _tiny_scanner(device=-1)
+    mi = np.array([200, 200], dtype=np.uint32)
+    spr = np.array([2, 2], dtype=np.uint32)
+    info = api.PdShardInfo(0, 1, 4, 2, mi.ctypes.data_as(C.POINTER(C.c_uint32)), spr.ctypes.data_as(C.POINTER(C.c_uint32)))
+    ctxs = (C.c_void_p * 2)(sc.ctx, sc.ctx)
+    assert lib.pd_shard_attach_group(ctxs, 1, C.byref(info)) == -1             # PD_ERR_ARG: world < 2
+    infos = (api.PdShardInfo * 2)(info, info)
+    assert lib.pd_shard_attach_group(ctxs, 2, infos) != 0                       # infos[r].rank / world do not describe rank r of 2
