@@ -221,6 +221,17 @@ def run_ours(args, rank, world, local_rank):
     dt2, _ = sharding.reduce_timing(dt2, float(evals), dist, "cuda")
     e2e = evals_all * e2e_steps / dt2
     assert int(r2["n_calls_check"]) == len(res["calls"]) if "n_calls_check" in r2 else len(r2["calls"]) == len(res["calls"])
+    # PCIe floor of that path: the same page-locked arrays copied to the device with nothing else going on
+    dev_bufs = [(torch.empty_like(p[0][0], device="cuda"), torch.empty_like(p[1][0], device="cuda")) for p in pinned]
+    for _ in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for (pp, dd), (dp, ddv) in zip(pinned, dev_bufs):
+            dp.copy_(pp[0], non_blocking=True), ddv.copy_(dd[0], non_blocking=True)
+        torch.cuda.synchronize()
+        dt_copy = time.perf_counter() - t0
+    raw_bytes = sum(p[0][0].numel() * 4 + p[1][0].numel() * 4 for p in pinned)
+    del dev_bufs
     # the same through pd_contig_push (sequential host packer, one thread per read group)
     push_all()
     r3 = sc.scan(copy=False)
@@ -259,6 +270,10 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clk,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(r2["h2d_bytes"]), "d2h_bytes_per_step": int(r2["d2h_bytes"]),
                 "steps": e2e_steps, "ms_per_step": dt2 / e2e_steps * 1e3, "path": "pd_contig_push_pinned (device-side packing)",
+                "pcie": {"h2d_gbs_plain_copy": raw_bytes / dt_copy / 1e9, "floor_ms_per_step": dt_copy * 1e3,
+                         "frac_of_floor": dt_copy / (dt2 / e2e_steps),
+                         "note": "floor = the same page-locked raw arrays copied host->device with nothing else running; "
+                                 "the e2e step additionally packs on the device, scans and writes the results back"},
                 "host_packer_value": evals_all / dt3, "host_packer_ms_per_step": dt3 * 1e3, "host_packer_h2d_bytes": int(r3["h2d_bytes"])},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "k_stream", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -1045,11 +1045,11 @@ cudaError_t launch_xr_t(const PdDev & a, const EmArgs & e, uint32_t T, cudaStrea
     return cudaGetLastError();
 }
 
-template <int LPS, int SLOTS, bool PREF, int MAXT, int MINB>
+template <int LPS, int SLOTS, bool PREF, int MAXT, int MINB, int BATCH = 2>
 cudaError_t launch_one_t(const PdDev & a, const EmArgs & e, uint32_t T, cudaStream_t st)
 {
     const size_t smem = (size_t)SLOTS * T * sizeof(int32_t);
-    k_em_one<LPS, SLOTS, 2, PREF, MAXT, MINB><<<e.npairs, T, smem, st>>>(a, e);
+    k_em_one<LPS, SLOTS, BATCH, PREF, MAXT, MINB><<<e.npairs, T, smem, st>>>(a, e);
     return cudaGetLastError();
 }
 
@@ -1089,7 +1089,16 @@ int pd_launch_em(pd_ctx * c, const PdDev & a, const EmArgs & e, cudaStream_t st,
             const uint32_t T1 = ((a.N * lps1 + 31) / 32) * 32;
             cudaError_t err1;
             const int minb = getenv("PD_EM_MINB") ? atoi(getenv("PD_EM_MINB")) : 0;
-            if (lps1 == 1 && T1 <= 128 && minb == 5) err1 = launch_one_t<1, 32, false, 128, 5>(a, e, T1, st);
+            // measured on B200 (100 samples x chr21): one look-up pair in flight at 80 registers (6 blocks per SM) beats
+            // deeper batching at 96-128 registers (5-4 blocks): 3.44 vs 3.56 / 3.72 / 4.02 ms per step
+            const int batch = getenv("PD_EM_BATCH") ? atoi(getenv("PD_EM_BATCH")) : (T1 <= 128 && lps1 == 1 ? 1 : 2);
+            if (lps1 == 1 && T1 <= 128 && batch == 3) err1 = launch_one_t<1, 32, false, 128, 5, 3>(a, e, T1, st);
+            else if (lps1 == 1 && T1 <= 128 && batch == 4) err1 = launch_one_t<1, 32, false, 128, 4, 4>(a, e, T1, st);
+            else if (lps1 == 1 && T1 <= 128 && batch == 1 && minb == 7) err1 = launch_one_t<1, 32, false, 128, 7, 1>(a, e, T1, st);
+            else if (lps1 == 1 && T1 <= 128 && batch == 1 && minb == 8) err1 = launch_one_t<1, 32, false, 128, 8, 1>(a, e, T1, st);
+            else if (lps1 == 1 && T1 <= 128 && batch == 1) err1 = launch_one_t<1, 32, false, 128, 6, 1>(a, e, T1, st);
+            else if (lps1 == 1 && T1 <= 128 && batch == 2 && minb == 6) err1 = launch_one_t<1, 32, false, 128, 6, 2>(a, e, T1, st);
+            else if (lps1 == 1 && T1 <= 128 && minb == 5) err1 = launch_one_t<1, 32, false, 128, 5>(a, e, T1, st);
             else if (lps1 == 1 && T1 <= 128 && minb == 4) err1 = launch_one_t<1, 32, false, 128, 4>(a, e, T1, st);
             else if (lps1 == 2 && T1 <= 224 && minb == 3) err1 = launch_one_t<2, 16, false, 224, 3>(a, e, T1, st);
             else if (lps1 == 2 && T1 <= 224 && minb == 2) err1 = launch_one_t<2, 16, false, 224, 2>(a, e, T1, st);

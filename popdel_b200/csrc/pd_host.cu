@@ -209,6 +209,7 @@ extern "C" void pd_destroy(pd_ctx * c)
         cudaSetDevice(c->device);
         cudaFree(c->d_words); cudaFree(c->d_tiles); cudaFree(c->d_longs);
         pd_shard_release(c);
+        for (auto & e : c->ev_pack) if (e) cudaEventDestroy(e);
         cudaFree(c->d_rgc); cudaFree(c->d_sample_rg); cudaFree(c->d_tab); cudaFree(c->d_min_init);
         if (c->res_ps) cudaFreeHost(c->res_ps);
         if (c->res_calls) cudaFreeHost(c->res_calls);

@@ -31,16 +31,19 @@ struct PackArgs {
     const uint64_t * rg_start;                             // [R+1]
     const PdRgConst * rgc;
     uint32_t R, NT, anchor, window_buffer;
+    uint32_t g0, ng;                                       // read groups handled by this launch
     uint32_t * tfirst;                                     // [R][NT+1] first read pair (RG-relative) of each tile
     uint32_t * flags;                                      // [0] unsorted, [1] cap would drop, [2] position before anchor
     uint32_t * span_tiles;                                 // [R] max (tile of last window - tile of the read pair)
 };
 
+// (all packing kernels work on the read groups [a.g0, a.g0 + a.ng) of one copy group)
 __global__ void k_tile_first(PackArgs a)
 {
-    const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t per = (uint64_t)a.NT + 1;
-    if (id >= per * a.R) return;
+    if (id >= per * a.ng) return;
+    id += per * a.g0;
     const uint32_t g = (uint32_t)(id / per), t = (uint32_t)(id % per);
     const uint32_t * p = a.pos + a.rg_start[g];
     const uint64_t n = a.rg_start[g + 1] - a.rg_start[g];
@@ -53,7 +56,7 @@ __global__ void k_tile_first(PackArgs a)
 // per read pair: order check and the largest tile span per read group. grid = (chunks of 1024 read pairs, read group)
 __global__ void __launch_bounds__(256) k_check_span(PackArgs a)
 {
-    const uint32_t g = blockIdx.y;
+    const uint32_t g = a.g0 + blockIdx.y;
     const uint64_t r0 = a.rg_start[g], n = a.rg_start[g + 1] - r0;
     const uint64_t first = (uint64_t)blockIdx.x * 1024;
     if (first >= n) return;
@@ -85,7 +88,7 @@ __global__ void __launch_bounds__(1024) k_cap_check(PackArgs a, uint32_t chunks_
 {
     __shared__ uint32_t hist[CAP_BINS + 1];
     __shared__ uint32_t wsum[32];
-    const uint32_t g = blockIdx.x / chunks_per_rg, ch = blockIdx.x % chunks_per_rg;
+    const uint32_t g = a.g0 + blockIdx.x / chunks_per_rg, ch = blockIdx.x % chunks_per_rg;
     const uint32_t max_load = a.rgc[g].max_load;
     if (max_load == 0xFFFFFFFFu) return;
     const uint32_t kl = max(a.span_tiles[g], a.rgc[g].lookback_tiles);
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(1024) k_tile_offsets(PackArgs a, uint32_t * re
 {
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t s_carry;
-    const uint32_t g = blockIdx.x;
+    const uint32_t g = a.g0 + blockIdx.x;
     const uint32_t * tf = a.tfirst + (size_t)g * (a.NT + 1);
     uint32_t * ro = rel_off + (size_t)g * (a.NT + 1);
     if (threadIdx.x == 0) s_carry = 0;
@@ -189,10 +192,11 @@ struct WriteArgs {
 // writes of the words): words, pads, count of long read pairs (pass 0) / wide entries in read order (pass 1)
 __global__ void __launch_bounds__(256) k_pack_tiles(PackArgs a, WriteArgs w, int pass)
 {
-    const uint64_t id = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    uint64_t id = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const uint64_t per = (uint64_t)a.NT + 1;
-    if (id >= per * a.R) return;
+    if (id >= per * a.ng) return;
+    id += per * a.g0;
     const uint32_t g = (uint32_t)(id / per), t = (uint32_t)(id % per);
     if (t >= a.NT) { if (pass == 0 && lane == 0) w.lcount[id] = 0; return; }
     if (pass == 1 && w.lcount[id + 1] == w.lcount[id]) return;            // no wide entries in this tile (the usual case)
@@ -378,33 +382,81 @@ int pd_pack_on_device(pd_ctx * c)
     if (grow_dev(c, 6, d_small, (size_t)R + 16)) return c->status;           // flags[4] | span_tiles[R]
     uint64_t * d_rg_start = d_u64, * d_rg_words = d_u64 + (R + 1), * d_word_base = d_u64 + 2 * (R + 1),
              * d_rg_longs = d_u64 + 3 * (R + 1), * d_long_base = d_u64 + 4 * (R + 1);
-    PD_CUDA(c, cudaEventRecord(c->ev[0], st));
+    // ---- word bases from UPPER BOUNDS of the packed sizes (every non-empty tile pads to a multiple of 4 words), so that
+    // packing needs no host round trip and can start while later read groups are still crossing PCIe
+    const uint64_t ntile = per * R;
+    std::vector<uint64_t> base(R + 1, 0);
+    uint64_t max_n = 0;
     for (uint32_t g = 0; g < R; ++g) {
-        const PdRawRg & r = c->raw[g];
-        if (!r.n) continue;
-        PD_CUDA(c, cudaMemcpyAsync(d_pos + rg_start[g], r.pos, r.n * 4, cudaMemcpyHostToDevice, st));
-        PD_CUDA(c, cudaMemcpyAsync(d_dev + rg_start[g], r.dev, r.n * 4, cudaMemcpyHostToDevice, st));
+        const uint64_t n = c->raw[g].n;
+        base[g + 1] = base[g] + ((n + 3 * std::min<uint64_t>(NT, n) + 3) & ~3ull);
+        max_n = std::max(max_n, n);
     }
+    if (base[R] > 0xFFFFFFF0ull) return pd_fail(c, PD_ERR_CAPACITY, "more than 2^32 packed words in one contig batch; split the cohort or the contig");
+    c->total_words = base[R];
+    c->h_word_base = base;
+    c->n_reads = total;
+    if (c->total_words + 4 > c->cap_words || !c->d_words) {
+        if (c->d_words) cudaFree(c->d_words);
+        c->d_words = nullptr; c->cap_words = 0;
+        size_t want = c->total_words + c->total_words / 8 + 1024;
+        PD_CUDA(c, cudaMalloc(&c->d_words, want * 4));
+        c->cap_words = want;
+    }
+    PD_CUDA(c, cudaEventRecord(c->ev[0], st));
     PD_CUDA(c, cudaMemcpyAsync(d_rg_start, rg_start.data(), (R + 1) * 8, cudaMemcpyHostToDevice, st));
+    PD_CUDA(c, cudaMemcpyAsync(d_word_base, base.data(), (R + 1) * 8, cudaMemcpyHostToDevice, st));
     PD_CUDA(c, cudaMemsetAsync(d_small, 0, ((size_t)R + 16) * 4, st));
-    c->h2d_bytes = total * 8 + (R + 1) * 8;
+    c->h2d_bytes = total * 8 + (R + 1) * 16;
 
     PackArgs a;
-    a.pos = d_pos; a.dev = d_dev; a.rg_start = d_rg_start; a.rgc = c->d_rgc; a.R = R; a.NT = NT;
+    a.pos = d_pos; a.dev = d_dev; a.rg_start = d_rg_start; a.rgc = c->d_rgc; a.R = R; a.NT = NT; a.g0 = 0; a.ng = R;
     a.anchor = c->grid.anchor; a.window_buffer = c->grid.window_buffer; a.tfirst = d_tfirst; a.flags = d_small; a.span_tiles = d_small + 16;
-    const uint64_t ntile = per * R;
-    uint64_t max_n = 0;
-    for (uint32_t g = 0; g < R; ++g) max_n = std::max<uint64_t>(max_n, c->raw[g].n);
-    if (total) k_check_span<<<dim3((unsigned)((max_n + 1023) / 1024), R), 256, 0, st>>>(a);
-    k_tile_first<<<(unsigned)((ntile + 255) / 256), 256, 0, st>>>(a);
+    WriteArgs w;
+    w.words = c->d_words; w.tiles = nullptr; w.longs = nullptr; w.rel_off = d_rel; w.word_base = d_word_base;
+    w.lcount = d_lcount; w.long_base = d_long_base; w.pmax = nullptr;
     const uint32_t chunks = (NT + CAP_CHUNK_TILES - 1) / CAP_CHUNK_TILES;
-    k_cap_check<<<R * chunks, 1024, 0, st>>>(a, chunks);
-    k_tile_offsets<<<R, 1024, 0, st>>>(a, d_rel, d_rg_words);
+
+    // ---- copy groups: the raw arrays of group k+1 cross PCIe (copy stream) while group k is checked and packed
+    constexpr int PACK_GROUPS = 8;
+    if (!c->ev_pack[0]) for (auto & e : c->ev_pack) PD_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaStream_t cp = c->stream2;
+    PD_CUDA(c, cudaEventRecord(c->ev_pack[PACK_GROUPS], st));             // the copy stream starts after everything queued before
+    PD_CUDA(c, cudaStreamWaitEvent(cp, c->ev_pack[PACK_GROUPS], 0));
+    uint32_t g_lo = 0;
+    for (int k = 0; k < PACK_GROUPS && g_lo < R; ++k) {
+        // groups of about equal read-pair counts
+        const uint64_t target = rg_start[g_lo] + (total - rg_start[g_lo] + (PACK_GROUPS - k) - 1) / (PACK_GROUPS - k);
+        uint32_t g_hi = g_lo + 1;
+        while (g_hi < R && (k == PACK_GROUPS - 1 || rg_start[g_hi + 1] <= target)) ++g_hi;
+        if (k == PACK_GROUPS - 1) g_hi = R;
+        uint64_t grp_max = 0;
+        for (uint32_t g = g_lo; g < g_hi; ++g) {
+            const PdRawRg & r = c->raw[g];
+            grp_max = std::max<uint64_t>(grp_max, r.n);
+            if (!r.n) continue;
+            PD_CUDA(c, cudaMemcpyAsync(d_pos + rg_start[g], r.pos, r.n * 4, cudaMemcpyHostToDevice, cp));
+            PD_CUDA(c, cudaMemcpyAsync(d_dev + rg_start[g], r.dev, r.n * 4, cudaMemcpyHostToDevice, cp));
+        }
+        PD_CUDA(c, cudaEventRecord(c->ev_pack[k], cp));
+        PD_CUDA(c, cudaStreamWaitEvent(st, c->ev_pack[k], 0));
+        a.g0 = g_lo; a.ng = g_hi - g_lo;
+        const uint64_t nt_grp = per * a.ng;
+        if (grp_max) k_check_span<<<dim3((unsigned)((grp_max + 1023) / 1024), a.ng), 256, 0, st>>>(a);
+        k_tile_first<<<(unsigned)((nt_grp + 255) / 256), 256, 0, st>>>(a);
+        k_cap_check<<<a.ng * chunks, 1024, 0, st>>>(a, chunks);
+        k_tile_offsets<<<a.ng, 1024, 0, st>>>(a, d_rel, d_rg_words);
+        k_pack_tiles<<<(unsigned)((nt_grp + 7) / 8), 256, 0, st>>>(a, w, 0);
+        PD_CUDA(c, cudaGetLastError());
+        g_lo = g_hi;
+    }
+    a.g0 = 0; a.ng = R;
+    k_long_offsets<<<R, 1024, 0, st>>>(a, d_lcount, d_rg_longs);
     PD_CUDA(c, cudaGetLastError());
     std::vector<uint32_t> h_small((size_t)R + 16);
-    std::vector<uint64_t> h_words(R);
+    std::vector<uint64_t> h_longs(R);
     PD_CUDA(c, cudaMemcpyAsync(h_small.data(), d_small, h_small.size() * 4, cudaMemcpyDeviceToHost, st));
-    PD_CUDA(c, cudaMemcpyAsync(h_words.data(), d_rg_words, R * 8, cudaMemcpyDeviceToHost, st));
+    PD_CUDA(c, cudaMemcpyAsync(h_longs.data(), d_rg_longs, R * 8, cudaMemcpyDeviceToHost, st));
     PD_CUDA(c, cudaStreamSynchronize(st));
     if (h_small[2]) return pd_fail(c, PD_ERR_ARG, "pd_contig_push_pinned: position before the contig anchor");
     if (h_small[0]) return pd_fail(c, PD_ERR_ORDER, "pd_contig_push_pinned: read pairs must be sorted by position");
@@ -413,20 +465,6 @@ int pd_pack_on_device(pd_ctx * c)
         if (c->rgc[g].max_load != 0xFFFFFFFFu && std::max(h_small[16 + g], c->rgc[g].lookback_tiles) > (uint32_t)CAP_MAX_LOOKBACK) fallback = true;
     if (fallback) return 1;
 
-    std::vector<uint64_t> base(R + 1, 0);
-    for (uint32_t g = 0; g < R; ++g) base[g + 1] = base[g] + h_words[g];
-    if (base[R] > 0xFFFFFFF0ull) return pd_fail(c, PD_ERR_CAPACITY, "more than 2^32 packed words in one contig batch; split the cohort or the contig");
-    c->total_words = base[R];
-    c->h_word_base = base;
-    c->n_reads = total;
-    PD_CUDA(c, cudaMemcpyAsync(d_word_base, base.data(), (R + 1) * 8, cudaMemcpyHostToDevice, st));
-    if (c->total_words + 4 > c->cap_words || !c->d_words) {
-        if (c->d_words) cudaFree(c->d_words);
-        c->d_words = nullptr; c->cap_words = 0;
-        size_t want = c->total_words + c->total_words / 8 + 1024;
-        PD_CUDA(c, cudaMalloc(&c->d_words, want * 4));
-        c->cap_words = want;
-    }
     if (ntile > c->cap_tiles || !c->d_tiles) {
         if (c->d_tiles) cudaFree(c->d_tiles);
         c->d_tiles = nullptr; c->cap_tiles = 0;
@@ -434,15 +472,7 @@ int pd_pack_on_device(pd_ctx * c)
         PD_CUDA(c, cudaMalloc(&c->d_tiles, want * sizeof(PdTile)));
         c->cap_tiles = want;
     }
-    WriteArgs w;
-    w.words = c->d_words; w.tiles = c->d_tiles; w.longs = nullptr; w.rel_off = d_rel; w.word_base = d_word_base;
-    w.lcount = d_lcount; w.long_base = d_long_base; w.pmax = nullptr;
-    k_pack_tiles<<<(unsigned)((ntile + 7) / 8), 256, 0, st>>>(a, w, 0);
-    k_long_offsets<<<R, 1024, 0, st>>>(a, d_lcount, d_rg_longs);
-    PD_CUDA(c, cudaGetLastError());
-    std::vector<uint64_t> h_longs(R);
-    PD_CUDA(c, cudaMemcpyAsync(h_longs.data(), d_rg_longs, R * 8, cudaMemcpyDeviceToHost, st));
-    PD_CUDA(c, cudaStreamSynchronize(st));
+    w.tiles = c->d_tiles;
     std::vector<uint64_t> lbase(R + 1, 0);
     for (uint32_t g = 0; g < R; ++g) lbase[g + 1] = lbase[g] + h_longs[g];
     c->total_longs = lbase[R];
