@@ -235,6 +235,31 @@ __global__ void __launch_bounds__(256) k_pack_tiles(PackArgs a, WriteArgs w, int
     }
 }
 
+// wide entries in read order: one THREAD per (read group, tile) -- almost every tile has none and returns at once
+__global__ void __launch_bounds__(256) k_pack_longs(PackArgs a, WriteArgs w)
+{
+    const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t per = (uint64_t)a.NT + 1;
+    if (id >= per * a.R) return;
+    const uint32_t g = (uint32_t)(id / per), t = (uint32_t)(id % per);
+    if (t >= a.NT || w.lcount[id + 1] == w.lcount[id]) return;
+    const PdRgConst k = a.rgc[g];
+    const uint32_t * tf = a.tfirst + (size_t)g * per;
+    const uint32_t * p = a.pos + a.rg_start[g];
+    const int32_t * d = a.dev + a.rg_start[g];
+    PdLong * lout = w.longs + w.long_base[g] + w.lcount[id];
+    uint32_t nl = 0;
+    for (uint32_t i = tf[t]; i < tf[t + 1]; ++i) {
+        const uint32_t pr = p[i] - a.anchor;
+        const int32_t dv = d[i];
+        int64_t s, e;
+        const bool act = pd_interval(pr, dv, k.inner_off, a.window_buffer, s, e);
+        bool is_long = dv > PD_DEV_MAX || dv < PD_DEV_MIN + 1;
+        if (act && (uint64_t)e / PD_TILE_WINDOWS > (uint64_t)t + k.lookback_tiles) is_long = true;
+        if (is_long && act) lout[nl++] = PdLong{(uint32_t)s, (uint32_t)e, pr, dv};
+    }
+}
+
 // exclusive scan of lcount per read group (in place) and totals; one block per read group
 __global__ void __launch_bounds__(1024) k_long_offsets(PackArgs a, uint32_t * lcount, uint64_t * rg_longs)
 {
@@ -330,19 +355,21 @@ static uint64_t last_window_from_raw(pd_ctx * c)
     }
     if (kf < 0) return 0;
     int64_t E = -1, S = -1, Esp = -1;
+    // segment of a read pair = floor(30 * floor(pr / 30) / wb): compare 30 * floor(pr / 30) with the segment starts
+    // instead of dividing per read pair (this loop walks the last two segments of every read group on the host)
+    const int64_t start_kf = kf * (int64_t)wb, start_km1 = (kf - 1) * (int64_t)wb;
+    const int64_t wl_kf = (int64_t)pd_seg_last_window((uint64_t)kf, wb), wl_km1 = kf > 0 ? (int64_t)pd_seg_last_window((uint64_t)(kf - 1), wb) : -1;
     for (uint32_t g = 0; g < c->R; ++g) {
         const PdRawRg & r = c->raw[g];
         const int32_t io = c->rgc[g].inner_off;
         for (uint64_t i = r.n; i-- > 0;) {
-            const uint64_t pr = r.pos[i] - anchor;
-            const uint64_t b = pr / PD_WIN;
-            const int64_t j = (int64_t)(b * PD_WIN / wb);
-            if (j < kf - 1) break;
+            const uint32_t pr = r.pos[i] - anchor;
+            const int64_t q = (int64_t)(pr - pr % PD_WIN);
+            if (q < start_km1) break;
             const int64_t inner = std::max<int64_t>(0, (int64_t)r.dev[i] + io);
-            const int64_t lw = (int64_t)((pr + inner) / PD_WIN);
-            const int64_t wl = (int64_t)pd_seg_last_window((uint64_t)j, wb);
-            if (j == kf) { S = std::max<int64_t>(S, (int64_t)pr); if (lw <= wl) E = std::max(E, lw); else Esp = std::max(Esp, lw); }
-            else if (lw > wl) E = std::max(E, lw);
+            const int64_t lw = (int64_t)(((uint64_t)pr + (uint64_t)inner) / PD_WIN);
+            if (q >= start_kf) { S = std::max<int64_t>(S, (int64_t)pr); if (lw <= wl_kf) E = std::max(E, lw); else Esp = std::max(Esp, lw); }
+            else if (lw > wl_km1) E = std::max(E, lw);
         }
     }
     c->tail.kf = kf; c->tail.S = S; c->tail.E = E; c->tail.E_spill = Esp;
@@ -366,15 +393,44 @@ int pd_pack_on_device(pd_ctx * c)
     }
     const uint64_t total = rg_start[R];
     if (total > 0xFFFFFFF0ull) return pd_fail(c, PD_ERR_CAPACITY, "more than 2^32 read pairs in one contig batch");
+    cudaStream_t st = c->stream;
+    uint32_t * d_pos; int32_t * d_dev; uint64_t * d_u64; uint32_t * d_tfirst, * d_rel, * d_lcount, * d_small, * d_pmax;
+    if (grow_dev(c, 0, d_pos, total)) return c->status;
+    if (grow_dev(c, 1, d_dev, total)) return c->status;
+
+    // ---- copy groups of about equal read-pair counts: all copies are queued on the copy stream FIRST; the host-side
+    // preparation below and the packing kernels of group k then overlap the PCIe transfer of the later groups
+    constexpr int PACK_GROUPS = 8;
+    if (!c->ev_pack[0]) for (auto & e : c->ev_pack) PD_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaStream_t cp = c->stream2;
+    PD_CUDA(c, cudaEventRecord(c->ev[0], st));
+    PD_CUDA(c, cudaEventRecord(c->ev_pack[PACK_GROUPS], st));             // the copy stream starts after everything queued before
+    PD_CUDA(c, cudaStreamWaitEvent(cp, c->ev_pack[PACK_GROUPS], 0));
+    uint32_t grp_lo[PACK_GROUPS + 1]; uint64_t grp_max[PACK_GROUPS];
+    int n_groups = 0;
+    for (uint32_t g_lo = 0; n_groups < PACK_GROUPS && g_lo < R; ++n_groups) {
+        const int k = n_groups;
+        const uint64_t target = rg_start[g_lo] + (total - rg_start[g_lo] + (PACK_GROUPS - k) - 1) / (PACK_GROUPS - k);
+        uint32_t g_hi = g_lo + 1;
+        while (g_hi < R && (k == PACK_GROUPS - 1 || rg_start[g_hi + 1] <= target)) ++g_hi;
+        grp_lo[k] = g_lo; grp_max[k] = 0;
+        for (uint32_t g = g_lo; g < g_hi; ++g) {
+            const PdRawRg & r = c->raw[g];
+            grp_max[k] = std::max<uint64_t>(grp_max[k], r.n);
+            if (!r.n) continue;
+            PD_CUDA(c, cudaMemcpyAsync(d_pos + rg_start[g], r.pos, r.n * 4, cudaMemcpyHostToDevice, cp));
+            PD_CUDA(c, cudaMemcpyAsync(d_dev + rg_start[g], r.dev, r.n * 4, cudaMemcpyHostToDevice, cp));
+        }
+        PD_CUDA(c, cudaEventRecord(c->ev_pack[k], cp));
+        g_lo = g_hi;
+        grp_lo[k + 1] = g_hi;
+    }
+
     c->n_windows_total = any ? last_window_from_raw(c) : 0;
     const uint32_t NT = (uint32_t)std::max<uint64_t>(std::max<uint64_t>((std::max(c->n_windows_total, c->min_windows) + PD_TILE_WINDOWS - 1) / PD_TILE_WINDOWS,
                                                                         any ? (uint64_t)max_pos_rel / PD_TILE_BP + 1 : 0), 1);
     c->NT = NT;
-    cudaStream_t st = c->stream;
-    uint32_t * d_pos; int32_t * d_dev; uint64_t * d_u64; uint32_t * d_tfirst, * d_rel, * d_lcount, * d_small, * d_pmax;
     const size_t per = (size_t)NT + 1;
-    if (grow_dev(c, 0, d_pos, total)) return c->status;
-    if (grow_dev(c, 1, d_dev, total)) return c->status;
     if (grow_dev(c, 2, d_u64, (size_t)5 * (R + 1))) return c->status;        // rg_start | rg_words | word_base | rg_longs | long_base
     if (grow_dev(c, 3, d_tfirst, per * R)) return c->status;
     if (grow_dev(c, 4, d_rel, per * R)) return c->status;
@@ -403,7 +459,6 @@ int pd_pack_on_device(pd_ctx * c)
         PD_CUDA(c, cudaMalloc(&c->d_words, want * 4));
         c->cap_words = want;
     }
-    PD_CUDA(c, cudaEventRecord(c->ev[0], st));
     PD_CUDA(c, cudaMemcpyAsync(d_rg_start, rg_start.data(), (R + 1) * 8, cudaMemcpyHostToDevice, st));
     PD_CUDA(c, cudaMemcpyAsync(d_word_base, base.data(), (R + 1) * 8, cudaMemcpyHostToDevice, st));
     PD_CUDA(c, cudaMemsetAsync(d_small, 0, ((size_t)R + 16) * 4, st));
@@ -417,38 +472,18 @@ int pd_pack_on_device(pd_ctx * c)
     w.lcount = d_lcount; w.long_base = d_long_base; w.pmax = nullptr;
     const uint32_t chunks = (NT + CAP_CHUNK_TILES - 1) / CAP_CHUNK_TILES;
 
-    // ---- copy groups: the raw arrays of group k+1 cross PCIe (copy stream) while group k is checked and packed
-    constexpr int PACK_GROUPS = 8;
-    if (!c->ev_pack[0]) for (auto & e : c->ev_pack) PD_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    cudaStream_t cp = c->stream2;
-    PD_CUDA(c, cudaEventRecord(c->ev_pack[PACK_GROUPS], st));             // the copy stream starts after everything queued before
-    PD_CUDA(c, cudaStreamWaitEvent(cp, c->ev_pack[PACK_GROUPS], 0));
-    uint32_t g_lo = 0;
-    for (int k = 0; k < PACK_GROUPS && g_lo < R; ++k) {
-        // groups of about equal read-pair counts
-        const uint64_t target = rg_start[g_lo] + (total - rg_start[g_lo] + (PACK_GROUPS - k) - 1) / (PACK_GROUPS - k);
-        uint32_t g_hi = g_lo + 1;
-        while (g_hi < R && (k == PACK_GROUPS - 1 || rg_start[g_hi + 1] <= target)) ++g_hi;
-        if (k == PACK_GROUPS - 1) g_hi = R;
-        uint64_t grp_max = 0;
-        for (uint32_t g = g_lo; g < g_hi; ++g) {
-            const PdRawRg & r = c->raw[g];
-            grp_max = std::max<uint64_t>(grp_max, r.n);
-            if (!r.n) continue;
-            PD_CUDA(c, cudaMemcpyAsync(d_pos + rg_start[g], r.pos, r.n * 4, cudaMemcpyHostToDevice, cp));
-            PD_CUDA(c, cudaMemcpyAsync(d_dev + rg_start[g], r.dev, r.n * 4, cudaMemcpyHostToDevice, cp));
-        }
-        PD_CUDA(c, cudaEventRecord(c->ev_pack[k], cp));
+    // ---- per copy group, as soon as its raw arrays have arrived: order / span check, tile search, coverage-cap check,
+    // tile offsets, words
+    for (int k = 0; k < n_groups; ++k) {
         PD_CUDA(c, cudaStreamWaitEvent(st, c->ev_pack[k], 0));
-        a.g0 = g_lo; a.ng = g_hi - g_lo;
+        a.g0 = grp_lo[k]; a.ng = grp_lo[k + 1] - grp_lo[k];
         const uint64_t nt_grp = per * a.ng;
-        if (grp_max) k_check_span<<<dim3((unsigned)((grp_max + 1023) / 1024), a.ng), 256, 0, st>>>(a);
+        if (grp_max[k]) k_check_span<<<dim3((unsigned)((grp_max[k] + 1023) / 1024), a.ng), 256, 0, st>>>(a);
         k_tile_first<<<(unsigned)((nt_grp + 255) / 256), 256, 0, st>>>(a);
         k_cap_check<<<a.ng * chunks, 1024, 0, st>>>(a, chunks);
         k_tile_offsets<<<a.ng, 1024, 0, st>>>(a, d_rel, d_rg_words);
         k_pack_tiles<<<(unsigned)((nt_grp + 7) / 8), 256, 0, st>>>(a, w, 0);
         PD_CUDA(c, cudaGetLastError());
-        g_lo = g_hi;
     }
     a.g0 = 0; a.ng = R;
     k_long_offsets<<<R, 1024, 0, st>>>(a, d_lcount, d_rg_longs);
@@ -489,7 +524,7 @@ int pd_pack_on_device(pd_ctx * c)
     }
     if (grow_dev(c, 7, d_pmax, (size_t)c->total_longs + 1)) return c->status;
     w.longs = c->d_longs; w.pmax = d_pmax;
-    k_pack_tiles<<<(unsigned)((ntile + 7) / 8), 256, 0, st>>>(a, w, 1);
+    k_pack_longs<<<(unsigned)((ntile + 255) / 256), 256, 0, st>>>(a, w);
     k_long_pmax<<<(R + 63) / 64, 64, 0, st>>>(a, w, d_rg_longs);
     k_tile_table<<<(unsigned)((ntile + 255) / 256), 256, 0, st>>>(a, w, d_rg_longs);
     PD_CUDA(c, cudaGetLastError());
