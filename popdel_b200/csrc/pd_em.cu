@@ -621,7 +621,7 @@ __device__ __forceinline__ void dl_one(const RgOne & k, const int32_t * cache_d,
     }
 }
 
-template <int LPS, int SLOTS, int BATCH, bool PREF>
+template <int LPS, int SLOTS, int BATCH, bool PREF, bool FUSED>
 __device__ __forceinline__ void em_one_body(const PdDev & a, const EmArgs & e, EmShared & sh, uint32_t * s_first, uint32_t * s_last,
                                             uint32_t & s_nsupp, uint16_t * s_perm, int32_t * cache_dev)
 {
@@ -685,7 +685,10 @@ __device__ __forceinline__ void em_one_body(const PdDev & a, const EmArgs & e, E
         gt = gt_prior(freq, e.somatic);
     }
     if (freq == 0) {
-        if (tid == 0) { e.valid[blockIdx.x] = 0; if (e.dbg) { e.dbg[4 * blockIdx.x] = 1; e.dbg[4 * blockIdx.x + 1] = len; e.dbg[4 * blockIdx.x + 2] = 0; } }
+        if (tid == 0) {
+            e.valid[blockIdx.x] = 0; if (e.dbg) { e.dbg[4 * blockIdx.x] = 1; e.dbg[4 * blockIdx.x + 1] = len; e.dbg[4 * blockIdx.x + 2] = 0; }
+            if (!FUSED) e.states[blockIdx.x].alive = 0;
+        }
         return;
     }
     int shift = 0;
@@ -771,7 +774,19 @@ __device__ __forceinline__ void em_one_body(const PdDev & a, const EmArgs & e, E
         mode = 1; dlL = (int)len; dlS = shift;
     }
     if (freq < 0.0000000001 || len < e.min_len) {
-        if (tid == 0) { e.valid[blockIdx.x] = 0; if (e.dbg) { e.dbg[4 * blockIdx.x] = 2; e.dbg[4 * blockIdx.x + 1] = len; e.dbg[4 * blockIdx.x + 2] = it; } }
+        if (tid == 0) {
+            e.valid[blockIdx.x] = 0; if (e.dbg) { e.dbg[4 * blockIdx.x] = 2; e.dbg[4 * blockIdx.x + 1] = len; e.dbg[4 * blockIdx.x + 2] = it; }
+            if (!FUSED) e.states[blockIdx.x].alive = 0;
+        }
+        return;
+    }
+    if (!FUSED) {                                        // hand over to k_final (separate launch, smaller register footprint here)
+        if (has && sub == 0) e.shifts[(size_t)blockIdx.x * a.R + s] = shift;
+        if (tid == 0) {
+            EmState st; st.len = len; st.it = it; st.alive = 1; st.pad = 0; st.freq = freq;
+            st.gt[0] = gt.a; st.gt[1] = gt.b; st.gt[2] = gt.c;
+            e.states[blockIdx.x] = st;
+        }
         return;
     }
 
@@ -934,8 +949,18 @@ __global__ void __launch_bounds__(MAXT, MINB) k_em_one(PdDev a, EmArgs e)
     __shared__ uint32_t s_nsupp;
     __shared__ uint16_t s_perm[256];
     extern __shared__ int32_t cache_dev[];              // [SLOTS][T] deviations of this block's read pairs
-    em_one_body<LPS, SLOTS, BATCH, PREF>(a, e, sh, s_first, s_last, s_nsupp, s_perm, cache_dev);
+    em_one_body<LPS, SLOTS, BATCH, PREF, true>(a, e, sh, s_first, s_last, s_nsupp, s_perm, cache_dev);
     publish_done(e, blockIdx.x);
+}
+// EM loop only (experiment PD_EM_SPLIT=1): the final pass runs as k_final<1, ...> in a second launch
+template <int LPS, int SLOTS, int BATCH, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_em_one_loop(PdDev a, EmArgs e)
+{
+    __shared__ EmShared sh;
+    __shared__ uint32_t s_nsupp;
+    __shared__ uint16_t s_perm[256];
+    extern __shared__ int32_t cache_dev[];
+    em_one_body<LPS, SLOTS, BATCH, false, false>(a, e, sh, nullptr, nullptr, s_nsupp, s_perm, cache_dev);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1092,6 +1117,17 @@ int pd_launch_em(pd_ctx * c, const PdDev & a, const EmArgs & e, cudaStream_t st,
             // measured on B200 (100 samples x chr21): one look-up pair in flight at 80 registers (6 blocks per SM) beats
             // deeper batching at 96-128 registers (5-4 blocks): 3.44 vs 3.56 / 3.72 / 4.02 ms per step
             const int batch = getenv("PD_EM_BATCH") ? atoi(getenv("PD_EM_BATCH")) : (T1 <= 128 && lps1 == 1 ? 1 : 2);
+            const int split = getenv("PD_EM_SPLIT") ? atoi(getenv("PD_EM_SPLIT")) : 0;
+            if (split && lps1 == 1 && T1 <= 128) {
+                const size_t smem = (size_t)32 * T1 * sizeof(int32_t);
+                if (split == 1) k_em_one_loop<1, 32, 1, 128, 8><<<e.npairs, T1, smem, st>>>(a, e);
+                else if (split == 2) k_em_one_loop<1, 32, 1, 128, 7><<<e.npairs, T1, smem, st>>>(a, e);
+                else k_em_one_loop<1, 32, 2, 128, 6><<<e.npairs, T1, smem, st>>>(a, e);
+                k_final<1, 128, 6><<<e.npairs, T1, 0, st>>>(a, e);
+                if (cudaGetLastError() != cudaSuccess) return pd_fail(c, PD_ERR_CUDA, "k_em_one_loop / k_final launch");
+                *launches += 2;
+                return 0;
+            }
             if (lps1 == 1 && T1 <= 128 && batch == 3) err1 = launch_one_t<1, 32, false, 128, 5, 3>(a, e, T1, st);
             else if (lps1 == 1 && T1 <= 128 && batch == 4) err1 = launch_one_t<1, 32, false, 128, 4, 4>(a, e, T1, st);
             else if (lps1 == 1 && T1 <= 128 && batch == 1 && minb == 7) err1 = launch_one_t<1, 32, false, 128, 7, 1>(a, e, T1, st);

@@ -252,7 +252,7 @@ extern "C" int pd_shard_attach_nccl(pd_ctx * c, const pd_shard_info * info, cons
     }
     int sms = 0;
     PD_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-    s->grid_cap = (uint32_t)sms * 2;
+    s->grid_cap = (uint32_t)sms * 2 - 12;           // persistent EM blocks, two per SM; 12 half-SMs stay free for the result emitter
     // nobody may post into a peer before that peer's slots are zeroed and mapped everywhere: one more collective
     if (pd_shard_allgather(c, s->d_small, (char *)s->d_small + 1024, 64, c->stream)) return c->status;
     PD_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -291,7 +291,7 @@ extern "C" int pd_shard_attach_group(pd_ctx ** ctxs, uint32_t n, const pd_shard_
         int sms = 0;
         PD_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
         // contexts sharing one GPU split it: all their persistent blocks must be resident at the same time
-        s->grid_cap = share > 1 ? std::max<uint32_t>(1, (uint32_t)sms / share) : (uint32_t)sms * 2;
+        s->grid_cap = share > 1 ? std::max<uint32_t>(1, (uint32_t)sms / share) : (uint32_t)sms * 2 - 12;
     }
     return 0;
 }

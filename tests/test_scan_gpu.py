@@ -130,3 +130,19 @@ def test_sample_sharded_larger_cohort(oracle_lib):
     ref_calls, ref_ps, _ = run_oracle(samples, params, rgs, oracle_lib)
     assert_calls_equal(merged["calls"], merged["per_sample"], ref_calls, ref_ps)
     assert len(merged["calls"]) > 100
+
+
+def test_device_packer_with_empty_and_single_read_groups():
+    """Pipelined device packer (8 copy groups) with fewer read groups than groups and with a read group without reads."""
+    samples, _ = simulate.simulate_cohort(seed=33, n_samples=3, contig_len=120_000, n_dels=1)
+    rg = samples[1].read_groups[0]
+    rg.pos, rg.isize = rg.pos[:0], rg.isize[:0]
+    params = api.CallParameters()
+    a, _ = api.scan_cohort(samples, params)
+    b, _ = api.scan_cohort(samples, params, pinned=True)
+    assert a["n_windows"] == b["n_windows"] and a["n_reads"] == b["n_reads"]
+    assert_calls_equal(b["calls"], b["per_sample"], a["calls"], a["per_sample"], rtol=0)
+    one, _ = simulate.simulate_cohort(seed=37, n_samples=1, contig_len=90_000, n_dels=1)
+    a, _ = api.scan_cohort(one, params)
+    b, _ = api.scan_cohort(one, params, pinned=True)
+    assert_calls_equal(b["calls"], b["per_sample"], a["calls"], a["per_sample"], rtol=0)
