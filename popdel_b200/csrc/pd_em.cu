@@ -8,7 +8,11 @@
 //             r = del/(del+ref) of the last data-likelihood pass are cached in shared memory for the length update.
 //   k_final   one block per surviving pair: final data likelihoods (:255-337), log10 genotype likelihoods -> PL
 //             (utils_popdel.h:1511-1528), LAD/DAD (:137-172), FL, supporting read-pair percentiles (:514-529), LR test.
-//   k_emit_*  ordered compaction of the emitted calls and their per-sample rows straight into mapped host memory.
+//   k_em_one  both fused, for cohorts with one read group per sample that fit one block (one sample per lane).
+//   k_em_xr / k_final_xr  the general kernels as persistent ticketed blocks with in-kernel cross-rank reductions
+//             (sample-sharded cohorts, pd_shard.cu / pd_em_common.cuh).
+//   k_emit_stream  concurrent with the EM launch: copies finished pairs (done flags) in pair order into mapped host
+//             memory.
 // Floating point: double. The two places where the reference's x87 long double is observable are emulated
 // (finish_triple): exp() underflow at -11399.5 and the ln2 - fl64(ln2) residue of read pairs with ref == del.
 #include <algorithm>
@@ -563,9 +567,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_final_xr(PdDev a, EmArgs e)
 // ------------------------------------------------------------------------------------------------------------------
 struct RgOne { const PdTab * fl; int hist_base; uint32_t hist_len; double min_prob, ln_min_prob; };   // fl = floor row of the read group
 
-__device__ __forceinline__ void prefetch_l1(const void * p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
-
-template <int LPS, int SLOTS, int BATCH, bool PREF>
+template <int LPS, int SLOTS, int BATCH>
 __device__ __forceinline__ void dl_one(const RgOne & k, const int32_t * cache_d, const int32_t * pd,
                                        int T, int tid, int sub, int nl, int shift, int L, uint32_t gmask, double * rgw /* group of read group 0 only */,
                                        double & x0, double & E0, double & E1, double & E2, double & Sr, double & Srd)
@@ -573,14 +575,6 @@ __device__ __forceinline__ void dl_one(const RgOne & k, const int32_t * cache_d,
     double l0 = 0, l1 = 0, l2 = 0, sr = 0, srd = 0;
     uint32_t nd = 0;
     const PdTab * fl = k.fl;
-    if (PREF) {
-        // the look-ups are L2-latency bound: pull every row this lane will touch into L1 first (no registers held)
-        for (int jj = 0; jj < nl; ++jj) {
-            const int dd = jj < SLOTS ? cache_d[jj * T + tid] : __ldg(pd + sub + jj * LPS);
-            if (tab_in(k, dd - shift)) prefetch_l1(&fl[dd - shift + k.hist_base + 1]);
-            if (tab_in(k, dd - L)) prefetch_l1(&fl[dd - L + k.hist_base + 1]);
-        }
-    }
     for (int b = 0; b < nl; b += BATCH) {
         int d[BATCH]; uint32_t id[BATCH]; D4 rr[BATCH]; double2 dv[BATCH];
 #pragma unroll
@@ -621,7 +615,7 @@ __device__ __forceinline__ void dl_one(const RgOne & k, const int32_t * cache_d,
     }
 }
 
-template <int LPS, int SLOTS, int BATCH, bool PREF, bool FUSED>
+template <int LPS, int SLOTS, int BATCH>
 __device__ __forceinline__ void em_one_body(const PdDev & a, const EmArgs & e, EmShared & sh, uint32_t * s_first, uint32_t * s_last,
                                             uint32_t & s_nsupp, uint16_t * s_perm, int32_t * cache_dev)
 {
@@ -687,7 +681,6 @@ __device__ __forceinline__ void em_one_body(const PdDev & a, const EmArgs & e, E
     if (freq == 0) {
         if (tid == 0) {
             e.valid[blockIdx.x] = 0; if (e.dbg) { e.dbg[4 * blockIdx.x] = 1; e.dbg[4 * blockIdx.x + 1] = len; e.dbg[4 * blockIdx.x + 2] = 0; }
-            if (!FUSED) e.states[blockIdx.x].alive = 0;
         }
         return;
     }
@@ -715,7 +708,7 @@ __device__ __forceinline__ void em_one_body(const PdDev & a, const EmArgs & e, E
         // whose reference shift did not change has exactly the likelihoods and moments it already holds: skip the pass.
         const bool same = e.sort_samples && curL != INT_MIN && dlS == curS && dmx < dlL - k.hist_base + 1 && dmx < curL - k.hist_base + 1;
         if (!same) {
-            dl_one<LPS, SLOTS, BATCH, PREF>(k, cache_dev, pd, T, tid, sub, nl, dlS, dlL, gmask, rgw, x0, E0, E1, E2, Sr, Srd);
+            dl_one<LPS, SLOTS, BATCH>(k, cache_dev, pd, T, tid, sub, nl, dlS, dlL, gmask, rgw, x0, E0, E1, E2, Sr, Srd);
             curL = dlL; curS = dlS;
         }
         if (mode == 2) {
@@ -776,20 +769,9 @@ __device__ __forceinline__ void em_one_body(const PdDev & a, const EmArgs & e, E
     if (freq < 0.0000000001 || len < e.min_len) {
         if (tid == 0) {
             e.valid[blockIdx.x] = 0; if (e.dbg) { e.dbg[4 * blockIdx.x] = 2; e.dbg[4 * blockIdx.x + 1] = len; e.dbg[4 * blockIdx.x + 2] = it; }
-            if (!FUSED) e.states[blockIdx.x].alive = 0;
         }
         return;
     }
-    if (!FUSED) {                                        // hand over to k_final (separate launch, smaller register footprint here)
-        if (has && sub == 0) e.shifts[(size_t)blockIdx.x * a.R + s] = shift;
-        if (tid == 0) {
-            EmState st; st.len = len; st.it = it; st.alive = 1; st.pad = 0; st.freq = freq;
-            st.gt[0] = gt.a; st.gt[1] = gt.b; st.gt[2] = gt.c;
-            e.states[blockIdx.x] = st;
-        }
-        return;
-    }
-
     // ---- final pass :665-727 (compute_data_likelihoods final overload :255-337)
     auto reject = [&](uint32_t reason) {
         if (tid == 0) {
@@ -808,12 +790,6 @@ __device__ __forceinline__ void em_one_body(const PdDev & a, const EmArgs & e, E
         uint32_t lad0 = 0, lad1 = 0, lad2 = 0, dad0 = 0, dad1 = 0, dad2 = 0, dad3 = 0, dad4 = 0;
         uint32_t fl_min = 0xFFFFFFFFu, fl_max = 0, ndeg = 0;
         double l0 = 0, l1 = 0, l2 = 0, t0 = 0, t1 = 0, t2 = 0;
-        if (PREF)
-            for (int j = 0; j < nl; ++j) {
-                const int d = j < SLOTS ? cache_dev[j * T + tid] : __ldg(pd + sub + j * LPS);
-                if (tab_in(k, d - shift)) prefetch_l1(k.fl + (d - shift + k.hist_base + 1));
-                if (tab_in(k, d - flen)) prefetch_l1(k.fl + (d - flen + k.hist_base + 1));
-            }
         for (int j = 0; j < nl; ++j) {
             const int d = j < SLOTS ? cache_dev[j * T + tid] : __ldg(pd + sub + j * LPS);
             if (d > upper_q) { if (d < delLower) ++dad2; else if (d <= delUpper) ++dad3; else ++dad4; }
@@ -941,7 +917,7 @@ __device__ __forceinline__ void em_one_body(const PdDev & a, const EmArgs & e, E
     }
 }
 
-template <int LPS, int SLOTS, int BATCH, bool PREF, int MAXT, int MINB>
+template <int LPS, int SLOTS, int BATCH, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_em_one(PdDev a, EmArgs e)
 {
     __shared__ EmShared sh;
@@ -949,20 +925,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_em_one(PdDev a, EmArgs e)
     __shared__ uint32_t s_nsupp;
     __shared__ uint16_t s_perm[256];
     extern __shared__ int32_t cache_dev[];              // [SLOTS][T] deviations of this block's read pairs
-    em_one_body<LPS, SLOTS, BATCH, PREF, true>(a, e, sh, s_first, s_last, s_nsupp, s_perm, cache_dev);
+    em_one_body<LPS, SLOTS, BATCH>(a, e, sh, s_first, s_last, s_nsupp, s_perm, cache_dev);
     publish_done(e, blockIdx.x);
 }
-// EM loop only (experiment PD_EM_SPLIT=1): the final pass runs as k_final<1, ...> in a second launch
-template <int LPS, int SLOTS, int BATCH, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) k_em_one_loop(PdDev a, EmArgs e)
-{
-    __shared__ EmShared sh;
-    __shared__ uint32_t s_nsupp;
-    __shared__ uint16_t s_perm[256];
-    extern __shared__ int32_t cache_dev[];
-    em_one_body<LPS, SLOTS, BATCH, false, false>(a, e, sh, nullptr, nullptr, s_nsupp, s_perm, cache_dev);
-}
-
 // ------------------------------------------------------------------------------------------------------------------
 // emission: calls of a chunk in pair order -> mapped host memory
 // ------------------------------------------------------------------------------------------------------------------
@@ -1070,11 +1035,11 @@ cudaError_t launch_xr_t(const PdDev & a, const EmArgs & e, uint32_t T, cudaStrea
     return cudaGetLastError();
 }
 
-template <int LPS, int SLOTS, bool PREF, int MAXT, int MINB, int BATCH = 2>
+template <int LPS, int SLOTS, int MAXT, int MINB, int BATCH>
 cudaError_t launch_one_t(const PdDev & a, const EmArgs & e, uint32_t T, cudaStream_t st)
 {
     const size_t smem = (size_t)SLOTS * T * sizeof(int32_t);
-    k_em_one<LPS, SLOTS, BATCH, PREF, MAXT, MINB><<<e.npairs, T, smem, st>>>(a, e);
+    k_em_one<LPS, SLOTS, BATCH, MAXT, MINB><<<e.npairs, T, smem, st>>>(a, e);
     return cudaGetLastError();
 }
 
@@ -1105,48 +1070,17 @@ int pd_launch_em(pd_ctx * c, const PdDev & a, const EmArgs & e, cudaStream_t st,
         *launches += 2;
         return 0;
     }
-    // one read group per sample and the cohort fits one block: fused EM + final pass with per-sample state in registers
+    // one read group per sample and the cohort fits one block: fused EM + final pass with per-sample state in registers.
+    // Measured on B200 (100 samples x chr21, ms per step): one look-up pair in flight at 80 registers / 6 blocks per SM
+    // 3.44; two in flight at 96 registers / 5 blocks 3.56; 3 / 4 in flight 3.72 / 4.02; 72 / 64 registers (7 / 8 blocks,
+    // spills) 3.78 / 3.86; L1 prefetch of the table rows 5.0; two lanes per sample 5.4; EM loop and final pass as two
+    // kernels 3.56-3.76.
     if (a.R == a.N && a.N <= 256 && !getenv("PD_EM_GENERAL")) {
-        uint32_t lps1 = a.N <= 256 ? 1 : 2;
-        if (getenv("PD_EM_LPS")) lps1 = (uint32_t)atoi(getenv("PD_EM_LPS"));                           // tuning knobs
-        const bool pref = getenv("PD_EM_PREFETCH") ? atoi(getenv("PD_EM_PREFETCH")) != 0 : false;
-        if (lps1 == 1 || lps1 == 2) {
-            const uint32_t T1 = ((a.N * lps1 + 31) / 32) * 32;
-            cudaError_t err1;
-            const int minb = getenv("PD_EM_MINB") ? atoi(getenv("PD_EM_MINB")) : 0;
-            // measured on B200 (100 samples x chr21): one look-up pair in flight at 80 registers (6 blocks per SM) beats
-            // deeper batching at 96-128 registers (5-4 blocks): 3.44 vs 3.56 / 3.72 / 4.02 ms per step
-            const int batch = getenv("PD_EM_BATCH") ? atoi(getenv("PD_EM_BATCH")) : (T1 <= 128 && lps1 == 1 ? 1 : 2);
-            const int split = getenv("PD_EM_SPLIT") ? atoi(getenv("PD_EM_SPLIT")) : 0;
-            if (split && lps1 == 1 && T1 <= 128) {
-                const size_t smem = (size_t)32 * T1 * sizeof(int32_t);
-                if (split == 1) k_em_one_loop<1, 32, 1, 128, 8><<<e.npairs, T1, smem, st>>>(a, e);
-                else if (split == 2) k_em_one_loop<1, 32, 1, 128, 7><<<e.npairs, T1, smem, st>>>(a, e);
-                else k_em_one_loop<1, 32, 2, 128, 6><<<e.npairs, T1, smem, st>>>(a, e);
-                k_final<1, 128, 6><<<e.npairs, T1, 0, st>>>(a, e);
-                if (cudaGetLastError() != cudaSuccess) return pd_fail(c, PD_ERR_CUDA, "k_em_one_loop / k_final launch");
-                *launches += 2;
-                return 0;
-            }
-            if (lps1 == 1 && T1 <= 128 && batch == 3) err1 = launch_one_t<1, 32, false, 128, 5, 3>(a, e, T1, st);
-            else if (lps1 == 1 && T1 <= 128 && batch == 4) err1 = launch_one_t<1, 32, false, 128, 4, 4>(a, e, T1, st);
-            else if (lps1 == 1 && T1 <= 128 && batch == 1 && minb == 7) err1 = launch_one_t<1, 32, false, 128, 7, 1>(a, e, T1, st);
-            else if (lps1 == 1 && T1 <= 128 && batch == 1 && minb == 8) err1 = launch_one_t<1, 32, false, 128, 8, 1>(a, e, T1, st);
-            else if (lps1 == 1 && T1 <= 128 && batch == 1) err1 = launch_one_t<1, 32, false, 128, 6, 1>(a, e, T1, st);
-            else if (lps1 == 1 && T1 <= 128 && batch == 2 && minb == 6) err1 = launch_one_t<1, 32, false, 128, 6, 2>(a, e, T1, st);
-            else if (lps1 == 1 && T1 <= 128 && minb == 5) err1 = launch_one_t<1, 32, false, 128, 5>(a, e, T1, st);
-            else if (lps1 == 1 && T1 <= 128 && minb == 4) err1 = launch_one_t<1, 32, false, 128, 4>(a, e, T1, st);
-            else if (lps1 == 2 && T1 <= 224 && minb == 3) err1 = launch_one_t<2, 16, false, 224, 3>(a, e, T1, st);
-            else if (lps1 == 2 && T1 <= 224 && minb == 2) err1 = launch_one_t<2, 16, false, 224, 2>(a, e, T1, st);
-            else if (lps1 == 1 && T1 <= 128 && minb == 7) err1 = launch_one_t<1, 32, false, 128, 7>(a, e, T1, st);
-            else if (lps1 == 1 && T1 <= 128) err1 = pref ? launch_one_t<1, 32, true, 128, 5>(a, e, T1, st) : launch_one_t<1, 32, false, 128, 5>(a, e, T1, st);
-            else if (lps1 == 1) err1 = pref ? launch_one_t<1, 32, true, 256, 3>(a, e, T1, st) : launch_one_t<1, 32, false, 256, 3>(a, e, T1, st);
-            else if (T1 <= 224) err1 = pref ? launch_one_t<2, 16, true, 224, 4>(a, e, T1, st) : launch_one_t<2, 16, false, 224, 4>(a, e, T1, st);
-            else err1 = pref ? launch_one_t<2, 16, true, 512, 2>(a, e, T1, st) : launch_one_t<2, 16, false, 512, 2>(a, e, T1, st);
-            if (err1 != cudaSuccess) return pd_fail(c, PD_ERR_CUDA, std::string("k_em_one launch: ") + cudaGetErrorString(err1));
-            *launches += 1;
-            return 0;
-        }
+        const uint32_t T1 = ((a.N + 31) / 32) * 32;
+        const cudaError_t err1 = T1 <= 128 ? launch_one_t<1, 32, 128, 6, 1>(a, e, T1, st) : launch_one_t<1, 32, 256, 3, 2>(a, e, T1, st);
+        if (err1 != cudaSuccess) return pd_fail(c, PD_ERR_CUDA, std::string("k_em_one launch: ") + cudaGetErrorString(err1));
+        *launches += 1;
+        return 0;
     }
     // lanes per sample (LPS): small cohorts get several lanes per sample so that one block covers all samples at once;
     // each (LPS, block size) class has its own register budget (launch bounds) to keep >= 2 blocks per SM
