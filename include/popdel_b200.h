@@ -82,6 +82,11 @@ typedef struct {
     uint64_t n_kernel_launches;    /* kernels of this library launched by this scan */
     float    ms_h2d, ms_screen, ms_genotype, ms_d2h, ms_total;   /* CUDA-event times on the library's stream */
     float    ms_stream;            /* the HBM-bound streaming kernel of the screen alone (k_stream) */
+    /* pd_set_unify only: calls / per_sample hold the MERGED variants of every segment (segment order, then
+     * position / length order like unifyCalls' output) */
+    const uint32_t * significant_windows;   /* n_calls x Call::significantWindows (SWIN); NULL without pd_set_unify */
+    uint64_t n_window_calls;       /* window calls before the merge (they stayed on the device) */
+    float    ms_unify;
 } pd_result;
 
 /* Host: processHistogram(hist, 256, smoothing, pseudoCountFraction), insert_histogram_popdel.h:974-986, in place.
@@ -121,6 +126,21 @@ int pd_contig_upload(pd_ctx * ctx);
  * window calls. Uploads first if needed. `out` stays valid until the next call on this context. */
 int pd_contig_scan(pd_ctx * ctx, uint64_t first_window, uint64_t n_windows, pd_result * out);
 
+/* = unifyCalls(calls, meanStddev, minRelWinCover, outputFailed) per processSegment() call (utils_popdel.h:567-654,
+ * workflow_popdel.h:48) ON THE DEVICE: after pd_set_unify(ctx, &p) every pd_contig_scan keeps its window calls and
+ * their per-sample rows in device memory, merges the windows of every segment into variants there (sort by position /
+ * length / LR, chain of similar calls, median start and length, PLs summed over the variant's windows and
+ * re-normalised, median LAD / DAD, allele frequency from the genotypes, CSWin filter bit 16) and returns only the
+ * merged variants. Segments with a single window call, or without a passing one (unless output_failed), return
+ * nothing, like the reference. pd_set_unify(ctx, NULL) switches back to window calls. Not available for
+ * sample-sharded contexts. */
+typedef struct {
+    double  mean_stddev;                   /* mean insert-size standard deviation over all read groups */
+    double  min_relative_window_cover;     /* -c, default 0.5 */
+    int32_t output_failed;                 /* -F */
+    int32_t reserved;
+} pd_unify_params;
+int pd_set_unify(pd_ctx * ctx, const pd_unify_params * p);
 /* Sizes the tile tables of the open contig for at least `n_windows` windows (call between pd_contig_begin and the
  * upload). Needed by sample-sharded cohorts, whose ranks must cover the COHORT's window range (normally contig length
  * / 30 + 2) although their own samples' read pairs may end earlier. */

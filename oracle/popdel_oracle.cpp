@@ -1214,6 +1214,35 @@ extern "C" int64_t orc_scan_contig(const orc_params * p, uint32_t n_samples, uin
     return (int64_t)raw.size();
 }
 
+// Segment-level merge of window calls given in memory (test hook for the device-side unify of popdel_b200): the calls of
+// one processSegment() = a run of equal `segment` tags; every run goes through unify() (ref utils_popdel.h:567-654) and
+// the surviving variants are appended to the output in run order. Returns the number of variants.
+extern "C" int64_t orc_unify_segments(const orc_call * calls, const uint32_t * per_sample, int64_t n_calls, uint32_t n_samples,
+                                      double mean_stddev, double min_cover, int output_failed,
+                                      orc_call * out_calls, uint32_t * out_ps, uint32_t * out_sig)
+{
+    int64_t n_out = 0;
+    const size_t row = 13ull * n_samples;
+    for (int64_t k = 0; k < n_calls;) {
+        std::vector<CallRec> seg;
+        const uint32_t sidx = calls[k].segment;
+        for (; k < n_calls && calls[k].segment == sidx; ++k) {
+            CallRec r;
+            r.c = calls[k];
+            r.ps.assign(per_sample + row * k, per_sample + row * (k + 1));
+            seg.push_back(std::move(r));
+        }
+        if (!unify(seg, mean_stddev, min_cover, output_failed != 0)) continue;
+        for (const CallRec & r : seg) {
+            out_calls[n_out] = r.c;
+            memcpy(out_ps + row * n_out, r.ps.data(), row * sizeof(uint32_t));
+            out_sig[n_out] = r.significantWindows;
+            ++n_out;
+        }
+    }
+    return n_out;
+}
+
 extern "C" int orc_call_files(const char * const * files, uint32_t n_files, const char * dump_path,
                               int window_wise, int dump_windows, int uncompressed, uint32_t min_init_len,
                               uint32_t max_load, int64_t * n_windows_scanned)

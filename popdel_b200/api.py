@@ -42,7 +42,13 @@ class PdResult(C.Structure):
                 ("n_reads", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_kernel_launches", C.c_uint64),
                 ("ms_h2d", C.c_float), ("ms_screen", C.c_float), ("ms_genotype", C.c_float), ("ms_d2h", C.c_float),
-                ("ms_total", C.c_float), ("ms_stream", C.c_float)]
+                ("ms_total", C.c_float), ("ms_stream", C.c_float),
+                ("significant_windows", C.POINTER(C.c_uint32)), ("n_window_calls", C.c_uint64), ("ms_unify", C.c_float)]
+
+
+class PdUnifyParams(C.Structure):
+    _fields_ = [("mean_stddev", C.c_double), ("min_relative_window_cover", C.c_double), ("output_failed", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 CALL_DTYPE = np.dtype([("initial_length", "<u4"), ("iterations", "<u4"), ("deletion_length", "<u4"), ("filter", "<u4"),
@@ -52,7 +58,7 @@ CALL_DTYPE = np.dtype([("initial_length", "<u4"), ("iterations", "<u4"), ("delet
 EXPORTS = ["pd_process_histogram", "pd_create", "pd_create_error", "pd_destroy", "pd_last_error", "pd_contig_begin",
            "pd_contig_push", "pd_contig_push_pinned", "pd_contig_upload", "pd_contig_scan", "pd_contig_window_count", "pd_synth_read_group",
            "pd_debug_host_window_sums", "pd_contig_reserve_windows", "pd_shard_unique_id", "pd_shard_attach_nccl",
-           "pd_shard_attach_group", "pd_shard_group_scan"]
+           "pd_shard_attach_group", "pd_shard_group_scan", "pd_set_unify"]
 
 _lib = None
 
@@ -97,6 +103,7 @@ def load_library(path: str = LIB_PATH):
     lib.pd_shard_attach_nccl.argtypes = [C.c_void_p, C.POINTER(PdShardInfo), C.POINTER(C.c_uint8)]
     lib.pd_shard_attach_group.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(PdShardInfo)]
     lib.pd_shard_group_scan.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(PdResult)]
+    lib.pd_set_unify.argtypes = [C.c_void_p, C.POINTER(PdUnifyParams)]
     _lib = lib
     return lib
 
@@ -258,11 +265,23 @@ class Scanner:
             if n:
                 C.memmove(calls.ctypes.data, res.calls, n * CALL_DTYPE.itemsize)
                 C.memmove(per.ctypes.data, res.per_sample, per.nbytes)
+        sig = None
+        if res.significant_windows:
+            sig = np.ctypeslib.as_array(res.significant_windows, shape=(max(n, 1),))[:n].copy()
         return dict(calls=calls, per_sample=per, n_windows=res.n_windows, n_flagged_windows=res.n_flagged_windows,
                     n_candidates=res.n_candidates, n_reads=res.n_reads, algorithmic_bytes=res.algorithmic_bytes,
                     h2d_bytes=res.h2d_bytes, d2h_bytes=res.d2h_bytes, n_kernel_launches=res.n_kernel_launches,
                     ms_h2d=res.ms_h2d, ms_screen=res.ms_screen, ms_genotype=res.ms_genotype, ms_total=res.ms_total,
-                    ms_stream=res.ms_stream)
+                    ms_stream=res.ms_stream, significant_windows=sig, n_window_calls=res.n_window_calls, ms_unify=res.ms_unify)
+
+    def set_unify(self, mean_stddev=None, min_relative_window_cover: float = 0.5, output_failed: bool = False):
+        """pd_set_unify: scans return the merged variants of every segment (unifyCalls, utils_popdel.h:567-654, run on the
+        device); mean_stddev=None switches back to window calls."""
+        if mean_stddev is None:
+            self._check(self.lib.pd_set_unify(self.ctx, None))
+            return
+        p = PdUnifyParams(float(mean_stddev), float(min_relative_window_cover), int(bool(output_failed)), 0)
+        self._check(self.lib.pd_set_unify(self.ctx, C.byref(p)))
 
     def reserve_windows(self, n_windows: int):
         self._check(self.lib.pd_contig_reserve_windows(self.ctx, int(n_windows)))
@@ -323,14 +342,17 @@ def cohort_anchor(samples) -> int:
 
 
 def scan_cohort(samples, params: CallParameters, device: int = 0, first_window: int = 0, n_windows: int = 0,
-                pinned: bool = False):
-    """Convenience: whole in-memory cohort (popdel_b200.simulate objects) -> window calls of one contig."""
+                pinned: bool = False, unify: dict = None):
+    """Convenience: whole in-memory cohort (popdel_b200.simulate objects) -> window calls of one contig, or -- with
+    unify=dict(mean_stddev=..., min_relative_window_cover=..., output_failed=...) -- the merged variants."""
     rgs = read_groups_from_headers([[dict(name=rg.spec.name, median=rg.median, stddev=rg.stddev,
                                           read_length=rg.spec.read_length, hist_start=rg.hist_start,
                                           hist_end=rg.hist_end, hist_counts=rg.hist_counts) for rg in s.read_groups]
                                     for s in samples], params)
     sc = Scanner(params, rgs, len(samples), device)
     try:
+        if unify:
+            sc.set_unify(**unify)
         sc.begin_contig(cohort_anchor(samples))
         g = 0
         for s in samples:

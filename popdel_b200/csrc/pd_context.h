@@ -117,6 +117,13 @@ struct pd_ctx {
     pd_call * res_calls = nullptr; size_t cap_res_calls = 0;   // page-locked, mapped: written by the device (k_emit_rows)
     uint32_t * res_ps = nullptr; size_t cap_res_ps = 0;        // page-locked, mapped
     uint32_t * res_count = nullptr;                            // page-locked, mapped: [0] = number of calls
+    // device-side unifyCalls (pd_unify.cu): window calls stay on the device, merged variants go to res_*
+    bool unify_on = false;
+    pd_unify_params unify{};
+    pd_call * d_u_calls = nullptr; size_t cap_u_calls = 0;
+    uint32_t * d_u_ps = nullptr; size_t cap_u_ps = 0;
+    void * d_unify[10] = {}; size_t cap_unify[10] = {};
+    uint32_t * res_sig = nullptr; size_t cap_res_sig = 0;     // page-locked, mapped: significantWindows per variant
     // word -> tile index of the current upload (k_stream's slow path) and wide-list ranges per read group
     bool index_built = false;
     uint32_t * d_gran_off = nullptr, * d_gran_tile = nullptr, * d_long_off = nullptr; size_t cap_gran = 0;
@@ -132,5 +139,9 @@ int pd_pack_on_device(pd_ctx * c);                // pd_pack.cu: 0 ok, 1 = use t
 int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result * out);   // pd_scan.cu
 uint64_t pd_tail_windows(const PdTail & t, uint32_t window_buffer);
 void pd_shard_release(pd_ctx * c);                // pd_shard.cu
+int pd_unify_ensure_raw(pd_ctx * c, size_t need_calls, size_t row, size_t keep_calls);       // pd_unify.cu
+void pd_unify_release(pd_ctx * c);
+int pd_run_unify(pd_ctx * c, uint32_t n_raw, size_t row, uint32_t nseg, int (*ensure_results)(pd_ctx *, size_t, size_t, size_t),
+                 uint64_t * n_out, uint64_t * launches);
 
 #endif

@@ -209,6 +209,7 @@ extern "C" void pd_destroy(pd_ctx * c)
         cudaSetDevice(c->device);
         cudaFree(c->d_words); cudaFree(c->d_tiles); cudaFree(c->d_longs);
         pd_shard_release(c);
+        pd_unify_release(c);
         for (auto & e : c->ev_pack) if (e) cudaEventDestroy(e);
         cudaFree(c->d_rgc); cudaFree(c->d_sample_rg); cudaFree(c->d_tab); cudaFree(c->d_min_init);
         if (c->res_ps) cudaFreeHost(c->res_ps);
@@ -527,6 +528,17 @@ extern "C" int pd_contig_upload(pd_ctx * c)
     PD_CUDA(c, cudaStreamSynchronize(c->stream));
     PD_CUDA(c, cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]));
     c->uploaded = true; c->index_built = false;
+    return 0;
+}
+
+extern "C" int pd_set_unify(pd_ctx * c, const pd_unify_params * p)
+{
+    if (!c) return PD_ERR_ARG;
+    if (c->status) return c->status;
+    if (!p) { c->unify_on = false; return 0; }
+    if (c->shard) return pd_fail(c, PD_ERR_ARG, "pd_set_unify: not available for sample-sharded contexts (merge the gathered rows on the host)");
+    if (!(p->mean_stddev >= 0) || !(p->min_relative_window_cover >= 0)) return pd_fail(c, PD_ERR_ARG, "pd_set_unify: negative or NaN parameter");
+    c->unify = *p; c->unify_on = true;
     return 0;
 }
 

@@ -116,7 +116,10 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
     // sizes that decide the batching must be the same on every rank of a sharded cohort
     const uint32_t Nb = sh ? sh->n_local_max : N, Rb = sh ? sh->r_global : R, Ng = sh ? sh->n_global : N;
     const size_t row = 13ull * N;
+    const bool uni = c->unify_on;                                     // window calls stay on the device, merged there
+    if (uni && sh) return pd_fail(c, PD_ERR_ARG, "device-side unify is not available for sample-sharded contexts");
     if (ensure_results(c, 1, row, 0)) return c->status;
+    if (uni && pd_unify_ensure_raw(c, 1, row, 0)) return c->status;
     c->res_count[0] = 0;
     out->n_reads = c->n_reads;
     out->algorithmic_bytes = 4ull * c->n_reads;
@@ -375,10 +378,10 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
                 PD_CUDA(c, cudaMemsetAsync(e.done, 0, (size_t)np * 4, st));
                 // result capacity: upper bound = calls emitted so far (exact once stream2 is drained) + this chunk
                 const size_t upper = (size_t)(n_pairs_total - n_pairs + p0 + np);
-                if (upper > c->cap_res_calls || upper * row > c->cap_res_ps) {
+                if (uni ? (upper > c->cap_u_calls || upper * row > c->cap_u_ps) : (upper > c->cap_res_calls || upper * row > c->cap_res_ps)) {
                     PD_CUDA(c, cudaStreamSynchronize(st2));
                     const size_t have = c->res_count[0];
-                    if (ensure_results(c, have + np, row, have)) return c->status;
+                    if (uni ? pd_unify_ensure_raw(c, have + np, row, have) : ensure_results(c, have + np, row, have)) return c->status;
                 }
                 // the emitter of this chunk starts on stream2 as soon as the flags are cleared and runs CONCURRENTLY with
                 // the EM launch below, copying finished pairs to the host in pair order while later pairs are computed
@@ -386,7 +389,7 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
                 EmitArgs m;
                 m.valid = e.valid; m.calls = e.calls; m.ps = e.ps; m.npairs = np; m.row_words = (uint32_t)row; m.done = e.done;
                 m.counters = d_counters; m.emit_blocks_done = d_emit_state;
-                m.out_calls = c->res_calls; m.out_ps = c->res_ps; m.out_count = c->res_count;
+                m.out_calls = uni ? c->d_u_calls : c->res_calls; m.out_ps = uni ? c->d_u_ps : c->res_ps; m.out_count = c->res_count;
                 if (sh && pd_shard_prelaunch(c)) return c->status;
                 // (EM first: CUDA loads kernels lazily and a first-time load may wait for running kernels -- the emitter,
                 // which only waits for ev[6], must never be the one that is running while the EM kernel is being loaded)
@@ -420,6 +423,16 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
         if (xerr) return pd_fail(c, PD_ERR_CUDA, "sample-sharded scan: a peer rank did not answer an in-kernel exchange in time");
     }
     out->n_calls = c->res_count[0];
+    out->n_window_calls = out->n_calls;
+    if (uni) {
+        const uint32_t nseg = (uint32_t)((w_end * PD_WIN) / c->grid.window_buffer + 2);
+        PD_CUDA(c, cudaEventRecord(c->ev[11], st));
+        if (pd_run_unify(c, (uint32_t)out->n_window_calls, row, nseg, ensure_results, &out->n_calls, nl)) return c->status;
+        PD_CUDA(c, cudaEventRecord(c->ev[5], st));
+        PD_CUDA(c, cudaStreamSynchronize(st));
+        PD_CUDA(c, cudaEventElapsedTime(&out->ms_unify, c->ev[11], c->ev[5]));
+        out->significant_windows = c->res_sig;
+    }
     out->calls = c->res_calls;
     out->per_sample = c->res_ps;
     out->n_candidates = n_pairs_total;

@@ -159,7 +159,8 @@ void convertWindow(const Win & w, std::vector<Bucket> & out)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// calls, segment-level merge (reference utils_popdel.h:237-654) and VCF (vcfout_popdel_call.h)
+// calls and VCF (vcfout_popdel_call.h); the segment-level merge (unifyCalls, utils_popdel.h:237-654) runs on the
+// device behind pd_set_unify
 // ---------------------------------------------------------------------------------------------------------------
 struct Call {
     uint32_t initialLength = 0, iterations = 0, deletionLength = 0, filter = 0;
@@ -169,120 +170,6 @@ struct Call {
 };
 inline bool allPass(const Call & c) { return (c.filter & 31u) == 0; }
 inline void invalidate(Call & c) { c.filter = 255; }
-
-bool sizeSimilar(unsigned a, unsigned b, double sd)
-{
-    const unsigned l = std::min(a, b), r = std::max(a, b);
-    return (l + 2 * sd >= r) || (l >= 0.5 * r);
-}
-bool similarCalls(Call & a, Call & b, double sd)
-{
-    if (!sizeSimilar(a.deletionLength, b.deletionLength, sd)) return false;
-    const unsigned aSpan = a.endPosition - a.position, bSpan = b.endPosition - b.position;
-    const unsigned minLen = std::min(aSpan, bSpan);
-    const unsigned left = std::max(a.position, b.position), right = std::min(a.position + aSpan, b.position + bSpan);
-    const int overlap = (int)(right - left);
-    if (overlap >= 0.25 * minLen || overlap + 2 * sd >= minLen) return true;
-    // checkAndExtend: one of the spans is shorter than its deletion and the starts are close enough
-    if ((aSpan < a.deletionLength || bSpan < b.deletionLength) &&
-        (b.position - a.position < (std::min(a.deletionLength, b.deletionLength) + 4 * sd))) { a.endPosition = b.endPosition; return true; }
-    return false;
-}
-
-struct Merger {
-    std::vector<std::vector<uint32_t>> lists;                // per sample x 8 (LAD 3 + DAD 5)
-    std::vector<uint32_t> plSum;                             // per sample x 3
-    std::vector<unsigned> starts, sizes;
-    long double lr = 0;
-    unsigned callCount = 1, winCount = 1, sigWin = 1;
-
-    void mergeRange(std::vector<Call> & calls, size_t start, size_t last, double minCover)
-    {
-        Call & st = calls[start];
-        std::sort(starts.begin(), starts.end()); st.position = starts[starts.size() / 2]; starts.clear();
-        std::sort(sizes.begin(), sizes.end()); st.deletionLength = sizes[sizes.size() / 2]; sizes.clear();
-        st.lr = (double)(lr / winCount);
-        const size_t N = st.ps.size() / 13;
-        unsigned inRange = 0;
-        for (size_t k = start; k < last; ++k) {
-            const Call & g = calls[k];
-            if (g.windowPosition > st.position && g.windowPosition - 30 < st.position + st.deletionLength) {
-                for (size_t s = 0; s < N; ++s) {
-                    for (int j = 0; j < 3; ++j) plSum[3 * s + j] += g.ps[13 * s + j];
-                    for (int j = 0; j < 8; ++j) lists[8 * s + j].push_back(g.ps[13 * s + 3 + j]);
-                }
-                ++inRange;
-            }
-        }
-        if (inRange == 0) { invalidate(st); return; }
-        unsigned alleles = 0;
-        for (size_t s = 0; s < N; ++s) {
-            uint32_t * g = &plSum[3 * s];
-            const double mn = std::min(std::min(g[0], g[1]), g[2]);
-            const double ref = static_cast<double>(g[0] - mn) / inRange, het = static_cast<double>(g[1] - mn) / inRange,
-                         hom = static_cast<double>(g[2] - mn) / inRange;
-            g[0] = g[1] = g[2] = 0;
-            uint32_t * o = &st.ps[13 * s];
-            o[0] = (uint32_t)std::round(ref); o[1] = (uint32_t)std::round(het); o[2] = (uint32_t)std::round(hom);
-            for (int j = 0; j < 8; ++j) {
-                std::vector<uint32_t> & v = lists[8 * s + j];
-                std::sort(v.begin(), v.end());
-                o[3 + j] = v[v.size() / 2];
-                v.clear();
-            }
-            if (o[1] == o[2]) { if (het > hom) ++o[1]; else ++o[2]; }
-            else if (o[0] == o[1]) { if (ref > het) ++o[0]; else ++o[1]; }
-            if (o[0] == 0) continue;
-            alleles += (o[1] == 0) ? 1 : 2;
-        }
-        st.frequency = static_cast<double>(alleles) / (N * 2);
-        st.significantWindows = sigWin;
-        if (30.0 * sigWin / st.deletionLength < minCover) st.filter |= 16;
-        winCount = 1; sigWin = 1; lr = 0.0; ++callCount;
-    }
-};
-
-bool unifySegment(std::vector<Call> & calls, double meanStddev, double minCover, bool outputFailed)
-{
-    if (calls.size() <= 1) return false;
-    std::stable_sort(calls.begin(), calls.end(), [](const Call & l, const Call & r) {
-        if (l.position != r.position) return l.position < r.position;
-        if (l.deletionLength != r.deletionLength) return l.deletionLength < r.deletionLength;
-        return l.lr > r.lr;
-    });
-    size_t cur = 0;
-    const size_t last = calls.size() - 1;
-    if (!outputFailed) {
-        while (!allPass(calls[cur])) { if (cur == last) return false; ++cur; }
-        if (cur == last) return false;
-    }
-    const size_t first = cur;
-    const size_t N = calls[cur].ps.size() / 13;
-    Merger m;
-    m.lists.resize(8 * N); m.plSum.assign(3 * N, 0);
-    m.starts.push_back(calls[cur].position); m.sizes.push_back(calls[cur].deletionLength);
-    m.lr = calls[cur].lr;
-    size_t it = first + 1;
-    while (true) {
-        if (similarCalls(calls[cur], calls[it], meanStddev)) {
-            if (allPass(calls[it])) { m.starts.push_back(calls[it].position); m.sizes.push_back(calls[it].deletionLength); ++m.sigWin; }
-            ++m.winCount;
-            m.lr += calls[it].lr;
-            invalidate(calls[it]);
-            if (it == last) { if (!m.starts.empty()) m.mergeRange(calls, cur, it, minCover); break; }
-        } else {
-            if (m.winCount != 1 && !m.starts.empty()) m.mergeRange(calls, cur, it, minCover);
-            else invalidate(calls[cur]);
-            cur = it;
-        }
-        if (it != last) ++it;
-        else { if (m.winCount == 1) { --m.callCount; invalidate(calls[cur]); } break; }
-    }
-    std::vector<Call> keep;
-    for (size_t k = first; k <= last; ++k) if (calls[k].filter != 255) keep.push_back(std::move(calls[k]));
-    calls.swap(keep);
-    return true;
-}
 
 // LR -> QUAL (reference QuantileMap, parameter_parsing_popdel_call.h:14-136, always built with prior 1e-4):
 // keys qchisq(1-10^(-i/10), df=1)/2 - ln(prior/(1-prior)), i = 1..100; QUAL = i of the largest key <= LR.
@@ -496,6 +383,11 @@ int main(int argc, char ** argv)
     pd_ctx * ctx = pd_create(&prm, (uint32_t)N, (uint32_t)R, rgs.data(), opt.device);
     if (!ctx) die(std::string("cannot create the scan context: ") + pd_create_error());
     auto check = [&](int rc) { if (rc != 0) die(std::string("scan library: ") + pd_last_error(ctx)); };
+    if (!opt.windowWise) {                                           // unifyCalls per segment, on the device
+        pd_unify_params up; memset(&up, 0, sizeof(up));
+        up.mean_stddev = meanStddev; up.min_relative_window_cover = opt.minCover; up.output_failed = opt.outputFailed;
+        check(pd_set_unify(ctx, &up));
+    }
 
     std::ofstream out(opt.out);
     if (!out.good()) die("cannot open output '" + opt.out + "'");
@@ -565,26 +457,19 @@ int main(int argc, char ** argv)
         pd_result res;
         check(pd_contig_scan(ctx, 0, 0, &res));
         totalWindows += res.n_windows;
-        // calls of one processSegment() call = calls with the same segment index
+        // window calls (-n) or the merged variants of every segment, already in output order
         const std::string & chrom = profiles[0].contigNames[c];
-        size_t k = 0;
-        while (k < res.n_calls) {
-            std::vector<Call> seg;
-            const uint32_t sidx = res.calls[k].segment;
-            for (; k < res.n_calls && res.calls[k].segment == sidx; ++k) {
-                const pd_call & pc = res.calls[k];
-                Call cl;
-                cl.initialLength = pc.initial_length; cl.iterations = pc.iterations; cl.deletionLength = pc.deletion_length;
-                cl.filter = pc.filter; cl.lr = pc.lr; cl.frequency = pc.frequency; cl.windowPosition = pc.window_position;
-                cl.position = pc.position; cl.endPosition = pc.end_position;
-                cl.ps.assign(res.per_sample + k * 13ull * N, res.per_sample + (k + 1) * 13ull * N);
-                seg.push_back(std::move(cl));
-            }
-            if (!opt.windowWise && !unifySegment(seg, meanStddev, opt.minCover, opt.outputFailed)) continue;
-            for (const Call & cl : seg)
-                if (cl.iterations != 0 && (opt.outputFailed || allPass(cl))) { writeRecord(out, chrom, cl, qm); ++totalCalls; }
-            out.flush();
+        for (size_t k = 0; k < res.n_calls; ++k) {
+            const pd_call & pc = res.calls[k];
+            Call cl;
+            cl.initialLength = pc.initial_length; cl.iterations = pc.iterations; cl.deletionLength = pc.deletion_length;
+            cl.filter = pc.filter; cl.lr = pc.lr; cl.frequency = pc.frequency; cl.windowPosition = pc.window_position;
+            cl.position = pc.position; cl.endPosition = pc.end_position;
+            cl.significantWindows = res.significant_windows ? res.significant_windows[k] : 0;
+            cl.ps.assign(res.per_sample + k * 13ull * N, res.per_sample + (k + 1) * 13ull * N);
+            if (cl.iterations != 0 && (opt.outputFailed || allPass(cl))) { writeRecord(out, chrom, cl, qm); ++totalCalls; }
         }
+        out.flush();
     }
     pd_destroy(ctx);
     std::cout << "[popdel_b200] scanned " << totalWindows << " windows x " << N << " samples, wrote " << totalCalls

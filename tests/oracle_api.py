@@ -42,6 +42,34 @@ class Oracle:
                                              C.c_uint32, C.c_uint32, C.POINTER(OrcCall), C.POINTER(C.c_uint32),
                                              C.c_int64, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)]
 
+    def unify_segments(self, calls, per_sample, mean_stddev, min_cover=0.5, output_failed=False):
+        """unifyCalls (utils_popdel.h:567-654) on in-memory window calls (popdel_b200.api.CALL_DTYPE records with
+        `segment` tags, per_sample [n, N, 13]). Returns (variants in the same dtype, per_sample, significant windows)."""
+        n, N = len(calls), per_sample.shape[1]
+        inp = (OrcCall * max(n, 1))()
+        for i, c in enumerate(calls):
+            inp[i] = OrcCall(initial_length=int(c["initial_length"]), iterations=int(c["iterations"]),
+                             deletion_length=int(c["deletion_length"]), lr=float(c["lr"]), frequency=float(c["frequency"]),
+                             window_position=int(c["window_position"]), position=int(c["position"]),
+                             end_position=int(c["end_position"]), filter=int(c["filter"]), segment=int(c["segment"]))
+        ps = np.ascontiguousarray(per_sample, dtype=np.uint32)
+        out = (OrcCall * max(n, 1))()
+        out_ps = np.zeros((max(n, 1), N, 13), dtype=np.uint32)
+        out_sig = np.zeros(max(n, 1), dtype=np.uint32)
+        self.lib.orc_unify_segments.restype = C.c_int64
+        self.lib.orc_unify_segments.argtypes = [C.POINTER(OrcCall), C.POINTER(C.c_uint32), C.c_int64, C.c_uint32, C.c_double,
+                                                C.c_double, C.c_int, C.POINTER(OrcCall), C.POINTER(C.c_uint32),
+                                                C.POINTER(C.c_uint32)]
+        m = self.lib.orc_unify_segments(inp, ps.ctypes.data_as(C.POINTER(C.c_uint32)), n, N, float(mean_stddev),
+                                        float(min_cover), int(bool(output_failed)), out,
+                                        out_ps.ctypes.data_as(C.POINTER(C.c_uint32)), out_sig.ctypes.data_as(C.POINTER(C.c_uint32)))
+        res = np.zeros(m, dtype=calls.dtype)
+        for i in range(m):
+            for f in ("initial_length", "iterations", "deletion_length", "lr", "frequency", "window_position", "position",
+                      "end_position", "filter", "segment"):
+                res[f][i] = getattr(out[i], f)
+        return res, out_ps[:m].copy(), out_sig[:m].copy()
+
     def process_histogram(self, counts, offset, median, read_length, smoothing=True, pseudo=500):
         v = np.ascontiguousarray(counts, dtype=np.float64).copy()
         lq, uq = C.c_uint32(0), C.c_uint32(0)

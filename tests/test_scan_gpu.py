@@ -146,3 +146,42 @@ def test_device_packer_with_empty_and_single_read_groups():
     a, _ = api.scan_cohort(one, params)
     b, _ = api.scan_cohort(one, params, pinned=True)
     assert_calls_equal(b["calls"], b["per_sample"], a["calls"], a["per_sample"], rtol=0)
+
+
+def _mean_stddev(rgs):
+    return float(np.mean([r.as_dict()["stddev"] for r in rgs]))
+
+
+@pytest.mark.parametrize("output_failed", [False, True])
+@pytest.mark.parametrize("kind", ["basic", "mixedrg", "gap", "highcov", "longspan"])
+def test_device_unify_equals_oracle_unify(kind, output_failed, oracle_lib):
+    """pd_set_unify (unifyCalls on the device): the merged variants equal the oracle's unifyCalls
+    (utils_popdel.h:567-654, pinned against the reference's merged VCFs) applied to the same window calls."""
+    samples, params = _cohort(kind)
+    raw, rgs = api.scan_cohort(samples, params)
+    sd = _mean_stddev(rgs)
+    uni, _ = api.scan_cohort(samples, params, unify=dict(mean_stddev=sd, min_relative_window_cover=0.5, output_failed=output_failed))
+    ref_calls, ref_ps, ref_sig = oracle_lib.unify_segments(raw["calls"], raw["per_sample"], sd, 0.5, output_failed)
+    assert uni["n_window_calls"] == len(raw["calls"]) and uni["n_windows"] == raw["n_windows"]
+    assert_calls_equal(uni["calls"], uni["per_sample"], ref_calls, ref_ps)
+    assert np.array_equal(uni["significant_windows"], ref_sig)
+    assert 0 < len(ref_calls) < len(raw["calls"])
+
+
+def test_device_unify_larger_cohort_and_buffer_growth(oracle_lib, monkeypatch):
+    """40 samples, several segments, tight window cover; the device-side call buffers start tiny and grow per EM chunk."""
+    samples, _ = simulate.simulate_cohort(seed=35, n_samples=40, contig_len=450_000, n_dels=6)
+    params = api.CallParameters()
+    raw, rgs = api.scan_cohort(samples, params)
+    sd = _mean_stddev(rgs)
+    monkeypatch.setenv("PD_UNIFY_CAP", "8")
+    monkeypatch.setenv("PD_EM_CHUNK", "16")
+    for cover in (0.5, 0.9):
+        uni, _ = api.scan_cohort(samples, params, unify=dict(mean_stddev=sd, min_relative_window_cover=cover, output_failed=True))
+        ref_calls, ref_ps, ref_sig = oracle_lib.unify_segments(raw["calls"], raw["per_sample"], sd, cover, True)
+        assert_calls_equal(uni["calls"], uni["per_sample"], ref_calls, ref_ps)
+        assert np.array_equal(uni["significant_windows"], ref_sig)
+    assert len(ref_calls) >= 3
+    # back to window calls on the same context kind
+    again, _ = api.scan_cohort(samples, params)
+    assert_calls_equal(again["calls"], again["per_sample"], raw["calls"], raw["per_sample"], rtol=0)
