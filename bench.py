@@ -207,6 +207,22 @@ def run_ours(args, rank, world, local_rank):
     dt, evals_all = sharding.reduce_timing(dt, float(evals), dist, "cuda")      # max over ranks / sum over ranks
     value = evals_all * args.steps / dt
 
+    # ---- the same resident scan with the segment-level merge (unifyCalls) on the device: only merged variants cross PCIe
+    sc.set_unify(float(np.mean([r.as_dict()["stddev"] for r in rgs])), 0.5, False)
+    ru = sc.scan(copy=False)
+    barrier()
+    t0 = time.perf_counter()
+    u_steps = max(1, min(args.steps, 5))
+    for _ in range(u_steps):
+        ru = sc.scan(copy=False)
+        launches_u = int(ru["n_kernel_launches"])
+    barrier()
+    dtu = time.perf_counter() - t0
+    sc.set_unify(None)
+    unify = {"ms_per_step": dtu / u_steps * 1e3, "ms_unify_kernels": float(ru["ms_unify"]), "window_calls": int(ru["n_window_calls"]),
+             "variants": int(len(ru["calls"])), "d2h_bytes_per_step": int(ru["d2h_bytes"]), "gpu_launches_per_step": launches_u,
+             "note": "pd_set_unify: window calls and their per-sample rows stay in device memory, every segment is merged there"}
+
     # ---- end to end through the C ABI from host arrays (pack -> pinned -> H2D -> scan -> D2H)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     push_all_pinned()
@@ -276,6 +292,7 @@ def run_ours(args, rank, world, local_rank):
                                  "the e2e step additionally packs on the device, scans and writes the results back"},
                 "host_packer_value": evals_all / dt3, "host_packer_ms_per_step": dt3 * 1e3, "host_packer_h2d_bytes": int(r3["h2d_bytes"])},
         "gpu_launches": launches,
+        "unify": unify,
         "roofline": {"bound": "hbm", "kernel": "k_stream", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "bytes_per_eval": res["algorithmic_bytes"] / evals,
                      "algorithmic_bytes_per_launch": int(res["algorithmic_bytes"]),

@@ -98,6 +98,10 @@ double pd_process_histogram(double * values, uint32_t len, int32_t offset, uint3
  * Returns NULL when no CUDA device is usable (pd_create_error() tells why). */
 pd_ctx * pd_create(const pd_params * params, uint32_t n_samples, uint32_t n_rg, const pd_rg * rgs, int device);
 const char * pd_create_error(void);
+/* Initialises the CUDA context of `device` (no pd_ctx needed). Optional: a caller that has host work to do first
+ * (decoding profiles) can run this on another thread so that pd_create does not pay the ~0.5 s context creation.
+ * Returns 0 or PD_ERR_CUDA. Thread-safe. */
+int pd_device_warmup(int device);
 void pd_destroy(pd_ctx * ctx);
 const char * pd_last_error(pd_ctx * ctx);
 

@@ -202,6 +202,12 @@ extern "C" pd_ctx * pd_create(const pd_params * p, uint32_t n_samples, uint32_t 
     return c;
 }
 
+extern "C" int pd_device_warmup(int device)
+{
+    if (cudaSetDevice(device) != cudaSuccess || cudaFree(nullptr) != cudaSuccess) { cudaGetLastError(); return PD_ERR_CUDA; }
+    return 0;
+}
+
 extern "C" void pd_destroy(pd_ctx * c)
 {
     if (!c) return;

@@ -14,6 +14,7 @@
 //   -g NUM   CUDA device (0)
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -28,6 +29,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <unistd.h>
 #include <zlib.h>
 
 #include "../../include/popdel_b200.h"
@@ -37,11 +39,46 @@ namespace {
 [[noreturn]] void die(const std::string & msg) { std::cerr << "[popdel_b200] " << msg << std::endl; exit(1); }
 inline int rnd(double d) { return (int)std::floor(d + 0.5); }
 
+// fn(i) for i in [0, n) on all host cores (dynamic schedule)
+template <typename F> void parallelFor(size_t n, F fn)
+{
+    const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(n, std::thread::hardware_concurrency()));
+    if (nt <= 1) { for (size_t i = 0; i < n; ++i) fn(i); return; }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nt; ++t) pool.emplace_back([&] { for (size_t i; (i = next.fetch_add(1)) < n;) fn(i); });
+    for (auto & th : pool) th.join();
+}
+
+struct StageTimer {                                          // PD_TIMING=1: wall time per stage on stderr
+    bool on = getenv("PD_TIMING") != nullptr;
+    std::map<std::string, double> acc;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(const char * stage)
+    {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        acc[stage] += std::chrono::duration<double>(t1 - t0).count();
+        t0 = t1;
+    }
+    void report() const { if (on) for (const auto & kv : acc) fprintf(stderr, "[popdel_b200] %-12s %9.3f s\n", kv.first.c_str(), kv.second); }
+};
+
+inline void appendUint(std::string & s, uint64_t v)
+{
+    char buf[24]; int n = 0;
+    do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) s.push_back(buf[--n]);
+}
+inline void appendG(std::string & s, double v)                // default ostream formatting of a double (= %g)
+{
+    char buf[40];
+    s.append(buf, (size_t)snprintf(buf, sizeof(buf), "%g", v));
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // profile files (format: reference insert_histogram_popdel.h:334-525 header, window_podel.h:211-251 records)
 // ---------------------------------------------------------------------------------------------------------------
-struct Rec { uint32_t pos; int32_t dev; };
-struct Win { int32_t chrom; uint32_t begin; std::vector<std::vector<Rec>> rg; };
 struct RgHeader { std::string name; uint32_t median, readLength; double stddev; int32_t offset; std::vector<double> counts; };
 struct Profile {
     std::string path;
@@ -49,8 +86,16 @@ struct Profile {
     std::vector<RgHeader> rgs;
     std::vector<std::string> contigNames;
     std::vector<int32_t> contigLengths;
-    std::vector<Win> wins;                                   // file order
-    std::vector<size_t> contigFirst;                         // first window of each contig (wins.size() if none)
+    // 256-bp window records in file order, flat: the read pairs of (window w, read group g) are
+    // recPos / recDev[winOff[w * nrg + g] .. winOff[w * nrg + g + 1])
+    size_t nrg = 0;
+    std::vector<int32_t> winChrom;
+    std::vector<uint32_t> winBegin;
+    std::vector<uint64_t> winOff;
+    std::vector<uint32_t> recPos;
+    std::vector<int32_t> recDev;
+    std::vector<size_t> contigFirst;                         // first window of each contig (number of windows if none)
+    size_t numWins() const { return winBegin.size(); }
 };
 
 template <typename T> T get(const std::vector<unsigned char> & d, size_t & o)
@@ -109,25 +154,28 @@ void loadProfile(const std::string & path, bool uncompressed, Profile & p)
     std::vector<unsigned char> body;
     if (uncompressed) body.assign(d.begin() + o, d.end());
     else if (o < d.size()) inflateMembers(d, o, body);
+    p.nrg = nrg;
+    p.recPos.reserve(body.size() / 5); p.recDev.reserve(body.size() / 5);
     size_t b = 0;
     while (b + 8 <= body.size()) {
-        Win w; w.chrom = (int32_t)get<uint32_t>(body, b); w.begin = get<uint32_t>(body, b);
-        w.rg.resize(nrg);
+        p.winChrom.push_back((int32_t)get<uint32_t>(body, b)); p.winBegin.push_back(get<uint32_t>(body, b));
+        const uint32_t begin = p.winBegin.back();
         for (uint32_t g = 0; g < nrg; ++g) {
             uint32_t n = get<uint32_t>(body, b);
             if (b + 5ull * n > body.size()) die("truncated window record in '" + path + "'");
-            w.rg[g].resize(n);
+            p.winOff.push_back(p.recPos.size());
             for (uint32_t i = 0; i < n; ++i) {
                 uint8_t offc = body[b]; b += 1;
                 int32_t dv; memcpy(&dv, body.data() + b, 4); b += 4;
-                w.rg[g][i] = Rec{w.begin + offc, dv};
+                p.recPos.push_back(begin + offc); p.recDev.push_back(dv);
             }
         }
-        p.wins.push_back(std::move(w));
     }
-    p.contigFirst.assign(nc + 1, p.wins.size());
-    for (size_t i = p.wins.size(); i-- > 0;) if (p.wins[i].chrom >= 0 && (uint32_t)p.wins[i].chrom < nc) p.contigFirst[p.wins[i].chrom] = i;
-    for (size_t c = nc; c-- > 0;) if (p.contigFirst[c] == p.wins.size()) p.contigFirst[c] = p.contigFirst[c + 1];
+    p.winOff.push_back(p.recPos.size());
+    const size_t nw = p.numWins();
+    p.contigFirst.assign(nc + 1, nw);
+    for (size_t i = nw; i-- > 0;) if (p.winChrom[i] >= 0 && (uint32_t)p.winChrom[i] < nc) p.contigFirst[p.winChrom[i]] = i;
+    for (size_t c = nc; c-- > 0;) if (p.contigFirst[c] == nw) p.contigFirst[c] = p.contigFirst[c + 1];
 }
 
 // first window (file order) whose (contig, index region) is >= (c, region): what the index seek lands on
@@ -136,41 +184,26 @@ size_t indexSeek(const Profile & p, int32_t c, uint32_t pos)
 {
     const uint32_t region = pos / p.indexRegionSize;
     size_t lo = p.contigFirst[c], hi = p.contigFirst[c + 1];
-    while (lo < hi) { size_t mid = (lo + hi) / 2; if (p.wins[mid].begin / p.indexRegionSize < region) lo = mid + 1; else hi = mid; }
+    while (lo < hi) { size_t mid = (lo + hi) / 2; if (p.winBegin[mid] / p.indexRegionSize < region) lo = mid + 1; else hi = mid; }
     return lo;
 }
 
-// 30-bp buckets of a 256-bp window, ascending (reference window_podel.h:314-418): anchored at the window's first read pair
-struct Bucket { uint32_t begin; std::vector<std::vector<Rec>> rg; };
-void convertWindow(const Win & w, std::vector<Bucket> & out)
+// 30-bp buckets of a 256-bp window (reference window_podel.h:314-418): the grid is anchored at the window's first read
+// pair over all read groups; returns that anchor (0xFFFFFFFF for a window without read pairs)
+uint32_t bucketBase(const Profile & p, size_t w)
 {
-    out.clear();
     uint32_t first = 0xFFFFFFFFu;
-    for (const auto & r : w.rg) if (!r.empty()) first = std::min(first, r[0].pos);
-    if (first == 0xFFFFFFFFu) return;
-    const uint32_t base = (first / 30) * 30;
-    std::map<uint32_t, size_t> slot;
-    for (const auto & r : w.rg) for (const Rec & x : r) slot[(x.pos - base) / 30] = 0;
-    size_t k = 0;
-    for (auto & kv : slot) kv.second = k++;
-    out.resize(slot.size());
-    for (auto & kv : slot) { out[kv.second].begin = base + kv.first * 30; out[kv.second].rg.resize(w.rg.size()); }
-    for (size_t g = 0; g < w.rg.size(); ++g) for (const Rec & x : w.rg[g]) out[slot[(x.pos - base) / 30]].rg[g].push_back(x);
+    for (size_t g = 0; g < p.nrg; ++g) {
+        const uint64_t a = p.winOff[w * p.nrg + g], b = p.winOff[w * p.nrg + g + 1];
+        if (a < b) first = std::min(first, p.recPos[a]);
+    }
+    return first == 0xFFFFFFFFu ? first : (first / 30) * 30;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // calls and VCF (vcfout_popdel_call.h); the segment-level merge (unifyCalls, utils_popdel.h:237-654) runs on the
 // device behind pd_set_unify
 // ---------------------------------------------------------------------------------------------------------------
-struct Call {
-    uint32_t initialLength = 0, iterations = 0, deletionLength = 0, filter = 0;
-    double lr = 0, frequency = 0;
-    uint32_t windowPosition = 0, position = 0, endPosition = 0, significantWindows = 0;
-    std::vector<uint32_t> ps;                                // 13 per sample: PL[3] LAD[3] DAD[5] FL[2]
-};
-inline bool allPass(const Call & c) { return (c.filter & 31u) == 0; }
-inline void invalidate(Call & c) { c.filter = 255; }
-
 // LR -> QUAL (reference QuantileMap, parameter_parsing_popdel_call.h:14-136, always built with prior 1e-4):
 // keys qchisq(1-10^(-i/10), df=1)/2 - ln(prior/(1-prior)), i = 1..100; QUAL = i of the largest key <= LR.
 struct QualMap {
@@ -239,13 +272,15 @@ void writeHeader(std::ostream & out, const Profile & first, const std::vector<st
     out << "\n";
 }
 
-void writeRecord(std::ostream & out, const std::string & chrom, const Call & c, const QualMap & qm)
+// one VCF record (vcfout_popdel_call.h:61-205) appended to `out`; per-sample columns are formatted without streams
+// (N samples x ~40 bytes per record)
+void formatRecord(std::string & out, const std::string & chrom, const pd_call & c, const uint32_t * ps, size_t N, uint32_t sigWin,
+                  const QualMap & qm)
 {
-    const size_t N = c.ps.size() / 13;
     unsigned genotyped = (unsigned)N;
-    for (size_t s = 0; s < N; ++s) if (c.ps[13 * s] + c.ps[13 * s + 1] + c.ps[13 * s + 2] == 0) --genotyped;
+    for (size_t s = 0; s < N; ++s) if (ps[13 * s] + ps[13 * s + 1] + ps[13 * s + 2] == 0) --genotyped;
     std::string filter;
-    if (allPass(c)) filter = "PASS";
+    if ((c.filter & 31u) == 0) filter = "PASS";
     else {
         auto add = [&](const char * t) { if (!filter.empty()) filter += ';'; filter += t; };
         if (c.filter & 1) add("lowLR");
@@ -254,25 +289,36 @@ void writeRecord(std::ostream & out, const std::string & chrom, const Call & c, 
         if (c.filter & 8) add("allRefGT");
         if (c.filter & 16) add("CSWin");
     }
-    std::ostringstream info;                                       // default stream precision (6), like the reference
-    info << "IMPRECISE;SVLEN=" << -static_cast<int>(c.deletionLength) << ";END=" << c.position + c.deletionLength
-         << ";SVTYPE=DEL;AF=" << c.frequency << ";LR=" << c.lr << ";SVMETHOD=PopDelv1.5.0;YIELD="
-         << (double)genotyped / N << ";SWIN=" << c.significantWindows;
     const uint32_t pos = c.position > 1 ? c.position - 1 : c.position;           // record.beginPos (0-based)
-    out << chrom << "\t" << pos + 1 << "\t.\tN\t<DEL>\t" << qm.qual(c.lr) << "\t" << filter << "\t" << info.str()
-        << "\tGT:PL:GQ:LAD:DAD:FL:FLD";
+    out.reserve(out.size() + 160 + 48 * N);
+    out += chrom; out += '\t'; appendUint(out, (uint64_t)pos + 1); out += "\t.\tN\t<DEL>\t"; appendUint(out, (uint64_t)qm.qual(c.lr));
+    out += '\t'; out += filter;
+    out += "\tIMPRECISE;SVLEN=";                                // default stream precision (6), like the reference
+    { const int sv = -static_cast<int>(c.deletion_length); if (sv < 0) { out += '-'; appendUint(out, (uint64_t)(-(int64_t)sv)); } else appendUint(out, (uint64_t)sv); }
+    out += ";END="; appendUint(out, (uint32_t)(c.position + c.deletion_length));
+    out += ";SVTYPE=DEL;AF="; appendG(out, c.frequency);
+    out += ";LR="; appendG(out, c.lr);
+    out += ";SVMETHOD=PopDelv1.5.0;YIELD="; appendG(out, (double)genotyped / N);
+    out += ";SWIN="; appendUint(out, sigWin);
+    out += "\tGT:PL:GQ:LAD:DAD:FL:FLD";
     for (size_t s = 0; s < N; ++s) {
-        const uint32_t * o = &c.ps[13 * s];
+        const uint32_t * o = &ps[13 * s];
         unsigned gq = 0;
         if (o[0] + o[1] + o[2] != 0) gq = o[0] == 0 ? std::min(o[1], o[2]) : (o[1] == 0 ? std::min(o[0], o[2]) : std::min(o[0], o[1]));
         gq = std::min(gq, 255u);
-        out << "\t";
-        if (gq == 0) out << "./.:0,0,0";
-        else out << (o[2] == 0 ? "1" : "0") << "/" << (o[0] != 0 ? "1" : "0") << ":" << std::min(o[0], 255u) << "," << std::min(o[1], 255u) << "," << std::min(o[2], 255u);
-        out << ":" << gq << ":" << o[3] << "," << o[4] << "," << o[5] << ":" << o[6] << "," << o[7] << "," << o[8] << "," << o[9] << "," << o[10]
-            << ":" << o[11] << "," << o[12] << ":" << o[12] - o[11];
+        out += '\t';
+        if (gq == 0) out += "./.:0,0,0";
+        else {
+            out += (o[2] == 0 ? '1' : '0'); out += '/'; out += (o[0] != 0 ? '1' : '0'); out += ':';
+            appendUint(out, std::min(o[0], 255u)); out += ','; appendUint(out, std::min(o[1], 255u)); out += ','; appendUint(out, std::min(o[2], 255u));
+        }
+        out += ':'; appendUint(out, gq);
+        out += ':'; appendUint(out, o[3]); out += ','; appendUint(out, o[4]); out += ','; appendUint(out, o[5]);
+        out += ':'; appendUint(out, o[6]); out += ','; appendUint(out, o[7]); out += ','; appendUint(out, o[8]); out += ','; appendUint(out, o[9]);
+        out += ','; appendUint(out, o[10]);
+        out += ':'; appendUint(out, o[11]); out += ','; appendUint(out, o[12]); out += ':'; appendUint(out, (uint32_t)(o[12] - o[11]));
     }
-    out << "\n";
+    out += '\n';
 }
 
 struct Options {
@@ -327,16 +373,13 @@ int main(int argc, char ** argv)
         }
     }
     const size_t N = opt.files.size();
-    std::vector<Profile> profiles(N);
-    {   // decode the profiles with all host cores (one file per task; SURVEY.md 8f rank 2: the reference re-opens and
-        // inflates every file per 200-kbp segment, single-threaded)
-        std::atomic<size_t> next{0};
-        const unsigned nthreads = (unsigned)std::max<size_t>(1, std::min<size_t>(N, std::thread::hardware_concurrency()));
-        std::vector<std::thread> pool;
-        for (unsigned t = 0; t < nthreads; ++t)
-            pool.emplace_back([&] { for (size_t i; (i = next.fetch_add(1)) < N;) loadProfile(opt.files[i], opt.uncompressed, profiles[i]); });
-        for (auto & th : pool) th.join();
-    }
+    std::vector<Profile> & profiles = *new std::vector<Profile>(N);  // never destroyed: the process exits right after the output is written
+    StageTimer tm;
+    std::thread warm([&] { if (!getenv("PD_NO_WARM")) pd_device_warmup(opt.device); });      // CUDA context creation overlaps the profile decoding
+    // decode the profiles with all host cores (one file per task; SURVEY.md 8f rank 2: the reference re-opens and
+    // inflates every file per 200-kbp segment, single-threaded)
+    parallelFor(N, [&](size_t i) { loadProfile(opt.files[i], opt.uncompressed, profiles[i]); });
+    tm.lap("decode");
 
     // ---- histograms and parameters (reference parameter_calculation_popdel_call.h:160-204)
     std::vector<pd_rg> rgs;
@@ -380,6 +423,9 @@ int main(int argc, char ** argv)
     prm.window_size = 30; prm.window_buffer = opt.buffer;
     prm.somatic = opt.somatic; prm.window_wise = opt.windowWise;
 
+    tm.lap("histograms");
+    warm.join();
+    tm.lap("cuda-init");
     pd_ctx * ctx = pd_create(&prm, (uint32_t)N, (uint32_t)R, rgs.data(), opt.device);
     if (!ctx) die(std::string("cannot create the scan context: ") + pd_create_error());
     auto check = [&](int rc) { if (rc != 0) die(std::string("scan library: ") + pd_last_error(ctx)); };
@@ -400,18 +446,18 @@ int main(int argc, char ** argv)
     for (int32_t c = 0; c < (int32_t)profiles[0].contigNames.size(); ++c) {
         // first 30-bp window of the contig over all samples (getFirstWindowCoordinate, load_profile :291-350)
         bool found = false; uint32_t anchor = 0xFFFFFFFFu;
-        std::vector<Bucket> buckets;
         for (size_t i = 0; i < N; ++i) {
             const Profile & p = profiles[i];
             if ((size_t)c >= p.contigNames.size()) continue;
             size_t w = indexSeek(p, c, 0);
             if (w >= p.contigFirst[c + 1]) continue;
-            convertWindow(p.wins[w], buckets);
-            if (buckets.empty()) continue;
-            found = true; anchor = std::min(anchor, buckets[0].begin);
+            const uint32_t base = bucketBase(p, w);
+            if (base == 0xFFFFFFFFu) continue;
+            found = true; anchor = std::min(anchor, base);
         }
         if (!found) continue;
         check(pd_contig_begin(ctx, anchor));
+        tm.lap("create");
 
         // segment loader: which read pairs does the reference load in which iteration of its segment loop
         // (workflow_popdel.h:297-366, readSegment load_profile :526-587). Iteration t accepts buckets below
@@ -420,59 +466,99 @@ int main(int argc, char ** argv)
         // 256-bp window are never loaded.
         std::vector<std::vector<uint32_t>> ppos(R);
         std::vector<std::vector<int32_t>> pdev(R);
+        parallelFor(N, [&](size_t i) {                               // one allocation per read group: its read pairs on this contig
+            const Profile & p = profiles[i];
+            if ((size_t)c >= p.contigNames.size()) return;
+            for (size_t r = 0; r < p.nrg; ++r) {
+                uint64_t n = 0;
+                for (size_t w = p.contigFirst[c]; w < p.contigFirst[c + 1]; ++w) n += p.winOff[w * p.nrg + r + 1] - p.winOff[w * p.nrg + r];
+                ppos[sampleRgs[i][r]].reserve(n); pdev[sampleRgs[i][r]].reserve(n);
+            }
+        });
         std::vector<uint32_t> cand(N, anchor);
-        std::vector<bool> fin(N, false);
+        std::vector<char> fin(N, 0);
         uint32_t rb = anchor;
         uint64_t Rt = (uint64_t)anchor + WB;
         while (true) {
-            uint32_t nextRead = 0xFFFFFFFFu;
-            bool allFin = true;
-            for (size_t i = 0; i < N; ++i) {
-                if (fin[i]) continue;
-                if ((uint64_t)cand[i] >= Rt) { allFin = false; continue; }            // sits out this iteration
+            std::atomic<uint32_t> nextRead{0xFFFFFFFFu};
+            std::atomic<bool> allFin{true};
+            parallelFor(N, [&](size_t i) {                           // samples are independent within one iteration
+                if (fin[i]) return;
+                if ((uint64_t)cand[i] >= Rt) { allFin = false; return; }                // sits out this iteration
                 const Profile & p = profiles[i];
-                if ((size_t)c >= p.contigNames.size()) { fin[i] = true; continue; }
+                if ((size_t)c >= p.contigNames.size()) { fin[i] = 1; return; }
                 size_t w = indexSeek(p, c, rb);
                 bool stopped = false;
                 for (; !stopped; ++w) {
-                    if (w >= p.contigFirst[c + 1]) { fin[i] = true; break; }         // next contig or end of file
-                    const Win & win = p.wins[w];
-                    if ((uint64_t)win.begin + 255 < rb) continue;
-                    convertWindow(win, buckets);
-                    for (const Bucket & b : buckets) {
-                        if (b.begin < rb) continue;
-                        if ((uint64_t)b.begin >= Rt) { cand[i] = b.begin; nextRead = std::min(nextRead, b.begin); stopped = true; break; }
-                        for (size_t r = 0; r < b.rg.size(); ++r)
-                            for (const Rec & x : b.rg[r]) { ppos[sampleRgs[i][r]].push_back(x.pos); pdev[sampleRgs[i][r]].push_back(x.dev); }
+                    if (w >= p.contigFirst[c + 1]) { fin[i] = 1; break; }            // next contig or end of file
+                    if ((uint64_t)p.winBegin[w] + 255 < rb) continue;
+                    // the window's 30-bp buckets in ascending order: those below rb are skipped, the first one at or beyond
+                    // Rt ends this sample's iteration; per read group the read pairs are sorted, so both are range scans
+                    const uint32_t base = bucketBase(p, w);
+                    if (base == 0xFFFFFFFFu) continue;
+                    uint32_t stopAt = 0xFFFFFFFFu;
+                    for (size_t r = 0; r < p.nrg; ++r) {
+                        std::vector<uint32_t> & dp = ppos[sampleRgs[i][r]];
+                        std::vector<int32_t> & dd = pdev[sampleRgs[i][r]];
+                        for (uint64_t k = p.winOff[w * p.nrg + r], e = p.winOff[w * p.nrg + r + 1]; k < e; ++k) {
+                            const uint32_t bb = base + ((p.recPos[k] - base) / 30) * 30;
+                            if (bb < rb) continue;
+                            if ((uint64_t)bb >= Rt) { stopAt = std::min(stopAt, bb); break; }
+                            dp.push_back(p.recPos[k]); dd.push_back(p.recDev[k]);
+                        }
+                    }
+                    if (stopAt != 0xFFFFFFFFu) {
+                        cand[i] = stopAt;
+                        uint32_t seen = nextRead.load();
+                        while (stopAt < seen && !nextRead.compare_exchange_weak(seen, stopAt)) {}
+                        stopped = true;
                     }
                 }
                 if (!fin[i]) allFin = false;
-            }
+            });
             if (allFin) break;
             if (nextRead != 0xFFFFFFFFu) rb = nextRead;
             Rt += WB;
         }
-        for (size_t g = 0; g < R; ++g) check(pd_contig_push(ctx, (uint32_t)g, ppos[g].size(), ppos[g].data(), pdev[g].data()));
+        tm.lap("segments");
+        {   // the add() loop of every read group (active-coverage cap + packing), one read group per task
+            std::atomic<int> bad{0};
+            parallelFor(R, [&](size_t g) { if (pd_contig_push(ctx, (uint32_t)g, ppos[g].size(), ppos[g].data(), pdev[g].data()) != 0) bad = 1; });
+            if (bad) check(-1);
+        }
+        tm.lap("push");
 
         pd_result res;
         check(pd_contig_scan(ctx, 0, 0, &res));
         totalWindows += res.n_windows;
-        // window calls (-n) or the merged variants of every segment, already in output order
+        tm.lap("scan");
+        // window calls (-n) or the merged variants of every segment, already in output order; records are formatted on
+        // all cores and written in order
         const std::string & chrom = profiles[0].contigNames[c];
+        std::vector<size_t> keep;
         for (size_t k = 0; k < res.n_calls; ++k) {
             const pd_call & pc = res.calls[k];
-            Call cl;
-            cl.initialLength = pc.initial_length; cl.iterations = pc.iterations; cl.deletionLength = pc.deletion_length;
-            cl.filter = pc.filter; cl.lr = pc.lr; cl.frequency = pc.frequency; cl.windowPosition = pc.window_position;
-            cl.position = pc.position; cl.endPosition = pc.end_position;
-            cl.significantWindows = res.significant_windows ? res.significant_windows[k] : 0;
-            cl.ps.assign(res.per_sample + k * 13ull * N, res.per_sample + (k + 1) * 13ull * N);
-            if (cl.iterations != 0 && (opt.outputFailed || allPass(cl))) { writeRecord(out, chrom, cl, qm); ++totalCalls; }
+            if (pc.iterations != 0 && (opt.outputFailed || (pc.filter & 31u) == 0)) keep.push_back(k);
         }
+        const size_t CHUNK = 64;
+        std::vector<std::string> text((keep.size() + CHUNK - 1) / CHUNK);
+        parallelFor(text.size(), [&](size_t t) {
+            for (size_t q = t * CHUNK; q < std::min(keep.size(), (t + 1) * CHUNK); ++q) {
+                const size_t k = keep[q];
+                formatRecord(text[t], chrom, res.calls[k], res.per_sample + k * 13ull * N, N,
+                             res.significant_windows ? res.significant_windows[k] : 0, qm);
+            }
+        });
+        for (const std::string & t : text) out.write(t.data(), (std::streamsize)t.size());
+        totalCalls += keep.size();
         out.flush();
+        tm.lap("vcf");
     }
-    pd_destroy(ctx);
+    out.close();
+    tm.report();
     std::cout << "[popdel_b200] scanned " << totalWindows << " windows x " << N << " samples, wrote " << totalCalls
               << " records to '" << opt.out << "'" << std::endl;
-    return 0;
+    // the output is complete: leave without tearing down the CUDA context and the decoded profiles one allocation at a time
+    fflush(nullptr);
+    _exit(0);
 }
