@@ -11,6 +11,7 @@
 //   -b NUM   segment length in bp (200000)  -t NUM  EM iterations (15)               -p NUM  prior (1e-4)
 //   -s NUM   min sample fraction (0.1)      -c NUM  min relative window cover (0.5)  -f NUM  pseudo-count fraction (500)
 //   -u       unsmoothed histograms          -x  uncompressed profiles                -C  cell-population priors
+//   -A FILE  per-read-group active-coverage caps ("ReadGroup maxCov" lines)        -e  rename conflicting read-group IDs per file
 //   -g NUM   CUDA device (0)
 #include <algorithm>
 #include <atomic>
@@ -324,7 +325,8 @@ void formatRecord(std::string & out, const std::string & chrom, const pd_call & 
 struct Options {
     std::vector<std::string> files;
     std::string out = "popdel.vcf";
-    bool windowWise = false, outputFailed = false, smoothing = true, uncompressed = false, somatic = false;
+    bool windowWise = false, outputFailed = false, smoothing = true, uncompressed = false, somatic = false, perSampleRgid = false;
+    std::string maxLoadFile;
     long minInit = -1, minLen = -1;
     unsigned maxLoad = 100, buffer = 200000, iterations = 15, pseudo = 500;
     double prior = 0.0001, minSampleFraction = 0.1, minCover = 0.5;
@@ -355,7 +357,10 @@ int main(int argc, char ** argv)
         else if (a == "-s" || a == "--min-sample-fraction") opt.minSampleFraction = atof(val().c_str());
         else if (a == "-c" || a == "--min-relative-window-cover") opt.minCover = atof(val().c_str());
         else if (a == "-g" || a == "--gpu") opt.device = atoi(val().c_str());
-        else if (a == "-r" || a == "-R" || a == "-A" || a == "-e" || a == "-d") die("option " + a + " is not supported by this build (whole contigs, default read-group handling)");
+        else if (a == "-A" || a == "--active-coverage-file") opt.maxLoadFile = val();
+        else if (a == "-e" || a == "--per-sample-rgid") opt.perSampleRgid = true;
+        else if (a == "-d" || a == "--max-deletion-size") val();           // parsed by the reference's call parser too, used by `popdel profile` only
+        else if (a == "-r" || a == "-R" || a == "--region-of-interest" || a == "--ROI-file") die("option " + a + " is not supported by this build (whole contigs only)");
         else if (!a.empty() && a[0] == '-') die("unknown option " + a);
         else opt.files.push_back(a);
     }
@@ -367,8 +372,12 @@ int main(int argc, char ** argv)
         lf.read(&first7[0], 7);
         if (first7 != std::string("POPDEL\1", 7)) {
             lf.clear(); lf.seekg(0);
-            std::vector<std::string> listed; std::string line;
-            while (std::getline(lf, line)) if (!line.empty()) listed.push_back(line);
+            std::vector<std::string> listed; std::string name;        // whitespace-separated, duplicates ignored (utils_popdel.h:879-912)
+            std::set<std::string> seenFiles;
+            while (lf >> name) {
+                if (seenFiles.insert(name).second) listed.push_back(name);
+                else std::cout << "WARNING: duplicate file " << name << ". Ignoring additional occurences." << std::endl;
+            }
             opt.files = listed;
         }
     }
@@ -386,9 +395,23 @@ int main(int argc, char ** argv)
     std::vector<std::vector<double>> tables;
     std::vector<std::vector<uint32_t>> sampleRgs(N);
     std::set<std::string> seen;
-    for (size_t i = 0; i < N; ++i)
-        for (const RgHeader & h : profiles[i].rgs) {
-            if (!seen.insert(h.name).second) die("duplicate read group '" + h.name + "' (use unique read-group IDs)");
+    std::vector<std::string> rgNames;
+    for (size_t i = 0; i < N; ++i) {
+        std::vector<std::string> names;
+        for (const RgHeader & h : profiles[i].rgs) names.push_back(h.name);
+        for (size_t k = 0; k < names.size(); ++k) {
+            if (!seen.insert(names[k]).second) {
+                // -e (insert_histogram_popdel.h:1041-1052): on the first conflict every read group of this file is renamed
+                if (!opt.perSampleRgid) die("duplicate read group '" + names[k] + "' (use unique read-group IDs or -e / --per-sample-rgid)");
+                for (std::string & nm : names) {
+                    const std::string renamed = sampleName(opt.files[i]) + ":" + nm;
+                    std::cout << "WARNING: Internally replacing read group ID '" << nm << "' of file '" << opt.files[i] << "' with '" << renamed << "'" << std::endl;
+                    nm = renamed;
+                }
+                if (!seen.insert(names[k]).second) die("could not de-duplicate read group '" + names[k] + "' of '" + opt.files[i] + "'");
+            }
+            const RgHeader & h = profiles[i].rgs[k];
+            rgNames.push_back(names[k]);
             tables.push_back(h.counts);
             pd_rg r; memset(&r, 0, sizeof(r));
             r.sample = (uint32_t)i; r.median = h.median; r.read_length = h.readLength; r.stddev = h.stddev; r.offset = h.offset;
@@ -398,6 +421,7 @@ int main(int argc, char ** argv)
             sampleRgs[i].push_back((uint32_t)rgs.size());
             rgs.push_back(r);
         }
+    }
     const size_t R = rgs.size();
     double meanStddev = 0;
     for (size_t g = 0; g < R; ++g) { rgs[g].values = tables[g].data(); meanStddev += rgs[g].stddev; }
@@ -407,6 +431,20 @@ int main(int argc, char ** argv)
         minInit[g] = opt.minInit >= 0 ? (unsigned)opt.minInit : (unsigned)rnd(4 * rgs[g].stddev);
         rgs[g].min_init_del_len = minInit[g];
         rgs[g].max_load = opt.maxLoad == 0 ? 0xFFFFFFFFu : opt.maxLoad;
+    }
+    if (!opt.maxLoadFile.empty()) {                                 // -A: "ReadGroup maxCov" lines (loadMaxLoad, parameter_calculation :83-155)
+        std::ifstream lf(opt.maxLoadFile);
+        if (!lf.is_open()) die("Could not open coverage file '" + opt.maxLoadFile + "' for reading.");
+        std::map<std::string, unsigned long> loads;
+        std::string name, load;
+        while (lf >> name) {
+            if (!(lf >> load)) die("Could not read maximum coverage for read group '" + name + "'.");
+            loads[name] = std::stoul(load);
+        }
+        for (size_t g = 0; g < R; ++g) {
+            auto it = loads.find(rgNames[g]);
+            if (it != loads.end()) rgs[g].max_load = it->second == 0 ? 0xFFFFFFFFu : (uint32_t)it->second;
+        }
     }
     pd_params prm; memset(&prm, 0, sizeof(prm));
     {

@@ -72,3 +72,20 @@ def test_cli_fails_loudly_without_gpu(tmp_path):
     r = subprocess.run([CLI, "profiles.txt", "-o", str(tmp_path / "x.vcf")], cwd=os.path.join(GOLDEN, "basic"),
                        capture_output=True, text=True)
     assert r.returncode != 0 and "no CPU scan path" in r.stderr
+
+
+def _option_variants():
+    import json
+    return json.load(open(os.path.join(GOLDEN, "options.json")))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("v", _option_variants(), ids=lambda v: f"{v['case']}-{v['name']}")
+def test_option_variants_equal_reference(v, tmp_path):
+    """-A (per-read-group coverage caps), -e (conflicting read-group IDs), -F / -c, -u / -t / -p / -s / -f: the VCF equals the
+    one the unmodified reference wrote with the same options (tests/golden/make_golden_options.py)."""
+    out = str(tmp_path / "out.vcf")
+    subprocess.run([CLI, v["list"], "-o", out] + v["args"], check=True, cwd=os.path.join(GOLDEN, v["case"]), stdout=subprocess.DEVNULL)
+    ref = _lines(os.path.join(GOLDEN, v["case"], v["vcf"]))
+    assert sum(1 for l in ref if not l.startswith("#")) == v["records"]
+    _compare(_lines(out), ref)
