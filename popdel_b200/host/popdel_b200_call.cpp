@@ -11,6 +11,7 @@
 //   -b NUM   segment length in bp (200000)  -t NUM  EM iterations (15)               -p NUM  prior (1e-4)
 //   -s NUM   min sample fraction (0.1)      -c NUM  min relative window cover (0.5)  -f NUM  pseudo-count fraction (500)
 //   -u       unsmoothed histograms          -x  uncompressed profiles                -C  cell-population priors
+//   -r CHR[:BEGIN[-END]]  region of interest (1-based, closed; may be repeated)        -R FILE  one region per line
 //   -A FILE  per-read-group active-coverage caps ("ReadGroup maxCov" lines)        -e  rename conflicting read-group IDs per file
 //   -g NUM   CUDA device (0)
 #include <algorithm>
@@ -322,11 +323,34 @@ void formatRecord(std::string & out, const std::string & chrom, const pd_call & 
     out += '\n';
 }
 
+// region of interest, 0-based half-open like the reference's GenomicRegion (parseGenomicRegion: "chr", "chr:begin",
+// "chr:begin-end", 1-based closed, thousands separators allowed)
+struct Roi { int32_t contig; std::string name; int64_t begin, end; };
+Roi parseRegion(const std::string & text)
+{
+    Roi r{-1, "", 0, 0x7FFFFFFF};
+    const size_t colon = text.rfind(':');
+    r.name = text.substr(0, colon);
+    if (colon == std::string::npos) return r;
+    std::string rest;
+    for (char ch : text.substr(colon + 1)) if (ch != ',') rest += ch;
+    const size_t dash = rest.find('-');
+    const std::string b = rest.substr(0, dash), e = dash == std::string::npos ? "" : rest.substr(dash + 1);
+    auto number = [&](const std::string & t) -> int64_t {
+        if (t.empty() || t.find_first_not_of("0123456789") != std::string::npos) die("Error while parsing genomic region '" + text + "'");
+        return atoll(t.c_str());
+    };
+    if (!b.empty()) r.begin = std::max<int64_t>(number(b) - 1, 0);
+    if (!e.empty()) r.end = number(e);
+    return r;
+}
+
 struct Options {
     std::vector<std::string> files;
     std::string out = "popdel.vcf";
     bool windowWise = false, outputFailed = false, smoothing = true, uncompressed = false, somatic = false, perSampleRgid = false;
-    std::string maxLoadFile;
+    std::string maxLoadFile, roiFile;
+    std::vector<std::string> regions;
     long minInit = -1, minLen = -1;
     unsigned maxLoad = 100, buffer = 200000, iterations = 15, pseudo = 500;
     double prior = 0.0001, minSampleFraction = 0.1, minCover = 0.5;
@@ -360,7 +384,8 @@ int main(int argc, char ** argv)
         else if (a == "-A" || a == "--active-coverage-file") opt.maxLoadFile = val();
         else if (a == "-e" || a == "--per-sample-rgid") opt.perSampleRgid = true;
         else if (a == "-d" || a == "--max-deletion-size") val();           // parsed by the reference's call parser too, used by `popdel profile` only
-        else if (a == "-r" || a == "-R" || a == "--region-of-interest" || a == "--ROI-file") die("option " + a + " is not supported by this build (whole contigs only)");
+        else if (a == "-r" || a == "--region-of-interest") opt.regions.push_back(val());
+        else if (a == "-R" || a == "--ROI-file") opt.roiFile = val();
         else if (!a.empty() && a[0] == '-') die("unknown option " + a);
         else opt.files.push_back(a);
     }
@@ -480,19 +505,54 @@ int main(int argc, char ** argv)
     const uint32_t WB = opt.buffer;
     uint64_t totalWindows = 0, totalCalls = 0;
 
-    // ---- regions of interest = the contigs of the first profile, in order (reference load_profile_popdel_call.h:108-157)
-    for (int32_t c = 0; c < (int32_t)profiles[0].contigNames.size(); ++c) {
-        // first 30-bp window of the contig over all samples (getFirstWindowCoordinate, load_profile :291-350)
+    // ---- regions of interest (initializeRois, load_profile_popdel_call.h:108-157): -r / -R regions per contig, sorted,
+    // overlapping ones merged, in the contig order of the first profile; default = every contig as a whole
+    std::vector<Roi> rois;
+    {
+        std::vector<std::string> texts = opt.regions;
+        if (!opt.roiFile.empty()) {
+            std::ifstream rf(opt.roiFile);
+            if (!rf.is_open()) die("Could not open ROI file '" + opt.roiFile + "' for reading.");
+            std::string line;
+            while (rf >> line) texts.push_back(line);
+        }
+        const std::vector<std::string> & names = profiles[0].contigNames;
+        if (texts.empty()) for (size_t c = 0; c < names.size(); ++c) rois.push_back(Roi{(int32_t)c, names[c], 0, 0x7FFFFFFF});
+        for (const std::string & t : texts) {
+            Roi r = parseRegion(t);
+            for (size_t c = 0; c < names.size(); ++c) if (names[c] == r.name) r.contig = (int32_t)c;
+            if (r.contig < 0) die("Invalid chromosome name '" + r.name + "' in region of interest.");
+            rois.push_back(r);
+        }
+        std::stable_sort(rois.begin(), rois.end(), [](const Roi & a, const Roi & b) {
+            if (a.contig != b.contig) return a.contig < b.contig;
+            if (a.begin != b.begin) return a.begin < b.begin;
+            return a.end < b.end;
+        });
+        std::vector<Roi> merged;
+        for (const Roi & r : rois) {
+            if (!merged.empty() && merged.back().contig == r.contig && merged.back().end >= r.begin) merged.back().end = std::max(merged.back().end, r.end);
+            else merged.push_back(r);
+        }
+        rois.swap(merged);
+    }
+    for (const Roi & roi : rois) {
+        const int32_t c = roi.contig;
+        // first 30-bp window over all samples (getFirstWindowCoordinate / getFirstWindowOnNextROI, load_profile :291-412): every
+        // sample jumps through its index to the region's begin and contributes the first bucket of the 256-bp window it
+        // lands on -- which may lie BEFORE the region (index granularity); the window grid and the segment borders of
+        // this region are anchored there
         bool found = false; uint32_t anchor = 0xFFFFFFFFu;
         for (size_t i = 0; i < N; ++i) {
             const Profile & p = profiles[i];
             if ((size_t)c >= p.contigNames.size()) continue;
-            size_t w = indexSeek(p, c, 0);
+            size_t w = indexSeek(p, c, (uint32_t)roi.begin);
             if (w >= p.contigFirst[c + 1]) continue;
             const uint32_t base = bucketBase(p, w);
             if (base == 0xFFFFFFFFu) continue;
             found = true; anchor = std::min(anchor, base);
         }
+        if (found && (int64_t)anchor >= roi.end) found = false;       // nothing inside the region (adaptRegions :218-236)
         if (!found) continue;
         check(pd_contig_begin(ctx, anchor));
         tm.lap("create");
@@ -515,7 +575,9 @@ int main(int argc, char ** argv)
         });
         std::vector<uint32_t> cand(N, anchor);
         std::vector<char> fin(N, 0);
-        uint32_t rb = anchor;
+        // adaptRegions (:218-236): the region's left end follows the current window once that window reaches it
+        uint32_t rb = (int64_t)anchor + 29 > roi.begin ? anchor : (uint32_t)roi.begin;
+        const uint64_t roiEnd = (uint64_t)roi.end;
         uint64_t Rt = (uint64_t)anchor + WB;
         while (true) {
             std::atomic<uint32_t> nextRead{0xFFFFFFFFu};
@@ -534,18 +596,21 @@ int main(int argc, char ** argv)
                     // Rt ends this sample's iteration; per read group the read pairs are sorted, so both are range scans
                     const uint32_t base = bucketBase(p, w);
                     if (base == 0xFFFFFFFFu) continue;
+                    // (a bucket at or beyond the region's end finishes the sample, readSegment :553-559)
+                    const uint64_t lim = std::min<uint64_t>(Rt, roiEnd);
                     uint32_t stopAt = 0xFFFFFFFFu;
                     for (size_t r = 0; r < p.nrg; ++r) {
                         std::vector<uint32_t> & dp = ppos[sampleRgs[i][r]];
                         std::vector<int32_t> & dd = pdev[sampleRgs[i][r]];
                         for (uint64_t k = p.winOff[w * p.nrg + r], e = p.winOff[w * p.nrg + r + 1]; k < e; ++k) {
                             const uint32_t bb = base + ((p.recPos[k] - base) / 30) * 30;
+                            if ((uint64_t)bb >= lim) { stopAt = std::min(stopAt, bb); break; }
                             if (bb < rb) continue;
-                            if ((uint64_t)bb >= Rt) { stopAt = std::min(stopAt, bb); break; }
                             dp.push_back(p.recPos[k]); dd.push_back(p.recDev[k]);
                         }
                     }
                     if (stopAt != 0xFFFFFFFFu) {
+                        if ((uint64_t)stopAt >= roiEnd) { fin[i] = 1; break; }
                         cand[i] = stopAt;
                         uint32_t seen = nextRead.load();
                         while (stopAt < seen && !nextRead.compare_exchange_weak(seen, stopAt)) {}

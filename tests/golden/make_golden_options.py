@@ -24,6 +24,17 @@ VARIANTS = [
          files={"opt_e_profiles.txt": "sample00000.profile\nsample00002.profile opt_e_dup.profile\nsample00000.profile\nsample00004.profile\n"}),
     # output of failed calls, tighter window cover, more EM iterations, unsmoothed histograms
     dict(case="mixedrg", name="F_c", list="profiles.txt", args=["-F", "-c", "0.9"], files={}),
+    # regions of interest: cut inside a contig (window-wise output shows every window next to the region's ends, a region
+    # that starts inside a deletion, several disjoint regions on two contigs (-r twice + -R file; OVERLAPPING regions make the reference write every record twice, which is not reproduced), a
+    # region through a gap, a whole contig by name
+    dict(case="basic", name="r_mid_n", list="profiles.txt", args=["-r", "chr21:100001-300000", "-n"], files={}),
+    dict(case="basic", name="r_mid", list="profiles.txt", args=["-r", "chr21:100,001-300,000"], files={}),
+    dict(case="basic", name="r_indel_n", list="profiles.txt", args=["-r", "chr21:283000-356000", "-n"], files={}),
+    dict(case="basic", name="r_open", list="profiles.txt", args=["-r", "chr21:250001"], files={}),
+    dict(case="twocontigs", name="r_multi_n", list="profiles.txt", args=["-r", "chrB:20001-60000", "-r", "chrA:50001-100000", "-R", "opt_rois.txt", "-n"],
+         files={"opt_rois.txt": "chrA:110001-135000\nchrB:100001-140000\n"}),
+    dict(case="twocontigs", name="r_contig", list="profiles.txt", args=["-r", "chrB"], files={}),
+    dict(case="gap", name="r_gap_n", list="profiles.txt", args=["-r", "chr2:110001-790000", "-n"], files={}),
     dict(case="offset", name="u_t_p", list="profiles.txt", args=["-u", "-t", "6", "-p", "0.01", "-s", "0.5", "-f", "200"], files={}),
 ]
 
