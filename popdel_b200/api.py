@@ -16,7 +16,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpopdel_b200.so")
+LIB_PATH = os.environ.get("POPDEL_B200_LIB") or os.path.join(_HERE, "libpopdel_b200.so")      # (override: A/B runs of two builds)
 
 
 class ScanError(RuntimeError):

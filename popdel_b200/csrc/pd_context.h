@@ -122,7 +122,7 @@ struct pd_ctx {
     pd_unify_params unify{};
     pd_call * d_u_calls = nullptr; size_t cap_u_calls = 0;
     uint32_t * d_u_ps = nullptr; size_t cap_u_ps = 0;
-    void * d_unify[10] = {}; size_t cap_unify[10] = {};
+    void * d_unify[16] = {}; size_t cap_unify[16] = {};
     uint32_t * res_sig = nullptr; size_t cap_res_sig = 0;     // page-locked, mapped: significantWindows per variant
     // word -> tile index of the current upload (k_stream's slow path) and wide-list ranges per read group
     bool index_built = false;

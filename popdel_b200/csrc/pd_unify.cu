@@ -14,8 +14,10 @@
 //                    call of a later group is not in the lists, `last` itself is outside the merged range). It
 //                    fixes position / length / LR / filter of every merged variant and lists its in-range windows.
 //   k_unify_offsets  exclusive scan of the variants per segment -> output slots (segment order).
-//   k_unify_emit     one block per segment, one thread per sample: PL sums -> setGenotypes, median LAD / DAD by value
-//                    bisection, allele count -> frequency; header + row go to mapped host memory.
+//   k_unify_list     output slot -> variant.
+//   k_unify_emit     grid (variants, sample groups), one WARP per (variant, sample) with the lanes over the variant's
+//                    in-range windows: PL sums -> setGenotypes, median LAD / DAD by bisection on the value over the
+//                    column staged in shared memory, allele count -> frequency; header + row go to mapped host memory.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -36,6 +38,8 @@ struct UnifyArgs {
     uint32_t * starts, * sizes;                        // the merge loop's running lists (append-only, "clear" = new offset)
     uint32_t * inr;                                    // window calls in range of the variant starting at a sorted slot
     uint32_t * gwc, * sig;                             // per sorted slot: in-range windows / significant windows (0: no merge)
+    uint32_t * vlist;                                  // output slot -> sorted slot of the variant
+    uint32_t * alleles, * blocks_done;                 // per output slot
     uint32_t * total;                                  // mapped host: number of variants
     pd_call * out_calls; uint32_t * out_ps; uint32_t * out_sig;     // mapped host
 };
@@ -71,15 +75,29 @@ __global__ void k_seg_bounds(UnifyArgs u)
     if (i == u.n_raw - 1 || u.calls[i + 1].segment != s) u.seg_last[s] = i + 1;
 }
 
-__device__ void sort_small(uint32_t * v, uint32_t n)                 // insertion sort (lists of a few dozen entries)
+// value of rank k (0-based) of v[0, n); reorders v. Quickselect with a middle pivot: the lists of a long deletion
+// hold a few hundred entries and one thread runs the merge loop.
+__device__ uint32_t select_rank(uint32_t * v, uint32_t n, uint32_t k)
 {
-    for (uint32_t i = 1; i < n; ++i) {
-        const uint32_t x = v[i];
-        uint32_t j = i;
-        for (; j > 0 && v[j - 1] > x; --j) v[j] = v[j - 1];
-        v[j] = x;
+    uint32_t lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const uint32_t pivot = v[lo + (hi - lo) / 2];
+        uint32_t i = lo, j = hi;
+        while (i <= j) {
+            while (v[i] < pivot) ++i;
+            while (v[j] > pivot) --j;
+            if (i <= j) { const uint32_t t = v[i]; v[i] = v[j]; v[j] = t; ++i; if (j == 0) break; --j; }
+        }
+        if (k <= j && j < hi) hi = j;
+        else if (k >= i) lo = i;
+        else break;                                                   // v[k] == pivot
     }
+    return v[k];
 }
+
+constexpr uint32_t PLAN_CAP = 512;
+__device__ void plan_segment(const UnifyArgs & u, uint32_t seg, uint32_t n, pd_call * W, uint32_t * S, uint32_t * Z, uint32_t * I,
+                             uint32_t * G, uint32_t * Q, const uint32_t * ord);
 
 __global__ void __launch_bounds__(256) k_unify_plan(UnifyArgs u)
 {
@@ -104,10 +122,29 @@ __global__ void __launch_bounds__(256) k_unify_plan(UnifyArgs u)
         u.gwc[first + rank] = 0; u.sig[first + rank] = 0;
     }
     __syncthreads();
-    if (tid != 0) return;
-    pd_call * W = u.wc + first;
-    uint32_t * S = u.starts + first, * Z = u.sizes + first, * I = u.inr + first, * G = u.gwc + first, * Q = u.sig + first;
-    const uint32_t * ord = u.order + first;
+    // the merge loop is sequential: run it on shared-memory copies when the segment fits (it nearly always does), so that
+    // its few hundred dependent accesses cost shared-memory instead of L2 latency
+    __shared__ pd_call s_w[PLAN_CAP];
+    __shared__ uint32_t s_s[PLAN_CAP], s_z[PLAN_CAP], s_i[PLAN_CAP], s_g[PLAN_CAP], s_q[PLAN_CAP], s_o[PLAN_CAP];
+    const bool fits = n <= PLAN_CAP;
+    if (fits) {
+        for (uint32_t i = tid; i < n; i += T) { s_w[i] = u.wc[first + i]; s_o[i] = u.order[first + i]; s_g[i] = 0; s_q[i] = 0; }
+        __syncthreads();
+    }
+    if (tid == 0) plan_segment(u, seg, n, fits ? s_w : u.wc + first, fits ? s_s : u.starts + first, fits ? s_z : u.sizes + first,
+                               fits ? s_i : u.inr + first, fits ? s_g : u.gwc + first, fits ? s_q : u.sig + first, fits ? s_o : u.order + first);
+    if (fits) {
+        __syncthreads();
+        for (uint32_t i = tid; i < n; i += T) {
+            u.wc[first + i] = s_w[i]; u.inr[first + i] = s_i[i]; u.gwc[first + i] = s_g[i]; u.sig[first + i] = s_q[i]; u.starts[first + i] = s_s[i];
+        }
+    }
+}
+
+// the reference's merge loop over the sorted headers W[0, n) of one segment (one thread)
+__device__ void plan_segment(const UnifyArgs & u, uint32_t seg, uint32_t n, pd_call * W, uint32_t * S, uint32_t * Z, uint32_t * I,
+                             uint32_t * G, uint32_t * Q, const uint32_t * ord)
+{
     const uint32_t last = n - 1;
     uint32_t cur = 0;
     auto drop_all = [&]() { u.seg_keep[seg] = 0; };
@@ -123,8 +160,7 @@ __global__ void __launch_bounds__(256) k_unify_plan(UnifyArgs u)
     uint32_t winCount = 1, sigWin = 1;
     auto merge_range = [&](uint32_t start, uint32_t lastx) {           // mergeWindowRange :512-559 without the per-sample part
         pd_call & st = W[start];
-        sort_small(S + loff, ln); sort_small(Z + loff, ln);
-        st.position = S[loff + ln / 2]; st.deletion_length = Z[loff + ln / 2];
+        st.position = select_rank(S + loff, ln, ln / 2); st.deletion_length = select_rank(Z + loff, ln, ln / 2);
         loff += ln; ln = 0;
         st.lr = lr / winCount;
         uint32_t g = 0;
@@ -154,7 +190,7 @@ __global__ void __launch_bounds__(256) k_unify_plan(UnifyArgs u)
         else { if (winCount == 1) W[cur].filter = 255; break; }
     }
     uint32_t keep = 0;
-    for (uint32_t k = first_idx; k <= last; ++k) keep += W[k].filter != 255;
+    for (uint32_t k = first_idx; k <= last; ++k) if (W[k].filter != 255) S[keep++] = k;       // (the lists are no longer needed)
     u.seg_keep[seg] = keep;
 }
 
@@ -174,68 +210,96 @@ __global__ void __launch_bounds__(1024) k_unify_offsets(UnifyArgs u)
     if (threadIdx.x == 0) { u.seg_keep[u.nseg] = (uint32_t)carry; *u.total = (uint32_t)carry; }
 }
 
-__global__ void __launch_bounds__(256) k_unify_emit(UnifyArgs u)
+// output slot -> sorted slot of its variant (segment order, then sorted order)
+__global__ void k_unify_list(UnifyArgs u)
 {
-    __shared__ unsigned long long ws[33];
-    const uint32_t seg = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
-    const uint32_t first = u.seg_first[seg], n = u.seg_last[seg] - first;
-    if (n <= 1 || u.seg_keep[seg + 1] == u.seg_keep[seg]) return;
+    const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg >= u.nseg) return;
     uint32_t slot = u.seg_keep[seg];
-    for (uint32_t k = 0; k < n; ++k) {
-        const pd_call hdr = u.wc[first + k];
-        if (hdr.filter == 255) continue;                               // block-uniform
-        const uint32_t g = u.gwc[first + k];
-        const uint32_t * own = u.ps + (size_t)u.order[first + k] * u.row_words;
-        uint32_t * orow = u.out_ps + (size_t)slot * u.row_words;
-        if (g == 0) {                                                  // kept without a merge (stale counters at the end of the loop)
-            for (uint32_t i = tid; i < u.row_words; i += T) orow[i] = own[i];
-            if (tid == 0) { u.out_calls[slot] = hdr; u.out_sig[slot] = 0; }
-            ++slot;
+    if (u.seg_keep[seg + 1] == slot) return;
+    const uint32_t first = u.seg_first[seg], cnt = u.seg_keep[seg + 1] - slot;
+    for (uint32_t i = 0; i < cnt; ++i) u.vlist[slot + i] = first + u.starts[first + i];         // kept sorted slots, left by k_unify_plan
+}
+
+constexpr int EMIT_WARPS_U = 8;
+constexpr uint32_t EMIT_STAGE = 1024;                     // in-range windows whose values a warp stages in shared memory
+
+// grid (variants, sample groups): one WARP per (variant, sample), lanes over the variant's in-range windows. Every value
+// is read once per column; the medians are found by bisection on the value over the staged column (warp-wide counts).
+__global__ void __launch_bounds__(EMIT_WARPS_U * 32) k_unify_emit(UnifyArgs u)
+{
+    __shared__ uint32_t s_vals[EMIT_WARPS_U][EMIT_STAGE];
+    __shared__ uint32_t s_last;
+    const uint32_t slot = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t vs = u.vlist[slot];                            // sorted slot of this variant
+    const pd_call hdr = u.wc[vs];
+    const uint32_t g = u.gwc[vs];
+    const uint32_t * own = u.ps + (size_t)u.order[vs] * u.row_words;
+    const uint32_t * inr = u.inr + vs;
+    uint32_t * orow = u.out_ps + (size_t)slot * u.row_words;
+    uint32_t * vals = s_vals[wid];
+    uint32_t alleles = 0;
+    for (uint32_t s = blockIdx.y * EMIT_WARPS_U + wid; s < u.N; s += gridDim.y * EMIT_WARPS_U) {
+        if (g == 0) {                                              // kept without a merge (stale counters at the end of the loop)
+            if (lane < 13) orow[13 * s + lane] = own[13 * s + lane];
             continue;
         }
-        const uint32_t * inr = u.inr + first + k;
-        unsigned long long alleles = 0;
-        for (uint32_t s = tid; s < u.N; s += T) {
-            // ---- setGenotypes :441-503
-            uint32_t p0 = 0, p1 = 0, p2 = 0;
-            for (uint32_t i = 0; i < g; ++i) {
-                const uint32_t * r = u.ps + (size_t)inr[i] * u.row_words + 13 * s;
-                p0 += r[0]; p1 += r[1]; p2 += r[2];
-            }
-            const double mn = (double)min(min(p0, p1), p2);
-            const double ref = (p0 - mn) / g, het = (p1 - mn) / g, hom = (p2 - mn) / g;
-            uint32_t o[13];
-            o[0] = (uint32_t)round(ref); o[1] = (uint32_t)round(het); o[2] = (uint32_t)round(hom);
-            // ---- median LAD / DAD over the in-range windows: element g/2 of the sorted values, by bisection on the value
-            for (int j = 0; j < 8; ++j) {
-                uint32_t lo = 0xFFFFFFFFu, hi = 0;
-                for (uint32_t i = 0; i < g; ++i) {
-                    const uint32_t v = u.ps[(size_t)inr[i] * u.row_words + 13 * s + 3 + j];
-                    lo = min(lo, v); hi = max(hi, v);
-                }
-                const uint32_t need = g / 2 + 1;
-                while (lo < hi) {
-                    const uint32_t mid = lo + (hi - lo) / 2;
-                    uint32_t cnt = 0;
-                    for (uint32_t i = 0; i < g; ++i) cnt += u.ps[(size_t)inr[i] * u.row_words + 13 * s + 3 + j] <= mid;
-                    if (cnt >= need) hi = mid; else lo = mid + 1;
-                }
-                o[3 + j] = lo;
-            }
-            o[11] = own[13 * s + 11]; o[12] = own[13 * s + 12];
-            if (o[1] == o[2]) { if (het > hom) ++o[1]; else ++o[2]; }
-            else if (o[0] == o[1]) { if (ref > het) ++o[0]; else ++o[1]; }
-            if (o[0] != 0) alleles += (o[1] == 0) ? 1 : 2;             // setFreqFromGTs :344-366
-            for (int j = 0; j < 13; ++j) orow[13 * s + j] = o[j];
+        // ---- setGenotypes :441-503: PL sums over the in-range windows
+        uint32_t p0 = 0, p1 = 0, p2 = 0;
+        for (uint32_t i = lane; i < g; i += 32) {
+            const uint32_t * r = u.ps + (size_t)inr[i] * u.row_words + 13 * s;
+            p0 += r[0]; p1 += r[1]; p2 += r[2];
         }
-        unsigned long long tot;
-        block_excl_scan(alleles, ws, tot);
-        if (tid == 0) {
-            pd_call h = hdr;
-            h.frequency = (double)tot / (u.N * 2.0);
-            u.out_calls[slot] = h; u.out_sig[slot] = u.sig[first + k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { p0 += __shfl_xor_sync(PD_FULL, p0, o); p1 += __shfl_xor_sync(PD_FULL, p1, o); p2 += __shfl_xor_sync(PD_FULL, p2, o); }
+        const double mn = (double)min(min(p0, p1), p2);
+        const double ref = (p0 - mn) / g, het = (p1 - mn) / g, hom = (p2 - mn) / g;
+        uint32_t o0 = (uint32_t)round(ref), o1 = (uint32_t)round(het), o2 = (uint32_t)round(hom);
+        // ---- median LAD / DAD: element g/2 of the sorted values, by bisection on the value
+        uint32_t med = 0;                                          // lane j keeps the median of column j
+        for (int j = 0; j < 8; ++j) {
+            uint32_t lo = 0xFFFFFFFFu, hi = 0;
+            for (uint32_t i = lane; i < g; i += 32) {
+                const uint32_t v = u.ps[(size_t)inr[i] * u.row_words + 13 * s + 3 + j];
+                if (i < EMIT_STAGE) vals[i] = v;
+                lo = min(lo, v); hi = max(hi, v);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(PD_FULL, lo, o)); hi = max(hi, __shfl_xor_sync(PD_FULL, hi, o)); }
+            __syncwarp();
+            const uint32_t need = g / 2 + 1;
+            while (lo < hi) {
+                const uint32_t mid = lo + (hi - lo) / 2;
+                uint32_t cnt = 0;
+                for (uint32_t i = lane; i < g; i += 32)
+                    cnt += (i < EMIT_STAGE ? vals[i] : u.ps[(size_t)inr[i] * u.row_words + 13 * s + 3 + j]) <= mid;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(PD_FULL, cnt, o);
+                if (cnt >= need) hi = mid; else lo = mid + 1;
+            }
+            if ((int)lane == j) med = lo;
+            __syncwarp();
         }
-        ++slot;
+        if (o1 == o2) { if (het > hom) ++o1; else ++o2; }
+        else if (o0 == o1) { if (ref > het) ++o0; else ++o1; }
+        if (o0 != 0) alleles += (o1 == 0) ? 1 : 2;                 // setFreqFromGTs :344-366 (counted by every lane alike)
+        const uint32_t mcol = __shfl_sync(PD_FULL, med, (lane >= 3 && lane < 11) ? (int)lane - 3 : 0);
+        uint32_t w = 0;
+        if (lane == 0) w = o0; else if (lane == 1) w = o1; else if (lane == 2) w = o2;
+        else if (lane < 11) w = mcol;
+        else if (lane < 13) w = own[13 * s + lane];
+        if (lane < 13) orow[13 * s + lane] = w;
+    }
+    // ---- allele count of the variant over all blocks of its row; the last block writes the header
+    if (lane == 0 && alleles) atomicAdd(u.alleles + slot, alleles);
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); s_last = atomicAdd(u.blocks_done + slot, 1u) == gridDim.y - 1; }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        pd_call h = hdr;
+        if (g) h.frequency = (double)atomicAdd(u.alleles + slot, 0u) / (u.N * 2.0);
+        u.out_calls[slot] = h; u.out_sig[slot] = g ? u.sig[vs] : 0u;
     }
 }
 
@@ -330,8 +394,17 @@ int pd_run_unify(pd_ctx * c, uint32_t n_raw, size_t row, uint32_t nseg, int (*en
             c->cap_res_sig = want;
         }
         u.out_calls = c->res_calls; u.out_ps = c->res_ps; u.out_sig = c->res_sig;
-        k_unify_emit<<<nseg, 256, 0, st>>>(u);
-        *launches += 1;
+        if (grow(c, 10, u.vlist, (size_t)total)) return c->status;
+        if (grow(c, 11, u.alleles, (size_t)total)) return c->status;
+        if (grow(c, 12, u.blocks_done, (size_t)total)) return c->status;
+        PD_CUDA(c, cudaMemsetAsync(u.alleles, 0, (size_t)total * 4, st));
+        PD_CUDA(c, cudaMemsetAsync(u.blocks_done, 0, (size_t)total * 4, st));
+        k_unify_list<<<(nseg + 127) / 128, 128, 0, st>>>(u);
+        // enough blocks per variant to occupy the GPU even when a scan yields few variants
+        const uint32_t per_row = (c->N + EMIT_WARPS_U - 1) / EMIT_WARPS_U;
+        const uint32_t gy = std::max<uint32_t>(1, std::min<uint32_t>(per_row, (4 * 148 + total - 1) / total));
+        k_unify_emit<<<dim3(total, gy), EMIT_WARPS_U * 32, 0, st>>>(u);
+        *launches += 2;
         PD_CUDA(c, cudaGetLastError());
         PD_CUDA(c, cudaStreamSynchronize(st));
     }
