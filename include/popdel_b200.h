@@ -114,6 +114,11 @@ int pd_contig_begin(pd_ctx * ctx, uint32_t anchor);
  * May be called several times per read group (positions must keep increasing). Host buffers are reusable on return. */
 int pd_contig_push(pd_ctx * ctx, uint32_t rg, uint64_t n, const uint32_t * pos, const int32_t * dev);
 
+/* Staging memory of pd_contig_push: page-locked (pinned != 0, the default: right for a context that uploads many
+ * contigs, the buffers are reused) or pageable (pinned == 0: right for a one-shot caller such as the command-line shell,
+ * for which page-locking a gigabyte once costs more than the slower pageable copy). Applies to buffers allocated
+ * afterwards. */
+int pd_set_staging(pd_ctx * ctx, int pinned);
 /* Fast path of pd_contig_push for PAGE-LOCKED host arrays (cudaHostAlloc / cudaHostRegister / torch pin_memory):
  * the library only records the pointers; pd_contig_upload copies the raw arrays to the device and packs them THERE
  * (tile search, scan, words, wide list). The arrays must stay valid and unchanged until pd_contig_upload (or the

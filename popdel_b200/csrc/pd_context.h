@@ -45,6 +45,7 @@ struct PdDev {
 struct PdHostRg {                    // host staging of one read group of the current contig (filled by pd_contig_push)
     uint32_t * words = nullptr;      // packed stream (pinned when the context has a device); tiles padded to 4 words
     size_t n_words = 0, cap_words = 0;
+    bool words_pinned = false;
     std::vector<uint32_t> tile_rel;  // tile_rel[t] = first word of tile t (relative to this read group), size = tiles seen + 1
     std::vector<PdLong> longs;
     uint32_t long_span = 0;
@@ -87,6 +88,7 @@ struct pd_ctx {
     std::vector<PdHostRg> hrg;
     std::vector<PdRawRg> raw;            // caller-owned page-locked arrays (device-side packing)
     bool dev_mode = false, host_mode = false;
+    bool pinned_staging = true;          // pd_set_staging: page-locked (default) or pageable staging of pd_contig_push
     // packed host image (offset tables; the words stay in the per-read-group staging vectors)
     std::vector<PdTile> h_tiles;
     std::vector<uint32_t> h_long_off;

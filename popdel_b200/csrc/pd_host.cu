@@ -237,7 +237,7 @@ extern "C" void pd_destroy(pd_ctx * c)
 // ---------------------------------------------------------------------------------------------------------
 static void free_words(pd_ctx * c, PdHostRg & h)
 {
-    if (h.words) { if (c->device >= 0) cudaFreeHost(h.words); else free(h.words); }
+    if (h.words) { if (h.words_pinned) cudaFreeHost(h.words); else free(h.words); }
     h.words = nullptr; h.n_words = h.cap_words = 0;
 }
 
@@ -246,12 +246,14 @@ static bool reserve_words(pd_ctx * c, PdHostRg & h, size_t need)
     if (need <= h.cap_words) return true;
     size_t want = std::max<size_t>(need + need / 4, 4096);
     uint32_t * p = nullptr;
-    if (c->device >= 0) { if (cudaMallocHost(&p, want * 4) != cudaSuccess) return false; }
+    const bool pin = c->device >= 0 && c->pinned_staging;
+    if (pin) { if (cudaMallocHost(&p, want * 4) != cudaSuccess) return false; }
     else { p = (uint32_t *)malloc(want * 4); if (!p) return false; }
     if (h.n_words) memcpy(p, h.words, h.n_words * 4);
     uint32_t * old = h.words;
-    h.words = p; h.cap_words = want;
-    if (old) { if (c->device >= 0) cudaFreeHost(old); else free(old); }
+    const bool old_pinned = h.words_pinned;
+    h.words = p; h.cap_words = want; h.words_pinned = pin;
+    if (old) { if (old_pinned) cudaFreeHost(old); else free(old); }
     return true;
 }
 
@@ -534,6 +536,14 @@ extern "C" int pd_contig_upload(pd_ctx * c)
     PD_CUDA(c, cudaStreamSynchronize(c->stream));
     PD_CUDA(c, cudaEventElapsedTime(&c->ms_h2d, c->ev[0], c->ev[1]));
     c->uploaded = true; c->index_built = false;
+    return 0;
+}
+
+extern "C" int pd_set_staging(pd_ctx * c, int pinned)
+{
+    if (!c) return PD_ERR_ARG;
+    if (c->status) return c->status;
+    c->pinned_staging = pinned != 0;
     return 0;
 }
 

@@ -13,7 +13,7 @@
 //   -u       unsmoothed histograms          -x  uncompressed profiles                -C  cell-population priors
 //   -r CHR[:BEGIN[-END]]  region of interest (1-based, closed; may be repeated)        -R FILE  one region per line
 //   -A FILE  per-read-group active-coverage caps ("ReadGroup maxCov" lines)        -e  rename conflicting read-group IDs per file
-//   -g NUM   CUDA device (0)
+//   -g NUM   CUDA device (0); -1 = dry run of the host path (no scan, header-only VCF; for profiling the loader)
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -44,7 +44,8 @@ inline int rnd(double d) { return (int)std::floor(d + 0.5); }
 // fn(i) for i in [0, n) on all host cores (dynamic schedule)
 template <typename F> void parallelFor(size_t n, F fn)
 {
-    const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(n, std::thread::hardware_concurrency()));
+    static const unsigned cores = getenv("PD_THREADS") ? (unsigned)std::max(1, atoi(getenv("PD_THREADS"))) : std::thread::hardware_concurrency();
+    const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(n, cores));
     if (nt <= 1) { for (size_t i = 0; i < n; ++i) fn(i); return; }
     std::atomic<size_t> next{0};
     std::vector<std::thread> pool;
@@ -409,7 +410,8 @@ int main(int argc, char ** argv)
     const size_t N = opt.files.size();
     std::vector<Profile> & profiles = *new std::vector<Profile>(N);  // never destroyed: the process exits right after the output is written
     StageTimer tm;
-    std::thread warm([&] { if (!getenv("PD_NO_WARM")) pd_device_warmup(opt.device); });      // CUDA context creation overlaps the profile decoding
+    const bool dryRun = opt.device < 0;                               // -g -1: host path only (decode, segments, packing), no scan, no records
+    std::thread warm([&] { if (!dryRun && !getenv("PD_NO_WARM")) pd_device_warmup(opt.device); });      // CUDA context creation overlaps the profile decoding
     // decode the profiles with all host cores (one file per task; SURVEY.md 8f rank 2: the reference re-opens and
     // inflates every file per 200-kbp segment, single-threaded)
     parallelFor(N, [&](size_t i) { loadProfile(opt.files[i], opt.uncompressed, profiles[i]); });
@@ -492,7 +494,8 @@ int main(int argc, char ** argv)
     pd_ctx * ctx = pd_create(&prm, (uint32_t)N, (uint32_t)R, rgs.data(), opt.device);
     if (!ctx) die(std::string("cannot create the scan context: ") + pd_create_error());
     auto check = [&](int rc) { if (rc != 0) die(std::string("scan library: ") + pd_last_error(ctx)); };
-    if (!opt.windowWise) {                                           // unifyCalls per segment, on the device
+    check(pd_set_staging(ctx, 0));                                   // one-shot process: pageable staging (see include/popdel_b200.h)
+    if (!opt.windowWise && !dryRun) {                                // unifyCalls per segment, on the device
         pd_unify_params up; memset(&up, 0, sizeof(up));
         up.mean_stddev = meanStddev; up.min_relative_window_cover = opt.minCover; up.output_failed = opt.outputFailed;
         check(pd_set_unify(ctx, &up));
@@ -562,15 +565,19 @@ int main(int argc, char ** argv)
         // R = anchor + (t+1)*buffer; every sample re-enters through the index at the smallest bucket any sample
         // stopped at, so read pairs between that position and the next 10-kbp index boundary of a straddling
         // 256-bp window are never loaded.
-        std::vector<std::vector<uint32_t>> ppos(R);
-        std::vector<std::vector<int32_t>> pdev(R);
+        // per read group: the read pairs the reference loads, in order. Raw arrays sized once (all read pairs of the read
+        // group on this contig); the fill counts sit on cache lines of their own (threads fill neighbouring read groups)
+        struct alignas(64) RgOut { uint32_t * pos = nullptr; int32_t * dev = nullptr; uint64_t n = 0; };
+        std::vector<RgOut> rgOut(R);
         parallelFor(N, [&](size_t i) {                               // one allocation per read group: its read pairs on this contig
             const Profile & p = profiles[i];
             if ((size_t)c >= p.contigNames.size()) return;
             for (size_t r = 0; r < p.nrg; ++r) {
                 uint64_t n = 0;
                 for (size_t w = p.contigFirst[c]; w < p.contigFirst[c + 1]; ++w) n += p.winOff[w * p.nrg + r + 1] - p.winOff[w * p.nrg + r];
-                ppos[sampleRgs[i][r]].reserve(n); pdev[sampleRgs[i][r]].reserve(n);
+                RgOut & o = rgOut[sampleRgs[i][r]];
+                o.pos = (uint32_t *)malloc(std::max<uint64_t>(n, 1) * 4); o.dev = (int32_t *)malloc(std::max<uint64_t>(n, 1) * 4);
+                if (!o.pos || !o.dev) die("out of memory");
             }
         });
         std::vector<uint32_t> cand(N, anchor);
@@ -600,14 +607,16 @@ int main(int argc, char ** argv)
                     const uint64_t lim = std::min<uint64_t>(Rt, roiEnd);
                     uint32_t stopAt = 0xFFFFFFFFu;
                     for (size_t r = 0; r < p.nrg; ++r) {
-                        std::vector<uint32_t> & dp = ppos[sampleRgs[i][r]];
-                        std::vector<int32_t> & dd = pdev[sampleRgs[i][r]];
+                        RgOut & o = rgOut[sampleRgs[i][r]];
+                        uint32_t * dp = o.pos; int32_t * dd = o.dev;
+                        uint64_t m = o.n;
                         for (uint64_t k = p.winOff[w * p.nrg + r], e = p.winOff[w * p.nrg + r + 1]; k < e; ++k) {
                             const uint32_t bb = base + ((p.recPos[k] - base) / 30) * 30;
                             if ((uint64_t)bb >= lim) { stopAt = std::min(stopAt, bb); break; }
                             if (bb < rb) continue;
-                            dp.push_back(p.recPos[k]); dd.push_back(p.recDev[k]);
+                            dp[m] = p.recPos[k]; dd[m] = p.recDev[k]; ++m;
                         }
+                        o.n = m;
                     }
                     if (stopAt != 0xFFFFFFFFu) {
                         if ((uint64_t)stopAt >= roiEnd) { fin[i] = 1; break; }
@@ -626,13 +635,16 @@ int main(int argc, char ** argv)
         tm.lap("segments");
         {   // the add() loop of every read group (active-coverage cap + packing), one read group per task
             std::atomic<int> bad{0};
-            parallelFor(R, [&](size_t g) { if (pd_contig_push(ctx, (uint32_t)g, ppos[g].size(), ppos[g].data(), pdev[g].data()) != 0) bad = 1; });
+            parallelFor(R, [&](size_t g) {
+                if (pd_contig_push(ctx, (uint32_t)g, rgOut[g].n, rgOut[g].pos, rgOut[g].dev) != 0) bad = 1;
+                free(rgOut[g].pos); free(rgOut[g].dev);
+            });
             if (bad) check(-1);
         }
         tm.lap("push");
 
-        pd_result res;
-        check(pd_contig_scan(ctx, 0, 0, &res));
+        pd_result res; memset(&res, 0, sizeof(res));
+        if (!dryRun) check(pd_contig_scan(ctx, 0, 0, &res));
         totalWindows += res.n_windows;
         tm.lap("scan");
         // window calls (-n) or the merged variants of every segment, already in output order; records are formatted on
