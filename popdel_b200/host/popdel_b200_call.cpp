@@ -113,14 +113,19 @@ void inflateMembers(const std::vector<unsigned char> & in, size_t off, std::vect
     if (inflateInit2(&zs, 31) != Z_OK) die("zlib init failed");
     zs.next_in = const_cast<unsigned char *>(in.data() + off);
     zs.avail_in = (uInt)(in.size() - off);
-    std::vector<unsigned char> buf(4u << 20);
+    // inflate straight into `out` (grown geometrically, ~3.5x the compressed size is typical): no bounce buffer
+    size_t have = out.size();
+    out.resize(have + std::max<size_t>((in.size() - off) * 4, 1u << 20));
     while (zs.avail_in > 0) {
-        zs.next_out = buf.data(); zs.avail_out = (uInt)buf.size();
+        if (have == out.size()) out.resize(out.size() + out.size() / 2);
+        zs.next_out = out.data() + have; zs.avail_out = (uInt)std::min<size_t>(out.size() - have, 1u << 30);
+        const size_t room = zs.avail_out;
         int rc = inflate(&zs, Z_NO_FLUSH);
-        out.insert(out.end(), buf.data(), buf.data() + (buf.size() - zs.avail_out));
+        have += room - zs.avail_out;
         if (rc == Z_STREAM_END) { if (zs.avail_in == 0) break; inflateReset(&zs); }
-        else if (rc != Z_OK) die("corrupt gzip block in profile");
+        else if (rc != Z_OK && !(rc == Z_BUF_ERROR && zs.avail_out == 0)) die("corrupt gzip block in profile");
     }
+    out.resize(have);
     inflateEnd(&zs);
 }
 
@@ -128,7 +133,11 @@ void loadProfile(const std::string & path, bool uncompressed, Profile & p)
 {
     std::ifstream f(path, std::ios::binary);
     if (!f.good()) die("cannot open profile '" + path + "'");
-    std::vector<unsigned char> d((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    f.seekg(0, std::ios::end);
+    const std::streamoff fileSize = f.tellg();
+    f.seekg(0);
+    std::vector<unsigned char> d((size_t)std::max<std::streamoff>(fileSize, 0));
+    if (!d.empty() && !f.read(reinterpret_cast<char *>(d.data()), (std::streamsize)d.size())) die("cannot read profile '" + path + "'");
     if (d.size() < 15 || memcmp(d.data(), "POPDEL\1", 7) != 0) die("'" + path + "' is not a PopDel profile (magic string)");
     p.path = path;
     size_t o = 7;
