@@ -196,10 +196,11 @@ def run_ours(args, rank, world, local_rank):
     clocks.start()
     barrier()
     t0 = time.perf_counter()
-    ms_screen, ms_dev, ms_scr_all, ms_gen, launches = [], [], [], [], 0
+    ms_screen, ms_dev, ms_scr_all, ms_gen, ms_em, launches = [], [], [], [], [], 0
     for _ in range(args.steps):
         res = sc.scan(copy=False)
         ms_screen.append(res["ms_stream"]), ms_dev.append(res["ms_total"]), ms_scr_all.append(res["ms_screen"]), ms_gen.append(res["ms_genotype"])
+        ms_em.append(res["ms_em"])
         launches += int(res["n_kernel_launches"])
     barrier()
     dt = time.perf_counter() - t0
@@ -293,6 +294,13 @@ def run_ours(args, rank, world, local_rank):
                 "host_packer_value": evals_all / dt3, "host_packer_ms_per_step": dt3 * 1e3, "host_packer_h2d_bytes": int(r3["h2d_bytes"])},
         "gpu_launches": launches,
         "unify": unify,
+        "dominant_kernel_by_time": {
+            "kernel": "k_em_one" if (R == N and N <= 256) else "k_em + k_final", "ms": float(np.mean(ms_em)),
+            "pairs_timed": int(res["n_em_pairs_timed"]), "pairs_per_step": int(res["n_candidates"]),
+            "share_of_step": float(np.mean(ms_em)) / ms_d if int(res["n_em_pairs_timed"]) == int(res["n_candidates"]) else None,
+            "bound": "instruction issue + L2 latency (fp64 likelihood look-ups in L2-resident tables); not HBM, not tensor",
+            "evidence": "profiles/r01/ncu_v15_k_em_one_full.txt (same kernel): issue-active 42.8 %, 15.5 of 32 lanes per instruction, "
+                        "fp64 pipe 14.8 %, L2 hit 90 %, DRAM 1.2 % of peak; DESIGN.md section 9 lists the restructurings measured and rejected"},
         "roofline": {"bound": "hbm", "kernel": "k_stream", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "bytes_per_eval": res["algorithmic_bytes"] / evals,
                      "algorithmic_bytes_per_launch": int(res["algorithmic_bytes"]),

@@ -87,6 +87,8 @@ typedef struct {
     const uint32_t * significant_windows;   /* n_calls x Call::significantWindows (SWIN); NULL without pd_set_unify */
     uint64_t n_window_calls;       /* window calls before the merge (they stayed on the device) */
     float    ms_unify;
+    float    ms_em;                /* the FIRST EM chunk's kernels alone (k_em_one, or k_em + k_final); the whole EM when */
+    uint32_t n_em_pairs_timed;     /* the scan has one chunk (<= 16384 (window, length) pairs) */
 } pd_result;
 
 /* Host: processHistogram(hist, 256, smoothing, pseudoCountFraction), insert_histogram_popdel.h:974-986, in place.

@@ -102,7 +102,7 @@ struct pd_ctx {
 
     // device
     cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: result compaction + D2H, overlapped with the EM
-    cudaEvent_t ev[12] = {};
+    cudaEvent_t ev[16] = {};
     cudaEvent_t ev_pack[9] = {};        // device packer: one per copy group (+1)
     uint32_t * d_words = nullptr; size_t cap_words = 0;
     PdTile * d_tiles = nullptr; size_t cap_tiles = 0;

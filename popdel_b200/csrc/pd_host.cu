@@ -264,9 +264,10 @@ extern "C" int pd_contig_begin(pd_ctx * c, uint32_t anchor)
     if (anchor % PD_WIN != 0) return pd_fail(c, PD_ERR_ARG, "pd_contig_begin: anchor must be a multiple of 30 (first 30-bp window of the contig)");
     c->grid.anchor = anchor;
     for (auto & h : c->hrg) {
-        uint32_t * w = h.words; size_t cap = h.cap_words;      // keep the (pinned) buffer across contigs
+        uint32_t * w = h.words; size_t cap = h.cap_words;      // keep the staging buffer across contigs
+        const bool pinned = h.words_pinned;
         h = PdHostRg();
-        h.words = w; h.cap_words = cap;
+        h.words = w; h.cap_words = cap; h.words_pinned = pinned;
         h.tile_rel.assign(1, 0u);
     }
     for (auto & r : c->raw) r = PdRawRg();

@@ -393,7 +393,10 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
                 if (sh && pd_shard_prelaunch(c)) return c->status;
                 // (EM first: CUDA loads kernels lazily and a first-time load may wait for running kernels -- the emitter,
                 // which only waits for ev[6], must never be the one that is running while the EM kernel is being loaded)
+                const bool time_em = chunk_no == 0;
+                if (time_em) PD_CUDA(c, cudaEventRecord(c->ev[12], st));
                 if (pd_launch_em(c, a, e, st, nl)) return c->status;
+                if (time_em) { PD_CUDA(c, cudaEventRecord(c->ev[13], st)); out->n_em_pairs_timed = np; }
                 PD_CUDA(c, cudaStreamWaitEvent(st2, c->ev[6 + par], 0));
                 pd_launch_emit(m, st2, nl);
                 PD_CUDA(c, cudaGetLastError());
@@ -424,6 +427,7 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
     }
     out->n_calls = c->res_count[0];
     out->n_window_calls = out->n_calls;
+    if (out->n_em_pairs_timed) PD_CUDA(c, cudaEventElapsedTime(&out->ms_em, c->ev[12], c->ev[13]));
     if (uni) {
         const uint32_t nseg = (uint32_t)((w_end * PD_WIN) / c->grid.window_buffer + 2);
         PD_CUDA(c, cudaEventRecord(c->ev[11], st));

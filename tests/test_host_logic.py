@@ -140,3 +140,44 @@ def test_shard_attach_rejects_bad_arguments():
     assert lib.pd_shard_attach_group(ctxs, 1, C.byref(info)) == -1             # PD_ERR_ARG: world < 2
     infos = (api.PdShardInfo * 2)(info, info)
     assert lib.pd_shard_attach_group(ctxs, 2, infos) != 0                       # infos[r].rank / world do not describe rank r of 2
+
+
+def test_unify_staging_and_warmup_argument_checks():
+    """pd_set_unify / pd_set_staging / pd_device_warmup: plain return codes, no GPU needed for the checks."""
+    import ctypes as C
+    lib = api.load_library()
+    sc, _ = _tiny_scanner(device=-1)
+    assert lib.pd_set_unify(None, None) == -1                                  # PD_ERR_ARG
+    assert lib.pd_set_staging(None, 0) == -1
+    sc.set_unify(50.0, 0.5, False)
+    sc.set_unify(None)                                                         # back to window calls
+    assert lib.pd_set_staging(sc.ctx, 0) == 0 and lib.pd_set_staging(sc.ctx, 1) == 0
+    lib.pd_device_warmup.argtypes = [C.c_int]
+    assert lib.pd_device_warmup(99) == -2                                      # PD_ERR_CUDA: no such device
+    bad = api.PdUnifyParams(float("nan"), 0.5, 0, 0)
+    assert lib.pd_set_unify(sc.ctx, C.byref(bad)) == -1
+    with pytest.raises(api.ScanError, match="negative or NaN"):                # sticky
+        sc.begin_contig(0)
+
+
+def test_cli_dry_run_of_the_host_path(tmp_path):
+    """`-g -1`: the shell's whole host path (profile decode, region handling, segment loader, host packer) without a scan:
+    runs on a box without a GPU and writes a header-only VCF; option errors are reported, not crashed on."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "popdel_b200", "popdel_b200_call")
+    if not os.path.exists(cli):                                                # g++ only: links against the built scan library
+        subprocess.run(["make", "-C", os.path.join(root, "popdel_b200", "host")], check=True, stdout=subprocess.DEVNULL)
+    case = os.path.join(root, "tests", "golden", "twocontigs")
+    out = tmp_path / "dry.vcf"
+    r = subprocess.run([cli, "profiles.txt", "-g", "-1", "-o", str(out), "-r", "chrB:20001-60000", "-r", "chrA:50,001-100,000"],
+                       cwd=case, capture_output=True, text=True, env=dict(os.environ, PD_TIMING="1"))
+    assert r.returncode == 0, r.stderr
+    assert "segments" in r.stderr and "decode" in r.stderr
+    lines = open(out).read().splitlines()
+    assert lines[0] == "##fileformat=VCFv4.3" and lines[-1].startswith("#CHROM") and lines[-1].endswith("sample00002")
+    r = subprocess.run([cli, "profiles.txt", "-g", "-1", "-o", str(out), "-r", "chrZ:1-100"], cwd=case, capture_output=True, text=True)
+    assert r.returncode != 0 and "Invalid chromosome name" in r.stderr
+    r = subprocess.run([cli, "profiles.txt", "-g", "-1", "-o", str(out), "-A", "missing.txt"], cwd=case, capture_output=True, text=True)
+    assert r.returncode != 0 and "coverage file" in r.stderr
