@@ -1,9 +1,10 @@
 // popdel_b200_call -- host shell of the B200 scan: a drop-in for `popdel call` (reference workflow_popdel.h:256-371).
 //
-// Host side (this file, plain C++17): command line, profile headers and histogram preprocessing, parameter
-// calculation, the segment loader (which read pairs the reference loads in which segment), the segment-level merge
-// (unifyCalls) and the VCF writer. Device side: every window of the scan, through the C ABI of libpopdel_b200.so
-// (include/popdel_b200.h). There is no CPU path for the scan: without a CUDA device the program stops with an error.
+// Host side (this file, plain C++17, all cores): command line, profile decoding into a flat structure-of-arrays image
+// per file, histogram preprocessing and parameter calculation, regions of interest, the segment loader (which read pairs
+// the reference loads in which segment), the VCF writer. Device side, through the C ABI of libpopdel_b200.so
+// (include/popdel_b200.h): every window of the scan and the segment-level merge (unifyCalls, pd_set_unify). There is
+// no CPU path for the scan: without a CUDA device the program stops with an error.
 //
 // Usage: popdel_b200_call [options] PROFILE-LIST-FILE | PROFILE1 PROFILE2 [...]
 //   -o FILE  output VCF (popdel.vcf)        -n  window-wise output, no merging       -F  also write failed calls
