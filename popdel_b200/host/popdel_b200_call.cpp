@@ -108,15 +108,16 @@ template <typename T> T get(const std::vector<unsigned char> & d, size_t & o)
     T v; memcpy(&v, d.data() + o, sizeof(T)); o += sizeof(T); return v;
 }
 
-void inflateMembers(const std::vector<unsigned char> & in, size_t off, std::vector<unsigned char> & out)
+// inflates the gzip members in in[off, end) and appends to `out`
+void inflateMembers(const std::vector<unsigned char> & in, size_t off, size_t end, std::vector<unsigned char> & out)
 {
     z_stream zs; memset(&zs, 0, sizeof(zs));
     if (inflateInit2(&zs, 31) != Z_OK) die("zlib init failed");
     zs.next_in = const_cast<unsigned char *>(in.data() + off);
-    zs.avail_in = (uInt)(in.size() - off);
+    zs.avail_in = (uInt)(end - off);
     // inflate straight into `out` (grown geometrically, ~3.5x the compressed size is typical): no bounce buffer
     size_t have = out.size();
-    out.resize(have + std::max<size_t>((in.size() - off) * 4, 1u << 20));
+    out.resize(have + std::max<size_t>((end - off) * 4, 1u << 16));
     while (zs.avail_in > 0) {
         if (have == out.size()) out.resize(out.size() + out.size() / 2);
         zs.next_out = out.data() + have; zs.avail_out = (uInt)std::min<size_t>(out.size() - have, 1u << 30);
@@ -130,7 +131,7 @@ void inflateMembers(const std::vector<unsigned char> & in, size_t off, std::vect
     inflateEnd(&zs);
 }
 
-void loadProfile(const std::string & path, bool uncompressed, Profile & p)
+void loadProfile(const std::string & path, bool uncompressed, Profile & p, unsigned threads)
 {
     std::ifstream f(path, std::ios::binary);
     if (!f.good()) die("cannot open profile '" + path + "'");
@@ -144,6 +145,8 @@ void loadProfile(const std::string & path, bool uncompressed, Profile & p)
     size_t o = 7;
     p.indexRegionSize = get<uint32_t>(d, o);
     uint32_t nRegions = get<uint32_t>(d, o);
+    const size_t indexAt = o;
+    if (o + 8ull * nRegions > d.size()) die("truncated profile index in '" + path + "'");
     o += 8ull * nRegions;
     uint32_t nrg = get<uint32_t>(d, o);
     if (nrg == 0) die("profile without read groups");
@@ -164,24 +167,74 @@ void loadProfile(const std::string & path, bool uncompressed, Profile & p)
         p.contigNames.emplace_back((const char *)d.data() + o, nl - 1); o += nl;
         p.contigLengths.push_back(get<int32_t>(d, o));
     }
-    std::vector<unsigned char> body;
-    if (uncompressed) body.assign(d.begin() + o, d.end());
-    else if (o < d.size()) inflateMembers(d, o, body);
     p.nrg = nrg;
-    p.recPos.reserve(body.size() / 5); p.recDev.reserve(body.size() / 5);
-    size_t b = 0;
-    while (b + 8 <= body.size()) {
-        p.winChrom.push_back((int32_t)get<uint32_t>(body, b)); p.winBegin.push_back(get<uint32_t>(body, b));
-        const uint32_t begin = p.winBegin.back();
-        for (uint32_t g = 0; g < nrg; ++g) {
-            uint32_t n = get<uint32_t>(body, b);
-            if (b + 5ull * n > body.size()) die("truncated window record in '" + path + "'");
-            p.winOff.push_back(p.recPos.size());
-            for (uint32_t i = 0; i < n; ++i) {
-                uint8_t offc = body[b]; b += 1;
-                int32_t dv; memcpy(&dv, body.data() + b, 4); b += 4;
-                p.recPos.push_back(begin + offc); p.recDev.push_back(dv);
+    // ---- body: 256-bp window records, one gzip member per 10-kbp index region (or raw with -x). The index offsets are
+    // record boundaries, so runs of members can be inflated and parsed independently: `threads` tasks per file when there
+    // are fewer files than cores
+    struct Part { std::vector<int32_t> chrom; std::vector<uint32_t> begin, pos; std::vector<uint64_t> off; std::vector<int32_t> dev; };
+    auto parse = [&](const unsigned char * body, size_t size, Part & q) {
+        q.pos.reserve(size / 5); q.dev.reserve(size / 5);
+        size_t b = 0;
+        auto u32 = [&]() { uint32_t v; if (b + 4 > size) die("truncated window record in '" + path + "'"); memcpy(&v, body + b, 4); b += 4; return v; };
+        while (b + 8 <= size) {
+            q.chrom.push_back((int32_t)u32()); q.begin.push_back(u32());
+            const uint32_t begin = q.begin.back();
+            for (uint32_t g = 0; g < nrg; ++g) {
+                const uint32_t n = u32();
+                if (b + 5ull * n > size) die("truncated window record in '" + path + "'");
+                q.off.push_back(q.pos.size());
+                for (uint32_t i = 0; i < n; ++i) {
+                    const uint8_t offc = body[b]; b += 1;
+                    int32_t dv; memcpy(&dv, body + b, 4); b += 4;
+                    q.pos.push_back(begin + offc); q.dev.push_back(dv);
+                }
             }
+        }
+    };
+    std::vector<size_t> cuts;                                        // distinct member starts in [o, size), ascending
+    for (uint32_t r = 0; r < nRegions; ++r) {
+        uint64_t v; memcpy(&v, d.data() + indexAt + 8ull * r, 8);
+        if (v >= o && v < d.size()) cuts.push_back((size_t)v);
+    }
+    std::sort(cuts.begin(), cuts.end());
+    cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+    size_t nTasks = std::max<unsigned>(threads, 1);
+    if (cuts.empty() || cuts[0] != o || nTasks == 1) { cuts.assign(1, o); nTasks = 1; }      // (index does not start at the body: one task)
+    nTasks = std::min(nTasks, cuts.size());
+    std::vector<size_t> taskBegin(nTasks + 1, d.size());
+    for (size_t t = 0; t < nTasks; ++t) {                            // balanced by compressed bytes, cut at member starts
+        const size_t want = o + (d.size() - o) * t / nTasks;
+        taskBegin[t] = *std::lower_bound(cuts.begin(), cuts.end(), want);
+    }
+    taskBegin[0] = o;
+    std::vector<Part> parts(nTasks);
+    auto runTask = [&](size_t t) {
+        const size_t a = taskBegin[t], e = taskBegin[t + 1];
+        if (a >= e) return;
+        if (uncompressed) parse(d.data() + a, e - a, parts[t]);
+        else { std::vector<unsigned char> body; inflateMembers(d, a, e, body); parse(body.data(), body.size(), parts[t]); }
+    };
+    if (nTasks == 1) runTask(0);
+    else {
+        std::vector<std::thread> pool;
+        for (size_t t = 0; t < nTasks; ++t) pool.emplace_back(runTask, t);
+        for (auto & th : pool) th.join();
+    }
+    if (nTasks == 1) {
+        p.winChrom.swap(parts[0].chrom); p.winBegin.swap(parts[0].begin); p.winOff.swap(parts[0].off);
+        p.recPos.swap(parts[0].pos); p.recDev.swap(parts[0].dev);
+    } else {
+        size_t nWin = 0, nRec = 0;
+        for (const Part & q : parts) { nWin += q.begin.size(); nRec += q.pos.size(); }
+        p.winChrom.reserve(nWin); p.winBegin.reserve(nWin); p.winOff.reserve(nWin * nrg + 1); p.recPos.reserve(nRec); p.recDev.reserve(nRec);
+        for (Part & q : parts) {
+            const uint64_t base = p.recPos.size();
+            p.winChrom.insert(p.winChrom.end(), q.chrom.begin(), q.chrom.end());
+            p.winBegin.insert(p.winBegin.end(), q.begin.begin(), q.begin.end());
+            for (uint64_t v : q.off) p.winOff.push_back(base + v);
+            p.recPos.insert(p.recPos.end(), q.pos.begin(), q.pos.end());
+            p.recDev.insert(p.recDev.end(), q.dev.begin(), q.dev.end());
+            q = Part();
         }
     }
     p.winOff.push_back(p.recPos.size());
@@ -424,8 +477,23 @@ int main(int argc, char ** argv)
     std::thread warm([&] { if (!dryRun && !getenv("PD_NO_WARM")) pd_device_warmup(opt.device); });      // CUDA context creation overlaps the profile decoding
     // decode the profiles with all host cores (one file per task; SURVEY.md 8f rank 2: the reference re-opens and
     // inflates every file per 200-kbp segment, single-threaded)
-    parallelFor(N, [&](size_t i) { loadProfile(opt.files[i], opt.uncompressed, profiles[i]); });
+    {
+        const unsigned cores = getenv("PD_THREADS") ? (unsigned)std::max(1, atoi(getenv("PD_THREADS"))) : std::thread::hardware_concurrency();
+        const unsigned perFile = (unsigned)std::max<size_t>(1, cores / std::max<size_t>(N, 1));      // fewer files than cores: split the files
+        parallelFor(N, [&](size_t i) { loadProfile(opt.files[i], opt.uncompressed, profiles[i], perFile); });
+    }
     tm.lap("decode");
+    if (getenv("PD_DEBUG_DECODE"))                                    // checksums of the decoded images (decode paths must agree)
+        for (size_t i = 0; i < N; ++i) {
+            const Profile & p = profiles[i];
+            uint64_t a = 0, b = 0, c2 = 0, e = 0;
+            for (uint32_t v : p.recPos) a += v;
+            for (int32_t v : p.recDev) b += (uint64_t)(int64_t)v;
+            for (uint64_t v : p.winOff) c2 += v;
+            for (size_t w = 0; w < p.numWins(); ++w) e += p.winBegin[w] * 31ull + (uint64_t)p.winChrom[w];
+            fprintf(stderr, "[popdel_b200] decode %zu: %zu windows %zu read pairs sums %llu %llu %llu %llu\n", i, p.numWins(), p.recPos.size(),
+                    (unsigned long long)a, (unsigned long long)b, (unsigned long long)c2, (unsigned long long)e);
+        }
 
     // ---- histograms and parameters (reference parameter_calculation_popdel_call.h:160-204)
     std::vector<pd_rg> rgs;

@@ -35,6 +35,10 @@ VARIANTS = [
          files={"opt_rois.txt": "chrA:110001-135000\nchrB:100001-140000\n"}),
     dict(case="twocontigs", name="r_contig", list="profiles.txt", args=["-r", "chrB"], files={}),
     dict(case="gap", name="r_gap_n", list="profiles.txt", args=["-r", "chr2:110001-790000", "-n"], files={}),
+    # uncompressed profiles (-x), unzipped by the reference's own `popdel view -o`
+    dict(case="highcov", name="x", list="opt_x_profiles.txt", args=["-x"],
+         unzip={"opt_x_s0.profile": "sample00000.profile", "opt_x_s1.profile": "sample00001.profile", "opt_x_s2.profile": "sample00002.profile"},
+         files={"opt_x_profiles.txt": "opt_x_s0.profile\nopt_x_s1.profile\nopt_x_s2.profile\n"}),
     dict(case="offset", name="u_t_p", list="profiles.txt", args=["-u", "-t", "6", "-p", "0.01", "-s", "0.5", "-f", "200"], files={}),
 ]
 
@@ -47,6 +51,8 @@ def main():
             open(os.path.join(d, fn), "w").write(text)
         for dst, src in v.get("copies", {}).items():
             shutil.copyfile(os.path.join(d, src), os.path.join(d, dst))
+        for dst, src in v.get("unzip", {}).items():
+            subprocess.run([REF, "view", src, "-o", dst], check=True, cwd=d, stdout=subprocess.DEVNULL)
         vcf = f"opt_{v['name']}.vcf"
         subprocess.run([REF, "call", v["list"], "-o", vcf] + v["args"], check=True, cwd=d, stdout=subprocess.DEVNULL)
         n = sum(1 for line in open(os.path.join(d, vcf)) if not line.startswith("#"))
