@@ -30,6 +30,7 @@ struct UnifyArgs {
     const pd_call * calls; const uint32_t * ps;        // window calls of the scan (device), window order
     uint32_t n_raw, row_words, N, nseg;
     double sd, min_cover; int output_failed;
+    int force_global;                                  // test knob (PD_UNIFY_GLOBAL): run the merge loop on global memory
     uint32_t * seg_first, * seg_last;                  // [nseg]
     uint32_t * seg_keep;                               // [nseg + 1] variants per segment, then their exclusive prefix
     // per window call; a segment owns the entries [seg_first, seg_last) of each array
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(256) k_unify_plan(UnifyArgs u)
     // its few hundred dependent accesses cost shared-memory instead of L2 latency
     __shared__ pd_call s_w[PLAN_CAP];
     __shared__ uint32_t s_s[PLAN_CAP], s_z[PLAN_CAP], s_i[PLAN_CAP], s_g[PLAN_CAP], s_q[PLAN_CAP], s_o[PLAN_CAP];
-    const bool fits = n <= PLAN_CAP;
+    const bool fits = n <= PLAN_CAP && !u.force_global;
     if (fits) {
         for (uint32_t i = tid; i < n; i += T) { s_w[i] = u.wc[first + i]; s_o[i] = u.order[first + i]; s_g[i] = 0; s_q[i] = 0; }
         __syncthreads();
@@ -363,6 +364,7 @@ int pd_run_unify(pd_ctx * c, uint32_t n_raw, size_t row, uint32_t nseg, int (*en
     UnifyArgs u;
     memset(&u, 0, sizeof(u));
     u.calls = c->d_u_calls; u.ps = c->d_u_ps; u.n_raw = n_raw; u.row_words = (uint32_t)row; u.N = c->N; u.nseg = nseg;
+    u.force_global = getenv("PD_UNIFY_GLOBAL") != nullptr;
     u.sd = c->unify.mean_stddev; u.min_cover = c->unify.min_relative_window_cover; u.output_failed = c->unify.output_failed;
     if (grow(c, 0, u.seg_first, (size_t)nseg)) return c->status;
     if (grow(c, 1, u.seg_last, (size_t)nseg)) return c->status;

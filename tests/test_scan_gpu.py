@@ -177,6 +177,8 @@ def test_device_unify_larger_cohort_and_buffer_growth(oracle_lib, monkeypatch):
     monkeypatch.setenv("PD_UNIFY_CAP", "8")
     monkeypatch.setenv("PD_EM_CHUNK", "16")
     for cover in (0.5, 0.9):
+        if cover == 0.9:
+            monkeypatch.setenv("PD_UNIFY_GLOBAL", "1")     # the path for segments with more window calls than the shared-memory copies hold
         uni, _ = api.scan_cohort(samples, params, unify=dict(mean_stddev=sd, min_relative_window_cover=cover, output_failed=True))
         ref_calls, ref_ps, ref_sig = oracle_lib.unify_segments(raw["calls"], raw["per_sample"], sd, cover, True)
         assert_calls_equal(uni["calls"], uni["per_sample"], ref_calls, ref_ps)
