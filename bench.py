@@ -105,7 +105,7 @@ class ClockSampler:
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
         except OSError:
             self.proc = None
@@ -113,7 +113,10 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
-        time.sleep(0.15)
+        t_end = time.time() + 5.0                # nvidia-smi can take longer to start than a short timed region lasts
+        while not self.lines and time.time() < t_end and self.proc.poll() is None:
+            time.sleep(0.05)
+        time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -190,10 +193,13 @@ def run_ours(args, rank, world, local_rank):
     sc.upload()
     res = sc.scan(copy=False)
     evals = int(res["n_windows"]) * N
+    clocks = ClockSampler(local_rank)             # started before the warm-up steps so that it is sampling when the timed steps run
+    clocks.start()
     for _ in range(args.warmup):
         res = sc.scan(copy=False)
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    t_w = time.time()
+    while clocks.proc and not clocks.lines and time.time() - t_w < 5.0:     # more untimed warm-up steps until nvidia-smi delivers samples
+        res = sc.scan(copy=False)
     barrier()
     t0 = time.perf_counter()
     ms_screen, ms_dev, ms_scr_all, ms_gen, ms_em, launches = [], [], [], [], [], 0
