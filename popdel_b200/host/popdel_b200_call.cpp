@@ -100,6 +100,10 @@ struct Profile {
     std::vector<int32_t> recDev;
     std::vector<size_t> contigFirst;                         // first window of each contig (number of windows if none)
     size_t numWins() const { return winBegin.size(); }
+    // file layout: byte offset of the body, the index (one entry per 10-kbp region, contig after contig), first entry per contig
+    uint64_t bodyStart = 0, fileSize = 0;
+    std::vector<uint64_t> index;
+    std::vector<size_t> regionBase;
 };
 
 template <typename T> T get(const std::vector<unsigned char> & d, size_t & o)
@@ -131,42 +135,116 @@ void inflateMembers(const std::vector<unsigned char> & in, size_t off, size_t en
     inflateEnd(&zs);
 }
 
-void loadProfile(const std::string & path, bool uncompressed, Profile & p, unsigned threads)
+// parses header + index + contig table from the first bytes of a file; false if `d` ends inside the header
+bool parseHeader(const std::string & path, const std::vector<unsigned char> & d, Profile & p)
 {
-    std::ifstream f(path, std::ios::binary);
-    if (!f.good()) die("cannot open profile '" + path + "'");
-    f.seekg(0, std::ios::end);
-    const std::streamoff fileSize = f.tellg();
-    f.seekg(0);
-    std::vector<unsigned char> d((size_t)std::max<std::streamoff>(fileSize, 0));
-    if (!d.empty() && !f.read(reinterpret_cast<char *>(d.data()), (std::streamsize)d.size())) die("cannot read profile '" + path + "'");
-    if (d.size() < 15 || memcmp(d.data(), "POPDEL\1", 7) != 0) die("'" + path + "' is not a PopDel profile (magic string)");
-    p.path = path;
     size_t o = 7;
-    p.indexRegionSize = get<uint32_t>(d, o);
-    uint32_t nRegions = get<uint32_t>(d, o);
-    const size_t indexAt = o;
-    if (o + 8ull * nRegions > d.size()) die("truncated profile index in '" + path + "'");
+    auto have = [&](size_t n) { return o + n <= d.size(); };
+    auto u32 = [&]() { uint32_t v; memcpy(&v, d.data() + o, 4); o += 4; return v; };
+    p.path = path; p.rgs.clear(); p.contigNames.clear(); p.contigLengths.clear(); p.index.clear();
+    if (!have(8)) return false;
+    p.indexRegionSize = u32();
+    const uint32_t nRegions = u32();
+    if (p.indexRegionSize == 0) die("'" + path + "': index region size 0");
+    if (!have(8ull * nRegions + 4)) return false;
+    p.index.resize(nRegions);
+    if (nRegions) memcpy(p.index.data(), d.data() + o, 8ull * nRegions);
     o += 8ull * nRegions;
-    uint32_t nrg = get<uint32_t>(d, o);
+    const uint32_t nrg = u32();
     if (nrg == 0) die("profile without read groups");
     for (uint32_t i = 0; i < nrg; ++i) {
         RgHeader h;
-        uint32_t nl = get<uint32_t>(d, o);
+        if (!have(4)) return false;
+        const uint32_t nl = u32();
+        if (nl == 0 || !have((size_t)nl + 24)) return false;
         h.name.assign((const char *)d.data() + o, nl - 1); o += nl;
-        h.median = get<uint32_t>(d, o); h.stddev = get<double>(d, o); h.readLength = get<uint32_t>(d, o);
-        h.offset = (int32_t)get<uint32_t>(d, o);
-        uint32_t end = get<uint32_t>(d, o);
+        h.median = u32(); memcpy(&h.stddev, d.data() + o, 8); o += 8; h.readLength = u32();
+        h.offset = (int32_t)u32();
+        const uint32_t end = u32();
+        if (end < (uint32_t)h.offset || !have(8ull * (end - h.offset))) return false;
         h.counts.resize(end - h.offset);
-        for (double & v : h.counts) v = get<double>(d, o);
+        if (!h.counts.empty()) memcpy(h.counts.data(), d.data() + o, 8ull * h.counts.size());
+        o += 8ull * h.counts.size();
         p.rgs.push_back(h);
     }
-    uint32_t nc = get<uint32_t>(d, o);
+    if (!have(4)) { p.rgs.clear(); return false; }
+    const uint32_t nc = u32();
     for (uint32_t i = 0; i < nc; ++i) {
-        uint32_t nl = get<uint32_t>(d, o);
+        if (!have(4)) { p.rgs.clear(); return false; }
+        const uint32_t nl = u32();
+        if (nl == 0 || !have((size_t)nl + 4)) { p.rgs.clear(); return false; }
         p.contigNames.emplace_back((const char *)d.data() + o, nl - 1); o += nl;
-        p.contigLengths.push_back(get<int32_t>(d, o));
+        int32_t len; memcpy(&len, d.data() + o, 4); o += 4;
+        p.contigLengths.push_back(len);
     }
+    p.nrg = nrg;
+    p.bodyStart = o;
+    p.regionBase.assign(nc + 1, 0);
+    for (uint32_t i = 0; i < nc; ++i) p.regionBase[i + 1] = p.regionBase[i] + (size_t)(std::max(p.contigLengths[i], 0) / p.indexRegionSize) + 1;
+    if (p.regionBase[nc] > p.index.size()) p.regionBase.assign(nc + 1, 0), p.index.clear();      // index does not cover the contigs: no seeking
+    return true;
+}
+
+// reads `n` bytes at `off`
+void readAt(const std::string & path, uint64_t off, size_t n, std::vector<unsigned char> & out)
+{
+    out.resize(n);
+    if (n == 0) return;
+    std::ifstream f(path, std::ios::binary);
+    if (!f.good()) die("cannot open profile '" + path + "'");
+    f.seekg((std::streamoff)off);
+    if (!f.read(reinterpret_cast<char *>(out.data()), (std::streamsize)n)) die("cannot read profile '" + path + "'");
+}
+
+// header, index and contig table of a profile (insert_histogram_popdel.h:334-525); the body stays on disk
+void loadHeader(const std::string & path, Profile & p)
+{
+    {
+        std::ifstream f(path, std::ios::binary);
+        if (!f.good()) die("cannot open profile '" + path + "'");
+        f.seekg(0, std::ios::end);
+        p.fileSize = (uint64_t)std::max<std::streamoff>(f.tellg(), 0);
+    }
+    std::vector<unsigned char> d;
+    readAt(path, 0, (size_t)std::min<uint64_t>(p.fileSize, 15), d);
+    if (d.size() < 15 || memcmp(d.data(), "POPDEL\1", 7) != 0) die("'" + path + "' is not a PopDel profile (magic string)");
+    uint32_t nRegions; memcpy(&nRegions, d.data() + 11, 4);
+    // the header is small next to the body but has no length field: read generously, everything if that was not enough
+    uint64_t guess = std::min<uint64_t>(p.fileSize, 15 + 8ull * nRegions + (4u << 20));
+    for (;;) {
+        readAt(path, 0, (size_t)guess, d);
+        if (parseHeader(path, d, p) || guess == p.fileSize) break;
+        guess = p.fileSize;
+    }
+    if (p.rgs.empty()) die("truncated profile '" + path + "'");
+}
+
+// one contig region of the body -> the flat image (previous contents are dropped): the windows of contig `c` from the
+// index region of `beginPos` to the one of `endPos + 29`; the byte range comes from the index like the reference's
+// jumpToRegion (insert_histogram_popdel.h:531-562), so a region query decodes only what it needs
+void loadBody(Profile & p, bool uncompressed, int32_t c, uint64_t beginPos, uint64_t endPos, unsigned threads)
+{
+    const std::string & path = p.path;
+    const uint32_t nrg = (uint32_t)p.nrg;
+    const size_t nc = p.contigNames.size();
+    p.winChrom.clear(); p.winBegin.clear(); p.winOff.clear(); p.recPos.clear(); p.recDev.clear();
+    p.contigFirst.assign(nc + 1, 0);
+    uint64_t a = p.fileSize, e = p.fileSize;
+    if ((size_t)c < nc && p.index.empty()) { a = p.bodyStart; e = p.fileSize; }      // no usable index: the whole body, filtered below
+    else if ((size_t)c < nc) {
+        const uint64_t irs = p.indexRegionSize;
+        const size_t r0 = p.regionBase[c], nr = p.regionBase[c + 1] - r0;
+        // (a 256-bp window that begins up to 29 bp beyond the region's end can still hold a 30-bp bucket below it: the
+        // bucket grid is anchored at the window's first read pair, window_podel.h:314-418)
+        const uint64_t rb = beginPos / irs, re = (endPos + 29) / irs + 1;
+        if (rb < nr) a = p.index[r0 + rb];
+        const size_t endEntry = r0 + (size_t)std::min<uint64_t>(re, nr);
+        if (endEntry < p.index.size()) e = p.index[endEntry];
+        a = std::min(std::max(a, p.bodyStart), p.fileSize); e = std::min(std::max(e, a), p.fileSize);
+    }
+    std::vector<unsigned char> d;
+    readAt(path, a, (size_t)(e - a), d);
+    const size_t o = 0;
     p.nrg = nrg;
     // ---- body: 256-bp window records, one gzip member per 10-kbp index region (or raw with -x). The index offsets are
     // record boundaries, so runs of members can be inflated and parsed independently: `threads` tasks per file when there
@@ -191,11 +269,8 @@ void loadProfile(const std::string & path, bool uncompressed, Profile & p, unsig
             }
         }
     };
-    std::vector<size_t> cuts;                                        // distinct member starts in [o, size), ascending
-    for (uint32_t r = 0; r < nRegions; ++r) {
-        uint64_t v; memcpy(&v, d.data() + indexAt + 8ull * r, 8);
-        if (v >= o && v < d.size()) cuts.push_back((size_t)v);
-    }
+    std::vector<size_t> cuts;                                        // distinct member starts in [a, e), relative to d, ascending
+    for (uint64_t v : p.index) if (v >= a && v < e) cuts.push_back((size_t)(v - a));
     std::sort(cuts.begin(), cuts.end());
     cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
     size_t nTasks = std::max<unsigned>(threads, 1);
@@ -204,7 +279,8 @@ void loadProfile(const std::string & path, bool uncompressed, Profile & p, unsig
     std::vector<size_t> taskBegin(nTasks + 1, d.size());
     for (size_t t = 0; t < nTasks; ++t) {                            // balanced by compressed bytes, cut at member starts
         const size_t want = o + (d.size() - o) * t / nTasks;
-        taskBegin[t] = *std::lower_bound(cuts.begin(), cuts.end(), want);
+        const auto it = std::lower_bound(cuts.begin(), cuts.end(), want);
+        taskBegin[t] = it == cuts.end() ? d.size() : *it;                // (no member starts at or after `want`: an empty task)
     }
     taskBegin[0] = o;
     std::vector<Part> parts(nTasks);
@@ -237,11 +313,25 @@ void loadProfile(const std::string & path, bool uncompressed, Profile & p, unsig
             q = Part();
         }
     }
-    p.winOff.push_back(p.recPos.size());
-    const size_t nw = p.numWins();
-    p.contigFirst.assign(nc + 1, nw);
-    for (size_t i = nw; i-- > 0;) if (p.winChrom[i] >= 0 && (uint32_t)p.winChrom[i] < nc) p.contigFirst[p.winChrom[i]] = i;
-    for (size_t c = nc; c-- > 0;) if (p.contigFirst[c] == nw) p.contigFirst[c] = p.contigFirst[c + 1];
+    // only contig c's windows are visible (a back-filled index entry may have led into the next contig)
+    size_t lo = 0;
+    while (lo < p.winBegin.size() && p.winChrom[lo] != c) ++lo;
+    if (lo > 0) {                                                     // (only without an index: windows of earlier contigs)
+        const uint64_t drop = lo < p.winBegin.size() ? p.winOff[lo * nrg] : (uint64_t)p.recPos.size();
+        p.winChrom.erase(p.winChrom.begin(), p.winChrom.begin() + lo); p.winBegin.erase(p.winBegin.begin(), p.winBegin.begin() + lo);
+        p.winOff.erase(p.winOff.begin(), p.winOff.begin() + lo * nrg);
+        for (uint64_t & v : p.winOff) v -= drop;
+        p.recPos.erase(p.recPos.begin(), p.recPos.begin() + drop); p.recDev.erase(p.recDev.begin(), p.recDev.begin() + drop);
+    }
+    size_t keep = 0;
+    while (keep < p.winBegin.size() && p.winChrom[keep] == c) ++keep;
+    const uint64_t endOff = keep < p.winBegin.size() ? p.winOff[keep * nrg] : (uint64_t)p.recPos.size();
+    if (keep < p.winBegin.size()) {
+        p.winChrom.resize(keep); p.winBegin.resize(keep); p.winOff.resize(keep * nrg);
+        p.recPos.resize(endOff); p.recDev.resize(endOff);
+    }
+    p.winOff.push_back(endOff);
+    for (size_t k = 0; k <= nc; ++k) p.contigFirst[k] = k <= (size_t)c ? 0 : keep;
 }
 
 // first window (file order) whose (contig, index region) is >= (c, region): what the index seek lands on
@@ -477,12 +567,11 @@ int main(int argc, char ** argv)
     std::thread warm([&] { if (!dryRun && !getenv("PD_NO_WARM")) pd_device_warmup(opt.device); });      // CUDA context creation overlaps the profile decoding
     // decode the profiles with all host cores (one file per task; SURVEY.md 8f rank 2: the reference re-opens and
     // inflates every file per 200-kbp segment, single-threaded)
-    {
-        const unsigned cores = getenv("PD_THREADS") ? (unsigned)std::max(1, atoi(getenv("PD_THREADS"))) : std::thread::hardware_concurrency();
-        const unsigned perFile = (unsigned)std::max<size_t>(1, cores / std::max<size_t>(N, 1));      // fewer files than cores: split the files
-        parallelFor(N, [&](size_t i) { loadProfile(opt.files[i], opt.uncompressed, profiles[i], perFile); });
-    }
-    tm.lap("decode");
+    const unsigned hostCores = getenv("PD_THREADS") ? (unsigned)std::max(1, atoi(getenv("PD_THREADS"))) : std::thread::hardware_concurrency();
+    const unsigned perFile = (unsigned)std::max<size_t>(1, hostCores / std::max<size_t>(N, 1));      // fewer files than cores: split the files
+    parallelFor(N, [&](size_t i) { loadHeader(opt.files[i], profiles[i]); });
+    tm.lap("headers");
+    auto debugDecode = [&]() {
     if (getenv("PD_DEBUG_DECODE"))                                    // checksums of the decoded images (decode paths must agree)
         for (size_t i = 0; i < N; ++i) {
             const Profile & p = profiles[i];
@@ -494,6 +583,7 @@ int main(int argc, char ** argv)
             fprintf(stderr, "[popdel_b200] decode %zu: %zu windows %zu read pairs sums %llu %llu %llu %llu\n", i, p.numWins(), p.recPos.size(),
                     (unsigned long long)a, (unsigned long long)b, (unsigned long long)c2, (unsigned long long)e);
         }
+    };
 
     // ---- histograms and parameters (reference parameter_calculation_popdel_call.h:160-204)
     std::vector<pd_rg> rgs;
@@ -623,6 +713,11 @@ int main(int argc, char ** argv)
         // sample jumps through its index to the region's begin and contributes the first bucket of the 256-bp window it
         // lands on -- which may lie BEFORE the region (index granularity); the window grid and the segment borders of
         // this region are anchored there
+        // decode this region of every profile (one pass per file and region on all cores; the reference
+        // re-opens, seeks and inflates every file once per 200-kbp segment, single-threaded)
+        parallelFor(N, [&](size_t i) { loadBody(profiles[i], opt.uncompressed, c, (uint64_t)roi.begin, (uint64_t)roi.end, perFile); });
+        tm.lap("decode");
+        debugDecode();
         bool found = false; uint32_t anchor = 0xFFFFFFFFu;
         for (size_t i = 0; i < N; ++i) {
             const Profile & p = profiles[i];
@@ -711,6 +806,13 @@ int main(int argc, char ** argv)
             Rt += WB;
         }
         tm.lap("segments");
+        if (getenv("PD_DEBUG_DECODE"))
+            for (size_t g = 0; g < R; ++g) {
+                uint64_t a = 0, b = 0;
+                for (uint64_t k = 0; k < rgOut[g].n; ++k) { a += rgOut[g].pos[k]; b += (uint64_t)(int64_t)rgOut[g].dev[k]; }
+                fprintf(stderr, "[popdel_b200] pushed rg %zu anchor %u: %llu read pairs sums %llu %llu\n", g, anchor, (unsigned long long)rgOut[g].n,
+                        (unsigned long long)a, (unsigned long long)b);
+            }
         {   // the add() loop of every read group (active-coverage cap + packing), one read group per task
             std::atomic<int> bad{0};
             parallelFor(R, [&](size_t g) {
