@@ -181,3 +181,25 @@ def test_cli_dry_run_of_the_host_path(tmp_path):
     assert r.returncode != 0 and "Invalid chromosome name" in r.stderr
     r = subprocess.run([cli, "profiles.txt", "-g", "-1", "-o", str(out), "-A", "missing.txt"], cwd=case, capture_output=True, text=True)
     assert r.returncode != 0 and "coverage file" in r.stderr
+
+
+@pytest.mark.parametrize("case,args", [("twocontigs", ["-r", "chrB:20001-60000", "-r", "chrA:50001-100000", "-R", "opt_rois.txt"]),
+                                       ("gap", ["-r", "chr2:110001-790000"]), ("mixedrg", []), ("highcov", ["-x"])])
+def test_cli_host_path_is_independent_of_the_thread_count(case, args, tmp_path):
+    """The read pairs the shell hands to the scan (dry run, PD_DEBUG_DECODE checksums per read group and region) do not
+    depend on how the decode is split: 1 thread, several tasks per file (index-offset cuts), more tasks than members."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "popdel_b200", "popdel_b200_call")
+    if not os.path.exists(cli):
+        subprocess.run(["make", "-C", os.path.join(root, "popdel_b200", "host")], check=True, stdout=subprocess.DEVNULL)
+    lst = "opt_x_profiles.txt" if "-x" in args else "profiles.txt"
+    seen = []
+    for threads in ("1", "7", "64"):
+        r = subprocess.run([cli, lst, "-g", "-1", "-o", str(tmp_path / "dry.vcf")] + args, cwd=os.path.join(root, "tests", "golden", case),
+                           capture_output=True, text=True, env=dict(os.environ, PD_DEBUG_DECODE="1", PD_THREADS=threads))
+        assert r.returncode == 0, r.stderr
+        seen.append([l for l in r.stderr.splitlines() if " pushed rg " in l])
+    assert len(seen[0]) >= 3 and sum(int(l.split()[6]) for l in seen[0]) > 10000
+    assert seen[0] == seen[1] == seen[2]
