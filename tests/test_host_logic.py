@@ -203,3 +203,33 @@ def test_cli_host_path_is_independent_of_the_thread_count(case, args, tmp_path):
         seen.append([l for l in r.stderr.splitlines() if " pushed rg " in l])
     assert len(seen[0]) >= 3 and sum(int(l.split()[6]) for l in seen[0]) > 10000
     assert seen[0] == seen[1] == seen[2]
+
+
+def test_cli_region_syntax_and_merging(tmp_path):
+    """Region strings like the reference's parseGenomicRegion ("chr", "chr:begin", "chr:begin-end", thousands separators),
+    -R files, sorting into the contig order of the first profile and merging of overlapping regions: equivalent
+    spellings hand the same read pairs to the scan (dry run)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "popdel_b200", "popdel_b200_call")
+    case = os.path.join(root, "tests", "golden", "twocontigs")
+
+    def pushed(args):
+        r = subprocess.run([cli, "profiles.txt", "-g", "-1", "-o", str(tmp_path / "dry.vcf")] + args, cwd=case, capture_output=True, text=True,
+                           env=dict(os.environ, PD_DEBUG_DECODE="1"))
+        assert r.returncode == 0, r.stderr
+        return [l for l in r.stderr.splitlines() if " pushed rg " in l]
+
+    rois = tmp_path / "rois.txt"
+    rois.write_text("chrB:20,001-60,000\nchrA:50001-100000\n")
+    a = pushed(["-r", "chrA:50001-100000", "-r", "chrB:20001-60000"])
+    assert a == pushed(["-r", "chrB:20001-60000", "-r", "chrA:50001-100000"])            # contig order of the profile, not of the command line
+    assert a == pushed(["-R", str(rois)])
+    assert a == pushed(["-r", "chrA:50001-80000", "-r", "chrA:70001-100000", "-R", str(rois)])   # overlapping regions are merged
+    assert len(a) == 6                                                                   # 2 regions x 3 read groups
+    whole = pushed([])
+    assert whole == pushed(["-r", "chrA", "-r", "chrB", "-r", "chrC"]) == pushed(["-r", "chrA:1", "-r", "chrB"])
+    assert pushed(["-r", "chrC"]) == []                                                  # a contig without read pairs
+    r = subprocess.run([cli, "profiles.txt", "-g", "-1", "-o", str(tmp_path / "dry.vcf"), "-r", "chrA:12x-40"], cwd=case, capture_output=True, text=True)
+    assert r.returncode != 0 and "parsing genomic region" in r.stderr
