@@ -105,6 +105,8 @@ def load_library(path: str = LIB_PATH):
     lib.pd_shard_attach_group.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(PdShardInfo)]
     lib.pd_shard_group_scan.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(PdResult)]
     lib.pd_set_unify.argtypes = [C.c_void_p, C.POINTER(PdUnifyParams)]
+    lib.pd_set_staging.argtypes = [C.c_void_p, C.c_int]
+    lib.pd_device_warmup.argtypes = [C.c_int]
     _lib = lib
     return lib
 
@@ -284,6 +286,10 @@ class Scanner:
             return
         p = PdUnifyParams(float(mean_stddev), float(min_relative_window_cover), int(bool(output_failed)), 0)
         self._check(self.lib.pd_set_unify(self.ctx, C.byref(p)))
+
+    def set_staging(self, pinned: bool):
+        """pd_set_staging: page-locked (default) or pageable staging buffers for push()."""
+        self._check(self.lib.pd_set_staging(self.ctx, int(bool(pinned))))
 
     def reserve_windows(self, n_windows: int):
         self._check(self.lib.pd_contig_reserve_windows(self.ctx, int(n_windows)))

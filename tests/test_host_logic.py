@@ -152,7 +152,7 @@ def test_unify_staging_and_warmup_argument_checks():
     sc.set_unify(50.0, 0.5, False)
     sc.set_unify(None)                                                         # back to window calls
     assert lib.pd_set_staging(sc.ctx, 0) == 0 and lib.pd_set_staging(sc.ctx, 1) == 0
-    lib.pd_device_warmup.argtypes = [C.c_int]
+    sc.set_staging(False)
     assert lib.pd_device_warmup(99) == -2                                      # PD_ERR_CUDA: no such device
     bad = api.PdUnifyParams(float("nan"), 0.5, 0, 0)
     assert lib.pd_set_unify(sc.ctx, C.byref(bad)) == -1
