@@ -23,6 +23,16 @@
 
 #include "pd_em_common.cuh"
 
+#ifdef PD_EM_STATS
+__device__ unsigned long long g_em_stats[32];
+#define ST_ADD(i, v) atomicAdd(&g_em_stats[i], (unsigned long long)(v))
+#define ST_T0 const long long st_t0_ = clock64()
+#define ST_CLK(i, t0) do { if (threadIdx.x == 0) ST_ADD(i, clock64() - (t0)); } while (0)
+#else
+#define ST_ADD(i, v) do {} while (0)
+#define ST_CLK(i, t0) do {} while (0)
+#endif
+
 namespace {
 
 // data likelihoods of every sample for (L, shifts) -> dlx (log domain) / dle (exp domain);
@@ -627,6 +637,11 @@ __device__ __forceinline__ void em_one_body(const PdDev & a, const EmArgs & e, E
     const int L0 = pr.L0;
     const uint32_t w = e.job_window[pr.job];
     int par = 0;
+#ifdef PD_EM_STATS
+    const long long st_begin = clock64();
+    long long st_t = st_begin;
+    if (tid == 0) ST_ADD(0, 1);
+#endif
     if (tid == 0) { sh.nvisited = 0; s_nsupp = 0; }
     // sample order: by largest deviation, descending, so that the carriers of the deletion share the leading warps and
     // the warps of non-carriers can skip the data-likelihood pass once their reference shift has settled (see below)
@@ -640,6 +655,9 @@ __device__ __forceinline__ void em_one_body(const PdDev & a, const EmArgs & e, E
         }
     }
     __syncthreads();
+#ifdef PD_EM_STATS
+    ST_CLK(2, st_t); st_t = clock64();
+#endif
     const bool has = (uint32_t)(tid / LPS) < a.N;
     const uint32_t s = has ? (e.sort_samples ? s_perm[tid / LPS] : (uint32_t)(tid / LPS)) : 0u;    // my sample = my read group
     const int dmx = has ? __ldg(dmx_all + s) : INT_MIN;
@@ -678,6 +696,9 @@ __device__ __forceinline__ void em_one_body(const PdDev & a, const EmArgs & e, E
         freq = t == 0 ? 0.0 : (double)c / (double)t;
         gt = gt_prior(freq, e.somatic);
     }
+#ifdef PD_EM_STATS
+    ST_CLK(3, st_t); st_t = clock64();
+#endif
     if (freq == 0) {
         if (tid == 0) {
             e.valid[blockIdx.x] = 0; if (e.dbg) { e.dbg[4 * blockIdx.x] = 1; e.dbg[4 * blockIdx.x + 1] = len; e.dbg[4 * blockIdx.x + 2] = 0; }
@@ -707,10 +728,22 @@ __device__ __forceinline__ void em_one_body(const PdDev & a, const EmArgs & e, E
         // A sample whose read pairs all lie below the histogram of the deletion hypothesis at both lengths (dmx) and
         // whose reference shift did not change has exactly the likelihoods and moments it already holds: skip the pass.
         const bool same = e.sort_samples && curL != INT_MIN && dlS == curS && dmx < dlL - k.hist_base + 1 && dmx < curL - k.hist_base + 1;
+#ifdef PD_EM_STATS
+        const long long st_p = clock64();
+        {
+            const uint32_t bm = __ballot_sync(PD_FULL, !same && nl > 0);
+            int mx = (!same) ? nl : 0, sm = mx;
+            for (int o = 16; o > 0; o >>= 1) { mx = max(mx, __shfl_xor_sync(PD_FULL, mx, o)); sm += __shfl_xor_sync(PD_FULL, sm, o); }
+            if ((tid & 31) == 0) { ST_ADD(10, bm != 0); ST_ADD(11, mx); ST_ADD(12, sm); ST_ADD(14 + mode, bm != 0); ST_ADD(17 + mode, sm); }
+        }
+#endif
         if (!same) {
             dl_one<LPS, SLOTS, BATCH>(k, cache_dev, pd, T, tid, sub, nl, dlS, dlL, gmask, rgw, x0, E0, E1, E2, Sr, Srd);
             curL = dlL; curS = dlS;
         }
+#ifdef PD_EM_STATS
+        if (tid == 0) { ST_ADD(4, clock64() - st_p); ST_ADD(5, 1); }
+#endif
         if (mode == 2) {
             const double plr = lr_now(gt_prior(prevFreq, e.somatic));
             if (plr > lr_conv) { len = prevLen; freq = prevFreq; shift = 0; }
@@ -766,6 +799,10 @@ __device__ __forceinline__ void em_one_body(const PdDev & a, const EmArgs & e, E
         else { const double nlen = wDel / sumDel; len = nlen < 0 ? 0u : (uint32_t)round(nlen); }
         mode = 1; dlL = (int)len; dlS = shift;
     }
+#ifdef PD_EM_STATS
+    ST_CLK(20, st_t); st_t = clock64();
+    if (tid == 0) ST_ADD(9, it);
+#endif
     if (freq < 0.0000000001 || len < e.min_len) {
         if (tid == 0) {
             e.valid[blockIdx.x] = 0; if (e.dbg) { e.dbg[4 * blockIdx.x] = 2; e.dbg[4 * blockIdx.x + 1] = len; e.dbg[4 * blockIdx.x + 2] = it; }
@@ -850,6 +887,10 @@ __device__ __forceinline__ void em_one_body(const PdDev & a, const EmArgs & e, E
         }
     }
     __syncthreads();
+#ifdef PD_EM_STATS
+    ST_CLK(6, st_t); st_t = clock64();
+    if (tid == 0) ST_ADD(13, 1);
+#endif
     block_sum2u(supp, ndata, sh.redu);
     if (supp == 0) { reject(3); return; }
     // percentiles of the supporting starts (80th) and ends (20th): getSuppFirstLast :514-529, by value bisection
@@ -896,8 +937,15 @@ __device__ __forceinline__ void em_one_body(const PdDev & a, const EmArgs & e, E
         }
         sF = loF; sL = loL;
     }
+#ifdef PD_EM_STATS
+    ST_CLK(7, st_t); st_t = clock64();
+    if (tid == 0) ST_ADD(21, supp);
+#endif
     if (sF == 0 && sL == 0) { reject(4); return; }
     const double lr = lr_now(gt);
+#ifdef PD_EM_STATS
+    ST_CLK(1, st_begin);
+#endif
     if (tid == 0) {
         const bool ok = lr >= e.min_lr;
         e.valid[blockIdx.x] = ok ? 1 : 0;
@@ -1044,6 +1092,16 @@ cudaError_t launch_one_t(const PdDev & a, const EmArgs & e, uint32_t T, cudaStre
 }
 
 }  // namespace
+
+#ifdef PD_EM_STATS
+extern "C" int pd_debug_em_stats(unsigned long long * out)
+{
+    unsigned long long z[32] = {};
+    if (cudaMemcpyFromSymbol(out, g_em_stats, sizeof(z)) != cudaSuccess) return -1;
+    if (cudaMemcpyToSymbol(g_em_stats, z, sizeof(z)) != cudaSuccess) return -1;
+    return 0;
+}
+#endif
 
 // CUDA loads kernels lazily, and loading may wait for running kernels: a sharded rank whose first k_final_xr launch had
 // to load the kernel while its k_em_xr blocks spin on a peer (whose launch sits behind the same lock) would never
