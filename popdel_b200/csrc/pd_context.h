@@ -113,7 +113,7 @@ struct pd_ctx {
     uint32_t * d_min_init = nullptr; // [R] minInitDelLengths (of the whole cohort when sharded by sample)
     PdShard * shard = nullptr;
     // scan scratch (grown on demand)
-    void * d_scratch[40] = {}; size_t cap_scratch[40] = {};
+    void * d_scratch[64] = {}; size_t cap_scratch[64] = {};
     void * d_pack[8] = {}; size_t cap_pack[8] = {};          // device packer scratch (raw arrays, tile firsts, ...)
     // results
     pd_call * res_calls = nullptr; size_t cap_res_calls = 0;   // page-locked, mapped: written by the device (k_emit_rows)
@@ -131,6 +131,8 @@ struct pd_ctx {
     uint32_t * d_gran_off = nullptr, * d_gran_tile = nullptr, * d_long_off = nullptr; size_t cap_gran = 0;
     uint32_t max_rg_words = 0;
     size_t pool_cap = 0;                                       // active read-pair pool capacity (persists across scans)
+    size_t e2_devt_cap = 0;                                    // lane-interleaved read-pair copies of pd_em2.cu (words)
+    int e2_retry = 0;
     float ms_h2d = 0;
     uint64_t h2d_bytes = 0;
 };

@@ -128,6 +128,14 @@ struct EmitArgs {
     pd_call * out_calls; uint32_t * out_ps; uint32_t * out_count;   // mapped page-locked host memory
 };
 int  pd_launch_em(pd_ctx * c, const PdDev & a, const EmArgs & e, cudaStream_t st, uint64_t * launches);
+// second-generation genotyping pipeline (pd_em2.cu): sample-major, likelihood tables in shared memory
+enum { PD_S_E2_ITEM = 40, PD_S_E2_CTL, PD_S_E2_CUR, PD_S_E2_REC, PD_S_E2_RECA, PD_S_E2_STAT, PD_S_E2_INV, PD_S_E2_FIN, PD_S_E2_PST,
+       PD_S_E2_BOFF, PD_S_E2_BNMAX, PD_S_E2_SUPPN, PD_S_E2_SUPPF, PD_S_E2_SUPPL, PD_S_E2_DEVT, PD_S_E2_POST, PD_S_E2_CNT, PD_S_END };
+int  pd_grow_scratch(pd_ctx * c, int slot, size_t bytes, void ** p);      // pd_scan.cu
+bool pd_em2_usable(const pd_ctx * c);
+size_t pd_em2_pair_bytes(uint32_t R, double reads_per_pair);
+int  pd_launch_em2(pd_ctx * c, const PdDev & a, const EmArgs & e, double reads_per_pair, cudaStream_t st, uint64_t * launches);
+int  pd_em2_overflow(pd_ctx * c, bool * ovf, size_t * need_words);
 int  pd_em_preload_xr(pd_ctx * c);
 void pd_launch_emit(const EmitArgs & m, cudaStream_t st, uint64_t * launches);
 

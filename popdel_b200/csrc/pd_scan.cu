@@ -37,6 +37,18 @@ int grow_scratch(pd_ctx * c, int slot, T *& p, size_t need)
     return 0;
 }
 
+}  // namespace
+
+int pd_grow_scratch(pd_ctx * c, int slot, size_t bytes, void ** p)
+{
+    uint8_t * q = nullptr;
+    if (grow_scratch(c, slot, q, bytes)) return c->status;
+    *p = q;
+    return 0;
+}
+
+namespace {
+
 // word -> tile index and wide-list ranges of the current upload (built once per upload)
 int build_index(pd_ctx * c, const PdDev & a)
 {
@@ -198,8 +210,11 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
     }
     uint32_t npad = 1; while (npad < Ng) npad <<= 1;
     if ((size_t)npad * 4 > 200 * 1024) return pd_fail(c, PD_ERR_CAPACITY, "more than 51200 samples per context: candidate sort does not fit shared memory (shard by sample)");
-    const size_t pair_bytes = 48ull * Nb + 4ull * Rb + 2 * 52ull * Nb + 128;
-    const uint32_t CH = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(2000000000ull / pair_bytes, 64), getenv("PD_EM_CHUNK") ? atoi(getenv("PD_EM_CHUNK")) : 16384);
+    const bool em2 = !sh && pd_em2_usable(c);                          // sample-major pipeline (pd_em2.cu)
+    // (reads per pair are not known before the gather: budget 40 active read pairs per read group)
+    const size_t pair_bytes = 48ull * Nb + 4ull * Rb + 2 * 52ull * Nb + 128 + (em2 ? pd_em2_pair_bytes(Rb, 40.0 * Rb) : 0);
+    const uint32_t CH = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((em2 ? 6000000000ull : 2000000000ull) / pair_bytes, 64),
+                                                     getenv("PD_EM_CHUNK") ? atoi(getenv("PD_EM_CHUNK")) : 16384);
     // (measured on B200, 100 samples x chr21: tapering costs more in small EM launches than it saves in the tail -> off by default)
     const uint32_t taper_min = std::min<uint32_t>(CH, getenv("PD_EM_TAPER") ? std::max(1, atoi(getenv("PD_EM_TAPER"))) : CH);
     XrArgs xr;
@@ -222,6 +237,12 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
     uint32_t * d_emit_state;
     if (grow_scratch(c, S_CHUNK_BASE, d_emit_state, (size_t)4)) return c->status;
     PD_CUDA(c, cudaMemsetAsync(d_emit_state, 0, 16, st));
+    if (em2) {
+        uint32_t * e2cnt;
+        if (grow_scratch(c, PD_S_E2_CNT, e2cnt, (size_t)8)) return c->status;
+        PD_CUDA(c, cudaMemsetAsync(e2cnt, 0, 32, st));
+    }
+    double pool_words_last = 0;                                       // read pairs in the pool of the current sub-batch
 
     for (uint32_t tj0 = 0; tj0 < n_tj;) {
         // batch = tile jobs [tj0, tj1) with at most JB window jobs
@@ -300,7 +321,7 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
             PD_CUDA(c, cudaMemcpyAsync(h_cnt, d_counters, CNT_N * 4, cudaMemcpyDeviceToHost, st));
             PD_CUDA(c, cudaStreamSynchronize(st));
             const bool pool_ok = h_cnt[CNT_POOL] <= c->pool_cap, pairs_ok = h_cnt[CNT_PAIRS] <= pair_cap;
-            if (pool_ok && pairs_ok) { n_pairs = h_cnt[CNT_PAIRS]; n_cj = h_cnt[CNT_CJOBS]; break; }
+            if (pool_ok && pairs_ok) { n_pairs = h_cnt[CNT_PAIRS]; n_cj = h_cnt[CNT_CJOBS]; pool_words_last = h_cnt[CNT_POOL]; break; }
             if (attempt == 3) return pd_fail(c, PD_ERR_CAPACITY, "active read-pair pool / candidate list overflow");
             if (!pool_ok) c->pool_cap = (size_t)h_cnt[CNT_POOL] + (size_t)h_cnt[CNT_POOL] / 8 + 1024;      // exact size known now: run again
             if (pairs_ok) cand_done = true;
@@ -336,7 +357,7 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
                         if (run_gather(cj_lo)) return c->status;
                         PD_CUDA(c, cudaMemcpyAsync(h_cnt, d_counters, CNT_N * 4, cudaMemcpyDeviceToHost, st));
                         PD_CUDA(c, cudaStreamSynchronize(st));
-                        if (h_cnt[CNT_POOL] <= c->pool_cap) break;
+                        if (h_cnt[CNT_POOL] <= c->pool_cap) { pool_words_last = h_cnt[CNT_POOL]; break; }
                         if (attempt == 2) return pd_fail(c, PD_ERR_CAPACITY, "active read-pair pool overflow");
                         c->pool_cap = (size_t)h_cnt[CNT_POOL] + (size_t)h_cnt[CNT_POOL] / 8 + 1024;
                     }
@@ -395,7 +416,11 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
                 // which only waits for ev[6], must never be the one that is running while the EM kernel is being loaded)
                 const bool time_em = chunk_no == 0;
                 if (time_em) PD_CUDA(c, cudaEventRecord(c->ev[12], st));
-                if (pd_launch_em(c, a, e, st, nl)) return c->status;
+                if (em2) {
+                    const uint32_t rows_here = std::max<uint32_t>(std::min<uint32_t>(n_cj - std::min(n_cj, cj_lo), rows_cap), 1);
+                    if (pd_launch_em2(c, a, e, pool_words_last / rows_here, st, nl)) return c->status;
+                    PD_CUDA(c, cudaEventRecord(c->ev[6 + par], st));            // the emitter starts when the chunk is complete
+                } else if (pd_launch_em(c, a, e, st, nl)) return c->status;
                 if (time_em) { PD_CUDA(c, cudaEventRecord(c->ev[13], st)); out->n_em_pairs_timed = np; }
                 PD_CUDA(c, cudaStreamWaitEvent(st2, c->ev[6 + par], 0));
                 pd_launch_emit(m, st2, nl);
@@ -419,6 +444,18 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
     PD_CUDA(c, cudaStreamSynchronize(st));
     PD_CUDA(c, cudaStreamSynchronize(st2));
     PD_CUDA(c, cudaMemcpy(h_cnt, d_counters, CNT_N * 4, cudaMemcpyDeviceToHost));
+    if (em2) {
+        bool ovf = false; size_t need = 0;
+        if (pd_em2_overflow(c, &ovf, &need)) return c->status;
+        if (ovf) {                                                    // the interleaved read-pair copies did not fit: once more with room
+            if (c->e2_retry >= 4) return pd_fail(c, PD_ERR_CAPACITY, "EM read-pair copies overflow");
+            ++c->e2_retry;
+            c->e2_devt_cap = std::max<size_t>(c->e2_devt_cap * 2, need + need / 4);
+            const int rc = pd_run_scan(c, first_window, n_windows, out);
+            --c->e2_retry;
+            return rc;
+        }
+    }
     if (h_cnt[CNT_ERR]) return pd_fail(c, PD_ERR_CUDA, "the result emitter gave up waiting for the EM kernels");
     if (sh) {
         uint32_t xerr = 0;
