@@ -187,17 +187,6 @@ int pd_shard_group_scan(pd_ctx ** ctxs, uint32_t n, uint64_t first_window, uint6
 /* Number of grid windows the reference would scan for the pushed contig (last scanned window index + 1). */
 int pd_contig_window_count(pd_ctx * ctx, uint64_t * n_windows);
 
-/* Synthetic read pairs of ONE read group, generated on the host with a counter-based RNG: per 30-bp
- * bucket and haplotype Poisson(pairs_per_bp*30/2) read pairs, insert size round(N(mu, sigma^2)) clipped to
- * (2*read_length, 20000); planted deletions are applied per haplotype (genotype 0/1/2): pairs whose forward read lies
- * in the deleted segment do not exist, pairs spanning the breakpoint get isize += length. Output sorted by
- * (pos, isize) like a profile. Returns the number of read pairs written (<= capacity) or a negative pd_status.
- * Thread-safe (no context); used by bench.py and the tests to build cohorts of BASELINE.json's sizes quickly. */
-int64_t pd_synth_read_group(uint64_t seed, uint32_t rg_index, double mu, double sigma, uint32_t read_length,
-                            double pairs_per_bp, uint32_t first_pos, uint32_t end_pos,
-                            uint32_t n_dels, const uint32_t * del_start, const uint32_t * del_len,
-                            const uint8_t * del_genotype, uint32_t * pos, int32_t * isize, uint64_t capacity);
-
 /* Host-side validation hook for the packed layout (NOT used by the scan): per-window active read-pair count,
  * sum of deviations and sum of positions of read group `rg`, computed from the packed words with the same
  * closed-form activity rule the kernels use. out = n_windows x 3 int64. Needs no GPU. */

@@ -57,7 +57,7 @@ CALL_DTYPE = np.dtype([("initial_length", "<u4"), ("iterations", "<u4"), ("delet
                        ("end_position", "<u4"), ("segment", "<u4")])
 
 EXPORTS = ["pd_process_histogram", "pd_create", "pd_create_error", "pd_destroy", "pd_last_error", "pd_contig_begin",
-           "pd_contig_push", "pd_contig_push_pinned", "pd_contig_upload", "pd_contig_scan", "pd_contig_window_count", "pd_synth_read_group",
+           "pd_contig_push", "pd_contig_push_pinned", "pd_contig_upload", "pd_contig_scan", "pd_contig_window_count",
            "pd_debug_host_window_sums", "pd_contig_reserve_windows", "pd_shard_unique_id", "pd_shard_attach_nccl",
            "pd_shard_attach_group", "pd_shard_group_scan", "pd_set_unify", "pd_device_warmup", "pd_set_staging"]
 
@@ -93,11 +93,6 @@ def load_library(path: str = LIB_PATH):
     lib.pd_contig_upload.argtypes = [C.c_void_p]
     lib.pd_contig_scan.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(PdResult)]
     lib.pd_contig_window_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
-    lib.pd_synth_read_group.restype = C.c_int64
-    lib.pd_synth_read_group.argtypes = [C.c_uint64, C.c_uint32, C.c_double, C.c_double, C.c_uint32, C.c_double,
-                                        C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32),
-                                        C.POINTER(C.c_uint32), C.POINTER(C.c_uint8), C.POINTER(C.c_uint32),
-                                        C.POINTER(C.c_int32), C.c_uint64]
     lib.pd_debug_host_window_sums.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(C.c_int64)]
     lib.pd_contig_reserve_windows.argtypes = [C.c_void_p, C.c_uint64]
     lib.pd_shard_unique_id.argtypes = [C.POINTER(C.c_uint8)]
@@ -109,6 +104,24 @@ def load_library(path: str = LIB_PATH):
     lib.pd_device_warmup.argtypes = [C.c_int]
     _lib = lib
     return lib
+
+
+_synth = None
+
+
+def load_synth_library():
+    global _synth
+    if _synth is None:
+        path = os.path.join(_HERE, "libpdsynth.so")
+        if not os.path.exists(path):
+            raise ScanError(f"{path} is missing: build it with `make -C popdel_b200/csrc`")
+        _synth = C.CDLL(path)
+        _synth.pd_synth_read_group.restype = C.c_int64
+        _synth.pd_synth_read_group.argtypes = [C.c_uint64, C.c_uint32, C.c_double, C.c_double, C.c_uint32, C.c_double,
+                                               C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32),
+                                               C.POINTER(C.c_uint32), C.POINTER(C.c_uint8), C.POINTER(C.c_uint32),
+                                               C.POINTER(C.c_int32), C.c_uint64]
+    return _synth
 
 
 def process_histogram(counts, offset: int, median: int, read_length: int, smoothing: bool = True,
@@ -325,8 +338,9 @@ class Scanner:
 
 def synth_read_group(seed: int, rg_index: int, mu: float, sigma: float, read_length: int, pairs_per_bp: float,
                      first_pos: int, end_pos: int, del_start=(), del_len=(), del_genotype=()):
-    """pd_synth_read_group: returns (pos uint32, isize int32), sorted by (pos, isize). Releases the GIL."""
-    lib = load_library()
+    """pd_synth_read_group (libpdsynth.so, include/pdsynth.h: test / benchmark infrastructure, not the scan library):
+    returns (pos uint32, isize int32), sorted by (pos, isize). Releases the GIL."""
+    lib = load_synth_library()
     ds = np.ascontiguousarray(del_start, dtype=np.uint32)
     dl = np.ascontiguousarray(del_len, dtype=np.uint32)
     dg = np.ascontiguousarray(del_genotype, dtype=np.uint8)

@@ -133,6 +133,7 @@ struct pd_ctx {
     size_t pool_cap = 0;                                       // active read-pair pool capacity (persists across scans)
     size_t e2_devt_cap = 0;                                    // lane-interleaved read-pair copies of pd_em2.cu (words)
     int e2_retry = 0;
+    bool e2_attr_set = false;
     float ms_h2d = 0;
     uint64_t h2d_bytes = 0;
 };

@@ -130,7 +130,7 @@ struct EmitArgs {
 int  pd_launch_em(pd_ctx * c, const PdDev & a, const EmArgs & e, cudaStream_t st, uint64_t * launches);
 // second-generation genotyping pipeline (pd_em2.cu): sample-major, likelihood tables in shared memory
 enum { PD_S_E2_ITEM = 40, PD_S_E2_CTL, PD_S_E2_CUR, PD_S_E2_REC, PD_S_E2_RECA, PD_S_E2_STAT, PD_S_E2_INV, PD_S_E2_FIN, PD_S_E2_PST,
-       PD_S_E2_BOFF, PD_S_E2_BNMAX, PD_S_E2_SUPPN, PD_S_E2_SUPPF, PD_S_E2_SUPPL, PD_S_E2_DEVT, PD_S_E2_POST, PD_S_E2_CNT, PD_S_END };
+       PD_S_E2_BOFF, PD_S_E2_BNMAX, PD_S_E2_SUPPN, PD_S_E2_SUPPF, PD_S_E2_SUPPL, PD_S_E2_DEVT, PD_S_E2_POST, PD_S_E2_CNT, PD_S_E2_FLAGS, PD_S_E2_ACT, PD_S_END };
 int  pd_grow_scratch(pd_ctx * c, int slot, size_t bytes, void ** p);      // pd_scan.cu
 bool pd_em2_usable(const pd_ctx * c);
 size_t pd_em2_pair_bytes(uint32_t R, double reads_per_pair);

@@ -1,10 +1,12 @@
-// pd_synth.cu -- host generator of synthetic read pairs, counter-based so that any read group of any
-// cohort size can be generated independently and in parallel. Not part of the scan path.
+// pd_synth.cpp -- host generator of synthetic read pairs, counter-based so that any read group of any
+// cohort size can be generated independently and in parallel. Not part of the scan library (libpdsynth.so).
 #include <algorithm>
 #include <cmath>
 #include <vector>
 
-#include "pd_context.h"
+#include "../../include/pdsynth.h"
+
+#define PD_WIN 30u
 
 namespace {
 
@@ -29,7 +31,7 @@ extern "C" int64_t pd_synth_read_group(uint64_t seed, uint32_t rg_index, double 
                                        const uint8_t * del_genotype, uint32_t * pos, int32_t * isize, uint64_t capacity)
 {
     if (!pos || !isize || end_pos <= first_pos || sigma <= 0 || (n_dels && (!del_start || !del_len || !del_genotype)))
-        return PD_ERR_ARG;
+        return -1;
     const double lambda = pairs_per_bp * PD_WIN / 2.0;          // per bucket and haplotype
     // Poisson inverse-CDF table
     std::vector<double> cdf;
@@ -70,7 +72,7 @@ extern "C" int64_t pd_synth_read_group(uint64_t seed, uint32_t rg_index, double 
             }
         }
         std::sort(bucket.begin(), bucket.end(), [](const P & x, const P & y) { return x.pos != y.pos ? x.pos < y.pos : x.isz < y.isz; });
-        if (n + bucket.size() > capacity) return PD_ERR_CAPACITY;
+        if (n + bucket.size() > capacity) return -4;
         for (const P & q : bucket) { pos[n] = q.pos; isize[n] = q.isz; ++n; }
     }
     return (int64_t)n;

@@ -80,9 +80,14 @@ def test_device_packer_equals_host_packer(kind):
     assert_calls_equal(b["calls"], b["per_sample"], a["calls"], a["per_sample"], rtol=0)
 
 
-@pytest.mark.parametrize("n_samples,contig_len", [(150, 90_000), (300, 70_000)])
-def test_many_samples(n_samples, contig_len, oracle_lib):
-    """More samples than one EM block handles with several lanes per sample (exercises the 2- and 1-lane variants)."""
+@pytest.mark.parametrize("n_samples,contig_len,env", [(150, 90_000, {}), (300, 70_000, {}), (150, 90_000, {"PD_EM_V2": "1"}),
+                                                      (300, 70_000, {"PD_EM_V1": "1"}), (600, 50_000, {}), (1100, 45_000, {})])
+def test_many_samples(n_samples, contig_len, env, oracle_lib, monkeypatch):
+    """Larger cohorts: the fused pair-major kernel (<= 256 samples), the general pair-major kernels (PD_EM_V1) and the
+    sample-major pipeline pd_em2.cu with one block per pair of 256 / 512 / 1024 threads and, beyond 1024 samples,
+    several samples per thread."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     dels = [simulate.Deletion(30_000, 1200, np.random.default_rng(5).binomial(2, 0.3, size=n_samples))]
     samples, _ = simulate.simulate_cohort(seed=36, n_samples=n_samples, contig_len=contig_len, n_dels=0, dels=dels)
     stats = compare_scan_with_oracle(samples, oracle_lib)
@@ -90,7 +95,7 @@ def test_many_samples(n_samples, contig_len, oracle_lib):
 
 
 @pytest.mark.parametrize("env", [{"PD_FORCE_SLOW": "7"}, {"PD_JOB_BATCH": "64", "PD_CJOB_ROWS": "7"}, {"PD_CJOB_ROWS": "1", "PD_EM_CHUNK": "5"},
-                                 {"PD_EM_GENERAL": "1"}])
+                                 {"PD_EM_GENERAL": "1"}, {"PD_EM_V2": "1"}, {"PD_EM_V1": "1"}])
 @pytest.mark.parametrize("kind", ["basic", "mixedrg", "highcov"])
 def test_scan_generic_paths_and_batching(kind, env, oracle_lib, monkeypatch):
     """The generic (no shared memory) Q3 / pool paths, small job batches, candidate-job sub-batches and EM chunks, and
