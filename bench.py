@@ -7,10 +7,13 @@
 Workload (BASELINE.json configs[1]): 100 synthetic profiles, chr21 (46,709,983 bp -> 1.56e6 windows of 30 bp), one
 read group each (30x, 2x150 bp, insert ~ N(500, 50^2)), planted deletions; per GPU one such window range (weak
 scaling over contiguous window ranges, no data-path collective). A step = one pass of the scan over the range.
-  value : evaluations/s with the packed read pairs already resident in HBM (all kernels + result copy-back)
-  e2e   : evaluations/s through the C ABI from host arrays: push (pack into pinned memory) + H2D + scan + D2H
-  roofline : k_stream (the screen's streaming kernel), algorithmic bytes = 4 B per resident read pair,
-             CUDA-event duration on the library's stream
+  value : evaluations/s with the packed read pairs already resident in HBM: all kernels of the scan incl. the
+          segment-level merge (unifyCalls on the device, the product's default: `popdel call` writes merged variants)
+          + result copy-back; `window_calls` = the same with every window call and its per-sample row copied back
+  e2e   : evaluations/s through the C ABI from host arrays: push + H2D + device packing + scan + D2H
+  roofline : the WHOLE scan: SURVEY.md 8d's 20 B per evaluation x evaluations per step / device time of a step
+             (CUDA events on the library's stream); `k_stream` = the HBM-bound screen kernel on its own
+  parity_check : the calls of the first --cpu-slice bp compared with the CPU oracle (integers exact, LR / AF 1e-6)
   cpu_baseline : the CPU oracle port (1 core) on a bounded slice of the same cohort
 The reference arm times the reference's own `popdel call` (oracle/_ref/popdel_ref, built from /root/reference by
 oracle/Makefile) on profile files of a bounded slice of the same workload, one process per host core over contiguous
@@ -96,16 +99,87 @@ def make_cohort(seed, n_samples, length, per_mbp, threads, mixed=False, sample_r
     return out, (ds, dl, gt)
 
 
+def workload_config(N, L, mixed, dels_per_mbp, world):
+    """`config` of the JSON line: the same for both arms (the reference arm times a bounded sample of this workload and says
+    so in cpu_baseline.sample)."""
+    return {"workload": f"{N} synthetic profiles x chr21-sized window range ({L} bp, {L // 30} windows of 30 bp) per GPU, "
+                        f"{'1-3 read groups per sample with mixed insert-size histograms' if mixed else 'single read group each'}, "
+                        f"30x, planted deletions {dels_per_mbp}/Mbp; inputs larger than the 126 MB L2",
+            "samples": N,
+            "parallelism": f"window-range x{world} (one range per GPU, same synthetic content in every range, no data-path collective)"}
+
+
+def write_profiles(cohort, N, tmp, cores):
+    from popdel_b200 import profile_format as pf
+    contigs = [("chr21", CHR21_LEN)]
+
+    def write(s):
+        p = os.path.join(tmp, f"s{s:05d}.profile")
+        pf.write_profile_single_rg(p, cohort[s][3], contigs, 0, cohort[s][0], cohort[s][1], compressed=True)
+        return p
+
+    with ThreadPoolExecutor(cores) as ex:
+        paths = list(ex.map(write, range(N)))
+    lst = os.path.join(tmp, "profiles.txt")
+    open(lst, "w").write("\n".join(paths) + "\n")
+    return paths, lst
+
+
+def run_reference_regions(binary, lst, tmp, slice_bp, cores):
+    """The unmodified reference binary, one process per core over contiguous -r regions; returns the wall time."""
+    regions = np.linspace(0, slice_bp, cores + 1).astype(int)
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen([binary, "call", lst, "-r", f"chr21:{regions[i] + 1}-{regions[i + 1]}", "-o",
+                               os.path.join(tmp, f"out{i}.vcf")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+             for i in range(cores)]
+    rc = [p.wait() for p in procs]
+    assert all(r == 0 for r in rc), rc
+    return time.perf_counter() - t0
+
+
+def e2e_files(args):
+    """Same files in, VCF out: the drop-in shell popdel_b200_call against the unmodified reference binary on the SAME gzip
+    profiles of a bounded slice of the workload (what scripts/cli_bench.py does)."""
+    binary = os.path.join(ROOT, "oracle", "_ref", "popdel_ref")
+    ours = os.path.join(ROOT, "popdel_b200", "popdel_b200_call")
+    if not (os.path.exists(binary) and os.path.exists(ours)):
+        return {"unavailable": "oracle/_ref/popdel_ref or popdel_b200/popdel_b200_call not built"}
+    cores = os.cpu_count() or 1
+    N = args.samples
+    slice_bp = int(min(args.ref_slice, args.length))
+    cohort, _ = make_cohort(args.seed, N, slice_bp, args.dels_per_mbp, cores)
+    tmp = tempfile.mkdtemp(prefix="popdel_e2e_files_")
+    try:
+        paths, lst = write_profiles(cohort, N, tmp, cores)
+        walls = []
+        for _ in range(2):                       # cold, warm
+            t0 = time.perf_counter()
+            r = subprocess.run([ours, lst, "-o", os.path.join(tmp, "ours.vcf")], capture_output=True, text=True)
+            walls.append(time.perf_counter() - t0)
+            assert r.returncode == 0, r.stderr
+        t_ref = run_reference_regions(binary, lst, tmp, slice_bp, cores)
+        evals = N * (slice_bp // 30)
+        return {"slice_bp": slice_bp, "profile_bytes": int(sum(os.path.getsize(p) for p in paths)), "host_cores": cores,
+                "ours_s": walls[-1], "ours_cold_s": walls[0], "reference_s": t_ref, "ours_evals_per_s": evals / walls[-1],
+                "reference_evals_per_s": evals / t_ref, "speedup": t_ref / walls[-1],
+                "note": "gzip profile files -> VCF: popdel_b200_call (1 GPU + host cores for the decode) vs the unmodified reference, "
+                        "one process per host core over -r regions"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 class ClockSampler:
     def __init__(self, dev):
         self.dev, self.proc, self.lines = dev, None, []
 
     def start(self):
+        if self.dev is None:                     # only rank 0 polls the driver (every rank doing so perturbs the timed steps)
+            return
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
         except OSError:
             self.proc = None
@@ -188,12 +262,16 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- resident-input throughput
+    # ---- resident-input throughput. Timed default = the product's default: window calls merged per segment on the device
+    # (unifyCalls), only the merged variants cross PCIe. `window_calls` below = every window call + per-sample row copied back.
     push_all()
     sc.upload()
+    mean_sd = float(np.mean([r.as_dict()["stddev"] for r in rgs]))
+    res_w = sc.scan(copy=True)                    # window calls (parity leg, counts)
+    evals = int(res_w["n_windows"]) * N
+    sc.set_unify(mean_sd, 0.5, False)
     res = sc.scan(copy=False)
-    evals = int(res["n_windows"]) * N
-    clocks = ClockSampler(local_rank)             # started before the warm-up steps so that it is sampling when the timed steps run
+    clocks = ClockSampler(local_rank if rank == 0 else None)      # started before the warm-up steps so that it is sampling when the timed steps run
     clocks.start()
     for _ in range(args.warmup):
         res = sc.scan(copy=False)
@@ -202,36 +280,46 @@ def run_ours(args, rank, world, local_rank):
         res = sc.scan(copy=False)
     barrier()
     t0 = time.perf_counter()
-    ms_screen, ms_dev, ms_scr_all, ms_gen, ms_em, launches = [], [], [], [], [], 0
+    ms_screen, ms_dev, ms_scr_all, ms_gen, ms_em, ms_uni, launches = [], [], [], [], [], [], 0
     for _ in range(args.steps):
         res = sc.scan(copy=False)
         ms_screen.append(res["ms_stream"]), ms_dev.append(res["ms_total"]), ms_scr_all.append(res["ms_screen"]), ms_gen.append(res["ms_genotype"])
-        ms_em.append(res["ms_em"])
+        ms_em.append(res["ms_em"]), ms_uni.append(res["ms_unify"])
         launches += int(res["n_kernel_launches"])
     barrier()
     dt = time.perf_counter() - t0
+    n_lines = len(clocks.lines)
+    t_w = time.time()
+    while clocks.proc and len(clocks.lines) == n_lines and time.time() - t_w < 1.0:   # keep the load up until the sampler has seen it
+        sc.scan(copy=False)
     clk = clocks.stop()
     dt, evals_all = sharding.reduce_timing(dt, float(evals), dist, "cuda")      # max over ranks / sum over ranks
     value = evals_all * args.steps / dt
+    n_variants, d2h_unify = int(len(res["calls"])), int(res["d2h_bytes"])
+    sc.set_unify(None)
 
-    # ---- the same resident scan with the segment-level merge (unifyCalls) on the device: only merged variants cross PCIe
-    sc.set_unify(float(np.mean([r.as_dict()["stddev"] for r in rgs])), 0.5, False)
-    ru = sc.scan(copy=False)
+    # ---- the same resident scan returning every window call (+ per-sample rows): 50 MB per chr21 step over PCIe
+    rw = sc.scan(copy=False)
     barrier()
     t0 = time.perf_counter()
-    u_steps = max(1, min(args.steps, 5))
-    for _ in range(u_steps):
-        ru = sc.scan(copy=False)
-        launches_u = int(ru["n_kernel_launches"])
+    w_steps = max(1, min(args.steps, 5))
+    ms_dev_w = []
+    for _ in range(w_steps):
+        rw = sc.scan(copy=False)
+        ms_dev_w.append(rw["ms_total"])
     barrier()
-    dtu = time.perf_counter() - t0
-    sc.set_unify(None)
-    unify = {"ms_per_step": dtu / u_steps * 1e3, "ms_unify_kernels": float(ru["ms_unify"]), "window_calls": int(ru["n_window_calls"]),
-             "variants": int(len(ru["calls"])), "d2h_bytes_per_step": int(ru["d2h_bytes"]), "gpu_launches_per_step": launches_u,
-             "note": "pd_set_unify: window calls and their per-sample rows stay in device memory, every segment is merged there"}
+    dtw = time.perf_counter() - t0
+    dtw, _ = sharding.reduce_timing(dtw, float(evals), dist, "cuda")
+    window_calls = {"value": evals_all * w_steps / dtw, "ms_per_step": dtw / w_steps * 1e3, "ms_device_per_step": float(np.mean(ms_dev_w)),
+                    "window_calls": int(len(rw["calls"])), "d2h_bytes_per_step": int(rw["d2h_bytes"]),
+                    "note": "pd_contig_scan without pd_set_unify: every window call and its per-sample row is copied to the host"}
+    unify = {"ms_unify_kernels": float(np.mean(ms_uni)), "window_calls": int(res["n_window_calls"]), "variants": n_variants,
+             "d2h_bytes_per_step": d2h_unify,
+             "note": "pd_set_unify (timed default): window calls and their per-sample rows stay in device memory, every segment is merged there"}
 
     # ---- end to end through the C ABI from host arrays (pack -> pinned -> H2D -> scan -> D2H)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    sc.set_unify(mean_sd, 0.5, False)                               # the product's default output: merged variants
     push_all_pinned()
     r2 = sc.scan(copy=False)                                        # warm-up (device buffers exist afterwards)
     barrier()
@@ -243,7 +331,7 @@ def run_ours(args, rank, world, local_rank):
     dt2 = time.perf_counter() - t0
     dt2, _ = sharding.reduce_timing(dt2, float(evals), dist, "cuda")
     e2e = evals_all * e2e_steps / dt2
-    assert int(r2["n_calls_check"]) == len(res["calls"]) if "n_calls_check" in r2 else len(r2["calls"]) == len(res["calls"])
+    assert len(r2["calls"]) == n_variants, (len(r2["calls"]), n_variants)
     # PCIe floor of that path: the same page-locked arrays copied to the device with nothing else going on
     dev_bufs = [(torch.empty_like(p[0][0], device="cuda"), torch.empty_like(p[1][0], device="cuda")) for p in pinned]
     for _ in range(2):
@@ -273,26 +361,27 @@ def run_ours(args, rank, world, local_rank):
         return
     peak, peak_src = measured_peak_gbs()
     ms_s = float(np.mean(ms_screen))
-    achieved = res["algorithmic_bytes"] / (ms_s * 1e-3) / 1e9
     ms_d = float(np.mean(ms_dev))
-    traffic = None                      # DRAM bytes of one k_stream launch from the committed ncu --set full capture (default workload only)
-    tpath = os.path.join(ROOT, "profiles", "r01", "traffic.json")
-    if os.path.exists(tpath) and N == 100 and L == CHR21_LEN and args.seed == 1 and not args.mixed and abs(args.dels_per_mbp - 2.0) < 1e-9:
-        traffic = json.load(open(tpath))["k_stream"]["dram_bytes_per_launch"]
+    default_wl = N == 100 and L == CHR21_LEN and args.seed == 1 and not args.mixed and abs(args.dels_per_mbp - 2.0) < 1e-9
+    traffic = None                      # DRAM bytes of one launch / one scan from the committed ncu --set full captures (default workload only)
+    tpath = os.path.join(ROOT, "profiles", "r02", "traffic.json")
+    tj = json.load(open(tpath)) if os.path.exists(tpath) and default_wl else {}
+    fused = R == N and N <= 256
+    algo_bytes = 20 * evals             # rho * 4 B + 8 B = 20 B per evaluation at 30x (the design moves 12: 4 B per read pair)
+    achieved = algo_bytes / (ms_d * 1e-3) / 1e9
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32 (screen) / f64 (likelihoods)", "data": "synthetic",
-        "config": {"workload": f"{N} synthetic profiles x chr21-sized window range ({L} bp, {res['n_windows']} windows of 30 bp) "
-                               f"per GPU, {'1-3 read groups per sample with mixed insert-size histograms' if args.mixed else 'single read group each'}, "
-                               f"30x, planted deletions {args.dels_per_mbp}/Mbp",
-                   "samples": N, "read_groups": R, "windows_per_gpu": int(res["n_windows"]), "read_pairs_per_gpu": int(res["n_reads"]),
-                   "parallelism": f"window-range x{world} (one range per GPU, same synthetic content in every range, no data-path collective)", "l2": "inputs (%.2f GB packed words) larger than the 126 MB L2" % (res["algorithmic_bytes"] / 1e9),
-                   "calls_per_step": int(len(res["calls"])), "flagged_windows": int(res["n_flagged_windows"]),
-                   "candidates": int(res["n_candidates"])},
+        "config": workload_config(N, L, args.mixed, args.dels_per_mbp, world),
+        "workload_detail": {"read_groups": R, "windows_per_gpu": int(res["n_windows"]), "read_pairs_per_gpu": int(res["n_reads"]),
+                            "packed_bytes": int(res["algorithmic_bytes"]),
+                            "output": "merged variants per segment (unifyCalls on the device, pd_set_unify), the product's default",
+                            "calls_per_step": int(res["n_window_calls"]), "variants_per_step": n_variants,
+                            "flagged_windows": int(res["n_flagged_windows"]), "candidates": int(res["n_candidates"])},
         "clocks": clk,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(r2["h2d_bytes"]), "d2h_bytes_per_step": int(r2["d2h_bytes"]),
-                "steps": e2e_steps, "ms_per_step": dt2 / e2e_steps * 1e3, "path": "pd_contig_push_pinned (device-side packing)",
+                "steps": e2e_steps, "ms_per_step": dt2 / e2e_steps * 1e3, "path": "pd_contig_push_pinned (device-side packing) + pd_contig_scan with pd_set_unify",
                 "pcie": {"h2d_gbs_plain_copy": raw_bytes / dt_copy / 1e9, "floor_ms_per_step": dt_copy * 1e3,
                          "frac_of_floor": dt_copy / (dt2 / e2e_steps),
                          "note": "floor = the same page-locked raw arrays copied host->device with nothing else running; "
@@ -300,30 +389,40 @@ def run_ours(args, rank, world, local_rank):
                 "host_packer_value": evals_all / dt3, "host_packer_ms_per_step": dt3 * 1e3, "host_packer_h2d_bytes": int(r3["h2d_bytes"])},
         "gpu_launches": launches,
         "unify": unify,
-        "dominant_kernel_by_time": {
-            "kernel": "k_em_one" if (R == N and N <= 256) else "k_em + k_final", "ms": float(np.mean(ms_em)),
-            "pairs_timed": int(res["n_em_pairs_timed"]), "pairs_per_step": int(res["n_candidates"]),
-            "share_of_step": float(np.mean(ms_em)) / ms_d if int(res["n_em_pairs_timed"]) == int(res["n_candidates"]) else None,
-            "bound": "instruction issue + L2 latency (fp64 likelihood look-ups in L2-resident tables); not HBM, not tensor",
-            "evidence": "profiles/r01/ncu_v15_k_em_one_full.txt (same kernel): issue-active 42.8 %, 15.5 of 32 lanes per instruction, "
-                        "fp64 pipe 14.8 %, L2 hit 90 %, DRAM 1.2 % of peak; DESIGN.md section 9 lists the restructurings measured and rejected"},
-        "roofline": {"bound": "hbm", "kernel": "k_stream", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "bytes_per_eval": res["algorithmic_bytes"] / evals,
-                     "algorithmic_bytes_per_launch": int(res["algorithmic_bytes"]),
-                     "ms_kernel": ms_s, "ms_screen_all_kernels": float(np.mean(ms_scr_all)), "ms_device_per_step": ms_d,
-                     "frac_at_survey_20B_per_eval": evals * 20 / (ms_s * 1e-3) / 1e9 / peak,
-                     "share_of_step": ms_s / ms_d,
-                     "whole_scan": {"achieved": res["algorithmic_bytes"] / (ms_d * 1e-3) / 1e9, "frac": res["algorithmic_bytes"] / (ms_d * 1e-3) / 1e9 / peak,
-                                    "frac_at_survey_20B_per_eval": evals * 20 / (ms_d * 1e-3) / 1e9 / peak,
-                                    "ms_screen": float(np.mean(ms_scr_all)), "ms_genotype": float(np.mean(ms_gen))},
-                     "note": "k_stream is the only HBM-bound kernel and the one that moves the algorithmic bytes (each packed read-pair word "
-                             "once, read-only; a read-only stream can exceed the read+write copy figure used as peak). By TIME the step is "
-                             "dominated by the genotyping stage (k_em_one: fp64 + L2 table look-ups, not HBM-bound; profiles/r01); "
-                             "whole_scan relates the same bytes to the whole device time of a step."},
+        "window_calls": window_calls,
+        "roofline": {"bound": "hbm", "kernel": "scan (all kernels of a step)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": tj.get("scan", {}).get("dram_bytes_per_step"),
+                     "peak_source": peak_src, "bytes_per_eval": 20, "algorithmic_bytes_per_launch": int(algo_bytes),
+                     "ms_device_per_step": ms_d, "ms_screen": float(np.mean(ms_scr_all)), "ms_genotype": float(np.mean(ms_gen)),
+                     "frac_at_own_bytes": res["algorithmic_bytes"] / (ms_d * 1e-3) / 1e9 / peak,
+                     "own_bytes_per_eval": res["algorithmic_bytes"] / evals,
+                     "k_stream": {"achieved": res["algorithmic_bytes"] / (ms_s * 1e-3) / 1e9, "frac": res["algorithmic_bytes"] / (ms_s * 1e-3) / 1e9 / peak,
+                                  "ms_kernel": ms_s, "share_of_step": ms_s / ms_d, "algorithmic_bytes_per_launch": int(res["algorithmic_bytes"]),
+                                  "traffic": tj.get("k_stream", {}).get("dram_bytes_per_launch"),
+                                  "note": "the only HBM-bound kernel: every packed read-pair word (4 B) once, read-only"},
+                     "dominant_kernel_by_time": {
+                         "kernel": "k_em_one" if fused else "k_e2_* (pd_em2.cu)", "ms": float(np.mean(ms_em)),
+                         "pairs_timed": int(res["n_em_pairs_timed"]), "pairs_per_step": int(res["n_candidates"]),
+                         "share_of_step": float(np.mean(ms_em)) / ms_d if int(res["n_em_pairs_timed"]) == int(res["n_candidates"]) else None,
+                         "bound": "L1TEX / LSU wavefronts of the likelihood-table gathers + fp64; not HBM, not tensor (profiles/r02)"},
+                     "note": "achieved = SURVEY.md 8d's algorithmic bytes (20 B per sample x window evaluation) / device time of one step "
+                             "(CUDA events on the library's stream around ALL kernels of the scan incl. the device-side merge)"},
         "setup_s": {"generate": t_gen},
     }
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(args, cohort, params, rgs)
+        base, ref_calls, ref_ps = cpu_baseline(args, cohort, params, rgs)
+        out["cpu_baseline"] = base
+        # parity leg: the window calls of the GPU scan inside the oracle's slice (minus the longest read-pair span at its end,
+        # where the oracle saw no read pairs beyond the slice) must equal the oracle's
+        lim = int(args.cpu_slice) - 25_000
+        gsel = res_w["calls"]["window_position"] < lim
+        osel = ref_calls["window_position"] < lim
+        from parity import assert_calls_equal
+        assert_calls_equal(res_w["calls"][gsel], res_w["per_sample"][gsel], ref_calls[osel], ref_ps[osel])
+        out["parity_check"] = (f"{int(osel.sum())} window calls == CPU oracle (windows below {lim} bp: integers and per-sample "
+                               f"PL/LAD/DAD/FL bit-exact, LR / AF within 1e-6 relative)")
+    if world == 1 and not args.no_e2e_files:
+        out["e2e_files"] = e2e_files(args)
     emit_json(out)
 
 
@@ -341,11 +440,12 @@ def cpu_baseline(args, cohort, params, rgs):
         n = int(np.searchsorted(c[0], slice_bp))
         pos.append(c[0][:n]), dev.append(c[2][:n]), off.append(off[-1] + n)
     t0 = time.perf_counter()
-    calls, _, nwin = orc.scan_contig(params.as_dict(), [r.as_dict() for r in rgs], np.array(off, np.uint64),
-                                     np.concatenate(pos), np.concatenate(dev), N, max_calls=200000)
+    calls, ps, nwin = orc.scan_contig(params.as_dict(), [r.as_dict() for r in rgs], np.array(off, np.uint64),
+                                      np.concatenate(pos), np.concatenate(dev), N, max_calls=200000)
     dt = time.perf_counter() - t0
-    return {"value": nwin * N / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"first {slice_bp} bp of the same cohort: {nwin} windows x {N} samples in {dt:.1f} s ({len(calls)} window calls)"}
+    return ({"value": nwin * N / dt, "unit": UNIT, "cores": 1, "kind": "port",
+             "sample": f"first {slice_bp} bp of the same cohort: {nwin} windows x {N} samples in {dt:.1f} s ({len(calls)} window calls)"},
+            calls, ps)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -451,42 +551,23 @@ def run_sample_sharded(args, rank, world, local_rank):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    from popdel_b200 import profile_format as pf
     binary = os.path.join(ROOT, "oracle", "_ref", "popdel_ref")
     cores = os.cpu_count() or 1
     N = args.samples
-    slice_bp = int(min(args.ref_slice_per_core * cores, args.length, 24_000_000))
-    cohort, _ = make_cohort(args.seed, N, slice_bp, args.dels_per_mbp, cores)
+    slice_bp = int(min(args.ref_slice, args.length))          # >= 24 Mbp: several segments per process, start-up does not dominate
+    cohort, _ = make_cohort(args.seed, N, slice_bp, args.dels_per_mbp, cores)      # (libpdsynth.so: nothing of the product is mapped here)
     tmp = tempfile.mkdtemp(prefix="popdel_ref_bench_")
     try:
-        contigs = [("chr21", CHR21_LEN)]
-
-        def write(s):
-            p = os.path.join(tmp, f"s{s:05d}.profile")
-            pf.write_profile_single_rg(p, cohort[s][3], contigs, 0, cohort[s][0], cohort[s][1], compressed=True)
-            return p
-
-        with ThreadPoolExecutor(cores) as ex:
-            paths = list(ex.map(write, range(N)))
-        lst = os.path.join(tmp, "profiles.txt")
-        open(lst, "w").write("\n".join(paths) + "\n")
-        kind = "reference"
-        if not os.path.exists(binary):
-            kind = "port"
-        regions = np.linspace(0, slice_bp, cores + 1).astype(int)
+        paths, lst = write_profiles(cohort, N, tmp, cores)
+        kind = "reference" if os.path.exists(binary) else "port"
 
         def step():
-            t0 = time.perf_counter()
             if kind == "reference":
-                procs = [subprocess.Popen([binary, "call", lst, "-r", f"chr21:{regions[i] + 1}-{regions[i + 1]}", "-o",
-                                           os.path.join(tmp, f"out{i}.vcf")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-                         for i in range(cores)]
-                rc = [p.wait() for p in procs]
-                assert all(r == 0 for r in rc), rc
-            else:
-                import oracle_api
-                orc = oracle_api.load(os.path.join(ROOT, "oracle", "liboracle.so"))
-                orc.call_files(paths, os.path.join(tmp, "dump.txt"))
+                return run_reference_regions(binary, lst, tmp, slice_bp, cores)
+            t0 = time.perf_counter()
+            import oracle_api
+            orc = oracle_api.load(os.path.join(ROOT, "oracle", "liboracle.so"))
+            orc.call_files(paths, os.path.join(tmp, "dump.txt"))
             return time.perf_counter() - t0
 
         for _ in range(min(args.warmup, 1)):
@@ -499,10 +580,10 @@ def run_reference(args, rank, world):
         out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "long double (x87)", "data": "synthetic",
-               "config": {"workload": f"{N} synthetic profiles x chr21, bounded sample: first {slice_bp} bp "
-                                      f"({slice_bp // 30} windows), gzip profile files on local disk", "samples": N},
+               "config": workload_config(N, args.length, args.mixed, args.dels_per_mbp, world),
                "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind,
-                                "sample": f"{N} samples x first {slice_bp} bp, {used} processes over contiguous -r regions"},
+                                "sample": f"bounded sample of the workload: {N} samples x first {slice_bp} bp ({slice_bp // 30} windows per step), "
+                                          f"gzip profile files on local disk -> VCF, {used} processes over contiguous -r regions"},
                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit_json(out)
     finally:
@@ -537,7 +618,8 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-slice", type=int, default=1_500_000)
-    ap.add_argument("--ref-slice-per-core", type=int, default=300_000)
+    ap.add_argument("--ref-slice", type=int, default=24_000_000, help="bp of the workload the reference binary is timed on per step")
+    ap.add_argument("--no-e2e-files", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shard-samples", action="store_true", help="sample-sharded cohort over the ranks (config 5 style) instead of window ranges")
     ap.add_argument("--check", action="store_true", help="--shard-samples: compare the merged calls with the CPU oracle (small cohorts)")

@@ -23,7 +23,8 @@ struct PdTab {
     // final pass only
     double l10;     // log10(val)
     double l10p;    // log10(val + min_prob) - log10(2)_d
-    double pad[2];
+    double val2;    // = val: the fused kernel's final pass reads this half row only
+    double fr2;     // = fr
 };
 
 // Device view handed to the kernels by value.

@@ -627,7 +627,7 @@ __device__ __forceinline__ void dl_one(const RgOne & k, const int32_t * cache_d,
 
 template <int LPS, int SLOTS, int BATCH>
 __device__ __forceinline__ void em_one_body(const PdDev & a, const EmArgs & e, EmShared & sh, uint32_t * s_first, uint32_t * s_last,
-                                            uint32_t & s_nsupp, uint16_t * s_perm, int32_t * cache_dev)
+                                            uint32_t & s_nsupp, uint16_t * s_perm, int32_t * cache_dev, double * s_slot)
 {
     const int tid = threadIdx.x, T = blockDim.x, sub = tid % LPS;
     const uint32_t gmask = group_mask<LPS>();
@@ -737,7 +737,17 @@ __device__ __forceinline__ void em_one_body(const PdDev & a, const EmArgs & e, E
             if ((tid & 31) == 0) { ST_ADD(10, bm != 0); ST_ADD(11, mx); ST_ADD(12, sm); ST_ADD(14 + mode, bm != 0); ST_ADD(17 + mode, sm); }
         }
 #endif
-        if (!same) {
+        if (mode == 2) {
+            // Previous estimate with zero shifts (:641-647). A sample without read pairs inside the deletion histogram at the
+            // initial AND the previous length has exactly the likelihoods of the first pass, which are kept in s_slot: swap
+            // them in. Every other sample parks its current likelihoods there and recomputes. Either way s_slot then holds
+            // what the registers must get back if the newest estimate wins, so the final pass never recomputes the ln sums.
+            const bool keep = nl == 0 || (dmx < L0 - k.hist_base + 1 && dmx < dlL - k.hist_base + 1);
+            const double a0 = s_slot[tid], a1 = s_slot[T + tid], a2 = s_slot[2 * T + tid], a3 = s_slot[3 * T + tid];
+            s_slot[tid] = x0; s_slot[T + tid] = E0; s_slot[2 * T + tid] = E1; s_slot[3 * T + tid] = E2;
+            if (keep) { x0 = a0; E0 = a1; E1 = a2; E2 = a3; }
+            else dl_one<LPS, SLOTS, BATCH>(k, cache_dev, pd, T, tid, sub, nl, dlS, dlL, gmask, rgw, x0, E0, E1, E2, Sr, Srd);
+        } else if (!same) {
             dl_one<LPS, SLOTS, BATCH>(k, cache_dev, pd, T, tid, sub, nl, dlS, dlL, gmask, rgw, x0, E0, E1, E2, Sr, Srd);
             curL = dlL; curS = dlS;
         }
@@ -747,9 +757,13 @@ __device__ __forceinline__ void em_one_body(const PdDev & a, const EmArgs & e, E
         if (mode == 2) {
             const double plr = lr_now(gt_prior(prevFreq, e.somatic));
             if (plr > lr_conv) { len = prevLen; freq = prevFreq; shift = 0; }
+            else { x0 = s_slot[tid]; E0 = s_slot[T + tid]; E1 = s_slot[2 * T + tid]; E2 = s_slot[3 * T + tid]; }
             break;
         }
-        if (mode == 0) __syncthreads();                   // sh.rgw / sh.nvisited visible
+        if (mode == 0) {
+            s_slot[tid] = x0; s_slot[T + tid] = E0; s_slot[2 * T + tid] = E1; s_slot[3 * T + tid] = E2;     // own entries only: no barrier
+            __syncthreads();                              // sh.rgw / sh.nvisited visible
+        }
         else {
             double fs = 0, dummy = 0;
             if (has && sub == 0) { const double p0 = E0 * gt.a, p1 = E1 * gt.b, p2 = E2 * gt.c; fs = (p1 + 2 * p2) / (p0 + p1 + p2); }
@@ -817,6 +831,7 @@ __device__ __forceinline__ void em_one_body(const PdDev & a, const EmArgs & e, E
         }
     };
     const int flen = (int)len;
+    __syncthreads();                                      // s_slot (read above) shares its memory with s_first / s_last (written below)
     const int lower_q = __ldg(&a.rgc[has ? s : 0].lower_q), upper_q = __ldg(&a.rgc[has ? s : 0].upper_q);
     const int inner_off = __ldg(&a.rgc[has ? s : 0].inner_off);
     const double l10_min_prob = __ldg(&a.rgc[has ? s : 0].l10_min_prob);
@@ -824,26 +839,28 @@ __device__ __forceinline__ void em_one_body(const PdDev & a, const EmArgs & e, E
     const uint32_t * pp = e.pool_pos + poff;
     unsigned long long supp = 0, ndata = 0;
     {
+        // The ln sums of the final overload (:255-337) equal those of the likelihood pass the registers hold (same read pairs,
+        // length and shift: see the state machine above), so only the log10 sums, LAD / DAD and the positions are taken
+        // here, from the second half of the table rows {log10, log10p, val, fr}.
         uint32_t lad0 = 0, lad1 = 0, lad2 = 0, dad0 = 0, dad1 = 0, dad2 = 0, dad3 = 0, dad4 = 0;
         uint32_t fl_min = 0xFFFFFFFFu, fl_max = 0, ndeg = 0;
-        double l0 = 0, l1 = 0, l2 = 0, t0 = 0, t1 = 0, t2 = 0;
+        double t0 = 0, t1 = 0, t2 = 0;
         for (int j = 0; j < nl; ++j) {
             const int d = j < SLOTS ? cache_dev[j * T + tid] : __ldg(pd + sub + j * LPS);
             if (d > upper_q) { if (d < delLower) ++dad2; else if (d <= delUpper) ++dad3; else ++dad4; }
             else { if (d < delUpper) ++dad0; else ++dad1; }
             const PdTab * tr = k.fl + (tab_in(k, d - shift) ? d - shift + k.hist_base + 1 : 0);
             const PdTab * td = k.fl + (tab_in(k, d - flen) ? d - flen + k.hist_base + 1 : 0);
-            const D4 r1 = ld4(&tr->val), r2 = ld4(&tr->l10);                                              // full row
-            D4 d1 = D4{k.min_prob, k.ln_min_prob, 0, 0}, d2 = D4{l10_min_prob, 0, 0, 0};                 // floor: .c / .b unused
-            if (td != k.fl) { d1 = ld4(&td->val); d2 = ld4(&td->l10); }
-            const double ref = r1.a, del = d1.a;
+            const D4 r2 = ld4(&tr->l10);                                                                  // log10 ref, log10p, ref, fr
+            D4 d2 = D4{l10_min_prob, 0, k.min_prob, 0};                                                  // floor: .b / .d unused
+            if (td != k.fl) d2 = ld4(&td->l10);
+            const double ref = r2.c, del = d2.c;
             if (ref >= 2 * del) ++lad0; else if (del >= 2 * ref) ++lad2; else ++lad1;
-            l0 += r1.b; t0 += r2.a;
-            l2 += d1.b; t2 += d2.a;
-            if (ref == del) { l1 += r1.b; t1 += r2.a; ++ndeg; }                          // residues applied below
-            else if (del == k.min_prob) { l1 += r1.c; t1 += r2.b; }
-            else if (ref == k.min_prob) { l1 += d1.c; t1 += d2.b; }
-            else { l1 += log(ref + del) - LN2_D; t1 += log10(ref + del) - LOG10_2_D; }
+            t0 += r2.a; t2 += d2.a;
+            if (ref == del) { t1 += r2.a; ++ndeg; }                                      // residue applied below
+            else if (del == k.min_prob) t1 += r2.b;
+            else if (ref == k.min_prob) t1 += d2.b;
+            else t1 += log10(ref + del) - LOG10_2_D;
             const uint32_t first = __ldg(pp + sub + j * LPS) + e.anchor;
             const uint32_t last = first + (uint32_t)max(0, d + inner_off);
             fl_min = min(fl_min, first); fl_max = max(fl_max, last);
@@ -857,19 +874,16 @@ __device__ __forceinline__ void em_one_body(const PdDev & a, const EmArgs & e, E
         dad0 = group_sum<LPS>(dad0, gmask); dad1 = group_sum<LPS>(dad1, gmask); dad2 = group_sum<LPS>(dad2, gmask);
         dad3 = group_sum<LPS>(dad3, gmask); dad4 = group_sum<LPS>(dad4, gmask); ndeg = group_sum<LPS>(ndeg, gmask);
         fl_min = group_min<LPS>(fl_min, gmask); fl_max = group_max<LPS>(fl_max, gmask);
-        l0 = group_sum<LPS>(l0, gmask); l1 = group_sum<LPS>(l1, gmask); l2 = group_sum<LPS>(l2, gmask);
         t0 = group_sum<LPS>(t0, gmask); t1 = group_sum<LPS>(t1, gmask); t2 = group_sum<LPS>(t2, gmask);
         if (fl_min == 0xFFFFFFFFu) fl_min = 0;
-        double g0l = t0, g1l = t1, g2l = t2, x1, x2;
-        if (t0 + t1 + t2 == 0.0) { x0 = 0; x1 = LN1E10; x2 = LN1E10; }       // sum(gtLogs) == 0 :307-308
+        double g0l = t0, g1l = t1, g2l = t2;
+        if (t0 + t1 + t2 == 0.0) { x0 = 0; E0 = 1.0; E1 = E2 = exp(LN1E10); }     // sum(gtLogs) == 0 :307-308
         else {
             const double mg = fmax(fmax(t0, t1), t2);
             g0l -= mg; g1l -= mg; g2l -= mg;
             if (ndeg) { g1l += ndeg * LOG10_2_RESIDUE; const double m2 = fmax(fmax(g0l, g1l), g2l); g0l -= m2; g1l -= m2; g2l -= m2; }
             if (g0l == g1l && g0l == g2l) { g0l = 0; g1l = -10; g2l = -10; }
-            finish_triple(l0, l1, l2, ndeg, x0, x1, x2);
         }
-        E0 = exp(x0); E1 = exp(x1); E2 = exp(x2);
         if (has && sub == 0) {
             // calculatePhredGL utils_popdel.h:1511-1528
             const double gTot = log10(exp(g0l) + exp(g1l) + exp(g2l));
@@ -969,11 +983,16 @@ template <int LPS, int SLOTS, int BATCH, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_em_one(PdDev a, EmArgs e)
 {
     __shared__ EmShared sh;
-    __shared__ uint32_t s_first[SUPP_CAP], s_last[SUPP_CAP];
+    __shared__ __align__(16) uint32_t s_sup[2 * SUPP_CAP];
+    uint32_t * s_first = s_sup, * s_last = s_sup + SUPP_CAP;
     __shared__ uint32_t s_nsupp;
     __shared__ uint16_t s_perm[256];
     extern __shared__ int32_t cache_dev[];              // [SLOTS][T] deviations of this block's read pairs
-    em_one_body<LPS, SLOTS, BATCH>(a, e, sh, s_first, s_last, s_nsupp, s_perm, cache_dev);
+    // parked likelihood triples (first pass / state before the convergence check): only live during the EM loop, so they
+    // share the memory of the supporting read-pair lists of the final pass
+    static_assert(4 * MAXT * sizeof(double) <= 2 * SUPP_CAP * sizeof(uint32_t), "s_slot must fit the supporting lists");
+    double * s_slot = reinterpret_cast<double *>(s_sup);
+    em_one_body<LPS, SLOTS, BATCH>(a, e, sh, s_first, s_last, s_nsupp, s_perm, cache_dev, s_slot);
     publish_done(e, blockIdx.x);
 }
 // ------------------------------------------------------------------------------------------------------------------

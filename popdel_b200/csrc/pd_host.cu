@@ -107,7 +107,7 @@ static int upload_static(pd_ctx * c)
         auto fill = [&](PdTab & e, double v) {
             e.val = v; e.ln = std::log(v); e.l10 = std::log10(v);
             e.lnp = std::log(v + mp) - LN2_D; e.l10p = std::log10(v + mp) - L10_2_D;
-            e.fr = mp / (mp + v); e.pad[0] = e.pad[1] = 0;
+            e.fr = mp / (mp + v); e.val2 = v; e.fr2 = e.fr;
         };
         size_t o = c->rgc[g].hist_off;
         fill(tab[o], mp);                                           // floor entry
