@@ -7,9 +7,9 @@
 Workload (BASELINE.json configs[1]): 100 synthetic profiles, chr21 (46,709,983 bp -> 1.56e6 windows of 30 bp), one
 read group each (30x, 2x150 bp, insert ~ N(500, 50^2)), planted deletions; per GPU one such window range (weak
 scaling over contiguous window ranges, no data-path collective). A step = one pass of the scan over the range.
-  value : evaluations/s with the packed read pairs already resident in HBM: all kernels of the scan incl. the
-          segment-level merge (unifyCalls on the device, the product's default: `popdel call` writes merged variants)
-          + result copy-back; `window_calls` = the same with every window call and its per-sample row copied back
+  value : evaluations/s with the packed read pairs already resident in HBM: all kernels of the scan + result copy-back
+          (every window call with its per-sample row, 50 MB per chr21 step); `other_output` = the same with the
+          segment-level merge on the device (pd_set_unify), only merged variants cross PCIe
   e2e   : evaluations/s through the C ABI from host arrays: push + H2D + device packing + scan + D2H
   roofline : the WHOLE scan: SURVEY.md 8d's 20 B per evaluation x evaluations per step / device time of a step
              (CUDA events on the library's stream); `k_stream` = the HBM-bound screen kernel on its own
@@ -257,19 +257,44 @@ def run_ours(args, rank, world, local_rank):
         for g in range(R):
             sc.push_pinned(g, pinned[g][0][1], pinned[g][1][1])
 
+    # the same read pairs in the 5-byte form of pd_contig_push_compact (what a profile decoder emits directly: the file stores
+    # a u8 offset per 256-bp window and an i32 deviation), page-locked
+    def pin_any(a, dt):
+        t = torch.from_numpy(a.view(dt)).pin_memory()
+        return t, t.numpy().view(a.dtype)
+    compact = []
+    for c in cohort:
+        lo, d24, blk = api.compact_encode(c[0], c[2])
+        compact.append((pin_any(lo, np.int16), pin_any(d24, np.uint8), pin_any(blk, np.int32)))
+
+    def push_all_compact():
+        sc.begin_contig(anchor)
+        for g in range(R):
+            sc.push_compact(g, compact[g][0][1], compact[g][1][1], compact[g][2][1])
+
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- resident-input throughput. Timed default = the product's default: window calls merged per segment on the device
-    # (unifyCalls), only the merged variants cross PCIe. `window_calls` below = every window call + per-sample row copied back.
+    # ---- resident-input throughput. --output calls (default): pd_contig_scan's own product, every window call of every
+    # processSegment() with its per-sample row (the reference's String<Call> before unifyCalls) copied back; --output unify:
+    # the segment-level merge on the device (pd_set_unify), only merged variants cross PCIe. The other mode is timed as well
+    # (fewer steps) and reported beside it.
     push_all()
     sc.upload()
     mean_sd = float(np.mean([r.as_dict()["stddev"] for r in rgs]))
     res_w = sc.scan(copy=True)                    # window calls (parity leg, counts)
     evals = int(res_w["n_windows"]) * N
-    sc.set_unify(mean_sd, 0.5, False)
+    main_unify = args.output == "unify"
+
+    def set_mode(unify_on):
+        if unify_on:
+            sc.set_unify(mean_sd, 0.5, False)
+        else:
+            sc.set_unify(None)
+
+    set_mode(main_unify)
     res = sc.scan(copy=False)
     clocks = ClockSampler(local_rank if rank == 0 else None)      # started before the warm-up steps so that it is sampling when the timed steps run
     clocks.start()
@@ -280,11 +305,11 @@ def run_ours(args, rank, world, local_rank):
         res = sc.scan(copy=False)
     barrier()
     t0 = time.perf_counter()
-    ms_screen, ms_dev, ms_scr_all, ms_gen, ms_em, ms_uni, launches = [], [], [], [], [], [], 0
+    ms_screen, ms_dev, ms_scr_all, ms_gen, ms_em, launches = [], [], [], [], [], 0
     for _ in range(args.steps):
         res = sc.scan(copy=False)
         ms_screen.append(res["ms_stream"]), ms_dev.append(res["ms_total"]), ms_scr_all.append(res["ms_screen"]), ms_gen.append(res["ms_genotype"])
-        ms_em.append(res["ms_em"]), ms_uni.append(res["ms_unify"])
+        ms_em.append(res["ms_em"])
         launches += int(res["n_kernel_launches"])
     barrier()
     dt = time.perf_counter() - t0
@@ -295,43 +320,55 @@ def run_ours(args, rank, world, local_rank):
     clk = clocks.stop()
     dt, evals_all = sharding.reduce_timing(dt, float(evals), dist, "cuda")      # max over ranks / sum over ranks
     value = evals_all * args.steps / dt
-    n_variants, d2h_unify = int(len(res["calls"])), int(res["d2h_bytes"])
-    sc.set_unify(None)
+    n_out, d2h_main, n_wcalls = int(len(res["calls"])), int(res["d2h_bytes"]), int(res["n_window_calls"])
 
-    # ---- the same resident scan returning every window call (+ per-sample rows): 50 MB per chr21 step over PCIe
-    rw = sc.scan(copy=False)
+    # ---- the other output mode
+    set_mode(not main_unify)
+    ro = sc.scan(copy=False)
     barrier()
     t0 = time.perf_counter()
-    w_steps = max(1, min(args.steps, 5))
-    ms_dev_w = []
-    for _ in range(w_steps):
-        rw = sc.scan(copy=False)
-        ms_dev_w.append(rw["ms_total"])
+    o_steps = max(1, min(args.steps, 5))
+    ms_dev_o, ms_uni = [], []
+    for _ in range(o_steps):
+        ro = sc.scan(copy=False)
+        ms_dev_o.append(ro["ms_total"]), ms_uni.append(ro["ms_unify"])
     barrier()
-    dtw = time.perf_counter() - t0
-    dtw, _ = sharding.reduce_timing(dtw, float(evals), dist, "cuda")
-    window_calls = {"value": evals_all * w_steps / dtw, "ms_per_step": dtw / w_steps * 1e3, "ms_device_per_step": float(np.mean(ms_dev_w)),
-                    "window_calls": int(len(rw["calls"])), "d2h_bytes_per_step": int(rw["d2h_bytes"]),
-                    "note": "pd_contig_scan without pd_set_unify: every window call and its per-sample row is copied to the host"}
-    unify = {"ms_unify_kernels": float(np.mean(ms_uni)), "window_calls": int(res["n_window_calls"]), "variants": n_variants,
-             "d2h_bytes_per_step": d2h_unify,
-             "note": "pd_set_unify (timed default): window calls and their per-sample rows stay in device memory, every segment is merged there"}
+    dto = time.perf_counter() - t0
+    dto, _ = sharding.reduce_timing(dto, float(evals), dist, "cuda")
+    other = {"output": "calls" if main_unify else "unify", "value": evals_all * o_steps / dto, "ms_per_step": dto / o_steps * 1e3,
+             "ms_device_per_step": float(np.mean(ms_dev_o)), "records": int(len(ro["calls"])), "d2h_bytes_per_step": int(ro["d2h_bytes"])}
+    if not main_unify:
+        other["ms_unify_kernels"] = float(np.mean(ms_uni))
+        other["note"] = "pd_set_unify: window calls and their per-sample rows stay in device memory, every segment is merged there (unifyCalls)"
+    n_variants = int(len(ro["calls"])) if not main_unify else n_out
 
     # ---- end to end through the C ABI from host arrays (pack -> pinned -> H2D -> scan -> D2H)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    sc.set_unify(mean_sd, 0.5, False)                               # the product's default output: merged variants
-    push_all_pinned()
+    set_mode(main_unify)
+    push_all_compact()
     r2 = sc.scan(copy=False)                                        # warm-up (device buffers exist afterwards)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        push_all_pinned()
+        push_all_compact()
         r2 = sc.scan(copy=False)
     barrier()
     dt2 = time.perf_counter() - t0
     dt2, _ = sharding.reduce_timing(dt2, float(evals), dist, "cuda")
     e2e = evals_all * e2e_steps / dt2
-    assert len(r2["calls"]) == n_variants, (len(r2["calls"]), n_variants)
+    assert len(r2["calls"]) == n_out, (len(r2["calls"]), n_out)
+    # the same from raw page-locked pos[] / dev[] arrays (8 bytes per read pair)
+    push_all_pinned()
+    r2r = sc.scan(copy=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        push_all_pinned()
+        r2r = sc.scan(copy=False)
+    barrier()
+    dt2r = time.perf_counter() - t0
+    dt2r, _ = sharding.reduce_timing(dt2r, float(evals), dist, "cuda")
+    assert len(r2r["calls"]) == n_out
     # PCIe floor of that path: the same page-locked arrays copied to the device with nothing else going on
     dev_bufs = [(torch.empty_like(p[0][0], device="cuda"), torch.empty_like(p[1][0], device="cuda")) for p in pinned]
     for _ in range(2):
@@ -342,6 +379,17 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
         dt_copy = time.perf_counter() - t0
     raw_bytes = sum(p[0][0].numel() * 4 + p[1][0].numel() * 4 for p in pinned)
+    del dev_bufs
+    dev_bufs = [tuple(torch.empty_like(q[0], device="cuda") for q in cq) for cq in compact]
+    for _ in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for cq, db in zip(compact, dev_bufs):
+            for q, d_ in zip(cq, db):
+                d_.copy_(q[0], non_blocking=True)
+        torch.cuda.synchronize()
+        dt_copy_c = time.perf_counter() - t0
+    compact_bytes = sum(sum(q[0].numel() * q[0].element_size() for q in cq) for cq in compact)
     del dev_bufs
     # the same through pd_contig_push (sequential host packer, one thread per read group)
     push_all()
@@ -376,20 +424,22 @@ def run_ours(args, rank, world, local_rank):
         "config": workload_config(N, L, args.mixed, args.dels_per_mbp, world),
         "workload_detail": {"read_groups": R, "windows_per_gpu": int(res["n_windows"]), "read_pairs_per_gpu": int(res["n_reads"]),
                             "packed_bytes": int(res["algorithmic_bytes"]),
-                            "output": "merged variants per segment (unifyCalls on the device, pd_set_unify), the product's default",
-                            "calls_per_step": int(res["n_window_calls"]), "variants_per_step": n_variants,
+                            "output": "merged variants per segment (unifyCalls on the device, pd_set_unify)" if main_unify else
+                                      "window calls of every processSegment() + per-sample rows (pd_contig_scan's own product)",
+                            "calls_per_step": n_wcalls, "variants_per_step": n_variants, "d2h_bytes_per_step": d2h_main,
                             "flagged_windows": int(res["n_flagged_windows"]), "candidates": int(res["n_candidates"])},
         "clocks": clk,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(r2["h2d_bytes"]), "d2h_bytes_per_step": int(r2["d2h_bytes"]),
-                "steps": e2e_steps, "ms_per_step": dt2 / e2e_steps * 1e3, "path": "pd_contig_push_pinned (device-side packing) + pd_contig_scan with pd_set_unify",
-                "pcie": {"h2d_gbs_plain_copy": raw_bytes / dt_copy / 1e9, "floor_ms_per_step": dt_copy * 1e3,
-                         "frac_of_floor": dt_copy / (dt2 / e2e_steps),
-                         "note": "floor = the same page-locked raw arrays copied host->device with nothing else running; "
-                                 "the e2e step additionally packs on the device, scans and writes the results back"},
+                "steps": e2e_steps, "ms_per_step": dt2 / e2e_steps * 1e3, "path": "pd_contig_push_compact (5 B per read pair over PCIe, expansion + packing on the device) + pd_contig_scan" + (" with pd_set_unify" if main_unify else ""),
+                "pcie": {"h2d_gbs_plain_copy": compact_bytes / dt_copy_c / 1e9, "floor_ms_per_step": dt_copy_c * 1e3,
+                         "frac_of_floor": dt_copy_c / (dt2 / e2e_steps),
+                         "note": "floor = the same page-locked arrays copied host->device with nothing else running; "
+                                 "the e2e step additionally expands and packs on the device, scans and writes the results back"},
+                "raw_arrays": {"value": evals_all * e2e_steps / dt2r, "ms_per_step": dt2r / e2e_steps * 1e3, "h2d_bytes_per_step": int(r2r["h2d_bytes"]),
+                               "floor_ms_per_step": dt_copy * 1e3, "path": "pd_contig_push_pinned: raw pos[] / dev[] arrays, 8 B per read pair"},
                 "host_packer_value": evals_all / dt3, "host_packer_ms_per_step": dt3 * 1e3, "host_packer_h2d_bytes": int(r3["h2d_bytes"])},
         "gpu_launches": launches,
-        "unify": unify,
-        "window_calls": window_calls,
+        "other_output": other,
         "roofline": {"bound": "hbm", "kernel": "scan (all kernels of a step)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": tj.get("scan", {}).get("dram_bytes_per_step"),
                      "peak_source": peak_src, "bytes_per_eval": 20, "algorithmic_bytes_per_launch": int(algo_bytes),
@@ -620,6 +670,7 @@ def main():
     ap.add_argument("--cpu-slice", type=int, default=1_500_000)
     ap.add_argument("--ref-slice", type=int, default=24_000_000, help="bp of the workload the reference binary is timed on per step")
     ap.add_argument("--no-e2e-files", action="store_true")
+    ap.add_argument("--output", default="calls", choices=["calls", "unify"], help="what the timed scan returns (see run_ours)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shard-samples", action="store_true", help="sample-sharded cohort over the ranks (config 5 style) instead of window ranges")
     ap.add_argument("--check", action="store_true", help="--shard-samples: compare the merged calls with the CPU oracle (small cohorts)")

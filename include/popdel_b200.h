@@ -129,6 +129,16 @@ int pd_set_staging(pd_ctx * ctx, int pinned);
  * pair, the contig is transparently re-packed by the sequential host path. */
 int pd_contig_push_pinned(pd_ctx * ctx, uint32_t rg, uint64_t n, const uint32_t * pos, const int32_t * dev);
 
+/* pd_contig_push_pinned with 5 instead of 8 bytes per read pair over PCIe (the profile file stores 5: a u8 offset inside
+ * its 256-bp window and an i32 deviation, window_podel.h:161-197): positions are split into 65 536-bp blocks,
+ *   blk_first[b]  index of the first read pair with pos >> 16 == b, b = 0 .. n_blocks (blk_first[n_blocks] = n),
+ *   pos_lo[i]     pos & 0xFFFF,
+ *   dev24[3 * i]  the deviation as a little-endian two's-complement 24-bit integer (|dev| < 2^20 in the packed layout).
+ * The arrays are expanded on the device. Same rules as pd_contig_push_pinned (page-locked, valid until the upload
+ * returns, one call per read group and contig, identical results). */
+int pd_contig_push_compact(pd_ctx * ctx, uint32_t rg, uint64_t n, const uint16_t * pos_lo, const uint8_t * dev24,
+                           uint32_t n_blocks, const uint32_t * blk_first);
+
 /* Packs what was pushed and copies it to the device (pinned staging, async on the context's stream). */
 int pd_contig_upload(pd_ctx * ctx);
 

@@ -57,7 +57,7 @@ CALL_DTYPE = np.dtype([("initial_length", "<u4"), ("iterations", "<u4"), ("delet
                        ("end_position", "<u4"), ("segment", "<u4")])
 
 EXPORTS = ["pd_process_histogram", "pd_create", "pd_create_error", "pd_destroy", "pd_last_error", "pd_contig_begin",
-           "pd_contig_push", "pd_contig_push_pinned", "pd_contig_upload", "pd_contig_scan", "pd_contig_window_count",
+           "pd_contig_push", "pd_contig_push_pinned", "pd_contig_push_compact", "pd_contig_upload", "pd_contig_scan", "pd_contig_window_count",
            "pd_debug_host_window_sums", "pd_contig_reserve_windows", "pd_shard_unique_id", "pd_shard_attach_nccl",
            "pd_shard_attach_group", "pd_shard_group_scan", "pd_set_unify", "pd_device_warmup", "pd_set_staging"]
 
@@ -90,6 +90,8 @@ def load_library(path: str = LIB_PATH):
     lib.pd_contig_begin.argtypes = [C.c_void_p, C.c_uint32]
     lib.pd_contig_push.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
     lib.pd_contig_push_pinned.argtypes = lib.pd_contig_push.argtypes
+    lib.pd_contig_push_compact.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint16), C.POINTER(C.c_uint8),
+                                           C.c_uint32, C.POINTER(C.c_uint32)]
     lib.pd_contig_upload.argtypes = [C.c_void_p]
     lib.pd_contig_scan.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(PdResult)]
     lib.pd_contig_window_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
@@ -258,6 +260,18 @@ class Scanner:
         self._check(self.lib.pd_contig_push_pinned(self.ctx, int(rg), pos.size, pos.ctypes.data_as(C.POINTER(C.c_uint32)),
                                                    dev.ctypes.data_as(C.POINTER(C.c_int32))))
 
+    def push_compact(self, rg: int, pos_lo: np.ndarray, dev24: np.ndarray, blk_first: np.ndarray):
+        """pd_contig_push_compact (5 bytes per read pair over PCIe, see compact_encode): C-contiguous views of page-locked
+        memory that stay alive and unchanged until upload()/scan() returns."""
+        assert pos_lo.dtype == np.uint16 and dev24.dtype == np.uint8 and blk_first.dtype == np.uint32
+        assert pos_lo.flags.c_contiguous and dev24.flags.c_contiguous and blk_first.flags.c_contiguous
+        assert dev24.size == 3 * pos_lo.size and blk_first.size >= 2
+        self._pinned_keep = getattr(self, "_pinned_keep", {})
+        self._pinned_keep[rg] = (pos_lo, dev24, blk_first)
+        self._check(self.lib.pd_contig_push_compact(self.ctx, int(rg), pos_lo.size, pos_lo.ctypes.data_as(C.POINTER(C.c_uint16)),
+                                                    dev24.ctypes.data_as(C.POINTER(C.c_uint8)), blk_first.size - 1,
+                                                    blk_first.ctypes.data_as(C.POINTER(C.c_uint32))))
+
     def upload(self):
         self._check(self.lib.pd_contig_upload(self.ctx))
 
@@ -357,6 +371,19 @@ def synth_read_group(seed: int, rg_index: int, mu: float, sigma: float, read_len
     return pos[:n], isz[:n]
 
 
+def compact_encode(pos: np.ndarray, dev: np.ndarray):
+    """(pos uint32 sorted, dev int32) -> (pos_lo uint16, dev24 uint8[3n], blk_first uint32) of pd_contig_push_compact: what a
+    profile decoder can emit directly (the file stores a u8 offset per 256-bp window and an i32 deviation)."""
+    pos = np.ascontiguousarray(pos, dtype=np.uint32)
+    dev = np.ascontiguousarray(dev, dtype=np.int32)
+    assert dev.size == 0 or (int(dev.min()) >= -(1 << 23) and int(dev.max()) < (1 << 23))
+    nblk = (int(pos[-1]) >> 16) + 1 if pos.size else 1
+    blk_first = np.searchsorted(pos >> 16, np.arange(nblk + 1, dtype=np.uint32), side="left").astype(np.uint32)
+    pos_lo = (pos & 0xFFFF).astype(np.uint16)
+    dev24 = np.ascontiguousarray(dev.astype("<i4").view(np.uint8).reshape(-1, 4)[:, :3]).reshape(-1)
+    return pos_lo, dev24, blk_first
+
+
 def cohort_anchor(samples) -> int:
     """First 30-bp window over all samples (getFirstWindowCoordinate, load_profile_popdel_call.h:291-350)."""
     first = [int(rg.pos[0]) for s in samples for rg in s.read_groups if rg.pos.size]
@@ -379,7 +406,9 @@ def scan_cohort(samples, params: CallParameters, device: int = 0, first_window: 
         g = 0
         for s in samples:
             for rg in s.read_groups:
-                if pinned:
+                if pinned == "compact":
+                    sc.push_compact(g, *compact_encode(rg.pos, rg.dev))
+                elif pinned:
                     sc.push_pinned(g, np.ascontiguousarray(rg.pos, dtype=np.uint32), np.ascontiguousarray(rg.dev, dtype=np.int32))
                 else:
                     sc.push(g, rg.pos, rg.dev)

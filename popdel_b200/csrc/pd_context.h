@@ -69,7 +69,12 @@ struct PdHostRg {                    // host staging of one read group of the cu
 struct PdTail { int64_t kf = -1, S = -1, E = -1, E_spill = -1; };
 struct PdShard;                      // sample sharding state (pd_shard.cu)
 
-struct PdRawRg { const uint32_t * pos = nullptr; const int32_t * dev = nullptr; uint64_t n = 0; };   // pd_contig_push_pinned
+// pd_contig_push_pinned: raw arrays; pd_contig_push_compact: 16-bit position remainders per 65 536-bp block + 24-bit deviations
+struct PdRawRg {
+    const uint32_t * pos = nullptr; const int32_t * dev = nullptr; uint64_t n = 0;
+    const uint16_t * lo = nullptr; const uint8_t * d24 = nullptr; const uint32_t * blk = nullptr; uint32_t nblk = 0;
+    bool compact() const { return lo != nullptr; }
+};
 
 struct pd_ctx {
     pd_params params;
@@ -88,6 +93,8 @@ struct pd_ctx {
     PdGrid grid{0, 200000};
     std::vector<PdHostRg> hrg;
     std::vector<PdRawRg> raw;            // caller-owned page-locked arrays (device-side packing)
+    std::vector<std::vector<uint32_t>> raw_pos_dec;    // compact input decoded on the host (only for the host-packer fallback)
+    std::vector<std::vector<int32_t>> raw_dev_dec;
     bool dev_mode = false, host_mode = false;
     bool pinned_staging = true;          // pd_set_staging: page-locked (default) or pageable staging of pd_contig_push
     // packed host image (offset tables; the words stay in the per-read-group staging vectors)
@@ -115,7 +122,7 @@ struct pd_ctx {
     PdShard * shard = nullptr;
     // scan scratch (grown on demand)
     void * d_scratch[64] = {}; size_t cap_scratch[64] = {};
-    void * d_pack[8] = {}; size_t cap_pack[8] = {};          // device packer scratch (raw arrays, tile firsts, ...)
+    void * d_pack[12] = {}; size_t cap_pack[12] = {};          // device packer scratch (raw arrays, tile firsts, ...)
     // results
     pd_call * res_calls = nullptr; size_t cap_res_calls = 0;   // page-locked, mapped: written by the device (k_emit_rows)
     uint32_t * res_ps = nullptr; size_t cap_res_ps = 0;        // page-locked, mapped

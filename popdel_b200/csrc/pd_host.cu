@@ -459,7 +459,26 @@ extern "C" int pd_contig_push_pinned(pd_ctx * c, uint32_t rg, uint64_t n, const 
     if (c->host_mode || c->packed) return pd_fail(c, PD_ERR_ARG, "pd_contig_push_pinned: cannot be mixed with pd_contig_push / contig already packed");
     if (c->raw[rg].n) return pd_fail(c, PD_ERR_ARG, "pd_contig_push_pinned: one call per read group and contig");
     c->dev_mode = true;
-    c->raw[rg] = PdRawRg{pos, dev, n};
+    PdRawRg r; r.pos = pos; r.dev = dev; r.n = n;
+    c->raw[rg] = r;
+    return 0;
+}
+
+extern "C" int pd_contig_push_compact(pd_ctx * c, uint32_t rg, uint64_t n, const uint16_t * pos_lo, const uint8_t * dev24,
+                                      uint32_t n_blocks, const uint32_t * blk_first)
+{
+    if (!c) return PD_ERR_ARG;
+    if (c->status) return c->status;
+    if (!c->contig_open || rg >= c->R || (n && (!pos_lo || !dev24 || !blk_first || !n_blocks)))
+        return pd_fail(c, PD_ERR_ARG, "pd_contig_push_compact: bad arguments or no open contig");
+    if (c->device < 0) return pd_fail(c, PD_ERR_CUDA, "pd_contig_push_compact: host-only context");
+    if (c->host_mode || c->packed) return pd_fail(c, PD_ERR_ARG, "pd_contig_push_compact: cannot be mixed with pd_contig_push / contig already packed");
+    if (c->raw[rg].n) return pd_fail(c, PD_ERR_ARG, "pd_contig_push_compact: one call per read group and contig");
+    if (n && (blk_first[n_blocks] != n || blk_first[0] != 0)) return pd_fail(c, PD_ERR_ARG, "pd_contig_push_compact: blk_first must run from 0 to n");
+    c->dev_mode = true;
+    PdRawRg r;
+    r.n = n; r.lo = pos_lo; r.d24 = dev24; r.blk = blk_first; r.nblk = n_blocks;
+    c->raw[rg] = r;
     return 0;
 }
 
@@ -510,11 +529,24 @@ extern "C" int pd_contig_upload(pd_ctx * c)
         if (prc == 0) { c->packed = true; c->uploaded = true; c->index_built = false; return 0; }
         // the active-coverage cap would drop read pairs (or a span exceeds the device look-back): sequential host path
         c->dev_mode = false;
+        c->raw_pos_dec.assign(c->R, {}); c->raw_dev_dec.assign(c->R, {});
         for (uint32_t g = 0; g < c->R; ++g) {
-            const PdRawRg r = c->raw[g];
+            PdRawRg r = c->raw[g];
+            if (r.compact() && r.n) {                              // decode the compact arrays for the sequential packer
+                auto & P = c->raw_pos_dec[g]; auto & D = c->raw_dev_dec[g];
+                P.resize(r.n); D.resize(r.n);
+                for (uint32_t b = 0; b < r.nblk; ++b)
+                    for (uint64_t i = r.blk[b]; i < r.blk[b + 1]; ++i) {
+                        P[i] = (b << 16) | r.lo[i];
+                        const uint32_t u = (uint32_t)r.d24[3 * i] | ((uint32_t)r.d24[3 * i + 1] << 8) | ((uint32_t)r.d24[3 * i + 2] << 16);
+                        D[i] = (int32_t)(u << 8) >> 8;
+                    }
+                r.pos = P.data(); r.dev = D.data();
+            }
             int hrc = pd_contig_push(c, g, r.n, r.pos, r.dev);
             if (hrc) return hrc;
         }
+        c->raw_pos_dec.clear(); c->raw_dev_dec.clear();
     }
     int rc = pd_pack_contig(c);
     if (rc) return rc;

@@ -344,6 +344,43 @@ int grow_dev(pd_ctx * c, int slot, T *& p, size_t need)
 }  // namespace
 
 // Last window the reference scans (see last_scanned_window in pd_host.cu), from the tails of the raw host arrays.
+// position / deviation of read pair i of a raw read group (either input form); `b` = block hint for compact input
+static inline uint32_t raw_pos_at(const PdRawRg & r, uint64_t i, uint32_t & b)
+{
+    if (!r.compact()) return r.pos[i];
+    while (b > 0 && r.blk[b] > i) --b;
+    while (b + 1 < r.nblk && r.blk[b + 1] <= i) ++b;
+    return (b << 16) | r.lo[i];
+}
+static inline int32_t raw_dev_at(const PdRawRg & r, uint64_t i)
+{
+    if (!r.compact()) return r.dev[i];
+    const uint32_t u = (uint32_t)r.d24[3 * i] | ((uint32_t)r.d24[3 * i + 1] << 8) | ((uint32_t)r.d24[3 * i + 2] << 16);
+    return (int32_t)(u << 8) >> 8;
+}
+
+// compact input (pd_contig_push_compact) -> the raw arrays the packing kernels read. grid (chunks of 4096 read pairs, read groups)
+__global__ void __launch_bounds__(256) k_expand_compact(const uint16_t * __restrict__ lo, const uint8_t * __restrict__ d24, const uint32_t * __restrict__ blk,
+                                                        const uint64_t * __restrict__ rg_start, const uint64_t * __restrict__ blk_start,
+                                                        const uint32_t * __restrict__ rg_nblk, uint32_t g0, uint32_t * __restrict__ pos, int32_t * __restrict__ dev)
+{
+    const uint32_t g = g0 + blockIdx.y;
+    const uint64_t s0 = rg_start[g], n = rg_start[g + 1] - s0;
+    const uint64_t c0 = (uint64_t)blockIdx.x * 4096;
+    if (c0 >= n) return;
+    const uint32_t * bk = blk + blk_start[g];
+    const uint32_t nb = rg_nblk[g];
+    if (nb == 0) return;                                           // this read group came as raw arrays
+    for (uint64_t i = c0 + threadIdx.x; i < min(n, c0 + 4096); i += 256) {
+        uint32_t a = 0, b = nb;                                   // largest block with blk[block] <= i
+        while (b - a > 1) { const uint32_t m = (a + b) >> 1; if (__ldg(bk + m) <= i) a = m; else b = m; }
+        pos[s0 + i] = (a << 16) | lo[s0 + i];
+        const uint8_t * q = d24 + 3 * (s0 + i);
+        const uint32_t u = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16);
+        dev[s0 + i] = (int32_t)(u << 8) >> 8;
+    }
+}
+
 static uint64_t last_window_from_raw(pd_ctx * c)
 {
     const uint32_t wb = c->grid.window_buffer, anchor = c->grid.anchor;
@@ -351,7 +388,8 @@ static uint64_t last_window_from_raw(pd_ctx * c)
     int64_t kf = -1;
     for (uint32_t g = 0; g < c->R; ++g) {
         const PdRawRg & r = c->raw[g];
-        if (r.n) kf = std::max<int64_t>(kf, (int64_t)((uint64_t)((r.pos[r.n - 1] - anchor) / PD_WIN) * PD_WIN / wb));
+        uint32_t bh = r.nblk ? r.nblk - 1 : 0;
+        if (r.n) kf = std::max<int64_t>(kf, (int64_t)((uint64_t)((raw_pos_at(r, r.n - 1, bh) - anchor) / PD_WIN) * PD_WIN / wb));
     }
     if (kf < 0) return 0;
     int64_t E = -1, S = -1, Esp = -1;
@@ -362,11 +400,12 @@ static uint64_t last_window_from_raw(pd_ctx * c)
     for (uint32_t g = 0; g < c->R; ++g) {
         const PdRawRg & r = c->raw[g];
         const int32_t io = c->rgc[g].inner_off;
+        uint32_t bh = r.nblk ? r.nblk - 1 : 0;
         for (uint64_t i = r.n; i-- > 0;) {
-            const uint32_t pr = r.pos[i] - anchor;
+            const uint32_t pr = raw_pos_at(r, i, bh) - anchor;
             const int64_t q = (int64_t)(pr - pr % PD_WIN);
             if (q < start_km1) break;
-            const int64_t inner = std::max<int64_t>(0, (int64_t)r.dev[i] + io);
+            const int64_t inner = std::max<int64_t>(0, (int64_t)raw_dev_at(r, i) + io);
             const int64_t lw = (int64_t)(((uint64_t)pr + (uint64_t)inner) / PD_WIN);
             if (q >= start_kf) { S = std::max<int64_t>(S, (int64_t)pr); if (lw <= wl_kf) E = std::max(E, lw); else Esp = std::max(Esp, lw); }
             else if (lw > wl_km1) E = std::max(E, lw);
@@ -382,14 +421,16 @@ int pd_pack_on_device(pd_ctx * c)
     PD_CUDA(c, cudaSetDevice(c->device));
     const uint32_t R = c->R;
     std::vector<uint64_t> rg_start(R + 1, 0);
-    uint32_t max_pos_rel = 0; bool any = false;
+    uint32_t max_pos_rel = 0; bool any = false, any_compact = false;
     for (uint32_t g = 0; g < R; ++g) {
         const PdRawRg & r = c->raw[g];
         rg_start[g + 1] = rg_start[g] + r.n;
         if (r.n) {
-            if (r.pos[0] < c->grid.anchor) return pd_fail(c, PD_ERR_ARG, "pd_contig_push_pinned: position before the contig anchor");
-            max_pos_rel = std::max(max_pos_rel, r.pos[r.n - 1] - c->grid.anchor); any = true;
+            uint32_t b0 = 0, b1 = r.nblk ? r.nblk - 1 : 0;
+            if (raw_pos_at(r, 0, b0) < c->grid.anchor) return pd_fail(c, PD_ERR_ARG, "pd_contig_push_pinned: position before the contig anchor");
+            max_pos_rel = std::max(max_pos_rel, raw_pos_at(r, r.n - 1, b1) - c->grid.anchor); any = true;
         }
+        any_compact = any_compact || r.compact();
     }
     const uint64_t total = rg_start[R];
     if (total > 0xFFFFFFF0ull) return pd_fail(c, PD_ERR_CAPACITY, "more than 2^32 read pairs in one contig batch");
@@ -397,6 +438,16 @@ int pd_pack_on_device(pd_ctx * c)
     uint32_t * d_pos; int32_t * d_dev; uint64_t * d_u64; uint32_t * d_tfirst, * d_rel, * d_lcount, * d_small, * d_pmax;
     if (grow_dev(c, 0, d_pos, total)) return c->status;
     if (grow_dev(c, 1, d_dev, total)) return c->status;
+    // compact input: staging of the 16-bit remainders, 24-bit deviations and block tables
+    uint16_t * d_lo = nullptr; uint8_t * d_d24 = nullptr; uint32_t * d_blk = nullptr, * d_nblk = nullptr; uint64_t * d_blk_start = nullptr;
+    std::vector<uint64_t> blk_start(R + 1, 0);
+    std::vector<uint32_t> h_nblk(R, 0);
+    if (any_compact) {
+        for (uint32_t g = 0; g < R; ++g) { h_nblk[g] = c->raw[g].compact() ? c->raw[g].nblk : 0; blk_start[g + 1] = blk_start[g] + (h_nblk[g] ? h_nblk[g] + 1 : 0); }
+        if (grow_dev(c, 8, d_lo, total) || grow_dev(c, 9, d_d24, total * 3 + 4) || grow_dev(c, 10, d_blk, blk_start[R] + 1) ||
+            grow_dev(c, 11, d_blk_start, (size_t)2 * (R + 1))) return c->status;
+        d_nblk = reinterpret_cast<uint32_t *>(d_blk_start + (R + 1));
+    }
 
     // ---- copy groups of about equal read-pair counts: all copies are queued on the copy stream FIRST; the host-side
     // preparation below and the packing kernels of group k then overlap the PCIe transfer of the later groups
@@ -407,6 +458,7 @@ int pd_pack_on_device(pd_ctx * c)
     PD_CUDA(c, cudaEventRecord(c->ev_pack[PACK_GROUPS], st));             // the copy stream starts after everything queued before
     PD_CUDA(c, cudaStreamWaitEvent(cp, c->ev_pack[PACK_GROUPS], 0));
     uint32_t grp_lo[PACK_GROUPS + 1]; uint64_t grp_max[PACK_GROUPS];
+    uint64_t h2d = 0;
     int n_groups = 0;
     for (uint32_t g_lo = 0; n_groups < PACK_GROUPS && g_lo < R; ++n_groups) {
         const int k = n_groups;
@@ -418,6 +470,14 @@ int pd_pack_on_device(pd_ctx * c)
             const PdRawRg & r = c->raw[g];
             grp_max[k] = std::max<uint64_t>(grp_max[k], r.n);
             if (!r.n) continue;
+            if (r.compact()) {
+                PD_CUDA(c, cudaMemcpyAsync(d_lo + rg_start[g], r.lo, r.n * 2, cudaMemcpyHostToDevice, cp));
+                PD_CUDA(c, cudaMemcpyAsync(d_d24 + 3 * rg_start[g], r.d24, r.n * 3, cudaMemcpyHostToDevice, cp));
+                PD_CUDA(c, cudaMemcpyAsync(d_blk + blk_start[g], r.blk, ((size_t)r.nblk + 1) * 4, cudaMemcpyHostToDevice, cp));
+                h2d += r.n * 5 + ((size_t)r.nblk + 1) * 4;
+                continue;
+            }
+            h2d += r.n * 8;
             PD_CUDA(c, cudaMemcpyAsync(d_pos + rg_start[g], r.pos, r.n * 4, cudaMemcpyHostToDevice, cp));
             PD_CUDA(c, cudaMemcpyAsync(d_dev + rg_start[g], r.dev, r.n * 4, cudaMemcpyHostToDevice, cp));
         }
@@ -462,7 +522,11 @@ int pd_pack_on_device(pd_ctx * c)
     PD_CUDA(c, cudaMemcpyAsync(d_rg_start, rg_start.data(), (R + 1) * 8, cudaMemcpyHostToDevice, st));
     PD_CUDA(c, cudaMemcpyAsync(d_word_base, base.data(), (R + 1) * 8, cudaMemcpyHostToDevice, st));
     PD_CUDA(c, cudaMemsetAsync(d_small, 0, ((size_t)R + 16) * 4, st));
-    c->h2d_bytes = total * 8 + (R + 1) * 16;
+    c->h2d_bytes = h2d + (R + 1) * 16;
+    if (any_compact) {
+        PD_CUDA(c, cudaMemcpyAsync(d_blk_start, blk_start.data(), (R + 1) * 8, cudaMemcpyHostToDevice, st));
+        PD_CUDA(c, cudaMemcpyAsync(d_nblk, h_nblk.data(), (size_t)R * 4, cudaMemcpyHostToDevice, st));
+    }
 
     PackArgs a;
     a.pos = d_pos; a.dev = d_dev; a.rg_start = d_rg_start; a.rgc = c->d_rgc; a.R = R; a.NT = NT; a.g0 = 0; a.ng = R;
@@ -478,6 +542,8 @@ int pd_pack_on_device(pd_ctx * c)
         PD_CUDA(c, cudaStreamWaitEvent(st, c->ev_pack[k], 0));
         a.g0 = grp_lo[k]; a.ng = grp_lo[k + 1] - grp_lo[k];
         const uint64_t nt_grp = per * a.ng;
+        if (any_compact && grp_max[k])           // (read groups pushed as raw arrays have no blocks: their chunks exit at once)
+            k_expand_compact<<<dim3((unsigned)((grp_max[k] + 4095) / 4096), a.ng), 256, 0, st>>>(d_lo, d_d24, d_blk, d_rg_start, d_blk_start, d_nblk, a.g0, d_pos, d_dev);
         if (grp_max[k]) k_check_span<<<dim3((unsigned)((grp_max[k] + 1023) / 1024), a.ng), 256, 0, st>>>(a);
         k_tile_first<<<(unsigned)((nt_grp + 255) / 256), 256, 0, st>>>(a);
         k_cap_check<<<a.ng * chunks, 1024, 0, st>>>(a, chunks);

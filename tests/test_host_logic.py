@@ -21,6 +21,24 @@ def test_library_exports_every_declared_symbol():
         assert getattr(lib, name) is not None
 
 
+def test_compact_encode_round_trip():
+    """pd_contig_push_compact's input form: 16-bit position remainders per 65 536-bp block + 24-bit deviations."""
+    rng = np.random.default_rng(11)
+    pos = np.sort(rng.integers(990, 400_000, size=5000)).astype(np.uint32)
+    pos[:3] = 990
+    dev = rng.integers(-400, 19_000, size=5000).astype(np.int32)
+    lo, d24, blk = api.compact_encode(pos, dev)
+    assert lo.size == 5000 and d24.size == 15000 and blk[0] == 0 and blk[-1] == 5000
+    back = np.zeros(5000, np.uint32)
+    for b in range(blk.size - 1):
+        back[blk[b]:blk[b + 1]] = (b << 16) | lo[blk[b]:blk[b + 1]].astype(np.uint32)
+    assert np.array_equal(back, pos)
+    u = d24.reshape(-1, 3).astype(np.uint32)
+    d = (u[:, 0] | (u[:, 1] << 8) | (u[:, 2] << 16)).astype(np.int64)
+    d = np.where(d >= 1 << 23, d - (1 << 24), d)
+    assert np.array_equal(d, dev)
+
+
 def test_process_histogram_equals_oracle(oracle_lib):
     rng = np.random.default_rng(3)
     for mu, sd, rl in [(500, 50, 150), (350, 30, 100), (550, 80, 150), (300, 100, 125)]:

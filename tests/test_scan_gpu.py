@@ -74,10 +74,11 @@ def test_device_packer_equals_host_packer(kind):
     """pd_contig_push_pinned (device-side packing; host fallback when the coverage cap bites) == pd_contig_push."""
     samples, params = _cohort(kind)
     a, _ = api.scan_cohort(samples, params)
-    b, _ = api.scan_cohort(samples, params, pinned=True)
-    assert a["n_windows"] == b["n_windows"] and a["n_flagged_windows"] == b["n_flagged_windows"]
-    assert a["n_reads"] == b["n_reads"]
-    assert_calls_equal(b["calls"], b["per_sample"], a["calls"], a["per_sample"], rtol=0)
+    for mode in (True, "compact"):              # raw page-locked arrays / 5 bytes per read pair (pd_contig_push_compact)
+        b, _ = api.scan_cohort(samples, params, pinned=mode)
+        assert a["n_windows"] == b["n_windows"] and a["n_flagged_windows"] == b["n_flagged_windows"]
+        assert a["n_reads"] == b["n_reads"]
+        assert_calls_equal(b["calls"], b["per_sample"], a["calls"], a["per_sample"], rtol=0)
 
 
 @pytest.mark.parametrize("n_samples,contig_len,env", [(150, 90_000, {}), (300, 70_000, {}), (150, 90_000, {"PD_EM_V2": "1"}),
