@@ -89,6 +89,8 @@ typedef struct {
     float    ms_unify;
     float    ms_em;                /* the FIRST EM chunk's kernels alone (k_em_one, or k_em + k_final); the whole EM when */
     uint32_t n_em_pairs_timed;     /* the scan has one chunk (<= 16384 (window, length) pairs) */
+    uint64_t n_screened_windows;   /* windows left after the second screen stage (= n_flagged_windows when it is off) */
+    uint64_t n_known_pairs;        /* second stage: (window, sample) pairs whose Q3 was computed before the stage decided */
 } pd_result;
 
 /* Host: processHistogram(hist, 256, smoothing, pseudoCountFraction), insert_histogram_popdel.h:974-986, in place.

@@ -44,7 +44,8 @@ class PdResult(C.Structure):
                 ("ms_h2d", C.c_float), ("ms_screen", C.c_float), ("ms_genotype", C.c_float), ("ms_d2h", C.c_float),
                 ("ms_total", C.c_float), ("ms_stream", C.c_float),
                 ("significant_windows", C.POINTER(C.c_uint32)), ("n_window_calls", C.c_uint64), ("ms_unify", C.c_float),
-                ("ms_em", C.c_float), ("n_em_pairs_timed", C.c_uint32)]
+                ("ms_em", C.c_float), ("n_em_pairs_timed", C.c_uint32), ("n_screened_windows", C.c_uint64),
+                ("n_known_pairs", C.c_uint64)]
 
 
 class PdUnifyParams(C.Structure):
@@ -303,7 +304,8 @@ class Scanner:
                     h2d_bytes=res.h2d_bytes, d2h_bytes=res.d2h_bytes, n_kernel_launches=res.n_kernel_launches,
                     ms_h2d=res.ms_h2d, ms_screen=res.ms_screen, ms_genotype=res.ms_genotype, ms_total=res.ms_total,
                     ms_stream=res.ms_stream, significant_windows=sig, n_window_calls=res.n_window_calls, ms_unify=res.ms_unify,
-                    ms_em=res.ms_em, n_em_pairs_timed=res.n_em_pairs_timed)
+                    ms_em=res.ms_em, n_em_pairs_timed=res.n_em_pairs_timed, n_screened_windows=res.n_screened_windows,
+                    n_known_pairs=res.n_known_pairs)
 
     def set_unify(self, mean_stddev=None, min_relative_window_cover: float = 0.5, output_failed: bool = False):
         """pd_set_unify: scans return the merged variants of every segment (unifyCalls, utils_popdel.h:567-654, run on the

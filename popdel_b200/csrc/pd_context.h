@@ -39,6 +39,8 @@ struct PdDev {
     uint32_t N, R;
     uint32_t window_buffer;
     int32_t  t_min;                  // min over read groups of min_init_del_len
+    int32_t  t_mark;                 // the screen marks / counts read pairs above this (t_min, or t_known with the second stage)
+    int32_t  t_known;                // second screen stage: samples whose Q3 can exceed this get an exact Q3 first (0: stage off)
     uint32_t w_begin, w_end;         // windows to scan [w_begin, w_end)
 };
 
@@ -121,7 +123,7 @@ struct pd_ctx {
     uint32_t * d_min_init = nullptr; // [R] minInitDelLengths (of the whole cohort when sharded by sample)
     PdShard * shard = nullptr;
     // scan scratch (grown on demand)
-    void * d_scratch[64] = {}; size_t cap_scratch[64] = {};
+    void * d_scratch[80] = {}; size_t cap_scratch[80] = {};
     void * d_pack[12] = {}; size_t cap_pack[12] = {};          // device packer scratch (raw arrays, tile firsts, ...)
     // results
     pd_call * res_calls = nullptr; size_t cap_res_calls = 0;   // page-locked, mapped: written by the device (k_emit_rows)

@@ -21,7 +21,7 @@ constexpr uint32_t PD_GRAN = 1024;                  // words per warp in k_strea
 constexpr int PD_CAND_INLINE = 6;                   // candidate lengths kept inline per window job
 
 // device counters of one scan (uint32 each)
-enum { CNT_TJOBS = 0, CNT_JOBS = 1, CNT_PAIRS = 2, CNT_POOL = 3, CNT_CALLS = 4, CNT_CJOBS = 5, CNT_ERR = 6, CNT_N = 16 };
+enum { CNT_TJOBS = 0, CNT_JOBS = 1, CNT_PAIRS = 2, CNT_POOL = 3, CNT_CALLS = 4, CNT_CJOBS = 5, CNT_ERR = 6, CNT_ALIVE = 7, CNT_KNOWN = 8, CNT_N = 16 };
 
 struct PdPair { uint32_t job; int32_t L0; };                         // (window job, initial deletion length)
 struct EmState { uint32_t len, it, alive, pad; double freq; double gt[3]; };   // handed from k_em to k_final
@@ -37,6 +37,7 @@ struct ScreenArgs {
     const uint32_t * gran_tile;         // tile that contains word (first word of g) + j * PD_GRAN
     const uint32_t * long_off;          // [R+1] wide-list ranges per read group
     uint32_t total_longs;
+    uint32_t * known;                   // second stage: [N][need_stride * 32] window bits per (sample, tile): Q3 can exceed t_known
 };
 struct JobArgs {
     const uint32_t * tile_flags; uint32_t n_tiles, tile_begin;
@@ -63,6 +64,12 @@ struct GatherArgs {
     uint32_t * counters;
     uint32_t * act_off, * act_cnt;      // [candidate jobs - cj_base][R]
     uint32_t debug_flags;               // tests: bit 0 = generic path in k_tile_q3, bit 1 = generic path in k_tile_gather
+    // second screen stage (pd_launch_q3 phases): 0 = every (flagged window, sample); 1 = only the pairs whose Q3 can exceed
+    // t_known; 2 = the rest, for the windows the stage could not reject
+    int phase;
+    const uint32_t * known; uint32_t known_stride, tb_al;
+    uint32_t * tj_alive;                // [ntj] windows of the tile job that survive the second stage
+    uint8_t * job_dead;                 // [jobs] 1 = rejected by the second stage (no candidates possible)
 };
 struct CandArgs {
     // Q3 / state of every (window job, sample): nparts blocks [njobs][part_n[p]] (one per rank when sharded by sample)
@@ -77,8 +84,10 @@ struct CandArgs {
     uint32_t * counters; unsigned long long * block_sums;
     uint32_t npad;
     uint32_t force_sort;                // tests: always take the sorting path of k_candidates
+    const uint8_t * job_dead;           // second screen stage: windows without any possible candidate (nullptr: stage off)
 };
 void pd_launch_q3(const PdDev & a, const GatherArgs & g, cudaStream_t st, uint64_t * launches);
+void pd_launch_screen2(const PdDev & a, const GatherArgs & g, cudaStream_t st, uint64_t * launches);
 void pd_launch_cmask(const GatherArgs & g, const CandArgs & ca, uint32_t * tj_cmask, uint32_t * tj_cfirst, cudaStream_t st, uint64_t * launches);
 void pd_launch_gather(const PdDev & a, const GatherArgs & g, cudaStream_t st, uint64_t * launches);
 int  pd_launch_candidates(pd_ctx * c, const PdDev & a, const CandArgs & ca, cudaStream_t st, uint64_t * launches);

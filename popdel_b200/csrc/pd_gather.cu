@@ -46,8 +46,10 @@ __device__ __forceinline__ int32_t q3_value(uint32_t nn, double r, int32_t lo_v,
 // K2a: Q3 of every (flagged window, sample)
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int TQ_WARPS = 4;
-constexpr int TQ_ACT = 48;                                          // usable active read pairs per (window, sample), fast path
-
+// usable active read pairs per (window, sample) via the fast path: 48 (9 blocks per SM) for the passes over every flagged
+// window; 92 for the pass over the few windows that survive the second screen stage -- they sit at deletions, where the
+// carriers' spanning read pairs pile up and the slow path would dominate
+template <int TQ_ACT>
 struct alignas(16) WarpQ3 {
     int32_t val[TQ_ACT][32];                                        // [slot][window]: deviations of the window's usable active pairs
     uint32_t cnt[32];
@@ -112,20 +114,32 @@ __device__ __noinline__ void q3_window_slow(const PdDev & a, const GatherArgs & 
     if (lane == 0) write_q3(ga, a.N, job, smp, cov, n, q, mx);
 }
 
-__global__ void __launch_bounds__(TQ_WARPS * 32, 9) k_tile_q3(PdDev a, GatherArgs ga)
+template <int TQ_ACT, int MINB>
+__global__ void __launch_bounds__(TQ_WARPS * 32, MINB) k_tile_q3(PdDev a, GatherArgs ga)
 {
-    __shared__ WarpQ3 sh_all[TQ_WARPS];
+    __shared__ WarpQ3<TQ_ACT> sh_all[TQ_WARPS];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t smp = blockIdx.y * TQ_WARPS + wib;
     if (smp >= a.N) return;
-    const uint32_t tj = ga.tj0 + blockIdx.x;
-    const uint32_t tile = ga.tj_tile[tj], wmask = ga.tj_mask[tj];
+    // (blocks walk several tile jobs: with the second screen stage most (tile job, sample) pairs have nothing to do)
+    for (uint32_t tjb = blockIdx.x; tjb < ga.ntj; tjb += gridDim.x) {
+    const uint32_t tj = ga.tj0 + tjb;
+    const uint32_t tile = ga.tj_tile[tj], jmask = ga.tj_mask[tj];        // jmask numbers the window jobs of the tile
+    // windows this launch handles for this sample (second screen stage: first the pairs whose Q3 can exceed t_known, later the
+    // rest of the windows that survived)
+    uint32_t wmask = jmask;
+    if (ga.phase) {
+        const uint32_t kn = ga.known[(size_t)smp * ga.known_stride + (tile - ga.tb_al)];
+        wmask = ga.phase == 1 ? (jmask & kn) : (jmask & ga.tj_alive[tjb] & ~kn);
+        if (wmask == 0) continue;
+        if (ga.phase == 1 && lane == 0) atomicAdd(&ga.counters[CNT_KNOWN], (uint32_t)__popc(wmask));
+    }
     const uint32_t job_first = ga.tj_wbase[tj] - ga.job_base;            // scratch row of the tile's first flagged window
     const uint32_t g0 = a.sample_rg[smp], g1 = a.sample_rg[smp + 1];
-    WarpQ3 & sh = sh_all[wib];
+    WarpQ3<TQ_ACT> & sh = sh_all[wib];
     const int32_t w0 = (int32_t)(tile * PD_TILE_WINDOWS);
     const uint32_t lane_bit = 1u << lane;
-    const uint32_t my_job = job_first + __popc(wmask & (lane_bit - 1u));
+    const uint32_t my_job = job_first + __popc(jmask & (lane_bit - 1u));
 
     sh.cnt[lane] = 0;
     uint32_t cov = 0;
@@ -188,8 +202,80 @@ __global__ void __launch_bounds__(TQ_WARPS * 32, 9) k_tile_q3(PdDev a, GatherArg
     __syncwarp();
     for (; slow_mask; slow_mask &= slow_mask - 1) {
         const int wl = __ffs(slow_mask) - 1;
-        q3_window_slow(a, ga, smp, w0 + wl, job_first + __popc(wmask & ((1u << wl) - 1u)), lane);
+        q3_window_slow(a, ga, smp, w0 + wl, job_first + __popc(jmask & ((1u << wl) - 1u)), lane);
     }
+    __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Second screen stage (cohorts with different thresholds per read group, where nearly every window has SOME sample whose
+// Q3 can exceed the smallest one). initialize_deletion_lengths (:58-86) keeps a chain cluster only if its integer mean
+// exceeds min T over its ranks >= t_min. Every Q3 that was NOT computed in phase 1 is <= t_known < t_min, so in the sorted
+// array the values above t_known are exactly the phase-1 values above t_known, their chain clusters among themselves are
+// exact, and the true cluster of a chain may only ADD values <= t_known below it, which lowers a mean that is above
+// t_known. Hence: if no chain of the values above t_known has an integer mean above t_min, the window has no candidate.
+// One warp per flagged window.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int S2_CAP = 256;                                         // values above t_known per window (more: the window survives)
+
+__global__ void __launch_bounds__(256) k_screen2(PdDev a, GatherArgs ga)
+{
+    __shared__ int32_t s_val[8][S2_CAP], s_sorted[8][S2_CAP];
+    __shared__ uint32_t s_alive;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t tj = ga.tj0 + blockIdx.x;
+    const uint32_t tile = ga.tj_tile[tj], jmask = ga.tj_mask[tj];
+    const uint32_t job_first = ga.tj_wbase[tj] - ga.job_base;
+    if (threadIdx.x == 0) s_alive = 0;
+    __syncthreads();
+    uint32_t rank = 0;
+    for (uint32_t m = jmask; m; m &= m - 1, ++rank) {
+        if ((rank & 7u) != (uint32_t)wib) continue;
+        const int wl = __ffs(m) - 1;
+        const uint32_t job = job_first + rank;
+        int32_t * val = s_val[wib], * srt = s_sorted[wib];
+        uint32_t n = 0;
+        for (uint32_t s0 = 0; s0 < a.N; s0 += 32) {
+            const uint32_t s = s0 + lane;
+            bool take = false; int32_t v = 0;
+            if (s < a.N && ((ga.known[(size_t)s * ga.known_stride + (tile - ga.tb_al)] >> wl) & 1u)) {
+                const size_t o = (size_t)job * a.N + s;
+                if (ga.sstat[o] == 2) { v = ga.q3[o]; take = v > a.t_known; }
+            }
+            const uint32_t bm = __ballot_sync(PD_FULL, take);
+            const uint32_t slot = n + __popc(bm & ((1u << lane) - 1u));
+            if (take && slot < (uint32_t)S2_CAP) val[slot] = v;
+            n += __popc(bm);
+        }
+        __syncwarp();
+        bool alive = n > (uint32_t)S2_CAP;
+        if (!alive && n) {
+            for (uint32_t i = lane; i < n; i += 32) {                // rank sort (ties by index)
+                const int32_t v = val[i];
+                uint32_t r = 0;
+                for (uint32_t j = 0; j < n; ++j) { const int32_t u = val[j]; r += (u < v) || (u == v && j < i); }
+                srt[r] = v;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                long long sum = srt[0]; int cnt = 1;
+                for (uint32_t i = 1; i <= n; ++i) {
+                    if (i < n && srt[i - 1] + 50 > srt[i]) { sum += srt[i]; ++cnt; continue; }
+                    if ((int)(sum / cnt) > a.t_min) { alive = true; break; }
+                    if (i < n) { sum = srt[i]; cnt = 1; }
+                }
+            }
+            alive = __shfl_sync(PD_FULL, alive ? 1 : 0, 0) != 0;
+        }
+        if (lane == 0) {
+            ga.job_dead[job] = alive ? 0 : 1;
+            if (alive) atomicOr(&s_alive, 1u << wl);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { ga.tj_alive[blockIdx.x] = s_alive; if (s_alive) atomicAdd(&ga.counters[CNT_ALIVE], (uint32_t)__popc(s_alive)); }
 }
 
 // candidate windows of every flagged tile (after the candidate counts are known)
@@ -382,6 +468,7 @@ __global__ void __launch_bounds__(256) k_candidates(PdDev a, CandArgs ca, int mo
     __shared__ int32_t s_min, s_max;
     const uint32_t job = blockIdx.x;
     if (mode == 1 && ca.cand_cnt[job] <= (uint32_t)PD_CAND_INLINE) return;
+    if (ca.job_dead && ca.job_dead[job]) { if (threadIdx.x == 0 && mode == 0) ca.cand_cnt[job] = 0; return; }      // rejected by the second screen stage
     if (threadIdx.x == 0) { s_n = 0; s_ntop = 0; s_min = INT_MAX; s_max = INT_MIN; }
     __syncthreads();
     for (uint32_t p = 0; p < ca.nparts; ++p) {
@@ -525,7 +612,15 @@ __global__ void __launch_bounds__(1024) k_cand_write(CandArgs ca)
 
 void pd_launch_q3(const PdDev & a, const GatherArgs & g, cudaStream_t st, uint64_t * launches)
 {
-    k_tile_q3<<<dim3(g.ntj, (a.N + TQ_WARPS - 1) / TQ_WARPS), TQ_WARPS * 32, 0, st>>>(a, g);
+    // (a 92-slot variant for the surviving windows of phase 2 was measured slower: 54.9 vs 49.9 ms per mixed 300 x 12 Mbp scan)
+    const uint32_t gx = g.phase ? std::min<uint32_t>(g.ntj, 1024u) : g.ntj;
+    k_tile_q3<48, 9><<<dim3(gx, (a.N + TQ_WARPS - 1) / TQ_WARPS), TQ_WARPS * 32, 0, st>>>(a, g);
+    ++*launches;
+}
+
+void pd_launch_screen2(const PdDev & a, const GatherArgs & g, cudaStream_t st, uint64_t * launches)
+{
+    k_screen2<<<g.ntj, 256, 0, st>>>(a, g);
     ++*launches;
 }
 

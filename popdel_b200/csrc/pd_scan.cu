@@ -19,7 +19,8 @@ namespace {
 enum Slot {                                     // d_scratch slots
     S_NEED = 0, S_TFLAGS, S_COUNTERS, S_TJ_TILE, S_TJ_MASK, S_TJ_WBASE, S_JOBWIN, S_BSUMS,
     S_ACT_OFF, S_ACT_CNT, S_Q3, S_SSTAT, S_CAND_CNT, S_CAND_INL, S_CAND_OFF, S_CJOB_OF, S_TJ_CMASK, S_TJ_CFIRST, S_PAIRS, S_POOL_POS, S_POOL_DEV,
-    S_DLX, S_DLE, S_SHIFTS, S_STATES, S_PS0, S_PS1, S_CALLS0, S_CALLS1, S_VALID0, S_VALID1, S_DONE0, S_DONE1, S_CHUNK_BASE, S_DBG, S_DMAX, S_ALL_Q3, S_ALL_SS
+    S_DLX, S_DLE, S_SHIFTS, S_STATES, S_PS0, S_PS1, S_CALLS0, S_CALLS1, S_VALID0, S_VALID1, S_DONE0, S_DONE1, S_CHUNK_BASE, S_DBG, S_DMAX, S_ALL_Q3, S_ALL_SS,
+    S_KNOWN = 64, S_TJ_ALIVE, S_JOB_DEAD
 };
 
 template <typename T>
@@ -145,6 +146,18 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
     a.words = c->d_words; a.tiles = c->d_tiles; a.longs = c->d_longs;
     a.rgc = c->d_rgc; a.sample_rg = c->d_sample_rg; a.tab = c->d_tab;
     a.NT = c->NT; a.N = N; a.R = R; a.window_buffer = c->grid.window_buffer; a.t_min = c->t_min;
+    // Second screen stage (pd_gather.cu, k_screen2): worth it when the read groups have different initial-length thresholds,
+    // i.e. when the cohort-minimum threshold t_min lets nearly every window through the first stage. PD_SCREEN2=0/1 overrides.
+    bool screen2 = false;
+    if (!sh) {
+        uint32_t tmax = 0;
+        for (const auto & k : c->rgc) tmax = std::max(tmax, k.min_init);
+        screen2 = (int64_t)tmax > (int64_t)c->t_min && c->t_min >= 60;
+        if (getenv("PD_SCREEN2")) screen2 = atoi(getenv("PD_SCREEN2")) != 0 && c->t_min >= 60;
+    }
+    const int s2gap = getenv("PD_SCREEN2_GAP") ? atoi(getenv("PD_SCREEN2_GAP")) : 30;     // (tuning knob)
+    a.t_known = screen2 ? std::max(c->t_min - s2gap, c->t_min / 2) : 0;
+    a.t_mark = screen2 ? a.t_known : a.t_min;
     a.w_begin = (uint32_t)w_begin; a.w_end = (uint32_t)w_end;
     if (!c->index_built && build_index(c, a)) return c->status;
 
@@ -165,6 +178,12 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
     uint32_t * d_counters; unsigned long long * d_bsums;
     if (grow_scratch(c, S_NEED, s.need, (size_t)N * s.need_stride)) return c->status;
     if (grow_scratch(c, S_TFLAGS, s.tile_flags, (size_t)n_tiles)) return c->status;
+    s.known = nullptr;
+    const size_t known_stride = (size_t)s.need_stride * 32;
+    if (screen2) {
+        if (grow_scratch(c, S_KNOWN, s.known, (size_t)N * known_stride)) return c->status;
+        PD_CUDA(c, cudaMemsetAsync(s.known, 0, (size_t)N * known_stride * 4, st));
+    }
     if (grow_scratch(c, S_COUNTERS, d_counters, (size_t)CNT_N)) return c->status;
     JobArgs j;
     j.tile_flags = s.tile_flags; j.n_tiles = n_tiles; j.tile_begin = s.tile_begin; j.counters = d_counters;
@@ -265,11 +284,17 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
         if (grow_scratch(c, S_TJ_CMASK, d_cmask, (size_t)ntj)) return c->status;
         if (grow_scratch(c, S_TJ_CFIRST, d_cfirst, (size_t)ntj)) return c->status;
         ga.tj_cmask = d_cmask; ga.tj_cfirst = d_cfirst;
+        ga.phase = 0; ga.known = s.known; ga.known_stride = (uint32_t)known_stride; ga.tb_al = s.tb_al;
+        if (screen2) {
+            if (grow_scratch(c, S_TJ_ALIVE, ga.tj_alive, (size_t)ntj)) return c->status;
+            if (grow_scratch(c, S_JOB_DEAD, ga.job_dead, (size_t)nj)) return c->status;
+        }
         CandArgs ca;
         memset(&ca, 0, sizeof(ca));
         ca.nparts = 1; ca.q3[0] = ga.q3; ca.sstat[0] = ga.sstat; ca.part_n[0] = N; ca.min_init = c->d_min_init;
         ca.njobs = nj; ca.job_base = job_base; ca.counters = d_counters; ca.block_sums = d_bsums; ca.npad = npad;
         ca.force_sort = (slow_env >> 2) & 1u;
+        ca.job_dead = screen2 ? ga.job_dead : nullptr;
         int32_t * all_q3 = nullptr; uint8_t * all_ss = nullptr;
         if (sh) {
             if (grow_scratch(c, S_ALL_Q3, all_q3, (size_t)nj * Nb * sh->world)) return c->status;
@@ -291,7 +316,12 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
         size_t pair_cap = std::max<size_t>(c->cap_scratch[S_PAIRS] / sizeof(PdPair), (size_t)nj * 2 + 1024);
         if (c->pool_cap == 0) c->pool_cap = std::max<size_t>((size_t)std::min<uint32_t>(nj, 16384) * R * 40, 1u << 20);
 
-        pd_launch_q3(a, ga, st, nl);
+        if (screen2) {
+            ga.phase = 1; pd_launch_q3(a, ga, st, nl);               // exact Q3 of the (window, sample) pairs that can exceed t_known
+            pd_launch_screen2(a, ga, st, nl);                        // windows without a possible candidate drop out
+            ga.phase = 2; pd_launch_q3(a, ga, st, nl);               // the rest of the surviving windows
+            ga.phase = 0;
+        } else pd_launch_q3(a, ga, st, nl);
         PD_CUDA(c, cudaGetLastError());
         if (sh) {                                                   // every rank derives the candidates from ALL samples' Q3
             if (pd_shard_allgather(c, ga.q3, all_q3, (size_t)nj * Nb * 4, st)) return c->status;
@@ -464,6 +494,8 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
     }
     out->n_calls = c->res_count[0];
     out->n_window_calls = out->n_calls;
+    out->n_screened_windows = screen2 ? h_cnt[CNT_ALIVE] : out->n_flagged_windows;
+    out->n_known_pairs = screen2 ? h_cnt[CNT_KNOWN] : 0;
     if (out->n_em_pairs_timed) PD_CUDA(c, cudaEventElapsedTime(&out->ms_em, c->ev[12], c->ev[13]));
     if (uni) {
         const uint32_t nseg = (uint32_t)((w_end * PD_WIN) / c->grid.window_buffer + 2);

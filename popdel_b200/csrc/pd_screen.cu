@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) k_stream(PdDev a, ScreenArgs s)
     const uint64_t a0l = (uint64_t)base + (uint64_t)j * PD_GRAN;
     if (a0l >= r1) return;
     const uint32_t a0 = (uint32_t)a0l, rem = r1 - a0;
-    const int32_t thr = (int32_t)(((uint32_t)a.t_min << 11) | 0x7FFu);      // (int)word > thr  <=>  dev > t_min
+    const int32_t thr = (int32_t)(((uint32_t)a.t_mark << 11) | 0x7FFu);     // (int)word > thr  <=>  dev > t_mark
     const uint4 * src = reinterpret_cast<const uint4 *>(a.words + a0) + lane;
     uint4 v[8];
 #pragma unroll
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) k_mark_long(PdDev a, ScreenArgs s)
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= s.total_longs) return;
     const PdLong L = a.longs[i];
-    if (L.dev <= a.t_min) return;
+    if (L.dev <= a.t_mark) return;
     uint32_t lo = 0, hi = a.R;                                      // largest g with long_off[g] <= i
     while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(&s.long_off[mid]) <= i) lo = mid; else hi = mid; }
     const uint32_t t0 = max(L.s / PD_TILE_WINDOWS, s.tile_begin), t1 = min(L.e / PD_TILE_WINDOWS, s.tile_end - 1);
@@ -120,30 +120,32 @@ __global__ void __launch_bounds__(256) k_mark_long(PdDev a, ScreenArgs s)
 // first window, -1 after the last); an inclusive warp scan turns that into per-window counts (lane = window): n = active
 // read pairs, x = those with dev > t_min.
 // ------------------------------------------------------------------------------------------------------------------
-struct CountHist { int n[33], x[33]; };
+struct CountHist { int n[33], x[33], y[33]; };        // y: read pairs above t_known (second stage)
 
 __device__ __forceinline__ void count_tile(const PdDev & a, uint32_t g, const PdRgConst & k, uint32_t tile, int lane, CountHist & h,
-                                           uint32_t & n_g, uint32_t & x_g)
+                                           uint32_t & n_g, uint32_t & x_g, uint32_t & y_g)
 {
     const int32_t w0 = (int32_t)(tile * PD_TILE_WINDOWS);
-    h.n[lane] = 0; h.x[lane] = 0;
-    if (lane == 0) { h.n[32] = 0; h.x[32] = 0; }
+    const bool two = a.t_known != 0;
+    h.n[lane] = 0; h.x[lane] = 0; h.y[lane] = 0;
+    if (lane == 0) { h.n[32] = 0; h.x[32] = 0; h.y[32] = 0; }
     __syncwarp();
     for_tile_batches(a, g, k, tile, lane, [&](bool valid, int32_t s, int32_t e, uint32_t, int32_t dev) {
         if (valid && e >= w0 && s <= w0 + 31) {
             const int sr = max(s - w0, 0), er = min(e - w0, 31) + 1;
             atomicAdd(&h.n[sr], 1); atomicSub(&h.n[er], 1);
             if (dev > a.t_min) { atomicAdd(&h.x[sr], 1); atomicSub(&h.x[er], 1); }
+            if (two && dev > a.t_known) { atomicAdd(&h.y[sr], 1); atomicSub(&h.y[er], 1); }
         }
     });
     __syncwarp();
-    int n = h.n[lane], x = h.x[lane];
+    int n = h.n[lane], x = h.x[lane], y = h.y[lane];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const int pn = __shfl_up_sync(PD_FULL, n, o), px = __shfl_up_sync(PD_FULL, x, o);
-        if (lane >= o) { n += pn; x += px; }
+        const int pn = __shfl_up_sync(PD_FULL, n, o), px = __shfl_up_sync(PD_FULL, x, o), py = __shfl_up_sync(PD_FULL, y, o);
+        if (lane >= o) { n += pn; x += px; y += py; }
     }
-    n_g = (uint32_t)n; x_g = (uint32_t)x;
+    n_g = (uint32_t)n; x_g = (uint32_t)x; y_g = (uint32_t)y;
     __syncwarp();
 }
 
@@ -162,18 +164,23 @@ __global__ void __launch_bounds__(256) k_count(PdDev a, ScreenArgs s)
         mq &= mq - 1;
         const uint32_t tile = s.tb_al + wq * 32 + b;
         if (tile < s.tile_begin || tile >= s.tile_end) continue;
-        uint32_t cov = 0, n = 0, x = 0;
+        uint32_t cov = 0, n = 0, x = 0, y = 0;
         for (uint32_t g = g0; g < g1; ++g) {
             const PdRgConst k = a.rgc[g];
-            uint32_t n_g = 0, x_g = 0;
-            count_tile(a, g, k, tile, lane, hist[wib], n_g, x_g);
+            uint32_t n_g = 0, x_g = 0, y_g = 0;
+            count_tile(a, g, k, tile, lane, hist[wib], n_g, x_g, y_g);
             cov += n_g;
-            if (n_g < k.max_load) { n += n_g; x += x_g; }
+            if (n_g < k.max_load) { n += n_g; x += x_g; y += y_g; }
         }
         const uint32_t w = tile * PD_TILE_WINDOWS + lane;
-        const bool pass = w >= a.w_begin && w < a.w_end && cov >= 2 && n >= 1 && x >= pd_q3_need(n);
+        const bool in = w >= a.w_begin && w < a.w_end && cov >= 2 && n >= 1;
+        const bool pass = in && x >= pd_q3_need(n);
         const uint32_t pm = __ballot_sync(PD_FULL, pass);
         if (pm && lane == 0) atomicOr(&s.tile_flags[tile - s.tile_begin], pm);
+        if (a.t_known != 0) {                                       // second stage: this sample's Q3 can exceed t_known in these windows
+            const uint32_t km = __ballot_sync(PD_FULL, in && y >= pd_q3_need(n));
+            if (lane == 0) s.known[(size_t)smp * (s.need_stride * 32) + (tile - s.tb_al)] = km;
+        }
     }
 }
 

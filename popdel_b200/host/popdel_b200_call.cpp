@@ -509,6 +509,7 @@ struct Options {
     unsigned maxLoad = 100, buffer = 200000, iterations = 15, pseudo = 500;
     double prior = 0.0001, minSampleFraction = 0.1, minCover = 0.5;
     int device = 0;
+    std::vector<int> devices;            // -g 0,1,...: window-range sharding, one scan context (and host thread) per entry
 };
 
 }  // namespace
@@ -534,7 +535,14 @@ int main(int argc, char ** argv)
         else if (a == "-p" || a == "--prior-probability") opt.prior = atof(val().c_str());
         else if (a == "-s" || a == "--min-sample-fraction") opt.minSampleFraction = atof(val().c_str());
         else if (a == "-c" || a == "--min-relative-window-cover") opt.minCover = atof(val().c_str());
-        else if (a == "-g" || a == "--gpu") opt.device = atoi(val().c_str());
+        else if (a == "-g" || a == "--gpu") {                        // one device, or a comma-separated list (an entry may repeat)
+            std::string v = val(), tok;
+            opt.devices.clear();
+            std::stringstream ss(v);
+            while (std::getline(ss, tok, ',')) if (!tok.empty()) opt.devices.push_back(atoi(tok.c_str()));
+            if (opt.devices.empty()) die("-g needs a device number or a comma-separated list");
+            opt.device = opt.devices[0];
+        }
         else if (a == "-A" || a == "--active-coverage-file") opt.maxLoadFile = val();
         else if (a == "-e" || a == "--per-sample-rgid") opt.perSampleRgid = true;
         else if (a == "-d" || a == "--max-deletion-size") val();           // parsed by the reference's call parser too, used by `popdel profile` only
@@ -659,14 +667,27 @@ int main(int argc, char ** argv)
     tm.lap("histograms");
     warm.join();
     tm.lap("cuda-init");
-    pd_ctx * ctx = pd_create(&prm, (uint32_t)N, (uint32_t)R, rgs.data(), opt.device);
-    if (!ctx) die(std::string("cannot create the scan context: ") + pd_create_error());
-    auto check = [&](int rc) { if (rc != 0) die(std::string("scan library: ") + pd_last_error(ctx)); };
-    check(pd_set_staging(ctx, 0));                                   // one-shot process: pageable staging (see include/popdel_b200.h)
-    if (!opt.windowWise && !dryRun) {                                // unifyCalls per segment, on the device
-        pd_unify_params up; memset(&up, 0, sizeof(up));
-        up.mean_stddev = meanStddev; up.min_relative_window_cover = opt.minCover; up.output_failed = opt.outputFailed;
-        check(pd_set_unify(ctx, &up));
+    // Window-range sharding (-g 0,1,...; SURVEY.md 8e, workflow_popdel.h:297-366): every context gets the read pairs of the
+    // contig and scans a contiguous range of whole segments (cuts at the reference's segment borders anchor + k * buffer, so
+    // every processSegment() group of calls -- and its unifyCalls -- lives on one device); the records are written in
+    // range order, which is the reference's order. No collective.
+    if (opt.devices.empty()) opt.devices.push_back(opt.device);
+    const size_t K = dryRun ? 1 : opt.devices.size();
+    std::vector<pd_ctx *> ctxs(K, nullptr);
+    for (size_t k = 0; k < K; ++k) {
+        ctxs[k] = pd_create(&prm, (uint32_t)N, (uint32_t)R, rgs.data(), dryRun ? opt.device : opt.devices[k]);
+        if (!ctxs[k]) die(std::string("cannot create the scan context: ") + pd_create_error());
+    }
+    pd_ctx * ctx = ctxs[0];
+    auto checkc = [&](pd_ctx * cx, int rc) { if (rc != 0) die(std::string("scan library: ") + pd_last_error(cx)); };
+    auto check = [&](int rc) { checkc(ctx, rc); };
+    for (size_t k = 0; k < K; ++k) {
+        checkc(ctxs[k], pd_set_staging(ctxs[k], 0));                 // one-shot process: pageable staging (see include/popdel_b200.h)
+        if (!opt.windowWise && !dryRun) {                            // unifyCalls per segment, on the device
+            pd_unify_params up; memset(&up, 0, sizeof(up));
+            up.mean_stddev = meanStddev; up.min_relative_window_cover = opt.minCover; up.output_failed = opt.outputFailed;
+            checkc(ctxs[k], pd_set_unify(ctxs[k], &up));
+        }
     }
 
     std::ofstream out(opt.out);
@@ -730,7 +751,7 @@ int main(int argc, char ** argv)
         }
         if (found && (int64_t)anchor >= roi.end) found = false;       // nothing inside the region (adaptRegions :218-236)
         if (!found) continue;
-        check(pd_contig_begin(ctx, anchor));
+        for (size_t k = 0; k < K; ++k) checkc(ctxs[k], pd_contig_begin(ctxs[k], anchor));
         tm.lap("create");
 
         // segment loader: which read pairs does the reference load in which iteration of its segment loop
@@ -815,21 +836,47 @@ int main(int argc, char ** argv)
             }
         {   // the add() loop of every read group (active-coverage cap + packing), one read group per task
             std::atomic<int> bad{0};
-            parallelFor(R, [&](size_t g) {
-                if (pd_contig_push(ctx, (uint32_t)g, rgOut[g].n, rgOut[g].pos, rgOut[g].dev) != 0) bad = 1;
-                free(rgOut[g].pos); free(rgOut[g].dev);
+            parallelFor(R * K, [&](size_t t) {
+                const size_t g = t % R, k = t / R;
+                if (pd_contig_push(ctxs[k], (uint32_t)g, rgOut[g].n, rgOut[g].pos, rgOut[g].dev) != 0) bad = 1;
             });
-            if (bad) check(-1);
+            for (size_t g = 0; g < R; ++g) { free(rgOut[g].pos); free(rgOut[g].dev); }
+            if (bad) {
+                for (size_t k = 0; k < K; ++k) if (pd_last_error(ctxs[k])[0]) checkc(ctxs[k], -1);
+                die("scan library: pd_contig_push failed");
+            }
         }
         tm.lap("push");
 
-        pd_result res; memset(&res, 0, sizeof(res));
-        if (!dryRun) check(pd_contig_scan(ctx, 0, 0, &res));
-        totalWindows += res.n_windows;
+        std::vector<pd_result> results(K);
+        for (auto & r : results) memset(&r, 0, sizeof(r));
+        if (!dryRun) {
+            if (K == 1) check(pd_contig_scan(ctx, 0, 0, &results[0]));
+            else {
+                uint64_t nWin = 0;
+                check(pd_contig_window_count(ctx, &nWin));
+                // ranges of whole segments: segment j = windows with anchor-relative position in [j * buffer, (j + 1) * buffer)
+                const uint64_t nSeg = nWin ? (30 * (nWin - 1)) / WB + 1 : 0;
+                auto segFirst = [&](uint64_t j) -> uint64_t { return j == 0 ? 0 : ((uint64_t)j * WB - 1) / 30 + 1; };
+                std::vector<std::thread> th;
+                std::vector<int> rcs(K, 0);
+                for (size_t k = 0; k < K; ++k) {
+                    const uint64_t s0 = nSeg * k / K, s1 = nSeg * (k + 1) / K;
+                    const uint64_t w0 = std::min(segFirst(s0), nWin), w1 = s1 >= nSeg ? nWin : std::min(segFirst(s1), nWin);
+                    if (s1 <= s0 || w1 <= w0) continue;
+                    th.emplace_back([&, k, w0, w1] { rcs[k] = pd_contig_scan(ctxs[k], w0, w1 - w0, &results[k]); });
+                }
+                for (auto & t : th) t.join();
+                for (size_t k = 0; k < K; ++k) checkc(ctxs[k], rcs[k]);
+            }
+        }
+        for (const auto & r : results) totalWindows += r.n_windows;
         tm.lap("scan");
         // window calls (-n) or the merged variants of every segment, already in output order; records are formatted on
         // all cores and written in order
         const std::string & chrom = profiles[0].contigNames[c];
+        for (size_t rk = 0; rk < K; ++rk) {
+        const pd_result & res = results[rk];
         std::vector<size_t> keep;
         for (size_t k = 0; k < res.n_calls; ++k) {
             const pd_call & pc = res.calls[k];
@@ -846,6 +893,7 @@ int main(int argc, char ** argv)
         });
         for (const std::string & t : text) out.write(t.data(), (std::streamsize)t.size());
         totalCalls += keep.size();
+        }
         out.flush();
         tm.lap("vcf");
     }

@@ -64,6 +64,20 @@ def test_window_wise_vcf_equals_reference(case, tmp_path):
     _compare(_lines(out), _lines(os.path.join(GOLDEN, case, "win.vcf.gz")))
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("devs", ["0,0", "0,0,0"])
+@pytest.mark.parametrize("case", ["basic", "gap", "twocontigs", "highcov"])
+def test_window_range_sharding_equals_reference(case, devs, tmp_path):
+    """-g D0,D1,...: one scan context and host thread per entry (here all on GPU 0), each scanning a contiguous range of
+    whole segments of every contig; the VCFs must still be the reference's (workflow_popdel.h:297-366 merge order)."""
+    out = str(tmp_path / "merged.vcf")
+    _run(case, ["-g", devs], out)
+    _compare(_lines(out), _lines(os.path.join(GOLDEN, case, "merged.vcf")))
+    out = str(tmp_path / "win.vcf")
+    _run(case, ["-n", "-g", devs], out)
+    _compare(_lines(out), _lines(os.path.join(GOLDEN, case, "win.vcf.gz")))
+
+
 def test_cli_fails_loudly_without_gpu(tmp_path):
     """No CPU fallback: on a box without a CUDA device the tool must stop with an error."""
     import torch

@@ -96,7 +96,8 @@ def test_many_samples(n_samples, contig_len, env, oracle_lib, monkeypatch):
 
 
 @pytest.mark.parametrize("env", [{"PD_FORCE_SLOW": "7"}, {"PD_JOB_BATCH": "64", "PD_CJOB_ROWS": "7"}, {"PD_CJOB_ROWS": "1", "PD_EM_CHUNK": "5"},
-                                 {"PD_EM_GENERAL": "1"}, {"PD_EM_V2": "1"}, {"PD_EM_V1": "1"}])
+                                 {"PD_EM_GENERAL": "1"}, {"PD_EM_V2": "1"}, {"PD_EM_V1": "1"}, {"PD_SCREEN2": "1"}, {"PD_SCREEN2": "0"},
+                                 {"PD_SCREEN2": "1", "PD_FORCE_SLOW": "7", "PD_JOB_BATCH": "64"}])
 @pytest.mark.parametrize("kind", ["basic", "mixedrg", "highcov"])
 def test_scan_generic_paths_and_batching(kind, env, oracle_lib, monkeypatch):
     """The generic (no shared memory) Q3 / pool paths, small job batches, candidate-job sub-batches and EM chunks, and
