@@ -140,6 +140,37 @@ def run_case(name):
     print(f"{name}: {len(paths)} profiles, {n} merged calls, {size / 1e6:.2f} MB")
 
 
+def run_big_case(name):
+    """BASELINE-sized cases (tests/bigcases.py): the profiles live in a scratch directory and are regenerated by the tests;
+    only the reference's outputs are committed."""
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import bigcases
+    d = os.path.join(HERE, name)
+    shutil.rmtree(d, ignore_errors=True)
+    os.makedirs(d)
+    tmp = tempfile.mkdtemp(prefix="popdel_golden_")
+    try:
+        paths = bigcases.profile_list(name, tmp)
+        quiet = dict(stdout=subprocess.DEVNULL, cwd=tmp)
+        subprocess.run([REF, "call", "profiles.txt", "-o", "merged.vcf"], check=True, **quiet)
+        subprocess.run([REF, "call", "profiles.txt", "-n", "-o", "win.vcf"], check=True, **quiet)
+        subprocess.run([HARNESS, "profiles.txt", "-o", "harness.vcf"], check=True, env=dict(os.environ, POPDEL_HARNESS_OUT="harness.dump"), **quiet)
+        shutil.copy(os.path.join(tmp, "merged.vcf"), os.path.join(d, "merged.vcf"))
+        for f in ("harness.dump", "win.vcf"):
+            with open(os.path.join(tmp, f), "rb") as src, gzip.GzipFile(os.path.join(d, f + ".gz"), "wb", mtime=0) as dst:
+                shutil.copyfileobj(src, dst)
+        with open(os.path.join(d, "args.txt"), "w") as fh:
+            fh.write("\n")
+        n = sum(1 for line in open(os.path.join(d, "merged.vcf")) if not line.startswith("#"))
+        size = sum(os.path.getsize(os.path.join(d, f)) for f in os.listdir(d))
+        print(f"{name}: {len(paths)} profiles (not committed), {n} merged calls, {size / 1e6:.2f} MB")
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+BIG_CASES = ["big100", "mixed200"]
+
 if __name__ == "__main__":
-    for c in (sys.argv[1:] or list(CASES)):
-        run_case(c)
+    for c in (sys.argv[1:] or list(CASES) + BIG_CASES):
+        run_big_case(c) if c in BIG_CASES else run_case(c)
