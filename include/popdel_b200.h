@@ -9,7 +9,9 @@
  * segment borders), pd_contig_push = the add() loop of one read group, pd_contig_scan = every processSegment() loop
  * of the contig (genotype_deletion_window for each 30-bp window). All functions return 0 on success or a negative
  * pd_status; no exception crosses the ABI; errors are sticky per context and described by pd_last_error().
- * Plain pointers and sizes only. One pd_ctx per GPU, driven by one host thread at a time.
+ * Plain pointers and sizes only. One pd_ctx per GPU, driven by one host thread at a time -- with one exception:
+ * pd_contig_push / pd_contig_push_pinned / pd_contig_push_compact may be called concurrently for DIFFERENT read groups of
+ * one context (the host packer of a read group touches only that read group's staging; errors are recorded under a lock).
  */
 #ifndef POPDEL_B200_H_
 #define POPDEL_B200_H_

@@ -334,7 +334,9 @@ class Scanner:
                     n_candidates=res.n_candidates, n_reads=res.n_reads, algorithmic_bytes=res.algorithmic_bytes,
                     h2d_bytes=res.h2d_bytes, d2h_bytes=res.d2h_bytes, n_kernel_launches=res.n_kernel_launches,
                     ms_h2d=res.ms_h2d, ms_screen=res.ms_screen, ms_genotype=res.ms_genotype, ms_total=res.ms_total,
-                    ms_stream=res.ms_stream)
+                    ms_stream=res.ms_stream, significant_windows=None, n_window_calls=res.n_window_calls, ms_unify=res.ms_unify,
+                    ms_em=res.ms_em, n_em_pairs_timed=res.n_em_pairs_timed, n_screened_windows=res.n_screened_windows,
+                    n_known_pairs=res.n_known_pairs)
 
     def attach_nccl(self, rank: int, world: int, samples_per_rank, min_init_global, unique_id: bytes):
         """Sample sharding, one process per GPU (pd_shard_attach_nccl; collective)."""
@@ -386,6 +388,26 @@ def compact_encode(pos: np.ndarray, dev: np.ndarray):
     return pos_lo, dev24, blk_first
 
 
+def _page_locked(a: np.ndarray) -> np.ndarray:
+    """A page-locked copy of `a` (torch pin_memory; the push_pinned / push_compact contract). Falls back to the array itself
+    when torch has no CUDA runtime (the copies are then staged by the driver: slower, same result)."""
+    try:
+        import torch
+        kinds = {np.dtype(np.uint32): np.int32, np.dtype(np.uint16): np.int16}
+        view = a.view(kinds.get(a.dtype, a.dtype))
+        t = torch.from_numpy(np.ascontiguousarray(view)).pin_memory()
+        out = t.numpy().view(a.dtype)
+        _page_locked.keep.append(t)
+        if len(_page_locked.keep) > 4096:
+            del _page_locked.keep[:2048]
+        return out
+    except Exception:
+        return a
+
+
+_page_locked.keep = []
+
+
 def cohort_anchor(samples) -> int:
     """First 30-bp window over all samples (getFirstWindowCoordinate, load_profile_popdel_call.h:291-350)."""
     first = [int(rg.pos[0]) for s in samples for rg in s.read_groups if rg.pos.size]
@@ -409,9 +431,10 @@ def scan_cohort(samples, params: CallParameters, device: int = 0, first_window: 
         for s in samples:
             for rg in s.read_groups:
                 if pinned == "compact":
-                    sc.push_compact(g, *compact_encode(rg.pos, rg.dev))
+                    sc.push_compact(g, *[_page_locked(a) for a in compact_encode(rg.pos, rg.dev)])
                 elif pinned:
-                    sc.push_pinned(g, np.ascontiguousarray(rg.pos, dtype=np.uint32), np.ascontiguousarray(rg.dev, dtype=np.int32))
+                    sc.push_pinned(g, _page_locked(np.ascontiguousarray(rg.pos, dtype=np.uint32)),
+                                   _page_locked(np.ascontiguousarray(rg.dev, dtype=np.int32)))
                 else:
                     sc.push(g, rg.pos, rg.dev)
                 g += 1

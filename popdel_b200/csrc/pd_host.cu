@@ -1,5 +1,6 @@
 // pd_host.cu -- host side of the scan library: context, histogram preprocessing, the push path with the
 // active-coverage cap, packing into the tiled 32-bit layout, upload, and the host-only validation hook.
+#include <mutex>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -14,9 +15,14 @@
 static std::string g_create_error;
 static void free_words(pd_ctx * c, PdHostRg & h);
 
+// (pd_contig_push may run concurrently for different read groups of one context: the first error wins, under a lock)
 int pd_fail(pd_ctx * c, int status, const std::string & msg)
 {
-    if (c && c->status == 0) { c->status = status; c->err = msg; }
+    static std::mutex mu;
+    if (c) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (c->status == 0) { c->err = msg; c->status = status; }
+    }
     return status;
 }
 

@@ -117,20 +117,26 @@ void inflateMembers(const std::vector<unsigned char> & in, size_t off, size_t en
 {
     z_stream zs; memset(&zs, 0, sizeof(zs));
     if (inflateInit2(&zs, 31) != Z_OK) die("zlib init failed");
+    // zlib counts its input in 32 bits: feed at most 1 GiB at a time
+    size_t fed = off;
     zs.next_in = const_cast<unsigned char *>(in.data() + off);
-    zs.avail_in = (uInt)(end - off);
+    zs.avail_in = 0;
     // inflate straight into `out` (grown geometrically, ~3.5x the compressed size is typical): no bounce buffer
     size_t have = out.size();
     out.resize(have + std::max<size_t>((end - off) * 4, 1u << 16));
-    while (zs.avail_in > 0) {
+    int rc = Z_STREAM_END;                                          // (an empty range is complete)
+    while (zs.avail_in > 0 || fed < end) {
+        if (zs.avail_in == 0) { const size_t n = std::min<size_t>(end - fed, 1u << 30); zs.avail_in = (uInt)n; fed += n; }
         if (have == out.size()) out.resize(out.size() + out.size() / 2);
         zs.next_out = out.data() + have; zs.avail_out = (uInt)std::min<size_t>(out.size() - have, 1u << 30);
         const size_t room = zs.avail_out;
-        int rc = inflate(&zs, Z_NO_FLUSH);
+        rc = inflate(&zs, Z_NO_FLUSH);
         have += room - zs.avail_out;
-        if (rc == Z_STREAM_END) { if (zs.avail_in == 0) break; inflateReset(&zs); }
+        if (rc == Z_STREAM_END) { if (zs.avail_in == 0 && fed == end) break; inflateReset(&zs); }
         else if (rc != Z_OK && !(rc == Z_BUF_ERROR && zs.avail_out == 0)) die("corrupt gzip block in profile");
     }
+    // the last member must have ended: a profile cut off inside a gzip member would otherwise lose read pairs silently
+    if (rc != Z_STREAM_END) die("truncated gzip member in profile");
     out.resize(have);
     inflateEnd(&zs);
 }
@@ -568,6 +574,7 @@ int main(int argc, char ** argv)
             opt.files = listed;
         }
     }
+    if (opt.files.empty()) die("no profiles given (the list file is empty)");
     const size_t N = opt.files.size();
     std::vector<Profile> & profiles = *new std::vector<Profile>(N);  // never destroyed: the process exits right after the output is written
     StageTimer tm;

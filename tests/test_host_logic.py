@@ -251,3 +251,21 @@ def test_cli_region_syntax_and_merging(tmp_path):
     assert pushed(["-r", "chrC"]) == []                                                  # a contig without read pairs
     r = subprocess.run([cli, "profiles.txt", "-g", "-1", "-o", str(tmp_path / "dry.vcf"), "-r", "chrA:12x-40"], cwd=case, capture_output=True, text=True)
     assert r.returncode != 0 and "parsing genomic region" in r.stderr
+
+
+def test_cli_rejects_truncated_and_empty_inputs(tmp_path):
+    """A profile cut off inside a gzip member must stop the shell (it used to lose read pairs silently), and so must an
+    empty profile list (dry run: -g -1 needs no GPU)."""
+    import subprocess
+    cli = os.path.join(ROOT, "popdel_b200", "popdel_b200_call")
+    src = os.path.join(ROOT, "tests", "golden", "basic", "sample00000.profile")
+    data = open(src, "rb").read()
+    cut = tmp_path / "cut.profile"
+    cut.write_bytes(data[:len(data) // 2])
+    lst = tmp_path / "list.txt"
+    lst.write_text(str(cut) + "\n")
+    r = subprocess.run([cli, str(lst), "-g", "-1", "-o", str(tmp_path / "x.vcf")], capture_output=True, text=True)
+    assert r.returncode != 0 and "truncated" in r.stderr
+    lst.write_text("\n")
+    r = subprocess.run([cli, str(lst), "-g", "-1", "-o", str(tmp_path / "x.vcf")], capture_output=True, text=True)
+    assert r.returncode != 0 and "no profiles" in r.stderr
