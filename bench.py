@@ -7,9 +7,10 @@
 Workload (BASELINE.json configs[1]): 100 synthetic profiles, chr21 (46,709,983 bp -> 1.56e6 windows of 30 bp), one
 read group each (30x, 2x150 bp, insert ~ N(500, 50^2)), planted deletions; per GPU one such window range (weak
 scaling over contiguous window ranges, no data-path collective). A step = one pass of the scan over the range.
-  value : evaluations/s with the packed read pairs already resident in HBM: all kernels of the scan + result copy-back
-          (every window call with its per-sample row, 50 MB per chr21 step); `other_output` = the same with the
-          segment-level merge on the device (pd_set_unify), only merged variants cross PCIe
+  value : evaluations/s with the packed read pairs already resident in HBM: all kernels of the scan incl. the
+          segment-level merge on the device (pd_set_unify, the product's default: `popdel call` writes merged variants)
+          + result copy-back; `other_output` = the same returning every window call with its per-sample row (50 MB
+          per chr21 step over PCIe)
   e2e   : evaluations/s through the C ABI from host arrays: push + H2D + device packing + scan + D2H
   roofline : the WHOLE scan: SURVEY.md 8d's 20 B per evaluation x evaluations per step / device time of a step
              (CUDA events on the library's stream); `k_stream` = the HBM-bound screen kernel on its own
@@ -168,6 +169,35 @@ def e2e_files(args):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Runs this rank (and therefore its page-locked buffers, first-touch) on the CPUs of the NUMA node its GPU hangs off:
+    at 8 ranks per box the host->device copies of the e2e step otherwise cross the socket interconnect. Best effort."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        if bus is None:
+            out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=20).stdout.strip()
+            bus = out[-12:] if len(out) >= 12 else out           # 00000000:1B:00.0 -> 0000:1b:00.0
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return {"node": node, "cpus": len(allowed)}
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     def __init__(self, dev):
         self.dev, self.proc, self.lines = dev, None, []
@@ -228,7 +258,8 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
-    threads = max(1, (os.cpu_count() or 8) // max(world, 1))
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
+    threads = max(1, min(len(os.sched_getaffinity(0)), (os.cpu_count() or 8) // max(world, 1)))
     N, L = args.samples, args.length
     t0 = time.time()
     # weak scaling over window ranges: every rank scans its own range; the ranges get the SAME synthetic content so that
@@ -277,10 +308,11 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- resident-input throughput. --output calls (default): pd_contig_scan's own product, every window call of every
-    # processSegment() with its per-sample row (the reference's String<Call> before unifyCalls) copied back; --output unify:
-    # the segment-level merge on the device (pd_set_unify), only merged variants cross PCIe. The other mode is timed as well
-    # (fewer steps) and reported beside it.
+    # ---- resident-input throughput. --output unify (default, the product's default: `popdel call` writes merged variants): the
+    # segment-level merge runs on the device (pd_set_unify), only merged variants cross PCIe; --output calls: every window call
+    # of every processSegment() with its per-sample row (the reference's String<Call> before unifyCalls) is copied back --
+    # 50 MB per chr21 step, 11 % faster on one GPU but 8 GPUs then push 80 GB/s into one host (measured r02: 67 % of linear
+    # at N=8 against 98 % with the merge on the device). The other mode is timed as well (fewer steps) and reported beside it.
     push_all()
     sc.upload()
     mean_sd = float(np.mean([r.as_dict()["stddev"] for r in rgs]))
@@ -457,7 +489,7 @@ def run_ours(args, rank, world, local_rank):
                          "bound": "L1TEX / LSU wavefronts of the likelihood-table gathers + fp64; not HBM, not tensor (profiles/r02)"},
                      "note": "achieved = SURVEY.md 8d's algorithmic bytes (20 B per sample x window evaluation) / device time of one step "
                              "(CUDA events on the library's stream around ALL kernels of the scan incl. the device-side merge)"},
-        "setup_s": {"generate": t_gen},
+        "setup_s": {"generate": t_gen}, "numa_binding_rank0": numa,
     }
     if world == 1 and not args.no_cpu_baseline:
         base, ref_calls, ref_ps = cpu_baseline(args, cohort, params, rgs)
@@ -670,7 +702,7 @@ def main():
     ap.add_argument("--cpu-slice", type=int, default=1_500_000)
     ap.add_argument("--ref-slice", type=int, default=24_000_000, help="bp of the workload the reference binary is timed on per step")
     ap.add_argument("--no-e2e-files", action="store_true")
-    ap.add_argument("--output", default="calls", choices=["calls", "unify"], help="what the timed scan returns (see run_ours)")
+    ap.add_argument("--output", default="unify", choices=["calls", "unify"], help="what the timed scan returns (see run_ours)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shard-samples", action="store_true", help="sample-sharded cohort over the ranks (config 5 style) instead of window ranges")
     ap.add_argument("--check", action="store_true", help="--shard-samples: compare the merged calls with the CPU oracle (small cohorts)")
