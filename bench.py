@@ -174,14 +174,13 @@ def bind_to_gpu_numa_node(local_rank):
     at 8 ranks per box the host->device copies of the e2e step otherwise cross the socket interconnect. Best effort."""
     try:
         import torch
-        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
-        if bus is None:
+        pr = torch.cuda.get_device_properties(local_rank)
+        if hasattr(pr, "pci_bus_id") and hasattr(pr, "pci_device_id"):
+            bus = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        else:
             out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
-                                 capture_output=True, text=True, timeout=20).stdout.strip()
-            bus = out[-12:] if len(out) >= 12 else out           # 00000000:1B:00.0 -> 0000:1b:00.0
-        bus = bus.lower()
-        if len(bus.split(":")[0]) == 8:
-            bus = bus[4:]
+                                 capture_output=True, text=True, timeout=20).stdout.strip().lower()
+            bus = out[4:] if len(out.split(":")[0]) == 8 else out          # 00000000:1b:00.0 -> 0000:1b:00.0
         node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
         if node < 0:
             return None
