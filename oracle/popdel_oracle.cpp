@@ -1147,6 +1147,30 @@ extern "C" double orc_process_histogram(double * values, uint32_t len, int32_t o
     return h.min_prob;
 }
 
+// Test hook: the stored / skipped decision of ChromosomeProfile::add (ref :1084-1113) for one read group's position-
+// sorted read pairs (start, end = start + max(0, inner distance), both relative to the position the tables were reset
+// to), with the end-table switches performSwitches (ref :1880-1893) applies at every segment border up to the read
+// pair's segment. stored[i] = 1 when read pair i entered the tables.
+extern "C" int orc_cap_replay(uint32_t window_buffer, uint32_t max_load, uint64_t n, const uint32_t * start, const uint32_t * end,
+                              uint8_t * stored)
+{
+    Profile pr;
+    pr.rg.resize(1);
+    pr.numWindows = window_buffer;
+    pr.rg[0].maxLoad = max_load;
+    pr.resetTo(0);
+    RgTab & t = pr.rg[0];
+    uint64_t seg = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t j = (uint64_t)(start[i] / 30 * 30) / window_buffer;
+        for (; seg < j; ++seg) { Profile::endSwitchWrite(t, window_buffer); Profile::endCorrectConsecutive(t); }
+        const size_t before = t.all.size();
+        pr.add(0, start[i], end[i], 0);
+        stored[i] = t.all.size() != before;
+    }
+    return 0;
+}
+
 extern "C" int64_t orc_scan_contig(const orc_params * p, uint32_t n_samples, uint32_t n_rg, const orc_rg * rgs,
                                    const uint64_t * rg_off, const uint32_t * pos, const int32_t * dev,
                                    uint32_t anchor, uint32_t last_pos,

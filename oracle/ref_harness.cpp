@@ -111,8 +111,46 @@ inline bool harness_genotype_deletion_window(String<Call> & calls,
 #undef unifyCalls
 #undef genotype_deletion_window
 
+// Replay mode (POPDEL_HARNESS_CAP_REPLAY=<input file>): drives the reference's own ChromosomeProfile::add for ONE read
+// group with the segment switches of performSwitches, and writes one byte per read pair (1 = stored) to the harness
+// output. Input: u32 windowBuffer, u32 maxLoad, u64 n, then n u32 start and n u32 end positions (sorted by start).
+static int capReplay(const char * inName, const char * outName)
+{
+    FILE * in = fopen(inName, "rb");
+    if (!in) return 2;
+    uint32_t hdr[2]; uint64_t n = 0;
+    if (fread(hdr, 4, 2, in) != 2 || fread(&n, 8, 1, in) != 1) return 2;
+    std::vector<uint32_t> start(n), end(n);
+    if (n && (fread(start.data(), 4, n, in) != n || fread(end.data(), 4, n, in) != n)) return 2;
+    fclose(in);
+    String<unsigned> maxLoad;
+    appendValue(maxLoad, hdr[1]);
+    ChromosomeProfile profile(1, maxLoad, hdr[0]);
+    profile.resetTo(0);
+    TReadGroupIndices rg;
+    appendValue(rg, 0u);
+    std::vector<unsigned char> stored(n);
+    uint64_t seg = 0;
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        const uint64_t j = (uint64_t)(start[i] / 30 * 30) / hdr[0];
+        for (; seg < j; ++seg)
+            performSwitches(profile, rg);
+        const unsigned before = profile.startProfiles[0].insertionCount;
+        profile.add(0, start[i], end[i], 0);
+        stored[i] = profile.startProfiles[0].insertionCount != before;
+    }
+    FILE * out = fopen(outName, "wb");
+    if (!out) return 2;
+    fwrite(stored.data(), 1, n, out);
+    fclose(out);
+    return 0;
+}
+
 int main(int argc, char const ** argv)
 {
+    if (getenv("POPDEL_HARNESS_CAP_REPLAY"))
+        return capReplay(getenv("POPDEL_HARNESS_CAP_REPLAY"), getenv("POPDEL_HARNESS_OUT") ? getenv("POPDEL_HARNESS_OUT") : "cap_replay.out");
     const char * outName = getenv("POPDEL_HARNESS_OUT");
     g_out = fopen(outName ? outName : "popdel_harness_dump.txt", "w");
     if (!g_out)

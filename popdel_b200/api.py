@@ -59,7 +59,7 @@ CALL_DTYPE = np.dtype([("initial_length", "<u4"), ("iterations", "<u4"), ("delet
 
 EXPORTS = ["pd_process_histogram", "pd_create", "pd_create_error", "pd_destroy", "pd_last_error", "pd_contig_begin",
            "pd_contig_push", "pd_contig_push_pinned", "pd_contig_push_compact", "pd_contig_upload", "pd_contig_scan", "pd_contig_window_count",
-           "pd_debug_host_window_sums", "pd_contig_reserve_windows", "pd_shard_unique_id", "pd_shard_attach_nccl",
+           "pd_debug_host_window_sums", "pd_debug_cap_replay", "pd_contig_reserve_windows", "pd_shard_unique_id", "pd_shard_attach_nccl",
            "pd_shard_attach_group", "pd_shard_group_scan", "pd_set_unify", "pd_device_warmup", "pd_set_staging"]
 
 _lib = None

@@ -4,6 +4,8 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -45,6 +47,89 @@ struct PdDev {
 };
 
 #define PD_CAP_RING 4096u
+// The active-coverage counter of ChromosomeProfile::add (profile_structure_popdel_call.h:1084-1113), exactly: the
+// reference counts stored read pairs minus the end entries a cursor has passed (getEndCount :870-928). The cursor walks
+// the per-segment end sets in order of last window, moves on to the next set lazily (the call that exhausts a set returns
+// before it looks into the next one), and correctConsecutiveSwitch (:722-737) zeroes the counter of a read group that sat
+// out a whole segment. Restated with a histogram of last windows per set instead of a sorted vector: within one call
+// every entry below the read pair's window is passed, so only the counts per set matter, not the order inside a set.
+// (The look-ahead branch of getEndCount cannot pass an entry: entries of the set after the write set end at or behind
+// the border of the segment being loaded.)
+struct PdCapState {
+    struct Set {
+        std::vector<uint32_t> ring;      // ring[lw % PD_CAP_RING] = entries with last window lw, kc <= lw < kc + PD_CAP_RING
+        std::vector<uint32_t> far;       // min-heap of last windows beyond the ring
+        uint64_t total = 0, passed = 0;  // entries added / passed by the cursor
+        uint64_t right = 0;              // right border of the set (bp, anchor-relative)
+        uint32_t kc = 0;                 // every entry with last window < kc has been passed
+    };
+    Set set[3];
+    int write_set = 0, pos_set = 0;      // writeSet, endPosSet
+    uint32_t load = 0;                   // activeLoad
+    int64_t seg = -1;                    // segment the write set belongs to
+
+    void clear_set(Set & s, uint64_t right, uint32_t wb)
+    {
+        if (s.ring.empty()) s.ring.assign(PD_CAP_RING, 0u);
+        else if (s.total != s.passed) std::fill(s.ring.begin(), s.ring.end(), 0u);
+        s.far.clear(); s.total = s.passed = 0; s.right = right; s.kc = (uint32_t)((right - wb) / PD_WIN);
+    }
+    void start(uint32_t wb)              // resetTo :1717-1748
+    {
+        for (int k = 0; k < 3; ++k) clear_set(set[k], (uint64_t)(k + 1) * wb, wb);
+        write_set = pos_set = 0; load = 0; seg = 0;
+    }
+    void next_segment(uint32_t wb)       // switchWriteSet :713-721 + correctConsecutiveSwitch :722-737
+    {
+        const int nxt = (write_set + 1) % 3, nn = (write_set + 2) % 3;
+        clear_set(set[nn], set[nxt].right + wb, wb);
+        write_set = nxt; ++seg;
+        if (pos_set != (write_set + 2) % 3) { pos_set = write_set; load = 0; }
+        else if (set[pos_set].total == 0) pos_set = write_set;
+    }
+    uint32_t end_count(uint32_t b)       // getEndCount :870-928 for a read pair of 30-bp bucket b
+    {
+        if (set[pos_set].passed == set[pos_set].total) {
+            if (pos_set == write_set) return 0;
+            pos_set = (pos_set + 1) % 3;
+        }
+        Set & s = set[pos_set];
+        if (s.total == 0) return 0;
+        uint32_t c = 0;
+        if (b > s.kc) {
+            if (s.passed + s.far.size() != s.total) {
+                const uint32_t lim = b - s.kc < PD_CAP_RING ? b : s.kc + PD_CAP_RING;
+                for (uint32_t k = s.kc; k != lim; ++k) { uint32_t & n = s.ring[k & (PD_CAP_RING - 1)]; c += n; n = 0; }
+            }
+            s.kc = b;
+            while (!s.far.empty() && s.far.front() < b) { std::pop_heap(s.far.begin(), s.far.end(), std::greater<uint32_t>()); s.far.pop_back(); ++c; }
+            s.passed += c;
+        }
+        if (c && s.passed == s.total && pos_set != write_set) pos_set = (pos_set + 1) % 3;
+        return c;
+    }
+    void insert(uint32_t lw)             // CyclicEndEntryTable::add :789-803
+    {
+        Set & s = set[(uint64_t)lw * PD_WIN >= set[write_set].right ? (write_set + 1) % 3 : write_set];
+        if (lw - s.kc < PD_CAP_RING) ++s.ring[lw & (PD_CAP_RING - 1)];
+        else { s.far.push_back(lw); std::push_heap(s.far.begin(), s.far.end(), std::greater<uint32_t>()); }
+        ++s.total;
+    }
+    // true: the read pair (bucket b, last window lw) is stored
+    bool admit(uint32_t b, uint32_t lw, uint32_t max_load)
+    {
+        if (load >= max_load) {
+            load -= end_count(b);
+            if (load >= max_load) return false;
+            insert(lw); ++load;
+        } else {
+            insert(lw); ++load;
+            load -= end_count(b);
+        }
+        return true;
+    }
+};
+
 struct PdHostRg {                    // host staging of one read group of the current contig (filled by pd_contig_push)
     uint32_t * words = nullptr;      // packed stream (pinned when the context has a device); tiles padded to 4 words
     size_t n_words = 0, cap_words = 0;
@@ -54,10 +139,7 @@ struct PdHostRg {                    // host staging of one read group of the cu
     uint32_t long_span = 0;
     uint32_t cur_tile = 0;           // tile being appended
     uint64_t n_reads = 0, dropped = 0;
-    // active-coverage cap state (ChromosomeProfile::add, profile_structure :1084-1113)
-    std::vector<uint32_t> ring;      // ring[lw % PD_CAP_RING] = stored read pairs whose last window is lw (lw >= ring_b)
-    std::vector<uint32_t> far;       // min-heap of last windows beyond the ring
-    uint32_t ring_b = 0, open = 0;   // open = stored read pairs with last window >= ring_b
+    PdCapState cap;                  // active-coverage cap (ChromosomeProfile::add, profile_structure :1084-1113)
     uint32_t last_pos = 0;
     bool any = false;
     // bookkeeping for the reference's last scanned window: per segment (current, previous)

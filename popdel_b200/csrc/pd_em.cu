@@ -729,11 +729,7 @@ __device__ __forceinline__ void em_one_body(const PdDev & a, const EmArgs & e, E
         // whose reference shift did not change has exactly the likelihoods and moments it already holds: skip the pass.
         // ... and so does any sample asked for exactly the (length, shift) it was last evaluated with.
         const bool same = e.sort_samples && curL != INT_MIN && dlS == curS &&
-#ifdef PD_AB_OLD_SAME
-                          (dmx < dlL - k.hist_base + 1 && dmx < curL - k.hist_base + 1);
-#else
                           (dlL == curL || (dmx < dlL - k.hist_base + 1 && dmx < curL - k.hist_base + 1));
-#endif
 #ifdef PD_EM_STATS
         const long long st_p = clock64();
         {

@@ -284,9 +284,8 @@ extern "C" int pd_contig_begin(pd_ctx * c, uint32_t anchor)
 }
 
 // The cap of ChromosomeProfile::add (profile_structure_popdel_call.h:1084-1113, getEndCount :870-928): a read pair is
-// stored iff fewer than max_load previously stored pairs of its read group are still open at its 30-bp bucket
-// (open = lastWindow >= bucket). The reference refreshes its counter lazily; the decision is the same except for the
-// single add that follows a segment switch while the cap is active (documented in DESIGN.md).
+// stored while the reference's activeLoad counter of its read group is below max_load (PdCapState, pd_context.h: the
+// counter with its lazy refresh at segment switches and the zeroing after a segment without read pairs).
 // Thread-compatible: may run concurrently for DIFFERENT read groups of one context.
 extern "C" int pd_contig_push(pd_ctx * c, uint32_t rg, uint64_t n, const uint32_t * pos, const int32_t * dev)
 {
@@ -308,9 +307,8 @@ extern "C" int pd_contig_push(pd_ctx * c, uint32_t rg, uint64_t n, const uint32_
     size_t nw = h.n_words, cap = h.cap_words;
     const int32_t inner_off = k.inner_off;
     const uint32_t lookback = k.lookback_tiles, max_load = k.max_load;
-    if (capped && h.ring.empty()) { h.ring.assign(PD_CAP_RING, 0u); h.ring_b = 0; h.open = 0; }
-    uint32_t * ring = capped ? h.ring.data() : nullptr;
-    uint32_t ring_b = h.ring_b, open = h.open, cur_tile = h.cur_tile, last_pos = h.last_pos;
+    PdCapState & cs = h.cap;
+    uint32_t cur_tile = h.cur_tile, last_pos = h.last_pos;
     int64_t S = h.S, E_own = h.E_own, E_spill = h.E_spill;
     uint64_t n_reads = h.n_reads, dropped = h.dropped;
     bool any = h.any;
@@ -328,17 +326,10 @@ extern "C" int pd_contig_push(pd_ctx * c, uint32_t rg, uint64_t n, const uint32_
         const uint64_t endp = (uint64_t)pr + (uint64_t)inner;
         const int64_t lw = endp < 0xFFFFFFFFull ? (int64_t)((uint32_t)endp / PD_WIN) : (int64_t)(endp / PD_WIN);
         if (capped) {
-            if (b - ring_b >= PD_CAP_RING) {                        // everything in the ring is closed
-                if (open != h.far.size()) std::fill(ring, ring + PD_CAP_RING, 0u);
-                open = (uint32_t)h.far.size(); ring_b = b;
-            }
-            while (ring_b < b) { uint32_t & c0 = ring[ring_b & (PD_CAP_RING - 1)]; open -= c0; c0 = 0; ++ring_b; }
-            while (!h.far.empty() && h.far.front() < b) { std::pop_heap(h.far.begin(), h.far.end(), std::greater<uint32_t>()); h.far.pop_back(); --open; }
-            if (open >= max_load) { ++dropped; continue; }
-            const uint32_t lwc = (uint32_t)std::min<int64_t>(lw, 0xFFFFFFFF);
-            if (lwc - b < PD_CAP_RING) ++ring[lwc & (PD_CAP_RING - 1)];
-            else { h.far.push_back(lwc); std::push_heap(h.far.begin(), h.far.end(), std::greater<uint32_t>()); }
-            ++open;
+            const int64_t j = (int64_t)((uint64_t)bp / wb);         // every segment switch up to this read pair's segment
+            if (cs.seg < 0) cs.start(wb);
+            while (cs.seg < j) cs.next_segment(wb);
+            if (!cs.admit(b, (uint32_t)std::min<int64_t>(lw, 0xFFFFFFFF), max_load)) { ++dropped; continue; }
         }
         if (bp >= seg_end_bp || h.seg < 0) {                        // first read pair of a new segment
             const int64_t j = (int64_t)((uint64_t)bp / wb);
@@ -375,7 +366,7 @@ extern "C" int pd_contig_push(pd_ctx * c, uint32_t rg, uint64_t n, const uint32_
         ++n_reads;
         if (nw > 0xFFFFFFF0ull) { rc = pd_fail(c, PD_ERR_CAPACITY, "more than 2^32 packed words in one read group"); break; }
     }
-    h.ring_b = ring_b; h.open = open; h.cur_tile = cur_tile; h.last_pos = last_pos; h.any = any;
+    h.cur_tile = cur_tile; h.last_pos = last_pos; h.any = any;
     h.S = S; h.E_own = E_own; h.E_spill = E_spill; h.n_reads = n_reads; h.dropped = dropped;
     if (rc) { h.n_words = nw; return rc; }
     h.n_words = nw;
@@ -612,6 +603,21 @@ extern "C" int pd_contig_scan(pd_ctx * c, uint64_t first_window, uint64_t n_wind
 // ---------------------------------------------------------------------------------------------------------
 // host-only validation hook: per-window sums from the PACKED image with the closed-form rule
 // ---------------------------------------------------------------------------------------------------------
+extern "C" int pd_debug_cap_replay(uint32_t window_buffer, uint32_t max_load, uint64_t n, const uint32_t * start,
+                                   const uint32_t * end, uint8_t * stored)
+{
+    if (!window_buffer || (n && (!start || !end || !stored))) return PD_ERR_ARG;
+    PdCapState cs;
+    cs.start(window_buffer);
+    for (uint64_t i = 0; i < n; ++i) {                              // the cap block of pd_contig_push
+        const uint32_t b = start[i] / PD_WIN;
+        const int64_t j = (int64_t)((uint64_t)b * PD_WIN / window_buffer);
+        while (cs.seg < j) cs.next_segment(window_buffer);
+        stored[i] = cs.admit(b, end[i] / PD_WIN, max_load);
+    }
+    return 0;
+}
+
 extern "C" int pd_debug_host_window_sums(pd_ctx * c, uint32_t rg, uint64_t first_window, uint64_t n_windows, int64_t * out)
 {
     if (!c || !out || rg >= c->R) return PD_ERR_ARG;

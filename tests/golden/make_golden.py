@@ -108,9 +108,29 @@ def case_offset(d):
     return pf.write_cohort(d, samples, ("chr5", 420_000)), {"args": ["-l", "150"]}
 
 
+def case_capfar(d):
+    """3 samples, 640 kbp; sample 0 carries three read pairs that span more than a segment (the cursor of getEndCount stays
+    inside their end set, so the activeLoad counter of that read group stops seeing read pairs that close in later sets) and
+    two 400x bursts in later segments that drive the stale counter to the cap; deletions inside and outside the bursts."""
+    dels = [sim.Deletion(120_000, 1100, np.array([1, 2, 1])), sim.Deletion(356_000, 900, np.array([2, 1, 0])),
+            sim.Deletion(470_000, 1500, np.array([1, 0, 2])), sim.Deletion(590_000, 700, np.array([1, 1, 1]))]
+    samples, _ = sim.simulate_cohort(seed=19, n_samples=3, contig_len=640_000, n_dels=0, dels=dels)
+    spec = sim.ReadGroupSpec(name="burst", coverage=400.0)
+    extra, _ = sim.simulate_cohort(seed=20, n_samples=1, contig_len=640_000, n_dels=0, rg_specs=[[spec]])
+    e = extra[0].read_groups[0]
+    m = ((e.pos >= 350_000) & (e.pos < 362_000)) | ((e.pos >= 520_000) & (e.pos < 528_000))
+    rg = samples[0].read_groups[0]
+    far_pos = np.array([150_003, 150_950, 188_000], dtype=rg.pos.dtype)
+    far_isz = np.array([262_000, 255_000, 420_000], dtype=rg.isize.dtype)
+    p, i = np.concatenate([rg.pos, e.pos[m], far_pos]), np.concatenate([rg.isize, e.isize[m], far_isz])
+    o = np.lexsort((i, p))
+    rg.pos, rg.isize = p[o], i[o]
+    return pf.write_cohort(d, samples, ("chr7", 640_000)), {}
+
+
 CASES = dict(basic=case_basic, mixedrg=case_mixedrg, gap=case_gap, highcov=case_highcov,
-             twocontigs=case_twocontigs, offset=case_offset)
-WINDOW_DUMPS = {"basic", "gap", "highcov", "twocontigs", "mixedrg", "offset"}
+             twocontigs=case_twocontigs, offset=case_offset, capfar=case_capfar)
+WINDOW_DUMPS = {"basic", "gap", "highcov", "twocontigs", "mixedrg", "offset", "capfar"}
 
 
 def run_case(name):
@@ -169,8 +189,32 @@ def run_big_case(name):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def run_cap_replay():
+    """tests/golden/cap_replay.npz: which read pairs of tests/capcases.py's streams the reference's own
+    ChromosomeProfile::add stores (popdel_ref_harness in replay mode), bit-packed."""
+    import tempfile
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import capcases
+    out = {}
+    with tempfile.TemporaryDirectory(prefix="popdel_golden_") as tmp:
+        for seed in capcases.SEEDS:
+            max_load, start, end = capcases.cap_stream(seed)
+            inp, res = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
+            with open(inp, "wb") as fh:
+                fh.write(np.array([capcases.WINDOW_BUFFER, max_load], np.uint32).tobytes() + np.uint64(start.size).tobytes())
+                fh.write(start.tobytes() + end.tobytes())
+            subprocess.run([HARNESS], check=True, env=dict(os.environ, POPDEL_HARNESS_CAP_REPLAY=inp, POPDEL_HARNESS_OUT=res))
+            stored = np.fromfile(res, dtype=np.uint8)
+            assert stored.size == start.size
+            out[f"n{seed}"] = np.array([start.size, int(stored.sum())], np.int64)
+            out[f"stored{seed}"] = np.packbits(stored)
+            print(f"cap_replay seed {seed}: max_load {max_load}, {start.size} read pairs, {int(stored.sum())} stored")
+    np.savez_compressed(os.path.join(HERE, "cap_replay.npz"), **out)
+
+
 BIG_CASES = ["big100", "mixed200"]
 
 if __name__ == "__main__":
-    for c in (sys.argv[1:] or list(CASES) + BIG_CASES):
-        run_big_case(c) if c in BIG_CASES else run_case(c)
+    for c in (sys.argv[1:] or list(CASES) + BIG_CASES + ["cap_replay"]):
+        run_cap_replay() if c == "cap_replay" else run_big_case(c) if c in BIG_CASES else run_case(c)

@@ -79,6 +79,43 @@ def _cohort(kind):
         o = np.lexsort((i, p))
         rg.pos, rg.isize = p[o], i[o]
         return samples, api.CallParameters()
+    if kind in ("capborder", "capgap", "capspill"):
+        # the active-coverage cap across segment borders (borders at anchor + k * 200 000):
+        #  capborder: a 400x burst that runs over a border, so the first add() of the new segment happens with the cap active
+        #  capgap:    the read group then sits out one / two whole segments (correctConsecutiveSwitch zeroes the counter)
+        #  capspill:  the burst carries a large deletion right before the border (many spill-over end entries)
+        dels = [simulate.Deletion(198_500, 1200, np.array([2, 1]))] if kind == "capspill" else []
+        samples, _ = simulate.simulate_cohort(seed=27, n_samples=2, contig_len=1_030_000, n_dels=0, dels=dels)
+        spec = simulate.ReadGroupSpec(name="burst", coverage=400.0)
+        extra, _ = simulate.simulate_cohort(seed=28, n_samples=1, contig_len=1_030_000, n_dels=0, dels=dels[:1] and
+                                            [simulate.Deletion(198_500, 1200, np.array([2]))], rg_specs=[[spec]])
+        e = extra[0].read_groups[0]
+        m = ((e.pos >= 185_000) & (e.pos < 215_000)) | ((e.pos >= 399_000) & (e.pos < 401_500)) | ((e.pos >= 795_000) & (e.pos < 830_000))
+        rg = samples[0].read_groups[0]
+        keep = np.ones(rg.pos.size, bool)
+        if kind == "capgap":
+            keep &= ~((rg.pos >= 215_000) & (rg.pos < 399_000))            # only bursts in segments 1 and 2, nothing in segment 3
+            keep &= ~((rg.pos >= 401_500) & (rg.pos < 795_000))
+            m &= ~((e.pos >= 200_000) & (e.pos < 215_000)) | (e.pos >= 399_000)
+        p, i = np.concatenate([rg.pos[keep], e.pos[m]]), np.concatenate([rg.isize[keep], e.isize[m]])
+        o = np.lexsort((i, p))
+        rg.pos, rg.isize = p[o], i[o]
+        return samples, api.CallParameters()
+    if kind == "capfar":
+        # read pairs spanning more than a segment keep the cursor of getEndCount inside their end set, so the reference's
+        # activeLoad counter stops seeing the read pairs that close in the following sets and sticks at maxLoad
+        samples, _ = simulate.simulate_cohort(seed=29, n_samples=2, contig_len=700_000, n_dels=2)
+        spec = simulate.ReadGroupSpec(name="burst", coverage=400.0)
+        extra, _ = simulate.simulate_cohort(seed=30, n_samples=1, contig_len=700_000, n_dels=0, rg_specs=[[spec]])
+        e = extra[0].read_groups[0]
+        m = ((e.pos >= 350_000) & (e.pos < 365_000)) | ((e.pos >= 520_000) & (e.pos < 530_000))
+        rg = samples[0].read_groups[0]
+        far_pos = np.array([150_003, 150_950, 188_000], dtype=rg.pos.dtype)
+        far_isz = np.array([262_000, 255_000, 420_000], dtype=rg.isize.dtype)
+        p, i = np.concatenate([rg.pos, e.pos[m], far_pos]), np.concatenate([rg.isize, e.isize[m], far_isz])
+        o = np.lexsort((i, p))
+        rg.pos, rg.isize = p[o], i[o]
+        return samples, api.CallParameters()
     if kind == "longspan":
         # a large deletion (long read pairs in the wide list) crossing a segment border
         dels = [simulate.Deletion(196_000, 9000, np.array([1, 2, 1]))]
@@ -86,7 +123,7 @@ def _cohort(kind):
     raise KeyError(kind)
 
 
-@pytest.mark.parametrize("kind", ["basic", "mixedrg", "gap", "highcov", "longspan"])
+@pytest.mark.parametrize("kind", ["basic", "mixedrg", "gap", "highcov", "longspan", "capborder", "capgap", "capspill", "capfar"])
 def test_packed_layout_reproduces_active_sets(kind, oracle_lib):
     from parity import run_oracle
     samples, params = _cohort(kind)
@@ -114,6 +151,44 @@ def test_packed_layout_reproduces_active_sets(kind, oracle_lib):
     with pytest.raises(api.ScanError):
         sc.scan()                                                              # no CPU scan path
     sc.close()
+
+
+def test_active_coverage_cap_equals_reference(oracle_lib):
+    """ChromosomeProfile::add's stored / skipped decisions (profile_structure_popdel_call.h:1084-1113 with the lazily
+    refreshed counter of getEndCount :870-928 and the zeroing of correctConsecutiveSwitch :722-737): the library's
+    restatement (PdCapState, what pd_contig_push runs) and the oracle's, against what the reference's own ChromosomeProfile
+    stored for the same streams (tests/golden/cap_replay.npz, made by make_golden.py with oracle/_ref/popdel_ref_harness)."""
+    import ctypes as C
+    import capcases
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "cap_replay.npz"))
+    lib = api.load_library()
+    u32p, u8p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)
+    for fn in (lib.pd_debug_cap_replay, oracle_lib.lib.orc_cap_replay):
+        fn.restype, fn.argtypes = C.c_int, [C.c_uint32, C.c_uint32, C.c_uint64, u32p, u32p, u8p]
+    dropped_by_stale_counter = 0
+    for seed in capcases.SEEDS:
+        max_load, start, end = capcases.cap_stream(seed)
+        n, n_stored = (int(x) for x in gold[f"n{seed}"])
+        assert n == start.size
+        ref = np.unpackbits(gold[f"stored{seed}"])[:n]
+        assert int(ref.sum()) == n_stored
+        for name, fn in (("library", lib.pd_debug_cap_replay), ("oracle", oracle_lib.lib.orc_cap_replay)):
+            got = np.zeros(n, dtype=np.uint8)
+            assert fn(capcases.WINDOW_BUFFER, max_load, n, start.ctypes.data_as(u32p), end.ctypes.data_as(u32p), got.ctypes.data_as(u8p)) == 0
+            bad = np.nonzero(got != ref)[0]
+            assert bad.size == 0, f"{name}, seed {seed}: first difference at read pair {bad[0]} of {n} (start {start[bad[0]]})"
+        # how often the reference's counter disagrees with the true number of open read pairs (round 1's rule)
+        open_end, simple = [], np.zeros(n, dtype=np.uint8)
+        for i in range(n):
+            b = start[i] // 30
+            open_end = [e for e in open_end if e >= b]
+            if ref[i]:
+                simple[i] = len(open_end) < max_load
+                open_end.append(end[i] // 30)
+            else:
+                simple[i] = len(open_end) < max_load
+        dropped_by_stale_counter += int((simple != ref).sum())
+    assert dropped_by_stale_counter > 0          # the streams do exercise the lazy counter
 
 
 def _tiny_scanner(device):

@@ -13,7 +13,7 @@ BIN = os.path.join(ROOT, "integration", "_build", "popdel_call_gpu")
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["basic", "mixedrg", "gap", "highcov", "twocontigs", "offset"])
+@pytest.mark.parametrize("case", ["basic", "mixedrg", "gap", "highcov", "twocontigs", "offset", "capfar"])
 def test_reference_tu_with_gpu_scan_writes_the_reference_vcfs(case, tmp_path):
     if not os.path.exists(BIN):
         pytest.skip("integration/_build/popdel_call_gpu not built (needs /root/reference at build time)")

@@ -11,7 +11,7 @@ from test_host_logic import _cohort
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("kind", ["basic", "mixedrg", "gap", "highcov", "longspan"])
+@pytest.mark.parametrize("kind", ["basic", "mixedrg", "gap", "highcov", "longspan", "capspill", "capfar"])
 def test_scan_matches_oracle(kind, oracle_lib):
     samples, params = _cohort(kind)
     stats = compare_scan_with_oracle(samples, oracle_lib, params)
@@ -69,7 +69,7 @@ def test_larger_cohort(oracle_lib):
     assert stats["n_calls"] > 100
 
 
-@pytest.mark.parametrize("kind", ["basic", "mixedrg", "gap", "highcov", "longspan"])
+@pytest.mark.parametrize("kind", ["basic", "mixedrg", "gap", "highcov", "longspan", "capspill", "capfar"])
 def test_device_packer_equals_host_packer(kind):
     """pd_contig_push_pinned (device-side packing; host fallback when the coverage cap bites) == pd_contig_push."""
     samples, params = _cohort(kind)
