@@ -37,6 +37,7 @@ struct PdDev {
     const PdRgConst * rgc;           // [R]
     const uint32_t * sample_rg;      // [N+1] read groups of sample s = sample_rg[s] .. sample_rg[s+1]
     const PdTab * tab;               // likelihood tables of all read groups; entry hist_off-1+... see PdRgConst
+    const uint4 * tseg;              // [NT + 1] per tile {nb, wlA, wlB, wlC} of tile_seg (pd_common.h), built once per contig
     uint32_t NT;                     // tiles per read group
     uint32_t N, R;
     uint32_t window_buffer;
@@ -221,6 +222,7 @@ struct pd_ctx {
     // word -> tile index of the current upload (k_stream's slow path) and wide-list ranges per read group
     bool index_built = false;
     uint32_t * d_gran_off = nullptr, * d_gran_tile = nullptr, * d_long_off = nullptr; size_t cap_gran = 0;
+    uint4 * d_tseg = nullptr; size_t cap_tseg = 0;
     uint32_t max_rg_words = 0;
     size_t pool_cap = 0;                                       // active read-pair pool capacity (persists across scans)
     size_t e2_devt_cap = 0;                                    // lane-interleaved read-pair copies of pd_em2.cu (words)

@@ -47,6 +47,7 @@ struct JobArgs {
     unsigned long long * block_sums;                // scratch of the two-level scan
 };
 void pd_launch_gran_index(const PdDev & a, uint32_t * gran_tile, const uint32_t * gran_off, cudaStream_t st);
+void pd_launch_tile_segs(uint4 * out, uint32_t n, uint32_t window_buffer, cudaStream_t st);
 void pd_launch_screen(const PdDev & a, const ScreenArgs & s, uint32_t max_rg_words, cudaStream_t st, cudaEvent_t after_stream, uint64_t * launches);
 void pd_launch_tile_jobs(const JobArgs & j, cudaStream_t st, uint64_t * launches);
 
@@ -202,8 +203,14 @@ __device__ __forceinline__ void for_tile_batches(const PdDev & a, uint32_t g, co
     const uint32_t b2 = nt > 2 ? __shfl_sync(PD_FULL, mine.off, 2) : 0xFFFFFFFFu;
     const uint32_t b3 = nt > 3 ? __shfl_sync(PD_FULL, mine.off, 3) : 0xFFFFFFFFu;
     // the segment constants of the look-back tiles differ only in base_bp unless a segment border lies between them
-    const TileSeg ts_lo = tile_seg(t_lo, a.window_buffer), ts_hi = nt > 1 ? tile_seg(tile, a.window_buffer) : ts_lo;
-    const bool one_seg = ts_lo.nb == ts_hi.nb;
+    // (tile_seg costs ~100 instructions: one 32-bit and three 64-bit divisions; the per-tile table is one 16-byte load)
+    auto seg_of = [&](uint32_t t) {
+        const uint4 q = __ldg(a.tseg + t);
+        TileSeg s; s.base_bp = t * PD_TILE_BP; s.nb = q.x; s.wlA = (int32_t)q.y; s.wlB = (int32_t)q.z; s.wlC = (int32_t)q.w;
+        return s;
+    };
+    const TileSeg ts_hi = seg_of(tile);
+    const bool one_seg = nt == 1 || __ldg(&a.tseg[t_lo].x) == ts_hi.nb;
     uint32_t next = (r_lo + lane) < r_hi ? __ldg(a.words + r_lo + lane) : PD_PAD_WORD;
     for (uint32_t base = r_lo; base < r_hi; base += 32) {
         const uint32_t i = base + lane, word = next;
@@ -212,7 +219,7 @@ __device__ __forceinline__ void for_tile_batches(const PdDev & a, uint32_t g, co
         for (uint32_t j = 4; j < nt; ++j) kk += __shfl_sync(PD_FULL, mine.off, (int)j) <= i;
         TileSeg ts = ts_hi;
         if (one_seg) ts.base_bp = (t_lo + kk) * PD_TILE_BP;
-        else ts = tile_seg(t_lo + kk, a.window_buffer);
+        else ts = seg_of(t_lo + kk);
         int32_t s = 0, e = 0, dev = 0; uint32_t pr = 0;
         const bool valid = word_interval(word, ts, k.inner_off, s, e, dev, pr);
         f(valid, s, e, pr, dev);

@@ -51,9 +51,10 @@ constexpr int TQ_WARPS = 4;
 // carriers' spanning read pairs pile up and the slow path would dominate
 template <int TQ_ACT>
 struct alignas(16) WarpQ3 {
-    int32_t val[TQ_ACT][32];                                        // [slot][window]: deviations of the window's usable active pairs
-    uint32_t cnt[32];
+    int32_t val[32][TQ_ACT + 1];                                    // [window][slot]: deviations of the window's usable active pairs
+    uint32_t cnt[32];                                               // (odd row stride: a lane per window and a lane per slot both hit 32 banks)
 };
+constexpr int TQ_COOP_MAX = 10;                                     // up to this many windows of a (tile, sample): one window at a time, whole warp
 
 __device__ __forceinline__ void write_q3(const GatherArgs & ga, uint32_t N, uint32_t job, uint32_t smp, uint32_t cov, uint32_t n,
                                          int32_t q, int32_t mx)
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(TQ_WARPS * 32, MINB) k_tile_q3(PdDev a, Gather
                     const int w = __ffs(m) - 1;
                     m &= m - 1;
                     const uint32_t slot = atomicAdd(&sh.cnt[w], 1u);
-                    if (slot < (uint32_t)TQ_ACT) sh.val[slot][w] = dev;
+                    if (slot < (uint32_t)TQ_ACT) sh.val[w][slot] = dev;
                 }
             }
         });
@@ -172,11 +173,41 @@ __global__ void __launch_bounds__(TQ_WARPS * 32, MINB) k_tile_q3(PdDev a, Gather
     const uint32_t n = sh.cnt[lane];
     const uint32_t over = __ballot_sync(PD_FULL, flagged && n > (uint32_t)TQ_ACT);
     uint32_t slow_mask = slow ? wmask : over;
-    if (!slow && flagged && n <= (uint32_t)TQ_ACT) {
+    const uint32_t fast_mask = slow ? 0u : (wmask & ~over);
+    if (__popc(fast_mask) <= TQ_COOP_MAX) {
+        // Few windows (the second screen stage leaves 1-4 per tile): the warp takes them one at a time, a value (or two) per
+        // lane, and pulls the largest values off with warp-wide max reductions until it holds the two order statistics --
+        // Q3 sits in the top quarter, so that is n/4 + 1 reductions instead of a bisection that keeps one lane busy.
+        for (uint32_t fm = fast_mask; fm; fm &= fm - 1) {
+            const int w = __ffs(fm) - 1;
+            const uint32_t nw = __shfl_sync(PD_FULL, n, w), cw = __shfl_sync(PD_FULL, cov, w);
+            int32_t v0 = (uint32_t)lane < nw ? sh.val[w][lane] : INT_MIN, v1 = INT_MIN;
+            if (nw > 32u && (uint32_t)lane + 32u < nw) v1 = sh.val[w][lane + 32];
+            int32_t q = 0, mx = INT_MIN;
+            if (nw) {
+                uint32_t l, l2; double r;
+                q3_position(nw, l, l2, r);
+                const uint32_t t0 = nw - 1u - l, t1 = nw - 1u - l2;          // ranks from the top of v[l] >= ... and v[l2]
+                int32_t lo_v = 0, hi_v = 0;
+                const uint32_t steps = (cw >= 2u) ? t0 + 1u : 1u;
+                for (uint32_t it = 0; it < steps; ++it) {
+                    const int32_t cur = max(v0, v1);
+                    const int32_t m = __reduce_max_sync(PD_FULL, cur);
+                    if (it == 0) mx = m;
+                    if (it == t1) hi_v = m;
+                    if (it == t0) lo_v = m;
+                    const uint32_t b = __ballot_sync(PD_FULL, cur == m);
+                    if (lane == __ffs(b) - 1) { if (v0 == m) v0 = INT_MIN; else v1 = INT_MIN; }
+                }
+                if (cw >= 2u) q = q3_value(nw, r, lo_v, hi_v);
+            }
+            if (lane == w) write_q3(ga, a.N, my_job, smp, cov, n, q, mx);
+        }
+    } else if (flagged && n <= (uint32_t)TQ_ACT && !slow) {
         int32_t q = 0, mx = INT_MIN;
         if (cov >= 2u && n) {
             int32_t mn = INT_MAX;
-            for (uint32_t i = 0; i < n; ++i) { const int32_t v = sh.val[i][lane]; mn = min(mn, v); mx = max(mx, v); }
+            for (uint32_t i = 0; i < n; ++i) { const int32_t v = sh.val[lane][i]; mn = min(mn, v); mx = max(mx, v); }
             uint32_t l, l2; double r;
             q3_position(n, l, l2, r);
             int32_t lo_v = mx, hi_v = mx;
@@ -185,17 +216,17 @@ __global__ void __launch_bounds__(TQ_WARPS * 32, MINB) k_tile_q3(PdDev a, Gather
                 while (lo < hi) {                                        // smallest v with #{x <= v} >= l + 1
                     const int32_t mid = lo + (int32_t)(((uint32_t)hi - (uint32_t)lo) >> 1);
                     uint32_t c = 0;
-                    for (uint32_t i = 0; i < n; ++i) c += sh.val[i][lane] <= mid;
+                    for (uint32_t i = 0; i < n; ++i) c += sh.val[lane][i] <= mid;
                     if (c >= l + 1) hi = mid; else lo = mid + 1;
                 }
                 lo_v = lo;
                 uint32_t c = 0; int32_t above = INT_MAX;
-                for (uint32_t i = 0; i < n; ++i) { const int32_t v = sh.val[i][lane]; c += v <= lo_v; if (v > lo_v) above = min(above, v); }
+                for (uint32_t i = 0; i < n; ++i) { const int32_t v = sh.val[lane][i]; c += v <= lo_v; if (v > lo_v) above = min(above, v); }
                 hi_v = c >= l2 + 1 ? lo_v : above;
             }
             q = q3_value(n, r, lo_v, hi_v);
         } else if (n) {
-            for (uint32_t i = 0; i < n; ++i) mx = max(mx, sh.val[i][lane]);
+            for (uint32_t i = 0; i < n; ++i) mx = max(mx, sh.val[lane][i]);
         }
         write_q3(ga, a.N, my_job, smp, cov, n, q, mx);
     }

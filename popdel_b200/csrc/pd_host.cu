@@ -227,7 +227,7 @@ extern "C" void pd_destroy(pd_ctx * c)
         if (c->res_ps) cudaFreeHost(c->res_ps);
         if (c->res_calls) cudaFreeHost(c->res_calls);
         if (c->res_count) cudaFreeHost(c->res_count);
-        cudaFree(c->d_gran_off); cudaFree(c->d_gran_tile); cudaFree(c->d_long_off);
+        cudaFree(c->d_gran_off); cudaFree(c->d_gran_tile); cudaFree(c->d_long_off); cudaFree(c->d_tseg);
         for (auto & p : c->d_scratch) cudaFree(p);
         for (auto & p : c->d_pack) cudaFree(p);
         for (auto & ev : c->ev) if (ev) cudaEventDestroy(ev);

@@ -51,9 +51,17 @@ int pd_grow_scratch(pd_ctx * c, int slot, size_t bytes, void ** p)
 namespace {
 
 // word -> tile index and wide-list ranges of the current upload (built once per upload)
-int build_index(pd_ctx * c, const PdDev & a)
+int build_index(pd_ctx * c, PdDev & a)
 {
     const uint32_t R = c->R;
+    if ((size_t)c->NT + 1 > c->cap_tseg || !c->d_tseg) {
+        cudaFree(c->d_tseg); c->d_tseg = nullptr; c->cap_tseg = 0;
+        const size_t want = (size_t)c->NT + 1 + c->NT / 8;
+        PD_CUDA(c, cudaMalloc(&c->d_tseg, want * sizeof(uint4)));
+        c->cap_tseg = want;
+    }
+    pd_launch_tile_segs(c->d_tseg, c->NT + 1, a.window_buffer, c->stream);
+    a.tseg = c->d_tseg;
     std::vector<uint32_t> goff(R + 1, 0);
     uint32_t max_words = 0;
     for (uint32_t g = 0; g < R; ++g) {
@@ -159,6 +167,7 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
     a.t_known = screen2 ? std::max(c->t_min - s2gap, c->t_min / 2) : 0;
     a.t_mark = screen2 ? a.t_known : a.t_min;
     a.w_begin = (uint32_t)w_begin; a.w_end = (uint32_t)w_end;
+    a.tseg = c->d_tseg;
     if (!c->index_built && build_index(c, a)) return c->status;
 
     cudaStream_t st = c->stream, st2 = c->stream2;

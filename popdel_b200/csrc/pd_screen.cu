@@ -228,6 +228,21 @@ __global__ void __launch_bounds__(1024) k_tj_write(JobArgs j)
 
 }  // namespace
 
+namespace {
+__global__ void __launch_bounds__(256) k_tile_segs(uint4 * __restrict__ out, uint32_t n, uint32_t wb)
+{
+    const uint32_t t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= n) return;
+    const TileSeg s = tile_seg(t, wb);
+    out[t] = make_uint4(s.nb, (uint32_t)s.wlA, (uint32_t)s.wlB, (uint32_t)s.wlC);
+}
+}  // namespace
+
+void pd_launch_tile_segs(uint4 * out, uint32_t n, uint32_t window_buffer, cudaStream_t st)
+{
+    k_tile_segs<<<(n + 255) / 256, 256, 0, st>>>(out, n, window_buffer);
+}
+
 void pd_launch_gran_index(const PdDev & a, uint32_t * gran_tile, const uint32_t * gran_off, cudaStream_t st)
 {
     const uint64_t n = (uint64_t)a.NT * a.R;
