@@ -14,7 +14,8 @@
 
 struct PdLong { uint32_t s, e, pos_rel; int32_t dev; };      // wide entry of a long read pair (16 B)
 // tile table entry: first stream word of the tile and the range of wide-list entries that can be active in it
-struct PdTile { uint32_t off, long_lo, long_hi, pad; };
+// reach (filled on the device after the upload, k_tile_reach): far << 24 | first word of the tile that reaches the next tile
+struct PdTile { uint32_t off, long_lo, long_hi, reach; };
 // interleaved likelihood tables, one entry per histogram index (and one floor entry per read group)
 struct PdTab {
     // first 32 bytes = everything the EM loop touches (one sector, two 128-bit loads)

@@ -48,6 +48,7 @@ struct JobArgs {
 };
 void pd_launch_gran_index(const PdDev & a, uint32_t * gran_tile, const uint32_t * gran_off, cudaStream_t st);
 void pd_launch_tile_segs(uint4 * out, uint32_t n, uint32_t window_buffer, cudaStream_t st);
+void pd_launch_tile_reach(const PdDev & a, PdTile * tiles, cudaStream_t st);
 void pd_launch_screen(const PdDev & a, const ScreenArgs & s, uint32_t max_rg_words, cudaStream_t st, cudaEvent_t after_stream, uint64_t * launches);
 void pd_launch_tile_jobs(const JobArgs & j, cudaStream_t st, uint64_t * launches);
 
@@ -196,7 +197,14 @@ __device__ __forceinline__ void for_tile_batches(const PdDev & a, uint32_t g, co
     const uint32_t nt = tile - t_lo + 1;                              // <= PD_MAX_LOOKBACK_TILES + 1
     PdTile mine = PdTile{0xFFFFFFFFu, 0, 0, 0};
     if ((uint32_t)lane <= nt) mine = load_tile(&tl[t_lo + lane]);
-    const uint32_t r_lo = __shfl_sync(PD_FULL, mine.off, 0), r_hi = __shfl_sync(PD_FULL, mine.off, (int)nt);
+    // Only the tail of the look-back matters: tile t_lo + j is needed iff one of its read pairs reaches nt-1-j tiles ahead
+    // (PdTile::reach, k_tile_reach); of the tile right before `tile` only the words from the first one that reaches over.
+    const uint32_t ahead = nt - 1u - (uint32_t)lane;
+    const uint32_t needed = __ballot_sync(PD_FULL, (uint32_t)lane + 1u < nt && (mine.reach >> 24) >= ahead);
+    const int j_first = needed ? __ffs(needed) - 1 : (int)nt - 1;
+    uint32_t r_lo = __shfl_sync(PD_FULL, mine.off + (((uint32_t)lane + 2u == nt) ? (mine.reach & 0xFFFFFFu) : 0u), j_first);
+    const uint32_t r_hi = __shfl_sync(PD_FULL, mine.off, (int)nt);
+    r_lo &= ~3u;                                                      // keep the 128-bit alignment of the tile starts
     const uint32_t l_lo = __shfl_sync(PD_FULL, mine.long_lo, (int)nt - 1), l_hi = __shfl_sync(PD_FULL, mine.long_hi, (int)nt - 1);
     // borders 1..3 in registers (warp-uniform); 0xFFFFFFFF beyond the look-back
     const uint32_t b1 = nt > 1 ? __shfl_sync(PD_FULL, mine.off, 1) : 0xFFFFFFFFu;

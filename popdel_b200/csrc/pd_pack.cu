@@ -322,7 +322,7 @@ __global__ void k_tile_table(PackArgs a, WriteArgs w, const uint64_t * rg_longs)
     tl.off = (uint32_t)(w.word_base[g] + w.rel_off[id]);
     tl.long_lo = (uint32_t)(w.long_base[g] + lo);
     tl.long_hi = (uint32_t)(w.long_base[g] + hi_t);
-    tl.pad = 0;
+    tl.reach = 0;
     w.tiles[id] = tl;
 }
 
