@@ -10,7 +10,7 @@
  * of the contig (genotype_deletion_window for each 30-bp window). All functions return 0 on success or a negative
  * pd_status; no exception crosses the ABI; errors are sticky per context and described by pd_last_error().
  * Plain pointers and sizes only. One pd_ctx per GPU, driven by one host thread at a time -- with one exception:
- * pd_contig_push / pd_contig_push_pinned / pd_contig_push_compact may be called concurrently for DIFFERENT read groups of
+ * pd_contig_push / pd_contig_push_pinned / _compact / _device may be called concurrently for DIFFERENT read groups of
  * one context (the host packer of a read group touches only that read group's staging; errors are recorded under a lock).
  */
 #ifndef POPDEL_B200_H_
@@ -142,6 +142,13 @@ int pd_contig_push_pinned(pd_ctx * ctx, uint32_t rg, uint64_t n, const uint32_t 
  * returns, one call per read group and contig, identical results). */
 int pd_contig_push_compact(pd_ctx * ctx, uint32_t rg, uint64_t n, const uint16_t * pos_lo, const uint8_t * dev24,
                            uint32_t n_blocks, const uint32_t * blk_first);
+
+/* pd_contig_push_pinned for arrays that are ALREADY in the memory of the context's GPU (written there by a device-side
+ * profile decoder or generator): pos / dev are device pointers; nothing crosses PCIe, the arrays are packed where they
+ * are. Same rules (valid until the upload returns, one call per read group and contig, may be mixed with
+ * pd_contig_push_pinned / _compact for other read groups, identical results; if the active-coverage cap would drop a read
+ * pair the arrays are copied to the host once and re-packed by the sequential host path). */
+int pd_contig_push_device(pd_ctx * ctx, uint32_t rg, uint64_t n, const uint32_t * d_pos, const int32_t * d_dev);
 
 /* Packs what was pushed and copies it to the device (pinned staging, async on the context's stream). */
 int pd_contig_upload(pd_ctx * ctx);

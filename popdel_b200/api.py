@@ -58,7 +58,7 @@ CALL_DTYPE = np.dtype([("initial_length", "<u4"), ("iterations", "<u4"), ("delet
                        ("end_position", "<u4"), ("segment", "<u4")])
 
 EXPORTS = ["pd_process_histogram", "pd_create", "pd_create_error", "pd_destroy", "pd_last_error", "pd_contig_begin",
-           "pd_contig_push", "pd_contig_push_pinned", "pd_contig_push_compact", "pd_contig_upload", "pd_contig_scan", "pd_contig_window_count",
+           "pd_contig_push", "pd_contig_push_pinned", "pd_contig_push_compact", "pd_contig_push_device", "pd_contig_upload", "pd_contig_scan", "pd_contig_window_count",
            "pd_debug_host_window_sums", "pd_debug_cap_replay", "pd_contig_reserve_windows", "pd_shard_unique_id", "pd_shard_attach_nccl",
            "pd_shard_attach_group", "pd_shard_group_scan", "pd_set_unify", "pd_device_warmup", "pd_set_staging"]
 
@@ -91,6 +91,7 @@ def load_library(path: str = LIB_PATH):
     lib.pd_contig_begin.argtypes = [C.c_void_p, C.c_uint32]
     lib.pd_contig_push.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
     lib.pd_contig_push_pinned.argtypes = lib.pd_contig_push.argtypes
+    lib.pd_contig_push_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.pd_contig_push_compact.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint16), C.POINTER(C.c_uint8),
                                            C.c_uint32, C.POINTER(C.c_uint32)]
     lib.pd_contig_upload.argtypes = [C.c_void_p]
@@ -273,6 +274,11 @@ class Scanner:
                                                     dev24.ctypes.data_as(C.POINTER(C.c_uint8)), blk_first.size - 1,
                                                     blk_first.ctypes.data_as(C.POINTER(C.c_uint32))))
 
+    def push_device(self, rg: int, n: int, d_pos: int, d_dev: int):
+        """pd_contig_push_device: d_pos (uint32[n]) / d_dev (int32[n]) are DEVICE addresses on this scanner's GPU (e.g.
+        torch_tensor.data_ptr()) that stay valid and unchanged until upload()/scan() returns."""
+        self._check(self.lib.pd_contig_push_device(self.ctx, int(rg), int(n), C.c_void_p(int(d_pos) if n else 0), C.c_void_p(int(d_dev) if n else 0)))
+
     def upload(self):
         self._check(self.lib.pd_contig_upload(self.ctx))
 
@@ -375,6 +381,65 @@ def synth_read_group(seed: int, rg_index: int, mu: float, sigma: float, read_len
     return pos[:n], isz[:n]
 
 
+class PdSynthRg(C.Structure):
+    _fields_ = [("mu", C.c_double), ("sigma", C.c_double), ("pairs_per_bp", C.c_double), ("rg_index", C.c_uint32), ("sample", C.c_uint32),
+                ("read_length", C.c_uint32), ("median", C.c_uint32)]
+
+
+class SynthDevice:
+    """pdsynth_dev_* (libpdsynth_cuda.so, include/pdsynth.h): the counter-based generator on the GPU. generate() returns
+    (total, d_pos, d_dev, rg_start): device addresses of uint32 positions / int32 deviations owned by this object (valid until
+    the next generate()) and the host array of read-group offsets -- what Scanner.push_device takes."""
+
+    def __init__(self, device: int = 0):
+        path = os.path.join(_HERE, "libpdsynth_cuda.so")
+        if not os.path.exists(path):
+            raise ScanError(f"{path} not built (make -C popdel_b200/csrc)")
+        self.lib = C.CDLL(path)
+        self.lib.pdsynth_dev_create.restype = C.c_void_p
+        self.lib.pdsynth_dev_create.argtypes = [C.c_int]
+        self.lib.pdsynth_dev_destroy.argtypes = [C.c_void_p]
+        self.lib.pdsynth_dev_generate.restype = C.c_int64
+        self.lib.pdsynth_dev_generate.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(PdSynthRg), C.c_uint32, C.c_uint32, C.c_uint32,
+                                                  C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8), C.c_uint32,
+                                                  C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        self.h = self.lib.pdsynth_dev_create(int(device))
+        if not self.h:
+            raise ScanError("pdsynth_dev_create failed (no usable CUDA device)")
+
+    def close(self):
+        if self.h:
+            self.lib.pdsynth_dev_destroy(self.h)
+            self.h = None
+
+    def to_host(self, d_ptr: int, n: int, dtype) -> np.ndarray:
+        out = np.empty(n, dtype=dtype)
+        self.lib.pdsynth_dev_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        if self.lib.pdsynth_dev_copy_to_host(self.h, out.ctypes.data_as(C.c_void_p), C.c_void_p(d_ptr), out.nbytes) != 0:
+            raise ScanError("pdsynth_dev_copy_to_host failed")
+        return out
+
+    def generate(self, seed, specs, first_pos, end_pos, del_start=(), del_len=(), del_genotype=None, n_samples=1):
+        """specs: sequence of (sample, rg_index, mu, sigma, pairs_per_bp[, read_length]); del_genotype: uint8 [n_dels, n_samples]."""
+        arr = (PdSynthRg * len(specs))()
+        for i, sp in enumerate(specs):
+            s, g, mu, sd, dens = sp[:5]
+            arr[i] = PdSynthRg(float(mu), float(sd), float(dens), int(g), int(s), int(sp[5]) if len(sp) > 5 else 150, int(mu))
+        ds = np.ascontiguousarray(del_start, dtype=np.uint32)
+        dl = np.ascontiguousarray(del_len, dtype=np.uint32)
+        gt = np.ascontiguousarray(del_genotype if del_genotype is not None else np.zeros((ds.size, n_samples)), dtype=np.uint8)
+        assert gt.shape == (ds.size, n_samples) or ds.size == 0
+        rg_start = np.zeros(len(specs) + 1, dtype=np.uint64)
+        dp, dd = C.c_void_p(0), C.c_void_p(0)
+        n = self.lib.pdsynth_dev_generate(self.h, int(seed), len(specs), arr, int(first_pos), int(end_pos), ds.size,
+                                          ds.ctypes.data_as(C.POINTER(C.c_uint32)), dl.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                          gt.ctypes.data_as(C.POINTER(C.c_uint8)), int(n_samples), C.byref(dp), C.byref(dd),
+                                          rg_start.ctypes.data_as(C.POINTER(C.c_uint64)))
+        if n < 0:
+            raise ScanError(f"pdsynth_dev_generate failed ({n})")
+        return int(n), int(dp.value or 0), int(dd.value or 0), rg_start
+
+
 def compact_encode(pos: np.ndarray, dev: np.ndarray):
     """(pos uint32 sorted, dev int32) -> (pos_lo uint16, dev24 uint8[3n], blk_first uint32) of pd_contig_push_compact: what a
     profile decoder can emit directly (the file stores a u8 offset per 256-bp window and an i32 deviation)."""
@@ -428,9 +493,16 @@ def scan_cohort(samples, params: CallParameters, device: int = 0, first_window: 
             sc.set_unify(**unify)
         sc.begin_contig(cohort_anchor(samples))
         g = 0
+        keep = []
         for s in samples:
             for rg in s.read_groups:
-                if pinned == "compact":
+                if pinned == "device":                          # arrays already resident on the GPU (pd_contig_push_device)
+                    import torch
+                    dp = torch.from_numpy(np.ascontiguousarray(rg.pos, dtype=np.uint32).view(np.int32)).to(f"cuda:{device}")
+                    dd = torch.from_numpy(np.ascontiguousarray(rg.dev, dtype=np.int32)).to(f"cuda:{device}")
+                    keep.append((dp, dd))
+                    sc.push_device(g, dp.numel(), dp.data_ptr(), dd.data_ptr())
+                elif pinned == "compact":
                     sc.push_compact(g, *[_page_locked(a) for a in compact_encode(rg.pos, rg.dev)])
                 elif pinned:
                     sc.push_pinned(g, _page_locked(np.ascontiguousarray(rg.pos, dtype=np.uint32)),

@@ -159,6 +159,7 @@ struct PdShard;                      // sample sharding state (pd_shard.cu)
 struct PdRawRg {
     const uint32_t * pos = nullptr; const int32_t * dev = nullptr; uint64_t n = 0;
     const uint16_t * lo = nullptr; const uint8_t * d24 = nullptr; const uint32_t * blk = nullptr; uint32_t nblk = 0;
+    bool on_device = false;          // pos / dev are device pointers (pd_contig_push_device)
     bool compact() const { return lo != nullptr; }
 };
 
@@ -208,7 +209,7 @@ struct pd_ctx {
     PdShard * shard = nullptr;
     // scan scratch (grown on demand)
     void * d_scratch[80] = {}; size_t cap_scratch[80] = {};
-    void * d_pack[12] = {}; size_t cap_pack[12] = {};          // device packer scratch (raw arrays, tile firsts, ...)
+    void * d_pack[16] = {}; size_t cap_pack[16] = {};          // device packer scratch (raw arrays, tile firsts, ...)
     // results
     pd_call * res_calls = nullptr; size_t cap_res_calls = 0;   // page-locked, mapped: written by the device (k_emit_rows)
     uint32_t * res_ps = nullptr; size_t cap_res_ps = 0;        // page-locked, mapped

@@ -461,6 +461,20 @@ extern "C" int pd_contig_push_pinned(pd_ctx * c, uint32_t rg, uint64_t n, const 
     return 0;
 }
 
+extern "C" int pd_contig_push_device(pd_ctx * c, uint32_t rg, uint64_t n, const uint32_t * d_pos, const int32_t * d_dev)
+{
+    if (!c) return PD_ERR_ARG;
+    if (c->status) return c->status;
+    if (!c->contig_open || rg >= c->R || (n && (!d_pos || !d_dev))) return pd_fail(c, PD_ERR_ARG, "pd_contig_push_device: bad arguments or no open contig");
+    if (c->device < 0) return pd_fail(c, PD_ERR_CUDA, "pd_contig_push_device: host-only context");
+    if (c->host_mode || c->packed) return pd_fail(c, PD_ERR_ARG, "pd_contig_push_device: cannot be mixed with pd_contig_push / contig already packed");
+    if (c->raw[rg].n) return pd_fail(c, PD_ERR_ARG, "pd_contig_push_device: one call per read group and contig");
+    c->dev_mode = true;
+    PdRawRg r; r.pos = d_pos; r.dev = d_dev; r.n = n; r.on_device = true;
+    c->raw[rg] = r;
+    return 0;
+}
+
 extern "C" int pd_contig_push_compact(pd_ctx * c, uint32_t rg, uint64_t n, const uint16_t * pos_lo, const uint8_t * dev24,
                                       uint32_t n_blocks, const uint32_t * blk_first)
 {
@@ -529,6 +543,13 @@ extern "C" int pd_contig_upload(pd_ctx * c)
         c->raw_pos_dec.assign(c->R, {}); c->raw_dev_dec.assign(c->R, {});
         for (uint32_t g = 0; g < c->R; ++g) {
             PdRawRg r = c->raw[g];
+            if (r.on_device && r.n) {                              // device-resident arrays: one copy to the host
+                auto & P = c->raw_pos_dec[g]; auto & D = c->raw_dev_dec[g];
+                P.resize(r.n); D.resize(r.n);
+                PD_CUDA(c, cudaMemcpy(P.data(), r.pos, r.n * 4, cudaMemcpyDeviceToHost));
+                PD_CUDA(c, cudaMemcpy(D.data(), r.dev, r.n * 4, cudaMemcpyDeviceToHost));
+                r.pos = P.data(); r.dev = D.data();
+            }
             if (r.compact() && r.n) {                              // decode the compact arrays for the sequential packer
                 auto & P = c->raw_pos_dec[g]; auto & D = c->raw_dev_dec[g];
                 P.resize(r.n); D.resize(r.n);

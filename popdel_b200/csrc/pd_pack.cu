@@ -381,15 +381,55 @@ __global__ void __launch_bounds__(256) k_expand_compact(const uint16_t * __restr
     }
 }
 
-static uint64_t last_window_from_raw(pd_ctx * c)
+// device-resident read groups (pd_contig_push_device): first / last position per read group, and the tail statistics
+// last_window_from_raw takes from the host arrays
+__global__ void __launch_bounds__(256) k_first_last(const uint32_t * const * __restrict__ pos, const uint64_t * __restrict__ n, uint32_t R, uint32_t * __restrict__ out)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= R) return;
+    out[2 * g] = 0; out[2 * g + 1] = 0;
+    if (pos[g] && n[g]) { out[2 * g] = pos[g][0]; out[2 * g + 1] = pos[g][n[g] - 1]; }
+}
+// one block per read group: the read pairs of the last two segments (q >= start_km1) -> max S, E, E_spill (see last_window_from_raw)
+__global__ void __launch_bounds__(256) k_tail_stats(const uint32_t * const * __restrict__ pos, const int32_t * const * __restrict__ dev, const uint64_t * __restrict__ n,
+                                                    const PdRgConst * __restrict__ rgc, uint32_t anchor, long long start_kf, long long start_km1,
+                                                    long long wl_kf, long long wl_km1, long long * __restrict__ out)
+{
+    const uint32_t g = blockIdx.x;
+    const uint32_t * p = pos[g];
+    if (!p || !n[g]) return;
+    const int32_t * d = dev[g];
+    const uint64_t cnt = n[g];
+    uint64_t lo = 0, hi = cnt;                                       // first read pair with q >= start_km1 (positions are sorted)
+    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; const uint32_t pr = p[mid] - anchor; if ((long long)(pr - pr % PD_WIN) < start_km1) lo = mid + 1; else hi = mid; }
+    const int32_t io = rgc[g].inner_off;
+    long long S = -1, E = -1, Esp = -1;
+    for (uint64_t i = lo + threadIdx.x; i < cnt; i += blockDim.x) {
+        const uint32_t pr = p[i] - anchor;
+        const long long q = (long long)(pr - pr % PD_WIN);
+        long long inner = (long long)d[i] + io; if (inner < 0) inner = 0;
+        const long long lw = (long long)(((unsigned long long)pr + (unsigned long long)inner) / PD_WIN);
+        if (q >= start_kf) { S = max(S, (long long)pr); if (lw <= wl_kf) E = max(E, lw); else Esp = max(Esp, lw); }
+        else if (lw > wl_km1) E = max(E, lw);
+    }
+    if (S >= 0) atomicMax(&out[0], S);
+    if (E >= 0) atomicMax(&out[1], E);
+    if (Esp >= 0) atomicMax(&out[2], Esp);
+}
+
+static uint64_t last_window_from_raw(pd_ctx * c, const std::vector<uint32_t> & dev_first_last, int * rc)
 {
     const uint32_t wb = c->grid.window_buffer, anchor = c->grid.anchor;
     c->tail = PdTail();
     int64_t kf = -1;
+    bool any_dev = false;
     for (uint32_t g = 0; g < c->R; ++g) {
         const PdRawRg & r = c->raw[g];
         uint32_t bh = r.nblk ? r.nblk - 1 : 0;
-        if (r.n) kf = std::max<int64_t>(kf, (int64_t)((uint64_t)((raw_pos_at(r, r.n - 1, bh) - anchor) / PD_WIN) * PD_WIN / wb));
+        if (!r.n) continue;
+        any_dev = any_dev || r.on_device;
+        const uint32_t last = r.on_device ? dev_first_last[2 * g + 1] : raw_pos_at(r, r.n - 1, bh);
+        kf = std::max<int64_t>(kf, (int64_t)((uint64_t)((last - anchor) / PD_WIN) * PD_WIN / wb));
     }
     if (kf < 0) return 0;
     int64_t E = -1, S = -1, Esp = -1;
@@ -397,8 +437,22 @@ static uint64_t last_window_from_raw(pd_ctx * c)
     // instead of dividing per read pair (this loop walks the last two segments of every read group on the host)
     const int64_t start_kf = kf * (int64_t)wb, start_km1 = (kf - 1) * (int64_t)wb;
     const int64_t wl_kf = (int64_t)pd_seg_last_window((uint64_t)kf, wb), wl_km1 = kf > 0 ? (int64_t)pd_seg_last_window((uint64_t)(kf - 1), wb) : -1;
+    if (any_dev) {                                                  // device-resident read groups: reduced on the device
+        long long * d_out = reinterpret_cast<long long *>(c->d_pack[12]) + 0;
+        const uint32_t * const * d_ptrs = reinterpret_cast<const uint32_t * const *>(reinterpret_cast<char *>(c->d_pack[12]) + 64);
+        const int32_t * const * d_dptrs = reinterpret_cast<const int32_t * const *>(d_ptrs + c->R);
+        const uint64_t * d_n = reinterpret_cast<const uint64_t *>(d_dptrs + c->R);
+        long long init[3] = {-1, -1, -1}, got[3];
+        cudaError_t e = cudaMemcpyAsync(d_out, init, sizeof(init), cudaMemcpyHostToDevice, c->stream);
+        k_tail_stats<<<c->R, 256, 0, c->stream>>>(d_ptrs, d_dptrs, d_n, c->d_rgc, anchor, start_kf, start_km1, wl_kf, wl_km1, d_out);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(got, d_out, sizeof(got), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { *rc = pd_fail(c, PD_ERR_CUDA, std::string("pd_contig_push_device: ") + cudaGetErrorString(e)); return 0; }
+        S = got[0]; E = got[1]; Esp = got[2];
+    }
     for (uint32_t g = 0; g < c->R; ++g) {
         const PdRawRg & r = c->raw[g];
+        if (r.on_device) continue;
         const int32_t io = c->rgc[g].inner_off;
         uint32_t bh = r.nblk ? r.nblk - 1 : 0;
         for (uint64_t i = r.n; i-- > 0;) {
@@ -421,14 +475,33 @@ int pd_pack_on_device(pd_ctx * c)
     PD_CUDA(c, cudaSetDevice(c->device));
     const uint32_t R = c->R;
     std::vector<uint64_t> rg_start(R + 1, 0);
-    uint32_t max_pos_rel = 0; bool any = false, any_compact = false;
+    uint32_t max_pos_rel = 0; bool any = false, any_compact = false, any_device = false;
+    for (uint32_t g = 0; g < R; ++g) any_device = any_device || (c->raw[g].on_device && c->raw[g].n);
+    std::vector<uint32_t> dev_fl;
+    if (any_device) {                                               // slot 12: tail statistics | pos pointers | dev pointers | counts | first/last
+        char * d_meta;
+        if (grow_dev(c, 12, d_meta, 64 + (size_t)R * 32)) return c->status;
+        std::vector<const uint32_t *> hp(R, nullptr); std::vector<const int32_t *> hd(R, nullptr); std::vector<uint64_t> hn(R, 0);
+        for (uint32_t g = 0; g < R; ++g) if (c->raw[g].on_device) { hp[g] = c->raw[g].pos; hd[g] = c->raw[g].dev; hn[g] = c->raw[g].n; }
+        PD_CUDA(c, cudaMemcpyAsync(d_meta + 64, hp.data(), (size_t)R * 8, cudaMemcpyHostToDevice, c->stream));
+        PD_CUDA(c, cudaMemcpyAsync(d_meta + 64 + (size_t)R * 8, hd.data(), (size_t)R * 8, cudaMemcpyHostToDevice, c->stream));
+        PD_CUDA(c, cudaMemcpyAsync(d_meta + 64 + (size_t)R * 16, hn.data(), (size_t)R * 8, cudaMemcpyHostToDevice, c->stream));
+        uint32_t * d_fl = reinterpret_cast<uint32_t *>(d_meta + 64 + (size_t)R * 24);
+        k_first_last<<<(R + 255) / 256, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t * const *>(d_meta + 64),
+                                                             reinterpret_cast<const uint64_t *>(d_meta + 64 + (size_t)R * 16), R, d_fl);
+        dev_fl.resize((size_t)2 * R);
+        PD_CUDA(c, cudaMemcpyAsync(dev_fl.data(), d_fl, (size_t)R * 8, cudaMemcpyDeviceToHost, c->stream));
+        PD_CUDA(c, cudaStreamSynchronize(c->stream));               // (hp / hd / hn are host vectors read by the async copies)
+    }
     for (uint32_t g = 0; g < R; ++g) {
         const PdRawRg & r = c->raw[g];
         rg_start[g + 1] = rg_start[g] + r.n;
         if (r.n) {
             uint32_t b0 = 0, b1 = r.nblk ? r.nblk - 1 : 0;
-            if (raw_pos_at(r, 0, b0) < c->grid.anchor) return pd_fail(c, PD_ERR_ARG, "pd_contig_push_pinned: position before the contig anchor");
-            max_pos_rel = std::max(max_pos_rel, raw_pos_at(r, r.n - 1, b1) - c->grid.anchor); any = true;
+            const uint32_t first = r.on_device ? dev_fl[2 * g] : raw_pos_at(r, 0, b0), last = r.on_device ? dev_fl[2 * g + 1] : raw_pos_at(r, r.n - 1, b1);
+            if (first < c->grid.anchor) return pd_fail(c, PD_ERR_ARG, "pd_contig_push_pinned: position before the contig anchor");
+            if (last < c->grid.anchor) return pd_fail(c, PD_ERR_ARG, "pd_contig_push_device: position before the contig anchor");
+            max_pos_rel = std::max(max_pos_rel, last - c->grid.anchor); any = true;
         }
         any_compact = any_compact || r.compact();
     }
@@ -477,16 +550,19 @@ int pd_pack_on_device(pd_ctx * c)
                 h2d += r.n * 5 + ((size_t)r.nblk + 1) * 4;
                 continue;
             }
-            h2d += r.n * 8;
-            PD_CUDA(c, cudaMemcpyAsync(d_pos + rg_start[g], r.pos, r.n * 4, cudaMemcpyHostToDevice, cp));
-            PD_CUDA(c, cudaMemcpyAsync(d_dev + rg_start[g], r.dev, r.n * 4, cudaMemcpyHostToDevice, cp));
+            if (!r.on_device) h2d += r.n * 8;
+            const cudaMemcpyKind kind = r.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+            PD_CUDA(c, cudaMemcpyAsync(d_pos + rg_start[g], r.pos, r.n * 4, kind, cp));
+            PD_CUDA(c, cudaMemcpyAsync(d_dev + rg_start[g], r.dev, r.n * 4, kind, cp));
         }
         PD_CUDA(c, cudaEventRecord(c->ev_pack[k], cp));
         g_lo = g_hi;
         grp_lo[k + 1] = g_hi;
     }
 
-    c->n_windows_total = any ? last_window_from_raw(c) : 0;
+    int tail_rc = 0;
+    c->n_windows_total = any ? last_window_from_raw(c, dev_fl, &tail_rc) : 0;
+    if (tail_rc) return tail_rc;
     const uint32_t NT = (uint32_t)std::max<uint64_t>(std::max<uint64_t>((std::max(c->n_windows_total, c->min_windows) + PD_TILE_WINDOWS - 1) / PD_TILE_WINDOWS,
                                                                         any ? (uint64_t)max_pos_rel / PD_TILE_BP + 1 : 0), 1);
     c->NT = NT;

@@ -71,14 +71,57 @@ def test_larger_cohort(oracle_lib):
 
 @pytest.mark.parametrize("kind", ["basic", "mixedrg", "gap", "highcov", "longspan", "capspill", "capfar"])
 def test_device_packer_equals_host_packer(kind):
-    """pd_contig_push_pinned (device-side packing; host fallback when the coverage cap bites) == pd_contig_push."""
+    """pd_contig_push_pinned / _compact / _device (device-side packing; host fallback when the coverage cap bites) == pd_contig_push."""
     samples, params = _cohort(kind)
     a, _ = api.scan_cohort(samples, params)
-    for mode in (True, "compact"):              # raw page-locked arrays / 5 bytes per read pair (pd_contig_push_compact)
+    # raw page-locked arrays / 5 bytes per read pair (pd_contig_push_compact) / arrays already in device memory (pd_contig_push_device)
+    for mode in (True, "compact", "device"):
         b, _ = api.scan_cohort(samples, params, pinned=mode)
         assert a["n_windows"] == b["n_windows"] and a["n_flagged_windows"] == b["n_flagged_windows"]
         assert a["n_reads"] == b["n_reads"]
         assert_calls_equal(b["calls"], b["per_sample"], a["calls"], a["per_sample"], rtol=0)
+
+
+def test_device_generator_equals_host_generator_and_device_push():
+    """libpdsynth_cuda.so (the on-device generator for cohorts that do not fit the host) writes the same read
+    pairs as the host generator, and pd_contig_push_device packs them where they are: same calls as pd_contig_push."""
+    import bench
+    N, L, seed = 14, 420_000, 5
+    ds, dl, gt = bench.plant(seed, N, L, 12.0)
+    specs = bench.cohort_specs(seed, N, mixed=True)
+    gen = api.SynthDevice(0)
+    total, dp, dd, rg_start = gen.generate(seed, specs, 0, L, ds, dl, gt, N)
+    pos_all, dev_all = gen.to_host(dp, total, np.uint32), gen.to_host(dd, total, np.int32)
+    cohort, _ = bench.make_cohort(seed, N, L, 12.0, 4, mixed=True)
+    assert int(rg_start[-1]) == total == sum(c[0].size for c in cohort)
+    for g, c in enumerate(cohort):
+        a, b = int(rg_start[g]), int(rg_start[g + 1])
+        assert np.array_equal(pos_all[a:b], c[0]) and np.array_equal(dev_all[a:b], c[2]), f"read group {g}"
+    # a window range of the same cohort: [first_pos, end_pos) is reproducible on its own
+    t2, dp2, dd2, rs2 = gen.generate(seed, specs[:5], 120_000, 300_000, ds, dl, gt, N)
+    p2 = gen.to_host(dp2, t2, np.uint32)
+    for g in range(5):
+        ref = cohort[g][0][(cohort[g][0] >= 120_000) & (cohort[g][0] < 300_000)]
+        assert np.array_equal(p2[int(rs2[g]):int(rs2[g + 1])], ref)
+    total, dp, dd, rg_start = gen.generate(seed, specs, 0, L, ds, dl, gt, N)
+    params = api.CallParameters()
+    rgs = api.read_groups_from_headers([[c[3] for c in cohort if c[4] == s] for s in range(N)], params)
+    res = []
+    for mode in ("host", "device"):
+        sc = api.Scanner(params, rgs, N, device=0)
+        sc.begin_contig(0)
+        for g, c in enumerate(cohort):
+            if mode == "host":
+                sc.push(g, c[0], c[2])
+            else:
+                sc.push_device(g, int(rg_start[g + 1] - rg_start[g]), dp + 4 * int(rg_start[g]), dd + 4 * int(rg_start[g]))
+        res.append(sc.scan())
+        sc.close()
+    gen.close()
+    a, b = res
+    assert a["n_windows"] == b["n_windows"] and a["n_reads"] == b["n_reads"] and len(a["calls"]) > 20
+    assert_calls_equal(b["calls"], b["per_sample"], a["calls"], a["per_sample"], rtol=0)
+    assert b["h2d_bytes"] < a["h2d_bytes"] // 100                     # nothing but the tables crossed PCIe
 
 
 @pytest.mark.parametrize("n_samples,contig_len,env", [(150, 90_000, {}), (300, 70_000, {}), (150, 90_000, {"PD_EM_V2": "1"}),
