@@ -74,7 +74,7 @@ def cohort_specs(seed, n_samples, mixed=False):
     return specs
 
 
-def make_cohort(seed, n_samples, length, per_mbp, threads, mixed=False, sample_range=None):
+def make_cohort(seed, n_samples, length, per_mbp, threads, mixed=False, sample_range=None, gen_length=None):
     """Returns (list of read groups [pos, isize, dev, header, sample], deletions). One read group per sample, or with
     `mixed` 1-3 read groups per sample with mu in {350,450,550} and sigma in {30,50,80} (BASELINE.json configs[2]).
     sample_range = (s0, s1): only the read groups of these samples of the cohort are generated (sample sharding)."""
@@ -84,9 +84,12 @@ def make_cohort(seed, n_samples, length, per_mbp, threads, mixed=False, sample_r
     if sample_range is not None:
         specs = [sp for sp in specs if sample_range[0] <= sp[0] < sample_range[1]]
 
+    glen = length if gen_length is None else gen_length        # (deletions are planted for `length`; only [0, glen) is generated)
+    near = ds < glen + 40_000
+
     def one(spec):
         s, g, mu, sd, dens = spec
-        pos, isz = api.synth_read_group(seed, g, mu, sd, 150, dens, 0, length, ds, dl, gt[:, s])
+        pos, isz = api.synth_read_group(seed, g, mu, sd, 150, dens, 0, glen, ds[near], dl[near], gt[near, s])
         med = int(mu)
         lo, hi = max(1, int(np.floor(med - 3 * sd))), int(np.ceil(med + 3 * sd)) + 1
         sel = isz[(isz >= lo) & (isz < hi)]
@@ -543,7 +546,9 @@ def run_sample_sharded(args, rank, world, local_rank):
     N, L = args.samples, args.length
     spr = api.split_samples(N, world)
     s0 = sum(spr[:rank])
-    cohort, dels = make_cohort(args.seed, N, L, args.dels_per_mbp, threads, args.mixed, sample_range=(s0, s0 + spr[rank]))
+    # with --device-gen the host generator only makes a short sample per read group for the histograms of the headers
+    hdr_len = min(L, 300_000) if args.device_gen else L
+    cohort, dels = make_cohort(args.seed, N, L, args.dels_per_mbp, threads, args.mixed, sample_range=(s0, s0 + spr[rank]), gen_length=hdr_len)
     params = api.CallParameters()
     # call parameters of the WHOLE cohort (only sigma of the other ranks' read groups is needed)
     specs = cohort_specs(args.seed, N, args.mixed)
@@ -562,8 +567,17 @@ def run_sample_sharded(args, rank, world, local_rank):
     sc.attach_nccl(rank, world, spr, min_init, bytes(uid.cpu().numpy()))
     sc.begin_contig(0)
     sc.reserve_windows(L // 30 + 2)
-    with ThreadPoolExecutor(threads) as ex:
-        list(ex.map(lambda g: sc.push(g, cohort[g][0], cohort[g][2]), range(len(cohort))))
+    if args.device_gen:
+        assert not args.check, "--check compares with the CPU oracle on host arrays"
+        ds, dl, gt = dels
+        local = [(sp[0] - s0,) + tuple(sp[1:]) for sp in specs if s0 <= sp[0] < s0 + spr[rank]]
+        gen = api.SynthDevice(local_rank)
+        _, dp, dd, rs = gen.generate(args.seed, local, 0, L, ds, dl, np.ascontiguousarray(gt[:, s0:s0 + spr[rank]]), spr[rank])
+        for g in range(len(local)):
+            sc.push_device(g, int(rs[g + 1] - rs[g]), dp + 4 * int(rs[g]), dd + 4 * int(rs[g]))
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(lambda g: sc.push(g, cohort[g][0], cohort[g][2]), range(len(cohort))))
     sc.upload()
     res = sc.scan(copy=True)
     evals = int(res["n_windows"]) * N
@@ -706,6 +720,8 @@ def main():
     ap.add_argument("--shard-samples", action="store_true", help="sample-sharded cohort over the ranks (config 5 style) instead of window ranges")
     ap.add_argument("--check", action="store_true", help="--shard-samples: compare the merged calls with the CPU oracle (small cohorts)")
     ap.add_argument("--mixed", action="store_true", help="1-3 read groups per sample with mixed insert-size histograms")
+    ap.add_argument("--device-gen", action="store_true", help="--shard-samples: generate the read pairs on the GPU (libpdsynth_cuda.so) and hand them "
+                                                               "over with pd_contig_push_device (cohorts too large for the host generator)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

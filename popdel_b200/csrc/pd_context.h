@@ -14,7 +14,8 @@
 
 struct PdLong { uint32_t s, e, pos_rel; int32_t dev; };      // wide entry of a long read pair (16 B)
 // tile table entry: first stream word of the tile and the range of wide-list entries that can be active in it
-// reach (filled on the device after the upload, k_tile_reach): far << 24 | first word of the tile that reaches the next tile
+// reach (filled by the packers): far << 24 | first stream word of the tile (relative to off) whose read pair is active in a
+// later tile; far = how many tiles ahead the tile's stream read pairs reach at most. for_tile_batches skips the rest.
 struct PdTile { uint32_t off, long_lo, long_hi, reach; };
 // interleaved likelihood tables, one entry per histogram index (and one floor entry per read group)
 struct PdTab {
@@ -137,6 +138,7 @@ struct PdHostRg {                    // host staging of one read group of the cu
     size_t n_words = 0, cap_words = 0;
     bool words_pinned = false;
     std::vector<uint32_t> tile_rel;  // tile_rel[t] = first word of tile t (relative to this read group), size = tiles seen + 1
+    std::vector<uint32_t> tile_reach;// PdTile::reach of tile t (same indexing)
     std::vector<PdLong> longs;
     uint32_t long_span = 0;
     uint32_t cur_tile = 0;           // tile being appended

@@ -48,7 +48,6 @@ struct JobArgs {
 };
 void pd_launch_gran_index(const PdDev & a, uint32_t * gran_tile, const uint32_t * gran_off, cudaStream_t st);
 void pd_launch_tile_segs(uint4 * out, uint32_t n, uint32_t window_buffer, cudaStream_t st);
-void pd_launch_tile_reach(const PdDev & a, PdTile * tiles, cudaStream_t st);
 void pd_launch_screen(const PdDev & a, const ScreenArgs & s, uint32_t max_rg_words, cudaStream_t st, cudaEvent_t after_stream, uint64_t * launches);
 void pd_launch_tile_jobs(const JobArgs & j, cudaStream_t st, uint64_t * launches);
 
@@ -198,7 +197,7 @@ __device__ __forceinline__ void for_tile_batches(const PdDev & a, uint32_t g, co
     PdTile mine = PdTile{0xFFFFFFFFu, 0, 0, 0};
     if ((uint32_t)lane <= nt) mine = load_tile(&tl[t_lo + lane]);
     // Only the tail of the look-back matters: tile t_lo + j is needed iff one of its read pairs reaches nt-1-j tiles ahead
-    // (PdTile::reach, k_tile_reach); of the tile right before `tile` only the words from the first one that reaches over.
+    // (PdTile::reach, written by the packers); of the tile right before `tile` only the words from the first one that reaches over.
     const uint32_t ahead = nt - 1u - (uint32_t)lane;
     const uint32_t needed = __ballot_sync(PD_FULL, (uint32_t)lane + 1u < nt && (mine.reach >> 24) >= ahead);
     const int j_first = needed ? __ffs(needed) - 1 : (int)nt - 1;

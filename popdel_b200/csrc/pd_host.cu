@@ -274,7 +274,7 @@ extern "C" int pd_contig_begin(pd_ctx * c, uint32_t anchor)
         const bool pinned = h.words_pinned;
         h = PdHostRg();
         h.words = w; h.cap_words = cap; h.words_pinned = pinned;
-        h.tile_rel.assign(1, 0u);
+        h.tile_rel.assign(1, 0u); h.tile_reach.assign(1, 0xFFFFFFu);
     }
     for (auto & r : c->raw) r = PdRawRg();
     c->dev_mode = c->host_mode = false;
@@ -348,7 +348,7 @@ extern "C" int pd_contig_push(pd_ctx * c, uint32_t rg, uint64_t n, const uint32_
         const uint32_t t = b / PD_TILE_WINDOWS;
         if (t != cur_tile) {
             while (nw & 3) words[nw++] = PD_PAD_WORD;
-            while (cur_tile < t) { ++cur_tile; h.tile_rel.push_back((uint32_t)nw); }
+            while (cur_tile < t) { ++cur_tile; h.tile_rel.push_back((uint32_t)nw); h.tile_reach.push_back(0xFFFFFFu); }
         }
         bool is_long = d > PD_DEV_MAX || d < PD_DEV_MIN + 1;
         if (act && (uint64_t)e / PD_TILE_WINDOWS > (uint64_t)t + lookback) is_long = true;
@@ -357,6 +357,11 @@ extern "C" int pd_contig_push(pd_ctx * c, uint32_t rg, uint64_t n, const uint32_
             h.n_words = nw;
             if (!reserve_words(c, h, nw + (n - i) + (n - i) / 8 + 64)) { rc = pd_fail(c, PD_ERR_CUDA, "pd_contig_push: out of (pinned) host memory"); break; }
             words = h.words; cap = h.cap_words;
+        }
+        if (act && !is_long && (uint64_t)e / PD_TILE_WINDOWS > t) {   // PdTile::reach: first word / furthest tile reached by this tile's stream
+            uint32_t & tr = h.tile_reach[t];
+            const uint32_t far = (uint32_t)std::min<uint64_t>((uint64_t)e / PD_TILE_WINDOWS - t, 255), first = std::min<uint32_t>(tr & 0xFFFFFFu, (uint32_t)(nw - h.tile_rel[t]));
+            tr = (std::max(tr >> 24, far) << 24) | std::min(first, 0xFFFFFFu);
         }
         words[nw++] = pd_pack(dc, pr - t * PD_TILE_BP, is_long);
         if (is_long && act) {
@@ -429,6 +434,7 @@ int pd_pack_contig(pd_ctx * c)
         const size_t nl = h.longs.size();
         for (uint32_t t = 0; t <= NT; ++t) {
             tl[t].off = (uint32_t)(total + (t < seen ? h.tile_rel[t] : h.n_words));
+            tl[t].reach = t < h.tile_reach.size() ? h.tile_reach[t] : 0u;
             const uint64_t w0 = (uint64_t)t * PD_TILE_WINDOWS;
             while (hi < nl && h.longs[hi].s <= w0 + PD_TILE_WINDOWS - 1) ++hi;
             while (lo < hi && h.longs[lo].e < w0) ++lo;

@@ -186,6 +186,7 @@ struct WriteArgs {
     uint32_t * lcount;                                              // [R][NT+1] long read pairs per tile -> offsets
     const uint64_t * long_base;                                     // [R]
     uint32_t * pmax;                                                // prefix max of e over the wide list
+    uint32_t * reach;                                               // [R][NT+1] PdTile::reach (written by pass 0 of k_pack_tiles)
 };
 
 // one WARP per (read group, tile), lanes over the tile's read pairs (coalesced reads of the raw arrays, coalesced
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(256) k_pack_tiles(PackArgs a, WriteArgs w, int
     if (id >= per * a.ng) return;
     id += per * a.g0;
     const uint32_t g = (uint32_t)(id / per), t = (uint32_t)(id % per);
-    if (t >= a.NT) { if (pass == 0 && lane == 0) w.lcount[id] = 0; return; }
+    if (t >= a.NT) { if (pass == 0 && lane == 0) { w.lcount[id] = 0; w.reach[id] = 0xFFFFFFu; } return; }
     if (pass == 1 && w.lcount[id + 1] == w.lcount[id]) return;            // no wide entries in this tile (the usual case)
     const PdRgConst k = a.rgc[g];
     const uint32_t * tf = a.tfirst + (size_t)g * per;
@@ -207,11 +208,12 @@ __global__ void __launch_bounds__(256) k_pack_tiles(PackArgs a, WriteArgs w, int
     const uint32_t i0 = tf[t], i1 = tf[t + 1];
     uint32_t * out = w.words + w.word_base[g] + w.rel_off[id];
     PdLong * lout = pass == 1 ? w.longs + w.long_base[g] + w.lcount[id] : nullptr;
-    uint32_t nl = 0;
+    uint32_t nl = 0, far = 0, first = 0xFFFFFFu;
     for (uint32_t base = i0; base < i1; base += 32) {
         const uint32_t i = base + lane;
         bool lng = false;
         uint32_t pr = 0; int32_t dv = 0; int64_t s = 0, e = 0;
+        uint32_t ahead = 0;
         if (i < i1) {
             pr = __ldcs(p + i) - a.anchor;
             dv = __ldcs(d + i);
@@ -223,6 +225,12 @@ __global__ void __launch_bounds__(256) k_pack_tiles(PackArgs a, WriteArgs w, int
                 out[i - i0] = pd_pack(dc, pr - t * PD_TILE_BP, is_long);
             }
             lng = is_long && act;
+            if (act && !is_long && (uint64_t)e / PD_TILE_WINDOWS > t) ahead = (uint32_t)min((uint64_t)e / PD_TILE_WINDOWS - t, (uint64_t)255);
+        }
+        if (pass == 0) {
+            const uint32_t rm = __ballot_sync(0xFFFFFFFFu, ahead != 0);
+            if (rm && first == 0xFFFFFFu) first = min(base - i0 + (uint32_t)(__ffs(rm) - 1), 0xFFFFFFu);
+            far = max(far, ahead);
         }
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, lng);
         if (pass == 1 && lng) lout[nl + __popc(m & ((1u << lane) - 1u))] = PdLong{(uint32_t)s, (uint32_t)e, pr, dv};
@@ -232,6 +240,8 @@ __global__ void __launch_bounds__(256) k_pack_tiles(PackArgs a, WriteArgs w, int
         const uint32_t cnt = i1 - i0, padded = (cnt + 3u) & ~3u;
         if (cnt + lane < padded) out[cnt + lane] = PD_PAD_WORD;
         if (lane == 0) w.lcount[id] = nl;
+        for (int o = 16; o > 0; o >>= 1) far = max(far, __shfl_xor_sync(0xFFFFFFFFu, far, o));
+        if (lane == 0) w.reach[id] = (far << 24) | first;
     }
 }
 
@@ -322,7 +332,7 @@ __global__ void k_tile_table(PackArgs a, WriteArgs w, const uint64_t * rg_longs)
     tl.off = (uint32_t)(w.word_base[g] + w.rel_off[id]);
     tl.long_lo = (uint32_t)(w.long_base[g] + lo);
     tl.long_hi = (uint32_t)(w.long_base[g] + hi_t);
-    tl.reach = 0;
+    tl.reach = w.reach[id];
     w.tiles[id] = tl;
 }
 
@@ -610,6 +620,7 @@ int pd_pack_on_device(pd_ctx * c)
     WriteArgs w;
     w.words = c->d_words; w.tiles = nullptr; w.longs = nullptr; w.rel_off = d_rel; w.word_base = d_word_base;
     w.lcount = d_lcount; w.long_base = d_long_base; w.pmax = nullptr;
+    if (grow_dev(c, 13, w.reach, per * R)) return c->status;
     const uint32_t chunks = (NT + CAP_CHUNK_TILES - 1) / CAP_CHUNK_TILES;
 
     // ---- per copy group, as soon as its raw arrays have arrived: order / span check, tile search, coverage-cap check,

@@ -62,7 +62,6 @@ int build_index(pd_ctx * c, PdDev & a)
     }
     pd_launch_tile_segs(c->d_tseg, c->NT + 1, a.window_buffer, c->stream);
     a.tseg = c->d_tseg;
-    pd_launch_tile_reach(a, c->d_tiles, c->stream);
     std::vector<uint32_t> goff(R + 1, 0);
     uint32_t max_words = 0;
     for (uint32_t g = 0; g < R; ++g) {

@@ -243,42 +243,6 @@ void pd_launch_tile_segs(uint4 * out, uint32_t n, uint32_t window_buffer, cudaSt
     k_tile_segs<<<(n + 255) / 256, 256, 0, st>>>(out, n, window_buffer);
 }
 
-namespace {
-// Per (read group, tile): how far the tile's stream read pairs reach into later tiles, and the first word that reaches the
-// next tile at all -- PdTile::reach = far << 24 | first reaching word (relative to the tile's first word). The per-tile
-// kernels (for_tile_batches) then start at that word of the previous tile instead of streaming every look-back tile.
-__global__ void __launch_bounds__(256) k_tile_reach(PdDev a, PdTile * __restrict__ tiles)
-{
-    const int lane = threadIdx.x & 31;
-    const uint64_t id = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (id >= (uint64_t)a.NT * a.R) return;
-    const uint32_t g = (uint32_t)(id / a.NT), t = (uint32_t)(id % a.NT);
-    PdTile * tl = tiles + (size_t)g * (a.NT + 1);
-    const uint32_t o0 = tl[t].off, o1 = tl[t + 1].off;
-    const int32_t inner_off = a.rgc[g].inner_off;
-    const uint4 q = __ldg(a.tseg + t);
-    TileSeg ts; ts.base_bp = t * PD_TILE_BP; ts.nb = q.x; ts.wlA = (int32_t)q.y; ts.wlB = (int32_t)q.z; ts.wlC = (int32_t)q.w;
-    uint32_t first = o1 - o0, far = 0;
-    for (uint32_t base = o0; base < o1; base += 32) {
-        const uint32_t i = base + lane;
-        int32_t s2 = 0, e = 0, dev = 0; uint32_t pr = 0;
-        const bool valid = i < o1 && word_interval(__ldg(a.words + i), ts, inner_off, s2, e, dev, pr);
-        const uint32_t d = valid && (uint32_t)e / PD_TILE_WINDOWS > t ? (uint32_t)e / PD_TILE_WINDOWS - t : 0u;
-        const uint32_t m = __ballot_sync(PD_FULL, d != 0);
-        if (m && first == o1 - o0) first = base - o0 + (uint32_t)(__ffs(m) - 1);
-        far = max(far, d);
-    }
-    for (int o = 16; o > 0; o >>= 1) far = max(far, __shfl_xor_sync(PD_FULL, far, o));
-    if (lane == 0) tl[t].reach = (min(far, 255u) << 24) | min(first, 0xFFFFFFu);
-}
-}  // namespace
-
-void pd_launch_tile_reach(const PdDev & a, PdTile * tiles, cudaStream_t st)
-{
-    const uint64_t n = (uint64_t)a.NT * a.R;
-    if (n) k_tile_reach<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(a, tiles);
-}
-
 void pd_launch_gran_index(const PdDev & a, uint32_t * gran_tile, const uint32_t * gran_off, cudaStream_t st)
 {
     const uint64_t n = (uint64_t)a.NT * a.R;
