@@ -565,18 +565,18 @@ __global__ void __launch_bounds__(256) k_candidates(PdDev a, CandArgs ca, int mo
         if (threadIdx.x == 0 && mode == 0) ca.cand_cnt[job] = emit.nc;
         return;
     }
-    // ---- fallback: bitonic sort of the occupied power of two, then the reference's linear pass
+    // ---- fallback: bitonic sort, then the reference's linear pass. Every compare-exchange sorts ascending (the first step
+    // of a merge pairs i with its mirror image inside the block), so the padding up to the next power of two is virtual:
+    // a partner at or beyond nv stands for +infinity and never moves -- shared memory holds nv values, not a power of two.
     uint32_t np2 = 1; while (np2 < nv) np2 <<= 1;
-    for (uint32_t i = nv + threadIdx.x; i < np2; i += blockDim.x) sv[i] = INT_MAX;
-    __syncthreads();
     for (uint32_t k = 2; k <= np2; k <<= 1)
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = threadIdx.x; i < np2; i += blockDim.x) {
-                const uint32_t ixj = i ^ j;
-                if (ixj > i) {
-                    const int32_t x = sv[i], y = sv[ixj];
-                    const bool up = (i & k) == 0;
-                    if ((x > y) == up) { sv[i] = y; sv[ixj] = x; }
+            const uint32_t flip = (j == (k >> 1)) ? k - 1 : j;
+            for (uint32_t i = threadIdx.x; i < nv; i += blockDim.x) {
+                const uint32_t p = i ^ flip;
+                if (p > i && p < nv) {
+                    const int32_t x = sv[i], y = sv[p];
+                    if (x > y) { sv[i] = y; sv[p] = x; }
                 }
             }
             __syncthreads();

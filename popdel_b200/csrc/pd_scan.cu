@@ -236,8 +236,8 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
         PD_CUDA(c, cudaMemcpyAsync(h_wbase.data(), j.tj_wbase, (size_t)n_tj * 4, cudaMemcpyDeviceToHost, st));
         PD_CUDA(c, cudaStreamSynchronize(st));
     }
-    uint32_t npad = 1; while (npad < Ng) npad <<= 1;
-    if ((size_t)npad * 4 > 200 * 1024) return pd_fail(c, PD_ERR_CAPACITY, "more than 51200 samples per context: candidate sort does not fit shared memory (shard by sample)");
+    const uint32_t npad = (std::max<uint32_t>(Ng, 32) + 31u) & ~31u;   // Q3 of every sample of the cohort in shared memory (k_candidates)
+    if ((size_t)npad * 4 > 202 * 1024) return pd_fail(c, PD_ERR_CAPACITY, "more than 51 700 samples per cohort: the candidate step keeps one Q3 per sample in shared memory");
     const bool em2 = !sh && pd_em2_usable(c);                          // sample-major pipeline (pd_em2.cu)
     // (reads per pair are not known before the gather: budget 40 active read pairs per read group)
     const size_t pair_bytes = 48ull * Nb + 4ull * Rb + 2 * 52ull * Nb + 128 + (em2 ? pd_em2_pair_bytes(Rb, 40.0 * Rb) : 0);
