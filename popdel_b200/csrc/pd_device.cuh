@@ -21,7 +21,7 @@ constexpr uint32_t PD_GRAN = 1024;                  // words per warp in k_strea
 constexpr int PD_CAND_INLINE = 6;                   // candidate lengths kept inline per window job
 
 // device counters of one scan (uint32 each)
-enum { CNT_TJOBS = 0, CNT_JOBS = 1, CNT_PAIRS = 2, CNT_POOL = 3, CNT_CALLS = 4, CNT_CJOBS = 5, CNT_ERR = 6, CNT_ALIVE = 7, CNT_KNOWN = 8, CNT_N = 16 };
+enum { CNT_TJOBS = 0, CNT_JOBS = 1, CNT_PAIRS = 2, CNT_POOL = 3, CNT_CALLS = 4, CNT_CJOBS = 5, CNT_ERR = 6, CNT_ALIVE = 7, CNT_KNOWN = 8, CNT_KJOBS = 9, CNT_N = 16 };
 
 struct PdPair { uint32_t job; int32_t L0; };                         // (window job, initial deletion length)
 struct EmState { uint32_t len, it, alive, pad; double freq; double gt[3]; };   // handed from k_em to k_final
@@ -38,11 +38,14 @@ struct ScreenArgs {
     const uint32_t * long_off;          // [R+1] wide-list ranges per read group
     uint32_t total_longs;
     uint32_t * known;                   // second stage: [N][need_stride * 32] window bits per (sample, tile): Q3 can exceed t_known
+    uint2 * kjobs; uint32_t kjobs_cap;  // second stage: the (sample, tile) pairs that have such windows (counters[CNT_KJOBS] of them, any order)
+    uint32_t * counters;
 };
 struct JobArgs {
     const uint32_t * tile_flags; uint32_t n_tiles, tile_begin;
     uint32_t * tj_tile, * tj_mask, * tj_wbase;      // flagged tiles in ascending order, window mask, first window job
     uint32_t * job_window;                           // window of every window job (ascending)
+    uint32_t * tj_of_tile;                           // [n_tiles] tile job of a flagged tile (0xFFFFFFFF: none); may be null
     uint32_t * counters;
     unsigned long long * block_sums;                // scratch of the two-level scan
 };
@@ -69,6 +72,8 @@ struct GatherArgs {
     // t_known; 2 = the rest, for the windows the stage could not reject
     int phase;
     const uint32_t * known; uint32_t known_stride, tb_al;
+    const uint2 * kjobs; uint32_t n_kjobs;          // phase 1 walks this list of (sample, tile) instead of every (tile job, sample)
+    const uint32_t * tj_of_tile; uint32_t tile_begin;
     uint32_t * tj_alive;                // [ntj] windows of the tile job that survive the second stage
     uint8_t * job_dead;                 // [jobs] 1 = rejected by the second stage (no candidates possible)
 };

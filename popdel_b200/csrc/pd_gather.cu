@@ -115,15 +115,10 @@ __device__ __noinline__ void q3_window_slow(const PdDev & a, const GatherArgs & 
     if (lane == 0) write_q3(ga, a.N, job, smp, cov, n, q, mx);
 }
 
-template <int TQ_ACT, int MINB>
-__global__ void __launch_bounds__(TQ_WARPS * 32, MINB) k_tile_q3(PdDev a, GatherArgs ga)
+// one (tile job, sample): Q3 of the windows of the tile this launch handles for the sample
+template <int TQ_ACT>
+__device__ __forceinline__ void q3_tile_job(const PdDev & a, const GatherArgs & ga, WarpQ3<TQ_ACT> & sh, int lane, uint32_t smp, uint32_t tjb)
 {
-    __shared__ WarpQ3<TQ_ACT> sh_all[TQ_WARPS];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t smp = blockIdx.y * TQ_WARPS + wib;
-    if (smp >= a.N) return;
-    // (blocks walk several tile jobs: with the second screen stage most (tile job, sample) pairs have nothing to do)
-    for (uint32_t tjb = blockIdx.x; tjb < ga.ntj; tjb += gridDim.x) {
     const uint32_t tj = ga.tj0 + tjb;
     const uint32_t tile = ga.tj_tile[tj], jmask = ga.tj_mask[tj];        // jmask numbers the window jobs of the tile
     // windows this launch handles for this sample (second screen stage: first the pairs whose Q3 can exceed t_known, later the
@@ -132,12 +127,11 @@ __global__ void __launch_bounds__(TQ_WARPS * 32, MINB) k_tile_q3(PdDev a, Gather
     if (ga.phase) {
         const uint32_t kn = ga.known[(size_t)smp * ga.known_stride + (tile - ga.tb_al)];
         wmask = ga.phase == 1 ? (jmask & kn) : (jmask & ga.tj_alive[tjb] & ~kn);
-        if (wmask == 0) continue;
+        if (wmask == 0) return;
         if (ga.phase == 1 && lane == 0) atomicAdd(&ga.counters[CNT_KNOWN], (uint32_t)__popc(wmask));
     }
     const uint32_t job_first = ga.tj_wbase[tj] - ga.job_base;            // scratch row of the tile's first flagged window
     const uint32_t g0 = a.sample_rg[smp], g1 = a.sample_rg[smp + 1];
-    WarpQ3<TQ_ACT> & sh = sh_all[wib];
     const int32_t w0 = (int32_t)(tile * PD_TILE_WINDOWS);
     const uint32_t lane_bit = 1u << lane;
     const uint32_t my_job = job_first + __popc(jmask & (lane_bit - 1u));
@@ -236,7 +230,29 @@ __global__ void __launch_bounds__(TQ_WARPS * 32, MINB) k_tile_q3(PdDev a, Gather
         q3_window_slow(a, ga, smp, w0 + wl, job_first + __popc(jmask & ((1u << wl) - 1u)), lane);
     }
     __syncwarp();
+}
+
+template <int TQ_ACT, int MINB>
+__global__ void __launch_bounds__(TQ_WARPS * 32, MINB) k_tile_q3(PdDev a, GatherArgs ga)
+{
+    __shared__ WarpQ3<TQ_ACT> sh_all[TQ_WARPS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (ga.phase == 1 && ga.kjobs) {
+        // second screen stage, first pass: the (sample, tile) pairs k_count listed, one per warp. (One warp per sample and a
+        // loop over the tiles left three of a block's four warps idle wherever their samples' read groups sit far below the
+        // threshold: 25 % active warps, ncu.)
+        for (uint32_t i = (blockIdx.x + blockIdx.y * gridDim.x) * TQ_WARPS + wib; i < ga.n_kjobs; i += gridDim.x * gridDim.y * TQ_WARPS) {
+            const uint2 e = ga.kjobs[i];
+            const uint32_t tj = ga.tj_of_tile[e.y - ga.tile_begin];
+            if (tj == 0xFFFFFFFFu || tj < ga.tj0 || tj >= ga.tj0 + ga.ntj) continue;      // no flagged window in the tile / another batch
+            q3_tile_job<TQ_ACT>(a, ga, sh_all[wib], lane, e.x, tj - ga.tj0);
+        }
+        return;
     }
+    const uint32_t smp = blockIdx.y * TQ_WARPS + wib;
+    if (smp >= a.N) return;
+    // (blocks walk several tile jobs: with the second screen stage most (tile job, sample) pairs have nothing to do)
+    for (uint32_t tjb = blockIdx.x; tjb < ga.ntj; tjb += gridDim.x) q3_tile_job<TQ_ACT>(a, ga, sh_all[wib], lane, smp, tjb);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -645,6 +661,12 @@ void pd_launch_q3(const PdDev & a, const GatherArgs & g, cudaStream_t st, uint64
 {
     // (a 92-slot variant for the surviving windows of phase 2 was measured slower: 54.9 vs 49.9 ms per mixed 300 x 12 Mbp scan)
     const uint32_t gx = g.phase ? std::min<uint32_t>(g.ntj, 1024u) : g.ntj;
+    if (g.phase == 1 && g.kjobs) {                                   // a list of (sample, tile) pairs: persistent-style grid
+        const uint32_t nb = std::min<uint32_t>((g.n_kjobs + TQ_WARPS - 1) / TQ_WARPS, 148u * 9u * 8u);
+        if (nb) k_tile_q3<48, 9><<<dim3(nb, 1), TQ_WARPS * 32, 0, st>>>(a, g);
+        ++*launches;
+        return;
+    }
     k_tile_q3<48, 9><<<dim3(gx, (a.N + TQ_WARPS - 1) / TQ_WARPS), TQ_WARPS * 32, 0, st>>>(a, g);
     ++*launches;
 }

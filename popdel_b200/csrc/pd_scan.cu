@@ -20,7 +20,7 @@ enum Slot {                                     // d_scratch slots
     S_NEED = 0, S_TFLAGS, S_COUNTERS, S_TJ_TILE, S_TJ_MASK, S_TJ_WBASE, S_JOBWIN, S_BSUMS,
     S_ACT_OFF, S_ACT_CNT, S_Q3, S_SSTAT, S_CAND_CNT, S_CAND_INL, S_CAND_OFF, S_CJOB_OF, S_TJ_CMASK, S_TJ_CFIRST, S_PAIRS, S_POOL_POS, S_POOL_DEV,
     S_DLX, S_DLE, S_SHIFTS, S_STATES, S_PS0, S_PS1, S_CALLS0, S_CALLS1, S_VALID0, S_VALID1, S_DONE0, S_DONE1, S_CHUNK_BASE, S_DBG, S_DMAX, S_ALL_Q3, S_ALL_SS,
-    S_KNOWN = 64, S_TJ_ALIVE, S_JOB_DEAD
+    S_KNOWN = 64, S_TJ_ALIVE, S_JOB_DEAD, S_KJOBS, S_TJ_OF_TILE
 };
 
 template <typename T>
@@ -187,14 +187,23 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
     uint32_t * d_counters; unsigned long long * d_bsums;
     if (grow_scratch(c, S_NEED, s.need, (size_t)N * s.need_stride)) return c->status;
     if (grow_scratch(c, S_TFLAGS, s.tile_flags, (size_t)n_tiles)) return c->status;
-    s.known = nullptr;
+    s.known = nullptr; s.kjobs = nullptr; s.kjobs_cap = 0; s.counters = nullptr;
     const size_t known_stride = (size_t)s.need_stride * 32;
     if (screen2) {
         if (grow_scratch(c, S_KNOWN, s.known, (size_t)N * known_stride)) return c->status;
         PD_CUDA(c, cudaMemsetAsync(s.known, 0, (size_t)N * known_stride * 4, st));
+        const size_t kcap = std::min<size_t>((size_t)N * n_tiles, 0xFFFFFFF0ull);
+        if (grow_scratch(c, S_KJOBS, s.kjobs, kcap)) return c->status;
+        s.kjobs_cap = (uint32_t)kcap;
     }
     if (grow_scratch(c, S_COUNTERS, d_counters, (size_t)CNT_N)) return c->status;
+    s.counters = d_counters;
     JobArgs j;
+    j.tj_of_tile = nullptr;
+    if (screen2) {
+        if (grow_scratch(c, S_TJ_OF_TILE, j.tj_of_tile, (size_t)n_tiles)) return c->status;
+        PD_CUDA(c, cudaMemsetAsync(j.tj_of_tile, 0xFF, (size_t)n_tiles * 4, st));
+    }
     j.tile_flags = s.tile_flags; j.n_tiles = n_tiles; j.tile_begin = s.tile_begin; j.counters = d_counters;
     if (grow_scratch(c, S_TJ_TILE, j.tj_tile, (size_t)n_tiles)) return c->status;
     if (grow_scratch(c, S_TJ_MASK, j.tj_mask, (size_t)n_tiles)) return c->status;
@@ -294,6 +303,7 @@ int pd_run_scan(pd_ctx * c, uint64_t first_window, uint64_t n_windows, pd_result
         if (grow_scratch(c, S_TJ_CFIRST, d_cfirst, (size_t)ntj)) return c->status;
         ga.tj_cmask = d_cmask; ga.tj_cfirst = d_cfirst;
         ga.phase = 0; ga.known = s.known; ga.known_stride = (uint32_t)known_stride; ga.tb_al = s.tb_al;
+        ga.kjobs = s.kjobs; ga.n_kjobs = std::min<uint32_t>(h_cnt[CNT_KJOBS], s.kjobs_cap); ga.tj_of_tile = j.tj_of_tile; ga.tile_begin = s.tile_begin;
         if (screen2) {
             if (grow_scratch(c, S_TJ_ALIVE, ga.tj_alive, (size_t)ntj)) return c->status;
             if (grow_scratch(c, S_JOB_DEAD, ga.job_dead, (size_t)nj)) return c->status;

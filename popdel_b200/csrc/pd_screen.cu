@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(256) k_count(PdDev a, ScreenArgs s)
     uint32_t mq = s.need[(size_t)smp * s.need_stride + wq];
     if (mq == 0) return;
     const uint32_t g0 = a.sample_rg[smp], g1 = a.sample_rg[smp + 1];
+    uint32_t kt = 0;                                                // tiles of this word with windows whose Q3 can exceed t_known
     while (mq) {
         const int b = __ffs(mq) - 1;
         mq &= mq - 1;
@@ -180,6 +181,16 @@ __global__ void __launch_bounds__(256) k_count(PdDev a, ScreenArgs s)
         if (a.t_known != 0) {                                       // second stage: this sample's Q3 can exceed t_known in these windows
             const uint32_t km = __ballot_sync(PD_FULL, in && y >= pd_q3_need(n));
             if (lane == 0) s.known[(size_t)smp * (s.need_stride * 32) + (tile - s.tb_al)] = km;
+            if (km) kt |= 1u << b;
+        }
+    }
+    if (kt && s.kjobs) {                                            // one reservation per warp: the list phase 1 of k_tile_q3 walks
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&s.counters[CNT_KJOBS], (uint32_t)__popc(kt));
+        base = __shfl_sync(PD_FULL, base, 0);
+        if ((kt >> lane) & 1u) {
+            const uint32_t slot = base + __popc(kt & ((1u << lane) - 1u));
+            if (slot < s.kjobs_cap) s.kjobs[slot] = make_uint2(smp, s.tb_al + wq * 32 + (uint32_t)lane);
         }
     }
 }
@@ -222,6 +233,7 @@ __global__ void __launch_bounds__(1024) k_tj_write(JobArgs j)
     if (!mask) return;
     const uint32_t k = (uint32_t)(ex >> 32), wb = (uint32_t)ex;
     j.tj_tile[k] = j.tile_begin + t; j.tj_mask[k] = mask; j.tj_wbase[k] = wb;
+    if (j.tj_of_tile) j.tj_of_tile[t] = k;
     uint32_t r = 0;
     for (uint32_t m = mask; m; m &= m - 1, ++r) j.job_window[wb + r] = (j.tile_begin + t) * PD_TILE_WINDOWS + (__ffs(m) - 1);
 }
