@@ -21,6 +21,18 @@ def test_library_exports_every_declared_symbol():
         assert getattr(lib, name) is not None
 
 
+def test_generator_libraries_export_every_declared_symbol():
+    """include/pdsynth.h: the host generator (libpdsynth.so) and its device-side twin (libpdsynth_cuda.so, loads without a GPU)."""
+    import ctypes as C
+    header = open(os.path.join(ROOT, "include", "pdsynth.h")).read()
+    declared = set(re.findall(r"\b(pd_synth_[a-z_]+|pdsynth_dev_[a-z_]+)\s*\(", header))
+    assert declared == {"pd_synth_read_group", "pdsynth_dev_create", "pdsynth_dev_destroy", "pdsynth_dev_generate", "pdsynth_dev_copy_to_host"}
+    host = C.CDLL(os.path.join(ROOT, "popdel_b200", "libpdsynth.so"))
+    dev = C.CDLL(os.path.join(ROOT, "popdel_b200", "libpdsynth_cuda.so"))
+    for name in declared:
+        assert getattr(host if name.startswith("pd_synth_") else dev, name) is not None
+
+
 def test_compact_encode_round_trip():
     """pd_contig_push_compact's input form: 16-bit position remainders per 65 536-bp block + 24-bit deviations."""
     rng = np.random.default_rng(11)
