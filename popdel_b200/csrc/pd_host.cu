@@ -326,9 +326,11 @@ extern "C" int pd_contig_push(pd_ctx * c, uint32_t rg, uint64_t n, const uint32_
         const uint64_t endp = (uint64_t)pr + (uint64_t)inner;
         const int64_t lw = endp < 0xFFFFFFFFull ? (int64_t)((uint32_t)endp / PD_WIN) : (int64_t)(endp / PD_WIN);
         if (capped) {
-            const int64_t j = (int64_t)((uint64_t)bp / wb);         // every segment switch up to this read pair's segment
             if (cs.seg < 0) cs.start(wb);
-            while (cs.seg < j) cs.next_segment(wb);
+            if ((uint64_t)bp >= cs.set[cs.write_set].right) {       // every segment switch up to this read pair's segment
+                const int64_t j = (int64_t)((uint64_t)bp / wb);
+                while (cs.seg < j) cs.next_segment(wb);
+            }
             if (!cs.admit(b, (uint32_t)std::min<int64_t>(lw, 0xFFFFFFFF), max_load)) { ++dropped; continue; }
         }
         if (bp >= seg_end_bp || h.seg < 0) {                        // first read pair of a new segment
