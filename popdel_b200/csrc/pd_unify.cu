@@ -7,7 +7,7 @@
 //
 //   k_seg_bounds     window calls are emitted in window order, so the calls of one processSegment() are a run of equal
 //                    `segment` tags: first / last index per segment.
-//   k_unify_plan     one block per segment. All threads: stable rank sort by (position, deletion length, LR descending)
+//   k_unify_plan     one block per segment (merge loop: one warp in lockstep). All threads: stable rank sort by (position, deletion length, LR descending)
 //                    and a working copy of the call headers in that order. Thread 0: the reference's merge loop -- a
 //                    sequential state machine over a few dozen headers whose quirks must be kept (the running lists of
 //                    starts / sizes and the window counters are only reset by a SUCCESSFUL mergeWindowRange, the first
@@ -76,29 +76,9 @@ __global__ void k_seg_bounds(UnifyArgs u)
     if (i == u.n_raw - 1 || u.calls[i + 1].segment != s) u.seg_last[s] = i + 1;
 }
 
-// value of rank k (0-based) of v[0, n); reorders v. Quickselect with a middle pivot: the lists of a long deletion
-// hold a few hundred entries and one thread runs the merge loop.
-__device__ uint32_t select_rank(uint32_t * v, uint32_t n, uint32_t k)
-{
-    uint32_t lo = 0, hi = n - 1;
-    while (lo < hi) {
-        const uint32_t pivot = v[lo + (hi - lo) / 2];
-        uint32_t i = lo, j = hi;
-        while (i <= j) {
-            while (v[i] < pivot) ++i;
-            while (v[j] > pivot) --j;
-            if (i <= j) { const uint32_t t = v[i]; v[i] = v[j]; v[j] = t; ++i; if (j == 0) break; --j; }
-        }
-        if (k <= j && j < hi) hi = j;
-        else if (k >= i) lo = i;
-        else break;                                                   // v[k] == pivot
-    }
-    return v[k];
-}
-
 constexpr uint32_t PLAN_CAP = 512;
-__device__ void plan_segment(const UnifyArgs & u, uint32_t seg, uint32_t n, pd_call * W, uint32_t * S, uint32_t * Z, uint32_t * I,
-                             uint32_t * G, uint32_t * Q, const uint32_t * ord);
+__device__ __forceinline__ void plan_segment(const UnifyArgs & u, uint32_t seg, uint32_t n, pd_call * W, uint32_t * S, uint32_t * Z, uint32_t * I,
+                             uint32_t * G, uint32_t * Q, const uint32_t * ord, int lane);
 
 __global__ void __launch_bounds__(256) k_unify_plan(UnifyArgs u)
 {
@@ -132,8 +112,8 @@ __global__ void __launch_bounds__(256) k_unify_plan(UnifyArgs u)
         for (uint32_t i = tid; i < n; i += T) { s_w[i] = u.wc[first + i]; s_o[i] = u.order[first + i]; s_g[i] = 0; s_q[i] = 0; }
         __syncthreads();
     }
-    if (tid == 0) plan_segment(u, seg, n, fits ? s_w : u.wc + first, fits ? s_s : u.starts + first, fits ? s_z : u.sizes + first,
-                               fits ? s_i : u.inr + first, fits ? s_g : u.gwc + first, fits ? s_q : u.sig + first, fits ? s_o : u.order + first);
+    if (tid < 32) plan_segment(u, seg, n, fits ? s_w : u.wc + first, fits ? s_s : u.starts + first, fits ? s_z : u.sizes + first,
+                               fits ? s_i : u.inr + first, fits ? s_g : u.gwc + first, fits ? s_q : u.sig + first, fits ? s_o : u.order + first, (int)tid);
     if (fits) {
         __syncthreads();
         for (uint32_t i = tid; i < n; i += T) {
@@ -142,57 +122,106 @@ __global__ void __launch_bounds__(256) k_unify_plan(UnifyArgs u)
     }
 }
 
-// the reference's merge loop over the sorted headers W[0, n) of one segment (one thread)
-__device__ void plan_segment(const UnifyArgs & u, uint32_t seg, uint32_t n, pd_call * W, uint32_t * S, uint32_t * Z, uint32_t * I,
-                             uint32_t * G, uint32_t * Q, const uint32_t * ord)
+// value of rank k (0-based, ascending) of v[0, n): bisection on the value with warp-wide counts (v is not reordered)
+__device__ __forceinline__ uint32_t warp_select_rank(const uint32_t * v, uint32_t n, uint32_t k, int lane)
+{
+    uint32_t lo = 0xFFFFFFFFu, hi = 0;
+    for (uint32_t i = lane; i < n; i += 32) { const uint32_t x = v[i]; lo = min(lo, x); hi = max(hi, x); }
+    lo = __reduce_min_sync(PD_FULL, lo); hi = __reduce_max_sync(PD_FULL, hi);
+    while (lo < hi) {                                                  // smallest x with #{v <= x} >= k + 1
+        const uint32_t mid = lo + (hi - lo) / 2;
+        uint32_t c = 0;
+        for (uint32_t i = lane; i < n; i += 32) c += v[i] <= mid;
+        c = __reduce_add_sync(PD_FULL, c);
+        if (c >= k + 1) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// The reference's merge loop over the sorted headers W[0, n) of one segment, run by ONE WARP in lockstep: every lane walks
+// the same sequential loop on the same values (the longest segment of the contig sets the kernel's time, and that time is
+// a chain of dependent shared-memory accesses), lane 0 does the stores, and the two parts that are not sequential -- the
+// medians of the running start / size lists (select by bisection, a few hundred entries for a long deletion) and the list
+// of in-range windows of a merged variant -- use all 32 lanes.
+__device__ __forceinline__ void plan_segment(const UnifyArgs & u, uint32_t seg, uint32_t n, pd_call * W, uint32_t * S, uint32_t * Z, uint32_t * I,
+                             uint32_t * G, uint32_t * Q, const uint32_t * ord, int lane)
 {
     const uint32_t last = n - 1;
+    const uint32_t lt = (1u << lane) - 1u;
     uint32_t cur = 0;
-    auto drop_all = [&]() { u.seg_keep[seg] = 0; };
+    auto drop_all = [&]() { if (lane == 0) u.seg_keep[seg] = 0; };
     if (!u.output_failed) {
         while (!all_pass(W[cur])) { if (cur == last) { drop_all(); return; } ++cur; }
         if (cur == last) { drop_all(); return; }
     }
     const uint32_t first_idx = cur;
-    for (uint32_t k = 0; k < first_idx; ++k) W[k].filter = 255;
+    for (uint32_t k = lane; k < first_idx; k += 32) W[k].filter = 255;
     uint32_t loff = 0, ln = 0;                                         // running lists = S/Z[loff, loff + ln)
-    S[0] = W[cur].position; Z[0] = W[cur].deletion_length; ln = 1;
+    if (lane == 0) { S[0] = W[cur].position; Z[0] = W[cur].deletion_length; }
+    ln = 1;
     double lr = W[cur].lr;                                             // (long double in the reference)
     uint32_t winCount = 1, sigWin = 1;
+    __syncwarp();
     auto merge_range = [&](uint32_t start, uint32_t lastx) {           // mergeWindowRange :512-559 without the per-sample part
+        __syncwarp();                                                  // (lane 0's appends to the lists)
         pd_call & st = W[start];
-        st.position = select_rank(S + loff, ln, ln / 2); st.deletion_length = select_rank(Z + loff, ln, ln / 2);
+        const uint32_t mp = warp_select_rank(S + loff, ln, ln / 2, lane), ml = warp_select_rank(Z + loff, ln, ln / 2, lane);
+        if (lane == 0) { st.position = mp; st.deletion_length = ml; st.lr = lr / winCount; }
         loff += ln; ln = 0;
-        st.lr = lr / winCount;
         uint32_t g = 0;
-        for (uint32_t k = start; k < lastx; ++k) {
-            const uint32_t wp = W[k].window_position;
-            if (wp > st.position && wp - 30 < st.position + st.deletion_length) I[start + g++] = ord[k];
+        for (uint32_t k0 = start; k0 < lastx; k0 += 32) {              // in-range windows, in sorted order
+            const uint32_t k = k0 + lane;
+            bool in = false;
+            if (k < lastx) { const uint32_t wp = W[k].window_position; in = wp > mp && wp - 30 < mp + ml; }
+            const uint32_t bm = __ballot_sync(PD_FULL, in);
+            if (in) I[start + g + __popc(bm & lt)] = ord[k];
+            g += __popc(bm);
         }
-        if (g == 0) { st.filter = 255; return; }                       // (returns before the counters are reset)
-        G[start] = g; Q[start] = sigWin;
-        if (30.0 * sigWin / st.deletion_length < u.min_cover) st.filter |= 16;
+        if (g == 0) { if (lane == 0) st.filter = 255; __syncwarp(); return; }      // (returns before the counters are reset)
+        if (lane == 0) {
+            G[start] = g; Q[start] = sigWin;
+            if (30.0 * sigWin / ml < u.min_cover) st.filter |= 16;
+        }
+        __syncwarp();
         winCount = 1; sigWin = 1; lr = 0.0;
     };
     uint32_t it = first_idx + 1;
+    // the three fields of W[cur] the comparison reads live in registers, W[it] is read once, W[it + 1] is in flight while W[it]
+    // is compared
+    pd_call a;
+    a.position = W[cur].position; a.end_position = W[cur].end_position; a.deletion_length = W[cur].deletion_length;
+    pd_call x = W[it];
     while (true) {
-        if (similar_calls(W[cur], W[it], u.sd)) {
-            if (all_pass(W[it])) { S[loff + ln] = W[it].position; Z[loff + ln] = W[it].deletion_length; ++ln; ++sigWin; }
+        pd_call nx = x;
+        if (it != last) nx = W[it + 1];
+        const uint32_t end_before = a.end_position;
+        const bool similar = similar_calls(a, x, u.sd);
+        if (a.end_position != end_before && lane == 0) W[cur].end_position = a.end_position;      // checkAndExtend
+        if (similar) {
+            if (all_pass(x)) { if (lane == 0) { S[loff + ln] = x.position; Z[loff + ln] = x.deletion_length; } ++ln; ++sigWin; }
             ++winCount;
-            lr += W[it].lr;
-            W[it].filter = 255;
+            lr += x.lr;
+            if (lane == 0) W[it].filter = 255;
             if (it == last) { if (ln) merge_range(cur, it); break; }
         } else {
             if (winCount != 1 && ln) merge_range(cur, it);
-            else W[cur].filter = 255;
+            else if (lane == 0) W[cur].filter = 255;
             cur = it;
+            a.position = x.position; a.end_position = x.end_position; a.deletion_length = x.deletion_length;
         }
-        if (it != last) ++it;
-        else { if (winCount == 1) W[cur].filter = 255; break; }
+        if (it != last) { ++it; x = nx; }
+        else { if (winCount == 1 && lane == 0) W[cur].filter = 255; break; }
     }
-    uint32_t keep = 0;
-    for (uint32_t k = first_idx; k <= last; ++k) if (W[k].filter != 255) S[keep++] = k;       // (the lists are no longer needed)
-    u.seg_keep[seg] = keep;
+    __syncwarp();
+    uint32_t keep = 0;                                                 // kept sorted slots, in order (the lists are no longer needed)
+    for (uint32_t k0 = first_idx; k0 <= last; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        const bool kp = k <= last && W[k].filter != 255;
+        const uint32_t bm = __ballot_sync(PD_FULL, kp);
+        if (kp) S[keep + __popc(bm & lt)] = k;
+        keep += __popc(bm);
+    }
+    if (lane == 0) u.seg_keep[seg] = keep;
 }
 
 __global__ void __launch_bounds__(1024) k_unify_offsets(UnifyArgs u)

@@ -21,5 +21,5 @@ for row in csv.reader(io.StringIO(out)):
     a[0] += s; a[1] += i; a[2] += t
 S = sum(a[0] for a in lines.values()); I = sum(a[1] for a in lines.values())
 print(f"total samples {S}, warp instructions {I}")
-for k, a in sorted(lines.items(), key=lambda kv: -kv[1][1])[:top]:
+for k, a in sorted(lines.items(), key=lambda kv: (-kv[1][0] if os.environ.get("BY_SAMPLES") else -kv[1][1]))[:top]:
     print(f"{100*a[0]/max(S,1):5.1f}% smp {100*a[1]/max(I,1):5.1f}% ins  thr/ins {a[2]/max(a[1],1):4.1f}  {k[0]}:{k[1]}  {a[3][:110]}")
