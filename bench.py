@@ -290,20 +290,27 @@ def run_ours(args, rank, world, local_rank):
         for g in range(R):
             sc.push_pinned(g, pinned[g][0][1], pinned[g][1][1])
 
-    # the same read pairs in the 5-byte form of pd_contig_push_compact (what a profile decoder emits directly: the file stores
-    # a u8 offset per 256-bp window and an i32 deviation), page-locked
+    # the same read pairs in the 4-byte form of pd_contig_push_compact32 (what a profile decoder emits directly: the file stores
+    # a u8 offset per 256-bp window and an i32 deviation), page-locked; and in round 2's earlier 5-byte form (65 536-bp blocks)
     def pin_any(a, dt):
         t = torch.from_numpy(a.view(dt)).pin_memory()
         return t, t.numpy().view(a.dtype)
-    compact = []
+    compact, compact5 = [], []
     for c in cohort:
+        w32, blk8 = api.compact32_encode(c[0], c[2])
+        compact.append((pin_any(w32, np.int32), pin_any(blk8, np.int32)))
         lo, d24, blk = api.compact_encode(c[0], c[2])
-        compact.append((pin_any(lo, np.int16), pin_any(d24, np.uint8), pin_any(blk, np.int32)))
+        compact5.append((pin_any(lo, np.int16), pin_any(d24, np.uint8), pin_any(blk, np.int32)))
 
     def push_all_compact():
         sc.begin_contig(anchor)
         for g in range(R):
-            sc.push_compact(g, compact[g][0][1], compact[g][1][1], compact[g][2][1])
+            sc.push_compact32(g, compact[g][0][1], compact[g][1][1])
+
+    def push_all_compact5():
+        sc.begin_contig(anchor)
+        for g in range(R):
+            sc.push_compact(g, compact5[g][0][1], compact5[g][1][1], compact5[g][2][1])
 
     def barrier():
         if dist is not None:
@@ -391,6 +398,18 @@ def run_ours(args, rank, world, local_rank):
     dt2, _ = sharding.reduce_timing(dt2, float(evals), dist, "cuda")
     e2e = evals_all * e2e_steps / dt2
     assert len(r2["calls"]) == n_out, (len(r2["calls"]), n_out)
+    # the same in the 5-byte form
+    push_all_compact5()
+    r25 = sc.scan(copy=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        push_all_compact5()
+        r25 = sc.scan(copy=False)
+    barrier()
+    dt25 = time.perf_counter() - t0
+    dt25, _ = sharding.reduce_timing(dt25, float(evals), dist, "cuda")
+    assert len(r25["calls"]) == n_out
     # the same from raw page-locked pos[] / dev[] arrays (8 bytes per read pair)
     push_all_pinned()
     r2r = sc.scan(copy=False)
@@ -464,11 +483,13 @@ def run_ours(args, rank, world, local_rank):
                             "flagged_windows": int(res["n_flagged_windows"]), "candidates": int(res["n_candidates"])},
         "clocks": clk,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(r2["h2d_bytes"]), "d2h_bytes_per_step": int(r2["d2h_bytes"]),
-                "steps": e2e_steps, "ms_per_step": dt2 / e2e_steps * 1e3, "path": "pd_contig_push_compact (5 B per read pair over PCIe, expansion + packing on the device) + pd_contig_scan" + (" with pd_set_unify" if main_unify else ""),
+                "steps": e2e_steps, "ms_per_step": dt2 / e2e_steps * 1e3, "path": "pd_contig_push_compact32 (4 B per read pair + 4 B per 256-bp block over PCIe, expansion + packing on the device) + pd_contig_scan" + (" with pd_set_unify" if main_unify else ""),
                 "pcie": {"h2d_gbs_plain_copy": compact_bytes / dt_copy_c / 1e9, "floor_ms_per_step": dt_copy_c * 1e3,
                          "frac_of_floor": dt_copy_c / (dt2 / e2e_steps),
                          "note": "floor = the same page-locked arrays copied host->device with nothing else running; "
                                  "the e2e step additionally expands and packs on the device, scans and writes the results back"},
+                "five_byte_form": {"value": evals_all * e2e_steps / dt25, "ms_per_step": dt25 / e2e_steps * 1e3, "h2d_bytes_per_step": int(r25["h2d_bytes"]),
+                                   "path": "pd_contig_push_compact: 16-bit position remainders per 65 536-bp block + 24-bit deviations"},
                 "raw_arrays": {"value": evals_all * e2e_steps / dt2r, "ms_per_step": dt2r / e2e_steps * 1e3, "h2d_bytes_per_step": int(r2r["h2d_bytes"]),
                                "floor_ms_per_step": dt_copy * 1e3, "path": "pd_contig_push_pinned: raw pos[] / dev[] arrays, 8 B per read pair"},
                 "host_packer_value": evals_all / dt3, "host_packer_ms_per_step": dt3 * 1e3, "host_packer_h2d_bytes": int(r3["h2d_bytes"])},

@@ -10,7 +10,7 @@
  * of the contig (genotype_deletion_window for each 30-bp window). All functions return 0 on success or a negative
  * pd_status; no exception crosses the ABI; errors are sticky per context and described by pd_last_error().
  * Plain pointers and sizes only. One pd_ctx per GPU, driven by one host thread at a time -- with one exception:
- * pd_contig_push / pd_contig_push_pinned / _compact / _device may be called concurrently for DIFFERENT read groups of
+ * pd_contig_push / pd_contig_push_pinned / _compact / _compact32 / _device may be called concurrently for DIFFERENT read groups of
  * one context (the host packer of a read group touches only that read group's staging; errors are recorded under a lock).
  */
 #ifndef POPDEL_B200_H_
@@ -142,6 +142,12 @@ int pd_contig_push_pinned(pd_ctx * ctx, uint32_t rg, uint64_t n, const uint32_t 
  * returns, one call per read group and contig, identical results). */
 int pd_contig_push_compact(pd_ctx * ctx, uint32_t rg, uint64_t n, const uint16_t * pos_lo, const uint8_t * dev24,
                            uint32_t n_blocks, const uint32_t * blk_first);
+
+/* The densest input form, 4 bytes per read pair (+ 4 bytes per 256-bp block): word[i] = deviation << 8 | (pos & 0xFF) with
+ * the deviation as a 24-bit two's-complement integer, and blk_first[b] = index of the first read pair with pos >> 8 == b,
+ * b = 0 .. n_blocks (blk_first[n_blocks] = n) -- the layout of the profile file itself (a u8 offset inside its 256-bp window,
+ * window_podel.h:161-197). Same rules and results as pd_contig_push_compact. */
+int pd_contig_push_compact32(pd_ctx * ctx, uint32_t rg, uint64_t n, const uint32_t * words, uint32_t n_blocks, const uint32_t * blk_first);
 
 /* pd_contig_push_pinned for arrays that are ALREADY in the memory of the context's GPU (written there by a device-side
  * profile decoder or generator): pos / dev are device pointers; nothing crosses PCIe, the arrays are packed where they

@@ -58,7 +58,7 @@ CALL_DTYPE = np.dtype([("initial_length", "<u4"), ("iterations", "<u4"), ("delet
                        ("end_position", "<u4"), ("segment", "<u4")])
 
 EXPORTS = ["pd_process_histogram", "pd_create", "pd_create_error", "pd_destroy", "pd_last_error", "pd_contig_begin",
-           "pd_contig_push", "pd_contig_push_pinned", "pd_contig_push_compact", "pd_contig_push_device", "pd_contig_upload", "pd_contig_scan", "pd_contig_window_count",
+           "pd_contig_push", "pd_contig_push_pinned", "pd_contig_push_compact", "pd_contig_push_compact32", "pd_contig_push_device", "pd_contig_upload", "pd_contig_scan", "pd_contig_window_count",
            "pd_debug_host_window_sums", "pd_debug_cap_replay", "pd_contig_reserve_windows", "pd_shard_unique_id", "pd_shard_attach_nccl",
            "pd_shard_attach_group", "pd_shard_group_scan", "pd_set_unify", "pd_device_warmup", "pd_set_staging"]
 
@@ -91,6 +91,7 @@ def load_library(path: str = LIB_PATH):
     lib.pd_contig_begin.argtypes = [C.c_void_p, C.c_uint32]
     lib.pd_contig_push.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
     lib.pd_contig_push_pinned.argtypes = lib.pd_contig_push.argtypes
+    lib.pd_contig_push_compact32.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32)]
     lib.pd_contig_push_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.pd_contig_push_compact.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint16), C.POINTER(C.c_uint8),
                                            C.c_uint32, C.POINTER(C.c_uint32)]
@@ -274,6 +275,16 @@ class Scanner:
                                                     dev24.ctypes.data_as(C.POINTER(C.c_uint8)), blk_first.size - 1,
                                                     blk_first.ctypes.data_as(C.POINTER(C.c_uint32))))
 
+    def push_compact32(self, rg: int, words: np.ndarray, blk_first: np.ndarray):
+        """pd_contig_push_compact32 (4 bytes per read pair over PCIe, see compact32_encode): C-contiguous views of page-locked
+        memory that stay alive and unchanged until upload()/scan() returns."""
+        assert words.dtype == np.uint32 and blk_first.dtype == np.uint32 and words.flags.c_contiguous and blk_first.flags.c_contiguous
+        assert blk_first.size >= 2
+        self._pinned_keep = getattr(self, "_pinned_keep", {})
+        self._pinned_keep[rg] = (words, blk_first)
+        self._check(self.lib.pd_contig_push_compact32(self.ctx, int(rg), words.size, words.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                      blk_first.size - 1, blk_first.ctypes.data_as(C.POINTER(C.c_uint32))))
+
     def push_device(self, rg: int, n: int, d_pos: int, d_dev: int):
         """pd_contig_push_device: d_pos (uint32[n]) / d_dev (int32[n]) are DEVICE addresses on this scanner's GPU (e.g.
         torch_tensor.data_ptr()) that stay valid and unchanged until upload()/scan() returns."""
@@ -453,6 +464,18 @@ def compact_encode(pos: np.ndarray, dev: np.ndarray):
     return pos_lo, dev24, blk_first
 
 
+def compact32_encode(pos: np.ndarray, dev: np.ndarray):
+    """(pos uint32 sorted, dev int32 with |dev| < 2^23) -> (words uint32, blk_first uint32) of pd_contig_push_compact32:
+    word = dev << 8 | pos & 0xFF, blk_first[b] = first read pair of 256-bp block b -- the profile file's own granularity."""
+    pos = np.ascontiguousarray(pos, dtype=np.uint32)
+    dev = np.ascontiguousarray(dev, dtype=np.int32)
+    assert dev.size == 0 or (int(dev.min()) >= -(1 << 23) and int(dev.max()) < (1 << 23))
+    words = ((dev.astype(np.uint32) << np.uint32(8)) | (pos & np.uint32(0xFF))).astype(np.uint32)
+    nb = int(pos[-1] >> 8) + 1 if pos.size else 1
+    blk = np.searchsorted(pos >> np.uint32(8), np.arange(nb + 1, dtype=np.uint32), side="left").astype(np.uint32)
+    return words, blk
+
+
 def _page_locked(a: np.ndarray) -> np.ndarray:
     """A page-locked copy of `a` (torch pin_memory; the push_pinned / push_compact contract). Falls back to the array itself
     when torch has no CUDA runtime (the copies are then staged by the driver: slower, same result)."""
@@ -502,6 +525,8 @@ def scan_cohort(samples, params: CallParameters, device: int = 0, first_window: 
                     dd = torch.from_numpy(np.ascontiguousarray(rg.dev, dtype=np.int32)).to(f"cuda:{device}")
                     keep.append((dp, dd))
                     sc.push_device(g, dp.numel(), dp.data_ptr(), dd.data_ptr())
+                elif pinned == "compact32":
+                    sc.push_compact32(g, *[_page_locked(a) for a in compact32_encode(rg.pos, rg.dev)])
                 elif pinned == "compact":
                     sc.push_compact(g, *[_page_locked(a) for a in compact_encode(rg.pos, rg.dev)])
                 elif pinned:

@@ -161,8 +161,9 @@ struct PdShard;                      // sample sharding state (pd_shard.cu)
 struct PdRawRg {
     const uint32_t * pos = nullptr; const int32_t * dev = nullptr; uint64_t n = 0;
     const uint16_t * lo = nullptr; const uint8_t * d24 = nullptr; const uint32_t * blk = nullptr; uint32_t nblk = 0;
+    const uint32_t * w32 = nullptr;  // pd_contig_push_compact32: dev:24 | pos & 0xFF per read pair, blk = 256-bp blocks
     bool on_device = false;          // pos / dev are device pointers (pd_contig_push_device)
-    bool compact() const { return lo != nullptr; }
+    bool compact() const { return lo != nullptr || w32 != nullptr; }
 };
 
 struct pd_ctx {

@@ -483,6 +483,23 @@ extern "C" int pd_contig_push_device(pd_ctx * c, uint32_t rg, uint64_t n, const 
     return 0;
 }
 
+extern "C" int pd_contig_push_compact32(pd_ctx * c, uint32_t rg, uint64_t n, const uint32_t * words, uint32_t n_blocks, const uint32_t * blk_first)
+{
+    if (!c) return PD_ERR_ARG;
+    if (c->status) return c->status;
+    if (!c->contig_open || rg >= c->R || (n && (!words || !blk_first || !n_blocks)) || n_blocks > 0x7FFFFFFFu)
+        return pd_fail(c, PD_ERR_ARG, "pd_contig_push_compact32: bad arguments or no open contig");
+    if (c->device < 0) return pd_fail(c, PD_ERR_CUDA, "pd_contig_push_compact32: host-only context");
+    if (c->host_mode || c->packed) return pd_fail(c, PD_ERR_ARG, "pd_contig_push_compact32: cannot be mixed with pd_contig_push / contig already packed");
+    if (c->raw[rg].n) return pd_fail(c, PD_ERR_ARG, "pd_contig_push_compact32: one call per read group and contig");
+    if (n && (blk_first[n_blocks] != n || blk_first[0] != 0)) return pd_fail(c, PD_ERR_ARG, "pd_contig_push_compact32: blk_first must run from 0 to n");
+    c->dev_mode = true;
+    PdRawRg r;
+    r.n = n; r.w32 = words; r.blk = blk_first; r.nblk = n_blocks;
+    c->raw[rg] = r;
+    return 0;
+}
+
 extern "C" int pd_contig_push_compact(pd_ctx * c, uint32_t rg, uint64_t n, const uint16_t * pos_lo, const uint8_t * dev24,
                                       uint32_t n_blocks, const uint32_t * blk_first)
 {
@@ -561,7 +578,9 @@ extern "C" int pd_contig_upload(pd_ctx * c)
             if (r.compact() && r.n) {                              // decode the compact arrays for the sequential packer
                 auto & P = c->raw_pos_dec[g]; auto & D = c->raw_dev_dec[g];
                 P.resize(r.n); D.resize(r.n);
-                for (uint32_t b = 0; b < r.nblk; ++b)
+                for (uint32_t b = 0; b < r.nblk && r.w32; ++b)
+                    for (uint64_t i = r.blk[b]; i < r.blk[b + 1]; ++i) { P[i] = (b << 8) | (r.w32[i] & 0xFFu); D[i] = (int32_t)r.w32[i] >> 8; }
+                for (uint32_t b = 0; b < r.nblk && !r.w32; ++b)
                     for (uint64_t i = r.blk[b]; i < r.blk[b + 1]; ++i) {
                         P[i] = (b << 16) | r.lo[i];
                         const uint32_t u = (uint32_t)r.d24[3 * i] | ((uint32_t)r.d24[3 * i + 1] << 8) | ((uint32_t)r.d24[3 * i + 2] << 16);

@@ -358,13 +358,19 @@ int grow_dev(pd_ctx * c, int slot, T *& p, size_t need)
 static inline uint32_t raw_pos_at(const PdRawRg & r, uint64_t i, uint32_t & b)
 {
     if (!r.compact()) return r.pos[i];
+    if (r.w32 && (r.blk[b] > i || r.blk[b + 1] <= i)) {              // 256-bp blocks: search instead of walking
+        uint32_t lo = 0, hi = r.nblk;
+        while (hi - lo > 1) { const uint32_t m = lo + (hi - lo) / 2; if (r.blk[m] <= i) lo = m; else hi = m; }
+        b = lo;
+    }
     while (b > 0 && r.blk[b] > i) --b;
     while (b + 1 < r.nblk && r.blk[b + 1] <= i) ++b;
-    return (b << 16) | r.lo[i];
+    return r.w32 ? ((b << 8) | (r.w32[i] & 0xFFu)) : ((b << 16) | r.lo[i]);
 }
 static inline int32_t raw_dev_at(const PdRawRg & r, uint64_t i)
 {
     if (!r.compact()) return r.dev[i];
+    if (r.w32) return (int32_t)r.w32[i] >> 8;
     const uint32_t u = (uint32_t)r.d24[3 * i] | ((uint32_t)r.d24[3 * i + 1] << 8) | ((uint32_t)r.d24[3 * i + 2] << 16);
     return (int32_t)(u << 8) >> 8;
 }
@@ -379,11 +385,14 @@ __global__ void __launch_bounds__(256) k_expand_compact(const uint16_t * __restr
     const uint64_t c0 = (uint64_t)blockIdx.x * 4096;
     if (c0 >= n) return;
     const uint32_t * bk = blk + blk_start[g];
-    const uint32_t nb = rg_nblk[g];
+    uint32_t nb = rg_nblk[g];
+    const bool w32 = (nb >> 31) != 0;                              // 4-byte form: the words were copied into dev[], 256-bp blocks
+    nb &= 0x7FFFFFFFu;
     if (nb == 0) return;                                           // this read group came as raw arrays
     for (uint64_t i = c0 + threadIdx.x; i < min(n, c0 + 4096); i += 256) {
         uint32_t a = 0, b = nb;                                   // largest block with blk[block] <= i
         while (b - a > 1) { const uint32_t m = (a + b) >> 1; if (__ldg(bk + m) <= i) a = m; else b = m; }
+        if (w32) { const uint32_t w = (uint32_t)dev[s0 + i]; pos[s0 + i] = (a << 8) | (w & 0xFFu); dev[s0 + i] = (int32_t)w >> 8; continue; }
         pos[s0 + i] = (a << 16) | lo[s0 + i];
         const uint8_t * q = d24 + 3 * (s0 + i);
         const uint32_t u = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16);
@@ -526,8 +535,14 @@ int pd_pack_on_device(pd_ctx * c)
     std::vector<uint64_t> blk_start(R + 1, 0);
     std::vector<uint32_t> h_nblk(R, 0);
     if (any_compact) {
-        for (uint32_t g = 0; g < R; ++g) { h_nblk[g] = c->raw[g].compact() ? c->raw[g].nblk : 0; blk_start[g + 1] = blk_start[g] + (h_nblk[g] ? h_nblk[g] + 1 : 0); }
-        if (grow_dev(c, 8, d_lo, total) || grow_dev(c, 9, d_d24, total * 3 + 4) || grow_dev(c, 10, d_blk, blk_start[R] + 1) ||
+        for (uint32_t g = 0; g < R; ++g) {
+            const uint32_t nb = c->raw[g].compact() ? c->raw[g].nblk : 0;
+            h_nblk[g] = nb | (nb && c->raw[g].w32 ? 0x80000000u : 0u);
+            blk_start[g + 1] = blk_start[g] + (nb ? nb + 1 : 0);
+        }
+        bool any5 = false;                                         // the 5-byte form needs its own staging, the 4-byte form lands in dev[]
+        for (uint32_t g = 0; g < R; ++g) any5 = any5 || (c->raw[g].lo != nullptr && c->raw[g].n);
+        if (grow_dev(c, 8, d_lo, any5 ? total : 1) || grow_dev(c, 9, d_d24, any5 ? total * 3 + 4 : 4) || grow_dev(c, 10, d_blk, blk_start[R] + 1) ||
             grow_dev(c, 11, d_blk_start, (size_t)2 * (R + 1))) return c->status;
         d_nblk = reinterpret_cast<uint32_t *>(d_blk_start + (R + 1));
     }
@@ -553,6 +568,12 @@ int pd_pack_on_device(pd_ctx * c)
             const PdRawRg & r = c->raw[g];
             grp_max[k] = std::max<uint64_t>(grp_max[k], r.n);
             if (!r.n) continue;
+            if (r.w32) {                                           // the words go straight into dev[]; k_expand_compact splits them in place
+                PD_CUDA(c, cudaMemcpyAsync(d_dev + rg_start[g], r.w32, r.n * 4, cudaMemcpyHostToDevice, cp));
+                PD_CUDA(c, cudaMemcpyAsync(d_blk + blk_start[g], r.blk, ((size_t)r.nblk + 1) * 4, cudaMemcpyHostToDevice, cp));
+                h2d += r.n * 4 + ((size_t)r.nblk + 1) * 4;
+                continue;
+            }
             if (r.compact()) {
                 PD_CUDA(c, cudaMemcpyAsync(d_lo + rg_start[g], r.lo, r.n * 2, cudaMemcpyHostToDevice, cp));
                 PD_CUDA(c, cudaMemcpyAsync(d_d24 + 3 * rg_start[g], r.d24, r.n * 3, cudaMemcpyHostToDevice, cp));

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_exports_every_declared_symbol():
     lib = api.load_library()
     header = open(os.path.join(ROOT, "include", "popdel_b200.h")).read()
-    declared = set(re.findall(r"\b(pd_[a-z_]+)\s*\(", header)) - {"pd_ctx"}
+    declared = set(re.findall(r"\b(pd_[a-z_0-9]+)\s*\(", header)) - {"pd_ctx"}
     assert declared == set(api.EXPORTS)
     for name in declared:
         assert getattr(lib, name) is not None
@@ -49,6 +49,13 @@ def test_compact_encode_round_trip():
     d = (u[:, 0] | (u[:, 1] << 8) | (u[:, 2] << 16)).astype(np.int64)
     d = np.where(d >= 1 << 23, d - (1 << 24), d)
     assert np.array_equal(d, dev)
+    # 4-byte form (pd_contig_push_compact32): 8-bit position remainders per 256-bp block, 24-bit deviations in one word
+    w, blk8 = api.compact32_encode(pos, dev)
+    assert w.size == 5000 and blk8[0] == 0 and blk8[-1] == 5000 and blk8.size == (int(pos[-1]) >> 8) + 2
+    back = np.zeros(5000, np.uint32)
+    for b in range(blk8.size - 1):
+        back[blk8[b]:blk8[b + 1]] = (b << 8) | (w[blk8[b]:blk8[b + 1]] & 0xFF)
+    assert np.array_equal(back, pos) and np.array_equal(w.view(np.int32) >> 8, dev)
 
 
 def test_process_histogram_equals_oracle(oracle_lib):

@@ -74,8 +74,8 @@ def test_device_packer_equals_host_packer(kind):
     """pd_contig_push_pinned / _compact / _device (device-side packing; host fallback when the coverage cap bites) == pd_contig_push."""
     samples, params = _cohort(kind)
     a, _ = api.scan_cohort(samples, params)
-    # raw page-locked arrays / 5 bytes per read pair (pd_contig_push_compact) / arrays already in device memory (pd_contig_push_device)
-    for mode in (True, "compact", "device"):
+    # raw page-locked arrays / 5 and 4 bytes per read pair (pd_contig_push_compact, _compact32) / arrays already in device memory (pd_contig_push_device)
+    for mode in (True, "compact", "compact32", "device"):
         b, _ = api.scan_cohort(samples, params, pinned=mode)
         assert a["n_windows"] == b["n_windows"] and a["n_flagged_windows"] == b["n_flagged_windows"]
         assert a["n_reads"] == b["n_reads"]
