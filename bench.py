@@ -527,6 +527,14 @@ def run_ours(args, rank, world, local_rank):
         out["parity_check"] = (f"{int(osel.sum())} window calls == CPU oracle (windows below {lim} bp: integers and per-sample "
                                f"PL/LAD/DAD/FL bit-exact, LR / AF within 1e-6 relative)")
     if world == 1 and not args.no_e2e_files:
+        # the command-line tool is a process of its own: give the GPU and the page-locked host memory back first (its CUDA
+        # start-up was measured between 0.3 and 4 s while this process still held its context and 8 GB of pinned buffers)
+        sc.close()
+        sc._pinned_keep = {}
+        pinned.clear(); compact.clear(); compact5.clear()
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
         out["e2e_files"] = e2e_files(args)
     emit_json(out)
 
