@@ -498,7 +498,7 @@ int pd_pack_on_device(pd_ctx * c)
     for (uint32_t g = 0; g < R; ++g) any_device = any_device || (c->raw[g].on_device && c->raw[g].n);
     std::vector<uint32_t> dev_fl;
     if (any_device) {                                               // slot 12: tail statistics | pos pointers | dev pointers | counts | first/last
-        char * d_meta;
+        char * d_meta = nullptr;
         if (grow_dev(c, 12, d_meta, 64 + (size_t)R * 32)) return c->status;
         std::vector<const uint32_t *> hp(R, nullptr); std::vector<const int32_t *> hd(R, nullptr); std::vector<uint64_t> hn(R, 0);
         for (uint32_t g = 0; g < R; ++g) if (c->raw[g].on_device) { hp[g] = c->raw[g].pos; hd[g] = c->raw[g].dev; hn[g] = c->raw[g].n; }
@@ -527,7 +527,7 @@ int pd_pack_on_device(pd_ctx * c)
     const uint64_t total = rg_start[R];
     if (total > 0xFFFFFFF0ull) return pd_fail(c, PD_ERR_CAPACITY, "more than 2^32 read pairs in one contig batch");
     cudaStream_t st = c->stream;
-    uint32_t * d_pos; int32_t * d_dev; uint64_t * d_u64; uint32_t * d_tfirst, * d_rel, * d_lcount, * d_small, * d_pmax;
+    uint32_t * d_pos = nullptr; int32_t * d_dev = nullptr; uint64_t * d_u64 = nullptr; uint32_t * d_tfirst = nullptr, * d_rel = nullptr, * d_lcount = nullptr, * d_small = nullptr, * d_pmax = nullptr;
     if (grow_dev(c, 0, d_pos, total)) return c->status;
     if (grow_dev(c, 1, d_dev, total)) return c->status;
     // compact input: staging of the 16-bit remainders, 24-bit deviations and block tables

@@ -28,6 +28,28 @@ def segment_aligned_ranges(n_windows: int, window_buffer: int, world: int) -> Li
     return out
 
 
+BATCH_BLOCK = 600_000      # lcm(200 000-bp segments, 30-bp windows): a batch that starts here has the contig's grid and borders
+
+
+def contig_batches(length: int, batch_bp: int, window_buffer: int = 200_000, window: int = 30):
+    """Window-range batches of a contig that does not fit one scan (scripts/run_config.py): (start, end, first_window,
+    n_windows) per batch. A batch is scanned as its own contig anchored at `start`, a multiple of lcm(window_buffer, window), so
+    its segment borders anchor + k * window_buffer and its window grid anchor + 30 w are the whole contig's; it begins one
+    block (3 segments) before the windows it owns -- the halo the segment artefacts and the longest read pairs need -- and
+    owns windows [first_window, first_window + n_windows) of ITS grid. The owned windows of all batches partition the contig's."""
+    block = int(np.lcm(window_buffer, window))
+    per = max(1, int(batch_bp) // block)
+    n_blocks = (int(length) + block - 1) // block
+    out = []
+    for b0 in range(0, n_blocks, per):
+        b1 = min(b0 + per, n_blocks)
+        halo = block if b0 > 0 else 0
+        start, end = b0 * block - halo, min(b1 * block, int(length))
+        first = halo // window
+        out.append((start, end, first, (end - start + window - 1) // window - first))
+    return out
+
+
 def gather_calls(calls: np.ndarray, per_sample: np.ndarray, rank: int, world: int, dist=None):
     """Host-side merge of the per-rank call lists on rank 0, in genomic order (ranks hold ascending ranges)."""
     if world == 1 or dist is None:

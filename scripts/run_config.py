@@ -37,9 +37,9 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 threads = max(1, (os.cpu_count() or 8) // world)
 N, L, mixed = a.samples, a.length, not a.single_rg
-BLOCK = 600_000
+from popdel_b200 import sharding
+BLOCK = sharding.BATCH_BLOCK
 blocks_per_batch = max(1, int(a.batch_mbp * 1e6) // BLOCK)
-n_blocks = (L + BLOCK - 1) // BLOCK
 ds, dl, gt = bench.plant(1, N, L, 2.0)
 specs = bench.cohort_specs(1, N, mixed)
 R = len(specs)
@@ -59,15 +59,13 @@ params = api.CallParameters()
 rgs = api.read_groups_from_headers([[h for h, s in hdrs if s == smp] for smp in range(N)], params)
 sc = api.Scanner(params, rgs, N, device=local)
 sc.set_unify(float(np.mean([r.stddev for r in rgs])), 0.5, False)
-batches = [(b0, min(b0 + blocks_per_batch, n_blocks)) for b0 in range(0, n_blocks, blocks_per_batch)][a.first_batch:]
+batches = sharding.contig_batches(L, blocks_per_batch * BLOCK)[a.first_batch:]          # (start, end, first owned window, owned windows)
 if a.max_batches:
     batches = batches[:a.max_batches]
 gen_dev = None if a.host_gen else api.SynthDevice(local)
 mine = batches[rank::world]
 tot = dict(evals=0, windows=0, reads=0, ms_dev=0.0, s_wall=0.0, s_gen=0.0, calls=0, variants=0, flagged=0, screened=0)
-for (b0, b1) in mine:
-    halo = BLOCK if b0 > 0 else 0
-    start, end = b0 * BLOCK - halo, min(b1 * BLOCK, L)
+for (start, end, w0, n_own) in mine:
     t0 = time.time()
     if gen_dev is not None:                                 # device generator -> pd_contig_push_device: nothing crosses PCIe
         n_reads, dp, dd, rg_start = gen_dev.generate(1, specs, start, end, ds, dl, gt, N)
@@ -92,15 +90,14 @@ for (b0, b1) in mine:
         del data
     sc.upload()
     t_up = time.time() - t0
-    w0 = halo // 30                                         # 600 000 / 30: the halo's windows are not counted
-    nw = min(sc.window_count(), (end - start + 29) // 30)   # windows at or after `end` belong to the next batch
+    nw = min(sc.window_count(), w0 + n_own)                 # the halo's windows are not counted; windows at or after `end` belong to the next batch
     res = sc.scan(first_window=w0, n_windows=max(nw - w0, 0), copy=False)
     tot["s_wall"] += time.time() - t0
     tot["windows"] += int(res["n_windows"]); tot["evals"] += int(res["n_windows"]) * N; tot["reads"] += n_reads
     tot["ms_dev"] += float(res["ms_total"]); tot["calls"] += int(res["n_window_calls"]); tot["variants"] += len(res["calls"])
     tot["flagged"] += int(res["n_flagged_windows"]); tot["screened"] += int(res["n_screened_windows"])
     if rank == 0:
-        print(f"[run_config] batch {b0}-{b1}: {n_reads} read pairs, {res['n_windows']} windows, scan {float(res['ms_total']):.1f} ms on the device "
+        print(f"[run_config] batch {start}-{end}: {n_reads} read pairs, {res['n_windows']} windows, scan {float(res['ms_total']):.1f} ms on the device "
               f"(EM {float(res['ms_em']):.1f}), push + upload {t_up:.2f} s, generation {tot['s_gen']:.1f} s so far", file=sys.stderr, flush=True)
 if dist is not None:
     import torch

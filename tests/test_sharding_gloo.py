@@ -59,6 +59,20 @@ def _worker_samples(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def test_contig_batches_keep_the_grid_and_partition_the_windows():
+    """scripts/run_config.py: a contig too large for one scan is walked in batches that are scanned as contigs of their own."""
+    for length, batch in [(248_956_422, 6_000_000), (3_100_000_000, 3_000_000), (1_234_567, 600_000), (500_000, 6_000_000), (600_000, 600_000)]:
+        bs = sharding.contig_batches(length, batch)
+        owned = 0
+        for k, (start, end, first, n) in enumerate(bs):
+            assert start % 200_000 == 0 and start % 30 == 0             # same segment borders, same window grid
+            assert (first == 0) == (k == 0) and first * 30 == (600_000 if k else 0)
+            assert (start + 30 * first) == owned * 30                   # owned windows are contiguous on the contig's grid
+            assert n > 0 and end <= length and end - start <= batch + 600_000 + 600_000
+            owned += n
+        assert owned == (length + 29) // 30                             # ... and partition it
+
+
 def test_sample_blocks_and_tail_combination():
     assert sharding.sample_blocks(7, 2) == [(0, 4), (4, 3)] and sharding.sample_blocks(50000, 8)[7] == (43750, 6250)
     assert [n for _, n in sharding.sample_blocks(10, 4)] == api.split_samples(10, 4)
